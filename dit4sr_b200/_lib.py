@@ -1,0 +1,87 @@
+"""ctypes binding of libdit4sr_b200.so (include/dit4sr_b200.h). There is no fallback: if the library is missing or
+fails to load, using the ops raises."""
+import ctypes as C
+import os
+
+from .build import LIB_PATH
+
+c_i64, c_int, c_float, c_vp = C.c_int64, C.c_int, C.c_float, C.c_void_p
+
+
+class LnModulateParams(C.Structure):
+    _fields_ = [("x", c_vp), ("ldx", c_i64), ("x_batch_stride", c_i64),
+                ("shift", c_vp), ("scale", c_vp), ("shift2", c_vp), ("scale2", c_vp),
+                ("mod_batch_stride", c_i64), ("out", c_vp), ("out2", c_vp),
+                ("ldo", c_i64), ("o_batch_stride", c_i64),
+                ("batches", c_int), ("rows", c_int), ("dim", c_int), ("eps", c_float)]
+
+
+class DwconvParams(C.Structure):
+    _fields_ = [("u_hq", c_vp), ("u_lr", c_vp), ("ld", c_i64), ("hq_batch_stride", c_i64),
+                ("lr_batch_stride", c_i64), ("weight9", c_vp), ("bias", c_vp),
+                ("batches", c_int), ("grid", c_int), ("channels", c_int)]
+
+
+class GemmParams(C.Structure):
+    _fields_ = [("A", c_vp), ("lda", c_i64), ("a_batch_stride", c_i64),
+                ("W", c_vp), ("ldw", c_i64), ("bias", c_vp),
+                ("C", c_vp), ("ldc", c_i64), ("c_batch_stride", c_i64), ("c_dtype", c_int),
+                ("batches", c_int), ("rows", c_int), ("N", c_int), ("K", c_int), ("epilogue", c_int),
+                ("gate", c_vp), ("gate_batch_stride", c_i64),
+                ("resid", c_vp), ("ldr", c_i64), ("r_batch_stride", c_i64),
+                ("norm_w0", c_vp), ("norm_w1", c_vp), ("sec_cols", c_int), ("eps", c_float),
+                ("dbl_row_offset", c_i64)]
+
+
+class AttnParams(C.Structure):
+    _fields_ = [("q", c_vp), ("k", c_vp), ("v", c_vp), ("qkv_row_stride", c_i64), ("qkv_batch_stride", c_i64),
+                ("o", c_vp), ("o_row_stride", c_i64), ("o_batch_stride", c_i64),
+                ("lr_res", c_vp), ("lr_row_stride", c_i64), ("lr_batch_stride", c_i64),
+                ("lr_row_begin", c_int), ("lr_row_end", c_int),
+                ("batches", c_int), ("heads", c_int), ("seq_q", c_int), ("seq_kv", c_int), ("scale", c_float)]
+
+
+# every symbol include/dit4sr_b200.h declares: name -> (restype, argtypes)
+SYMBOLS = {
+    "dit4sr_abi_version": (c_int, []),
+    "dit4sr_last_error": (C.c_char_p, []),
+    "dit4sr_check_device": (c_int, []),
+    "dit4sr_ln_modulate": (c_int, [C.POINTER(LnModulateParams), c_vp]),
+    "dit4sr_dwconv3x3_add": (c_int, [C.POINTER(DwconvParams), c_vp]),
+    "dit4sr_gemm_bf16": (c_int, [C.POINTER(GemmParams), c_vp]),
+    "dit4sr_attn_fwd": (c_int, [C.POINTER(AttnParams), c_vp]),
+    "dit4sr_patchify": (c_int, [c_vp, c_int, c_vp, c_int, c_int, c_int, c_int, c_vp]),
+    "dit4sr_unpatchify": (c_int, [c_vp, c_vp, c_int, c_vp, c_float, c_int, c_int, c_int, c_int, c_vp]),
+    "dit4sr_timestep_features": (c_int, [c_vp, c_vp, c_int, c_vp]),
+    "dit4sr_silu_cast": (c_int, [c_vp, c_vp, c_i64, c_vp]),
+    "dit4sr_cast": (c_int, [c_vp, c_vp, c_i64, c_int, c_vp]),
+}
+
+_lib = None
+
+
+def load():
+    """Load the library (once). Raises RuntimeError with the build hint if it is absent."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise RuntimeError(f"{LIB_PATH} not built: run `python -m dit4sr_b200.build` (or __graft_entry__.build()); "
+                           "the dit4sr_b200 ops have no fallback path")
+    lib = C.CDLL(LIB_PATH)
+    for name, (res, args) in SYMBOLS.items():
+        fn = getattr(lib, name)  # AttributeError if the symbol is missing
+        fn.restype = res
+        fn.argtypes = args
+    _lib = lib
+    return lib
+
+
+class Dit4srError(RuntimeError):
+    pass
+
+
+def check(rc, what):
+    if rc != 0:
+        msg = load().dit4sr_last_error().decode("utf-8", "replace")
+        raise Dit4srError(f"{what} failed (rc={rc}): {msg}")

@@ -1,0 +1,328 @@
+// Joint attention forward (non-causal, head_dim 64) on sm_100a tensor cores, flash style.
+//
+// One CTA = one 128-row query tile of one (batch, head); two CTAs are co-resident per SM so that one CTA's softmax
+// overlaps the other's MMAs.  Warp roles (192 threads): warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer,
+// warps 2..5 = softmax / correction / epilogue (thread = one query row = one TMEM lane; no cross-thread reductions).
+//
+// TMEM (256 columns): S = Q K^T fp32 [0,128) | O accumulator fp32 [128,192) | P = softmax numerators bf16 [192,256).
+// Per KV tile j:  MMA: S = Q K_j^T  ->  softmax: m,l update, P_j -> TMEM, lazily rescale O  ->  MMA: O += P_j V_j
+// (A operand from TMEM, V consumed MN-major straight from the TMA tile), with S_{j+1} issued before PV_j.
+#include "host_util.h"
+#include "ptx.cuh"
+
+namespace attn {
+
+constexpr int BQ = 128;    // query rows per CTA
+constexpr int BKV = 128;   // kv rows per tile
+constexpr int DH = 64;
+constexpr int KV_STAGES = 2;
+constexpr int TILE_BYTES = 128 * DH * 2;  // 16 KB
+constexpr int NUM_THREADS = 192;
+constexpr int TMEM_COLS = 256;
+constexpr int COL_S = 0, COL_O = 128, COL_P = 192;
+constexpr int SMEM_BYTES = (1 + 2 * KV_STAGES) * TILE_BYTES + 1024 + 256;
+
+struct Args {
+  __nv_bfloat16* o;
+  int64_t o_row_stride, o_batch_stride;
+  const __nv_bfloat16* lr_res;
+  int64_t lr_row_stride, lr_batch_stride;
+  int lr_row_begin, lr_row_end;
+  int seq_q, seq_kv, n_kv_tiles;
+  float scale_log2;  // scale * log2(e)
+};
+
+__global__ void __launch_bounds__(NUM_THREADS, 2)
+attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
+                const __grid_constant__ CUtensorMap tmV, const Args args) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sQ = smem;
+  uint8_t* sK = smem + TILE_BYTES;
+  uint8_t* sV = smem + (1 + KV_STAGES) * TILE_BYTES;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (1 + 2 * KV_STAGES) * TILE_BYTES);
+  uint64_t* q_full = bars;
+  uint64_t* k_full = bars + 1;
+  uint64_t* k_empty = k_full + KV_STAGES;
+  uint64_t* v_full = k_empty + KV_STAGES;
+  uint64_t* v_empty = v_full + KV_STAGES;
+  uint64_t* s_full = v_empty + KV_STAGES;
+  uint64_t* p_full = s_full + 1;
+  uint64_t* o_done = p_full + 1;
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(o_done + 1);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int q_tile = blockIdx.x;
+  const int head = blockIdx.y;
+  const int b = blockIdx.z;
+  const int n_tiles = args.n_kv_tiles;
+
+  if (warp == 0 && lane == 0) {
+    ptx::prefetch_tmap(&tmQ);
+    ptx::prefetch_tmap(&tmK);
+    ptx::prefetch_tmap(&tmV);
+    ptx::mbar_init(q_full, 1);
+    for (int i = 0; i < KV_STAGES; ++i) {
+      ptx::mbar_init(&k_full[i], 1);
+      ptx::mbar_init(&k_empty[i], 1);
+      ptx::mbar_init(&v_full[i], 1);
+      ptx::mbar_init(&v_empty[i], 1);
+    }
+    ptx::mbar_init(s_full, 1);
+    ptx::mbar_init(p_full, 4);
+    ptx::mbar_init(o_done, 1);
+    ptx::fence_barrier_init();
+  }
+  if (warp == 1) {
+    ptx::tmem_alloc(tmem_ptr, TMEM_COLS);
+    ptx::tmem_relinquish();
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      // ===================== TMA producer =====================
+      ptx::mbar_expect_tx(q_full, TILE_BYTES);
+      ptx::tma_load_3d(sQ, &tmQ, q_full, head * DH, q_tile * BQ, b);
+      for (int j = 0; j < n_tiles; ++j) {
+        const int st = j % KV_STAGES;
+        const uint32_t ph = (j / KV_STAGES) & 1;
+        ptx::mbar_wait(&k_empty[st], ph ^ 1);
+        ptx::mbar_expect_tx(&k_full[st], TILE_BYTES);
+        ptx::tma_load_3d(sK + st * TILE_BYTES, &tmK, &k_full[st], head * DH, j * BKV, b);
+        ptx::mbar_wait(&v_empty[st], ph ^ 1);
+        ptx::mbar_expect_tx(&v_full[st], TILE_BYTES);
+        ptx::tma_load_3d(sV + st * TILE_BYTES, &tmV, &v_full[st], head * DH, j * BKV, b);
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      // ===================== MMA issuer =====================
+      constexpr uint32_t idesc_qk = ptx::make_idesc_bf16(BQ, BKV, 0, 0);  // A = Q (K-major), B = K tile (K-major)
+      constexpr uint32_t idesc_pv = ptx::make_idesc_bf16(BQ, DH, 0, 1);   // A = P (TMEM), B = V tile (MN-major)
+      const uint64_t qdesc = ptx::make_sdesc_sw128(ptx::smem_u32(sQ));
+      const uint32_t tS = tmem_base + COL_S, tO = tmem_base + COL_O, tP = tmem_base + COL_P;
+
+      auto issue_qk = [&](int j) {
+        const int st = j % KV_STAGES;
+        ptx::mbar_wait(&k_full[st], (j / KV_STAGES) & 1);
+        ptx::tc_fence_after();
+        const uint64_t kdesc = ptx::make_sdesc_sw128(ptx::smem_u32(sK + st * TILE_BYTES));
+#pragma unroll
+        for (int k = 0; k < DH / 16; ++k) ptx::mma_ss(tS, qdesc + 2 * k, kdesc + 2 * k, idesc_qk, k != 0);
+        ptx::tc_commit(&k_empty[st]);
+        ptx::tc_commit(s_full);
+      };
+
+      ptx::mbar_wait(q_full, 0);
+      issue_qk(0);
+      for (int j = 0; j < n_tiles; ++j) {
+        const int st = j % KV_STAGES;
+        ptx::mbar_wait(p_full, j & 1);  // P_j written, S consumed, O rescaled
+        ptx::tc_fence_after();
+        if (j + 1 < n_tiles) issue_qk(j + 1);
+        ptx::mbar_wait(&v_full[st], (j / KV_STAGES) & 1);
+        ptx::tc_fence_after();
+        const uint64_t vdesc = ptx::make_sdesc_sw128(ptx::smem_u32(sV + st * TILE_BYTES));
+#pragma unroll
+        for (int k = 0; k < BKV / 16; ++k) {
+          // A: 16 bf16 of K per step = 8 TMEM columns; B: 16 kv rows = 2048 bytes further down the V tile
+          ptx::mma_ts(tO, tP + 8 * k, vdesc + (uint64_t)(128 * k), idesc_pv, (j | k) != 0);
+        }
+        ptx::tc_commit(&v_empty[st]);
+        ptx::tc_commit(o_done);
+      }
+    }
+  } else {
+    // ===================== softmax / correction / epilogue =====================
+    const int q = warp & 3;
+    const uint32_t lane_off = (uint32_t)(q * 32) << 16;
+    const uint32_t tS = tmem_base + COL_S + lane_off, tO = tmem_base + COL_O + lane_off,
+                   tP = tmem_base + COL_P + lane_off;
+    const float sl2 = args.scale_log2;
+    float m_run = -INFINITY;  // running max of the raw scores
+    float l_run = 0.f;
+    for (int j = 0; j < n_tiles; ++j) {
+      ptx::mbar_wait(s_full, j & 1);
+      ptx::tc_fence_after();
+      const int kv_left = args.seq_kv - j * BKV;  // valid columns in this tile (>=1)
+      // pass 1: row max
+      float mx = m_run;
+#pragma unroll 1
+      for (int c = 0; c < BKV / 32; ++c) {
+        uint32_t v[32];
+        ptx::tmem_ld32(tS + c * 32, v);
+        ptx::tmem_wait_ld();
+        if (kv_left >= (c + 1) * 32) {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) mx = fmaxf(mx, __uint_as_float(v[i]));
+        } else {
+#pragma unroll
+          for (int i = 0; i < 32; ++i)
+            if (c * 32 + i < kv_left) mx = fmaxf(mx, __uint_as_float(v[i]));
+        }
+      }
+      const float m_new = mx;
+      const float alpha = ptx::ex2((m_run - m_new) * sl2);  // 0 on the first tile (m_run = -inf)
+      const float neg_m = -m_new * sl2;
+      // P region and O are read by PV_{j-1}: wait for it before overwriting them
+      if (j > 0) {
+        ptx::mbar_wait(o_done, (j - 1) & 1);
+        ptx::tc_fence_after();
+      }
+      // pass 2: p = 2^(s*sl2 - m*sl2), row sum, bf16 pack -> TMEM
+      float rsum = 0.f;
+#pragma unroll 1
+      for (int c = 0; c < BKV / 32; ++c) {
+        uint32_t v[32];
+        ptx::tmem_ld32(tS + c * 32, v);
+        ptx::tmem_wait_ld();
+        float pv[32];
+        if (kv_left >= (c + 1) * 32) {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) pv[i] = ptx::ex2(fmaf(__uint_as_float(v[i]), sl2, neg_m));
+        } else {
+#pragma unroll
+          for (int i = 0; i < 32; ++i)
+            pv[i] = (c * 32 + i < kv_left) ? ptx::ex2(fmaf(__uint_as_float(v[i]), sl2, neg_m)) : 0.f;
+        }
+        uint32_t pk[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          rsum += pv[2 * i] + pv[2 * i + 1];
+          pk[i] = ptx::pack_bf16(pv[2 * i], pv[2 * i + 1]);
+        }
+        ptx::tmem_st16(tP + c * 16, pk);
+      }
+      // correction: O *= alpha (skipped warp-uniformly when no row's max moved)
+      if (j > 0 && __any_sync(0xffffffffu, alpha != 1.0f)) {
+#pragma unroll 1
+        for (int c = 0; c < DH / 32; ++c) {
+          uint32_t v[32];
+          ptx::tmem_ld32(tO + c * 32, v);
+          ptx::tmem_wait_ld();
+#pragma unroll
+          for (int i = 0; i < 32; ++i) v[i] = __float_as_uint(__uint_as_float(v[i]) * alpha);
+          ptx::tmem_st32(tO + c * 32, v);
+        }
+      }
+      l_run = l_run * alpha + rsum;
+      m_run = m_new;
+      ptx::tmem_wait_st();
+      ptx::tc_fence_before();
+      __syncwarp();
+      if (lane == 0) ptx::mbar_arrive(p_full);
+    }
+    // epilogue: O / l (+ LR residual) -> bf16 global
+    ptx::mbar_wait(o_done, (n_tiles - 1) & 1);
+    ptx::tc_fence_after();
+    const int row = q_tile * BQ + q * 32 + lane;
+    const float inv_l = 1.0f / l_run;
+    const bool row_ok = row < args.seq_q;
+    const bool add_lr = args.lr_res != nullptr && row >= args.lr_row_begin && row < args.lr_row_end;
+#pragma unroll 1
+    for (int c = 0; c < DH / 32; ++c) {
+      uint32_t v[32];
+      ptx::tmem_ld32(tO + c * 32, v);
+      ptx::tmem_wait_ld();
+      if (row_ok) {
+        float f[32];
+#pragma unroll
+        for (int i = 0; i < 32; ++i) f[i] = __uint_as_float(v[i]) * inv_l;
+        if (add_lr) {
+          const uint4* lr = reinterpret_cast<const uint4*>(args.lr_res + (int64_t)b * args.lr_batch_stride +
+                                                           (int64_t)row * args.lr_row_stride + head * DH + c * 32);
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const uint4 u = __ldg(lr + i);
+            const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&u);
+#pragma unroll
+            for (int t = 0; t < 4; ++t) {
+              const float2 ff = __bfloat1622float2(h2[t]);
+              f[8 * i + 2 * t] += ff.x;
+              f[8 * i + 2 * t + 1] += ff.y;
+            }
+          }
+        }
+        uint4* dst = reinterpret_cast<uint4*>(args.o + (int64_t)b * args.o_batch_stride +
+                                              (int64_t)row * args.o_row_stride + head * DH + c * 32);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          uint4 u;
+          u.x = ptx::pack_bf16(f[8 * i + 0], f[8 * i + 1]);
+          u.y = ptx::pack_bf16(f[8 * i + 2], f[8 * i + 3]);
+          u.z = ptx::pack_bf16(f[8 * i + 4], f[8 * i + 5]);
+          u.w = ptx::pack_bf16(f[8 * i + 6], f[8 * i + 7]);
+          dst[i] = u;
+        }
+      }
+    }
+  }
+
+  __syncwarp();
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    ptx::tc_fence_after();
+    ptx::tmem_dealloc(tmem_base, TMEM_COLS);
+  }
+}
+
+}  // namespace attn
+
+extern "C" int dit4sr_attn_fwd(const dit4sr_attn_params* p, void* stream_) {
+  using namespace attn;
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  DIT4SR_REQUIRE(p && p->q && p->k && p->v && p->o, DIT4SR_E_BADARG, "attn: null pointer argument");
+  DIT4SR_REQUIRE(p->batches > 0 && p->heads > 0 && p->seq_q > 0 && p->seq_kv > 0 && p->seq_q <= p->seq_kv,
+                 DIT4SR_E_BADARG, "attn: bad sizes (batches %d heads %d seq_q %d seq_kv %d)", p->batches, p->heads,
+                 p->seq_q, p->seq_kv);
+  DIT4SR_REQUIRE(p->batches <= 65535 && p->heads <= 65535, DIT4SR_E_SHAPE, "attn: batches/heads > 65535");
+  DIT4SR_REQUIRE(p->qkv_row_stride % 8 == 0 && p->qkv_batch_stride % 8 == 0 && p->o_row_stride % 8 == 0 &&
+                     p->o_batch_stride % 8 == 0 && host::aligned16(p->o),
+                 DIT4SR_E_ALIGN, "attn: strides must be multiples of 8 elements, pointers 16-byte aligned");
+  if (p->lr_res != nullptr) {
+    DIT4SR_REQUIRE(p->lr_row_stride % 8 == 0 && p->lr_batch_stride % 8 == 0 && host::aligned16(p->lr_res) &&
+                       p->lr_row_begin >= 0 && p->lr_row_end >= p->lr_row_begin,
+                   DIT4SR_E_ALIGN, "attn: bad lr_res arguments");
+  }
+  int rc = dit4sr_check_device();
+  if (rc != 0) return rc;
+
+  CUtensorMap tmQ, tmK, tmV;
+  const uint64_t dims[3] = {(uint64_t)p->heads * DH, (uint64_t)p->seq_kv, (uint64_t)p->batches};
+  const uint64_t strides[2] = {(uint64_t)p->qkv_row_stride * 2,
+                               (uint64_t)(p->batches > 1 ? p->qkv_batch_stride : p->qkv_row_stride * p->seq_kv) * 2};
+  const uint32_t box[3] = {DH, 128, 1};
+  if ((rc = host::make_tmap_bf16(&tmQ, p->q, 3, dims, strides, box)) != 0) return rc;
+  if ((rc = host::make_tmap_bf16(&tmK, p->k, 3, dims, strides, box)) != 0) return rc;
+  if ((rc = host::make_tmap_bf16(&tmV, p->v, 3, dims, strides, box)) != 0) return rc;
+
+  Args a;
+  a.o = reinterpret_cast<__nv_bfloat16*>(p->o);
+  a.o_row_stride = p->o_row_stride;
+  a.o_batch_stride = p->o_batch_stride;
+  a.lr_res = reinterpret_cast<const __nv_bfloat16*>(p->lr_res);
+  a.lr_row_stride = p->lr_row_stride;
+  a.lr_batch_stride = p->lr_batch_stride;
+  a.lr_row_begin = p->lr_row_begin;
+  a.lr_row_end = p->lr_row_end;
+  a.seq_q = p->seq_q;
+  a.seq_kv = p->seq_kv;
+  a.n_kv_tiles = (p->seq_kv + BKV - 1) / BKV;
+  a.scale_log2 = p->scale * 1.4426950408889634f;
+
+  static bool configured = false;
+  if (!configured) {
+    DIT4SR_CUDA(cudaFuncSetAttribute(attn_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+    configured = true;
+  }
+  dim3 grid((p->seq_q + BQ - 1) / BQ, p->heads, p->batches);
+  attn_fwd_kernel<<<grid, NUM_THREADS, SMEM_BYTES, stream>>>(tmQ, tmK, tmV, a);
+  DIT4SR_CUDA(cudaGetLastError());
+  return 0;
+}

@@ -1,0 +1,41 @@
+// Host-side helpers shared by the C-ABI entry points: error reporting and TMA tensor-map construction.
+#pragma once
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <stdarg.h>
+
+#include "../../include/dit4sr_b200.h"
+
+namespace host {
+
+void set_error(const char* fmt, ...);
+
+#define DIT4SR_REQUIRE(cond, code, ...)      \
+  do {                                       \
+    if (!(cond)) {                           \
+      host::set_error(__VA_ARGS__);          \
+      return (code);                         \
+    }                                        \
+  } while (0)
+
+#define DIT4SR_CUDA(expr)                                                              \
+  do {                                                                                 \
+    cudaError_t _e = (expr);                                                           \
+    if (_e != cudaSuccess) {                                                           \
+      host::set_error("%s failed: %s", #expr, cudaGetErrorString(_e));                 \
+      return (int)_e;                                                                  \
+    }                                                                                  \
+  } while (0)
+
+inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+
+// Encode a bf16 tensor map with 128-byte swizzle. dims/strides innermost first; strides in BYTES for dims 1..rank-1.
+// Out-of-bounds box elements read as zero. Returns 0 or a DIT4SR_E_* code.
+int make_tmap_bf16(CUtensorMap* out, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
+                   const uint32_t* box);
+
+int sm_count();
+
+}  // namespace host

@@ -1,0 +1,142 @@
+// Small data-movement kernels of the model head and tail (transformer_sd3.py:326-332,379-391): patchify (im2col for the
+// k=2,s=2 PatchEmbed conv), unpatchify (+ optional fused flow-match Euler update), timestep features, casts.
+#include "host_util.h"
+#include "ptx.cuh"
+
+namespace misc {
+
+template <typename T> __device__ __forceinline__ float to_f(T v);
+template <> __device__ __forceinline__ float to_f<float>(float v) { return v; }
+template <> __device__ __forceinline__ float to_f<__nv_bfloat16>(__nv_bfloat16 v) { return __bfloat162float(v); }
+
+// one thread per (b, token, c): writes 4 contiguous bf16 (ph, pw)
+template <typename T>
+__global__ void patchify_kernel(const T* __restrict__ x, __nv_bfloat16* __restrict__ out, int B, int C, int H, int W) {
+  const int Hp = H / 2, Wp = W / 2;
+  const int64_t total = (int64_t)B * Hp * Wp * C;
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const int c = (int)(i % C);
+  const int64_t tok = i / C;
+  const int wp = (int)(tok % Wp);
+  const int hp = (int)((tok / Wp) % Hp);
+  const int b = (int)(tok / ((int64_t)Wp * Hp));
+  const T* src = x + (((int64_t)b * C + c) * H + 2 * hp) * W + 2 * wp;
+  uint2 o;
+  o.x = ptx::pack_bf16(to_f<T>(src[0]), to_f<T>(src[1]));
+  o.y = ptx::pack_bf16(to_f<T>(src[W]), to_f<T>(src[W + 1]));
+  *reinterpret_cast<uint2*>(out + tok * (C * 4) + c * 4) = o;
+}
+
+// one thread per output element (b, d, y, x); tok layout [B, Hp*Wp, (pH pW d)]
+template <typename TO>
+__global__ void unpatchify_kernel(const float* __restrict__ tok, TO* __restrict__ out, const TO* __restrict__ latents,
+                                  float dsigma, int B, int C, int H, int W) {
+  const int64_t total = (int64_t)B * C * H * W;
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const int x = (int)(i % W);
+  const int y = (int)((i / W) % H);
+  const int d = (int)((i / ((int64_t)W * H)) % C);
+  const int b = (int)(i / ((int64_t)W * H * C));
+  const int Wp = W / 2;
+  const int64_t t = ((int64_t)b * (H / 2) + y / 2) * Wp + x / 2;
+  float v = tok[t * (4 * C) + ((y & 1) * 2 + (x & 1)) * C + d];
+  if (latents != nullptr) v = to_f<TO>(latents[i]) + dsigma * v;
+  if constexpr (sizeof(TO) == 2) out[i] = __float2bfloat16_rn(v);
+  else out[i] = v;
+}
+
+__global__ void timestep_features_kernel(const float* __restrict__ t, __nv_bfloat16* __restrict__ out, int B) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= B * 128) return;
+  const int b = i / 128, k = i % 128;
+  // freq = exp(-ln(10000) * k / 128), fp32 as in diffusers get_timestep_embedding
+  const float freq = expf(-9.210340371976184f * (float)k / 128.0f);
+  const float a = t[b] * freq;
+  out[b * 256 + k] = __float2bfloat16_rn(cosf(a));        // flip_sin_to_cos: [cos | sin]
+  out[b * 256 + 128 + k] = __float2bfloat16_rn(sinf(a));
+}
+
+__global__ void silu_cast_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ y, int64_t n) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float v = x[i];
+  y[i] = __float2bfloat16_rn(v / (1.0f + expf(-v)));
+}
+__global__ void cast_f2b_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ y, int64_t n) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) y[i] = __float2bfloat16_rn(x[i]);
+}
+__global__ void cast_b2f_kernel(const __nv_bfloat16* __restrict__ x, float* __restrict__ y, int64_t n) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) y[i] = __bfloat162float(x[i]);
+}
+
+static inline unsigned blocks(int64_t n, int t) { return (unsigned)((n + t - 1) / t); }
+
+}  // namespace misc
+
+extern "C" {
+
+int dit4sr_patchify(const void* x, int x_dtype, void* patches, int batches, int channels, int height, int width,
+                    void* stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  DIT4SR_REQUIRE(x && patches && batches > 0 && channels > 0, DIT4SR_E_BADARG, "patchify: bad argument");
+  DIT4SR_REQUIRE(height % 2 == 0 && width % 2 == 0 && height > 0 && width > 0, DIT4SR_E_SHAPE,
+                 "patchify: height/width must be even");
+  DIT4SR_REQUIRE((reinterpret_cast<uintptr_t>(patches) & 7) == 0, DIT4SR_E_ALIGN, "patchify: output not 8-byte aligned");
+  const int64_t total = (int64_t)batches * (height / 2) * (width / 2) * channels;
+  if (x_dtype == DIT4SR_DT_F32)
+    misc::patchify_kernel<float><<<misc::blocks(total, 256), 256, 0, stream>>>(
+        (const float*)x, (__nv_bfloat16*)patches, batches, channels, height, width);
+  else
+    misc::patchify_kernel<__nv_bfloat16><<<misc::blocks(total, 256), 256, 0, stream>>>(
+        (const __nv_bfloat16*)x, (__nv_bfloat16*)patches, batches, channels, height, width);
+  DIT4SR_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int dit4sr_unpatchify(const float* tok, void* out, int out_dtype, const void* latents, float dsigma, int batches,
+                      int channels, int height, int width, void* stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  DIT4SR_REQUIRE(tok && out && batches > 0 && channels > 0, DIT4SR_E_BADARG, "unpatchify: bad argument");
+  DIT4SR_REQUIRE(height % 2 == 0 && width % 2 == 0 && height > 0 && width > 0, DIT4SR_E_SHAPE,
+                 "unpatchify: height/width must be even");
+  const int64_t total = (int64_t)batches * channels * height * width;
+  if (out_dtype == DIT4SR_DT_F32)
+    misc::unpatchify_kernel<float><<<misc::blocks(total, 256), 256, 0, stream>>>(
+        tok, (float*)out, (const float*)latents, dsigma, batches, channels, height, width);
+  else
+    misc::unpatchify_kernel<__nv_bfloat16><<<misc::blocks(total, 256), 256, 0, stream>>>(
+        tok, (__nv_bfloat16*)out, (const __nv_bfloat16*)latents, dsigma, batches, channels, height, width);
+  DIT4SR_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int dit4sr_timestep_features(const float* timesteps, void* out_bf16, int batches, void* stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  DIT4SR_REQUIRE(timesteps && out_bf16 && batches > 0, DIT4SR_E_BADARG, "timestep_features: bad argument");
+  misc::timestep_features_kernel<<<misc::blocks((int64_t)batches * 128, 128), 128, 0, stream>>>(
+      timesteps, (__nv_bfloat16*)out_bf16, batches);
+  DIT4SR_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int dit4sr_silu_cast(const float* x, void* y_bf16, int64_t n, void* stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  DIT4SR_REQUIRE(x && y_bf16 && n > 0, DIT4SR_E_BADARG, "silu_cast: bad argument");
+  misc::silu_cast_kernel<<<misc::blocks(n, 256), 256, 0, stream>>>(x, (__nv_bfloat16*)y_bf16, n);
+  DIT4SR_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int dit4sr_cast(const void* x, void* y, int64_t n, int dir, void* stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  DIT4SR_REQUIRE(x && y && n > 0, DIT4SR_E_BADARG, "cast: bad argument");
+  if (dir == 0) misc::cast_f2b_kernel<<<misc::blocks(n, 256), 256, 0, stream>>>((const float*)x, (__nv_bfloat16*)y, n);
+  else misc::cast_b2f_kernel<<<misc::blocks(n, 256), 256, 0, stream>>>((const __nv_bfloat16*)x, (float*)y, n);
+  DIT4SR_CUDA(cudaGetLastError());
+  return 0;
+}
+}

@@ -1,0 +1,205 @@
+"""Tensor-level wrappers over the C-ABI (include/dit4sr_b200.h): they only translate torch tensors into device
+pointers / strides and launch on torch's current CUDA stream.  No math happens in Python and there is no fallback."""
+import ctypes as C
+
+import torch
+
+from . import _lib
+from ._lib import AttnParams, DwconvParams, GemmParams, LnModulateParams, check
+
+EPI_BIAS, EPI_BIAS_GELU, EPI_BIAS_SILU, EPI_QKV_NORM, EPI_GATE_RESID = 0, 1, 2, 3, 4
+DT_BF16, DT_F32 = 0, 1
+
+_launches = 0  # number of kernel launches issued through this module (bench.py reports it as gpu_launches)
+
+
+def launch_count():
+    return _launches
+
+
+def _count(n=1):
+    global _launches
+    _launches += n
+
+
+def _stream():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _ptr(t):
+    return None if t is None else C.c_void_p(t.data_ptr())
+
+
+def _req(t, dtype, name):
+    if not t.is_cuda:
+        raise _lib.Dit4srError(f"{name}: expected a CUDA tensor (dit4sr_b200 has no CPU path)")
+    if t.dtype != dtype:
+        raise _lib.Dit4srError(f"{name}: expected dtype {dtype}, got {t.dtype}")
+    if t.stride(-1) != 1:
+        raise _lib.Dit4srError(f"{name}: innermost dimension must be contiguous")
+
+
+def _as3(t):
+    """View [M, K] as [1, M, K]; keep [B, R, K]."""
+    return t.unsqueeze(0) if t.dim() == 2 else t
+
+
+def ln_modulate(x, shift, scale, out, shift2=None, scale2=None, out2=None, eps=1e-6):
+    """out = LN(x) * (1 + scale[b]) + shift[b]  (and optionally out2 with shift2/scale2). x fp32 [B,R,D]; out bf16."""
+    x = _as3(x)
+    out = _as3(out)
+    _req(x, torch.float32, "x")
+    _req(out, torch.bfloat16, "out")
+    for n, t in (("shift", shift), ("scale", scale)):
+        _req(t, torch.float32, n)
+    B, R, D = x.shape
+    p = LnModulateParams()
+    p.x, p.ldx, p.x_batch_stride = _ptr(x), x.stride(1), x.stride(0)
+    p.shift, p.scale = _ptr(shift), _ptr(scale)
+    p.mod_batch_stride = shift.stride(0) if shift.dim() == 2 else 0
+    if scale.dim() == 2 and scale.stride(0) != p.mod_batch_stride:
+        raise _lib.Dit4srError("ln_modulate: shift and scale must share the batch stride")
+    p.out, p.ldo, p.o_batch_stride = _ptr(out), out.stride(1), out.stride(0)
+    if out2 is not None:
+        out2 = _as3(out2)
+        _req(out2, torch.bfloat16, "out2")
+        if out2.stride() != out.stride():
+            raise _lib.Dit4srError("ln_modulate: out and out2 must share strides")
+        p.out2, p.shift2, p.scale2 = _ptr(out2), _ptr(shift2), _ptr(scale2)
+    p.batches, p.rows, p.dim, p.eps = B, R, D, eps
+    check(_lib.load().dit4sr_ln_modulate(C.byref(p), _stream()), "dit4sr_ln_modulate")
+    _count()
+
+
+def dwconv3x3_add(u_hq, u_lr, weight9, bias, grid):
+    """u_hq[b, y*grid+x, c] += bias[c] + dwconv3x3(u_lr)[...]; u_* bf16 [B, grid*grid, C] views of the MLP hidden state."""
+    _req(u_hq, torch.bfloat16, "u_hq")
+    _req(u_lr, torch.bfloat16, "u_lr")
+    _req(weight9, torch.float32, "weight9")
+    _req(bias, torch.float32, "bias")
+    B, N, Cc = u_hq.shape
+    if N != grid * grid or u_lr.shape != u_hq.shape or u_hq.stride(1) != u_lr.stride(1):
+        raise _lib.Dit4srError("dwconv3x3_add: shape mismatch (token grid must be square, attention.py:169-172)")
+    p = DwconvParams()
+    p.u_hq, p.u_lr, p.ld = _ptr(u_hq), _ptr(u_lr), u_hq.stride(1)
+    p.hq_batch_stride, p.lr_batch_stride = u_hq.stride(0), u_lr.stride(0)
+    p.weight9, p.bias = _ptr(weight9), _ptr(bias)
+    p.batches, p.grid, p.channels = B, grid, Cc
+    check(_lib.load().dit4sr_dwconv3x3_add(C.byref(p), _stream()), "dit4sr_dwconv3x3_add")
+    _count()
+
+
+def gemm(A, W, bias, out, epilogue=EPI_BIAS, gate=None, resid=None, norm_w0=None, norm_w1=None, sec_cols=0,
+         eps=1e-6, dbl_row_offset=0):
+    """out[b, r, :] = epilogue(A[b, r, :] @ W.T).  A bf16 [B,R,K] or [M,K]; W bf16 [N,K]; out bf16/fp32 same rows."""
+    A = _as3(A)
+    out = _as3(out)
+    _req(A, torch.bfloat16, "A")
+    _req(W, torch.bfloat16, "W")
+    if out.dtype not in (torch.bfloat16, torch.float32):
+        raise _lib.Dit4srError("gemm: out must be bf16 or fp32")
+    _req(out, out.dtype, "out")
+    B, R, K = A.shape
+    N = W.shape[0]
+    if W.shape[1] != K or out.shape[0] != B or out.shape[1] != R or out.shape[2] != N:
+        raise _lib.Dit4srError(f"gemm: shape mismatch A{tuple(A.shape)} W{tuple(W.shape)} out{tuple(out.shape)}")
+    p = GemmParams()
+    p.A, p.lda, p.a_batch_stride = _ptr(A), A.stride(1), A.stride(0)
+    p.W, p.ldw = _ptr(W), W.stride(0)
+    if bias is not None:
+        _req(bias, torch.float32, "bias")
+    p.bias = _ptr(bias)
+    p.C, p.ldc, p.c_batch_stride = _ptr(out), out.stride(1), out.stride(0)
+    p.c_dtype = DT_F32 if out.dtype == torch.float32 else DT_BF16
+    p.batches, p.rows, p.N, p.K, p.epilogue = B, R, N, K, epilogue
+    if epilogue == EPI_GATE_RESID:
+        resid = out if resid is None else _as3(resid)
+        _req(resid, torch.float32, "resid")
+        p.resid, p.ldr = _ptr(resid), resid.stride(1)
+        p.r_batch_stride = resid.stride(0) if resid.shape[0] == B else 0
+        if gate is not None:
+            _req(gate, torch.float32, "gate")
+            p.gate = _ptr(gate)
+            p.gate_batch_stride = gate.stride(0) if gate.dim() == 2 else 0
+    if epilogue == EPI_QKV_NORM:
+        for n, t in (("norm_w0", norm_w0), ("norm_w1", norm_w1)):
+            if t is not None:
+                _req(t, torch.float32, n)
+        p.norm_w0, p.norm_w1 = _ptr(norm_w0), _ptr(norm_w1)
+        p.sec_cols, p.dbl_row_offset = sec_cols or N, dbl_row_offset
+    p.eps = eps
+    check(_lib.load().dit4sr_gemm_bf16(C.byref(p), _stream()), "dit4sr_gemm_bf16")
+    _count()
+
+
+def attention(q, k, v, o, heads, seq_q=None, scale=None, lr_res=None, lr_rows=(0, 0)):
+    """o = softmax(q k^T * scale) v over [B, S, heads*64] bf16 views (row stride may be 3*heads*64 for a fused buffer).
+
+    Only the first seq_q query rows are produced. lr_res (bf16 [B, >=lr_rows[1], heads*64]) is added to rows lr_rows."""
+    for n, t in (("q", q), ("k", k), ("v", v), ("o", o)):
+        _req(t, torch.bfloat16, n)
+    B, S, D = k.shape
+    if D != heads * 64:
+        raise _lib.Dit4srError("attention: head_dim must be 64")
+    if not (q.stride() == k.stride() == v.stride()):
+        raise _lib.Dit4srError("attention: q/k/v must share strides")
+    seq_q = q.shape[1] if seq_q is None else seq_q
+    p = AttnParams()
+    p.q, p.k, p.v = _ptr(q), _ptr(k), _ptr(v)
+    p.qkv_row_stride, p.qkv_batch_stride = k.stride(1), k.stride(0)
+    p.o, p.o_row_stride, p.o_batch_stride = _ptr(o), o.stride(1), o.stride(0)
+    if lr_res is not None:
+        _req(lr_res, torch.bfloat16, "lr_res")
+        p.lr_res, p.lr_row_stride, p.lr_batch_stride = _ptr(lr_res), lr_res.stride(1), lr_res.stride(0)
+        p.lr_row_begin, p.lr_row_end = lr_rows
+    p.batches, p.heads, p.seq_q, p.seq_kv = B, heads, seq_q, S
+    p.scale = (1.0 / 8.0) if scale is None else scale
+    check(_lib.load().dit4sr_attn_fwd(C.byref(p), _stream()), "dit4sr_attn_fwd")
+    _count()
+
+
+def patchify(x, out):
+    """x [B,C,H,W] fp32/bf16 -> out bf16 [B, (H/2)(W/2), 4C] (im2col of PatchEmbed's k=2,s=2 conv)."""
+    if not x.is_contiguous() or not out.is_contiguous():
+        raise _lib.Dit4srError("patchify: tensors must be contiguous")
+    _req(out, torch.bfloat16, "out")
+    B, Cc, H, W = x.shape
+    dt = DT_F32 if x.dtype == torch.float32 else DT_BF16
+    check(_lib.load().dit4sr_patchify(_ptr(x), dt, _ptr(out), B, Cc, H, W, _stream()), "dit4sr_patchify")
+    _count()
+
+
+def unpatchify(tok, out, latents=None, dsigma=0.0):
+    """tok fp32 [B, (H/2)(W/2), 4C] -> out [B,C,H,W]; with latents: out = latents + dsigma * velocity (Euler step)."""
+    _req(tok, torch.float32, "tok")
+    if not tok.is_contiguous() or not out.is_contiguous():
+        raise _lib.Dit4srError("unpatchify: tensors must be contiguous")
+    B, Cc, H, W = out.shape
+    dt = DT_F32 if out.dtype == torch.float32 else DT_BF16
+    if latents is not None and (latents.dtype != out.dtype or not latents.is_contiguous()):
+        raise _lib.Dit4srError("unpatchify: latents must match out")
+    check(_lib.load().dit4sr_unpatchify(_ptr(tok), _ptr(out), dt, _ptr(latents), float(dsigma), B, Cc, H, W,
+                                        _stream()), "dit4sr_unpatchify")
+    _count()
+
+
+def timestep_features(t, out):
+    _req(t, torch.float32, "timestep")
+    _req(out, torch.bfloat16, "out")
+    check(_lib.load().dit4sr_timestep_features(_ptr(t), _ptr(out), t.shape[0], _stream()), "dit4sr_timestep_features")
+    _count()
+
+
+def silu_cast(x, out):
+    _req(x, torch.float32, "x")
+    _req(out, torch.bfloat16, "out")
+    check(_lib.load().dit4sr_silu_cast(_ptr(x), _ptr(out), x.numel(), _stream()), "dit4sr_silu_cast")
+    _count()
+
+
+def cast(x, out):
+    if not x.is_contiguous() or not out.is_contiguous():
+        raise _lib.Dit4srError("cast: tensors must be contiguous")
+    d = 0 if x.dtype == torch.float32 else 1
+    check(_lib.load().dit4sr_cast(_ptr(x), _ptr(out), x.numel(), d, _stream()), "dit4sr_cast")
+    _count()

@@ -1,0 +1,161 @@
+/* dit4sr_b200 -- C ABI of the B200 (sm_100a) kernels behind DiT4SR's denoising hot path.
+ *
+ * This is the drop-in boundary: plain C entry points, plain pointers and sizes, no torch types.
+ * The Python host (dit4sr_b200/ops.py) binds them with ctypes; INTEGRATION.md shows the binding a reference
+ * maintainer would add.  Each entry point names the reference code it replaces (paths relative to the
+ * jinlovespho/DiT4SR repository).
+ *
+ * Conventions
+ *   - All pointers are DEVICE pointers owned by the caller (e.g. PyTorch's caching allocator); the library never
+ *     allocates or frees device memory and keeps no pointer after a call returns.
+ *   - Every call is asynchronous on `stream` (a cudaStream_t passed as void*); no hidden synchronisation.
+ *   - Return value: 0 = success; negative = DIT4SR_E_* (bad argument / unsupported device); positive = cudaError_t.
+ *     dit4sr_last_error() returns a thread-local, human-readable description of the last failure.
+ *   - "bf16" = __nv_bfloat16 (uint16_t storage); all strides/leading dimensions are in ELEMENTS.
+ *   - Re-entrant and thread-safe (no mutable global state besides one-time function-attribute setup).
+ */
+#ifndef DIT4SR_B200_H_
+#define DIT4SR_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DIT4SR_ABI_VERSION 1
+
+enum {
+  DIT4SR_OK = 0,
+  DIT4SR_E_BADARG = -1,      /* null pointer, non-positive size */
+  DIT4SR_E_ALIGN = -2,       /* pointer / stride alignment not met */
+  DIT4SR_E_SHAPE = -3,       /* shape not supported by the kernel (documented per entry point) */
+  DIT4SR_E_ARCH = -4,        /* device is not compute capability 10.x */
+  DIT4SR_E_DRIVER = -5       /* cuTensorMapEncodeTiled unavailable / failed */
+};
+
+int dit4sr_abi_version(void);
+const char* dit4sr_last_error(void);
+/* 0 if the current device can run the kernels (compute capability 10.x), DIT4SR_E_ARCH otherwise. */
+int dit4sr_check_device(void);
+
+/* ---------------------------------------------------------------------------------------------------------------
+ * LayerNorm (no affine, eps) fused with adaLN modulation:  out = LN(x) * (1 + scale[b]) + shift[b]
+ * Replaces: diffusers AdaLayerNormZero / SD35AdaLayerNormZeroX / AdaLayerNormContinuous normalisation + modulation
+ * as called at model_dit4sr/attention.py:286-302,322-323,384-385 and model_dit4sr/transformer_sd3.py:382.
+ * One read of x, one or two bf16 outputs (the dual-attention blocks need two modulations of the same LN(x)).
+ * x: fp32 [batches, rows, dim] (row stride ldx, batch stride x_batch_stride). dim % 128 == 0, dim <= 4096.
+ * shift/scale: fp32, one vector of `dim` per batch (stride mod_batch_stride).  out2/shift2/scale2 may be NULL.
+ */
+typedef struct {
+  const float* x; int64_t ldx; int64_t x_batch_stride;
+  const float* shift; const float* scale;
+  const float* shift2; const float* scale2;
+  int64_t mod_batch_stride;
+  void* out; void* out2;               /* bf16 */
+  int64_t ldo; int64_t o_batch_stride;
+  int batches; int rows; int dim;
+  float eps;
+} dit4sr_ln_modulate_params;
+int dit4sr_ln_modulate(const dit4sr_ln_modulate_params* p, void* stream);
+
+/* ---------------------------------------------------------------------------------------------------------------
+ * Depthwise 3x3 convolution (zero pad 1, bias) of the LR half of the MLP hidden state, added into the HQ half,
+ * in place, directly on the token-major layout (tokens = rows of a grid x grid image, channels innermost):
+ *     u_hq[b, y, x, c] += bias[c] + sum_{dy,dx} w[c, dy, dx] * u_lr[b, y+dy-1, x+dx-1, c]
+ * Replaces: FeedForwardControl's reshape/permute + control_conv + add + cat, model_dit4sr/attention.py:168-177.
+ * u_hq / u_lr: bf16 [batches, grid*grid, channels] (row stride ld, batch stride given per pointer).
+ * weight: fp32 repacked tap-major [9, channels] (tap = dy*3+dx); bias fp32 [channels]. channels % 8 == 0.
+ */
+typedef struct {
+  void* u_hq; const void* u_lr;
+  int64_t ld; int64_t hq_batch_stride; int64_t lr_batch_stride;
+  const float* weight9; const float* bias;
+  int batches; int grid; int channels;
+} dit4sr_dwconv3x3_params;
+int dit4sr_dwconv3x3_add(const dit4sr_dwconv3x3_params* p, void* stream);
+
+/* ---------------------------------------------------------------------------------------------------------------
+ * Batched-row GEMM on tcgen05 tensor cores:  C[b, r, :] = epilogue( A[b, r, :] . W^T )
+ *   A: bf16 [batches, rows, K]  (lda, a_batch_stride)     W: bf16 [N, K] (ldw; nn.Linear weight layout)
+ * Replaces every nn.Linear on the path (model_dit4sr/attention.py:463-465,475-477,494-496,539,548,552, the
+ * GELU/Linear pair of FeedForward(Control) :94-100,:165-166, the adaLN `linear`s, context_embedder / proj_out /
+ * PatchEmbed.proj / time_text_embed in transformer_sd3.py:326-331,382-383) together with the elementwise work
+ * that follows it in the reference, selected by `epilogue`:
+ *   DIT4SR_EPI_BIAS       C = acc + bias                                   (C bf16 or fp32)
+ *   DIT4SR_EPI_BIAS_GELU  C = gelu_tanh(acc + bias)                        (diffusers GELU(approximate="tanh"))
+ *   DIT4SR_EPI_BIAS_SILU  C = silu(acc + bias)
+ *   DIT4SR_EPI_QKV_NORM   per 64-wide head: y = acc + bias; columns [0,sec_cols) use RMSNorm weight norm_w0,
+ *                         [sec_cols,2*sec_cols) norm_w1, the rest none (q|k|v fused projection followed by
+ *                         attn.norm_q / attn.norm_k, attention.py:484-489,502-505). If dbl_row_offset != 0 the k
+ *                         section is normalised a second time and also written dbl_row_offset rows further down
+ *                         (the reference's `key_control = attn.norm_k(key)` quirk, attention.py:489).
+ *   DIT4SR_EPI_GATE_RESID C(fp32) = resid + gate[b,:] * (acc + bias)        (gated residual, attention.py:314-320,
+ *                         329-347,381-393; gate NULL means 1; resid may alias C or be a broadcast tensor)
+ * Constraints: K % 8 == 0, N % 32 == 0 (N % 64 == 0 for QKV_NORM), 16-byte aligned pointers / strides.
+ */
+enum {
+  DIT4SR_EPI_BIAS = 0,
+  DIT4SR_EPI_BIAS_GELU = 1,
+  DIT4SR_EPI_BIAS_SILU = 2,
+  DIT4SR_EPI_QKV_NORM = 3,
+  DIT4SR_EPI_GATE_RESID = 4
+};
+enum { DIT4SR_DT_BF16 = 0, DIT4SR_DT_F32 = 1 };
+typedef struct {
+  const void* A; int64_t lda; int64_t a_batch_stride;
+  const void* W; int64_t ldw;
+  const float* bias;                       /* [N] or NULL */
+  void* C; int64_t ldc; int64_t c_batch_stride; int c_dtype;
+  int batches; int rows; int N; int K;
+  int epilogue;
+  const float* gate; int64_t gate_batch_stride;           /* GATE_RESID */
+  const float* resid; int64_t ldr; int64_t r_batch_stride;
+  const float* norm_w0; const float* norm_w1;             /* QKV_NORM: fp32 [64] each (NULL = no norm) */
+  int sec_cols; float eps; int64_t dbl_row_offset;
+} dit4sr_gemm_params;
+int dit4sr_gemm_bf16(const dit4sr_gemm_params* p, void* stream);
+
+/* ---------------------------------------------------------------------------------------------------------------
+ * Joint attention, flash-style on tcgen05:  O = softmax(Q K^T * scale) V, non-causal, no mask, head_dim 64.
+ * Replaces F.scaled_dot_product_attention over the concatenated [HQ | LR | text] sequence
+ * (model_dit4sr/attention.py:508-530) plus the LR-stream residual add at :545.
+ * q/k/v: bf16, element (b, s, h, d) at  ptr + b*batch_stride + s*row_stride + h*64 + d   (the fused projection
+ * buffer [B, S, 3*H*64] is addressed with row_stride = 3*H*64 and q/k/v pointers 0 / H*64 / 2*H*64 apart).
+ * o: bf16 [B, Sq, H*64] (row stride o_row_stride).  Only the first seq_q query rows are computed (the last block
+ * drops the text queries).  If lr_res != NULL, rows [lr_row_begin, lr_row_end) of o get lr_res[b, row, :] added.
+ */
+typedef struct {
+  const void* q; const void* k; const void* v;
+  int64_t qkv_row_stride; int64_t qkv_batch_stride;
+  void* o; int64_t o_row_stride; int64_t o_batch_stride;
+  const void* lr_res; int64_t lr_row_stride; int64_t lr_batch_stride;   /* bf16, indexed by the same row ids as o */
+  int lr_row_begin; int lr_row_end;
+  int batches; int heads; int seq_q; int seq_kv;
+  float scale;
+} dit4sr_attn_params;
+int dit4sr_attn_fwd(const dit4sr_attn_params* p, void* stream);
+
+/* ---------------------------------------------------------------------------------------------------------------
+ * Small data-movement kernels of the model head / tail (transformer_sd3.py:326-332,379-391).
+ */
+/* im2col for PatchEmbed's k=2,s=2 conv: x [B, C, H, W] (fp32 or bf16) -> patches bf16 [B, (H/2)*(W/2), C*4],
+ * inner order (c, ph, pw) = the flattened conv weight [D, C, 2, 2]. */
+int dit4sr_patchify(const void* x, int x_dtype, void* patches, int batches, int channels, int height, int width,
+                    void* stream);
+/* unpatchify 'b (H W) (pH pW d) -> b d (H pH) (W pW)': tok fp32 [B, (H/2)*(W/2), 4*C] -> out [B, C, H, W].
+ * If `latents` != NULL performs the flow-match Euler update instead of a plain store:
+ *   out = latents + dsigma * velocity   (pipelines/pipeline_dit4sr.py:1567, scheduler.step) */
+int dit4sr_unpatchify(const float* tok, void* out, int out_dtype, const void* latents, float dsigma, int batches,
+                      int channels, int height, int width, void* stream);
+/* sinusoidal timestep features [cos | sin] (diffusers Timesteps(256, flip_sin_to_cos=True, shift 0)) -> bf16 [B, 256] */
+int dit4sr_timestep_features(const float* timesteps, void* out_bf16, int batches, void* stream);
+/* y = silu(x) (fp32 -> bf16), n elements */
+int dit4sr_silu_cast(const float* x, void* y_bf16, int64_t n, void* stream);
+/* y = x (fp32 -> bf16 or bf16 -> fp32), n elements; dir 0 = f32->bf16, 1 = bf16->f32 */
+int dit4sr_cast(const void* x, void* y, int64_t n, int dir, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DIT4SR_B200_H_ */
