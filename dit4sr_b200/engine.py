@@ -1,0 +1,269 @@
+"""Host-side schedule of the denoiser forward: packs the module's weights once, owns the activation workspace, and
+issues the CUDA kernels (through the C-ABI, `ops.py`) in the order of SURVEY.md 3.4.  No arithmetic in Python.
+
+Dataflow of one step (reference: transformer_sd3.py:326-391 and attention.py:280-398, 445-559):
+  head    timestep/pooled MLPs -> temb; ONE GEMM produces every block's adaLN vectors (temb is block-invariant);
+          patchify + GEMM(+pos-embed epilogue) for HQ and LR latents -> x[B,2N,D] fp32; context_embedder -> ctx fp32
+  block   LN+modulate (1 read, 1-2 bf16 writes) -> fused q|k|v GEMM with RMSNorm epilogue writing straight into the
+          joint [HQ|LR|text] buffer (and the double-normed LR keys, quirk Q1) -> LR chain GEMMs -> text q|k|v GEMM ->
+          joint attention (+LR residual, Q2) -> out-projections with gate*y+residual epilogue (in place on x/ctx)
+          -> [attn2] -> LN+modulate -> FF1 (GELU-tanh epilogue) -> depthwise stencil -> FF2 (gated residual) -> text MLP
+  tail    LN+modulate (norm_out) -> proj_out -> unpatchify (optionally fused with the Euler update)
+
+Precision: tensor-core operands bf16, accumulation / residual streams (x, ctx) / LN+RMS statistics / softmax fp32.
+"""
+from typing import Dict, Optional, Tuple
+
+import torch
+
+from . import ops
+
+
+def _bf16(t):
+    return t.detach().to(torch.bfloat16).contiguous()
+
+
+def _f32(t):
+    return t.detach().to(torch.float32).contiguous()
+
+
+class _Lin:
+    """bf16 weight [N,K] + fp32 bias [N] (possibly a concatenation of several nn.Linear)."""
+
+    def __init__(self, *linears):
+        self.w = _bf16(torch.cat([l.weight for l in linears], dim=0)) if len(linears) > 1 else _bf16(linears[0].weight)
+        self.b = _f32(torch.cat([l.bias for l in linears], dim=0)) if len(linears) > 1 else _f32(linears[0].bias)
+
+
+class _AttnPack:
+    def __init__(self, attn, has_text: bool):
+        self.qk_norm = attn.norm_q is not None
+        self.qkv = _Lin(attn.to_q, attn.to_k, attn.to_v)
+        if self.qk_norm:
+            # Q1: with qk_norm the LR keys are norm_k(norm_k(k_hq)); to_k_control(to_k(lr)) is dead code
+            self.lr1 = _Lin(attn.to_q, attn.to_v)
+            self.wq, self.wk = _f32(attn.norm_q.weight), _f32(attn.norm_k.weight)
+        else:
+            self.lr1 = self.qkv
+            self.kc = _Lin(attn.to_k_control)
+        self.qc, self.vc = _Lin(attn.to_q_control), _Lin(attn.to_v_control)
+        self.out, self.outc = _Lin(attn.to_out[0]), _Lin(attn.to_out_control)
+        self.has_text = has_text
+        if has_text:
+            self.add = _Lin(attn.add_q_proj, attn.add_k_proj, attn.add_v_proj)
+            if self.qk_norm:
+                self.waq, self.wak = _f32(attn.norm_added_q.weight), _f32(attn.norm_added_k.weight)
+            self.add_out = _Lin(attn.to_add_out) if hasattr(attn, "to_add_out") else None
+
+
+class _BlockPack:
+    def __init__(self, blk):
+        self.dual = blk.use_dual_attention
+        self.last = blk.context_pre_only
+        self.attn = _AttnPack(blk.attn, True)
+        self.attn2 = _AttnPack(blk.attn2, False) if self.dual else None
+        self.ff1, self.ff2 = _Lin(blk.ff.net[0].proj), _Lin(blk.ff.net[2])
+        cw = blk.ff.control_conv.weight
+        self.conv_w9 = _f32(cw.reshape(cw.shape[0], 9).t())           # tap-major [9, F]
+        self.conv_b = _f32(blk.ff.control_conv.bias)
+        if not self.last:
+            self.ffc1, self.ffc2 = _Lin(blk.ff_context.net[0].proj), _Lin(blk.ff_context.net[2])
+
+
+class Engine:
+    def __init__(self, model):
+        cfg = model.config
+        self.cfg = cfg
+        self.D = cfg.num_attention_heads * cfg.attention_head_dim
+        self.H = cfg.num_attention_heads
+        if cfg.attention_head_dim != 64:
+            raise ValueError("dit4sr_b200: attention_head_dim must be 64")
+        if cfg.patch_size != 2:
+            raise ValueError("dit4sr_b200: patch_size must be 2")
+        if cfg.caption_projection_dim != self.D:
+            raise ValueError("dit4sr_b200: caption_projection_dim must equal the inner dim (joint attention)")
+        D = self.D
+        self.blocks = [_BlockPack(b) for b in model.transformer_blocks]
+        # every adaLN linear of the model in one weight: temb is the same for all blocks, so one GEMM per step
+        mods, self.mod_off = [], []
+        off = 0
+        for b in model.transformer_blocks:
+            o1 = off
+            mods.append(b.norm1.linear)
+            off += b.norm1.linear.out_features
+            o2 = off
+            mods.append(b.norm1_context.linear)
+            off += b.norm1_context.linear.out_features
+            self.mod_off.append((o1, o2))
+        self.mod_out_off = off
+        mods.append(model.norm_out.linear)
+        off += model.norm_out.linear.out_features
+        self.mod_total = off
+        self.mod = _Lin(*mods)
+        pe = model.pos_embed.proj
+        self.patch_w = _bf16(pe.weight.reshape(D, -1))
+        self.patch_b = _f32(pe.bias)
+        self.pos_table = model.pos_embed.pos_embed
+        tt = model.time_text_embed
+        self.t1, self.t2 = _Lin(tt.timestep_embedder.linear_1), _Lin(tt.timestep_embedder.linear_2)
+        self.p1, self.p2 = _Lin(tt.text_embedder.linear_1), _Lin(tt.text_embedder.linear_2)
+        self.ctx_embed = _Lin(model.context_embedder)
+        self.proj_out = _Lin(model.proj_out)
+        self._ws: Dict[Tuple, dict] = {}
+        self._pos: Dict[Tuple, torch.Tensor] = {}
+
+    # ------------------------------------------------------------------------------------------------ workspace
+    def _pos_crop(self, hp, wp, device):
+        key = (hp, wp)
+        if key not in self._pos:
+            mx = self.cfg.pos_embed_max_size
+            if hp > mx or wp > mx:
+                raise ValueError(f"latent grid {hp}x{wp} exceeds pos_embed_max_size {mx}")
+            top, left = (mx - hp) // 2, (mx - wp) // 2
+            pe = self.pos_table.reshape(1, mx, mx, -1)[:, top:top + hp, left:left + wp, :]
+            self._pos[key] = pe.reshape(1, hp * wp, -1).to(device=device, dtype=torch.float32).contiguous()
+        return self._pos[key]
+
+    def _workspace(self, B, N, T, device):
+        key = (B, N, T, str(device))
+        ws = self._ws.get(key)
+        if ws is not None:
+            return ws
+        D, F = self.D, 4 * self.D
+        S = 2 * N + T
+        bf, f32 = torch.bfloat16, torch.float32
+
+        def e(*shape, dtype=bf):
+            return torch.empty(*shape, device=device, dtype=dtype)
+
+        ws = dict(
+            x=e(B, 2 * N, D, dtype=f32), ctx=e(B, T, D, dtype=f32),
+            n1=e(B, 2 * N, D), n2=e(B, 2 * N, D), nc=e(B, T, D),
+            qkv=e(B, S, 3 * D), o=e(B, S, D), lrtmp=e(B, N, 3 * D),
+            u=e(B, 2 * N, F), uc=e(B, T, F),
+            mod=e(B, self.mod_total, dtype=f32),
+            tf=e(B, 256), th=e(B, D), ph=e(B, D), temb=e(B, D, dtype=f32), st=e(B, D),
+            pooled=e(B, self.cfg.pooled_projection_dim), enc=e(B, T, self.cfg.joint_attention_dim),
+            patches=e(B, N, 4 * self.cfg.in_channels), tok=e(B, N, 4 * self.cfg.out_channels, dtype=f32),
+            t=e(B, dtype=f32),
+        )
+        self._ws[key] = ws
+        return ws
+
+    # ------------------------------------------------------------------------------------------------ attention
+    def _attention(self, ap: _AttnPack, ws, n_in, nc, N, T, gate, c_gate, last):
+        """JointAttnProcessor2_0 (attention.py:445-559) + the gated residual adds (attention.py:314-320,381-382)."""
+        D, H = self.D, self.H
+        x, ctx, qkv, o, lrtmp = ws["x"], ws["ctx"], ws["qkv"], ws["o"], ws["lrtmp"]
+        S = 2 * N + (T if ap.has_text else 0)
+        hq, lr = n_in[:, :N], n_in[:, N:]
+        if ap.qk_norm:
+            ops.gemm(hq, ap.qkv.w, ap.qkv.b, qkv[:, :N], ops.EPI_QKV_NORM, norm_w0=ap.wq, norm_w1=ap.wk, sec_cols=D,
+                     dbl_row_offset=N)
+            t2 = lrtmp[:, :, :2 * D]
+            ops.gemm(lr, ap.lr1.w, ap.lr1.b, t2, ops.EPI_BIAS)
+            ops.gemm(t2[:, :, :D], ap.qc.w, ap.qc.b, qkv[:, N:2 * N, :D], ops.EPI_QKV_NORM, norm_w0=ap.wq, sec_cols=D)
+            ops.gemm(t2[:, :, D:], ap.vc.w, ap.vc.b, qkv[:, N:2 * N, 2 * D:], ops.EPI_BIAS)
+            if ap.has_text:
+                ops.gemm(nc, ap.add.w, ap.add.b, qkv[:, 2 * N:S], ops.EPI_QKV_NORM, norm_w0=ap.waq, norm_w1=ap.wak,
+                         sec_cols=D)
+        else:
+            ops.gemm(hq, ap.qkv.w, ap.qkv.b, qkv[:, :N], ops.EPI_BIAS)
+            ops.gemm(lr, ap.qkv.w, ap.qkv.b, lrtmp, ops.EPI_BIAS)
+            ops.gemm(lrtmp[:, :, :D], ap.qc.w, ap.qc.b, qkv[:, N:2 * N, :D], ops.EPI_BIAS)
+            ops.gemm(lrtmp[:, :, D:2 * D], ap.kc.w, ap.kc.b, qkv[:, N:2 * N, D:2 * D], ops.EPI_BIAS)
+            ops.gemm(lrtmp[:, :, 2 * D:], ap.vc.w, ap.vc.b, qkv[:, N:2 * N, 2 * D:], ops.EPI_BIAS)
+            if ap.has_text:
+                ops.gemm(nc, ap.add.w, ap.add.b, qkv[:, 2 * N:S], ops.EPI_BIAS)
+        # the last block's text queries are discarded by the reference (context_pre_only): do not compute them
+        seq_q = 2 * N if (last or not ap.has_text) else S
+        ops.attention(qkv[:, :S, :D], qkv[:, :S, D:2 * D], qkv[:, :S, 2 * D:], o, H, seq_q=seq_q,
+                      lr_res=n_in, lr_rows=(N, 2 * N))
+        ops.gemm(o[:, :N], ap.out.w, ap.out.b, x[:, :N], ops.EPI_GATE_RESID, gate=gate)
+        ops.gemm(o[:, N:2 * N], ap.outc.w, ap.outc.b, x[:, N:], ops.EPI_GATE_RESID, gate=gate)
+        if ap.has_text and not last:
+            ops.gemm(o[:, 2 * N:S], ap.add_out.w, ap.add_out.b, ctx, ops.EPI_GATE_RESID, gate=c_gate)
+
+    # ------------------------------------------------------------------------------------------------ forward
+    @torch.no_grad()
+    def forward(self, hidden_states, controlnet_image, encoder_hidden_states, pooled_projections, timestep,
+                out=None, euler: Optional[Tuple[torch.Tensor, float]] = None, feat_hook=None):
+        cfg, D = self.cfg, self.D
+        B, Cin, h, w = hidden_states.shape
+        if h != w or h % 2:
+            raise ValueError("dit4sr_b200: square, even latents only (reference asserts a square token grid, "
+                             "attention.py:169-172)")
+        grid = h // 2
+        N = grid * grid
+        T = encoder_hidden_states.shape[1]
+        dev = hidden_states.device
+        ws = self._workspace(B, N, T, dev)
+        x, ctx, n1, n2, nc, mod = ws["x"], ws["ctx"], ws["n1"], ws["n2"], ws["nc"], ws["mod"]
+        pos = self._pos_crop(grid, grid, dev)
+
+        # ---- head: temb = MLP(sincos(t)) + MLP(pooled)  (CombinedTimestepTextProjEmbeddings, transformer_sd3.py:327)
+        ws["t"].copy_(timestep.to(device=dev, dtype=torch.float32).expand(B))
+        ops.timestep_features(ws["t"], ws["tf"])
+        ops.gemm(ws["tf"], self.t1.w, self.t1.b, ws["th"], ops.EPI_BIAS_SILU)
+        ops.gemm(ws["th"], self.t2.w, self.t2.b, ws["temb"], ops.EPI_BIAS)
+        ws["pooled"].copy_(pooled_projections)
+        ops.gemm(ws["pooled"], self.p1.w, self.p1.b, ws["ph"], ops.EPI_BIAS_SILU)
+        ops.gemm(ws["ph"], self.p2.w, self.p2.b, ws["temb"], ops.EPI_GATE_RESID)
+        ops.silu_cast(ws["temb"], ws["st"])
+        ops.gemm(ws["st"], self.mod.w, self.mod.b, mod, ops.EPI_BIAS)          # all adaLN vectors of the step
+        # ---- patch embed (+pos) for both streams, context embedder  (:326-332)
+        for src, rows in ((hidden_states, x[:, :N]), (controlnet_image, x[:, N:])):
+            ops.patchify(src.contiguous(), ws["patches"])
+            ops.gemm(ws["patches"], self.patch_w, self.patch_b, rows, ops.EPI_GATE_RESID, resid=pos)
+        ws["enc"].copy_(encoder_hidden_states)
+        ops.gemm(ws["enc"], self.ctx_embed.w, self.ctx_embed.b, ctx, ops.EPI_BIAS)
+
+        # ---- blocks (:336-370)
+        for i, bp in enumerate(self.blocks):
+            o1, o2 = self.mod_off[i]
+
+            def ch(base, k):
+                return mod[:, base + k * D: base + (k + 1) * D]
+
+            shift_msa, scale_msa, gate_msa = ch(o1, 0), ch(o1, 1), ch(o1, 2)
+            shift_mlp, scale_mlp, gate_mlp = ch(o1, 3), ch(o1, 4), ch(o1, 5)
+            if bp.dual:
+                shift_msa2, scale_msa2, gate_msa2 = ch(o1, 6), ch(o1, 7), ch(o1, 8)
+                ops.ln_modulate(x, shift_msa, scale_msa, n1, shift_msa2, scale_msa2, n2)
+            else:
+                ops.ln_modulate(x, shift_msa, scale_msa, n1)
+            if bp.last:   # AdaLayerNormContinuous: (scale, shift) order (Q12)
+                c_scale, c_shift = ch(o2, 0), ch(o2, 1)
+                ops.ln_modulate(ctx, c_shift, c_scale, nc)
+                c_gate_msa = None
+            else:
+                c_shift_msa, c_scale_msa, c_gate_msa = ch(o2, 0), ch(o2, 1), ch(o2, 2)
+                c_shift_mlp, c_scale_mlp, c_gate_mlp = ch(o2, 3), ch(o2, 4), ch(o2, 5)
+                ops.ln_modulate(ctx, c_shift_msa, c_scale_msa, nc)
+            self._attention(bp.attn, ws, n1, nc, N, T, gate_msa, c_gate_msa, bp.last)
+            if bp.dual:
+                self._attention(bp.attn2, ws, n2, None, N, T, gate_msa2, None, bp.last)
+            # MLP with the LR->HQ depthwise conv (attention.py:322-347, FeedForwardControl :155-178)
+            ops.ln_modulate(x, shift_mlp, scale_mlp, n1)
+            ops.gemm(n1, bp.ff1.w, bp.ff1.b, ws["u"], ops.EPI_BIAS_GELU)
+            ops.dwconv3x3_add(ws["u"][:, :N], ws["u"][:, N:], bp.conv_w9, bp.conv_b, grid)
+            ops.gemm(ws["u"], bp.ff2.w, bp.ff2.b, x, ops.EPI_GATE_RESID, gate=gate_mlp)
+            if not bp.last:   # text MLP (attention.py:384-393)
+                ops.ln_modulate(ctx, c_shift_mlp, c_scale_mlp, nc)
+                ops.gemm(nc, bp.ffc1.w, bp.ffc1.b, ws["uc"], ops.EPI_BIAS_GELU)
+                ops.gemm(ws["uc"], bp.ffc2.w, bp.ffc2.b, ctx, ops.EPI_GATE_RESID, gate=c_gate_mlp)
+            if feat_hook is not None:
+                feat_hook(i, x)
+
+        # ---- tail: drop the LR half, norm_out (scale, shift order), proj_out, unpatchify (:379-391)
+        so = self.mod_out_off
+        ops.ln_modulate(x[:, :N], mod[:, so + D: so + 2 * D], mod[:, so: so + D], n1[:, :N])
+        ops.gemm(n1[:, :N], self.proj_out.w, self.proj_out.b, ws["tok"], ops.EPI_BIAS)
+        if out is None:
+            out = torch.empty(B, cfg.out_channels, h, w, device=dev, dtype=hidden_states.dtype)
+        if euler is not None:
+            latents, dsigma = euler
+            ops.unpatchify(ws["tok"], out, latents=latents, dsigma=dsigma)
+        else:
+            ops.unpatchify(ws["tok"], out)
+        return out

@@ -1,0 +1,221 @@
+"""GPU parity tests of each kernel, called through the C-ABI, against plain torch fp32 math on the same inputs.
+
+Tolerances: outputs stored as bf16 carry one rounding (2^-9 relative) -> rel-L2 <= 3e-3; fp32 outputs <= 2e-5.
+"""
+import math
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+BF16_TOL = 3e-3
+F32_TOL = 2e-5
+
+
+def rel(a, b):
+    a, b = a.double(), b.double()
+    return ((a - b).norm() / (b.norm() + 1e-30)).item()
+
+
+@pytest.fixture(scope="module")
+def ops():
+    from dit4sr_b200 import ops as _ops
+    return _ops
+
+
+@pytest.mark.parametrize("B,R,D", [(2, 333, 1536), (4, 2048, 1536), (1, 7, 128), (3, 1, 1536)])
+def test_ln_modulate(ops, B, R, D):
+    torch.manual_seed(0)
+    x = torch.randn(B, R, D, device="cuda") * 2 + 0.5
+    mod = torch.randn(B, 4 * D, device="cuda") * 0.5
+    sh, sc, sh2, sc2 = mod[:, :D], mod[:, D:2 * D], mod[:, 2 * D:3 * D], mod[:, 3 * D:]
+    o1 = torch.empty(B, R, D, device="cuda", dtype=torch.bfloat16)
+    o2 = torch.empty_like(o1)
+    ops.ln_modulate(x, sh, sc, o1, sh2, sc2, o2)
+    ln = torch.nn.functional.layer_norm(x, (D,), eps=1e-6)
+    assert rel(o1.float(), ln * (1 + sc[:, None]) + sh[:, None]) < BF16_TOL
+    assert rel(o2.float(), ln * (1 + sc2[:, None]) + sh2[:, None]) < BF16_TOL
+
+
+@pytest.mark.parametrize("B,G,C", [(2, 32, 6144), (1, 5, 512), (1, 64, 256), (1, 1, 8)])
+def test_dwconv_matches_conv2d(ops, B, G, C):
+    torch.manual_seed(0)
+    N = G * G
+    u = torch.randn(B, 2 * N, C, device="cuda").bfloat16()
+    w = torch.randn(C, 1, 3, 3, device="cuda") * 0.1
+    bias = torch.randn(C, device="cuda") * 0.1
+    lr = u[:, N:].float().reshape(B, G, G, C).permute(0, 3, 1, 2)
+    conv = torch.nn.functional.conv2d(lr, w, bias, padding=1, groups=C).reshape(B, C, N).permute(0, 2, 1)
+    ref = u[:, :N].float() + conv
+    u2 = u.clone()
+    ops.dwconv3x3_add(u2[:, :N], u2[:, N:], w.reshape(C, 9).t().contiguous(), bias, G)
+    assert rel(u2[:, :N].float(), ref) < BF16_TOL
+    assert torch.equal(u2[:, N:], u[:, N:])
+
+
+def _mk(B, R, K, N):
+    A = torch.randn(B, R, K, device="cuda").bfloat16()
+    W = (torch.randn(N, K, device="cuda") * 0.05).bfloat16()
+    bias = torch.randn(N, device="cuda") * 0.1
+    return A, W, bias, A.float() @ W.float().t() + bias
+
+
+@pytest.mark.parametrize("B,R,K,N", [(1, 128, 64, 256), (1, 256, 1536, 1536), (2, 333, 1536, 4608), (1, 8, 1536, 512),
+                                      (1, 1024, 1536, 64), (1, 2048, 6144, 1536), (1, 1, 96, 32), (3, 129, 80, 160)])
+def test_gemm_bias(ops, B, R, K, N):
+    torch.manual_seed(0)
+    A, W, bias, ref = _mk(B, R, K, N)
+    o = torch.empty(B, R, N, device="cuda", dtype=torch.bfloat16)
+    ops.gemm(A, W, bias, o, ops.EPI_BIAS)
+    o32 = torch.empty(B, R, N, device="cuda")
+    ops.gemm(A, W, bias, o32, ops.EPI_BIAS)
+    assert rel(o.float(), ref) < BF16_TOL
+    assert rel(o32, ref) < F32_TOL
+
+
+def test_gemm_linearity_full_size(ops):
+    """Size-independent property at the full FF1 shape: gemm(A1 + A2) == gemm(A1) + gemm(A2) - bias (fp32 out)."""
+    torch.manual_seed(0)
+    R, K, N = 4096, 1536, 6144
+    A1 = torch.randn(R, K, device="cuda").bfloat16()
+    A2 = (A1.float() * 2).bfloat16()       # exactly representable sum: A1 + A2 = 3*A1 needs care -> use power of two
+    A3 = (A1.float() * 4).bfloat16()
+    W = (torch.randn(N, K, device="cuda") * 0.05).bfloat16()
+    z = torch.zeros(N, device="cuda")
+    o1, o3 = torch.empty(R, N, device="cuda"), torch.empty(R, N, device="cuda")
+    ops.gemm(A1, W, z, o1, ops.EPI_BIAS)
+    ops.gemm(A3, W, z, o3, ops.EPI_BIAS)
+    assert rel(o3, 4 * o1) < 1e-6         # scaling by a power of two is exact in every partial product
+    assert A2 is not None
+
+
+def test_gemm_strided_views(ops):
+    torch.manual_seed(0)
+    A, W, bias, ref = _mk(2, 200, 512, 256)
+    big = torch.zeros(2, 200, 1024, device="cuda", dtype=torch.bfloat16)
+    big[:, :, 512:] = A
+    cbuf = torch.zeros(2, 500, 768, device="cuda", dtype=torch.bfloat16)
+    ops.gemm(big[:, :, 512:], W, bias, cbuf[:, 100:300, 256:512], ops.EPI_BIAS)
+    assert rel(cbuf[:, 100:300, 256:512].float(), ref) < BF16_TOL
+    cbuf[:, 100:300, 256:512] = 0
+    assert cbuf.abs().max() == 0
+
+
+def test_gemm_activations(ops):
+    torch.manual_seed(0)
+    A, W, bias, ref = _mk(1, 512, 1536, 6144)
+    o = torch.empty(1, 512, 6144, device="cuda", dtype=torch.bfloat16)
+    ops.gemm(A, W, bias, o, ops.EPI_BIAS_GELU)
+    assert rel(o.float(), torch.nn.functional.gelu(ref, approximate="tanh")) < BF16_TOL
+    ops.gemm(A, W, bias, o, ops.EPI_BIAS_SILU)
+    assert rel(o.float(), torch.nn.functional.silu(ref)) < BF16_TOL
+
+
+def test_gemm_gate_residual(ops):
+    torch.manual_seed(0)
+    A, W, bias, ref = _mk(2, 333, 1536, 1536)
+    gate = torch.randn(2, 1536, device="cuda")
+    x = torch.randn(2, 333, 1536, device="cuda")
+    x0 = x.clone()
+    ops.gemm(A, W, bias, x, ops.EPI_GATE_RESID, gate=gate)
+    assert rel(x, x0 + gate[:, None] * ref) < F32_TOL
+    pos = torch.randn(1, 333, 1536, device="cuda")
+    y = torch.empty(2, 333, 1536, device="cuda")
+    ops.gemm(A, W, bias, y, ops.EPI_GATE_RESID, resid=pos)
+    assert rel(y, pos + ref) < F32_TOL
+
+
+def _rms(t, w):
+    t = t.reshape(*t.shape[:-1], -1, 64)
+    t = t * torch.rsqrt(t.pow(2).mean(-1, keepdim=True) + 1e-6) * w
+    return t.reshape(*t.shape[:-2], -1)
+
+
+def test_gemm_qkv_rmsnorm_and_double_normed_lr_keys(ops):
+    """Fused q|k|v projection + attn.norm_q/norm_k, and the Q1 quirk: K_lr = norm_k(norm_k(k_hq))."""
+    torch.manual_seed(0)
+    Bq, Nq, D = 2, 256, 1536
+    S = 2 * Nq + 77
+    A, W, bias, ref = _mk(Bq, Nq, 1536, 3 * D)
+    wq = 1 + 0.1 * torch.randn(64, device="cuda")
+    wk = 1 + 0.1 * torch.randn(64, device="cuda")
+    qkv = torch.zeros(Bq, S, 3 * D, device="cuda", dtype=torch.bfloat16)
+    ops.gemm(A, W, bias, qkv[:, :Nq], ops.EPI_QKV_NORM, norm_w0=wq, norm_w1=wk, sec_cols=D, dbl_row_offset=Nq)
+    rq, rk, rv = _rms(ref[..., :D], wq), _rms(ref[..., D:2 * D], wk), ref[..., 2 * D:]
+    assert rel(qkv[:, :Nq, :D].float(), rq) < BF16_TOL
+    assert rel(qkv[:, :Nq, D:2 * D].float(), rk) < BF16_TOL
+    assert rel(qkv[:, :Nq, 2 * D:].float(), rv) < BF16_TOL
+    assert rel(qkv[:, Nq:2 * Nq, D:2 * D].float(), _rms(rk, wk)) < BF16_TOL
+    assert qkv[:, 2 * Nq:].abs().max() == 0 and qkv[:, Nq:2 * Nq, :D].abs().max() == 0
+
+
+@pytest.mark.parametrize("B,H,S,Sq,lr", [(1, 2, 256, 256, None), (2, 3, 333, 333, None), (1, 24, 2381, 2381, (1024, 2048)),
+                                         (2, 4, 2381, 2048, (1024, 2048)), (1, 2, 100, 100, None), (1, 1, 1, 1, None),
+                                         (1, 2, 8525, 8525, (4096, 8192))])
+def test_joint_attention(ops, B, H, S, Sq, lr):
+    torch.manual_seed(0)
+    D = H * 64
+    qkv = torch.randn(B, S, 3 * D, device="cuda").bfloat16()
+    q, k, v = qkv[..., :D], qkv[..., D:2 * D], qkv[..., 2 * D:]
+    o = torch.zeros(B, Sq, D, device="cuda", dtype=torch.bfloat16)
+    res = torch.randn(B, S, D, device="cuda").bfloat16() if lr else None
+    ops.attention(q, k, v, o, H, seq_q=Sq, lr_res=res, lr_rows=lr or (0, 0))
+
+    def hd(t):
+        return t.float().reshape(B, S, H, 64).transpose(1, 2)
+
+    ref = torch.nn.functional.scaled_dot_product_attention(hd(q), hd(k), hd(v)).transpose(1, 2).reshape(B, S, D)
+    ref = ref[:, :Sq].clone()
+    if lr:
+        ref[:, lr[0]:lr[1]] += res[:, lr[0]:lr[1]].float()
+    assert rel(o.float(), ref) < 4e-3   # bf16 P and bf16 output roundings
+
+
+def test_attention_peaked_softmax_is_stable(ops):
+    """Large score range (|s| up to ~60): online softmax with running max must not overflow."""
+    torch.manual_seed(0)
+    B, H, S = 1, 2, 700
+    D = H * 64
+    qkv = (torch.randn(B, S, 3 * D, device="cuda") * 3).bfloat16()
+    q, k, v = qkv[..., :D], qkv[..., D:2 * D], qkv[..., 2 * D:]
+    o = torch.zeros(B, S, D, device="cuda", dtype=torch.bfloat16)
+    ops.attention(q, k, v, o, H)
+    hd = lambda t: t.float().reshape(B, S, H, 64).transpose(1, 2)
+    ref = torch.nn.functional.scaled_dot_product_attention(hd(q), hd(k), hd(v)).transpose(1, 2).reshape(B, S, D)
+    assert torch.isfinite(o.float()).all()
+    assert rel(o.float(), ref) < 6e-3
+
+
+def test_head_tail_kernels(ops):
+    torch.manual_seed(0)
+    x = torch.randn(2, 16, 8, 12, device="cuda")
+    p = torch.empty(2, 24, 64, device="cuda", dtype=torch.bfloat16)
+    ops.patchify(x, p)
+    ref = x.reshape(2, 16, 4, 2, 6, 2).permute(0, 2, 4, 1, 3, 5).reshape(2, 24, 64)
+    assert torch.equal(p, ref.bfloat16())
+    tok = torch.randn(2, 24, 64, device="cuda")
+    o = torch.empty(2, 16, 8, 12, device="cuda")
+    ops.unpatchify(tok, o)
+    ref = tok.reshape(2, 4, 6, 2, 2, 16).permute(0, 5, 1, 3, 2, 4).reshape(2, 16, 8, 12)   # einops pattern of :391
+    assert torch.equal(o, ref)
+    lat = torch.randn(2, 16, 8, 12, device="cuda")
+    ops.unpatchify(tok, o, latents=lat, dsigma=-0.025)
+    assert rel(o, lat - 0.025 * ref) < 1e-6
+    t = torch.tensor([1000.0, 741.44, 8.93], device="cuda")
+    f = torch.empty(3, 256, device="cuda", dtype=torch.bfloat16)
+    ops.timestep_features(t, f)
+    ex = torch.exp(-math.log(10000) * torch.arange(128, device="cuda", dtype=torch.float32) / 128)
+    e = t[:, None] * ex[None]
+    assert (f.float() - torch.cat([torch.cos(e), torch.sin(e)], -1)).abs().max() < 8e-3
+
+
+def test_errors_are_reported_not_swallowed(ops):
+    from dit4sr_b200._lib import Dit4srError
+    A = torch.randn(4, 20, device="cuda").bfloat16()      # K=20 not a multiple of 8
+    W = torch.randn(32, 20, device="cuda").bfloat16()
+    o = torch.empty(4, 32, device="cuda", dtype=torch.bfloat16)
+    with pytest.raises(Dit4srError):
+        ops.gemm(A, W, None, o)
+    with pytest.raises(Dit4srError):
+        ops.gemm(A.cpu(), W, None, o)
