@@ -1,0 +1,364 @@
+#!/usr/bin/env python
+"""Benchmark of the DiT4SR denoising hot path (BASELINE.json metric: DiT denoise steps/sec).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--workload c2|c3|px1024|px2048]
+
+Workload at N=1 (default): BASELINE config C2 -- SD3.5-medium-shaped DiT4SR transformer (24 joint blocks, hidden 1536,
+24 heads, dual attention in blocks 0-12, QK-RMSNorm, random init), bf16, batch 8, 512px (64x64 latents -> 1024 HQ +
+1024 LR + 333 text tokens), stepping through the 40-step flow-match schedule.  One "step" = one denoise step of the
+whole batch (model forward + fused Euler update).  N>1: one process per GPU (torchrun), every rank runs its own batch
+(data-parallel sampling, no data-path collective) -> weak scaling; time = max over ranks.
+
+Prints ONE JSON line (see README / DESIGN.md for the keys).  `--impl reference` times the CPU restatement of the
+reference (oracle/, plain PyTorch fp32, all host threads) on a bounded sample of the same workload.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    # name: (latent side, per-GPU batch, text tokens, description)
+    "c2": (64, 8, 333, "C2: SD3.5-medium-shaped DiT4SR, bf16, 512px (1024 HQ + 1024 LR + 333 text tokens), batch 8 per GPU, "
+                       "40-step flow-match schedule"),
+    "c3": (128, 4, 333, "C3-per-GPU slice: 1024px (4096 HQ + 4096 LR + 333 text), batch 4 per GPU"),
+    "px1024": (128, 1, 333, "1024px batch 1"),
+    "px2048": (256, 1, 333, "2048px batch 1 (single GPU, no sequence parallelism)"),
+}
+
+
+def flops_per_image_step(N, T, L=24, dual=13, D=1536):
+    """Algorithmic FLOPs of one denoise step of one image (dead LR-key GEMMs removed, no folding)."""
+    F = 4 * D
+    gemm = 0.0
+    attn = 0.0
+    for i in range(L):
+        last = i == L - 1
+        gemm += 2 * D * D * (3 * N + 4 * N + 3 * T + 2 * N + (0 if last else T))
+        attn += 4 * (2 * N + T) ** 2 * D
+        if i < dual:
+            gemm += 2 * D * D * (3 * N + 4 * N + 2 * N)
+            attn += 4 * (2 * N) ** 2 * D
+        gemm += 4 * (2 * N) * D * F + (0 if last else 4 * T * D * F)
+    return gemm, attn
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return dict(tf_burst=d["bf16_tflops"], tf_sustained=d.get("bf16_tflops_sustained", d["bf16_tflops"]),
+                    hbm=d["hbm_gbs"], source="MEASURED_PEAKS.json (measured)")
+    return dict(tf_burst=1590.0, tf_sustained=1400.0, hbm=6650.0, source="B200_PROFILING.md fallback")
+
+
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                       "-lms", "100", "-i", str(gpu_index)], stdout=self.f, stderr=subprocess.DEVNULL)
+        except OSError:
+            self.p = None
+
+    def stop(self):
+        out = dict(sm_mhz=None, sm_max_mhz=None, reasons=[])
+        if self.p is None:
+            return out
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.p.kill()
+        self.f.flush()
+        rows = [l.strip().split(", ") for l in open(self.f.name) if l.strip()]
+        os.unlink(self.f.name)
+        sm, reasons, mx = [], set(), None
+        for r in rows:
+            try:
+                sm.append(float(r[1]))
+                mx = float(r[2])
+            except (ValueError, IndexError):
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[4:8]):
+                if v.strip().lower().startswith("active"):
+                    reasons.add(name)
+        if sm:
+            sm.sort()
+            hi = [s for s in sm if s >= 0.5 * sm[-1]]   # samples under load
+            out.update(sm_mhz=hi[len(hi) // 2], sm_max_mhz=mx, samples=len(sm))
+        out["reasons"] = sorted(reasons)
+        return out
+
+
+def build_model_gpu(device, seed=0):
+    """SD3.5-medium-shaped model with EVERY parameter random (SURVEY 8d scales), created directly on the GPU."""
+    import torch
+    import dit4sr_b200
+    from oracle.dit4sr_oracle import sd35_medium_config
+    cfg = sd35_medium_config()
+    with torch.device(device):
+        m = dit4sr_b200.SD3Transformer2DModel(**vars(cfg))
+    g = torch.Generator(device=device).manual_seed(seed)
+    with torch.no_grad():
+        for name, p in m.named_parameters():
+            if ".norm_" in name and p.dim() == 1 and p.numel() == 64:
+                p.copy_(1.0 + 0.1 * torch.randn(p.shape, device=device, generator=g))
+            elif "control_conv.weight" in name:
+                p.copy_(0.1 * torch.randn(p.shape, device=device, generator=g))
+            else:
+                p.copy_(0.02 * torch.randn(p.shape, device=device, generator=g))
+    return m.to(torch.bfloat16).requires_grad_(False).eval(), cfg
+
+
+def run_ours(args):
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    from dit4sr_b200 import ops
+    from dit4sr_b200.sampler import flow_match_sigmas
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    side, B, T, desc = WORKLOADS[args.workload]
+    N = (side // 2) ** 2
+    bf = torch.bfloat16
+
+    model, cfg = build_model_gpu(dev, seed=0)
+    eng = model.engine()
+    g = torch.Generator(device=dev).manual_seed(1 + rank)
+    x = torch.randn(B, 16, side, side, device=dev, generator=g)
+    ctrl = torch.randn(B, 16, side, side, device=dev, generator=g).to(bf)
+    enc = (0.5 * torch.randn(B, T, 4096, device=dev, generator=g)).to(bf)
+    pooled = torch.randn(B, 2048, device=dev, generator=g).to(bf)
+    sig = flow_match_sigmas(40)
+    t = torch.empty(B, device=dev, dtype=torch.float32)
+    nxt = torch.empty_like(x)
+
+    def step(i, xin, xout):
+        k = i % 40
+        t.fill_(float(sig[k]) * 1000.0)
+        eng.forward(xin, ctrl, enc, pooled, t, out=xout, euler=(xin, float(sig[k + 1]) - float(sig[k])))
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- device-resident timing (`value`)
+    cur, oth = x, nxt
+    for i in range(args.warmup):
+        step(i, cur, oth)
+        cur, oth = oth, cur
+    barrier()
+    sampler = ClockSampler(local) if rank == 0 else None
+    l0 = ops.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    eng.profile_kernel("ff1")   # CUDA events around the dominant kernel's launches inside the timed region
+    e0.record()
+    for i in range(args.steps):
+        step(i, cur, oth)
+        cur, oth = oth, cur
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1)
+    launches = ops.launch_count() - l0
+    ff1_ms = eng.profile_result()
+    clocks = sampler.stop() if sampler else None
+    if world > 1:
+        tt = torch.tensor([ms], device=dev)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        ms = tt.item()
+
+    # ---- end-to-end through the public module API with host buffers (`e2e`)
+    hx = torch.randn(B, 16, side, side).to(bf).pin_memory()
+    hc, he, hp = ctrl.cpu().pin_memory(), enc.cpu().pin_memory(), pooled.cpu().pin_memory()
+    ht = torch.full((B,), 741.44).pin_memory()
+    hout = torch.empty(B, 16, side, side, dtype=bf).pin_memory()
+
+    def e2e_step():
+        with torch.no_grad():
+            v = model(hidden_states=hx.to(dev, non_blocking=True), controlnet_image=hc.to(dev, non_blocking=True),
+                      encoder_hidden_states=he.to(dev, non_blocking=True),
+                      pooled_projections=hp.to(dev, non_blocking=True), timestep=ht.to(dev, non_blocking=True),
+                      return_dict=False)[0]
+        hout.copy_(v, non_blocking=True)
+
+    for _ in range(max(1, args.warmup)):
+        e2e_step()
+    barrier()
+    f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    f0.record()
+    for _ in range(args.steps):
+        e2e_step()
+    f1.record()
+    barrier()
+    e2e_ms = f0.elapsed_time(f1)
+    if world > 1:
+        tt = torch.tensor([e2e_ms], device=dev)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        e2e_ms = tt.item()
+    h2d = sum(a.numel() * a.element_size() for a in (hx, hc, he, hp, ht))
+    d2h = hout.numel() * hout.element_size()
+
+    # ---- per-kernel-class breakdown of one extra, instrumented step (not part of any timed number)
+    breakdown = None
+    if rank == 0 and not args.no_breakdown:
+        eng.profile_kernel("*")
+        step(0, cur, oth)
+        torch.cuda.synchronize()
+        breakdown = eng.profile_result()
+
+    # ---- CPU baseline on rank 0 (bounded sample)
+    cpu = None
+    if rank == 0 and not args.no_cpu:
+        cpu = cpu_reference_sample(max_seconds=25.0)
+
+    if rank == 0:
+        peaks = measured_peaks()
+        gemm_f, attn_f = flops_per_image_step(N, T)
+        step_flops = (gemm_f + attn_f) * B
+        img_steps = B * world * args.steps
+        value = img_steps / (ms / 1e3)
+        ff1_flops = 2.0 * (B * 2 * N) * 1536 * 6144
+        ff1_avg_ms = (sum(ff1_ms["ff1"]) / len(ff1_ms["ff1"])) if ff1_ms and ff1_ms.get("ff1") else None
+        roof = None
+        if ff1_avg_ms:
+            ach = ff1_flops / (ff1_avg_ms / 1e3) / 1e12
+            roof = dict(bound="tensor", kernel="gemm_kernel<BIAS_GELU> (FF1: [B*2N,1536]x[1536,6144])", achieved=round(ach, 1),
+                        peak=peaks["tf_sustained"], unit="TFLOP/s", frac=round(ach / peaks["tf_sustained"], 4),
+                        peak_source=peaks["source"] + ", sustained figure (kernel timed inside a long step)",
+                        frac_of_burst=round(ach / peaks["tf_burst"], 4), frac_of_spec_2250=round(ach / 2250.0, 4),
+                        launch_ms=round(ff1_avg_ms, 4), flops_per_launch=ff1_flops, launches_timed=len(ff1_ms["ff1"]),
+                        traffic=None)
+        line = dict(
+            metric="denoise_steps_per_sec", value=round(value, 3), unit="image-steps/s (one image advanced one denoise step)",
+            n_gpus=world, steps=args.steps, warmup=args.warmup, ms_per_step=round(ms / args.steps, 3),
+            higher_is_better=True, scaling="weak", vs_baseline=None, dtype="bf16", data="synthetic",
+            config=dict(workload=desc, per_gpu_batch=B, global_batch=B * world, latent=f"{side}x{side}", tokens_hq=N,
+                        tokens_lr=N, tokens_text=T, parallelism=f"dp{world}",
+                        l2="working set (5.4 GB bf16 weights + activations) >> 126 MB L2; no explicit flush"),
+            batch_steps_per_sec=round(args.steps * world / (ms / 1e3), 3),
+            step_tflop=round(step_flops / 1e12, 3),
+            step_tflops_achieved=round(step_flops * world / (ms / args.steps / 1e3) / 1e12, 1),
+            step_frac_of_sustained_peak=round(step_flops / (ms / args.steps / 1e3) / 1e12 / peaks["tf_sustained"], 4),
+            e2e=dict(value=round(img_steps / (e2e_ms / 1e3), 3), unit="image-steps/s", h2d_bytes_per_step=h2d,
+                     d2h_bytes_per_step=d2h, ms_per_step=round(e2e_ms / args.steps, 3),
+                     api="dit4sr_b200.SD3Transformer2DModel.forward, pinned host inputs, velocity copied back"),
+            gpu_launches=launches, clocks=clocks, roofline=roof, cpu_baseline=cpu, kernel_breakdown_ms=breakdown,
+        )
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def cpu_reference_sample(max_seconds=25.0, steps=1, warmup=1):
+    """Times the oracle (plain-PyTorch fp32 restatement of the reference) on the host cores: B=1, 512px, 24 blocks."""
+    import torch
+    from oracle import dit4sr_oracle as O
+    ncpu = os.cpu_count() or 1
+    torch.set_num_threads(ncpu)
+    cfg = O.sd35_medium_config(pos_embed_max_size=96)   # the cropped 32x32 window is what the step reads
+    man = O.state_dict_manifest(cfg)
+    sd = {}
+    for k, shp in man.items():
+        sd[k] = torch.empty(shp).normal_(0, 0.02)
+    for k in sd:
+        if ".norm_" in k and sd[k].dim() == 1 and sd[k].numel() == 64:
+            sd[k] = 1 + 0.1 * torch.randn(64)
+    inp = O.make_inputs(cfg, 1, 64, 64, 333, seed=1, timestep=741.44)
+    times = []
+    t_begin = time.perf_counter()
+    with torch.no_grad():
+        for i in range(warmup + steps):
+            t0 = time.perf_counter()
+            O.model_forward(sd, cfg, *inp, as_written=True)
+            dt = time.perf_counter() - t0
+            if i >= warmup:
+                times.append(dt)
+            if time.perf_counter() - t_begin > max_seconds and times:
+                break
+    if not times:
+        times = [dt]
+    sec = sum(times) / len(times)
+    return dict(value=round(1.0 / sec, 4), unit="image-steps/s", cores=torch.get_num_threads(), kind="port",
+                sample=f"oracle (plain PyTorch fp32 restatement of the reference), B=1 512px 24 blocks, "
+                       f"{len(times)} timed step(s) after {warmup} warm-up, {sec:.2f} s/step, host cpu_count={ncpu}")
+
+
+def run_reference(args):
+    """Reference arm: the reference's algorithm on the host CPU (oracle port; diffusers is not installable offline so
+    the reference module itself cannot run), all host threads, same metric/unit/config, bounded sample per step."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import torch
+    from oracle import dit4sr_oracle as O
+    ncpu = os.cpu_count() or 1
+    torch.set_num_threads(ncpu)
+    side, B, T, desc = WORKLOADS[args.workload]
+    cfg = O.sd35_medium_config(pos_embed_max_size=max(96, side // 2))
+    sd = {k: torch.empty(shp).normal_(0, 0.02) for k, shp in O.state_dict_manifest(cfg).items()}
+    inp = O.make_inputs(cfg, 1, side, side, T, seed=1, timestep=741.44)
+    budget = float(os.environ.get("DIT4SR_REF_BUDGET_S", "240"))
+    t_begin = time.perf_counter()
+    times = []
+    done_w = 0
+    with torch.no_grad():
+        for i in range(args.warmup + args.steps):
+            t0 = time.perf_counter()
+            O.model_forward(sd, cfg, *inp, as_written=True)
+            dt = time.perf_counter() - t0
+            if i < args.warmup and time.perf_counter() - t_begin < budget / 3:
+                done_w += 1
+                continue
+            times.append(dt)
+            if time.perf_counter() - t_begin > budget:
+                break
+    sec = sum(times) / len(times)
+    val = round(1.0 / sec, 4)
+    unit = "image-steps/s (one image advanced one denoise step)"
+    print(json.dumps(dict(
+        impl="reference", metric="denoise_steps_per_sec", value=val, unit=unit, n_gpus=int(os.environ.get("WORLD_SIZE", "1")),
+        steps=len(times), warmup=done_w, ms_per_step=round(sec * 1e3, 1), higher_is_better=True, scaling="weak",
+        vs_baseline=None, dtype="f32", data="synthetic",
+        config=dict(workload=desc, sample="each step = ONE image of the batch (B=1) through all 24 blocks on the CPU"),
+        cpu_baseline=dict(value=val, unit=unit, cores=torch.get_num_threads(), kind="port",
+                          sample=f"oracle port, B=1 {side * 8}px, {len(times)} timed steps, wall budget {budget:.0f}s"),
+        e2e=dict(value=val, unit=unit, h2d_bytes_per_step=0, d2h_bytes_per_step=0))))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-breakdown", action="store_true", help="skip the per-kernel breakdown step")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -110,7 +110,33 @@ class Engine:
         self.ctx_embed = _Lin(model.context_embedder)
         self.proj_out = _Lin(model.proj_out)
         self._ws: Dict[Tuple, dict] = {}
+        self._prof = None
         self._pos: Dict[Tuple, torch.Tensor] = {}
+
+    # ------------------------------------------------------------------------------------------------ profiling
+    def profile_kernel(self, pattern: str):
+        """Record CUDA events around every launch of kernel class `pattern` ('*' = all) until profile_result()."""
+        self._prof = (pattern, {})
+
+    def profile_result(self):
+        """{kernel class: [ms per launch]} for the launches recorded since profile_kernel(); stops recording."""
+        if self._prof is None:
+            return None
+        torch.cuda.synchronize()
+        res = {k: [a.elapsed_time(b) for a, b in v] for k, v in self._prof[1].items()}
+        self._prof = None
+        return res
+
+    def _run(self, name, fn, *args, **kwargs):
+        p = self._prof
+        if p is not None and (p[0] == "*" or p[0] == name):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            fn(*args, **kwargs)
+            e1.record()
+            p[1].setdefault(name, []).append((e0, e1))
+        else:
+            fn(*args, **kwargs)
 
     # ------------------------------------------------------------------------------------------------ workspace
     def _pos_crop(self, hp, wp, device):
@@ -153,42 +179,43 @@ class Engine:
     # ------------------------------------------------------------------------------------------------ attention
     def _attention(self, ap: _AttnPack, ws, n_in, nc, N, T, gate, c_gate, last):
         """JointAttnProcessor2_0 (attention.py:445-559) + the gated residual adds (attention.py:314-320,381-382)."""
-        D, H = self.D, self.H
+        D, H, R = self.D, self.H, self._run
         x, ctx, qkv, o, lrtmp = ws["x"], ws["ctx"], ws["qkv"], ws["o"], ws["lrtmp"]
         S = 2 * N + (T if ap.has_text else 0)
         hq, lr = n_in[:, :N], n_in[:, N:]
         if ap.qk_norm:
-            ops.gemm(hq, ap.qkv.w, ap.qkv.b, qkv[:, :N], ops.EPI_QKV_NORM, norm_w0=ap.wq, norm_w1=ap.wk, sec_cols=D,
-                     dbl_row_offset=N)
+            R("qkv_gemm", ops.gemm, hq, ap.qkv.w, ap.qkv.b, qkv[:, :N], ops.EPI_QKV_NORM, norm_w0=ap.wq, norm_w1=ap.wk,
+              sec_cols=D, dbl_row_offset=N)
             t2 = lrtmp[:, :, :2 * D]
-            ops.gemm(lr, ap.lr1.w, ap.lr1.b, t2, ops.EPI_BIAS)
-            ops.gemm(t2[:, :, :D], ap.qc.w, ap.qc.b, qkv[:, N:2 * N, :D], ops.EPI_QKV_NORM, norm_w0=ap.wq, sec_cols=D)
-            ops.gemm(t2[:, :, D:], ap.vc.w, ap.vc.b, qkv[:, N:2 * N, 2 * D:], ops.EPI_BIAS)
+            R("lr_gemm", ops.gemm, lr, ap.lr1.w, ap.lr1.b, t2, ops.EPI_BIAS)
+            R("lr_gemm", ops.gemm, t2[:, :, :D], ap.qc.w, ap.qc.b, qkv[:, N:2 * N, :D], ops.EPI_QKV_NORM, norm_w0=ap.wq,
+              sec_cols=D)
+            R("lr_gemm", ops.gemm, t2[:, :, D:], ap.vc.w, ap.vc.b, qkv[:, N:2 * N, 2 * D:], ops.EPI_BIAS)
             if ap.has_text:
-                ops.gemm(nc, ap.add.w, ap.add.b, qkv[:, 2 * N:S], ops.EPI_QKV_NORM, norm_w0=ap.waq, norm_w1=ap.wak,
-                         sec_cols=D)
+                R("txt_gemm", ops.gemm, nc, ap.add.w, ap.add.b, qkv[:, 2 * N:S], ops.EPI_QKV_NORM, norm_w0=ap.waq,
+                  norm_w1=ap.wak, sec_cols=D)
         else:
-            ops.gemm(hq, ap.qkv.w, ap.qkv.b, qkv[:, :N], ops.EPI_BIAS)
-            ops.gemm(lr, ap.qkv.w, ap.qkv.b, lrtmp, ops.EPI_BIAS)
-            ops.gemm(lrtmp[:, :, :D], ap.qc.w, ap.qc.b, qkv[:, N:2 * N, :D], ops.EPI_BIAS)
-            ops.gemm(lrtmp[:, :, D:2 * D], ap.kc.w, ap.kc.b, qkv[:, N:2 * N, D:2 * D], ops.EPI_BIAS)
-            ops.gemm(lrtmp[:, :, 2 * D:], ap.vc.w, ap.vc.b, qkv[:, N:2 * N, 2 * D:], ops.EPI_BIAS)
+            R("qkv_gemm", ops.gemm, hq, ap.qkv.w, ap.qkv.b, qkv[:, :N], ops.EPI_BIAS)
+            R("lr_gemm", ops.gemm, lr, ap.qkv.w, ap.qkv.b, lrtmp, ops.EPI_BIAS)
+            R("lr_gemm", ops.gemm, lrtmp[:, :, :D], ap.qc.w, ap.qc.b, qkv[:, N:2 * N, :D], ops.EPI_BIAS)
+            R("lr_gemm", ops.gemm, lrtmp[:, :, D:2 * D], ap.kc.w, ap.kc.b, qkv[:, N:2 * N, D:2 * D], ops.EPI_BIAS)
+            R("lr_gemm", ops.gemm, lrtmp[:, :, 2 * D:], ap.vc.w, ap.vc.b, qkv[:, N:2 * N, 2 * D:], ops.EPI_BIAS)
             if ap.has_text:
-                ops.gemm(nc, ap.add.w, ap.add.b, qkv[:, 2 * N:S], ops.EPI_BIAS)
+                R("txt_gemm", ops.gemm, nc, ap.add.w, ap.add.b, qkv[:, 2 * N:S], ops.EPI_BIAS)
         # the last block's text queries are discarded by the reference (context_pre_only): do not compute them
         seq_q = 2 * N if (last or not ap.has_text) else S
-        ops.attention(qkv[:, :S, :D], qkv[:, :S, D:2 * D], qkv[:, :S, 2 * D:], o, H, seq_q=seq_q,
-                      lr_res=n_in, lr_rows=(N, 2 * N))
-        ops.gemm(o[:, :N], ap.out.w, ap.out.b, x[:, :N], ops.EPI_GATE_RESID, gate=gate)
-        ops.gemm(o[:, N:2 * N], ap.outc.w, ap.outc.b, x[:, N:], ops.EPI_GATE_RESID, gate=gate)
+        R("attn", ops.attention, qkv[:, :S, :D], qkv[:, :S, D:2 * D], qkv[:, :S, 2 * D:], o, H, seq_q=seq_q,
+          lr_res=n_in, lr_rows=(N, 2 * N))
+        R("out_gemm", ops.gemm, o[:, :N], ap.out.w, ap.out.b, x[:, :N], ops.EPI_GATE_RESID, gate=gate)
+        R("out_gemm", ops.gemm, o[:, N:2 * N], ap.outc.w, ap.outc.b, x[:, N:], ops.EPI_GATE_RESID, gate=gate)
         if ap.has_text and not last:
-            ops.gemm(o[:, 2 * N:S], ap.add_out.w, ap.add_out.b, ctx, ops.EPI_GATE_RESID, gate=c_gate)
+            R("txt_gemm", ops.gemm, o[:, 2 * N:S], ap.add_out.w, ap.add_out.b, ctx, ops.EPI_GATE_RESID, gate=c_gate)
 
     # ------------------------------------------------------------------------------------------------ forward
     @torch.no_grad()
     def forward(self, hidden_states, controlnet_image, encoder_hidden_states, pooled_projections, timestep,
                 out=None, euler: Optional[Tuple[torch.Tensor, float]] = None, feat_hook=None):
-        cfg, D = self.cfg, self.D
+        cfg, D, R = self.cfg, self.D, self._run
         B, Cin, h, w = hidden_states.shape
         if h != w or h % 2:
             raise ValueError("dit4sr_b200: square, even latents only (reference asserts a square token grid, "
@@ -203,20 +230,20 @@ class Engine:
 
         # ---- head: temb = MLP(sincos(t)) + MLP(pooled)  (CombinedTimestepTextProjEmbeddings, transformer_sd3.py:327)
         ws["t"].copy_(timestep.to(device=dev, dtype=torch.float32).expand(B))
-        ops.timestep_features(ws["t"], ws["tf"])
-        ops.gemm(ws["tf"], self.t1.w, self.t1.b, ws["th"], ops.EPI_BIAS_SILU)
-        ops.gemm(ws["th"], self.t2.w, self.t2.b, ws["temb"], ops.EPI_BIAS)
+        R("head", ops.timestep_features, ws["t"], ws["tf"])
+        R("head", ops.gemm, ws["tf"], self.t1.w, self.t1.b, ws["th"], ops.EPI_BIAS_SILU)
+        R("head", ops.gemm, ws["th"], self.t2.w, self.t2.b, ws["temb"], ops.EPI_BIAS)
         ws["pooled"].copy_(pooled_projections)
-        ops.gemm(ws["pooled"], self.p1.w, self.p1.b, ws["ph"], ops.EPI_BIAS_SILU)
-        ops.gemm(ws["ph"], self.p2.w, self.p2.b, ws["temb"], ops.EPI_GATE_RESID)
-        ops.silu_cast(ws["temb"], ws["st"])
-        ops.gemm(ws["st"], self.mod.w, self.mod.b, mod, ops.EPI_BIAS)          # all adaLN vectors of the step
+        R("head", ops.gemm, ws["pooled"], self.p1.w, self.p1.b, ws["ph"], ops.EPI_BIAS_SILU)
+        R("head", ops.gemm, ws["ph"], self.p2.w, self.p2.b, ws["temb"], ops.EPI_GATE_RESID)
+        R("head", ops.silu_cast, ws["temb"], ws["st"])
+        R("mod_gemm", ops.gemm, ws["st"], self.mod.w, self.mod.b, mod, ops.EPI_BIAS)   # all adaLN vectors of the step
         # ---- patch embed (+pos) for both streams, context embedder  (:326-332)
         for src, rows in ((hidden_states, x[:, :N]), (controlnet_image, x[:, N:])):
-            ops.patchify(src.contiguous(), ws["patches"])
-            ops.gemm(ws["patches"], self.patch_w, self.patch_b, rows, ops.EPI_GATE_RESID, resid=pos)
+            R("head", ops.patchify, src.contiguous(), ws["patches"])
+            R("head", ops.gemm, ws["patches"], self.patch_w, self.patch_b, rows, ops.EPI_GATE_RESID, resid=pos)
         ws["enc"].copy_(encoder_hidden_states)
-        ops.gemm(ws["enc"], self.ctx_embed.w, self.ctx_embed.b, ctx, ops.EPI_BIAS)
+        R("head", ops.gemm, ws["enc"], self.ctx_embed.w, self.ctx_embed.b, ctx, ops.EPI_BIAS)
 
         # ---- blocks (:336-370)
         for i, bp in enumerate(self.blocks):
@@ -229,41 +256,41 @@ class Engine:
             shift_mlp, scale_mlp, gate_mlp = ch(o1, 3), ch(o1, 4), ch(o1, 5)
             if bp.dual:
                 shift_msa2, scale_msa2, gate_msa2 = ch(o1, 6), ch(o1, 7), ch(o1, 8)
-                ops.ln_modulate(x, shift_msa, scale_msa, n1, shift_msa2, scale_msa2, n2)
+                R("ln_mod", ops.ln_modulate, x, shift_msa, scale_msa, n1, shift_msa2, scale_msa2, n2)
             else:
-                ops.ln_modulate(x, shift_msa, scale_msa, n1)
+                R("ln_mod", ops.ln_modulate, x, shift_msa, scale_msa, n1)
             if bp.last:   # AdaLayerNormContinuous: (scale, shift) order (Q12)
                 c_scale, c_shift = ch(o2, 0), ch(o2, 1)
-                ops.ln_modulate(ctx, c_shift, c_scale, nc)
+                R("ln_mod", ops.ln_modulate, ctx, c_shift, c_scale, nc)
                 c_gate_msa = None
             else:
                 c_shift_msa, c_scale_msa, c_gate_msa = ch(o2, 0), ch(o2, 1), ch(o2, 2)
                 c_shift_mlp, c_scale_mlp, c_gate_mlp = ch(o2, 3), ch(o2, 4), ch(o2, 5)
-                ops.ln_modulate(ctx, c_shift_msa, c_scale_msa, nc)
+                R("ln_mod", ops.ln_modulate, ctx, c_shift_msa, c_scale_msa, nc)
             self._attention(bp.attn, ws, n1, nc, N, T, gate_msa, c_gate_msa, bp.last)
             if bp.dual:
                 self._attention(bp.attn2, ws, n2, None, N, T, gate_msa2, None, bp.last)
             # MLP with the LR->HQ depthwise conv (attention.py:322-347, FeedForwardControl :155-178)
-            ops.ln_modulate(x, shift_mlp, scale_mlp, n1)
-            ops.gemm(n1, bp.ff1.w, bp.ff1.b, ws["u"], ops.EPI_BIAS_GELU)
-            ops.dwconv3x3_add(ws["u"][:, :N], ws["u"][:, N:], bp.conv_w9, bp.conv_b, grid)
-            ops.gemm(ws["u"], bp.ff2.w, bp.ff2.b, x, ops.EPI_GATE_RESID, gate=gate_mlp)
+            R("ln_mod", ops.ln_modulate, x, shift_mlp, scale_mlp, n1)
+            R("ff1", ops.gemm, n1, bp.ff1.w, bp.ff1.b, ws["u"], ops.EPI_BIAS_GELU)
+            R("dwconv", ops.dwconv3x3_add, ws["u"][:, :N], ws["u"][:, N:], bp.conv_w9, bp.conv_b, grid)
+            R("ff2", ops.gemm, ws["u"], bp.ff2.w, bp.ff2.b, x, ops.EPI_GATE_RESID, gate=gate_mlp)
             if not bp.last:   # text MLP (attention.py:384-393)
-                ops.ln_modulate(ctx, c_shift_mlp, c_scale_mlp, nc)
-                ops.gemm(nc, bp.ffc1.w, bp.ffc1.b, ws["uc"], ops.EPI_BIAS_GELU)
-                ops.gemm(ws["uc"], bp.ffc2.w, bp.ffc2.b, ctx, ops.EPI_GATE_RESID, gate=c_gate_mlp)
+                R("ln_mod", ops.ln_modulate, ctx, c_shift_mlp, c_scale_mlp, nc)
+                R("txt_gemm", ops.gemm, nc, bp.ffc1.w, bp.ffc1.b, ws["uc"], ops.EPI_BIAS_GELU)
+                R("txt_gemm", ops.gemm, ws["uc"], bp.ffc2.w, bp.ffc2.b, ctx, ops.EPI_GATE_RESID, gate=c_gate_mlp)
             if feat_hook is not None:
                 feat_hook(i, x)
 
         # ---- tail: drop the LR half, norm_out (scale, shift order), proj_out, unpatchify (:379-391)
         so = self.mod_out_off
-        ops.ln_modulate(x[:, :N], mod[:, so + D: so + 2 * D], mod[:, so: so + D], n1[:, :N])
-        ops.gemm(n1[:, :N], self.proj_out.w, self.proj_out.b, ws["tok"], ops.EPI_BIAS)
+        R("tail", ops.ln_modulate, x[:, :N], mod[:, so + D: so + 2 * D], mod[:, so: so + D], n1[:, :N])
+        R("tail", ops.gemm, n1[:, :N], self.proj_out.w, self.proj_out.b, ws["tok"], ops.EPI_BIAS)
         if out is None:
             out = torch.empty(B, cfg.out_channels, h, w, device=dev, dtype=hidden_states.dtype)
         if euler is not None:
             latents, dsigma = euler
-            ops.unpatchify(ws["tok"], out, latents=latents, dsigma=dsigma)
+            R("tail", ops.unpatchify, ws["tok"], out, latents=latents, dsigma=dsigma)
         else:
-            ops.unpatchify(ws["tok"], out)
+            R("tail", ops.unpatchify, ws["tok"], out)
         return out

@@ -216,7 +216,7 @@ def rms_norm(x, weight, eps=1e-6):
 def timestep_sincos(t: torch.Tensor, dim: int = 256) -> torch.Tensor:
     """diffusers Timesteps(256, flip_sin_to_cos=True, downscale_freq_shift=0): [cos|sin], fp32."""
     half = dim // 2
-    exponent = -math.log(10000) * torch.arange(half, dtype=torch.float32) / half
+    exponent = -math.log(10000) * torch.arange(half, dtype=torch.float32, device=t.device) / half
     emb = t[:, None].float() * torch.exp(exponent)[None, :]
     return torch.cat([torch.cos(emb), torch.sin(emb)], dim=-1)
 
