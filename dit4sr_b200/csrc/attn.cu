@@ -9,6 +9,7 @@
 // (A operand from TMEM, V consumed MN-major straight from the TMA tile), with S_{j+1} issued before PV_j.
 #include "host_util.h"
 #include "ptx.cuh"
+#include <stdlib.h>
 
 namespace attn {
 
@@ -272,6 +273,276 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   }
 }
 
+
+// =====================================================================================================================
+// v2: one CTA = TWO 128-row query tiles of one (batch, head) sharing every K/V tile (halves the L2->smem traffic), one
+// CTA per SM (all 512 TMEM columns).  Warps (384 threads): 0 = TMA producer, 1 = MMA issuer, 2 = TMEM allocator,
+// 4..7 = softmax warpgroup of tile 0, 8..11 = softmax warpgroup of tile 1.  Each softmax thread owns one query row, pulls
+// its whole 128-wide score row into registers with one TMEM round trip, releases S immediately (so the next Q K^T is
+// issued while the exponentials run), rescales O lazily (only when the running max grew by more than 2^8).
+// TMEM: S0 [0,128) S1 [128,256) | O0 [256,320) O1 [320,384) | P0 [384,448) P1 [448,512).
+namespace v2 {
+
+constexpr int KV_STAGES = 4;
+constexpr int NUM_THREADS = 384;
+constexpr int TMEM_COLS = 512;
+constexpr int SMEM_BYTES = (2 + 2 * KV_STAGES) * TILE_BYTES + 1024 + 256;
+constexpr float RESCALE_THRESHOLD = 8.0f;   // in log2 units: skip the O rescale while p stays <= 2^8
+
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+attn_fwd2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
+                 const __grid_constant__ CUtensorMap tmV, const Args args) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sQ = smem;                                   // 2 tiles
+  uint8_t* sK = smem + 2 * TILE_BYTES;                  // KV_STAGES tiles
+  uint8_t* sV = smem + (2 + KV_STAGES) * TILE_BYTES;    // KV_STAGES tiles
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (2 + 2 * KV_STAGES) * TILE_BYTES);
+  uint64_t* q_full = bars;
+  uint64_t* k_full = bars + 1;
+  uint64_t* k_empty = k_full + KV_STAGES;
+  uint64_t* v_full = k_empty + KV_STAGES;
+  uint64_t* v_empty = v_full + KV_STAGES;
+  uint64_t* s_full = v_empty + KV_STAGES;   // [2]
+  uint64_t* s_free = s_full + 2;            // [2]
+  uint64_t* p_full = s_free + 2;            // [2]
+  uint64_t* o_done = p_full + 2;            // [2]
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(o_done + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int q_pair = blockIdx.x;
+  const int head = blockIdx.y;
+  const int b = blockIdx.z;
+  const int n_tiles = args.n_kv_tiles;
+
+  if (warp == 0 && lane == 0) {
+    ptx::prefetch_tmap(&tmQ);
+    ptx::prefetch_tmap(&tmK);
+    ptx::prefetch_tmap(&tmV);
+    ptx::mbar_init(q_full, 1);
+    for (int i = 0; i < KV_STAGES; ++i) {
+      ptx::mbar_init(&k_full[i], 1);
+      ptx::mbar_init(&k_empty[i], 1);
+      ptx::mbar_init(&v_full[i], 1);
+      ptx::mbar_init(&v_empty[i], 1);
+    }
+    for (int t = 0; t < 2; ++t) {
+      ptx::mbar_init(&s_full[t], 1);
+      ptx::mbar_init(&s_free[t], 4);
+      ptx::mbar_init(&p_full[t], 4);
+      ptx::mbar_init(&o_done[t], 1);
+    }
+    ptx::fence_barrier_init();
+  }
+  if (warp == 2) {
+    ptx::tmem_alloc(tmem_ptr, TMEM_COLS);
+    ptx::tmem_relinquish();
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      // ===================== TMA producer =====================
+      ptx::mbar_expect_tx(q_full, 2 * TILE_BYTES);
+      ptx::tma_load_3d(sQ, &tmQ, q_full, head * DH, q_pair * 2 * BQ, b);
+      ptx::tma_load_3d(sQ + TILE_BYTES, &tmQ, q_full, head * DH, q_pair * 2 * BQ + BQ, b);
+      for (int j = 0; j < n_tiles; ++j) {
+        const int st = j % KV_STAGES;
+        const uint32_t ph = (j / KV_STAGES) & 1;
+        ptx::mbar_wait(&k_empty[st], ph ^ 1);
+        ptx::mbar_expect_tx(&k_full[st], TILE_BYTES);
+        ptx::tma_load_3d(sK + st * TILE_BYTES, &tmK, &k_full[st], head * DH, j * BKV, b);
+        ptx::mbar_wait(&v_empty[st], ph ^ 1);
+        ptx::mbar_expect_tx(&v_full[st], TILE_BYTES);
+        ptx::tma_load_3d(sV + st * TILE_BYTES, &tmV, &v_full[st], head * DH, j * BKV, b);
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      // ===================== MMA issuer =====================
+      constexpr uint32_t idesc_qk = ptx::make_idesc_bf16(BQ, BKV, 0, 0);
+      constexpr uint32_t idesc_pv = ptx::make_idesc_bf16(BQ, DH, 0, 1);
+      const uint64_t qdesc0 = ptx::make_sdesc_sw128(ptx::smem_u32(sQ));
+      const uint64_t qdesc1 = ptx::make_sdesc_sw128(ptx::smem_u32(sQ + TILE_BYTES));
+
+      auto issue_qk = [&](int t, int st) {   // S_t = Q_t K^T
+        const uint64_t kdesc = ptx::make_sdesc_sw128(ptx::smem_u32(sK + st * TILE_BYTES));
+        const uint64_t qd = t ? qdesc1 : qdesc0;
+#pragma unroll
+        for (int k = 0; k < DH / 16; ++k) ptx::mma_ss(tmem_base + t * 128, qd + 2 * k, kdesc + 2 * k, idesc_qk, k != 0);
+        ptx::tc_commit(&s_full[t]);
+      };
+      auto issue_pv = [&](int t, int st, int j) {   // O_t += P_t V
+        const uint64_t vdesc = ptx::make_sdesc_sw128(ptx::smem_u32(sV + st * TILE_BYTES));
+#pragma unroll
+        for (int k = 0; k < BKV / 16; ++k)
+          ptx::mma_ts(tmem_base + 256 + t * 64, tmem_base + 384 + t * 64 + 8 * k, vdesc + (uint64_t)(128 * k), idesc_pv,
+                      (j | k) != 0);
+        ptx::tc_commit(&o_done[t]);
+      };
+
+      ptx::mbar_wait(q_full, 0);
+      ptx::mbar_wait(&k_full[0], 0);
+      ptx::tc_fence_after();
+      issue_qk(0, 0);
+      issue_qk(1, 0);
+      ptx::tc_commit(&k_empty[0]);
+      for (int j = 0; j < n_tiles; ++j) {
+        const int st = j % KV_STAGES;
+        if (j + 1 < n_tiles) {
+          const int st1 = (j + 1) % KV_STAGES;
+          ptx::mbar_wait(&k_full[st1], ((j + 1) / KV_STAGES) & 1);
+          ptx::mbar_wait(&s_free[0], j & 1);      // softmax 0 has S0(j) in registers
+          ptx::tc_fence_after();
+          issue_qk(0, st1);
+          ptx::mbar_wait(&s_free[1], j & 1);
+          ptx::tc_fence_after();
+          issue_qk(1, st1);
+          ptx::tc_commit(&k_empty[st1]);
+        }
+        ptx::mbar_wait(&v_full[st], (j / KV_STAGES) & 1);
+        ptx::mbar_wait(&p_full[0], j & 1);
+        ptx::tc_fence_after();
+        issue_pv(0, st, j);
+        ptx::mbar_wait(&p_full[1], j & 1);
+        ptx::tc_fence_after();
+        issue_pv(1, st, j);
+        ptx::tc_commit(&v_empty[st]);
+      }
+    }
+  } else if (warp >= 4) {
+    // ===================== softmax warpgroups =====================
+    const int t = (warp - 4) >> 2;   // query tile of this warpgroup
+    const int q = warp & 3;          // TMEM lane quarter
+    const uint32_t lane_off = (uint32_t)(q * 32) << 16;
+    const uint32_t tS = tmem_base + t * 128 + lane_off;
+    const uint32_t tO = tmem_base + 256 + t * 64 + lane_off;
+    const uint32_t tP = tmem_base + 384 + t * 64 + lane_off;
+    const float sl2 = args.scale_log2;
+    float m_run = -INFINITY;   // the max the running sums are scaled with (raw score units)
+    float l_run = 0.f;
+    for (int j = 0; j < n_tiles; ++j) {
+      ptx::mbar_wait(&s_full[t], j & 1);
+      ptx::tc_fence_after();
+      uint32_t v[128];
+#pragma unroll
+      for (int c = 0; c < 4; ++c) ptx::tmem_ld32(tS + c * 32, *reinterpret_cast<uint32_t(*)[32]>(&v[c * 32]));
+      ptx::tmem_wait_ld();
+      ptx::tc_fence_before();
+      __syncwarp();
+      if (lane == 0) ptx::mbar_arrive(&s_free[t]);   // S_t may be overwritten by the next Q K^T
+
+      const int kv_left = args.seq_kv - j * BKV;
+      if (kv_left < BKV) {
+#pragma unroll
+        for (int i = 0; i < 128; ++i)
+          if (i >= kv_left) v[i] = 0xff800000u;   // -inf
+      }
+      float mx = __uint_as_float(v[0]);
+#pragma unroll
+      for (int i = 1; i < 128; ++i) mx = fmaxf(mx, __uint_as_float(v[i]));
+      // lazy rescale: keep the old reference max unless the new one exceeds it by more than the threshold
+      float alpha = 1.0f;
+      const bool grow = (mx - m_run) * sl2 > RESCALE_THRESHOLD;   // true on the first tile (m_run = -inf)
+      if (grow) {
+        alpha = ptx::ex2((m_run - mx) * sl2);
+        m_run = mx;
+      }
+      const float neg_m = -m_run * sl2;
+      float rsum = 0.f;
+      uint32_t pk[64];
+#pragma unroll
+      for (int i = 0; i < 64; ++i) {
+        const float p0 = ptx::ex2(fmaf(__uint_as_float(v[2 * i]), sl2, neg_m));
+        const float p1 = ptx::ex2(fmaf(__uint_as_float(v[2 * i + 1]), sl2, neg_m));
+        rsum += p0 + p1;
+        pk[i] = ptx::pack_bf16(p0, p1);
+      }
+      // P_t and O_t are in use by PV_t(j-1) until o_done fires
+      if (j > 0) {
+        ptx::mbar_wait(&o_done[t], (j - 1) & 1);
+        ptx::tc_fence_after();
+        if (__any_sync(0xffffffffu, grow)) {
+#pragma unroll 1
+          for (int c = 0; c < DH / 32; ++c) {
+            uint32_t o[32];
+            ptx::tmem_ld32(tO + c * 32, o);
+            ptx::tmem_wait_ld();
+#pragma unroll
+            for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
+            ptx::tmem_st32(tO + c * 32, o);
+          }
+        }
+      }
+#pragma unroll
+      for (int c = 0; c < 4; ++c) ptx::tmem_st16(tP + c * 16, &pk[c * 16]);
+      l_run = l_run * alpha + rsum;
+      ptx::tmem_wait_st();
+      ptx::tc_fence_before();
+      __syncwarp();
+      if (lane == 0) ptx::mbar_arrive(&p_full[t]);
+    }
+    // epilogue: O / l (+ LR residual) -> bf16 global
+    ptx::mbar_wait(&o_done[t], (n_tiles - 1) & 1);
+    ptx::tc_fence_after();
+    const int row = (q_pair * 2 + t) * BQ + q * 32 + lane;
+    const float inv_l = 1.0f / l_run;
+    const bool row_ok = row < args.seq_q;
+    const bool add_lr = args.lr_res != nullptr && row >= args.lr_row_begin && row < args.lr_row_end;
+#pragma unroll 1
+    for (int c = 0; c < DH / 32; ++c) {
+      uint32_t o[32];
+      ptx::tmem_ld32(tO + c * 32, o);
+      ptx::tmem_wait_ld();
+      if (row_ok) {
+        float f[32];
+#pragma unroll
+        for (int i = 0; i < 32; ++i) f[i] = __uint_as_float(o[i]) * inv_l;
+        if (add_lr) {
+          const uint4* lr = reinterpret_cast<const uint4*>(args.lr_res + (int64_t)b * args.lr_batch_stride +
+                                                           (int64_t)row * args.lr_row_stride + head * DH + c * 32);
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const uint4 u = __ldg(lr + i);
+            const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&u);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              const float2 ff = __bfloat1622float2(h2[k]);
+              f[8 * i + 2 * k] += ff.x;
+              f[8 * i + 2 * k + 1] += ff.y;
+            }
+          }
+        }
+        uint4* dst = reinterpret_cast<uint4*>(args.o + (int64_t)b * args.o_batch_stride +
+                                              (int64_t)row * args.o_row_stride + head * DH + c * 32);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          uint4 u;
+          u.x = ptx::pack_bf16(f[8 * i + 0], f[8 * i + 1]);
+          u.y = ptx::pack_bf16(f[8 * i + 2], f[8 * i + 3]);
+          u.z = ptx::pack_bf16(f[8 * i + 4], f[8 * i + 5]);
+          u.w = ptx::pack_bf16(f[8 * i + 6], f[8 * i + 7]);
+          dst[i] = u;
+        }
+      }
+    }
+  }
+
+  __syncwarp();
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    ptx::tc_fence_after();
+    ptx::tmem_dealloc(tmem_base, TMEM_COLS);
+  }
+}
+
+}  // namespace v2
+
 }  // namespace attn
 
 extern "C" int dit4sr_attn_fwd(const dit4sr_attn_params* p, void* stream_) {
@@ -317,12 +588,21 @@ extern "C" int dit4sr_attn_fwd(const dit4sr_attn_params* p, void* stream_) {
   a.scale_log2 = p->scale * 1.4426950408889634f;
 
   static bool configured = false;
+  static int variant = 2;   // development switch: DIT4SR_ATTN_VARIANT=1 selects the one-tile-per-CTA kernel
   if (!configured) {
     DIT4SR_CUDA(cudaFuncSetAttribute(attn_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+    DIT4SR_CUDA(cudaFuncSetAttribute(v2::attn_fwd2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, v2::SMEM_BYTES));
+    const char* e = getenv("DIT4SR_ATTN_VARIANT");
+    if (e != nullptr && e[0] == '1') variant = 1;
     configured = true;
   }
-  dim3 grid((p->seq_q + BQ - 1) / BQ, p->heads, p->batches);
-  attn_fwd_kernel<<<grid, NUM_THREADS, SMEM_BYTES, stream>>>(tmQ, tmK, tmV, a);
+  if (variant == 1) {
+    dim3 grid((p->seq_q + BQ - 1) / BQ, p->heads, p->batches);
+    attn_fwd_kernel<<<grid, NUM_THREADS, SMEM_BYTES, stream>>>(tmQ, tmK, tmV, a);
+  } else {
+    dim3 grid((p->seq_q + 2 * BQ - 1) / (2 * BQ), p->heads, p->batches);
+    v2::attn_fwd2_kernel<<<grid, v2::NUM_THREADS, v2::SMEM_BYTES, stream>>>(tmQ, tmK, tmV, a);
+  }
   DIT4SR_CUDA(cudaGetLastError());
   return 0;
 }

@@ -1,14 +1,30 @@
 // Depthwise 3x3 (pad 1, bias) of the LR half added into the HQ half, in place, on the token-major (NHWC) layout.
-// HBM-bound stencil: lane = 8 consecutive channels (16-byte vectors, a warp covers 512 contiguous bytes), warp = one x
-// position of an 8-wide strip, each thread walks down a y segment keeping the 3x3 window of its channels in registers
-// (the x-1/x/x+1 rows loaded by neighbouring warps of the CTA are L1 hits). Weights live in registers.
+// HBM-bound stencil, shared-memory staged:
+//   * one CTA = a TY x TX pixel tile x 64 channels; ONE 4-D TMA box load brings the (TY+2) x (TX+2) x 64 halo tile of
+//     the LR stream into shared memory -- TMA's out-of-bounds zero fill IS the conv's zero padding;
+//   * several CTAs are resident per SM (26 KB of smem each), so many tiles are in flight per SM (memory-level
+//     parallelism comes from the TMA engine, not from per-thread loads);
+//   * thread = 8 channels (16 B) x one pixel column: it slides a 3x3 register window down the tile rows, weights in
+//     registers, HQ read-modify-written with 16-byte accesses issued before the TMA wait.
 #include "host_util.h"
 #include "ptx.cuh"
 
 namespace dwconv {
 
-constexpr int XT = 8;    // x positions per CTA (one per warp)
-constexpr int TY = 8;    // y rows per CTA
+constexpr int CH = 64;        // channels per CTA (128 bytes per pixel)
+constexpr int TX = 32;        // pixel columns per CTA
+constexpr int TY = 4;         // pixel rows per CTA
+constexpr int BX = TX + 2, BY = TY + 2;
+constexpr int THREADS = 128;  // 8 channel groups x 16 pixel columns; each thread does columns x and x+16
+constexpr int TILE_BYTES = BY * BX * CH * 2;
+
+struct Args {
+  __nv_bfloat16* u_hq;
+  int64_t ld, hq_batch_stride;
+  const float* weight9;
+  const float* bias;
+  int grid, channels, x_tiles, y_tiles;
+};
 
 __device__ __forceinline__ void unpack8(const uint4& u, float* f) {
   const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
@@ -20,78 +36,102 @@ __device__ __forceinline__ void unpack8(const uint4& u, float* f) {
   }
 }
 
-__global__ void __launch_bounds__(XT * 32)
-dwconv3x3_kernel(const dit4sr_dwconv3x3_params p, int x_tiles) {
-  const int lane = threadIdx.x & 31;
-  const int warp = threadIdx.x >> 5;
-  const int c0 = (blockIdx.x * 32 + lane) * 8;
-  const int xt = blockIdx.y % x_tiles;
-  const int ys = blockIdx.y / x_tiles;
+__global__ void __launch_bounds__(THREADS, 3)
+dwconv3x3_kernel(const __grid_constant__ CUtensorMap tmLR, const Args a) {
+  __shared__ __align__(128) uint8_t tile[TILE_BYTES];
+  __shared__ __align__(8) uint64_t bar;
+
+  const int tid = threadIdx.x;
+  const int cg = tid & 7;           // channel group (8 channels)
+  const int px = tid >> 3;          // 0..15
+  const int c_base = blockIdx.x * CH;
+  const int xt = blockIdx.y % a.x_tiles;
+  const int yt = blockIdx.y / a.x_tiles;
   const int b = blockIdx.z;
-  const int x = xt * XT + warp;
-  const int G = p.grid;
-  if (c0 >= p.channels || x >= G) return;
+  const int x0 = xt * TX, y0 = yt * TY;
+  const int c0 = c_base + cg * 8;
 
+  if (tid == 0) {
+    ptx::mbar_init(&bar, 1);
+    ptx::fence_barrier_init();
+    ptx::mbar_expect_tx(&bar, TILE_BYTES);
+    ptx::tma_load_4d(tile, &tmLR, &bar, c_base, x0 - 1, y0 - 1, b);   // negative / past-the-end coords read as zero
+  }
+
+  // weights + bias for this thread's 8 channels (L2-resident, 221 KB for F=6144)
   float w[9][8], bias[8];
+  const bool c_ok = c0 < a.channels;
+  if (c_ok) {
 #pragma unroll
-  for (int t = 0; t < 9; ++t) {
-    const float4 a = __ldg(reinterpret_cast<const float4*>(p.weight9 + (int64_t)t * p.channels + c0));
-    const float4 c = __ldg(reinterpret_cast<const float4*>(p.weight9 + (int64_t)t * p.channels + c0) + 1);
-    w[t][0] = a.x; w[t][1] = a.y; w[t][2] = a.z; w[t][3] = a.w;
-    w[t][4] = c.x; w[t][5] = c.y; w[t][6] = c.z; w[t][7] = c.w;
-  }
-  {
-    const float4 a = __ldg(reinterpret_cast<const float4*>(p.bias + c0));
-    const float4 c = __ldg(reinterpret_cast<const float4*>(p.bias + c0) + 1);
-    bias[0] = a.x; bias[1] = a.y; bias[2] = a.z; bias[3] = a.w;
-    bias[4] = c.x; bias[5] = c.y; bias[6] = c.z; bias[7] = c.w;
-  }
-  const __nv_bfloat16* lr = reinterpret_cast<const __nv_bfloat16*>(p.u_lr) + (int64_t)b * p.lr_batch_stride + c0;
-  __nv_bfloat16* hq = reinterpret_cast<__nv_bfloat16*>(p.u_hq) + (int64_t)b * p.hq_batch_stride + c0;
-
-  const uint4 zero = make_uint4(0, 0, 0, 0);
-  auto load_row = [&](int y, uint4 (&row)[3]) {
-    if (y < 0 || y >= G) {
-      row[0] = row[1] = row[2] = zero;
-      return;
+    for (int t = 0; t < 9; ++t) {
+      const float4* p = reinterpret_cast<const float4*>(a.weight9 + (int64_t)t * a.channels + c0);
+      const float4 lo = __ldg(p), hi = __ldg(p + 1);
+      w[t][0] = lo.x; w[t][1] = lo.y; w[t][2] = lo.z; w[t][3] = lo.w;
+      w[t][4] = hi.x; w[t][5] = hi.y; w[t][6] = hi.z; w[t][7] = hi.w;
     }
-    const __nv_bfloat16* base = lr + ((int64_t)y * G + x) * p.ld;
-    row[0] = x > 0 ? __ldg(reinterpret_cast<const uint4*>(base - p.ld)) : zero;
-    row[1] = __ldg(reinterpret_cast<const uint4*>(base));
-    row[2] = x + 1 < G ? __ldg(reinterpret_cast<const uint4*>(base + p.ld)) : zero;
-  };
+    const float4* p = reinterpret_cast<const float4*>(a.bias + c0);
+    const float4 lo = __ldg(p), hi = __ldg(p + 1);
+    bias[0] = lo.x; bias[1] = lo.y; bias[2] = lo.z; bias[3] = lo.w;
+    bias[4] = hi.x; bias[5] = hi.y; bias[6] = hi.z; bias[7] = hi.w;
+  }
+  __syncthreads();   // barrier init visible to all waiters
 
-  const int y_begin = ys * TY;
-  const int y_end = min(y_begin + TY, G);
-  uint4 win[3][3];  // [row: y-1, y, y+1][col: x-1, x, x+1]
-  load_row(y_begin - 1, win[0]);
-  load_row(y_begin, win[1]);
-  for (int y = y_begin; y < y_end; ++y) {
-    load_row(y + 1, win[2]);
-    uint4* dst = reinterpret_cast<uint4*>(hq + ((int64_t)y * G + x) * p.ld);
-    const uint4 hv = *dst;
-    float acc[8], t[8];
-    unpack8(hv, acc);
+  __nv_bfloat16* hq = a.u_hq + (int64_t)b * a.hq_batch_stride + c0;
+  const int G = a.grid;
+
+#pragma unroll 1
+  for (int half = 0; half < 2; ++half) {
+    const int lx = px + half * 16;         // column inside the tile
+    const int x = x0 + lx;
+    const bool col_ok = c_ok && x < G;
+    // HQ values of this column (issued before the TMA wait)
+    uint4 hv[TY];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) acc[j] += bias[j];
+    for (int r = 0; r < TY; ++r) {
+      const int y = y0 + r;
+      hv[r] = (col_ok && y < G) ? *reinterpret_cast<const uint4*>(hq + ((int64_t)y * G + x) * a.ld) : make_uint4(0, 0, 0, 0);
+    }
+    if (half == 0) ptx::mbar_wait(&bar, 0);
+    if (!col_ok) continue;
+    // smem tile layout: [BY][BX][CH] bf16; this thread reads 16 B at channel offset cg*16
+    const uint8_t* sbase = tile + (size_t)lx * (CH * 2) + cg * 16;
+    uint4 win[3][3];
 #pragma unroll
-    for (int dy = 0; dy < 3; ++dy)
+    for (int rr = 0; rr < 2; ++rr)
+#pragma unroll
+      for (int dx = 0; dx < 3; ++dx)
+        win[rr][dx] = *reinterpret_cast<const uint4*>(sbase + ((size_t)rr * BX + dx) * (CH * 2));
+#pragma unroll
+    for (int r = 0; r < TY; ++r) {
+#pragma unroll
+      for (int dx = 0; dx < 3; ++dx)
+        win[2][dx] = *reinterpret_cast<const uint4*>(sbase + ((size_t)(r + 2) * BX + dx) * (CH * 2));
+      const int y = y0 + r;
+      if (y < G) {
+        float acc[8], t[8];
+        unpack8(hv[r], acc);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[j] += bias[j];
+#pragma unroll
+        for (int dy = 0; dy < 3; ++dy)
+#pragma unroll
+          for (int dx = 0; dx < 3; ++dx) {
+            unpack8(win[dy][dx], t);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) acc[j] = fmaf(w[dy * 3 + dx][j], t[j], acc[j]);
+          }
+        uint4 o;
+        o.x = ptx::pack_bf16(acc[0], acc[1]);
+        o.y = ptx::pack_bf16(acc[2], acc[3]);
+        o.z = ptx::pack_bf16(acc[4], acc[5]);
+        o.w = ptx::pack_bf16(acc[6], acc[7]);
+        *reinterpret_cast<uint4*>(hq + ((int64_t)y * G + x) * a.ld) = o;
+      }
 #pragma unroll
       for (int dx = 0; dx < 3; ++dx) {
-        unpack8(win[dy][dx], t);
-#pragma unroll
-        for (int j = 0; j < 8; ++j) acc[j] = fmaf(w[dy * 3 + dx][j], t[j], acc[j]);
+        win[0][dx] = win[1][dx];
+        win[1][dx] = win[2][dx];
       }
-    uint4 o;
-    o.x = ptx::pack_bf16(acc[0], acc[1]);
-    o.y = ptx::pack_bf16(acc[2], acc[3]);
-    o.z = ptx::pack_bf16(acc[4], acc[5]);
-    o.w = ptx::pack_bf16(acc[6], acc[7]);
-    *dst = o;
-#pragma unroll
-    for (int dx = 0; dx < 3; ++dx) {
-      win[0][dx] = win[1][dx];
-      win[1][dx] = win[2][dx];
     }
   }
 }
@@ -99,6 +139,7 @@ dwconv3x3_kernel(const dit4sr_dwconv3x3_params p, int x_tiles) {
 }  // namespace dwconv
 
 extern "C" int dit4sr_dwconv3x3_add(const dit4sr_dwconv3x3_params* p, void* stream_) {
+  using namespace dwconv;
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
   DIT4SR_REQUIRE(p && p->u_hq && p->u_lr && p->weight9 && p->bias, DIT4SR_E_BADARG, "dwconv: null pointer argument");
   DIT4SR_REQUIRE(p->batches > 0 && p->grid > 0 && p->channels > 0, DIT4SR_E_BADARG, "dwconv: non-positive size");
@@ -108,10 +149,28 @@ extern "C" int dit4sr_dwconv3x3_add(const dit4sr_dwconv3x3_params* p, void* stre
                      host::aligned16(p->bias),
                  DIT4SR_E_ALIGN, "dwconv: pointers/strides not 16-byte aligned");
   DIT4SR_REQUIRE(p->batches <= 65535, DIT4SR_E_SHAPE, "dwconv: batches > 65535");
-  const int x_tiles = (p->grid + dwconv::XT - 1) / dwconv::XT;
-  const int y_segs = (p->grid + dwconv::TY - 1) / dwconv::TY;
-  dim3 grid((p->channels / 8 + 31) / 32, x_tiles * y_segs, p->batches);
-  dwconv::dwconv3x3_kernel<<<grid, dwconv::XT * 32, 0, stream>>>(*p, x_tiles);
+  int rc = dit4sr_check_device();
+  if (rc != 0) return rc;
+
+  CUtensorMap tm;
+  const uint64_t dims[4] = {(uint64_t)p->channels, (uint64_t)p->grid, (uint64_t)p->grid, (uint64_t)p->batches};
+  const uint64_t strides[3] = {(uint64_t)p->ld * 2, (uint64_t)p->ld * 2 * p->grid,
+                               (uint64_t)(p->batches > 1 ? p->lr_batch_stride : p->ld * (int64_t)p->grid * p->grid) * 2};
+  const uint32_t box[4] = {CH, BX, BY, 1};
+  if ((rc = host::make_tmap_bf16_noswizzle(&tm, p->u_lr, 4, dims, strides, box)) != 0) return rc;
+
+  Args a;
+  a.u_hq = reinterpret_cast<__nv_bfloat16*>(p->u_hq);
+  a.ld = p->ld;
+  a.hq_batch_stride = p->hq_batch_stride;
+  a.weight9 = p->weight9;
+  a.bias = p->bias;
+  a.grid = p->grid;
+  a.channels = p->channels;
+  a.x_tiles = (p->grid + TX - 1) / TX;
+  a.y_tiles = (p->grid + TY - 1) / TY;
+  dim3 grid((p->channels + CH - 1) / CH, a.x_tiles * a.y_tiles, p->batches);
+  dwconv3x3_kernel<<<grid, THREADS, 0, stream>>>(tm, a);
   DIT4SR_CUDA(cudaGetLastError());
   return 0;
 }

@@ -1,5 +1,7 @@
-// Batched-row bf16 GEMM on sm_100a: TMA -> 128B-swizzled smem ring -> tcgen05.mma (128x256 tiles, fp32 accumulators
-// in TMEM, double-buffered) -> fused epilogues.  Persistent: one CTA per SM walks the tile list.
+// Grouped batched-row bf16 GEMM on sm_100a: TMA -> 128B-swizzled smem ring -> tcgen05.mma (128x256 tiles, fp32
+// accumulators in TMEM, double-buffered) -> fused epilogues.  Persistent: one CTA per SM walks the tile list of up to
+// MAX_PROBLEMS independent problems (e.g. the HQ, LR and text projections of one attention) in a single launch, which
+// removes the per-launch fill/drain bubbles and the wave-quantisation tail of the small problems.
 //
 // Warp roles (256 threads): warp 0 = TMA producer (1 thread), warp 1 = MMA issuer (1 thread), warp 2 = TMEM
 // allocator, warps 4..7 = epilogue (each owns the 32 TMEM lanes of its lane quarter; thread = one output row).
@@ -19,14 +21,16 @@ constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
 constexpr int NUM_THREADS = 256;
 constexpr int TMEM_COLS = ACC_STAGES * BN;  // 512
 constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+constexpr int MAX_PROBLEMS = DIT4SR_GEMM_MAX_GROUP;
 
-struct Args {
+struct Problem {
   const float* bias;
   void* C;
   int64_t ldc, c_batch_stride;
   int c_f32;
-  int batches, rows, N, K;
-  int m_tiles, n_tiles, num_tiles, k_blocks;
+  int rows, N;
+  int m_tiles, n_tiles, k_blocks;
+  int tile_begin;  // first global tile index of this problem
   const float* gate;
   int64_t gate_batch_stride;
   const float* resid;
@@ -37,6 +41,37 @@ struct Args {
   float eps;
   int64_t dbl_row_offset;
 };
+
+struct Group {
+  int num_problems;
+  int num_tiles;
+  Problem p[MAX_PROBLEMS];
+};
+
+struct Maps {
+  CUtensorMap a[MAX_PROBLEMS];
+  CUtensorMap w[MAX_PROBLEMS];
+};
+
+struct TileCoord {
+  int pi, b, m_tile, n_tile;
+};
+
+__device__ __forceinline__ TileCoord decode_tile(const Group& g, int tile) {
+  int pi = 0;
+#pragma unroll
+  for (int i = 1; i < MAX_PROBLEMS; ++i)
+    if (i < g.num_problems && tile >= g.p[i].tile_begin) pi = i;
+  const Problem& p = g.p[pi];
+  const int local = tile - p.tile_begin;
+  TileCoord c;
+  c.pi = pi;
+  c.n_tile = local % p.n_tiles;
+  const int rest = local / p.n_tiles;
+  c.m_tile = rest % p.m_tiles;
+  c.b = rest / p.m_tiles;
+  return c;
+}
 
 __device__ __forceinline__ float gelu_tanh(float x) {
   // 0.5 x (1 + tanh( sqrt(2/pi) (x + 0.044715 x^3) ))
@@ -66,7 +101,7 @@ __device__ __forceinline__ void store_f32x32(float* dst, const float* f) {
 
 template <int EPI>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
-gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW, const Args args) {
+gemm_kernel(const __grid_constant__ Maps maps, const __grid_constant__ Group grp) {
   extern __shared__ uint8_t smem_raw[];
   // 1024-byte alignment for SWIZZLE_128B tiles
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -81,8 +116,10 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
   const int lane = threadIdx.x & 31;
 
   if (warp == 0 && lane == 0) {
-    ptx::prefetch_tmap(&tmA);
-    ptx::prefetch_tmap(&tmW);
+    for (int i = 0; i < grp.num_problems; ++i) {
+      ptx::prefetch_tmap(&maps.a[i]);
+      ptx::prefetch_tmap(&maps.w[i]);
+    }
   }
   if (warp == 1 && lane == 0) {
     for (int i = 0; i < STAGES; ++i) {
@@ -104,8 +141,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
 
-  const int num_tiles = args.num_tiles;
-  const int k_blocks = args.k_blocks;
+  const int num_tiles = grp.num_tiles;
 
   if (warp == 0) {
     if (lane == 0) {
@@ -113,17 +149,17 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       int stage = 0;
       uint32_t phase = 0;
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-        const int n_tile = tile % args.n_tiles;
-        const int rest = tile / args.n_tiles;
-        const int m_tile = rest % args.m_tiles;
-        const int b = rest / args.m_tiles;
+        const TileCoord tc = decode_tile(grp, tile);
+        const int k_blocks = grp.p[tc.pi].k_blocks;
+        const CUtensorMap* ma = &maps.a[tc.pi];
+        const CUtensorMap* mw = &maps.w[tc.pi];
         for (int kb = 0; kb < k_blocks; ++kb) {
           ptx::mbar_wait(&empty_bar[stage], phase ^ 1);
           uint8_t* sa = smem + stage * STAGE_BYTES;
           uint8_t* sb = sa + A_BYTES;
           ptx::mbar_expect_tx(&full_bar[stage], STAGE_BYTES);
-          ptx::tma_load_3d(sa, &tmA, &full_bar[stage], kb * BK, m_tile * BM, b);
-          ptx::tma_load_2d(sb, &tmW, &full_bar[stage], kb * BK, n_tile * BN);
+          ptx::tma_load_3d(sa, ma, &full_bar[stage], kb * BK, tc.m_tile * BM, tc.b);
+          ptx::tma_load_2d(sb, mw, &full_bar[stage], kb * BK, tc.n_tile * BN);
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
       }
@@ -136,6 +172,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       uint32_t phase = 0;
       int it = 0;
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+        const TileCoord tc = decode_tile(grp, tile);
+        const int k_blocks = grp.p[tc.pi].k_blocks;
         const int as = it & 1;
         const uint32_t aphase = (it >> 1) & 1;
         ptx::mbar_wait(&tempty_bar[as], aphase ^ 1);
@@ -163,102 +201,161 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     const int q = warp & 3;  // TMEM lane quarter this warp may access
     int it = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
-      const int n_tile = tile % args.n_tiles;
-      const int rest = tile / args.n_tiles;
-      const int m_tile = rest % args.m_tiles;
-      const int b = rest / args.m_tiles;
+      const TileCoord tc = decode_tile(grp, tile);
+      const Problem& P = grp.p[tc.pi];
       const int as = it & 1;
       const uint32_t aphase = (it >> 1) & 1;
-      ptx::mbar_wait(&tfull_bar[as], aphase);
-      ptx::tc_fence_after();
 
-      const int r = m_tile * BM + q * 32 + lane;
-      const bool row_ok = r < args.rows;
+      const int r = tc.m_tile * BM + q * 32 + lane;
+      const bool row_ok = r < P.rows;
       const uint32_t taddr = tmem_base + as * BN + ((uint32_t)(q * 32) << 16);
-      const int n_base = n_tile * BN;
-      const int64_t c_off = (int64_t)b * args.c_batch_stride + (int64_t)r * args.ldc;
+      const int n_base = tc.n_tile * BN;
+      const int64_t c_off = (int64_t)tc.b * P.c_batch_stride + (int64_t)r * P.ldc;
+      const int n_valid = min(BN, P.N - n_base);   // multiple of 32
 
       if constexpr (EPI == DIT4SR_EPI_QKV_NORM) {
-        __nv_bfloat16* Cb = reinterpret_cast<__nv_bfloat16*>(args.C);
-#pragma unroll 1
+        __nv_bfloat16* Cb = reinterpret_cast<__nv_bfloat16*>(P.C);
+        ptx::mbar_wait(&tfull_bar[as], aphase);
+        ptx::tc_fence_after();
+        uint32_t v[2][64];
+        ptx::tmem_ld32(taddr, *reinterpret_cast<uint32_t(*)[32]>(&v[0][0]));
+        ptx::tmem_ld32(taddr + 32, *reinterpret_cast<uint32_t(*)[32]>(&v[0][32]));
+#pragma unroll
         for (int hgrp = 0; hgrp < BN / 64; ++hgrp) {
           const int n0 = n_base + hgrp * 64;
-          if (n0 >= args.N) break;
-          uint32_t v0[32], v1[32];
-          ptx::tmem_ld32(taddr + hgrp * 64, v0);
-          ptx::tmem_ld32(taddr + hgrp * 64 + 32, v1);
-          ptx::tmem_wait_ld();
-          float f[64];
+          if (hgrp * 64 < n_valid) {
+            ptx::tmem_wait_ld();
+            if ((hgrp + 1) * 64 < n_valid) {   // prefetch the next head's accumulators while this one is normalised
+              ptx::tmem_ld32(taddr + (hgrp + 1) * 64, *reinterpret_cast<uint32_t(*)[32]>(&v[(hgrp + 1) & 1][0]));
+              ptx::tmem_ld32(taddr + (hgrp + 1) * 64 + 32, *reinterpret_cast<uint32_t(*)[32]>(&v[(hgrp + 1) & 1][32]));
+            }
+            float f[64];
+            if (P.bias != nullptr) {
 #pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            f[j] = __uint_as_float(v0[j]) + (args.bias ? __ldg(args.bias + n0 + j) : 0.f);
-            f[32 + j] = __uint_as_float(v1[j]) + (args.bias ? __ldg(args.bias + n0 + 32 + j) : 0.f);
-          }
-          const int sec = n0 / args.sec_cols;
-          const float* w = sec == 0 ? args.norm_w0 : (sec == 1 ? args.norm_w1 : nullptr);
-          if (w != nullptr) {
-            float ss = 0.f;
+              for (int j4 = 0; j4 < 16; ++j4) {
+                const float4 bb = __ldg(reinterpret_cast<const float4*>(P.bias + n0) + j4);
+                f[4 * j4 + 0] = __uint_as_float(v[hgrp & 1][4 * j4 + 0]) + bb.x;
+                f[4 * j4 + 1] = __uint_as_float(v[hgrp & 1][4 * j4 + 1]) + bb.y;
+                f[4 * j4 + 2] = __uint_as_float(v[hgrp & 1][4 * j4 + 2]) + bb.z;
+                f[4 * j4 + 3] = __uint_as_float(v[hgrp & 1][4 * j4 + 3]) + bb.w;
+              }
+            } else {
 #pragma unroll
-            for (int j = 0; j < 64; ++j) ss += f[j] * f[j];
-            const float inv = rsqrtf(ss * (1.0f / 64.0f) + args.eps);
+              for (int j = 0; j < 64; ++j) f[j] = __uint_as_float(v[hgrp & 1][j]);
+            }
+            const int sec = n0 / P.sec_cols;
+            const float* w = sec == 0 ? P.norm_w0 : (sec == 1 ? P.norm_w1 : nullptr);
+            if (w != nullptr) {
+              float ss = 0.f;
 #pragma unroll
-            for (int j = 0; j < 64; ++j) f[j] = f[j] * inv * __ldg(w + j);
-          }
-          if (row_ok) {
-            store_bf16x32(Cb + c_off + n0, f);
-            store_bf16x32(Cb + c_off + n0 + 32, f + 32);
-          }
-          if (sec == 1 && args.dbl_row_offset != 0 && w != nullptr) {
-            float ss = 0.f;
+              for (int j = 0; j < 64; ++j) ss += f[j] * f[j];
+              const float inv = rsqrtf(ss * (1.0f / 64.0f) + P.eps);
 #pragma unroll
-            for (int j = 0; j < 64; ++j) ss += f[j] * f[j];
-            const float inv = rsqrtf(ss * (1.0f / 64.0f) + args.eps);
-#pragma unroll
-            for (int j = 0; j < 64; ++j) f[j] = f[j] * inv * __ldg(w + j);
+              for (int j4 = 0; j4 < 16; ++j4) {
+                const float4 ww = __ldg(reinterpret_cast<const float4*>(w) + j4);
+                f[4 * j4 + 0] *= inv * ww.x;
+                f[4 * j4 + 1] *= inv * ww.y;
+                f[4 * j4 + 2] *= inv * ww.z;
+                f[4 * j4 + 3] *= inv * ww.w;
+              }
+            }
             if (row_ok) {
-              __nv_bfloat16* d = Cb + c_off + args.dbl_row_offset * args.ldc + n0;
-              store_bf16x32(d, f);
-              store_bf16x32(d + 32, f + 32);
+              store_bf16x32(Cb + c_off + n0, f);
+              store_bf16x32(Cb + c_off + n0 + 32, f + 32);
+            }
+            if (sec == 1 && P.dbl_row_offset != 0 && w != nullptr) {
+              float ss = 0.f;
+#pragma unroll
+              for (int j = 0; j < 64; ++j) ss += f[j] * f[j];
+              const float inv = rsqrtf(ss * (1.0f / 64.0f) + P.eps);
+#pragma unroll
+              for (int j4 = 0; j4 < 16; ++j4) {
+                const float4 ww = __ldg(reinterpret_cast<const float4*>(w) + j4);
+                f[4 * j4 + 0] *= inv * ww.x;
+                f[4 * j4 + 1] *= inv * ww.y;
+                f[4 * j4 + 2] *= inv * ww.z;
+                f[4 * j4 + 3] *= inv * ww.w;
+              }
+              if (row_ok) {
+                __nv_bfloat16* d = Cb + c_off + P.dbl_row_offset * P.ldc + n0;
+                store_bf16x32(d, f);
+                store_bf16x32(d + 32, f + 32);
+              }
             }
           }
         }
       } else {
-#pragma unroll 1
+        // residual rows / gates do not depend on the accumulator: fetch the first chunk before waiting for the MMAs
+        const float* rs_row = nullptr;
+        const float* g_row = nullptr;
+        if constexpr (EPI == DIT4SR_EPI_GATE_RESID) {
+          rs_row = P.resid + (int64_t)tc.b * P.r_batch_stride + (int64_t)r * P.ldr + n_base;
+          g_row = P.gate ? P.gate + (int64_t)tc.b * P.gate_batch_stride + n_base : nullptr;
+        }
+        float4 rv[2][8];
+        if constexpr (EPI == DIT4SR_EPI_GATE_RESID) {
+          if (row_ok) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) rv[0][i] = reinterpret_cast<const float4*>(rs_row)[i];
+          }
+        }
+        ptx::mbar_wait(&tfull_bar[as], aphase);
+        ptx::tc_fence_after();
+        uint32_t v[2][32];
+        ptx::tmem_ld32(taddr, v[0]);
+#pragma unroll
         for (int ch = 0; ch < BN / 32; ++ch) {
           const int n0 = n_base + ch * 32;
-          if (n0 >= args.N) break;
-          uint32_t v[32];
-          ptx::tmem_ld32(taddr + ch * 32, v);
-          ptx::tmem_wait_ld();
-          float f[32];
+          if (ch * 32 < n_valid) {
+            ptx::tmem_wait_ld();
+            if ((ch + 1) * 32 < n_valid) {   // software pipeline: next chunk's TMEM + residual loads in flight
+              ptx::tmem_ld32(taddr + (ch + 1) * 32, v[(ch + 1) & 1]);
+              if constexpr (EPI == DIT4SR_EPI_GATE_RESID) {
+                if (row_ok) {
 #pragma unroll
-          for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]) + (args.bias ? __ldg(args.bias + n0 + j) : 0.f);
-          if constexpr (EPI == DIT4SR_EPI_BIAS_GELU) {
-#pragma unroll
-            for (int j = 0; j < 32; ++j) f[j] = gelu_tanh(f[j]);
-          } else if constexpr (EPI == DIT4SR_EPI_BIAS_SILU) {
-#pragma unroll
-            for (int j = 0; j < 32; ++j) f[j] = silu(f[j]);
-          } else if constexpr (EPI == DIT4SR_EPI_GATE_RESID) {
-            if (row_ok) {
-              const float4* rs = reinterpret_cast<const float4*>(args.resid + (int64_t)b * args.r_batch_stride +
-                                                                 (int64_t)r * args.ldr + n0);
-              const float* g = args.gate ? args.gate + (int64_t)b * args.gate_batch_stride + n0 : nullptr;
-#pragma unroll
-              for (int i = 0; i < 8; ++i) {
-                const float4 rv = rs[i];
-                const float g0 = g ? __ldg(g + 4 * i + 0) : 1.f, g1 = g ? __ldg(g + 4 * i + 1) : 1.f;
-                const float g2 = g ? __ldg(g + 4 * i + 2) : 1.f, g3 = g ? __ldg(g + 4 * i + 3) : 1.f;
-                f[4 * i + 0] = rv.x + g0 * f[4 * i + 0];
-                f[4 * i + 1] = rv.y + g1 * f[4 * i + 1];
-                f[4 * i + 2] = rv.z + g2 * f[4 * i + 2];
-                f[4 * i + 3] = rv.w + g3 * f[4 * i + 3];
+                  for (int i = 0; i < 8; ++i)
+                    rv[(ch + 1) & 1][i] = reinterpret_cast<const float4*>(rs_row + (ch + 1) * 32)[i];
+                }
               }
             }
-          }
-          if (row_ok) {
-            if (args.c_f32) store_f32x32(reinterpret_cast<float*>(args.C) + c_off + n0, f);
-            else store_bf16x32(reinterpret_cast<__nv_bfloat16*>(args.C) + c_off + n0, f);
+            float f[32];
+            if (P.bias != nullptr) {
+#pragma unroll
+              for (int j4 = 0; j4 < 8; ++j4) {
+                const float4 bb = __ldg(reinterpret_cast<const float4*>(P.bias + n0) + j4);
+                f[4 * j4 + 0] = __uint_as_float(v[ch & 1][4 * j4 + 0]) + bb.x;
+                f[4 * j4 + 1] = __uint_as_float(v[ch & 1][4 * j4 + 1]) + bb.y;
+                f[4 * j4 + 2] = __uint_as_float(v[ch & 1][4 * j4 + 2]) + bb.z;
+                f[4 * j4 + 3] = __uint_as_float(v[ch & 1][4 * j4 + 3]) + bb.w;
+              }
+            } else {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[ch & 1][j]);
+            }
+            if constexpr (EPI == DIT4SR_EPI_BIAS_GELU) {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) f[j] = gelu_tanh(f[j]);
+            } else if constexpr (EPI == DIT4SR_EPI_BIAS_SILU) {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) f[j] = silu(f[j]);
+            } else if constexpr (EPI == DIT4SR_EPI_GATE_RESID) {
+              if (row_ok) {
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                  float4 gg = make_float4(1.f, 1.f, 1.f, 1.f);
+                  if (g_row != nullptr) gg = __ldg(reinterpret_cast<const float4*>(g_row + ch * 32) + i);
+                  const float4 rr = rv[ch & 1][i];
+                  f[4 * i + 0] = fmaf(gg.x, f[4 * i + 0], rr.x);
+                  f[4 * i + 1] = fmaf(gg.y, f[4 * i + 1], rr.y);
+                  f[4 * i + 2] = fmaf(gg.z, f[4 * i + 2], rr.z);
+                  f[4 * i + 3] = fmaf(gg.w, f[4 * i + 3], rr.w);
+                }
+              }
+            }
+            if (row_ok) {
+              if (P.c_f32) store_f32x32(reinterpret_cast<float*>(P.C) + c_off + n0, f);
+              else store_bf16x32(reinterpret_cast<__nv_bfloat16*>(P.C) + c_off + n0, f);
+            }
           }
         }
       }
@@ -279,25 +376,21 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
 }
 
 template <int EPI>
-static int launch(const CUtensorMap& tmA, const CUtensorMap& tmW, const Args& a, cudaStream_t stream) {
+static int launch(const Maps& maps, const Group& g, cudaStream_t stream) {
   static bool configured = false;  // benign race: idempotent attribute set
   if (!configured) {
     DIT4SR_CUDA(cudaFuncSetAttribute(gemm_kernel<EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
     configured = true;
   }
   int grid = host::sm_count();
-  if (grid > a.num_tiles) grid = a.num_tiles;
-  gemm_kernel<EPI><<<grid, NUM_THREADS, SMEM_BYTES, stream>>>(tmA, tmW, a);
+  if (grid > g.num_tiles) grid = g.num_tiles;
+  gemm_kernel<EPI><<<grid, NUM_THREADS, SMEM_BYTES, stream>>>(maps, g);
   DIT4SR_CUDA(cudaGetLastError());
   return 0;
 }
 
-}  // namespace gemm
-
-extern "C" int dit4sr_gemm_bf16(const dit4sr_gemm_params* p, void* stream_) {
-  using namespace gemm;
-  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
-  DIT4SR_REQUIRE(p != nullptr && p->A && p->W && p->C, DIT4SR_E_BADARG, "gemm: null pointer argument");
+static int check_problem(const dit4sr_gemm_params* p, int epilogue) {
+  DIT4SR_REQUIRE(p->A && p->W && p->C, DIT4SR_E_BADARG, "gemm: null pointer argument");
   DIT4SR_REQUIRE(p->batches > 0 && p->rows > 0 && p->N > 0 && p->K > 0, DIT4SR_E_BADARG,
                  "gemm: non-positive size (batches %d rows %d N %d K %d)", p->batches, p->rows, p->N, p->K);
   DIT4SR_REQUIRE(p->K % 8 == 0 && p->N % 32 == 0, DIT4SR_E_SHAPE, "gemm: need K %% 8 == 0 and N %% 32 == 0 (K %d N %d)",
@@ -306,66 +399,103 @@ extern "C" int dit4sr_gemm_bf16(const dit4sr_gemm_params* p, void* stream_) {
                  "gemm: lda/ldw/a_batch_stride must be multiples of 8 elements");
   DIT4SR_REQUIRE(p->ldc % 8 == 0 && p->c_batch_stride % 8 == 0 && host::aligned16(p->C), DIT4SR_E_ALIGN,
                  "gemm: C pointer/strides must be 16-byte aligned");
-  DIT4SR_REQUIRE(p->epilogue >= DIT4SR_EPI_BIAS && p->epilogue <= DIT4SR_EPI_GATE_RESID, DIT4SR_E_BADARG,
-                 "gemm: unknown epilogue %d", p->epilogue);
-  if (p->epilogue == DIT4SR_EPI_QKV_NORM) {
-    DIT4SR_REQUIRE(p->N % 64 == 0 && p->sec_cols > 0 && p->sec_cols % 64 == 0 && p->c_dtype == DIT4SR_DT_BF16,
+  DIT4SR_REQUIRE(p->bias == nullptr || host::aligned16(p->bias), DIT4SR_E_ALIGN, "gemm: bias must be 16-byte aligned");
+  DIT4SR_REQUIRE(p->epilogue == epilogue, DIT4SR_E_BADARG, "gemm: all problems of a group must share the epilogue");
+  if (epilogue == DIT4SR_EPI_QKV_NORM) {
+    DIT4SR_REQUIRE(p->N % 64 == 0 && p->sec_cols >= 0 && p->sec_cols % 64 == 0 && p->c_dtype == DIT4SR_DT_BF16,
                    DIT4SR_E_SHAPE, "gemm/QKV_NORM: N and sec_cols must be multiples of 64 and C bf16");
+    DIT4SR_REQUIRE((p->norm_w0 == nullptr || host::aligned16(p->norm_w0)) &&
+                       (p->norm_w1 == nullptr || host::aligned16(p->norm_w1)),
+                   DIT4SR_E_ALIGN, "gemm/QKV_NORM: norm weights must be 16-byte aligned");
   }
-  if (p->epilogue == DIT4SR_EPI_GATE_RESID) {
-    DIT4SR_REQUIRE(p->resid != nullptr && p->c_dtype == DIT4SR_DT_F32 && p->ldr % 4 == 0 && p->r_batch_stride % 4 == 0,
-                   DIT4SR_E_BADARG, "gemm/GATE_RESID: needs fp32 resid and fp32 C");
+  if (epilogue == DIT4SR_EPI_GATE_RESID) {
+    DIT4SR_REQUIRE(p->resid != nullptr && p->c_dtype == DIT4SR_DT_F32 && p->ldr % 4 == 0 && p->r_batch_stride % 4 == 0 &&
+                       host::aligned16(p->resid),
+                   DIT4SR_E_BADARG, "gemm/GATE_RESID: needs 16-byte aligned fp32 resid and fp32 C");
+    DIT4SR_REQUIRE(p->gate == nullptr || (host::aligned16(p->gate) && p->gate_batch_stride % 4 == 0), DIT4SR_E_ALIGN,
+                   "gemm/GATE_RESID: gate must be 16-byte aligned");
   }
-  if (p->epilogue == DIT4SR_EPI_BIAS_GELU || p->epilogue == DIT4SR_EPI_BIAS_SILU) {
+  if (epilogue == DIT4SR_EPI_BIAS_GELU || epilogue == DIT4SR_EPI_BIAS_SILU) {
     DIT4SR_REQUIRE(p->c_dtype == DIT4SR_DT_BF16, DIT4SR_E_BADARG, "gemm: activation epilogues write bf16");
   }
-  int rc = dit4sr_check_device();
-  if (rc != 0) return rc;
+  return 0;
+}
 
-  CUtensorMap tmA, tmW;
-  {
-    uint64_t dims[3] = {(uint64_t)p->K, (uint64_t)p->rows, (uint64_t)p->batches};
-    uint64_t strides[2] = {(uint64_t)p->lda * 2, (uint64_t)(p->batches > 1 ? p->a_batch_stride : (int64_t)p->rows * p->lda) * 2};
-    uint32_t box[3] = {BK, BM, 1};
-    rc = host::make_tmap_bf16(&tmA, p->A, 3, dims, strides, box);
-    if (rc != 0) return rc;
+}  // namespace gemm
+
+extern "C" int dit4sr_gemm_bf16_grouped(const dit4sr_gemm_params* probs, int count, void* stream_) {
+  using namespace gemm;
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  DIT4SR_REQUIRE(probs != nullptr && count >= 1 && count <= MAX_PROBLEMS, DIT4SR_E_BADARG,
+                 "gemm: group size must be 1..%d", MAX_PROBLEMS);
+  const int epilogue = probs[0].epilogue;
+  DIT4SR_REQUIRE(epilogue >= DIT4SR_EPI_BIAS && epilogue <= DIT4SR_EPI_GATE_RESID, DIT4SR_E_BADARG,
+                 "gemm: unknown epilogue %d", epilogue);
+  int rc;
+  for (int i = 0; i < count; ++i)
+    if ((rc = check_problem(&probs[i], epilogue)) != 0) return rc;
+  if ((rc = dit4sr_check_device()) != 0) return rc;
+
+  Maps maps;
+  Group g;
+  g.num_problems = count;
+  int tiles = 0;
+  for (int i = 0; i < count; ++i) {
+    const dit4sr_gemm_params* p = &probs[i];
+    {
+      uint64_t dims[3] = {(uint64_t)p->K, (uint64_t)p->rows, (uint64_t)p->batches};
+      uint64_t strides[2] = {(uint64_t)p->lda * 2,
+                             (uint64_t)(p->batches > 1 ? p->a_batch_stride : (int64_t)p->rows * p->lda) * 2};
+      uint32_t box[3] = {BK, BM, 1};
+      if ((rc = host::make_tmap_bf16(&maps.a[i], p->A, 3, dims, strides, box)) != 0) return rc;
+    }
+    {
+      uint64_t dims[2] = {(uint64_t)p->K, (uint64_t)p->N};
+      uint64_t strides[1] = {(uint64_t)p->ldw * 2};
+      uint32_t box[2] = {BK, BN};
+      if ((rc = host::make_tmap_bf16(&maps.w[i], p->W, 2, dims, strides, box)) != 0) return rc;
+    }
+    Problem& P = g.p[i];
+    P.bias = p->bias;
+    P.C = p->C;
+    P.ldc = p->ldc;
+    P.c_batch_stride = p->c_batch_stride;
+    P.c_f32 = p->c_dtype == DIT4SR_DT_F32;
+    P.rows = p->rows;
+    P.N = p->N;
+    P.m_tiles = (p->rows + BM - 1) / BM;
+    P.n_tiles = (p->N + BN - 1) / BN;
+    P.k_blocks = (p->K + BK - 1) / BK;
+    P.tile_begin = tiles;
+    tiles += P.m_tiles * P.n_tiles * p->batches;
+    P.gate = p->gate;
+    P.gate_batch_stride = p->gate_batch_stride;
+    P.resid = p->resid;
+    P.ldr = p->ldr;
+    P.r_batch_stride = p->r_batch_stride;
+    P.norm_w0 = p->norm_w0;
+    P.norm_w1 = p->norm_w1;
+    P.sec_cols = p->sec_cols > 0 ? p->sec_cols : p->N;
+    P.eps = p->eps;
+    P.dbl_row_offset = p->dbl_row_offset;
   }
-  {
-    uint64_t dims[2] = {(uint64_t)p->K, (uint64_t)p->N};
-    uint64_t strides[1] = {(uint64_t)p->ldw * 2};
-    uint32_t box[2] = {BK, BN};
-    rc = host::make_tmap_bf16(&tmW, p->W, 2, dims, strides, box);
-    if (rc != 0) return rc;
+  for (int i = count; i < MAX_PROBLEMS; ++i) {
+    g.p[i] = g.p[0];
+    g.p[i].tile_begin = 0x7fffffff;
+    maps.a[i] = maps.a[0];
+    maps.w[i] = maps.w[0];
   }
-  Args a;
-  a.bias = p->bias;
-  a.C = p->C;
-  a.ldc = p->ldc;
-  a.c_batch_stride = p->c_batch_stride;
-  a.c_f32 = p->c_dtype == DIT4SR_DT_F32;
-  a.batches = p->batches;
-  a.rows = p->rows;
-  a.N = p->N;
-  a.K = p->K;
-  a.m_tiles = (p->rows + BM - 1) / BM;
-  a.n_tiles = (p->N + BN - 1) / BN;
-  a.num_tiles = a.m_tiles * a.n_tiles * p->batches;
-  a.k_blocks = (p->K + BK - 1) / BK;
-  a.gate = p->gate;
-  a.gate_batch_stride = p->gate_batch_stride;
-  a.resid = p->resid;
-  a.ldr = p->ldr;
-  a.r_batch_stride = p->r_batch_stride;
-  a.norm_w0 = p->norm_w0;
-  a.norm_w1 = p->norm_w1;
-  a.sec_cols = p->sec_cols > 0 ? p->sec_cols : p->N;
-  a.eps = p->eps;
-  a.dbl_row_offset = p->dbl_row_offset;
-  switch (p->epilogue) {
-    case DIT4SR_EPI_BIAS: return launch<DIT4SR_EPI_BIAS>(tmA, tmW, a, stream);
-    case DIT4SR_EPI_BIAS_GELU: return launch<DIT4SR_EPI_BIAS_GELU>(tmA, tmW, a, stream);
-    case DIT4SR_EPI_BIAS_SILU: return launch<DIT4SR_EPI_BIAS_SILU>(tmA, tmW, a, stream);
-    case DIT4SR_EPI_QKV_NORM: return launch<DIT4SR_EPI_QKV_NORM>(tmA, tmW, a, stream);
-    default: return launch<DIT4SR_EPI_GATE_RESID>(tmA, tmW, a, stream);
+  g.num_tiles = tiles;
+  switch (epilogue) {
+    case DIT4SR_EPI_BIAS: return launch<DIT4SR_EPI_BIAS>(maps, g, stream);
+    case DIT4SR_EPI_BIAS_GELU: return launch<DIT4SR_EPI_BIAS_GELU>(maps, g, stream);
+    case DIT4SR_EPI_BIAS_SILU: return launch<DIT4SR_EPI_BIAS_SILU>(maps, g, stream);
+    case DIT4SR_EPI_QKV_NORM: return launch<DIT4SR_EPI_QKV_NORM>(maps, g, stream);
+    default: return launch<DIT4SR_EPI_GATE_RESID>(maps, g, stream);
   }
+}
+
+extern "C" int dit4sr_gemm_bf16(const dit4sr_gemm_params* p, void* stream) {
+  DIT4SR_REQUIRE(p != nullptr, DIT4SR_E_BADARG, "gemm: null pointer argument");
+  return dit4sr_gemm_bf16_grouped(p, 1, stream);
 }

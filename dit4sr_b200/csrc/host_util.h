@@ -36,6 +36,10 @@ inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 
 int make_tmap_bf16(CUtensorMap* out, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
                    const uint32_t* box);
 
+// Same, without swizzle: the shared-memory image is the plain row-major box.
+int make_tmap_bf16_noswizzle(CUtensorMap* out, const void* base, int rank, const uint64_t* dims,
+                             const uint64_t* strides_bytes, const uint32_t* box);
+
 int sm_count();
 
 }  // namespace host

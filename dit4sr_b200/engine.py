@@ -178,38 +178,47 @@ class Engine:
 
     # ------------------------------------------------------------------------------------------------ attention
     def _attention(self, ap: _AttnPack, ws, n_in, nc, N, T, gate, c_gate, last):
-        """JointAttnProcessor2_0 (attention.py:445-559) + the gated residual adds (attention.py:314-320,381-382)."""
+        """JointAttnProcessor2_0 (attention.py:445-559) + the gated residual adds (attention.py:314-320,381-382).
+
+        Three grouped GEMM launches + one attention launch: {HQ q|k|v, LR stage-1, text q|k|v}, {LR q_c, (k_c,) v_c},
+        attention, {to_out, to_out_control, to_add_out}."""
         D, H, R = self.D, self.H, self._run
         x, ctx, qkv, o, lrtmp = ws["x"], ws["ctx"], ws["qkv"], ws["o"], ws["lrtmp"]
         S = 2 * N + (T if ap.has_text else 0)
         hq, lr = n_in[:, :N], n_in[:, N:]
         if ap.qk_norm:
-            R("qkv_gemm", ops.gemm, hq, ap.qkv.w, ap.qkv.b, qkv[:, :N], ops.EPI_QKV_NORM, norm_w0=ap.wq, norm_w1=ap.wk,
-              sec_cols=D, dbl_row_offset=N)
+            E = ops.EPI_QKV_NORM
             t2 = lrtmp[:, :, :2 * D]
-            R("lr_gemm", ops.gemm, lr, ap.lr1.w, ap.lr1.b, t2, ops.EPI_BIAS)
-            R("lr_gemm", ops.gemm, t2[:, :, :D], ap.qc.w, ap.qc.b, qkv[:, N:2 * N, :D], ops.EPI_QKV_NORM, norm_w0=ap.wq,
-              sec_cols=D)
-            R("lr_gemm", ops.gemm, t2[:, :, D:], ap.vc.w, ap.vc.b, qkv[:, N:2 * N, 2 * D:], ops.EPI_BIAS)
+            g1 = [dict(A=hq, W=ap.qkv.w, bias=ap.qkv.b, out=qkv[:, :N], epilogue=E, norm_w0=ap.wq, norm_w1=ap.wk,
+                       sec_cols=D, dbl_row_offset=N),                     # Q1: also emits K_lr = norm_k(norm_k(k_hq))
+                  dict(A=lr, W=ap.lr1.w, bias=ap.lr1.b, out=t2, epilogue=E)]           # to_q|to_v of the LR stream
             if ap.has_text:
-                R("txt_gemm", ops.gemm, nc, ap.add.w, ap.add.b, qkv[:, 2 * N:S], ops.EPI_QKV_NORM, norm_w0=ap.waq,
-                  norm_w1=ap.wak, sec_cols=D)
+                g1.append(dict(A=nc, W=ap.add.w, bias=ap.add.b, out=qkv[:, 2 * N:S], epilogue=E, norm_w0=ap.waq,
+                               norm_w1=ap.wak, sec_cols=D))
+            g2 = [dict(A=t2[:, :, :D], W=ap.qc.w, bias=ap.qc.b, out=qkv[:, N:2 * N, :D], epilogue=E, norm_w0=ap.wq,
+                       sec_cols=D),
+                  dict(A=t2[:, :, D:], W=ap.vc.w, bias=ap.vc.b, out=qkv[:, N:2 * N, 2 * D:], epilogue=E)]
         else:
-            R("qkv_gemm", ops.gemm, hq, ap.qkv.w, ap.qkv.b, qkv[:, :N], ops.EPI_BIAS)
-            R("lr_gemm", ops.gemm, lr, ap.qkv.w, ap.qkv.b, lrtmp, ops.EPI_BIAS)
-            R("lr_gemm", ops.gemm, lrtmp[:, :, :D], ap.qc.w, ap.qc.b, qkv[:, N:2 * N, :D], ops.EPI_BIAS)
-            R("lr_gemm", ops.gemm, lrtmp[:, :, D:2 * D], ap.kc.w, ap.kc.b, qkv[:, N:2 * N, D:2 * D], ops.EPI_BIAS)
-            R("lr_gemm", ops.gemm, lrtmp[:, :, 2 * D:], ap.vc.w, ap.vc.b, qkv[:, N:2 * N, 2 * D:], ops.EPI_BIAS)
+            E = ops.EPI_BIAS
+            g1 = [dict(A=hq, W=ap.qkv.w, bias=ap.qkv.b, out=qkv[:, :N], epilogue=E),
+                  dict(A=lr, W=ap.qkv.w, bias=ap.qkv.b, out=lrtmp, epilogue=E)]
             if ap.has_text:
-                R("txt_gemm", ops.gemm, nc, ap.add.w, ap.add.b, qkv[:, 2 * N:S], ops.EPI_BIAS)
+                g1.append(dict(A=nc, W=ap.add.w, bias=ap.add.b, out=qkv[:, 2 * N:S], epilogue=E))
+            g2 = [dict(A=lrtmp[:, :, :D], W=ap.qc.w, bias=ap.qc.b, out=qkv[:, N:2 * N, :D], epilogue=E),
+                  dict(A=lrtmp[:, :, D:2 * D], W=ap.kc.w, bias=ap.kc.b, out=qkv[:, N:2 * N, D:2 * D], epilogue=E),
+                  dict(A=lrtmp[:, :, 2 * D:], W=ap.vc.w, bias=ap.vc.b, out=qkv[:, N:2 * N, 2 * D:], epilogue=E)]
+        R("qkv_group", ops.gemm_grouped, g1)
+        R("lr2_group", ops.gemm_grouped, g2)
         # the last block's text queries are discarded by the reference (context_pre_only): do not compute them
         seq_q = 2 * N if (last or not ap.has_text) else S
         R("attn", ops.attention, qkv[:, :S, :D], qkv[:, :S, D:2 * D], qkv[:, :S, 2 * D:], o, H, seq_q=seq_q,
           lr_res=n_in, lr_rows=(N, 2 * N))
-        R("out_gemm", ops.gemm, o[:, :N], ap.out.w, ap.out.b, x[:, :N], ops.EPI_GATE_RESID, gate=gate)
-        R("out_gemm", ops.gemm, o[:, N:2 * N], ap.outc.w, ap.outc.b, x[:, N:], ops.EPI_GATE_RESID, gate=gate)
+        G = ops.EPI_GATE_RESID
+        g3 = [dict(A=o[:, :N], W=ap.out.w, bias=ap.out.b, out=x[:, :N], epilogue=G, gate=gate),
+              dict(A=o[:, N:2 * N], W=ap.outc.w, bias=ap.outc.b, out=x[:, N:], epilogue=G, gate=gate)]
         if ap.has_text and not last:
-            R("txt_gemm", ops.gemm, o[:, 2 * N:S], ap.add_out.w, ap.add_out.b, ctx, ops.EPI_GATE_RESID, gate=c_gate)
+            g3.append(dict(A=o[:, 2 * N:S], W=ap.add_out.w, bias=ap.add_out.b, out=ctx, epilogue=G, gate=c_gate))
+        R("out_group", ops.gemm_grouped, g3)
 
     # ------------------------------------------------------------------------------------------------ forward
     @torch.no_grad()
@@ -272,13 +281,16 @@ class Engine:
                 self._attention(bp.attn2, ws, n2, None, N, T, gate_msa2, None, bp.last)
             # MLP with the LR->HQ depthwise conv (attention.py:322-347, FeedForwardControl :155-178)
             R("ln_mod", ops.ln_modulate, x, shift_mlp, scale_mlp, n1)
-            R("ff1", ops.gemm, n1, bp.ff1.w, bp.ff1.b, ws["u"], ops.EPI_BIAS_GELU)
-            R("dwconv", ops.dwconv3x3_add, ws["u"][:, :N], ws["u"][:, N:], bp.conv_w9, bp.conv_b, grid)
-            R("ff2", ops.gemm, ws["u"], bp.ff2.w, bp.ff2.b, x, ops.EPI_GATE_RESID, gate=gate_mlp)
-            if not bp.last:   # text MLP (attention.py:384-393)
+            ff1 = [dict(A=n1, W=bp.ff1.w, bias=bp.ff1.b, out=ws["u"], epilogue=ops.EPI_BIAS_GELU)]
+            ff2 = [dict(A=ws["u"], W=bp.ff2.w, bias=bp.ff2.b, out=x, epilogue=ops.EPI_GATE_RESID, gate=gate_mlp)]
+            if not bp.last:   # text MLP (attention.py:384-393) rides in the same launches
                 R("ln_mod", ops.ln_modulate, ctx, c_shift_mlp, c_scale_mlp, nc)
-                R("txt_gemm", ops.gemm, nc, bp.ffc1.w, bp.ffc1.b, ws["uc"], ops.EPI_BIAS_GELU)
-                R("txt_gemm", ops.gemm, ws["uc"], bp.ffc2.w, bp.ffc2.b, ctx, ops.EPI_GATE_RESID, gate=c_gate_mlp)
+                ff1.append(dict(A=nc, W=bp.ffc1.w, bias=bp.ffc1.b, out=ws["uc"], epilogue=ops.EPI_BIAS_GELU))
+                ff2.append(dict(A=ws["uc"], W=bp.ffc2.w, bias=bp.ffc2.b, out=ctx, epilogue=ops.EPI_GATE_RESID,
+                                gate=c_gate_mlp))
+            R("ff1", ops.gemm_grouped, ff1)
+            R("dwconv", ops.dwconv3x3_add, ws["u"][:, :N], ws["u"][:, N:], bp.conv_w9, bp.conv_b, grid)
+            R("ff2", ops.gemm_grouped, ff2)
             if feat_hook is not None:
                 feat_hook(i, x)
 

@@ -89,9 +89,8 @@ def dwconv3x3_add(u_hq, u_lr, weight9, bias, grid):
     _count()
 
 
-def gemm(A, W, bias, out, epilogue=EPI_BIAS, gate=None, resid=None, norm_w0=None, norm_w1=None, sec_cols=0,
-         eps=1e-6, dbl_row_offset=0):
-    """out[b, r, :] = epilogue(A[b, r, :] @ W.T).  A bf16 [B,R,K] or [M,K]; W bf16 [N,K]; out bf16/fp32 same rows."""
+def _gemm_params(p, A, W, bias, out, epilogue=EPI_BIAS, gate=None, resid=None, norm_w0=None, norm_w1=None, sec_cols=0,
+                 eps=1e-6, dbl_row_offset=0):
     A = _as3(A)
     out = _as3(out)
     _req(A, torch.bfloat16, "A")
@@ -103,7 +102,6 @@ def gemm(A, W, bias, out, epilogue=EPI_BIAS, gate=None, resid=None, norm_w0=None
     N = W.shape[0]
     if W.shape[1] != K or out.shape[0] != B or out.shape[1] != R or out.shape[2] != N:
         raise _lib.Dit4srError(f"gemm: shape mismatch A{tuple(A.shape)} W{tuple(W.shape)} out{tuple(out.shape)}")
-    p = GemmParams()
     p.A, p.lda, p.a_batch_stride = _ptr(A), A.stride(1), A.stride(0)
     p.W, p.ldw = _ptr(W), W.stride(0)
     if bias is not None:
@@ -128,7 +126,29 @@ def gemm(A, W, bias, out, epilogue=EPI_BIAS, gate=None, resid=None, norm_w0=None
         p.norm_w0, p.norm_w1 = _ptr(norm_w0), _ptr(norm_w1)
         p.sec_cols, p.dbl_row_offset = sec_cols or N, dbl_row_offset
     p.eps = eps
+
+
+def gemm(A, W, bias, out, epilogue=EPI_BIAS, **kw):
+    """out[b, r, :] = epilogue(A[b, r, :] @ W.T).  A bf16 [B,R,K] or [M,K]; W bf16 [N,K]; out bf16/fp32 same rows."""
+    p = GemmParams()
+    _gemm_params(p, A, W, bias, out, epilogue, **kw)
     check(_lib.load().dit4sr_gemm_bf16(C.byref(p), _stream()), "dit4sr_gemm_bf16")
+    _count()
+
+
+GEMM_MAX_GROUP = 4
+
+
+def gemm_grouped(problems):
+    """Several independent GEMMs with the same epilogue kind in ONE persistent launch.
+    problems: list of dicts with the keyword arguments of `gemm` (A, W, bias, out, epilogue, ...)."""
+    n = len(problems)
+    if not 1 <= n <= GEMM_MAX_GROUP:
+        raise _lib.Dit4srError(f"gemm_grouped: 1..{GEMM_MAX_GROUP} problems per launch")
+    arr = (GemmParams * n)()
+    for p, kw in zip(arr, problems):
+        _gemm_params(p, **kw)
+    check(_lib.load().dit4sr_gemm_bf16_grouped(arr, n, _stream()), "dit4sr_gemm_bf16_grouped")
     _count()
 
 

@@ -115,6 +115,11 @@ typedef struct {
   int sec_cols; float eps; int64_t dbl_row_offset;
 } dit4sr_gemm_params;
 int dit4sr_gemm_bf16(const dit4sr_gemm_params* p, void* stream);
+/* Up to DIT4SR_GEMM_MAX_GROUP independent problems sharing one epilogue kind, run by ONE persistent launch (e.g. the HQ,
+ * LR and text projections of one attention: attention.py:463-465,475-477,494-496). Shapes, pointers and epilogue operands
+ * are per problem; tiles of problem i are scheduled before those of problem i+1. */
+#define DIT4SR_GEMM_MAX_GROUP 4
+int dit4sr_gemm_bf16_grouped(const dit4sr_gemm_params* problems, int count, void* stream);
 
 /* ---------------------------------------------------------------------------------------------------------------
  * Joint attention, flash-style on tcgen05:  O = softmax(Q K^T * scale) V, non-causal, no mask, head_dim 64.

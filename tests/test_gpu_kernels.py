@@ -126,6 +126,30 @@ def test_gemm_gate_residual(ops):
     assert rel(y, pos + ref) < F32_TOL
 
 
+def test_gemm_grouped_launch(ops):
+    """Three independent problems (different M, N, outputs) in one persistent launch == three single launches."""
+    torch.manual_seed(0)
+    probs, refs, outs = [], [], []
+    for (B, R, K, N) in [(2, 256, 1536, 1536), (2, 333, 1536, 512), (1, 40, 256, 4608)]:
+        A, W, bias, ref = _mk(B, R, K, N)
+        o = torch.zeros(B, R, N, device="cuda", dtype=torch.bfloat16)
+        probs.append(dict(A=A, W=W, bias=bias, out=o, epilogue=ops.EPI_BIAS_GELU))
+        refs.append(torch.nn.functional.gelu(ref, approximate="tanh"))
+        outs.append(o)
+    ops.gemm_grouped(probs)
+    for o, r in zip(outs, refs):
+        assert rel(o.float(), r) < BF16_TOL
+    # mixed gate/residual group: image rows in place + text rows with another gate
+    A1, W1, b1, r1 = _mk(2, 300, 512, 256)
+    A2, W2, b2, r2 = _mk(2, 77, 512, 256)
+    x1, x2 = torch.randn(2, 300, 256, device="cuda"), torch.randn(2, 77, 256, device="cuda")
+    g1, g2 = torch.randn(2, 256, device="cuda"), torch.randn(2, 256, device="cuda")
+    e1, e2 = x1 + g1[:, None] * r1, x2 + g2[:, None] * r2
+    ops.gemm_grouped([dict(A=A1, W=W1, bias=b1, out=x1, epilogue=ops.EPI_GATE_RESID, gate=g1),
+                      dict(A=A2, W=W2, bias=b2, out=x2, epilogue=ops.EPI_GATE_RESID, gate=g2)])
+    assert rel(x1, e1) < F32_TOL and rel(x2, e2) < F32_TOL
+
+
 def _rms(t, w):
     t = t.reshape(*t.shape[:-1], -1, 64)
     t = t * torch.rsqrt(t.pow(2).mean(-1, keepdim=True) + 1e-6) * w
