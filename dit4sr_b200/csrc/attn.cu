@@ -10,6 +10,7 @@
 #include "host_util.h"
 #include "ptx.cuh"
 #include <stdlib.h>
+#include <type_traits>
 
 namespace attn {
 
@@ -425,7 +426,7 @@ attn_fwd2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
     const float sl2 = args.scale_log2;
     float m_run = -INFINITY;   // the max the running sums are scaled with (raw score units)
     float l_run = 0.f;
-    for (int j = 0; j < n_tiles; ++j) {
+    auto tile_step = [&](int j, auto masked) {
       ptx::mbar_wait(&s_full[t], j & 1);
       ptx::tc_fence_after();
       uint32_t v[128];
@@ -436,15 +437,22 @@ attn_fwd2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
       __syncwarp();
       if (lane == 0) ptx::mbar_arrive(&s_free[t]);   // S_t may be overwritten by the next Q K^T
 
-      const int kv_left = args.seq_kv - j * BKV;
-      if (kv_left < BKV) {
+      if constexpr (decltype(masked)::value) {   // only the last KV tile can be ragged
+        const int kv_left = args.seq_kv - j * BKV;
 #pragma unroll
         for (int i = 0; i < 128; ++i)
           if (i >= kv_left) v[i] = 0xff800000u;   // -inf
       }
-      float mx = __uint_as_float(v[0]);
+      // 8 independent max chains (a single chain of 128 dependent FMNMX is latency-bound), then a small tree
+      float mxa[8];
 #pragma unroll
-      for (int i = 1; i < 128; ++i) mx = fmaxf(mx, __uint_as_float(v[i]));
+      for (int a = 0; a < 8; ++a) mxa[a] = __uint_as_float(v[a]);
+#pragma unroll
+      for (int i = 8; i < 128; i += 8)
+#pragma unroll
+        for (int a = 0; a < 8; ++a) mxa[a] = fmaxf(mxa[a], __uint_as_float(v[i + a]));
+      const float mx = fmaxf(fmaxf(fmaxf(mxa[0], mxa[1]), fmaxf(mxa[2], mxa[3])),
+                             fmaxf(fmaxf(mxa[4], mxa[5]), fmaxf(mxa[6], mxa[7])));
       // lazy rescale: keep the old reference max unless the new one exceeds it by more than the threshold
       float alpha = 1.0f;
       const bool grow = (mx - m_run) * sl2 > RESCALE_THRESHOLD;   // true on the first tile (m_run = -inf)
@@ -453,15 +461,16 @@ attn_fwd2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
         m_run = mx;
       }
       const float neg_m = -m_run * sl2;
-      float rsum = 0.f;
+      float rs[4] = {0.f, 0.f, 0.f, 0.f};   // independent partial row sums
       uint32_t pk[64];
 #pragma unroll
       for (int i = 0; i < 64; ++i) {
         const float p0 = ptx::ex2(fmaf(__uint_as_float(v[2 * i]), sl2, neg_m));
         const float p1 = ptx::ex2(fmaf(__uint_as_float(v[2 * i + 1]), sl2, neg_m));
-        rsum += p0 + p1;
+        rs[i & 3] += p0 + p1;
         pk[i] = ptx::pack_bf16(p0, p1);
       }
+      const float rsum = (rs[0] + rs[1]) + (rs[2] + rs[3]);
       // P_t and O_t are in use by PV_t(j-1) until o_done fires
       if (j > 0) {
         ptx::mbar_wait(&o_done[t], (j - 1) & 1);
@@ -485,7 +494,11 @@ attn_fwd2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
       ptx::tc_fence_before();
       __syncwarp();
       if (lane == 0) ptx::mbar_arrive(&p_full[t]);
-    }
+    };
+    const bool ragged = (args.seq_kv % BKV) != 0;
+    for (int j = 0; j + 1 < n_tiles; ++j) tile_step(j, std::false_type{});
+    if (ragged) tile_step(n_tiles - 1, std::true_type{});
+    else tile_step(n_tiles - 1, std::false_type{});
     // epilogue: O / l (+ LR residual) -> bf16 global
     ptx::mbar_wait(&o_done[t], (n_tiles - 1) & 1);
     ptx::tc_fence_after();

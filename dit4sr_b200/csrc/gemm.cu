@@ -20,7 +20,9 @@ constexpr int B_BYTES = BN * BK * 2;
 constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
 constexpr int NUM_THREADS = 256;
 constexpr int TMEM_COLS = ACC_STAGES * BN;  // 512
-constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+constexpr int EPI_ROW_BYTES = 144;                       // 128 B of payload + 16 B pad: conflict-free 16 B accesses
+constexpr int EPI_STAGE_BYTES = 32 * EPI_ROW_BYTES;      // per epilogue warp
+constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/ + 4 * EPI_STAGE_BYTES;
 constexpr int MAX_PROBLEMS = DIT4SR_GEMM_MAX_GROUP;
 
 struct Problem {
@@ -198,7 +200,12 @@ gemm_kernel(const __grid_constant__ Maps maps, const __grid_constant__ Group grp
     }
   } else if (warp >= 4) {
     // ===================== epilogue =====================
+    // The accumulator row of a thread (TMEM lane) gets bias / activation / RMSNorm applied in registers, then goes
+    // through a per-warp shared-memory staging tile so that every global access of the warp is a few whole contiguous
+    // row segments (128 B per row per instruction) instead of 32 scattered 16-byte pieces.
     const int q = warp & 3;  // TMEM lane quarter this warp may access
+    uint8_t* stg = smem + STAGES * STAGE_BYTES + 256 + q * EPI_STAGE_BYTES;
+    const int sub = lane >> 3, seg = lane & 7;
     int it = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
       const TileCoord tc = decode_tile(grp, tile);
@@ -206,97 +213,114 @@ gemm_kernel(const __grid_constant__ Maps maps, const __grid_constant__ Group grp
       const int as = it & 1;
       const uint32_t aphase = (it >> 1) & 1;
 
-      const int r = tc.m_tile * BM + q * 32 + lane;
-      const bool row_ok = r < P.rows;
+      const int row_base = tc.m_tile * BM + q * 32;       // first row of this warp
       const uint32_t taddr = tmem_base + as * BN + ((uint32_t)(q * 32) << 16);
       const int n_base = tc.n_tile * BN;
-      const int64_t c_off = (int64_t)tc.b * P.c_batch_stride + (int64_t)r * P.ldc;
-      const int n_valid = min(BN, P.N - n_base);   // multiple of 32
+      const int n_valid = min(BN, P.N - n_base);          // multiple of 32
+      const int64_t c_tile_off = (int64_t)tc.b * P.c_batch_stride + n_base;
 
-      if constexpr (EPI == DIT4SR_EPI_QKV_NORM) {
-        __nv_bfloat16* Cb = reinterpret_cast<__nv_bfloat16*>(P.C);
+      if (EPI == DIT4SR_EPI_QKV_NORM || !P.c_f32) {
+        // ---------------- bf16 outputs: 64 columns (one head) per pass ----------------
+        __nv_bfloat16* Cb = reinterpret_cast<__nv_bfloat16*>(P.C) + c_tile_off;
         ptx::mbar_wait(&tfull_bar[as], aphase);
         ptx::tc_fence_after();
-        uint32_t v[2][64];
-        ptx::tmem_ld32(taddr, *reinterpret_cast<uint32_t(*)[32]>(&v[0][0]));
-        ptx::tmem_ld32(taddr + 32, *reinterpret_cast<uint32_t(*)[32]>(&v[0][32]));
-#pragma unroll
-        for (int hgrp = 0; hgrp < BN / 64; ++hgrp) {
-          const int n0 = n_base + hgrp * 64;
-          if (hgrp * 64 < n_valid) {
+#pragma unroll 1
+        for (int pass = 0; pass < BN / 64; ++pass) {
+          const int c0 = pass * 64;                      // column offset inside the tile
+          if (c0 < n_valid) {
+            const int cols = min(64, n_valid - c0);      // 32 or 64
+            uint32_t v[64];
+            ptx::tmem_ld32(taddr + c0, *reinterpret_cast<uint32_t(*)[32]>(&v[0]));
+            ptx::tmem_ld32(taddr + c0 + 32, *reinterpret_cast<uint32_t(*)[32]>(&v[32]));
             ptx::tmem_wait_ld();
-            if ((hgrp + 1) * 64 < n_valid) {   // prefetch the next head's accumulators while this one is normalised
-              ptx::tmem_ld32(taddr + (hgrp + 1) * 64, *reinterpret_cast<uint32_t(*)[32]>(&v[(hgrp + 1) & 1][0]));
-              ptx::tmem_ld32(taddr + (hgrp + 1) * 64 + 32, *reinterpret_cast<uint32_t(*)[32]>(&v[(hgrp + 1) & 1][32]));
-            }
             float f[64];
-            if (P.bias != nullptr) {
 #pragma unroll
-              for (int j4 = 0; j4 < 16; ++j4) {
-                const float4 bb = __ldg(reinterpret_cast<const float4*>(P.bias + n0) + j4);
-                f[4 * j4 + 0] = __uint_as_float(v[hgrp & 1][4 * j4 + 0]) + bb.x;
-                f[4 * j4 + 1] = __uint_as_float(v[hgrp & 1][4 * j4 + 1]) + bb.y;
-                f[4 * j4 + 2] = __uint_as_float(v[hgrp & 1][4 * j4 + 2]) + bb.z;
-                f[4 * j4 + 3] = __uint_as_float(v[hgrp & 1][4 * j4 + 3]) + bb.w;
-              }
-            } else {
-#pragma unroll
-              for (int j = 0; j < 64; ++j) f[j] = __uint_as_float(v[hgrp & 1][j]);
+            for (int j4 = 0; j4 < 16; ++j4) {
+              float4 bb = make_float4(0.f, 0.f, 0.f, 0.f);
+              if (P.bias != nullptr && 4 * j4 < cols) bb = __ldg(reinterpret_cast<const float4*>(P.bias + n_base + c0) + j4);
+              f[4 * j4 + 0] = __uint_as_float(v[4 * j4 + 0]) + bb.x;
+              f[4 * j4 + 1] = __uint_as_float(v[4 * j4 + 1]) + bb.y;
+              f[4 * j4 + 2] = __uint_as_float(v[4 * j4 + 2]) + bb.z;
+              f[4 * j4 + 3] = __uint_as_float(v[4 * j4 + 3]) + bb.w;
             }
-            const int sec = n0 / P.sec_cols;
-            const float* w = sec == 0 ? P.norm_w0 : (sec == 1 ? P.norm_w1 : nullptr);
-            if (w != nullptr) {
-              float ss = 0.f;
+            bool dbl = false;
+            const float* w = nullptr;
+            if constexpr (EPI == DIT4SR_EPI_BIAS_GELU) {
 #pragma unroll
-              for (int j = 0; j < 64; ++j) ss += f[j] * f[j];
-              const float inv = rsqrtf(ss * (1.0f / 64.0f) + P.eps);
+              for (int j = 0; j < 64; ++j) f[j] = gelu_tanh(f[j]);
+            } else if constexpr (EPI == DIT4SR_EPI_BIAS_SILU) {
 #pragma unroll
-              for (int j4 = 0; j4 < 16; ++j4) {
-                const float4 ww = __ldg(reinterpret_cast<const float4*>(w) + j4);
-                f[4 * j4 + 0] *= inv * ww.x;
-                f[4 * j4 + 1] *= inv * ww.y;
-                f[4 * j4 + 2] *= inv * ww.z;
-                f[4 * j4 + 3] *= inv * ww.w;
-              }
+              for (int j = 0; j < 64; ++j) f[j] = silu(f[j]);
+            } else if constexpr (EPI == DIT4SR_EPI_QKV_NORM) {
+              const int sec = (n_base + c0) / P.sec_cols;
+              w = sec == 0 ? P.norm_w0 : (sec == 1 ? P.norm_w1 : nullptr);
+              dbl = sec == 1 && P.dbl_row_offset != 0 && w != nullptr;
             }
-            if (row_ok) {
-              store_bf16x32(Cb + c_off + n0, f);
-              store_bf16x32(Cb + c_off + n0 + 32, f + 32);
-            }
-            if (sec == 1 && P.dbl_row_offset != 0 && w != nullptr) {
-              float ss = 0.f;
+#pragma unroll 1
+            for (int rep = 0; rep < 2; ++rep) {          // rep 1 = the second normalisation of the LR keys (quirk Q1)
+              if (rep == 1 && !dbl) break;
+              if (w != nullptr) {
+                float ss0 = 0.f, ss1 = 0.f, ss2 = 0.f, ss3 = 0.f;
 #pragma unroll
-              for (int j = 0; j < 64; ++j) ss += f[j] * f[j];
-              const float inv = rsqrtf(ss * (1.0f / 64.0f) + P.eps);
+                for (int j = 0; j < 64; j += 4) {
+                  ss0 = fmaf(f[j], f[j], ss0);
+                  ss1 = fmaf(f[j + 1], f[j + 1], ss1);
+                  ss2 = fmaf(f[j + 2], f[j + 2], ss2);
+                  ss3 = fmaf(f[j + 3], f[j + 3], ss3);
+                }
+                const float inv = rsqrtf(((ss0 + ss1) + (ss2 + ss3)) * (1.0f / 64.0f) + P.eps);
 #pragma unroll
-              for (int j4 = 0; j4 < 16; ++j4) {
-                const float4 ww = __ldg(reinterpret_cast<const float4*>(w) + j4);
-                f[4 * j4 + 0] *= inv * ww.x;
-                f[4 * j4 + 1] *= inv * ww.y;
-                f[4 * j4 + 2] *= inv * ww.z;
-                f[4 * j4 + 3] *= inv * ww.w;
+                for (int j4 = 0; j4 < 16; ++j4) {
+                  const float4 ww = __ldg(reinterpret_cast<const float4*>(w) + j4);
+                  f[4 * j4 + 0] *= inv * ww.x;
+                  f[4 * j4 + 1] *= inv * ww.y;
+                  f[4 * j4 + 2] *= inv * ww.z;
+                  f[4 * j4 + 3] *= inv * ww.w;
+                }
               }
-              if (row_ok) {
-                __nv_bfloat16* d = Cb + c_off + P.dbl_row_offset * P.ldc + n0;
-                store_bf16x32(d, f);
-                store_bf16x32(d + 32, f + 32);
+              // stage this thread's row (64 bf16 = 128 B), then store 4 whole rows per warp instruction
+              __syncwarp();
+              uint4* wr = reinterpret_cast<uint4*>(stg + lane * EPI_ROW_BYTES);
+#pragma unroll
+              for (int i = 0; i < 8; ++i) {
+                uint4 u;
+                u.x = ptx::pack_bf16(f[8 * i + 0], f[8 * i + 1]);
+                u.y = ptx::pack_bf16(f[8 * i + 2], f[8 * i + 3]);
+                u.z = ptx::pack_bf16(f[8 * i + 4], f[8 * i + 5]);
+                u.w = ptx::pack_bf16(f[8 * i + 6], f[8 * i + 7]);
+                wr[i] = u;
+              }
+              __syncwarp();
+              const int64_t row_shift = rep == 1 ? P.dbl_row_offset : 0;
+              if (seg * 8 < cols) {
+#pragma unroll
+                for (int r4 = 0; r4 < 8; ++r4) {
+                  const int rl = r4 * 4 + sub;
+                  const uint4 u = *reinterpret_cast<const uint4*>(stg + rl * EPI_ROW_BYTES + seg * 16);
+                  const int rg = row_base + rl;
+                  if (rg < P.rows)
+                    *reinterpret_cast<uint4*>(Cb + (rg + row_shift) * P.ldc + c0 + seg * 8) = u;
+                }
               }
             }
           }
         }
       } else {
-        // residual rows / gates do not depend on the accumulator: fetch the first chunk before waiting for the MMAs
-        const float* rs_row = nullptr;
+        // ---------------- fp32 outputs (plain bias, or gate * y + residual): 32 columns per pass ----------------
+        float* Cf = reinterpret_cast<float*>(P.C) + c_tile_off;
+        const float* Rf = nullptr;
         const float* g_row = nullptr;
         if constexpr (EPI == DIT4SR_EPI_GATE_RESID) {
-          rs_row = P.resid + (int64_t)tc.b * P.r_batch_stride + (int64_t)r * P.ldr + n_base;
+          Rf = P.resid + (int64_t)tc.b * P.r_batch_stride + n_base;
           g_row = P.gate ? P.gate + (int64_t)tc.b * P.gate_batch_stride + n_base : nullptr;
         }
+        // the residual does not depend on the accumulator: fetch the first pass before waiting for the MMAs
         float4 rv[2][8];
         if constexpr (EPI == DIT4SR_EPI_GATE_RESID) {
-          if (row_ok) {
 #pragma unroll
-            for (int i = 0; i < 8; ++i) rv[0][i] = reinterpret_cast<const float4*>(rs_row)[i];
+          for (int r4 = 0; r4 < 8; ++r4) {
+            const int rg = row_base + r4 * 4 + sub;
+            if (rg < P.rows) rv[0][r4] = *reinterpret_cast<const float4*>(Rf + (int64_t)rg * P.ldr + seg * 4);
           }
         }
         ptx::mbar_wait(&tfull_bar[as], aphase);
@@ -305,56 +329,46 @@ gemm_kernel(const __grid_constant__ Maps maps, const __grid_constant__ Group grp
         ptx::tmem_ld32(taddr, v[0]);
 #pragma unroll
         for (int ch = 0; ch < BN / 32; ++ch) {
-          const int n0 = n_base + ch * 32;
-          if (ch * 32 < n_valid) {
+          const int c0 = ch * 32;
+          if (c0 < n_valid) {
             ptx::tmem_wait_ld();
-            if ((ch + 1) * 32 < n_valid) {   // software pipeline: next chunk's TMEM + residual loads in flight
-              ptx::tmem_ld32(taddr + (ch + 1) * 32, v[(ch + 1) & 1]);
+            if (c0 + 32 < n_valid) {   // software pipeline: next pass's TMEM + residual loads in flight
+              ptx::tmem_ld32(taddr + c0 + 32, v[(ch + 1) & 1]);
               if constexpr (EPI == DIT4SR_EPI_GATE_RESID) {
-                if (row_ok) {
 #pragma unroll
-                  for (int i = 0; i < 8; ++i)
-                    rv[(ch + 1) & 1][i] = reinterpret_cast<const float4*>(rs_row + (ch + 1) * 32)[i];
+                for (int r4 = 0; r4 < 8; ++r4) {
+                  const int rg = row_base + r4 * 4 + sub;
+                  if (rg < P.rows)
+                    rv[(ch + 1) & 1][r4] = *reinterpret_cast<const float4*>(Rf + (int64_t)rg * P.ldr + c0 + 32 + seg * 4);
                 }
               }
             }
-            float f[32];
-            if (P.bias != nullptr) {
+            __syncwarp();
+            float4* wr = reinterpret_cast<float4*>(stg + lane * EPI_ROW_BYTES);
 #pragma unroll
-              for (int j4 = 0; j4 < 8; ++j4) {
-                const float4 bb = __ldg(reinterpret_cast<const float4*>(P.bias + n0) + j4);
-                f[4 * j4 + 0] = __uint_as_float(v[ch & 1][4 * j4 + 0]) + bb.x;
-                f[4 * j4 + 1] = __uint_as_float(v[ch & 1][4 * j4 + 1]) + bb.y;
-                f[4 * j4 + 2] = __uint_as_float(v[ch & 1][4 * j4 + 2]) + bb.z;
-                f[4 * j4 + 3] = __uint_as_float(v[ch & 1][4 * j4 + 3]) + bb.w;
-              }
-            } else {
-#pragma unroll
-              for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[ch & 1][j]);
+            for (int i = 0; i < 8; ++i)
+              wr[i] = make_float4(__uint_as_float(v[ch & 1][4 * i]), __uint_as_float(v[ch & 1][4 * i + 1]),
+                                  __uint_as_float(v[ch & 1][4 * i + 2]), __uint_as_float(v[ch & 1][4 * i + 3]));
+            __syncwarp();
+            float4 bb = make_float4(0.f, 0.f, 0.f, 0.f), gg = make_float4(1.f, 1.f, 1.f, 1.f);
+            if (P.bias != nullptr) bb = __ldg(reinterpret_cast<const float4*>(P.bias + n_base + c0) + seg);
+            if constexpr (EPI == DIT4SR_EPI_GATE_RESID) {
+              if (g_row != nullptr) gg = __ldg(reinterpret_cast<const float4*>(g_row + c0) + seg);
             }
-            if constexpr (EPI == DIT4SR_EPI_BIAS_GELU) {
 #pragma unroll
-              for (int j = 0; j < 32; ++j) f[j] = gelu_tanh(f[j]);
-            } else if constexpr (EPI == DIT4SR_EPI_BIAS_SILU) {
-#pragma unroll
-              for (int j = 0; j < 32; ++j) f[j] = silu(f[j]);
-            } else if constexpr (EPI == DIT4SR_EPI_GATE_RESID) {
-              if (row_ok) {
-#pragma unroll
-                for (int i = 0; i < 8; ++i) {
-                  float4 gg = make_float4(1.f, 1.f, 1.f, 1.f);
-                  if (g_row != nullptr) gg = __ldg(reinterpret_cast<const float4*>(g_row + ch * 32) + i);
-                  const float4 rr = rv[ch & 1][i];
-                  f[4 * i + 0] = fmaf(gg.x, f[4 * i + 0], rr.x);
-                  f[4 * i + 1] = fmaf(gg.y, f[4 * i + 1], rr.y);
-                  f[4 * i + 2] = fmaf(gg.z, f[4 * i + 2], rr.z);
-                  f[4 * i + 3] = fmaf(gg.w, f[4 * i + 3], rr.w);
-                }
+            for (int r4 = 0; r4 < 8; ++r4) {
+              const int rl = r4 * 4 + sub;
+              const int rg = row_base + rl;
+              float4 a = *reinterpret_cast<const float4*>(stg + rl * EPI_ROW_BYTES + seg * 16);
+              a.x += bb.x; a.y += bb.y; a.z += bb.z; a.w += bb.w;
+              if constexpr (EPI == DIT4SR_EPI_GATE_RESID) {
+                const float4 rr = rv[ch & 1][r4];
+                a.x = fmaf(gg.x, a.x, rr.x);
+                a.y = fmaf(gg.y, a.y, rr.y);
+                a.z = fmaf(gg.z, a.z, rr.z);
+                a.w = fmaf(gg.w, a.w, rr.w);
               }
-            }
-            if (row_ok) {
-              if (P.c_f32) store_f32x32(reinterpret_cast<float*>(P.C) + c_off + n0, f);
-              else store_bf16x32(reinterpret_cast<__nv_bfloat16*>(P.C) + c_off + n0, f);
+              if (rg < P.rows) *reinterpret_cast<float4*>(Cf + (int64_t)rg * P.ldc + c0 + seg * 4) = a;
             }
           }
         }
