@@ -1,0 +1,80 @@
+"""Developer micro-benchmarks of single kernels at the C2 / 1024px shapes (CUDA-event timing, L2 flushed by size).
+Usage: python tools/kbench.py attn|gemm|dwconv|ln [--reps N] [--shape c2|px1024]"""
+import argparse
+import os
+import sys
+
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from dit4sr_b200 import ops  # noqa: E402
+
+
+def timeit(fn, reps, warm=3):
+    for _ in range(warm):
+        fn()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(reps):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / reps
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("what")
+    ap.add_argument("--reps", type=int, default=20)
+    ap.add_argument("--shape", default="c2")
+    a = ap.parse_args()
+    B, N, T = (8, 1024, 333) if a.shape == "c2" else (2, 4096, 333)
+    D, H, F = 1536, 24, 6144
+    S = 2 * N + T
+    dev = "cuda"
+    torch.manual_seed(0)
+    if a.what == "attn":
+        qkv = torch.randn(B, S, 3 * D, device=dev).bfloat16()
+        o = torch.empty(B, S, D, device=dev, dtype=torch.bfloat16)
+        res = torch.randn(B, 2 * N, D, device=dev).bfloat16()
+        fn = lambda: ops.attention(qkv[..., :D], qkv[..., D:2 * D], qkv[..., 2 * D:], o, H, lr_res=res, lr_rows=(N, 2 * N))
+        ms = timeit(fn, a.reps)
+        fl = 4.0 * S * S * D * B
+        print(f"attn B={B} S={S}: {ms:.4f} ms  {fl / ms / 1e9:.1f} TFLOP/s")
+    elif a.what == "gemm":
+        for name, M, K, Nn, epi in [("ff1", B * 2 * N, D, F, ops.EPI_BIAS_GELU), ("ff2", B * 2 * N, F, D, ops.EPI_GATE_RESID),
+                                    ("qkv", B * N, D, 3 * D, ops.EPI_QKV_NORM), ("out", B * N, D, D, ops.EPI_GATE_RESID)]:
+            A = torch.randn(M, K, device=dev).bfloat16()
+            W = (torch.randn(Nn, K, device=dev) * 0.02).bfloat16()
+            bias = torch.randn(Nn, device=dev)
+            out = torch.empty(M, Nn, device=dev, dtype=torch.float32 if epi == ops.EPI_GATE_RESID else torch.bfloat16)
+            if epi == ops.EPI_GATE_RESID:
+                out.zero_()
+            kw = {}
+            if epi == ops.EPI_QKV_NORM:
+                w = torch.ones(64, device=dev)
+                kw = dict(norm_w0=w, norm_w1=w, sec_cols=D)
+            ms = timeit(lambda: ops.gemm(A, W, bias, out, epi, **kw), a.reps)
+            print(f"gemm {name} M={M} K={K} N={Nn}: {ms:.4f} ms  {2.0 * M * K * Nn / ms / 1e9:.1f} TFLOP/s")
+    elif a.what == "dwconv":
+        g = int(N ** 0.5)
+        u = torch.randn(B, 2 * N, F, device=dev).bfloat16()
+        w9 = torch.randn(9, F, device=dev) * 0.1
+        bias = torch.randn(F, device=dev) * 0.1
+        ms = timeit(lambda: ops.dwconv3x3_add(u[:, :N], u[:, N:], w9, bias, g), a.reps)
+        print(f"dwconv B={B} grid={g}: {ms:.4f} ms  {3.0 * B * N * F * 2 / ms / 1e6:.0f} GB/s (algorithmic)")
+    elif a.what == "ln":
+        x = torch.randn(B, 2 * N, D, device=dev)
+        mod = torch.randn(B, 4 * D, device=dev)
+        o1 = torch.empty(B, 2 * N, D, device=dev, dtype=torch.bfloat16)
+        o2 = torch.empty_like(o1)
+        ms = timeit(lambda: ops.ln_modulate(x, mod[:, :D], mod[:, D:2 * D], o1), a.reps)
+        print(f"ln single: {ms:.4f} ms  {B * 2 * N * D * 6 / ms / 1e6:.0f} GB/s")
+        ms = timeit(lambda: ops.ln_modulate(x, mod[:, :D], mod[:, D:2 * D], o1, mod[:, 2 * D:3 * D], mod[:, 3 * D:], o2), a.reps)
+        print(f"ln dual: {ms:.4f} ms  {B * 2 * N * D * 8 / ms / 1e6:.0f} GB/s")
+
+
+if __name__ == "__main__":
+    main()
