@@ -278,15 +278,22 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
 // =====================================================================================================================
 // v2: one CTA = TWO 128-row query tiles of one (batch, head) sharing every K/V tile (halves the L2->smem traffic), one
 // CTA per SM (all 512 TMEM columns).  Warps (384 threads): 0 = TMA producer, 1 = MMA issuer, 2 = TMEM allocator,
-// 4..7 = softmax warpgroup of tile 0, 8..11 = softmax warpgroup of tile 1.  Each softmax thread owns one query row, pulls
-// its whole 128-wide score row into registers with one TMEM round trip, releases S immediately (so the next Q K^T is
-// issued while the exponentials run), rescales O lazily (only when the running max grew by more than 2^8).
-// TMEM: S0 [0,128) S1 [128,256) | O0 [256,320) O1 [320,384) | P0 [384,448) P1 [448,512).
+// 4..7 = softmax warpgroup of tile 0, 8..11 = softmax warpgroup of tile 1 (thread = one query row).
+//
+// The (tile, kv-step) pairs form a sequence of "slots" n = 2*j + t that rotate over THREE score buffers in TMEM
+// (buffer n % 3): Q_t K_j^T for slot n+3 is issued right after P V of slot n (same buffer, in-order tensor pipe), i.e.
+// one and a half tiles ahead of the softmax that consumes it, so the softmax warpgroups never wait for an MMA round
+// trip.  P (bf16) overwrites the first 64 columns of its own score buffer once the row is in registers.
+// TMEM: S/P buffers [0,128) [128,256) [256,384) | O0 [384,448) O1 [448,512).
+// Softmax: whole 128-wide score row in registers after one tcgen05.ld round trip, log2-domain online softmax
+// (ex2.approx), O rescaled lazily (only when the running max grew by more than 2^8).
 namespace v2 {
 
 constexpr int KV_STAGES = 4;
 constexpr int NUM_THREADS = 384;
 constexpr int TMEM_COLS = 512;
+constexpr int NBUF = 3;
+constexpr int COL_O = 384;
 constexpr int SMEM_BYTES = (2 + 2 * KV_STAGES) * TILE_BYTES + 1024 + 256;
 constexpr float RESCALE_THRESHOLD = 8.0f;   // in log2 units: skip the O rescale while p stays <= 2^8
 
@@ -304,10 +311,9 @@ attn_fwd2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
   uint64_t* k_empty = k_full + KV_STAGES;
   uint64_t* v_full = k_empty + KV_STAGES;
   uint64_t* v_empty = v_full + KV_STAGES;
-  uint64_t* s_full = v_empty + KV_STAGES;   // [2]
-  uint64_t* s_free = s_full + 2;            // [2]
-  uint64_t* p_full = s_free + 2;            // [2]
-  uint64_t* o_done = p_full + 2;            // [2]
+  uint64_t* s_full = v_empty + KV_STAGES;   // [NBUF] scores of the slot using this buffer are in TMEM
+  uint64_t* p_full = s_full + NBUF;         // [NBUF] probabilities written back into the buffer
+  uint64_t* o_done = p_full + NBUF;         // [2]    P V of the tile's latest step has completed
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(o_done + 2);
 
   const int warp = threadIdx.x >> 5;
@@ -316,6 +322,7 @@ attn_fwd2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
   const int head = blockIdx.y;
   const int b = blockIdx.z;
   const int n_tiles = args.n_kv_tiles;
+  const int n_slots = 2 * n_tiles;
 
   if (warp == 0 && lane == 0) {
     ptx::prefetch_tmap(&tmQ);
@@ -328,12 +335,12 @@ attn_fwd2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
       ptx::mbar_init(&v_full[i], 1);
       ptx::mbar_init(&v_empty[i], 1);
     }
-    for (int t = 0; t < 2; ++t) {
-      ptx::mbar_init(&s_full[t], 1);
-      ptx::mbar_init(&s_free[t], 4);
-      ptx::mbar_init(&p_full[t], 4);
-      ptx::mbar_init(&o_done[t], 1);
+    for (int i = 0; i < NBUF; ++i) {
+      ptx::mbar_init(&s_full[i], 1);
+      ptx::mbar_init(&p_full[i], 4);
     }
+    ptx::mbar_init(&o_done[0], 1);
+    ptx::mbar_init(&o_done[1], 1);
     ptx::fence_barrier_init();
   }
   if (warp == 2) {
@@ -363,80 +370,71 @@ attn_fwd2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      // ===================== MMA issuer =====================
-      constexpr uint32_t idesc_qk = ptx::make_idesc_bf16(BQ, BKV, 0, 0);
-      constexpr uint32_t idesc_pv = ptx::make_idesc_bf16(BQ, DH, 0, 1);
-      const uint64_t qdesc0 = ptx::make_sdesc_sw128(ptx::smem_u32(sQ));
-      const uint64_t qdesc1 = ptx::make_sdesc_sw128(ptx::smem_u32(sQ + TILE_BYTES));
+    // ===================== MMA issuer =====================
+    // The whole warp runs this loop so that barrier addresses and descriptors stay warp-uniform (uniform datapath);
+    // one elected lane issues the tcgen05 instructions.
+    constexpr uint32_t idesc_qk = ptx::make_idesc_bf16(BQ, BKV, 0, 0);
+    constexpr uint32_t idesc_pv = ptx::make_idesc_bf16(BQ, DH, 0, 1);
+    const uint64_t qdesc0 = ptx::make_sdesc_sw128(ptx::smem_u32(sQ));
+    const uint64_t qdesc1 = ptx::make_sdesc_sw128(ptx::smem_u32(sQ + TILE_BYTES));
+    const uint64_t kdesc_base = ptx::make_sdesc_sw128(ptx::smem_u32(sK));
+    const uint64_t vdesc_base = ptx::make_sdesc_sw128(ptx::smem_u32(sV));
 
-      auto issue_qk = [&](int t, int st) {   // S_t = Q_t K^T
-        const uint64_t kdesc = ptx::make_sdesc_sw128(ptx::smem_u32(sK + st * TILE_BYTES));
-        const uint64_t qd = t ? qdesc1 : qdesc0;
+    // S[buffer n%3] = Q_t K_j^T for slot n = 2j + t
+    auto issue_qk = [&](int n) {
+      const int t = n & 1, j = n >> 1, st = j % KV_STAGES, buf = n % NBUF;
+      ptx::mbar_wait(&k_full[st], (j / KV_STAGES) & 1);
+      ptx::tc_fence_after();
+      const uint64_t kdesc = kdesc_base + (uint64_t)(st * (TILE_BYTES >> 4));
+      const uint64_t qd = t ? qdesc1 : qdesc0;
+      if (ptx::elect_one()) {
 #pragma unroll
-        for (int k = 0; k < DH / 16; ++k) ptx::mma_ss(tmem_base + t * 128, qd + 2 * k, kdesc + 2 * k, idesc_qk, k != 0);
-        ptx::tc_commit(&s_full[t]);
-      };
-      auto issue_pv = [&](int t, int st, int j) {   // O_t += P_t V
-        const uint64_t vdesc = ptx::make_sdesc_sw128(ptx::smem_u32(sV + st * TILE_BYTES));
+        for (int k = 0; k < DH / 16; ++k)
+          ptx::mma_ss(tmem_base + buf * 128, qd + 2 * k, kdesc + 2 * k, idesc_qk, k != 0);
+        ptx::tc_commit(&s_full[buf]);
+        if (t == 1) ptx::tc_commit(&k_empty[st]);   // both tiles have consumed K_j
+      }
+      __syncwarp();
+    };
+
+    ptx::mbar_wait(q_full, 0);
+    for (int n = 0; n < NBUF && n < n_slots; ++n) issue_qk(n);
+    for (int n = 0; n < n_slots; ++n) {
+      const int t = n & 1, j = n >> 1, st = j % KV_STAGES, buf = n % NBUF;
+      ptx::mbar_wait(&v_full[st], (j / KV_STAGES) & 1);
+      ptx::mbar_wait(&p_full[buf], (n / NBUF) & 1);      // softmax wrote P into the buffer (and rescaled O if needed)
+      ptx::tc_fence_after();
+      const uint64_t vdesc = vdesc_base + (uint64_t)(st * (TILE_BYTES >> 4));
+      if (ptx::elect_one()) {
 #pragma unroll
-        for (int k = 0; k < BKV / 16; ++k)
-          ptx::mma_ts(tmem_base + 256 + t * 64, tmem_base + 384 + t * 64 + 8 * k, vdesc + (uint64_t)(128 * k), idesc_pv,
+        for (int k = 0; k < BKV / 16; ++k)   // O_t += P V_j: A = P from TMEM (8 columns per 16 kv), B = V MN-major
+          ptx::mma_ts(tmem_base + COL_O + t * 64, tmem_base + buf * 128 + 8 * k, vdesc + (uint64_t)(128 * k), idesc_pv,
                       (j | k) != 0);
         ptx::tc_commit(&o_done[t]);
-      };
-
-      ptx::mbar_wait(q_full, 0);
-      ptx::mbar_wait(&k_full[0], 0);
-      ptx::tc_fence_after();
-      issue_qk(0, 0);
-      issue_qk(1, 0);
-      ptx::tc_commit(&k_empty[0]);
-      for (int j = 0; j < n_tiles; ++j) {
-        const int st = j % KV_STAGES;
-        if (j + 1 < n_tiles) {
-          const int st1 = (j + 1) % KV_STAGES;
-          ptx::mbar_wait(&k_full[st1], ((j + 1) / KV_STAGES) & 1);
-          ptx::mbar_wait(&s_free[0], j & 1);      // softmax 0 has S0(j) in registers
-          ptx::tc_fence_after();
-          issue_qk(0, st1);
-          ptx::mbar_wait(&s_free[1], j & 1);
-          ptx::tc_fence_after();
-          issue_qk(1, st1);
-          ptx::tc_commit(&k_empty[st1]);
-        }
-        ptx::mbar_wait(&v_full[st], (j / KV_STAGES) & 1);
-        ptx::mbar_wait(&p_full[0], j & 1);
-        ptx::tc_fence_after();
-        issue_pv(0, st, j);
-        ptx::mbar_wait(&p_full[1], j & 1);
-        ptx::tc_fence_after();
-        issue_pv(1, st, j);
-        ptx::tc_commit(&v_empty[st]);
+        if (t == 1) ptx::tc_commit(&v_empty[st]);
       }
+      __syncwarp();
+      if (n + NBUF < n_slots) issue_qk(n + NBUF);   // reuses this buffer; ordered behind the P V above in the tensor pipe
     }
   } else if (warp >= 4) {
     // ===================== softmax warpgroups =====================
     const int t = (warp - 4) >> 2;   // query tile of this warpgroup
     const int q = warp & 3;          // TMEM lane quarter
     const uint32_t lane_off = (uint32_t)(q * 32) << 16;
-    const uint32_t tS = tmem_base + t * 128 + lane_off;
-    const uint32_t tO = tmem_base + 256 + t * 64 + lane_off;
-    const uint32_t tP = tmem_base + 384 + t * 64 + lane_off;
+    const uint32_t tO = tmem_base + COL_O + t * 64 + lane_off;
     const float sl2 = args.scale_log2;
     float m_run = -INFINITY;   // the max the running sums are scaled with (raw score units)
     float l_run = 0.f;
     auto tile_step = [&](int j, auto masked) {
-      ptx::mbar_wait(&s_full[t], j & 1);
+      const int n = 2 * j + t;
+      const int buf = n % NBUF;
+      const uint32_t tS = tmem_base + buf * 128 + lane_off;
+      ptx::mbar_wait(&s_full[buf], (n / NBUF) & 1);
       ptx::tc_fence_after();
       uint32_t v[128];
 #pragma unroll
       for (int c = 0; c < 4; ++c) ptx::tmem_ld32(tS + c * 32, *reinterpret_cast<uint32_t(*)[32]>(&v[c * 32]));
       ptx::tmem_wait_ld();
-      ptx::tc_fence_before();
-      __syncwarp();
-      if (lane == 0) ptx::mbar_arrive(&s_free[t]);   // S_t may be overwritten by the next Q K^T
-
       if constexpr (decltype(masked)::value) {   // only the last KV tile can be ragged
         const int kv_left = args.seq_kv - j * BKV;
 #pragma unroll
@@ -471,34 +469,34 @@ attn_fwd2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
         pk[i] = ptx::pack_bf16(p0, p1);
       }
       const float rsum = (rs[0] + rs[1]) + (rs[2] + rs[3]);
-      // P_t and O_t are in use by PV_t(j-1) until o_done fires
-      if (j > 0) {
+      // O_t may only be touched between P V(j-1) completing and P V(j) being issued (it is issued after our arrive)
+      if (j > 0 && __any_sync(0xffffffffu, grow)) {
         ptx::mbar_wait(&o_done[t], (j - 1) & 1);
         ptx::tc_fence_after();
-        if (__any_sync(0xffffffffu, grow)) {
 #pragma unroll 1
-          for (int c = 0; c < DH / 32; ++c) {
-            uint32_t o[32];
-            ptx::tmem_ld32(tO + c * 32, o);
-            ptx::tmem_wait_ld();
+        for (int c = 0; c < DH / 32; ++c) {
+          uint32_t o[32];
+          ptx::tmem_ld32(tO + c * 32, o);
+          ptx::tmem_wait_ld();
 #pragma unroll
-            for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
-            ptx::tmem_st32(tO + c * 32, o);
-          }
+          for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
+          ptx::tmem_st32(tO + c * 32, o);
         }
       }
+      // P overwrites the first 64 columns of the score buffer (the whole row is already in registers)
 #pragma unroll
-      for (int c = 0; c < 4; ++c) ptx::tmem_st16(tP + c * 16, &pk[c * 16]);
+      for (int c = 0; c < 4; ++c) ptx::tmem_st16(tS + c * 16, &pk[c * 16]);
       l_run = l_run * alpha + rsum;
       ptx::tmem_wait_st();
       ptx::tc_fence_before();
       __syncwarp();
-      if (lane == 0) ptx::mbar_arrive(&p_full[t]);
+      if (lane == 0) ptx::mbar_arrive(&p_full[buf]);
     };
     const bool ragged = (args.seq_kv % BKV) != 0;
     for (int j = 0; j + 1 < n_tiles; ++j) tile_step(j, std::false_type{});
     if (ragged) tile_step(n_tiles - 1, std::true_type{});
     else tile_step(n_tiles - 1, std::false_type{});
+
     // epilogue: O / l (+ LR residual) -> bf16 global
     ptx::mbar_wait(&o_done[t], (n_tiles - 1) & 1);
     ptx::tc_fence_after();

@@ -167,36 +167,39 @@ gemm_kernel(const __grid_constant__ Maps maps, const __grid_constant__ Group grp
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      // ===================== MMA issuer =====================
-      constexpr uint32_t idesc = ptx::make_idesc_bf16(BM, BN, 0, 0);
-      int stage = 0;
-      uint32_t phase = 0;
-      int it = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
-        const TileCoord tc = decode_tile(grp, tile);
-        const int k_blocks = grp.p[tc.pi].k_blocks;
-        const int as = it & 1;
-        const uint32_t aphase = (it >> 1) & 1;
-        ptx::mbar_wait(&tempty_bar[as], aphase ^ 1);
+    // ===================== MMA issuer =====================
+    // The whole warp runs the loop (warp-uniform barrier addresses / descriptors); one elected lane issues.
+    constexpr uint32_t idesc = ptx::make_idesc_bf16(BM, BN, 0, 0);
+    const uint64_t desc_base = ptx::make_sdesc_sw128(ptx::smem_u32(smem));
+    int stage = 0;
+    uint32_t phase = 0;
+    int it = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+      const TileCoord tc = decode_tile(grp, tile);
+      const int k_blocks = grp.p[tc.pi].k_blocks;
+      const int as = it & 1;
+      const uint32_t aphase = (it >> 1) & 1;
+      ptx::mbar_wait(&tempty_bar[as], aphase ^ 1);
+      ptx::tc_fence_after();
+      const uint32_t d_tmem = tmem_base + as * BN;
+      for (int kb = 0; kb < k_blocks; ++kb) {
+        ptx::mbar_wait(&full_bar[stage], phase);
         ptx::tc_fence_after();
-        const uint32_t d_tmem = tmem_base + as * BN;
-        for (int kb = 0; kb < k_blocks; ++kb) {
-          ptx::mbar_wait(&full_bar[stage], phase);
-          ptx::tc_fence_after();
-          const uint32_t sa = ptx::smem_u32(smem + stage * STAGE_BYTES);
-          const uint64_t adesc = ptx::make_sdesc_sw128(sa);
-          const uint64_t bdesc = ptx::make_sdesc_sw128(sa + A_BYTES);
+        const uint64_t adesc = desc_base + (uint64_t)(stage * (STAGE_BYTES >> 4));
+        const uint64_t bdesc = adesc + (uint64_t)(A_BYTES >> 4);
+        if (ptx::elect_one()) {
 #pragma unroll
           for (int k = 0; k < BK / 16; ++k) {
             // advance 16 bf16 = 32 bytes along K inside the 128B swizzle atom: +2 in the (addr>>4) field
             ptx::mma_ss(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0);
           }
           ptx::tc_commit(&empty_bar[stage]);  // frees the smem slot when these MMAs have read it
-          if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
-        ptx::tc_commit(&tfull_bar[as]);  // accumulator complete
+        __syncwarp();
+        if (++stage == STAGES) { stage = 0; phase ^= 1; }
       }
+      if (ptx::elect_one()) ptx::tc_commit(&tfull_bar[as]);  // accumulator complete
+      __syncwarp();
     }
   } else if (warp >= 4) {
     // ===================== epilogue =====================
