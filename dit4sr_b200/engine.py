@@ -35,18 +35,35 @@ class _Lin:
         self.b = _f32(torch.cat([l.bias for l in linears], dim=0)) if len(linears) > 1 else _f32(linears[0].bias)
 
 
+class _Folded:
+    """Exact-algebra fold of a chained pair of Linears  y = Wc (W x + b) + bc  =  (Wc W) x + (Wc b + bc)  (quirk Q3:
+    `to_x_control(to_x(lr))`, attention.py:475-477). Product formed in fp32, stored as one bf16 weight."""
+
+    def __init__(self, inner, outer):
+        wc, w = outer.weight.detach().float(), inner.weight.detach().float()
+        self.w = (wc @ w).to(torch.bfloat16).contiguous()
+        self.b = (wc @ inner.bias.detach().float() + outer.bias.detach().float()).contiguous()
+
+
 class _AttnPack:
-    def __init__(self, attn, has_text: bool):
+    def __init__(self, attn, has_text: bool, fold: bool):
         self.qk_norm = attn.norm_q is not None
+        self.fold = fold
         self.qkv = _Lin(attn.to_q, attn.to_k, attn.to_v)
         if self.qk_norm:
             # Q1: with qk_norm the LR keys are norm_k(norm_k(k_hq)); to_k_control(to_k(lr)) is dead code
-            self.lr1 = _Lin(attn.to_q, attn.to_v)
             self.wq, self.wk = _f32(attn.norm_q.weight), _f32(attn.norm_k.weight)
+        if fold:
+            self.qf, self.vf = _Folded(attn.to_q, attn.to_q_control), _Folded(attn.to_v, attn.to_v_control)
+            if not self.qk_norm:
+                self.kf = _Folded(attn.to_k, attn.to_k_control)
         else:
-            self.lr1 = self.qkv
-            self.kc = _Lin(attn.to_k_control)
-        self.qc, self.vc = _Lin(attn.to_q_control), _Lin(attn.to_v_control)
+            if self.qk_norm:
+                self.lr1 = _Lin(attn.to_q, attn.to_v)
+            else:
+                self.lr1 = self.qkv
+                self.kc = _Lin(attn.to_k_control)
+            self.qc, self.vc = _Lin(attn.to_q_control), _Lin(attn.to_v_control)
         self.out, self.outc = _Lin(attn.to_out[0]), _Lin(attn.to_out_control)
         self.has_text = has_text
         if has_text:
@@ -57,11 +74,11 @@ class _AttnPack:
 
 
 class _BlockPack:
-    def __init__(self, blk):
+    def __init__(self, blk, fold):
         self.dual = blk.use_dual_attention
         self.last = blk.context_pre_only
-        self.attn = _AttnPack(blk.attn, True)
-        self.attn2 = _AttnPack(blk.attn2, False) if self.dual else None
+        self.attn = _AttnPack(blk.attn, True, fold)
+        self.attn2 = _AttnPack(blk.attn2, False, fold) if self.dual else None
         self.ff1, self.ff2 = _Lin(blk.ff.net[0].proj), _Lin(blk.ff.net[2])
         cw = blk.ff.control_conv.weight
         self.conv_w9 = _f32(cw.reshape(cw.shape[0], 9).t())           # tap-major [9, F]
@@ -71,7 +88,13 @@ class _BlockPack:
 
 
 class Engine:
-    def __init__(self, model):
+    def __init__(self, model, fold_lr_chains: Optional[bool] = None):
+        """fold_lr_chains: fold `to_x_control(to_x(.))` into one GEMM per projection (exact algebra, one bf16 rounding
+        of the product weight instead of a bf16 intermediate activation). Default on; DIT4SR_FOLD_LR=0 turns it off."""
+        import os
+        if fold_lr_chains is None:
+            fold_lr_chains = os.environ.get("DIT4SR_FOLD_LR", "1") != "0"
+        self.fold_lr_chains = fold_lr_chains
         cfg = model.config
         self.cfg = cfg
         self.D = cfg.num_attention_heads * cfg.attention_head_dim
@@ -83,7 +106,7 @@ class Engine:
         if cfg.caption_projection_dim != self.D:
             raise ValueError("dit4sr_b200: caption_projection_dim must equal the inner dim (joint attention)")
         D = self.D
-        self.blocks = [_BlockPack(b) for b in model.transformer_blocks]
+        self.blocks = [_BlockPack(b, fold_lr_chains) for b in model.transformer_blocks]
         # every adaLN linear of the model in one weight: temb is the same for all blocks, so one GEMM per step
         mods, self.mod_off = [], []
         off = 0
@@ -186,29 +209,33 @@ class Engine:
         x, ctx, qkv, o, lrtmp = ws["x"], ws["ctx"], ws["qkv"], ws["o"], ws["lrtmp"]
         S = 2 * N + (T if ap.has_text else 0)
         hq, lr = n_in[:, :N], n_in[:, N:]
-        if ap.qk_norm:
-            E = ops.EPI_QKV_NORM
+        E = ops.EPI_QKV_NORM if ap.qk_norm else ops.EPI_BIAS
+        nq = dict(norm_w0=ap.wq, sec_cols=D) if ap.qk_norm else {}
+        g1 = [dict(A=hq, W=ap.qkv.w, bias=ap.qkv.b, out=qkv[:, :N], epilogue=E,
+                   **(dict(norm_w0=ap.wq, norm_w1=ap.wk, sec_cols=D, dbl_row_offset=N) if ap.qk_norm else {}))]
+        #          ^ Q1: with qk_norm this launch also emits K_lr = norm_k(norm_k(k_hq)) N rows further down
+        g2 = []
+        if ap.fold:       # LR projections straight from the LR tokens with the folded weights
+            g1.append(dict(A=lr, W=ap.qf.w, bias=ap.qf.b, out=qkv[:, N:2 * N, :D], epilogue=E, **nq))
+            g1.append(dict(A=lr, W=ap.vf.w, bias=ap.vf.b, out=qkv[:, N:2 * N, 2 * D:], epilogue=E))
+            if not ap.qk_norm:
+                g2.append(dict(A=lr, W=ap.kf.w, bias=ap.kf.b, out=qkv[:, N:2 * N, D:2 * D], epilogue=E))
+        elif ap.qk_norm:  # as written: stage 1 = to_q|to_v of the LR stream, stage 2 = the control projections
             t2 = lrtmp[:, :, :2 * D]
-            g1 = [dict(A=hq, W=ap.qkv.w, bias=ap.qkv.b, out=qkv[:, :N], epilogue=E, norm_w0=ap.wq, norm_w1=ap.wk,
-                       sec_cols=D, dbl_row_offset=N),                     # Q1: also emits K_lr = norm_k(norm_k(k_hq))
-                  dict(A=lr, W=ap.lr1.w, bias=ap.lr1.b, out=t2, epilogue=E)]           # to_q|to_v of the LR stream
-            if ap.has_text:
-                g1.append(dict(A=nc, W=ap.add.w, bias=ap.add.b, out=qkv[:, 2 * N:S], epilogue=E, norm_w0=ap.waq,
-                               norm_w1=ap.wak, sec_cols=D))
-            g2 = [dict(A=t2[:, :, :D], W=ap.qc.w, bias=ap.qc.b, out=qkv[:, N:2 * N, :D], epilogue=E, norm_w0=ap.wq,
-                       sec_cols=D),
+            g1.append(dict(A=lr, W=ap.lr1.w, bias=ap.lr1.b, out=t2, epilogue=E))
+            g2 = [dict(A=t2[:, :, :D], W=ap.qc.w, bias=ap.qc.b, out=qkv[:, N:2 * N, :D], epilogue=E, **nq),
                   dict(A=t2[:, :, D:], W=ap.vc.w, bias=ap.vc.b, out=qkv[:, N:2 * N, 2 * D:], epilogue=E)]
         else:
-            E = ops.EPI_BIAS
-            g1 = [dict(A=hq, W=ap.qkv.w, bias=ap.qkv.b, out=qkv[:, :N], epilogue=E),
-                  dict(A=lr, W=ap.qkv.w, bias=ap.qkv.b, out=lrtmp, epilogue=E)]
-            if ap.has_text:
-                g1.append(dict(A=nc, W=ap.add.w, bias=ap.add.b, out=qkv[:, 2 * N:S], epilogue=E))
+            g1.append(dict(A=lr, W=ap.qkv.w, bias=ap.qkv.b, out=lrtmp, epilogue=E))
             g2 = [dict(A=lrtmp[:, :, :D], W=ap.qc.w, bias=ap.qc.b, out=qkv[:, N:2 * N, :D], epilogue=E),
                   dict(A=lrtmp[:, :, D:2 * D], W=ap.kc.w, bias=ap.kc.b, out=qkv[:, N:2 * N, D:2 * D], epilogue=E),
                   dict(A=lrtmp[:, :, 2 * D:], W=ap.vc.w, bias=ap.vc.b, out=qkv[:, N:2 * N, 2 * D:], epilogue=E)]
+        if ap.has_text:
+            g1.append(dict(A=nc, W=ap.add.w, bias=ap.add.b, out=qkv[:, 2 * N:S], epilogue=E,
+                           **(dict(norm_w0=ap.waq, norm_w1=ap.wak, sec_cols=D) if ap.qk_norm else {})))
         R("qkv_group", ops.gemm_grouped, g1)
-        R("lr2_group", ops.gemm_grouped, g2)
+        if g2:
+            R("lr2_group", ops.gemm_grouped, g2)
         # the last block's text queries are discarded by the reference (context_pre_only): do not compute them
         seq_q = 2 * N if (last or not ap.has_text) else S
         R("attn", ops.attention, qkv[:, :S, :D], qkv[:, :S, D:2 * D], qkv[:, :S, 2 * D:], o, H, seq_q=seq_q,

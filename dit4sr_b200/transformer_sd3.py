@@ -236,9 +236,9 @@ class SD3Transformer2DModel(nn.Module):
         self._engine = None
         return super().load_state_dict(*args, **kwargs)
 
-    def engine(self) -> Engine:
-        if self._engine is None:
-            self._engine = Engine(self)
+    def engine(self, fold_lr_chains: Optional[bool] = None) -> Engine:
+        if self._engine is None or (fold_lr_chains is not None and self._engine.fold_lr_chains != fold_lr_chains):
+            self._engine = Engine(self, fold_lr_chains=fold_lr_chains)
         return self._engine
 
     # ------------------------------------------------------------------ forward

@@ -96,6 +96,27 @@ def test_full_model_24_blocks_velocity():
     assert ebf <= VEL_TOL + floor
 
 
+def test_unfolded_lr_chains_as_written():
+    """fold_lr_chains=False runs the chained LR projections with a bf16 intermediate, as the reference is written."""
+    cfg = O.sd35_medium_config(num_layers=3, dual_attention_layers=(0,), pos_embed_max_size=96)
+    sd = O.init_state_dict(cfg, seed=0)
+    inputs = O.make_inputs(cfg, 1, 32, 32, 77, seed=1, timestep=300.0)
+    ref32 = _oracle_gpu(sd, cfg, inputs, torch.float32)
+    m = build(cfg, sd)
+    m.engine(fold_lr_chains=False)
+    e_unfolded = rel(run(m, inputs), ref32)
+    m.engine(fold_lr_chains=True)
+    e_folded = rel(run(m, inputs), ref32)
+    print(f"unfolded {e_unfolded:.3e}  folded {e_folded:.3e}")
+    assert e_unfolded <= VEL_TOL and e_folded <= VEL_TOL
+    # and the no-qk_norm flavour unfolded (three live control chains)
+    cfg2 = O.sd35_medium_config(num_layers=2, dual_attention_layers=(), qk_norm=None, pos_embed_max_size=96)
+    sd2 = O.init_state_dict(cfg2, seed=0)
+    m2 = build(cfg2, sd2)
+    m2.engine(fold_lr_chains=False)
+    assert rel(run(m2, inputs), _oracle_gpu(sd2, cfg2, inputs, torch.float32)) <= VEL_TOL
+
+
 def test_sd3_medium_flavour_without_qk_norm():
     """qk_norm=None, no dual attention: the to_k_control(to_k(lr)) chain is live (attention.py:476)."""
     cfg = O.sd35_medium_config(num_layers=3, dual_attention_layers=(), qk_norm=None, pos_embed_max_size=96)
