@@ -33,8 +33,13 @@ class AdaNormLinear(nn.Module):
 
 
 class AttentionZero(nn.Module):
-    def __init__(self, dim: int, heads: int, dim_head: int, context_pre_only: Optional[bool], qk_norm: Optional[str]):
+    """`ocr_branch=True` gives AttentionZero_OCR2HQ2OCR (attention_ocrbranch_ocr2hq2ocr.py:471-514): the same module
+    plus `to_{q,k,v,out}_ocr` for the third (OCR) stream."""
+
+    def __init__(self, dim: int, heads: int, dim_head: int, context_pre_only: Optional[bool], qk_norm: Optional[str],
+                 ocr_branch: bool = False):
         super().__init__()
+        self.ocr_branch = ocr_branch
         self.heads = heads
         self.inner_dim = dim
         self.context_pre_only = context_pre_only
@@ -68,6 +73,13 @@ class AttentionZero(nn.Module):
         self.to_out_control = nn.Linear(dim, dim, bias=True)
         self.to_out_control.weight.data.copy_(self.to_out[0].weight.data)
         self.to_out_control.bias.data.copy_(self.to_out[0].bias.data)
+        if ocr_branch:
+            self.to_q_ocr = zero_module(nn.Linear(dim, dim, bias=True))
+            self.to_k_ocr = zero_module(nn.Linear(dim, dim, bias=True))
+            self.to_v_ocr = zero_module(nn.Linear(dim, dim, bias=True))
+            self.to_out_ocr = nn.Linear(dim, dim, bias=True)
+            self.to_out_ocr.weight.data.copy_(self.to_out[0].weight.data)
+            self.to_out_ocr.bias.data.copy_(self.to_out[0].bias.data)
 
 
 def zero_module(module):
@@ -90,25 +102,33 @@ class FeedForward(nn.Module):
 
 
 class FeedForwardControl(nn.Module):
-    def __init__(self, dim: int, mult: int = 4):
+    """`ocr_branch=True` gives FeedForwardControl_OCR2HQ2OCR (attention_ocrbranch_ocr2hq2ocr.py:102-211)."""
+
+    def __init__(self, dim: int, mult: int = 4, ocr_branch: bool = False):
         super().__init__()
         inner = dim * mult
         self.net = nn.ModuleList([_GELUProj(dim, inner), nn.Dropout(0.0), nn.Linear(inner, dim, bias=True)])
         self.control_conv = zero_module(nn.Conv2d(inner, inner, 3, stride=1, padding=1, groups=inner))
+        if ocr_branch:
+            self.ocr_to_hidden_conv = zero_module(nn.Conv2d(inner, inner, 3, stride=1, padding=1, groups=inner))
+            self.hidden_to_ocr_conv = zero_module(nn.Conv2d(inner, inner, 3, stride=1, padding=1, groups=inner))
 
 
 class JointTransformerBlock(nn.Module):
     def __init__(self, dim, num_attention_heads, attention_head_dim, context_pre_only=False,
-                 qk_norm: Optional[str] = None, use_dual_attention: bool = False):
+                 qk_norm: Optional[str] = None, use_dual_attention: bool = False, ocr_branch: bool = False):
         super().__init__()
         self.use_dual_attention = use_dual_attention
         self.context_pre_only = context_pre_only
+        self.ocr_branch = ocr_branch
         self.norm1 = AdaNormLinear(dim, 9 if use_dual_attention else 6)
         self.norm1_context = AdaNormLinear(dim, 2 if context_pre_only else 6)
-        self.attn = AttentionZero(dim, num_attention_heads, attention_head_dim, context_pre_only, qk_norm)
+        self.attn = AttentionZero(dim, num_attention_heads, attention_head_dim, context_pre_only, qk_norm,
+                                  ocr_branch=ocr_branch)
+        # the OCR model keeps the plain 2-stream AttentionZero for attn2 (attention_ocrbranch_ocr2hq2ocr.py:279-293, Q6)
         self.attn2 = (AttentionZero(dim, num_attention_heads, attention_head_dim, context_pre_only, qk_norm)
                       if use_dual_attention else None)
-        self.ff = FeedForwardControl(dim)
+        self.ff = FeedForwardControl(dim, ocr_branch=ocr_branch)
         self.ff_context = None if context_pre_only else FeedForward(dim)
         self._chunk_size = None
         self._chunk_dim = 0

@@ -39,10 +39,17 @@ class _Folded:
     """Exact-algebra fold of a chained pair of Linears  y = Wc (W x + b) + bc  =  (Wc W) x + (Wc b + bc)  (quirk Q3:
     `to_x_control(to_x(lr))`, attention.py:475-477). Product formed in fp32, stored as one bf16 weight."""
 
-    def __init__(self, inner, outer):
-        wc, w = outer.weight.detach().float(), inner.weight.detach().float()
-        self.w = (wc @ w).to(torch.bfloat16).contiguous()
-        self.b = (wc @ inner.bias.detach().float() + outer.bias.detach().float()).contiguous()
+    def __init__(self, *pairs):
+        """pairs: (inner, outer) Linears; several pairs are concatenated along the output dimension."""
+        if len(pairs) == 2 and not isinstance(pairs[0], (tuple, list)):
+            pairs = (pairs,)
+        ws, bs = [], []
+        for inner, outer in pairs:
+            wc, w = outer.weight.detach().float(), inner.weight.detach().float()
+            ws.append(wc @ w)
+            bs.append(wc @ inner.bias.detach().float() + outer.bias.detach().float())
+        self.w = torch.cat(ws, 0).to(torch.bfloat16).contiguous()
+        self.b = torch.cat(bs, 0).contiguous()
 
 
 class _AttnPack:
@@ -65,6 +72,10 @@ class _AttnPack:
                 self.kc = _Lin(attn.to_k_control)
             self.qc, self.vc = _Lin(attn.to_q_control), _Lin(attn.to_v_control)
         self.out, self.outc = _Lin(attn.to_out[0]), _Lin(attn.to_out_control)
+        self.ocr = getattr(attn, "ocr_branch", False)
+        if self.ocr:   # third stream: to_x_ocr(to_x(ocr)) chains, always folded; its keys get a live norm_k
+            self.of = _Folded((attn.to_q, attn.to_q_ocr), (attn.to_k, attn.to_k_ocr), (attn.to_v, attn.to_v_ocr))
+            self.outo = _Lin(attn.to_out_ocr)
         self.has_text = has_text
         if has_text:
             self.add = _Lin(attn.add_q_proj, attn.add_k_proj, attn.add_v_proj)
@@ -83,6 +94,12 @@ class _BlockPack:
         cw = blk.ff.control_conv.weight
         self.conv_w9 = _f32(cw.reshape(cw.shape[0], 9).t())           # tap-major [9, F]
         self.conv_b = _f32(blk.ff.control_conv.bias)
+        self.ocr = getattr(blk, "ocr_branch", False)
+        if self.ocr:
+            def taps(conv):
+                return _f32(conv.weight.reshape(conv.weight.shape[0], 9).t()), _f32(conv.bias)
+            self.conv_o_w9, self.conv_o_b = taps(blk.ff.ocr_to_hidden_conv)
+            self.conv_h_w9, self.conv_h_b = taps(blk.ff.hidden_to_ocr_conv)
         if not self.last:
             self.ffc1, self.ffc2 = _Lin(blk.ff_context.net[0].proj), _Lin(blk.ff_context.net[2])
 
@@ -95,6 +112,7 @@ class Engine:
         if fold_lr_chains is None:
             fold_lr_chains = os.environ.get("DIT4SR_FOLD_LR", "1") != "0"
         self.fold_lr_chains = fold_lr_chains
+        self.streams = 3 if getattr(model, "_ocr_branch", False) else 2   # image streams: [HQ | LR] or [HQ | LR | OCR]
         cfg = model.config
         self.cfg = cfg
         self.D = cfg.num_attention_heads * cfg.attention_head_dim
@@ -179,17 +197,18 @@ class Engine:
         if ws is not None:
             return ws
         D, F = self.D, 4 * self.D
-        S = 2 * N + T
+        I = self.streams * N            # image tokens
+        S = I + T
         bf, f32 = torch.bfloat16, torch.float32
 
         def e(*shape, dtype=bf):
             return torch.empty(*shape, device=device, dtype=dtype)
 
         ws = dict(
-            x=e(B, 2 * N, D, dtype=f32), ctx=e(B, T, D, dtype=f32),
-            n1=e(B, 2 * N, D), n2=e(B, 2 * N, D), nc=e(B, T, D),
-            qkv=e(B, S, 3 * D), o=e(B, S, D), lrtmp=e(B, N, 3 * D),
-            u=e(B, 2 * N, F), uc=e(B, T, F),
+            x=e(B, I, D, dtype=f32), ctx=e(B, T, D, dtype=f32),
+            n1=e(B, I, D), n2=e(B, I, D), nc=e(B, T, D),
+            qkv=e(B, S, 3 * D), o=e(B, S, D), lrtmp=e(B, I // 2, 3 * D),
+            u=e(B, I, F), uc=e(B, T, F),
             mod=e(B, self.mod_total, dtype=f32),
             tf=e(B, 256), th=e(B, D), ph=e(B, D), temb=e(B, D, dtype=f32), st=e(B, D),
             pooled=e(B, self.cfg.pooled_projection_dim), enc=e(B, T, self.cfg.joint_attention_dim),
@@ -207,8 +226,9 @@ class Engine:
         attention, {to_out, to_out_control, to_add_out}."""
         D, H, R = self.D, self.H, self._run
         x, ctx, qkv, o, lrtmp = ws["x"], ws["ctx"], ws["qkv"], ws["o"], ws["lrtmp"]
-        S = 2 * N + (T if ap.has_text else 0)
-        hq, lr = n_in[:, :N], n_in[:, N:]
+        I = (3 if ap.ocr else 2) * N      # image rows seen by this processor (N = rows per segment)
+        S = I + (T if ap.has_text else 0)
+        hq, lr = n_in[:, :N], n_in[:, N:2 * N]
         E = ops.EPI_QKV_NORM if ap.qk_norm else ops.EPI_BIAS
         nq = dict(norm_w0=ap.wq, sec_cols=D) if ap.qk_norm else {}
         g1 = [dict(A=hq, W=ap.qkv.w, bias=ap.qkv.b, out=qkv[:, :N], epilogue=E,
@@ -230,21 +250,26 @@ class Engine:
             g2 = [dict(A=lrtmp[:, :, :D], W=ap.qc.w, bias=ap.qc.b, out=qkv[:, N:2 * N, :D], epilogue=E),
                   dict(A=lrtmp[:, :, D:2 * D], W=ap.kc.w, bias=ap.kc.b, out=qkv[:, N:2 * N, D:2 * D], epilogue=E),
                   dict(A=lrtmp[:, :, 2 * D:], W=ap.vc.w, bias=ap.vc.b, out=qkv[:, N:2 * N, 2 * D:], epilogue=E)]
+        if ap.ocr:        # OCR stream: folded q|k|v chains; norm_q on q, a live norm_k on k (ocr file :585,:589)
+            g1.append(dict(A=n_in[:, 2 * N:I], W=ap.of.w, bias=ap.of.b, out=qkv[:, 2 * N:I], epilogue=E,
+                           **(dict(norm_w0=ap.wq, norm_w1=ap.wk, sec_cols=D) if ap.qk_norm else {})))
         if ap.has_text:
-            g1.append(dict(A=nc, W=ap.add.w, bias=ap.add.b, out=qkv[:, 2 * N:S], epilogue=E,
+            g1.append(dict(A=nc, W=ap.add.w, bias=ap.add.b, out=qkv[:, I:S], epilogue=E,
                            **(dict(norm_w0=ap.waq, norm_w1=ap.wak, sec_cols=D) if ap.qk_norm else {})))
         R("qkv_group", ops.gemm_grouped, g1)
         if g2:
             R("lr2_group", ops.gemm_grouped, g2)
         # the last block's text queries are discarded by the reference (context_pre_only): do not compute them
-        seq_q = 2 * N if (last or not ap.has_text) else S
+        seq_q = I if (last or not ap.has_text) else S
         R("attn", ops.attention, qkv[:, :S, :D], qkv[:, :S, D:2 * D], qkv[:, :S, 2 * D:], o, H, seq_q=seq_q,
-          lr_res=n_in, lr_rows=(N, 2 * N))
+          lr_res=n_in, lr_rows=(N, I))       # Q2: the LR (and OCR) rows get their normed+modulated input added back
         G = ops.EPI_GATE_RESID
         g3 = [dict(A=o[:, :N], W=ap.out.w, bias=ap.out.b, out=x[:, :N], epilogue=G, gate=gate),
-              dict(A=o[:, N:2 * N], W=ap.outc.w, bias=ap.outc.b, out=x[:, N:], epilogue=G, gate=gate)]
+              dict(A=o[:, N:2 * N], W=ap.outc.w, bias=ap.outc.b, out=x[:, N:2 * N], epilogue=G, gate=gate)]
+        if ap.ocr:
+            g3.append(dict(A=o[:, 2 * N:I], W=ap.outo.w, bias=ap.outo.b, out=x[:, 2 * N:I], epilogue=G, gate=gate))
         if ap.has_text and not last:
-            g3.append(dict(A=o[:, 2 * N:S], W=ap.add_out.w, bias=ap.add_out.b, out=ctx, epilogue=G, gate=c_gate))
+            g3.append(dict(A=o[:, I:S], W=ap.add_out.w, bias=ap.add_out.b, out=ctx, epilogue=G, gate=c_gate))
         R("out_group", ops.gemm_grouped, g3)
 
     # ------------------------------------------------------------------------------------------------ forward
@@ -258,6 +283,8 @@ class Engine:
                              "attention.py:169-172)")
         grid = h // 2
         N = grid * grid
+        if self.streams == 3 and (3 * N) % 2:
+            raise ValueError("3-stream model: attn2 halves the 3N image tokens, N must be even")
         T = encoder_hidden_states.shape[1]
         dev = hidden_states.device
         ws = self._workspace(B, N, T, dev)
@@ -275,7 +302,10 @@ class Engine:
         R("head", ops.silu_cast, ws["temb"], ws["st"])
         R("mod_gemm", ops.gemm, ws["st"], self.mod.w, self.mod.b, mod, ops.EPI_BIAS)   # all adaLN vectors of the step
         # ---- patch embed (+pos) for both streams, context embedder  (:326-332)
-        for src, rows in ((hidden_states, x[:, :N]), (controlnet_image, x[:, N:])):
+        streams = [(hidden_states, x[:, :N]), (controlnet_image, x[:, N:2 * N])]
+        if self.streams == 3:   # the OCR stream starts as a second pos_embed(controlnet_image) (ocr model :334-337)
+            streams.append((controlnet_image, x[:, 2 * N:]))
+        for src, rows in streams:
             R("head", ops.patchify, src.contiguous(), ws["patches"])
             R("head", ops.gemm, ws["patches"], self.patch_w, self.patch_b, rows, ops.EPI_GATE_RESID, resid=pos)
         ws["enc"].copy_(encoder_hidden_states)
@@ -305,7 +335,9 @@ class Engine:
                 R("ln_mod", ops.ln_modulate, ctx, c_shift_msa, c_scale_msa, nc)
             self._attention(bp.attn, ws, n1, nc, N, T, gate_msa, c_gate_msa, bp.last)
             if bp.dual:
-                self._attention(bp.attn2, ws, n2, None, N, T, gate_msa2, None, bp.last)
+                # 3-stream model: attn2 is still the 2-stream processor, so it halves the 3N tokens at 1.5N (Q6)
+                n_seg = N if self.streams == 2 else (3 * N) // 2
+                self._attention(bp.attn2, ws, n2, None, n_seg, T, gate_msa2, None, bp.last)
             # MLP with the LR->HQ depthwise conv (attention.py:322-347, FeedForwardControl :155-178)
             R("ln_mod", ops.ln_modulate, x, shift_mlp, scale_mlp, n1)
             ff1 = [dict(A=n1, W=bp.ff1.w, bias=bp.ff1.b, out=ws["u"], epilogue=ops.EPI_BIAS_GELU)]
@@ -316,7 +348,11 @@ class Engine:
                 ff2.append(dict(A=ws["uc"], W=bp.ffc2.w, bias=bp.ffc2.b, out=ctx, epilogue=ops.EPI_GATE_RESID,
                                 gate=c_gate_mlp))
             R("ff1", ops.gemm_grouped, ff1)
-            R("dwconv", ops.dwconv3x3_add, ws["u"][:, :N], ws["u"][:, N:], bp.conv_w9, bp.conv_b, grid)
+            u = ws["u"]
+            R("dwconv", ops.dwconv3x3_add, u[:, :N], u[:, N:2 * N], bp.conv_w9, bp.conv_b, grid)
+            if bp.ocr:   # u_hq += conv_o(u_ocr); then u_ocr += conv_h(u_hq updated)  (ocr attention file :184-206)
+                R("dwconv", ops.dwconv3x3_add, u[:, :N], u[:, 2 * N:], bp.conv_o_w9, bp.conv_o_b, grid)
+                R("dwconv", ops.dwconv3x3_add, u[:, 2 * N:], u[:, :N], bp.conv_h_w9, bp.conv_h_b, grid)
             R("ff2", ops.gemm_grouped, ff2)
             if feat_hook is not None:
                 feat_hook(i, x)

@@ -136,7 +136,7 @@ def gemm(A, W, bias, out, epilogue=EPI_BIAS, **kw):
     _count()
 
 
-GEMM_MAX_GROUP = 4
+GEMM_MAX_GROUP = 6
 
 
 def gemm_grouped(problems):

@@ -90,6 +90,7 @@ class _AdaNormOut(nn.Module):
 class SD3Transformer2DModel(nn.Module):
     _supports_gradient_checkpointing = True
     config_name = CONFIG_NAME
+    _ocr_branch = False   # True in SD3Transformer2DModel_OCRBranch_OCR2HQ2OCR (three image streams)
 
     def __init__(
         self,
@@ -124,7 +125,8 @@ class SD3Transformer2DModel(nn.Module):
         self.transformer_blocks = nn.ModuleList([
             JointTransformerBlock(dim=self.inner_dim, num_attention_heads=num_attention_heads,
                                   attention_head_dim=attention_head_dim, context_pre_only=i == num_layers - 1,
-                                  qk_norm=qk_norm, use_dual_attention=i in dual_attention_layers)
+                                  qk_norm=qk_norm, use_dual_attention=i in dual_attention_layers,
+                                  ocr_branch=self._ocr_branch)
             for i in range(num_layers)])
         self.norm_out = _AdaNormOut(self.inner_dim)
         self.proj_out = nn.Linear(self.inner_dim, patch_size * patch_size * self.out_channels, bias=True)
@@ -264,14 +266,19 @@ class SD3Transformer2DModel(nn.Module):
         if block_controlnet_hidden_states is not None or skip_layers:
             raise NotImplementedError("block_controlnet_hidden_states / skip_layers are never set by DiT4SR's callers")
         # Q7: the reference dereferences cfg.train.model unconditionally; cfg=None here means "no ts_module".
-        want_feats = cfg is not None and "ts_module" in cfg.train.model
+        # (the 3-stream model extracts features for cfg.train.transformer.feat_extract_layer unconditionally and always
+        #  returns the (output, trans_blk_outs) pair: transformer_sd3_ocrbranch_ocr2hq2ocr.py:344,371-374,407-408)
+        want_feats = cfg is not None and (self._ocr_branch or "ts_module" in cfg.train.model)
         trans_blk_outs = []
         hook = None
         in_dtype = hidden_states.dtype
         if want_feats:
             layers = set(cfg.train.transformer.feat_extract_layer)
             mode = cfg.train.transformer.feat_extract
-            sl = {"hq_feat": (0, 1024), "lq_feat": (1024, 2048), "hqlq_feat": (0, 2048)}.get(mode)   # attention.py:363-374
+            slices = {"hq_feat": (0, 1024), "lq_feat": (1024, 2048), "hqlq_feat": (0, 2048)}          # attention.py:363-374
+            if self._ocr_branch:
+                slices["ocr_feat"] = (2048, 3072)
+            sl = slices.get(mode)
 
             def hook(i, x):
                 if i in layers:
@@ -286,7 +293,7 @@ class SD3Transformer2DModel(nn.Module):
         out = self.engine().forward(hs, ci, encoder_hidden_states, pooled_projections, timestep, feat_hook=hook)
         output = out.to(in_dtype)
         if not return_dict:
-            if want_feats:
+            if want_feats or self._ocr_branch:
                 return (output, trans_blk_outs)
             return (output,)
         return Transformer2DModelOutput(sample=output)

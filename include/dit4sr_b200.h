@@ -118,7 +118,7 @@ int dit4sr_gemm_bf16(const dit4sr_gemm_params* p, void* stream);
 /* Up to DIT4SR_GEMM_MAX_GROUP independent problems sharing one epilogue kind, run by ONE persistent launch (e.g. the HQ,
  * LR and text projections of one attention: attention.py:463-465,475-477,494-496). Shapes, pointers and epilogue operands
  * are per problem; tiles of problem i are scheduled before those of problem i+1. */
-#define DIT4SR_GEMM_MAX_GROUP 4
+#define DIT4SR_GEMM_MAX_GROUP 6
 int dit4sr_gemm_bf16_grouped(const dit4sr_gemm_params* problems, int count, void* stream);
 
 /* ---------------------------------------------------------------------------------------------------------------

@@ -79,7 +79,9 @@ def tiny_config(**kw) -> SimpleNamespace:
 # state_dict layout (transformer_sd3.py:63-119, attention.py:201-268,401-431)
 # --------------------------------------------------------------------------------------------------------------
 
-def state_dict_manifest(cfg) -> "OrderedDict[str, Tuple[int, ...]]":
+def state_dict_manifest(cfg, ocr: bool = False) -> "OrderedDict[str, Tuple[int, ...]]":
+    """ocr=True: the 3-stream SD3Transformer2DModel_OCRBranch_OCR2HQ2OCR layout (extra `attn.to_*_ocr` and the two
+    extra depthwise convs, attention_ocrbranch_ocr2hq2ocr.py:150-158,497-513); `attn2` stays the 2-stream AttentionZero."""
     D = cfg.num_attention_heads * cfg.attention_head_dim
     dh = cfg.attention_head_dim
     Fi = 4 * D
@@ -99,7 +101,7 @@ def state_dict_manifest(cfg) -> "OrderedDict[str, Tuple[int, ...]]":
     lin("time_text_embed.text_embedder.linear_2", D, D)
     lin("context_embedder", cfg.caption_projection_dim, cfg.joint_attention_dim)
 
-    def attn(prefix, context_pre_only):
+    def attn(prefix, context_pre_only, with_ocr=False):
         # diffusers Attention ctor order, then AttentionZero's extra modules (attention.py:426-429)
         if cfg.qk_norm == "rms_norm":
             m[prefix + ".norm_q.weight"] = (dh,)
@@ -120,6 +122,11 @@ def state_dict_manifest(cfg) -> "OrderedDict[str, Tuple[int, ...]]":
         lin(prefix + ".to_k_control", D, D)
         lin(prefix + ".to_v_control", D, D)
         lin(prefix + ".to_out_control", D, D)
+        if with_ocr:
+            lin(prefix + ".to_q_ocr", D, D)
+            lin(prefix + ".to_k_ocr", D, D)
+            lin(prefix + ".to_v_ocr", D, D)
+            lin(prefix + ".to_out_ocr", D, D)
 
     for i in range(cfg.num_layers):
         b = f"transformer_blocks.{i}"
@@ -127,13 +134,17 @@ def state_dict_manifest(cfg) -> "OrderedDict[str, Tuple[int, ...]]":
         dual = i in cfg.dual_attention_layers
         lin(b + ".norm1.linear", (9 if dual else 6) * D, D)
         lin(b + ".norm1_context.linear", (2 if last else 6) * D, D)
-        attn(b + ".attn", last)
+        attn(b + ".attn", last, with_ocr=ocr)
         if dual:
             attn(b + ".attn2", last)  # Q5: owns unused add_*/to_add_out/norm_added_* parameters
         lin(b + ".ff.net.0.proj", Fi, D)
         lin(b + ".ff.net.2", D, Fi)
         m[b + ".ff.control_conv.weight"] = (Fi, 1, 3, 3)
         m[b + ".ff.control_conv.bias"] = (Fi,)
+        if ocr:
+            for cname in ("ocr_to_hidden_conv", "hidden_to_ocr_conv"):
+                m[b + f".ff.{cname}.weight"] = (Fi, 1, 3, 3)
+                m[b + f".ff.{cname}.bias"] = (Fi,)
         if not last:
             lin(b + ".ff_context.net.0.proj", Fi, D)
             lin(b + ".ff_context.net.2", D, Fi)
@@ -159,7 +170,7 @@ def sincos_pos_embed_2d(embed_dim: int, grid_size: int, base_size: int, interpol
     return torch.from_numpy(emb).float().unsqueeze(0)
 
 
-def init_state_dict(cfg, seed: int = 0, dtype=torch.float32) -> "OrderedDict[str, torch.Tensor]":
+def init_state_dict(cfg, seed: int = 0, dtype=torch.float32, ocr: bool = False) -> "OrderedDict[str, torch.Tensor]":
     """Random-init EVERY parameter, including the zero-initialised *_control / control_conv ones (Q4).
 
     Scales follow SURVEY.md 8d: Linear weights/biases N(0,0.02^2), conv weights N(0,0.1^2), RMSNorm weights
@@ -168,7 +179,7 @@ def init_state_dict(cfg, seed: int = 0, dtype=torch.float32) -> "OrderedDict[str
     g = torch.Generator().manual_seed(seed)
     D = cfg.num_attention_heads * cfg.attention_head_dim
     sd: "OrderedDict[str, torch.Tensor]" = OrderedDict()
-    for name, shape in state_dict_manifest(cfg).items():
+    for name, shape in state_dict_manifest(cfg, ocr=ocr).items():
         if name == "pos_embed.pos_embed":
             t = sincos_pos_embed_2d(D, cfg.pos_embed_max_size, cfg.sample_size // cfg.patch_size)
         elif ".norm_" in name and name.endswith(".weight") and len(shape) == 1 and shape[0] == cfg.attention_head_dim:
@@ -321,13 +332,84 @@ def feed_forward_control(sd, prefix, x):
     return _linear(sd, prefix + ".net.2", u)
 
 
+def joint_attention_ocr(sd, cfg, prefix, hidden_states, encoder_hidden_states=None, context_pre_only=False):
+    """JointAttnProcessor2_0_OCRBranch_OCR2HQ2OCR.__call__ (attention_ocrbranch_ocr2hq2ocr.py:520-664): three image
+    streams [HQ | LR | OCR] + text. key_control keeps quirk Q1 (:588); key_ocr = norm_k(to_k_ocr(to_k(ocr))) is live (:589)."""
+    H = cfg.num_attention_heads
+    B = hidden_states.shape[0]
+    residual = hidden_states
+    hq, lr, oc = hidden_states.chunk(3, dim=1)                                         # :542
+
+    def heads(t):
+        return t.view(B, -1, H, t.shape[-1] // H).transpose(1, 2)
+
+    def chain(x, a, b_):
+        return heads(_linear(sd, prefix + b_, _linear(sd, prefix + a, x)))
+
+    q, k, v = (heads(_linear(sd, prefix + n, hq)) for n in (".to_q", ".to_k", ".to_v"))   # :550-559
+    qc, kc, vc = chain(lr, ".to_q", ".to_q_control"), chain(lr, ".to_k", ".to_k_control"), chain(lr, ".to_v", ".to_v_control")
+    qo, ko, vo = chain(oc, ".to_q", ".to_q_ocr"), chain(oc, ".to_k", ".to_k_ocr"), chain(oc, ".to_v", ".to_v_ocr")
+    if cfg.qk_norm == "rms_norm":
+        wq, wk = sd[prefix + ".norm_q.weight"], sd[prefix + ".norm_k.weight"]
+        q, qc, qo = rms_norm(q, wq), rms_norm(qc, wq), rms_norm(qo, wq)                 # :582-585
+        k = rms_norm(k, wk)                                                              # :587
+        kc = rms_norm(k, wk)                                                             # :588 (Q1)
+        ko = rms_norm(ko, wk)                                                            # :589
+    if encoder_hidden_states is not None:
+        tq = heads(_linear(sd, prefix + ".add_q_proj", encoder_hidden_states))
+        tk = heads(_linear(sd, prefix + ".add_k_proj", encoder_hidden_states))
+        tv = heads(_linear(sd, prefix + ".add_v_proj", encoder_hidden_states))
+        if cfg.qk_norm == "rms_norm":
+            tq = rms_norm(tq, sd[prefix + ".norm_added_q.weight"])
+            tk = rms_norm(tk, sd[prefix + ".norm_added_k.weight"])
+        Q, K, V = torch.cat([q, qc, qo, tq], 2), torch.cat([k, kc, ko, tk], 2), torch.cat([v, vc, vo, tv], 2)   # :612-614
+    else:
+        Q, K, V = torch.cat([q, qc, qo], 2), torch.cat([k, kc, ko], 2), torch.cat([v, vc, vo], 2)
+    o = F.scaled_dot_product_attention(Q, K, V, dropout_p=0.0, is_causal=False)
+    o = o.transpose(1, 2).reshape(B, -1, Q.shape[1] * Q.shape[-1]).to(Q.dtype)
+    ctx_out = None
+    if encoder_hidden_states is not None:
+        o, ctx_out = o[:, : residual.shape[1]], o[:, residual.shape[1]:]
+        if not context_pre_only:
+            ctx_out = _linear(sd, prefix + ".to_add_out", ctx_out)
+    o_hq, o_lr, o_oc = o.chunk(3, dim=1)                                                # :642
+    o_lr = o_lr + lr                                                                    # :644
+    o_oc = o_oc + oc                                                                    # :645
+    out = torch.cat([_linear(sd, prefix + ".to_out.0", o_hq), _linear(sd, prefix + ".to_out_control", o_lr),
+                     _linear(sd, prefix + ".to_out_ocr", o_oc)], dim=1)                 # :648-656
+    if encoder_hidden_states is not None:
+        return out, ctx_out
+    return out
+
+
+def feed_forward_ocr2hq2ocr(sd, prefix, x):
+    """FeedForwardControl_OCR2HQ2OCR.forward (attention_ocrbranch_ocr2hq2ocr.py:164-211): LR->HQ and OCR->HQ convs,
+    then HQ(updated)->OCR conv."""
+    u = F.gelu(_linear(sd, prefix + ".net.0.proj", x), approximate="tanh")
+    u_hq, u_lr, u_oc = u.chunk(3, dim=1)                                                # :177
+    B, N, C = u_hq.shape
+    h = w = int(np.sqrt(N))
+    assert h * w == N
+
+    def conv(t, name):
+        t = t.reshape(B, h, w, C).permute(0, 3, 1, 2)
+        t = F.conv2d(t, sd[prefix + f".{name}.weight"], sd[prefix + f".{name}.bias"], padding=1, groups=C)
+        return t.reshape(B, C, N).permute(0, 2, 1)
+
+    u_hq = u_hq + 1.0 * conv(u_lr, "control_conv") + 1.0 * conv(u_oc, "ocr_to_hidden_conv")   # :184-196
+    u_oc = u_oc + 1.0 * conv(u_hq, "hidden_to_ocr_conv")                                       # :200-206
+    return _linear(sd, prefix + ".net.2", torch.cat([u_hq, u_lr, u_oc], dim=1))                # :210
+
+
 def feed_forward(sd, prefix, x):
     """FeedForward.forward (attention.py:94-100), gelu-approximate."""
     return _linear(sd, prefix + ".net.2", F.gelu(_linear(sd, prefix + ".net.0.proj", x), approximate="tanh"))
 
 
-def block_forward(sd, cfg, i, hidden_states, encoder_hidden_states, temb, as_written=True):
-    """JointTransformerBlock.forward (attention.py:280-398). Returns (encoder_hidden_states, hidden_states)."""
+def block_forward(sd, cfg, i, hidden_states, encoder_hidden_states, temb, as_written=True, ocr=False):
+    """JointTransformerBlock.forward (attention.py:280-398). Returns (encoder_hidden_states, hidden_states).
+    ocr=True: the 3-stream block (attention_ocrbranch_ocr2hq2ocr.py:317-433): `attn` is the 3-stream processor, `attn2`
+    stays the 2-stream processor and therefore splits the 3N tokens at 1.5N (quirk Q6, :354,:686), `ff` has 3 convs."""
     b = f"transformer_blocks.{i}"
     dual = i in cfg.dual_attention_layers
     last = i == cfg.num_layers - 1
@@ -350,13 +432,17 @@ def block_forward(sd, cfg, i, hidden_states, encoder_hidden_states, temb, as_wri
         c_shift_msa, c_scale_msa, c_gate_msa, c_shift_mlp, c_scale_mlp, c_gate_mlp = cemb.chunk(6, dim=1)
         nc = _layer_norm(encoder_hidden_states) * (1 + c_scale_msa[:, None]) + c_shift_msa[:, None]
 
-    attn_out, ctx_attn = joint_attention(sd, cfg, b + ".attn", n1, nc, context_pre_only=last, as_written=as_written)
+    if ocr:
+        attn_out, ctx_attn = joint_attention_ocr(sd, cfg, b + ".attn", n1, nc, context_pre_only=last)
+    else:
+        attn_out, ctx_attn = joint_attention(sd, cfg, b + ".attn", n1, nc, context_pre_only=last, as_written=as_written)
     hidden_states = hidden_states + gate_msa.unsqueeze(1) * attn_out                  # :314-315
     if dual:
         attn_out2 = joint_attention(sd, cfg, b + ".attn2", n2, None, as_written=as_written)   # :318
         hidden_states = hidden_states + gate_msa2.unsqueeze(1) * attn_out2           # :319-320
     m = _layer_norm(hidden_states) * (1 + scale_mlp[:, None]) + shift_mlp[:, None]   # :322-323
-    hidden_states = hidden_states + gate_mlp.unsqueeze(1) * feed_forward_control(sd, b + ".ff", m)  # :328-347
+    ff = feed_forward_ocr2hq2ocr if ocr else feed_forward_control
+    hidden_states = hidden_states + gate_mlp.unsqueeze(1) * ff(sd, b + ".ff", m)      # :328-347
     if last:
         encoder_hidden_states = None                                                  # :379
     else:
@@ -380,18 +466,20 @@ def unpatchify(x, cfg, height, width):
 
 
 def model_forward(sd, cfg, hidden_states, controlnet_image, encoder_hidden_states, pooled_projections, timestep,
-                  as_written=True, feat_extract_layers=(), feat_extract=None, return_block_states=False):
-    """SD3Transformer2DModel.forward. Returns velocity [B,C,h,w] (and optionally extras)."""
+                  as_written=True, feat_extract_layers=(), feat_extract=None, return_block_states=False, ocr=False):
+    """SD3Transformer2DModel.forward. Returns velocity [B,C,h,w] (and optionally extras).
+    ocr=True: SD3Transformer2DModel_OCRBranch_OCR2HQ2OCR.forward (transformer_sd3_ocrbranch_ocr2hq2ocr.py:269-410):
+    the third stream is a second pos_embed(controlnet_image) (:334-337); chunk(3) at the end (:384)."""
     height, width = hidden_states.shape[-2:]
     x = patch_embed(sd, cfg, hidden_states)                                           # :326
     temb = time_text_embed(sd, timestep, pooled_projections)                          # :327
     ctx = _linear(sd, "context_embedder", encoder_hidden_states)                     # :328
     lr = patch_embed(sd, cfg, controlnet_image)                                       # :331
-    x = torch.cat([x, lr], dim=-2)                                                    # :332
+    x = torch.cat([x, lr, patch_embed(sd, cfg, controlnet_image)] if ocr else [x, lr], dim=-2)   # :332 / ocr :334-337
     feats: List[torch.Tensor] = []
     states = []
     for i in range(cfg.num_layers):                                                   # :336-370
-        ctx, x = block_forward(sd, cfg, i, x, ctx, temb, as_written=as_written)
+        ctx, x = block_forward(sd, cfg, i, x, ctx, temb, as_written=as_written, ocr=ocr)
         if i in feat_extract_layers:                                                  # attention.py:353-374 (Q10)
             if feat_extract == "hq_feat":
                 feats.append(x[:, 0:1024])
@@ -399,9 +487,11 @@ def model_forward(sd, cfg, hidden_states, controlnet_image, encoder_hidden_state
                 feats.append(x[:, 1024:2048])
             elif feat_extract == "hqlq_feat":
                 feats.append(x[:, 0:2048])
+            elif feat_extract == "ocr_feat" and ocr:
+                feats.append(x[:, 2048:3072])
         if return_block_states:
             states.append((x.clone(), None if ctx is None else ctx.clone()))
-    x, _ = x.chunk(2, dim=1)                                                          # :379
+    x = x.chunk(3 if ocr else 2, dim=1)[0]                                            # :379 / ocr :384
     emb = _linear(sd, "norm_out.linear", F.silu(temb).to(x.dtype))                    # :382 AdaLayerNormContinuous
     scale, shift = emb.chunk(2, dim=1)                                                # (scale, shift) order, Q12
     x = _layer_norm(x) * (1 + scale)[:, None, :] + shift[:, None, :]

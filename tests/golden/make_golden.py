@@ -30,8 +30,11 @@ def ref_cfg(feat_layers=(), feat="hq_feat", ts=False):
                                                                        feat_extract=feat)))
 
 
-def run_reference(cfg, sd, inputs):
-    from model_dit4sr.transformer_sd3 import SD3Transformer2DModel
+def run_reference(cfg, sd, inputs, ocr=False):
+    if ocr:
+        from model_dit4sr.transformer_sd3_ocrbranch_ocr2hq2ocr import SD3Transformer2DModel_OCRBranch_OCR2HQ2OCR as SD3Transformer2DModel
+    else:
+        from model_dit4sr.transformer_sd3 import SD3Transformer2DModel
     m = SD3Transformer2DModel(**vars(cfg)).eval()
     m.load_state_dict(sd, strict=True)
     hs, lr, enc, pooled, t = inputs
@@ -48,14 +51,19 @@ def main():
         ("tiny_qknorm_dual", dict(), 2, 16, 16, 13, 741.44),
         ("tiny_noqknorm", dict(qk_norm=None, dual_attention_layers=()), 1, 8, 8, 5, 1000.0),
         ("tiny_t9", dict(), 1, 16, 16, 13, 8.93),
+        # 3-stream OCR-branch model (transformer_sd3_ocrbranch_ocr2hq2ocr.py)
+        ("tiny_ocr_qknorm_dual", dict(), 2, 16, 16, 13, 741.44),
+        ("tiny_ocr_noqknorm", dict(qk_norm=None, dual_attention_layers=()), 1, 8, 8, 5, 500.0),
     ]
     for name, kw, B, h, w, T, ts in cases:
+        ocr = "_ocr_" in name
         cfg = O.tiny_config(**kw)
-        sd = O.init_state_dict(cfg, seed=0)
+        sd = O.init_state_dict(cfg, seed=0, ocr=ocr)
         inputs = O.make_inputs(cfg, B, h, w, T, seed=1, timestep=ts)
-        y = run_reference(cfg, sd, inputs)
+        y = run_reference(cfg, sd, inputs, ocr=ocr)
         out[name + ".velocity"] = y.contiguous()
-        meta["cases"].append(dict(name=name, cfg_kwargs={k: (list(v) if isinstance(v, tuple) else v) for k, v in kw.items()},
+        meta["cases"].append(dict(name=name, ocr=ocr,
+                                  cfg_kwargs={k: (list(v) if isinstance(v, tuple) else v) for k, v in kw.items()},
                                   batch=B, height=h, width=w, text_tokens=T, timestep=ts, weight_seed=0, input_seed=1))
     save_file(out, os.path.join(HERE, "reference_tiny.safetensors"))
 
@@ -74,6 +82,10 @@ def main():
         full = SD3Transformer2DModel(**vars(O.sd35_medium_config(pos_embed_max_size=4, sample_size=8)))
     meta["full_manifest_note"] = "pos_embed_max_size shrunk to 4 to keep ctor cheap; other shapes are SD3.5-medium"
     meta["full_manifest"] = {k: list(v.shape) for k, v in full.state_dict().items()}
+    from model_dit4sr.transformer_sd3_ocrbranch_ocr2hq2ocr import SD3Transformer2DModel_OCRBranch_OCR2HQ2OCR
+    with torch.device("meta"):
+        full = SD3Transformer2DModel_OCRBranch_OCR2HQ2OCR(**vars(O.sd35_medium_config(pos_embed_max_size=4, sample_size=8)))
+    meta["full_manifest_ocr"] = {k: list(v.shape) for k, v in full.state_dict().items()}
     json.dump(meta, open(os.path.join(HERE, "reference_meta.json"), "w"), indent=1)
     print("wrote", len(out), "tensors;", len(meta["full_manifest"]), "manifest keys")
 

@@ -23,9 +23,10 @@ def rel(a, b):
     return ((a - b).norm() / (b.norm() + 1e-30)).item()
 
 
-def build(cfg, sd, dtype=torch.bfloat16):
+def build(cfg, sd, dtype=torch.bfloat16, ocr=False):
     import dit4sr_b200
-    m = dit4sr_b200.SD3Transformer2DModel(**vars(cfg))
+    cls = dit4sr_b200.SD3Transformer2DModel_OCRBranch_OCR2HQ2OCR if ocr else dit4sr_b200.SD3Transformer2DModel
+    m = cls(**vars(cfg))
     m.load_state_dict(sd)
     return m.to("cuda", dtype).requires_grad_(False).eval()
 
@@ -46,21 +47,40 @@ META = json.load(open(os.path.join(GOLD, "reference_meta.json")))
 def test_tiny_model_matches_reference_golden(case):
     """The committed outputs of the reference's own model code (fp32) vs the bf16 CUDA path."""
     ref = load_file(os.path.join(GOLD, "reference_tiny.safetensors"))[case["name"] + ".velocity"]
+    ocr = case.get("ocr", False)
     cfg = O.tiny_config(**case["cfg_kwargs"])
-    sd = O.init_state_dict(cfg, seed=case["weight_seed"])
+    sd = O.init_state_dict(cfg, seed=case["weight_seed"], ocr=ocr)
     inputs = O.make_inputs(cfg, case["batch"], case["height"], case["width"], case["text_tokens"],
                            seed=case["input_seed"], timestep=case["timestep"])
-    y = run(build(cfg, sd), inputs)
+    y = run(build(cfg, sd, ocr=ocr), inputs)
     assert y.shape == ref.shape
     assert rel(y, ref) <= VEL_TOL
 
 
-def _oracle_gpu(sd, cfg, inputs, dtype):
+def _oracle_gpu(sd, cfg, inputs, dtype, ocr=False):
     sdg = {k: v.cuda().to(dtype) for k, v in sd.items()}
     hs, lr, enc, pooled, t = inputs
     with torch.no_grad():
         return O.model_forward(sdg, cfg, hs.cuda().to(dtype), lr.cuda().to(dtype), enc.cuda().to(dtype),
-                               pooled.cuda().to(dtype), t.cuda(), as_written=False).float().cpu()
+                               pooled.cuda().to(dtype), t.cuda(), as_written=False, ocr=ocr).float().cpu()
+
+
+def test_ocr_branch_model_full_width():
+    """BASELINE config #5 shape family: 3-stream OCR2HQ2OCR model, full width, 4 blocks (2 dual -> exercises the Q6
+    half-split of attn2), 512px, B=1; returns (output, trans_blk_outs) like the reference."""
+    cfg = O.sd35_medium_config(num_layers=4, dual_attention_layers=(0, 1), pos_embed_max_size=96)
+    sd = O.init_state_dict(cfg, seed=0, ocr=True)
+    inputs = O.make_inputs(cfg, 1, 64, 64, 333, seed=1, timestep=600.0)
+    ref32 = _oracle_gpu(sd, cfg, inputs, torch.float32, ocr=True)
+    m = build(cfg, sd, ocr=True)
+    hs, lr, enc, pooled, t = inputs
+    bf = torch.bfloat16
+    with torch.no_grad():
+        out = m(hs.cuda().to(bf), lr.cuda().to(bf), enc.cuda().to(bf), pooled.cuda().to(bf), t.cuda(), return_dict=False)
+    assert isinstance(out, tuple) and len(out) == 2 and out[1] == []
+    e = rel(out[0].float().cpu(), ref32)
+    print(f"ocr model: cuda-vs-fp32 {e:.3e}")
+    assert e <= VEL_TOL
 
 
 @pytest.mark.parametrize("timestep", [1000.0, 741.44, 8.93])

@@ -18,11 +18,12 @@ REF = load_file(os.path.join(GOLD, "reference_tiny.safetensors"))
 @pytest.mark.parametrize("as_written", [True, False])
 def test_oracle_matches_reference_golden(case, as_written):
     """fp32, tolerance 1e-6 abs (bit-exact in the generating container; slack for other BLAS builds)."""
+    ocr = case.get("ocr", False)
     cfg = O.tiny_config(**case["cfg_kwargs"])
-    sd = O.init_state_dict(cfg, seed=case["weight_seed"])
+    sd = O.init_state_dict(cfg, seed=case["weight_seed"], ocr=ocr)
     inp = O.make_inputs(cfg, case["batch"], case["height"], case["width"], case["text_tokens"],
                         seed=case["input_seed"], timestep=case["timestep"])
-    y = O.model_forward(sd, cfg, *inp, as_written=as_written)
+    y = O.model_forward(sd, cfg, *inp, as_written=as_written, ocr=ocr)
     ref = REF[case["name"] + ".velocity"]
     assert y.shape == ref.shape
     assert (y - ref).abs().max().item() <= 1e-6
@@ -44,6 +45,27 @@ def test_manifest_matches_reference_ctor_full_shape():
     assert list(man.keys()) == list(ref.keys())
     for k, shp in man.items():
         assert list(shp) == ref[k], k
+
+
+def test_manifest_matches_reference_ctor_full_shape_ocr():
+    cfg = O.sd35_medium_config(pos_embed_max_size=4, sample_size=8)
+    man = O.state_dict_manifest(cfg, ocr=True)
+    ref = META["full_manifest_ocr"]
+    assert list(man.keys()) == list(ref.keys())
+    for k, shp in man.items():
+        assert list(shp) == ref[k], k
+
+
+def test_ocr_attn2_splits_three_streams_in_half():
+    """Q6: attn2 of the OCR model is the 2-stream processor fed 3N tokens -> halves of 1.5N. Feeding the 2-stream oracle
+    attention a [1.5N | 1.5N] input must equal what the OCR block computes for attn2."""
+    cfg = O.tiny_config()
+    sd = O.init_state_dict(cfg, ocr=True)
+    x = torch.randn(1, 3 * 16, 128)
+    a = O.joint_attention(sd, cfg, "transformer_blocks.0.attn2", x, None)
+    hq, lr = x[:, :24], x[:, 24:]
+    b = O.joint_attention(sd, cfg, "transformer_blocks.0.attn2", torch.cat([hq, lr], 1), None)
+    assert a.shape == (1, 48, 128) and torch.equal(a, b)
 
 
 def test_dead_key_chain_elision_is_exact_fp64():
