@@ -19,7 +19,8 @@ class LnModulateParams(C.Structure):
 class DwconvParams(C.Structure):
     _fields_ = [("u_hq", c_vp), ("u_lr", c_vp), ("ld", c_i64), ("hq_batch_stride", c_i64),
                 ("lr_batch_stride", c_i64), ("weight9", c_vp), ("bias", c_vp),
-                ("batches", c_int), ("grid", c_int), ("channels", c_int)]
+                ("batches", c_int), ("grid", c_int), ("channels", c_int),
+                ("grid_w", c_int), ("lr_grid_h", c_int), ("lr_row_offset", c_int)]
 
 
 class GemmParams(C.Structure):
@@ -55,6 +56,7 @@ SYMBOLS = {
     "dit4sr_unpatchify": (c_int, [c_vp, c_vp, c_int, c_vp, c_float, c_int, c_int, c_int, c_int, c_vp]),
     "dit4sr_timestep_features": (c_int, [c_vp, c_vp, c_int, c_vp]),
     "dit4sr_silu_cast": (c_int, [c_vp, c_vp, c_i64, c_vp]),
+    "dit4sr_add_bf16": (c_int, [c_vp, c_i64, c_i64, c_vp, c_i64, c_i64, c_int, c_int, c_int, c_vp]),
     "dit4sr_cast": (c_int, [c_vp, c_vp, c_i64, c_int, c_vp]),
 }
 

@@ -23,7 +23,7 @@ struct Args {
   int64_t ld, hq_batch_stride;
   const float* weight9;
   const float* bias;
-  int grid, channels, x_tiles, y_tiles;
+  int grid_h, grid_w, lr_row_offset, channels, x_tiles, y_tiles;
 };
 
 __device__ __forceinline__ void unpack8(const uint4& u, float* f) {
@@ -55,7 +55,8 @@ dwconv3x3_kernel(const __grid_constant__ CUtensorMap tmLR, const Args a) {
     ptx::mbar_init(&bar, 1);
     ptx::fence_barrier_init();
     ptx::mbar_expect_tx(&bar, TILE_BYTES);
-    ptx::tma_load_4d(tile, &tmLR, &bar, c_base, x0 - 1, y0 - 1, b);   // negative / past-the-end coords read as zero
+    // negative / past-the-end coordinates read as zero: the conv's zero padding
+    ptx::tma_load_4d(tile, &tmLR, &bar, c_base, x0 - 1, y0 - 1 + a.lr_row_offset, b);
   }
 
   // weights + bias for this thread's 8 channels (L2-resident, 221 KB for F=6144)
@@ -77,19 +78,19 @@ dwconv3x3_kernel(const __grid_constant__ CUtensorMap tmLR, const Args a) {
   __syncthreads();   // barrier init visible to all waiters
 
   __nv_bfloat16* hq = a.u_hq + (int64_t)b * a.hq_batch_stride + c0;
-  const int G = a.grid;
+  const int GH = a.grid_h, GW = a.grid_w;
 
 #pragma unroll 1
   for (int half = 0; half < 2; ++half) {
     const int lx = px + half * 16;         // column inside the tile
     const int x = x0 + lx;
-    const bool col_ok = c_ok && x < G;
+    const bool col_ok = c_ok && x < GW;
     // HQ values of this column (issued before the TMA wait)
     uint4 hv[TY];
 #pragma unroll
     for (int r = 0; r < TY; ++r) {
       const int y = y0 + r;
-      hv[r] = (col_ok && y < G) ? *reinterpret_cast<const uint4*>(hq + ((int64_t)y * G + x) * a.ld) : make_uint4(0, 0, 0, 0);
+      hv[r] = (col_ok && y < GH) ? *reinterpret_cast<const uint4*>(hq + ((int64_t)y * GW + x) * a.ld) : make_uint4(0, 0, 0, 0);
     }
     if (half == 0) ptx::mbar_wait(&bar, 0);
     if (!col_ok) continue;
@@ -107,7 +108,7 @@ dwconv3x3_kernel(const __grid_constant__ CUtensorMap tmLR, const Args a) {
       for (int dx = 0; dx < 3; ++dx)
         win[2][dx] = *reinterpret_cast<const uint4*>(sbase + ((size_t)(r + 2) * BX + dx) * (CH * 2));
       const int y = y0 + r;
-      if (y < G) {
+      if (y < GH) {
         float acc[8], t[8];
         unpack8(hv[r], acc);
 #pragma unroll
@@ -125,7 +126,7 @@ dwconv3x3_kernel(const __grid_constant__ CUtensorMap tmLR, const Args a) {
         o.y = ptx::pack_bf16(acc[2], acc[3]);
         o.z = ptx::pack_bf16(acc[4], acc[5]);
         o.w = ptx::pack_bf16(acc[6], acc[7]);
-        *reinterpret_cast<uint4*>(hq + ((int64_t)y * G + x) * a.ld) = o;
+        *reinterpret_cast<uint4*>(hq + ((int64_t)y * GW + x) * a.ld) = o;
       }
 #pragma unroll
       for (int dx = 0; dx < 3; ++dx) {
@@ -152,10 +153,13 @@ extern "C" int dit4sr_dwconv3x3_add(const dit4sr_dwconv3x3_params* p, void* stre
   int rc = dit4sr_check_device();
   if (rc != 0) return rc;
 
+  const int gw = p->grid_w > 0 ? p->grid_w : p->grid;
+  const int lr_h = p->lr_grid_h > 0 ? p->lr_grid_h : p->grid;
+  DIT4SR_REQUIRE(p->grid_w >= 0 && p->lr_grid_h >= 0, DIT4SR_E_BADARG, "dwconv: negative grid extents");
   CUtensorMap tm;
-  const uint64_t dims[4] = {(uint64_t)p->channels, (uint64_t)p->grid, (uint64_t)p->grid, (uint64_t)p->batches};
-  const uint64_t strides[3] = {(uint64_t)p->ld * 2, (uint64_t)p->ld * 2 * p->grid,
-                               (uint64_t)(p->batches > 1 ? p->lr_batch_stride : p->ld * (int64_t)p->grid * p->grid) * 2};
+  const uint64_t dims[4] = {(uint64_t)p->channels, (uint64_t)gw, (uint64_t)lr_h, (uint64_t)p->batches};
+  const uint64_t strides[3] = {(uint64_t)p->ld * 2, (uint64_t)p->ld * 2 * gw,
+                               (uint64_t)(p->batches > 1 ? p->lr_batch_stride : p->ld * (int64_t)gw * lr_h) * 2};
   const uint32_t box[4] = {CH, BX, BY, 1};
   if ((rc = host::make_tmap_bf16_noswizzle(&tm, p->u_lr, 4, dims, strides, box)) != 0) return rc;
 
@@ -165,9 +169,11 @@ extern "C" int dit4sr_dwconv3x3_add(const dit4sr_dwconv3x3_params* p, void* stre
   a.hq_batch_stride = p->hq_batch_stride;
   a.weight9 = p->weight9;
   a.bias = p->bias;
-  a.grid = p->grid;
+  a.grid_h = p->grid;
+  a.grid_w = gw;
+  a.lr_row_offset = p->lr_row_offset;
   a.channels = p->channels;
-  a.x_tiles = (p->grid + TX - 1) / TX;
+  a.x_tiles = (gw + TX - 1) / TX;
   a.y_tiles = (p->grid + TY - 1) / TY;
   dim3 grid((p->channels + CH - 1) / CH, a.x_tiles * a.y_tiles, p->batches);
   dwconv3x3_kernel<<<grid, THREADS, 0, stream>>>(tm, a);

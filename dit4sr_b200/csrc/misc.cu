@@ -73,6 +73,27 @@ __global__ void cast_b2f_kernel(const __nv_bfloat16* __restrict__ x, float* __re
   if (i < n) y[i] = __bfloat162float(x[i]);
 }
 
+// one thread per 8 bf16 (16 bytes)
+__global__ void add_bf16_kernel(__nv_bfloat16* __restrict__ dst, int64_t drs, int64_t dbs,
+                                const __nv_bfloat16* __restrict__ src, int64_t srs, int64_t sbs, int B, int R, int C8) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (int64_t)B * R * C8) return;
+  const int c = (int)(i % C8);
+  const int r = (int)((i / C8) % R);
+  const int b = (int)(i / ((int64_t)C8 * R));
+  uint4* d = reinterpret_cast<uint4*>(dst + b * dbs + r * drs) + c;
+  const uint4 s4 = *(reinterpret_cast<const uint4*>(src + b * sbs + r * srs) + c);
+  uint4 d4 = *d;
+  __nv_bfloat162* dp = reinterpret_cast<__nv_bfloat162*>(&d4);
+  const __nv_bfloat162* sp = reinterpret_cast<const __nv_bfloat162*>(&s4);
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const float2 a = __bfloat1622float2(dp[k]), bb = __bfloat1622float2(sp[k]);
+    dp[k] = __floats2bfloat162_rn(a.x + bb.x, a.y + bb.y);
+  }
+  *d = d4;
+}
+
 static inline unsigned blocks(int64_t n, int t) { return (unsigned)((n + t - 1) / t); }
 
 }  // namespace misc
@@ -127,6 +148,21 @@ int dit4sr_silu_cast(const float* x, void* y_bf16, int64_t n, void* stream_) {
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
   DIT4SR_REQUIRE(x && y_bf16 && n > 0, DIT4SR_E_BADARG, "silu_cast: bad argument");
   misc::silu_cast_kernel<<<misc::blocks(n, 256), 256, 0, stream>>>(x, (__nv_bfloat16*)y_bf16, n);
+  DIT4SR_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int dit4sr_add_bf16(void* dst, int64_t dst_row_stride, int64_t dst_batch_stride, const void* src, int64_t src_row_stride,
+                    int64_t src_batch_stride, int batches, int rows, int cols, void* stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  DIT4SR_REQUIRE(dst && src && batches > 0 && rows > 0 && cols > 0, DIT4SR_E_BADARG, "add_bf16: bad argument");
+  DIT4SR_REQUIRE(cols % 8 == 0 && dst_row_stride % 8 == 0 && src_row_stride % 8 == 0 && dst_batch_stride % 8 == 0 &&
+                     src_batch_stride % 8 == 0 && host::aligned16(dst) && host::aligned16(src),
+                 DIT4SR_E_ALIGN, "add_bf16: 16-byte alignment required");
+  const int64_t n = (int64_t)batches * rows * (cols / 8);
+  misc::add_bf16_kernel<<<misc::blocks(n, 256), 256, 0, stream>>>((__nv_bfloat16*)dst, dst_row_stride, dst_batch_stride,
+                                                                  (const __nv_bfloat16*)src, src_row_stride,
+                                                                  src_batch_stride, batches, rows, cols / 8);
   DIT4SR_CUDA(cudaGetLastError());
   return 0;
 }

@@ -105,13 +105,14 @@ class _BlockPack:
 
 
 class Engine:
-    def __init__(self, model, fold_lr_chains: Optional[bool] = None):
+    def __init__(self, model, fold_lr_chains: Optional[bool] = None, sp=None):
         """fold_lr_chains: fold `to_x_control(to_x(.))` into one GEMM per projection (exact algebra, one bf16 rounding
         of the product weight instead of a bf16 intermediate activation). Default on; DIT4SR_FOLD_LR=0 turns it off."""
         import os
         if fold_lr_chains is None:
             fold_lr_chains = os.environ.get("DIT4SR_FOLD_LR", "1") != "0"
         self.fold_lr_chains = fold_lr_chains
+        self.sp = sp    # parallel.SequenceParallel or None: Ulysses sequence parallelism over the token-grid rows
         self.streams = 3 if getattr(model, "_ocr_branch", False) else 2   # image streams: [HQ | LR] or [HQ | LR | OCR]
         cfg = model.config
         self.cfg = cfg
@@ -191,8 +192,8 @@ class Engine:
             self._pos[key] = pe.reshape(1, hp * wp, -1).to(device=device, dtype=torch.float32).contiguous()
         return self._pos[key]
 
-    def _workspace(self, B, N, T, device):
-        key = (B, N, T, str(device))
+    def _workspace(self, B, N, T, device, grid_w=0):
+        key = (B, N, T, str(device), grid_w)
         ws = self._ws.get(key)
         if ws is not None:
             return ws
@@ -215,6 +216,11 @@ class Engine:
             patches=e(B, N, 4 * self.cfg.in_channels), tok=e(B, N, 4 * self.cfg.out_channels, dtype=f32),
             t=e(B, dtype=f32),
         )
+        if self.sp is not None:   # attention-side buffers of the head<->sequence exchange + halo-padded LR hidden state
+            P = self.sp.world
+            Dl = D // P
+            ws.update(qkv_sp=e(B, P * I + T, 3, Dl), o_sp=e(B, P * I + T, Dl),
+                      lr_pad=e(B, N + 2 * grid_w, F))
         self._ws[key] = ws
         return ws
 
@@ -260,9 +266,12 @@ class Engine:
         if g2:
             R("lr2_group", ops.gemm_grouped, g2)
         # the last block's text queries are discarded by the reference (context_pre_only): do not compute them
-        seq_q = I if (last or not ap.has_text) else S
-        R("attn", ops.attention, qkv[:, :S, :D], qkv[:, :S, D:2 * D], qkv[:, :S, 2 * D:], o, H, seq_q=seq_q,
-          lr_res=n_in, lr_rows=(N, I))       # Q2: the LR (and OCR) rows get their normed+modulated input added back
+        if self.sp is None:
+            seq_q = I if (last or not ap.has_text) else S
+            R("attn", ops.attention, qkv[:, :S, :D], qkv[:, :S, D:2 * D], qkv[:, :S, 2 * D:], o, H, seq_q=seq_q,
+              lr_res=n_in, lr_rows=(N, I))   # Q2: the LR (and OCR) rows get their normed+modulated input added back
+        else:
+            self._attention_sp(ap, ws, n_in, N, I, S, last)
         G = ops.EPI_GATE_RESID
         g3 = [dict(A=o[:, :N], W=ap.out.w, bias=ap.out.b, out=x[:, :N], epilogue=G, gate=gate),
               dict(A=o[:, N:2 * N], W=ap.outc.w, bias=ap.outc.b, out=x[:, N:2 * N], epilogue=G, gate=gate)]
@@ -271,6 +280,38 @@ class Engine:
         if ap.has_text and not last:
             g3.append(dict(A=o[:, I:S], W=ap.add_out.w, bias=ap.add_out.b, out=ctx, epilogue=G, gate=c_gate))
         R("out_group", ops.gemm_grouped, g3)
+
+    def _attention_sp(self, ap, ws, n_in, N, I, S, last):
+        """Ulysses: all-to-all (tokens -> heads), local attention on H/P heads over the whole joint sequence,
+        all-to-all back, all-gather of the text rows over heads (parallel.SequenceParallel)."""
+        sp, R, H = self.sp, self._run, self.H
+        P = sp.world
+        Hl = H // P
+        Dl = Hl * 64
+        qkv, o, qs, os_ = ws["qkv"], ws["o"], ws["qkv_sp"], ws["o_sp"]
+        B = qkv.shape[0]
+        T = S - I
+        xs = sp.seq_to_heads(qkv[:, :I].reshape(B, I, 3, H, 64))           # [B, P*I, 3, Hl, 64] rank-major tokens
+        qs[:, :P * I] = xs.reshape(B, P * I, 3, Dl)
+        if T:
+            h0, h1 = sp.head_slice(H)
+            qs[:, P * I:P * I + T] = qkv[:, I:S].reshape(B, T, 3, H, 64)[:, :, :, h0:h1].reshape(B, T, 3, Dl)
+        Ssp = P * I + T
+        seq_q = P * I if (last or not T) else Ssp
+        R("attn", ops.attention, qs[:, :Ssp, 0], qs[:, :Ssp, 1], qs[:, :Ssp, 2], os_, Hl, seq_q=seq_q)
+        o[:, :I] = sp.heads_to_seq(os_[:, :P * I])
+        if T and not last:
+            o[:, I:S] = sp.gather_heads(os_[:, P * I:Ssp])
+        R("attn", ops.add_bf16, o[:, N:I], n_in[:, N:I])                    # Q2 residual on the LR (and OCR) rows
+
+    def _conv_add(self, ws, dst, src, w9, b, rows, grid_w):
+        """dst += dwconv3x3(src) + b on a (rows x grid_w) token grid; with sequence parallelism the source rows get a
+        1-row halo from the neighbouring ranks first."""
+        if self.sp is None:
+            self._run("dwconv", ops.dwconv3x3_add, dst, src, w9, b, rows, grid_w=grid_w)
+        else:
+            padded = self.sp.halo_rows(src, grid_w, out=ws["lr_pad"])
+            self._run("dwconv", ops.dwconv3x3_add, dst, padded, w9, b, rows, grid_w=grid_w, lr_row_offset=1)
 
     # ------------------------------------------------------------------------------------------------ forward
     @torch.no_grad()
@@ -282,14 +323,27 @@ class Engine:
             raise ValueError("dit4sr_b200: square, even latents only (reference asserts a square token grid, "
                              "attention.py:169-172)")
         grid = h // 2
-        N = grid * grid
+        rows = grid                     # token-grid rows handled by this rank
+        pos = self._pos_crop(grid, grid, hidden_states.device)
+        full_out, full_euler = out, euler
+        if self.sp is not None:         # Ulysses: this rank keeps grid/P contiguous rows of every image stream
+            if self.H % self.sp.world:
+                raise ValueError(f"{self.H} heads do not divide over {self.sp.world} ranks")
+            g0, g1 = self.sp.row_slice(grid)
+            rows = g1 - g0
+            hidden_states = hidden_states[:, :, 2 * g0:2 * g1].contiguous()
+            controlnet_image = controlnet_image[:, :, 2 * g0:2 * g1].contiguous()
+            pos = pos[:, g0 * grid:g1 * grid]
+            out = None
+            if euler is not None:
+                euler = (euler[0][:, :, 2 * g0:2 * g1].contiguous(), euler[1])
+        N = rows * grid
         if self.streams == 3 and (3 * N) % 2:
             raise ValueError("3-stream model: attn2 halves the 3N image tokens, N must be even")
         T = encoder_hidden_states.shape[1]
         dev = hidden_states.device
-        ws = self._workspace(B, N, T, dev)
+        ws = self._workspace(B, N, T, dev, grid_w=grid if self.sp is not None else 0)
         x, ctx, n1, n2, nc, mod = ws["x"], ws["ctx"], ws["n1"], ws["n2"], ws["nc"], ws["mod"]
-        pos = self._pos_crop(grid, grid, dev)
 
         # ---- head: temb = MLP(sincos(t)) + MLP(pooled)  (CombinedTimestepTextProjEmbeddings, transformer_sd3.py:327)
         ws["t"].copy_(timestep.to(device=dev, dtype=torch.float32).expand(B))
@@ -349,10 +403,10 @@ class Engine:
                                 gate=c_gate_mlp))
             R("ff1", ops.gemm_grouped, ff1)
             u = ws["u"]
-            R("dwconv", ops.dwconv3x3_add, u[:, :N], u[:, N:2 * N], bp.conv_w9, bp.conv_b, grid)
+            self._conv_add(ws, u[:, :N], u[:, N:2 * N], bp.conv_w9, bp.conv_b, rows, grid)
             if bp.ocr:   # u_hq += conv_o(u_ocr); then u_ocr += conv_h(u_hq updated)  (ocr attention file :184-206)
-                R("dwconv", ops.dwconv3x3_add, u[:, :N], u[:, 2 * N:], bp.conv_o_w9, bp.conv_o_b, grid)
-                R("dwconv", ops.dwconv3x3_add, u[:, 2 * N:], u[:, :N], bp.conv_h_w9, bp.conv_h_b, grid)
+                self._conv_add(ws, u[:, :N], u[:, 2 * N:], bp.conv_o_w9, bp.conv_o_b, rows, grid)
+                self._conv_add(ws, u[:, 2 * N:], u[:, :N], bp.conv_h_w9, bp.conv_h_b, rows, grid)
             R("ff2", ops.gemm_grouped, ff2)
             if feat_hook is not None:
                 feat_hook(i, x)
@@ -362,10 +416,16 @@ class Engine:
         R("tail", ops.ln_modulate, x[:, :N], mod[:, so + D: so + 2 * D], mod[:, so: so + D], n1[:, :N])
         R("tail", ops.gemm, n1[:, :N], self.proj_out.w, self.proj_out.b, ws["tok"], ops.EPI_BIAS)
         if out is None:
-            out = torch.empty(B, cfg.out_channels, h, w, device=dev, dtype=hidden_states.dtype)
+            out = torch.empty(B, cfg.out_channels, 2 * rows, w, device=dev, dtype=hidden_states.dtype)
         if euler is not None:
             latents, dsigma = euler
             R("tail", ops.unpatchify, ws["tok"], out, latents=latents, dsigma=dsigma)
         else:
             R("tail", ops.unpatchify, ws["tok"], out)
+        if self.sp is not None:        # every rank returns the whole image (row strips gathered)
+            gathered = self.sp.gather_rows(out, dim=2)
+            if full_out is not None:
+                full_out.copy_(gathered)
+                return full_out
+            return gathered
         return out

@@ -71,21 +71,39 @@ def ln_modulate(x, shift, scale, out, shift2=None, scale2=None, out2=None, eps=1
     _count()
 
 
-def dwconv3x3_add(u_hq, u_lr, weight9, bias, grid):
-    """u_hq[b, y*grid+x, c] += bias[c] + dwconv3x3(u_lr)[...]; u_* bf16 [B, grid*grid, C] views of the MLP hidden state."""
+def dwconv3x3_add(u_hq, u_lr, weight9, bias, grid, grid_w=0, lr_row_offset=0):
+    """u_hq[b, y*W+x, c] += bias[c] + dwconv3x3(u_lr)[...]; u_* bf16 views of the MLP hidden state, channels innermost.
+
+    Square case: u_hq, u_lr [B, grid*grid, C]. Row-sharded case (sequence parallelism): u_hq [B, grid*grid_w, C] holds
+    `grid` rows of `grid_w` columns, u_lr [B, lr_rows*grid_w, C] holds the LR rows including halo rows, and u_hq row 0 lies
+    over u_lr row `lr_row_offset`."""
     _req(u_hq, torch.bfloat16, "u_hq")
     _req(u_lr, torch.bfloat16, "u_lr")
     _req(weight9, torch.float32, "weight9")
     _req(bias, torch.float32, "bias")
     B, N, Cc = u_hq.shape
-    if N != grid * grid or u_lr.shape != u_hq.shape or u_hq.stride(1) != u_lr.stride(1):
-        raise _lib.Dit4srError("dwconv3x3_add: shape mismatch (token grid must be square, attention.py:169-172)")
+    W = grid_w or grid
+    if N != grid * W or u_lr.shape[1] % W or u_lr.shape[0] != B or u_lr.shape[2] != Cc or u_hq.stride(1) != u_lr.stride(1):
+        raise _lib.Dit4srError("dwconv3x3_add: shape mismatch (token grid must be rows x columns, attention.py:169-172)")
     p = DwconvParams()
     p.u_hq, p.u_lr, p.ld = _ptr(u_hq), _ptr(u_lr), u_hq.stride(1)
     p.hq_batch_stride, p.lr_batch_stride = u_hq.stride(0), u_lr.stride(0)
     p.weight9, p.bias = _ptr(weight9), _ptr(bias)
     p.batches, p.grid, p.channels = B, grid, Cc
+    p.grid_w, p.lr_grid_h, p.lr_row_offset = W, u_lr.shape[1] // W, lr_row_offset
     check(_lib.load().dit4sr_dwconv3x3_add(C.byref(p), _stream()), "dit4sr_dwconv3x3_add")
+    _count()
+
+
+def add_bf16(dst, src):
+    """dst += src for bf16 [B, R, C] views (innermost contiguous)."""
+    _req(dst, torch.bfloat16, "dst")
+    _req(src, torch.bfloat16, "src")
+    if dst.shape != src.shape or dst.dim() != 3:
+        raise _lib.Dit4srError("add_bf16: shapes must match ([B, R, C])")
+    B, Rr, Cc = dst.shape
+    check(_lib.load().dit4sr_add_bf16(_ptr(dst), dst.stride(1), dst.stride(0), _ptr(src), src.stride(1), src.stride(0),
+                                      B, Rr, Cc, _stream()), "dit4sr_add_bf16")
     _count()
 
 

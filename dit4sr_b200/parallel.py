@@ -46,3 +46,108 @@ def dp_denoise(denoise_fn: Callable, latents, controlnet_image, encoder_hidden_s
         r0, r1 = shard_range(B, world, r)
         out.append(p[: r1 - r0])
     return torch.cat(out, dim=0)
+
+
+# ======================================================================================================================
+# Ulysses-style sequence parallelism (BASELINE config C4: one 2048px image over P GPUs)
+# ======================================================================================================================
+class SequenceParallel:
+    """Head <-> sequence exchange for joint attention plus the 1-row halo exchange of the depthwise stencil.
+
+    Partitioning: every rank owns `grid/P` contiguous rows of the sqrt(N) x sqrt(N) token grid of BOTH image streams
+    (so LayerNorm, GEMMs and the HQ/LR pairing of the conv stay local); the T text tokens are replicated.  Per attention:
+      all-to-all #1   [my tokens, all heads]  ->  [all tokens, my H/P heads]      (q, k, v)
+      local attention over the full joint sequence on H/P heads                   (text heads: local slice, no comm)
+      all-to-all #2   [all tokens, my heads]  ->  [my tokens, all heads]          (o)
+      all-gather      text rows of o over the head dimension (before to_add_out)
+    Token order on the attention side is rank-major ([r0 tokens | r1 tokens | ... | text]): softmax attention is
+    invariant to a permutation of the keys, and the query permutation is undone by all-to-all #2.
+    The collectives go through torch.distributed (NCCL over NVLink on the GPUs; gloo in the CPU tests).
+    """
+
+    def __init__(self, group: Optional[dist.ProcessGroup] = None):
+        self.group = group
+        self.world = dist.get_world_size(group)
+        self.rank = dist.get_rank(group)
+
+    # ---- attention exchange -------------------------------------------------------------------------------------
+    def seq_to_heads(self, t: torch.Tensor) -> torch.Tensor:
+        """t [B, Sl, C, H, dh] (my tokens, all heads) -> [B, P*Sl, C, H/P, dh] (all tokens rank-major, my heads)."""
+        P = self.world
+        B, Sl, C, H, dh = t.shape
+        if H % P:
+            raise ValueError(f"{H} heads do not divide over {P} ranks")
+        Hl = H // P
+        send = t.reshape(B, Sl, C, P, Hl, dh).permute(3, 0, 1, 2, 4, 5).contiguous()      # [P, B, Sl, C, Hl, dh]
+        recv = torch.empty_like(send)
+        dist.all_to_all_single(recv, send, group=self.group)
+        return recv.permute(1, 0, 2, 3, 4, 5).reshape(B, P * Sl, C, Hl, dh)
+
+    def heads_to_seq(self, o: torch.Tensor) -> torch.Tensor:
+        """o [B, P*Sl, Hl*dh] (all tokens rank-major, my heads) -> [B, Sl, P*Hl*dh] (my tokens, all heads)."""
+        P = self.world
+        B, S, Dl = o.shape
+        Sl = S // P
+        send = o.reshape(B, P, Sl, Dl).permute(1, 0, 2, 3).contiguous()                    # [P, B, Sl, Dl]
+        recv = torch.empty_like(send)
+        dist.all_to_all_single(recv, send, group=self.group)
+        return recv.permute(1, 2, 0, 3).reshape(B, Sl, P * Dl)
+
+    def gather_heads(self, t: torch.Tensor) -> torch.Tensor:
+        """t [B, T, Dl] (replicated tokens, my heads) -> [B, T, P*Dl] (all heads)."""
+        parts = [torch.empty_like(t) for _ in range(self.world)]
+        dist.all_gather(parts, t.contiguous(), group=self.group)
+        return torch.cat(parts, dim=-1)
+
+    def head_slice(self, H: int) -> Tuple[int, int]:
+        Hl = H // self.world
+        return self.rank * Hl, (self.rank + 1) * Hl
+
+    # ---- stencil halo -------------------------------------------------------------------------------------------
+    def halo_rows(self, u_lr: torch.Tensor, grid_w: int, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """u_lr [B, rows*grid_w, F]: my rows of the LR hidden state. Returns [B, (rows+2)*grid_w, F] with the neighbours'
+        adjacent row above and below (zeros at the image border)."""
+        B, n, F = u_lr.shape
+        rows = n // grid_w
+        if out is None:
+            out = torch.empty(B, (rows + 2) * grid_w, F, dtype=u_lr.dtype, device=u_lr.device)
+        out[:, grid_w:(rows + 1) * grid_w] = u_lr
+        top, bot = out[:, :grid_w], out[:, (rows + 1) * grid_w:]
+        ops_, bufs = [], []
+        up, down = self.rank - 1, self.rank + 1
+
+        def peer(r):
+            return r if self.group is None else dist.get_global_rank(self.group, r)
+
+        if up >= 0:
+            s = u_lr[:, :grid_w].contiguous()
+            r_ = torch.empty_like(s)
+            ops_ += [dist.P2POp(dist.isend, s, peer(up), self.group), dist.P2POp(dist.irecv, r_, peer(up), self.group)]
+            bufs.append((top, r_))
+        else:
+            top.zero_()
+        if down < self.world:
+            s = u_lr[:, (rows - 1) * grid_w:].contiguous()
+            r_ = torch.empty_like(s)
+            ops_ += [dist.P2POp(dist.isend, s, peer(down), self.group), dist.P2POp(dist.irecv, r_, peer(down), self.group)]
+            bufs.append((bot, r_))
+        else:
+            bot.zero_()
+        if ops_:
+            for w in dist.batch_isend_irecv(ops_):
+                w.wait()
+        for dst, src in bufs:
+            dst.copy_(src)
+        return out
+
+    # ---- row sharding of images -------------------------------------------------------------------------------------
+    def row_slice(self, rows: int) -> Tuple[int, int]:
+        if rows % self.world:
+            raise ValueError(f"{rows} rows do not divide over {self.world} ranks")
+        per = rows // self.world
+        return self.rank * per, (self.rank + 1) * per
+
+    def gather_rows(self, t: torch.Tensor, dim: int) -> torch.Tensor:
+        parts = [torch.empty_like(t) for _ in range(self.world)]
+        dist.all_gather(parts, t.contiguous(), group=self.group)
+        return torch.cat(parts, dim=dim)

@@ -72,6 +72,12 @@ typedef struct {
   int64_t ld; int64_t hq_batch_stride; int64_t lr_batch_stride;
   const float* weight9; const float* bias;
   int batches; int grid; int channels;
+  /* Rectangular / row-sharded grids (sequence parallelism: a rank owns `grid` rows of `grid_w` columns and holds the LR
+   * stream with halo rows). All zero = square grid x grid image without halo.
+   *   grid_w        columns per row (0 -> grid)
+   *   lr_grid_h     rows present in u_lr (0 -> grid)
+   *   lr_row_offset u_lr row that lies under u_hq row 0 (rows outside [0, lr_grid_h) read as zero padding) */
+  int grid_w; int lr_grid_h; int lr_row_offset;
 } dit4sr_dwconv3x3_params;
 int dit4sr_dwconv3x3_add(const dit4sr_dwconv3x3_params* p, void* stream);
 
@@ -157,6 +163,10 @@ int dit4sr_unpatchify(const float* tok, void* out, int out_dtype, const void* la
 int dit4sr_timestep_features(const float* timesteps, void* out_bf16, int batches, void* stream);
 /* y = silu(x) (fp32 -> bf16), n elements */
 int dit4sr_silu_cast(const float* x, void* y_bf16, int64_t n, void* stream);
+/* dst[b, r, :] += src[b, r, :] for bf16 [batches, rows, cols] views (cols % 8 == 0, strides in elements): the LR-stream
+ * residual add of attention.py:545 when the attention output arrives through the sequence-parallel all-to-all. */
+int dit4sr_add_bf16(void* dst, int64_t dst_row_stride, int64_t dst_batch_stride, const void* src, int64_t src_row_stride,
+                    int64_t src_batch_stride, int batches, int rows, int cols, void* stream);
 /* y = x (fp32 -> bf16 or bf16 -> fp32), n elements; dir 0 = f32->bf16, 1 = bf16->f32 */
 int dit4sr_cast(const void* x, void* y, int64_t n, int dir, void* stream);
 
