@@ -359,9 +359,9 @@ class Engine:
         streams = [(hidden_states, x[:, :N]), (controlnet_image, x[:, N:2 * N])]
         if self.streams == 3:   # the OCR stream starts as a second pos_embed(controlnet_image) (ocr model :334-337)
             streams.append((controlnet_image, x[:, 2 * N:]))
-        for src, rows in streams:
+        for src, dst_rows in streams:
             R("head", ops.patchify, src.contiguous(), ws["patches"])
-            R("head", ops.gemm, ws["patches"], self.patch_w, self.patch_b, rows, ops.EPI_GATE_RESID, resid=pos)
+            R("head", ops.gemm, ws["patches"], self.patch_w, self.patch_b, dst_rows, ops.EPI_GATE_RESID, resid=pos)
         ws["enc"].copy_(encoder_hidden_states)
         R("head", ops.gemm, ws["enc"], self.ctx_embed.w, self.ctx_embed.b, ctx, ops.EPI_BIAS)
 
