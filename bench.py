@@ -24,12 +24,16 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 WORKLOADS = {
-    # name: (latent side, per-GPU batch, text tokens, description)
-    "c2": (64, 8, 333, "C2: SD3.5-medium-shaped DiT4SR, bf16, 512px (1024 HQ + 1024 LR + 333 text tokens), batch 8 per GPU, "
-                       "40-step flow-match schedule"),
-    "c3": (128, 4, 333, "C3-per-GPU slice: 1024px (4096 HQ + 4096 LR + 333 text), batch 4 per GPU"),
-    "px1024": (128, 1, 333, "1024px batch 1"),
-    "px2048": (256, 1, 333, "2048px batch 1 (single GPU, no sequence parallelism)"),
+    # name: (latent side, batch, text tokens, mode, description)
+    #   mode dp_weak  : `batch` images PER GPU, data-parallel sampling, no data-path collective (weak scaling)
+    #   mode dp_strong: `batch` images IN TOTAL, split over the GPUs (strong scaling)
+    #   mode sp       : `batch` images IN TOTAL, every image sharded over all GPUs with Ulysses sequence parallelism
+    "c2": (64, 8, 333, "dp_weak", "C2: SD3.5-medium-shaped DiT4SR, bf16, 512px (1024 HQ + 1024 LR + 333 text tokens), "
+                                  "batch 8 per GPU, 40-step flow-match schedule"),
+    "c3": (128, 32, 333, "dp_strong", "C3: 1024px (4096 HQ + 4096 LR + 333 text tokens), batch 32 in total, data-parallel"),
+    "c4": (256, 1, 333, "sp", "C4: 2048px (16384 HQ + 16384 LR + 333 text tokens), batch 1, Ulysses sequence parallelism "
+                              "(head<->sequence all-to-all over NCCL)"),
+    "px1024": (128, 1, 333, "dp_weak", "1024px batch 1 per GPU"),
 }
 
 
@@ -138,13 +142,23 @@ def run_ours(args):
     dev = torch.device("cuda", local)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
-    side, B, T, desc = WORKLOADS[args.workload]
+    side, B, T, mode, desc = WORKLOADS[args.workload]
+    if mode == "dp_strong":
+        if B % world:
+            raise SystemExit(f"workload {args.workload}: batch {B} does not divide over {world} GPUs")
+        B //= world
     N = (side // 2) ** 2
     bf = torch.bfloat16
 
     model, cfg = build_model_gpu(dev, seed=0)
-    eng = model.engine()
-    g = torch.Generator(device=dev).manual_seed(1 + rank)
+    if mode == "sp" and world > 1:
+        from dit4sr_b200.parallel import SequenceParallel
+        eng = model.engine(sequence_parallel=SequenceParallel())
+    else:
+        eng = model.engine()
+    images_total = B * (1 if mode == "sp" else world)       # images advanced per step by the whole job
+    rank_seed = 1 if mode == "sp" else 1 + rank              # sequence parallelism: every rank holds the same image
+    g = torch.Generator(device=dev).manual_seed(rank_seed)
     x = torch.randn(B, 16, side, side, device=dev, generator=g)
     ctrl = torch.randn(B, 16, side, side, device=dev, generator=g).to(bf)
     enc = (0.5 * torch.randn(B, T, 4096, device=dev, generator=g)).to(bf)
@@ -241,8 +255,8 @@ def run_ours(args):
     if rank == 0:
         peaks = measured_peaks()
         gemm_f, attn_f = flops_per_image_step(N, T, folded=eng.fold_lr_chains)
-        step_flops = (gemm_f + attn_f) * B
-        img_steps = B * world * args.steps
+        step_flops = (gemm_f + attn_f) * images_total / world      # per-GPU share of one step
+        img_steps = images_total * args.steps
         value = img_steps / (ms / 1e3)
         # FF1 launch = image FF1 [B*2N,1536]x[1536,6144] grouped with the text FF1 [B*T,...] (absent in the last block)
         ff1_flops = 2.0 * (B * 2 * N + B * T * 23.0 / 24.0) * 1536 * 6144
@@ -260,13 +274,14 @@ def run_ours(args):
         line = dict(
             metric="denoise_steps_per_sec", value=round(value, 3), unit="image-steps/s (one image advanced one denoise step)",
             n_gpus=world, steps=args.steps, warmup=args.warmup, ms_per_step=round(ms / args.steps, 3),
-            higher_is_better=True, scaling="weak", vs_baseline=None, dtype="bf16", data="synthetic",
-            config=dict(workload=desc, per_gpu_batch=B, global_batch=B * world, latent=f"{side}x{side}", tokens_hq=N,
-                        tokens_lr=N, tokens_text=T, parallelism=f"dp{world}",
+            higher_is_better=True, scaling="weak" if mode == "dp_weak" else "strong", vs_baseline=None, dtype="bf16",
+            data="synthetic",
+            config=dict(workload=desc, per_gpu_batch=B, global_batch=images_total, latent=f"{side}x{side}", tokens_hq=N,
+                        tokens_lr=N, tokens_text=T, parallelism=(f"ulysses{world}" if mode == "sp" else f"dp{world}"),
                         l2="working set (5.4 GB bf16 weights + activations) >> 126 MB L2; no explicit flush"),
-            batch_steps_per_sec=round(args.steps * world / (ms / 1e3), 3),
+            batch_steps_per_sec=round(args.steps * (world if mode == "dp_weak" else 1) / (ms / 1e3), 3),
             step_tflop=round(step_flops / 1e12, 3), lr_chains_folded=bool(eng.fold_lr_chains),
-            step_tflops_achieved=round(step_flops * world / (ms / args.steps / 1e3) / 1e12, 1),
+            step_tflops_achieved=round(step_flops * world / (ms / args.steps / 1e3) / 1e12, 1),   # whole job
             step_frac_of_sustained_peak=round(step_flops / (ms / args.steps / 1e3) / 1e12 / peaks["tf_sustained"], 4),
             e2e=dict(value=round(img_steps / (e2e_ms / 1e3), 3), unit="image-steps/s", h2d_bytes_per_step=h2d,
                      d2h_bytes_per_step=d2h, ms_per_step=round(e2e_ms / args.steps, 3),
@@ -322,7 +337,7 @@ def run_reference(args):
     from oracle import dit4sr_oracle as O
     ncpu = os.cpu_count() or 1
     torch.set_num_threads(ncpu)
-    side, B, T, desc = WORKLOADS[args.workload]
+    side, B, T, mode, desc = WORKLOADS[args.workload]
     cfg = O.sd35_medium_config(pos_embed_max_size=max(96, side // 2))
     sd = {k: torch.empty(shp).normal_(0, 0.02) for k, shp in O.state_dict_manifest(cfg).items()}
     inp = O.make_inputs(cfg, 1, side, side, T, seed=1, timestep=741.44)

@@ -327,6 +327,11 @@ class Engine:
         pos = self._pos_crop(grid, grid, hidden_states.device)
         full_out, full_euler = out, euler
         if self.sp is not None:         # Ulysses: this rank keeps grid/P contiguous rows of every image stream
+            if self.streams == 3 and any(b.dual for b in self.blocks):
+                # Q6: attn2 of the 3-stream model pairs token j of the first 1.5N tokens with token j of the last 1.5N;
+                # under row sharding those partners live on different ranks. BASELINE config #5 is data-parallel.
+                raise NotImplementedError("sequence parallelism is not supported for the OCR-branch model with dual "
+                                          "attention blocks (use data-parallel sampling, BASELINE config #5)")
             if self.H % self.sp.world:
                 raise ValueError(f"{self.H} heads do not divide over {self.sp.world} ranks")
             g0, g1 = self.sp.row_slice(grid)
