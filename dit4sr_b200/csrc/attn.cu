@@ -297,6 +297,32 @@ constexpr int COL_O = 384;
 constexpr int SMEM_BYTES = (2 + 2 * KV_STAGES) * TILE_BYTES + 1024 + 256;
 constexpr float RESCALE_THRESHOLD = 8.0f;   // in log2 units: skip the O rescale while p stays <= 2^8
 
+// 2^x for x <= ~8 on the FMA pipe (Cody-Waite range reduction + degree-3 minimax polynomial, max rel. error 7.5e-5,
+// far below the bf16 rounding of P): takes exponentials off the MUFU unit, which bounds head_dim-64 attention.
+// Two values per instruction with the packed fp32x2 forms (FFMA2 / FADD2).
+__device__ __forceinline__ void exp2_poly2(uint64_t x2, float& p0, float& p1) {
+  const uint64_t magic = ptx::pack2(12582912.0f, 12582912.0f);        // 1.5 * 2^23: x + magic rounds x to an integer
+  const uint64_t nmagic = ptx::pack2(-12582912.0f, -12582912.0f);
+  const uint64_t neg1 = ptx::pack2(-1.0f, -1.0f);
+  const uint64_t c3 = ptx::pack2(0.05517165f, 0.05517165f), c2 = ptx::pack2(0.24261113f, 0.24261113f);
+  const uint64_t c1 = ptx::pack2(0.69326097f, 0.69326097f), c0 = ptx::pack2(0.99992806f, 0.99992806f);
+  float xa, xb;
+  ptx::unpack2(x2, xa, xb);
+  x2 = ptx::pack2(fmaxf(xa, -125.0f), fmaxf(xb, -125.0f));            // keep 2^n representable
+  const uint64_t t2 = ptx::add2(x2, magic);                            // integer part lives in the low mantissa bits
+  const uint64_t n2 = ptx::add2(t2, nmagic);
+  const uint64_t f2 = ptx::fma2(n2, neg1, x2);                         // f in [-0.5, 0.5]
+  uint64_t q2 = ptx::fma2(f2, c3, c2);
+  q2 = ptx::fma2(q2, f2, c1);
+  q2 = ptx::fma2(q2, f2, c0);
+  float qa, qb, ta, tb;
+  ptx::unpack2(q2, qa, qb);
+  ptx::unpack2(t2, ta, tb);
+  p0 = __int_as_float(__float_as_int(qa) + (__float_as_int(ta) << 23));   // add n to the exponent field
+  p1 = __int_as_float(__float_as_int(qb) + (__float_as_int(tb) << 23));
+}
+
+template <int POLY8>   // of every 8 score pairs, POLY8 use the polynomial and 8-POLY8 use MUFU.EX2
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 attn_fwd2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                  const __grid_constant__ CUtensorMap tmV, const Args args) {
@@ -459,16 +485,30 @@ attn_fwd2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
         m_run = mx;
       }
       const float neg_m = -m_run * sl2;
-      float rs[4] = {0.f, 0.f, 0.f, 0.f};   // independent partial row sums
+      uint64_t rs2[4];                         // independent packed partial row sums
+#pragma unroll
+      for (int a = 0; a < 4; ++a) rs2[a] = ptx::pack2(0.f, 0.f);
+      const uint64_t sl2_2 = ptx::pack2(sl2, sl2), negm_2 = ptx::pack2(neg_m, neg_m);
       uint32_t pk[64];
 #pragma unroll
       for (int i = 0; i < 64; ++i) {
-        const float p0 = ptx::ex2(fmaf(__uint_as_float(v[2 * i]), sl2, neg_m));
-        const float p1 = ptx::ex2(fmaf(__uint_as_float(v[2 * i + 1]), sl2, neg_m));
-        rs[i & 3] += p0 + p1;
+        const uint64_t x2 = ptx::fma2(ptx::pack2(__uint_as_float(v[2 * i]), __uint_as_float(v[2 * i + 1])), sl2_2, negm_2);
+        float p0, p1;
+        if (!decltype(masked)::value && (i & 7) < POLY8) {
+          exp2_poly2(x2, p0, p1);
+        } else {
+          float xa, xb;
+          ptx::unpack2(x2, xa, xb);
+          p0 = ptx::ex2(xa);
+          p1 = ptx::ex2(xb);
+        }
+        rs2[i & 3] = ptx::add2(rs2[i & 3], ptx::pack2(p0, p1));
         pk[i] = ptx::pack_bf16(p0, p1);
       }
-      const float rsum = (rs[0] + rs[1]) + (rs[2] + rs[3]);
+      float ra, rb, rc, rd;
+      ptx::unpack2(ptx::add2(rs2[0], rs2[1]), ra, rb);
+      ptx::unpack2(ptx::add2(rs2[2], rs2[3]), rc, rd);
+      const float rsum = (ra + rb) + (rc + rd);
       // O_t may only be touched between P V(j-1) completing and P V(j) being issued (it is issued after our arrive)
       if (j > 0 && __any_sync(0xffffffffu, grow)) {
         ptx::mbar_wait(&o_done[t], (j - 1) & 1);
@@ -599,12 +639,19 @@ extern "C" int dit4sr_attn_fwd(const dit4sr_attn_params* p, void* stream_) {
   a.scale_log2 = p->scale * 1.4426950408889634f;
 
   static bool configured = false;
-  static int variant = 2;   // development switch: DIT4SR_ATTN_VARIANT=1 selects the one-tile-per-CTA kernel
+  // development switches: DIT4SR_ATTN_VARIANT=1 selects the one-tile-per-CTA kernel; DIT4SR_ATTN_POLY=0..4 the number
+  // of score pairs (of every 8) exponentiated on the FMA pipe instead of MUFU
+  static int variant = 2, poly8 = 0;
   if (!configured) {
     DIT4SR_CUDA(cudaFuncSetAttribute(attn_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
-    DIT4SR_CUDA(cudaFuncSetAttribute(v2::attn_fwd2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, v2::SMEM_BYTES));
+    DIT4SR_CUDA(cudaFuncSetAttribute(v2::attn_fwd2_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, v2::SMEM_BYTES));
+    DIT4SR_CUDA(cudaFuncSetAttribute(v2::attn_fwd2_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, v2::SMEM_BYTES));
+    DIT4SR_CUDA(cudaFuncSetAttribute(v2::attn_fwd2_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, v2::SMEM_BYTES));
+    DIT4SR_CUDA(cudaFuncSetAttribute(v2::attn_fwd2_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, v2::SMEM_BYTES));
+    DIT4SR_CUDA(cudaFuncSetAttribute(v2::attn_fwd2_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, v2::SMEM_BYTES));
     const char* e = getenv("DIT4SR_ATTN_VARIANT");
     if (e != nullptr && e[0] == '1') variant = 1;
+    if ((e = getenv("DIT4SR_ATTN_POLY")) != nullptr) poly8 = atoi(e);
     configured = true;
   }
   if (variant == 1) {
@@ -612,7 +659,13 @@ extern "C" int dit4sr_attn_fwd(const dit4sr_attn_params* p, void* stream_) {
     attn_fwd_kernel<<<grid, NUM_THREADS, SMEM_BYTES, stream>>>(tmQ, tmK, tmV, a);
   } else {
     dim3 grid((p->seq_q + 2 * BQ - 1) / (2 * BQ), p->heads, p->batches);
-    v2::attn_fwd2_kernel<<<grid, v2::NUM_THREADS, v2::SMEM_BYTES, stream>>>(tmQ, tmK, tmV, a);
+    switch (poly8) {
+      case 0: v2::attn_fwd2_kernel<0><<<grid, v2::NUM_THREADS, v2::SMEM_BYTES, stream>>>(tmQ, tmK, tmV, a); break;
+      case 1: v2::attn_fwd2_kernel<1><<<grid, v2::NUM_THREADS, v2::SMEM_BYTES, stream>>>(tmQ, tmK, tmV, a); break;
+      case 3: v2::attn_fwd2_kernel<3><<<grid, v2::NUM_THREADS, v2::SMEM_BYTES, stream>>>(tmQ, tmK, tmV, a); break;
+      case 4: v2::attn_fwd2_kernel<4><<<grid, v2::NUM_THREADS, v2::SMEM_BYTES, stream>>>(tmQ, tmK, tmV, a); break;
+      default: v2::attn_fwd2_kernel<2><<<grid, v2::NUM_THREADS, v2::SMEM_BYTES, stream>>>(tmQ, tmK, tmV, a); break;
+    }
   }
   DIT4SR_CUDA(cudaGetLastError());
   return 0;
