@@ -170,7 +170,7 @@ def run_ours(args):
     def step(i, xin, xout):
         k = i % 40
         t.fill_(float(sig[k]) * 1000.0)
-        eng.forward(xin, ctrl, enc, pooled, t, out=xout, euler=(xin, float(sig[k + 1]) - float(sig[k])))
+        eng.step(xin, ctrl, enc, pooled, t, out=xout, euler=(xin, float(sig[k + 1]) - float(sig[k])))
 
     def barrier():
         if world > 1:
@@ -186,7 +186,6 @@ def run_ours(args):
     sampler = ClockSampler(local) if rank == 0 else None
     l0 = ops.launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    eng.profile_kernel("ff1")   # CUDA events around the dominant kernel's launches inside the timed region
     prof_range = os.environ.get("DIT4SR_PROFILE_RANGE") == "1"   # ncu --profile-from-start off
     if prof_range:
         torch.cuda.profiler.start()
@@ -200,6 +199,12 @@ def run_ours(args):
         torch.cuda.profiler.stop()
     ms = e0.elapsed_time(e1)
     launches = ops.launch_count() - l0
+    # dominant kernel: CUDA events around every FF1-group launch of the same steps, run again right after the timed region
+    # (same stream, same shapes, same clocks; direct launches because events cannot be recorded inside a graph replay)
+    eng.profile_kernel("ff1")
+    for i in range(args.steps):
+        step(i, cur, oth)
+        cur, oth = oth, cur
     ff1_ms = eng.profile_result()
     clocks = sampler.stop() if sampler else None
     if world > 1:

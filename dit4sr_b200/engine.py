@@ -153,6 +153,9 @@ class Engine:
         self.proj_out = _Lin(model.proj_out)
         self._ws: Dict[Tuple, dict] = {}
         self._prof = None
+        self._graphs: Dict[Tuple, tuple] = {}
+        import os as _os
+        self.use_cuda_graph = _os.environ.get("DIT4SR_CUDA_GRAPH", "1") != "0"
         self._pos: Dict[Tuple, torch.Tensor] = {}
 
     # ------------------------------------------------------------------------------------------------ profiling
@@ -312,6 +315,61 @@ class Engine:
         else:
             padded = self.sp.halo_rows(src, grid_w, out=ws["lr_pad"])
             self._run("dwconv", ops.dwconv3x3_add, dst, padded, w9, b, rows, grid_w=grid_w, lr_row_offset=1)
+
+    # ------------------------------------------------------------------------------------------------ CUDA graph
+    @torch.no_grad()
+    def step(self, hidden_states, controlnet_image, encoder_hidden_states, pooled_projections, timestep,
+             out=None, euler: Optional[Tuple[torch.Tensor, float]] = None):
+        """One denoiser call, replayed from a captured CUDA graph when possible (the ~300 kernel launches of a step are
+        recorded once per input shape; replay removes the per-launch host cost, which matters for small batches).
+        Same results as `forward` -- the same kernels run. Falls back to direct launches under sequence parallelism,
+        while profiling, or if capture is unavailable."""
+        if not self.use_cuda_graph or self.sp is not None or self._prof is not None:
+            return self.forward(hidden_states, controlnet_image, encoder_hidden_states, pooled_projections, timestep,
+                                out=out, euler=euler)
+        B = hidden_states.shape[0]
+        key = (tuple(hidden_states.shape), hidden_states.dtype, tuple(encoder_hidden_states.shape),
+               encoder_hidden_states.dtype, pooled_projections.dtype, str(hidden_states.device))
+        entry = self._graphs.get(key)
+        if entry is None:
+            st = dict(hs=hidden_states.clone().contiguous(), ci=controlnet_image.clone().contiguous(),
+                      enc=encoder_hidden_states.clone().contiguous(), pooled=pooled_projections.clone().contiguous(),
+                      t=torch.zeros(B, device=hidden_states.device, dtype=torch.float32))
+            try:
+                self.forward(st["hs"], st["ci"], st["enc"], st["pooled"], st["t"])      # warm-up outside capture
+                torch.cuda.synchronize()
+                n0 = ops.launch_count()
+                graph = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(graph):
+                    vel = self.forward(st["hs"], st["ci"], st["enc"], st["pooled"], st["t"])
+                entry = (graph, st, vel, ops.launch_count() - n0)
+            except Exception as e:   # capture not possible here: keep launching directly
+                import warnings
+                warnings.warn(f"dit4sr_b200: CUDA graph capture failed ({e}); using direct launches")
+                self.use_cuda_graph = False
+                torch.cuda.synchronize()
+                return self.forward(hidden_states, controlnet_image, encoder_hidden_states, pooled_projections,
+                                    timestep, out=out, euler=euler)
+            self._graphs[key] = entry
+        graph, st, vel, n_launch = entry
+        st["hs"].copy_(hidden_states)
+        st["ci"].copy_(controlnet_image)
+        st["enc"].copy_(encoder_hidden_states)
+        st["pooled"].copy_(pooled_projections)
+        st["t"].copy_(timestep.to(device=st["t"].device, dtype=torch.float32).expand(B))
+        graph.replay()
+        ops._count(n_launch)
+        if euler is not None:        # x_next = x + dsigma * v straight from the velocity tokens the graph left behind
+            h = hidden_states.shape[-1]
+            ws = self._workspace(B, (h // 2) ** 2, encoder_hidden_states.shape[1], hidden_states.device)
+            if out is None:
+                out = torch.empty_like(euler[0])
+            ops.unpatchify(ws["tok"], out, latents=euler[0], dsigma=euler[1])
+            return out
+        if out is not None:
+            out.copy_(vel)
+            return out
+        return vel.clone()
 
     # ------------------------------------------------------------------------------------------------ forward
     @torch.no_grad()

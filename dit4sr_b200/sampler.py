@@ -30,7 +30,7 @@ def denoise(model, latents, controlnet_image, encoder_hidden_states, pooled_proj
     t = torch.empty(B, device=latents.device, dtype=torch.float32)
     for i in range(len(sig) - 1):
         t.fill_(float(sig[i]) * 1000.0)
-        eng.forward(x, controlnet_image, encoder_hidden_states, pooled_projections, t, out=nxt,
-                    euler=(x, float(sig[i + 1]) - float(sig[i])))
+        eng.step(x, controlnet_image, encoder_hidden_states, pooled_projections, t, out=nxt,
+                 euler=(x, float(sig[i + 1]) - float(sig[i])))
         x, nxt = nxt, x
     return x.to(latents.dtype)

@@ -295,7 +295,11 @@ class SD3Transformer2DModel(nn.Module):
         hs, ci = hidden_states, controlnet_image
         if in_dtype not in (torch.float32, torch.bfloat16):
             hs, ci = hs.float(), ci.float()
-        out = self.engine().forward(hs, ci, encoder_hidden_states, pooled_projections, timestep, feat_hook=hook)
+        eng = self.engine()
+        if hook is None:
+            out = eng.step(hs, ci, encoder_hidden_states, pooled_projections, timestep)
+        else:
+            out = eng.forward(hs, ci, encoder_hidden_states, pooled_projections, timestep, feat_hook=hook)
         output = out.to(in_dtype)
         if not return_dict:
             if want_feats or self._ocr_branch:
