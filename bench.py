@@ -266,6 +266,17 @@ def run_ours(args):
         # FF1 launch = image FF1 [B*2N,1536]x[1536,6144] grouped with the text FF1 [B*T,...] (absent in the last block)
         ff1_flops = 2.0 * (B * 2 * N + B * T * 23.0 / 24.0) * 1536 * 6144
         ff1_avg_ms = (sum(ff1_ms["ff1"]) / len(ff1_ms["ff1"])) if ff1_ms and ff1_ms.get("ff1") else None
+        # DRAM traffic of the same kernel from the committed `ncu --set full` capture (dram__bytes_read + write per launch)
+        traffic = None
+        try:
+            prof = json.load(open(os.path.join(ROOT, "profiles", "r01_ncu_full_kernels.json")))
+            vals = [float(k["dram__bytes_read.sum [Mbyte]"]) + float(k["dram__bytes_write.sum [Mbyte]"])
+                    for k in prof if "gemm_kernel<1>" in k["Kernel Name"]]
+            if vals:
+                traffic = dict(bytes_per_launch=round(sum(vals) / len(vals) * 1e6), source="profiles/r01_ncu_full_kernels.json "
+                               "(FF1 image problem alone, M=16384: algorithmic 50.3 MB A + 18.9 MB W read + 201.3 MB written)")
+        except (OSError, KeyError, ValueError):
+            pass
         roof = None
         if ff1_avg_ms:
             ach = ff1_flops / (ff1_avg_ms / 1e3) / 1e12
@@ -275,7 +286,7 @@ def run_ours(args):
                         peak_source=peaks["source"] + ", sustained figure (kernel timed inside a long step)",
                         frac_of_burst=round(ach / peaks["tf_burst"], 4), frac_of_spec_2250=round(ach / 2250.0, 4),
                         launch_ms=round(ff1_avg_ms, 4), flops_per_launch=ff1_flops, launches_timed=len(ff1_ms["ff1"]),
-                        traffic=None)
+                        traffic=traffic)
         line = dict(
             metric="denoise_steps_per_sec", value=round(value, 3), unit="image-steps/s (one image advanced one denoise step)",
             n_gpus=world, steps=args.steps, warmup=args.warmup, ms_per_step=round(ms / args.steps, 3),

@@ -317,6 +317,23 @@ gemm_kernel(const __grid_constant__ Maps maps, const __grid_constant__ Group grp
           Rf = P.resid + (int64_t)tc.b * P.r_batch_stride + n_base;
           g_row = P.gate ? P.gate + (int64_t)tc.b * P.gate_batch_stride + n_base : nullptr;
         }
+        // The residual rows are the only cold global reads of this epilogue and each warp has just one 32-column pass
+        // of them in flight, so pull the NEXT tile's residual rows into L2 now (a whole tile ahead of their use).
+        if constexpr (EPI == DIT4SR_EPI_GATE_RESID) {
+          const int nt = tile + gridDim.x;
+          if (nt < num_tiles) {
+            const TileCoord nc = decode_tile(grp, nt);
+            const Problem& NP = grp.p[nc.pi];
+            const int nr = nc.m_tile * BM + q * 32 + lane;
+            if (nr < NP.rows) {
+              const float* np = NP.resid + (int64_t)nc.b * NP.r_batch_stride + (int64_t)nr * NP.ldr + nc.n_tile * BN;
+              const int ncols = min(BN, NP.N - nc.n_tile * BN);
+#pragma unroll
+              for (int i = 0; i < BN / 32; ++i)
+                if (i * 32 < ncols) ptx::prefetch_l2(np + i * 32);
+            }
+          }
+        }
         // the residual does not depend on the accumulator: fetch the first pass before waiting for the MMAs
         float4 rv[2][8];
         if constexpr (EPI == DIT4SR_EPI_GATE_RESID) {
