@@ -1,0 +1,51 @@
+"""Latent tiling around the denoiser (row N3 of SURVEY 8f; reference: pipelines/pipeline_dit4sr.py:746-761,1449-1558).
+
+Large latents are cut into overlapping square tiles, every tile goes through the model (here: ALL tiles of a step as
+one batch -- tiles are independent, so this is the same batch data-parallelism as `parallel.dp_denoise`), and the
+per-tile velocities are blended with a gaussian weight window.  Tile placement and weights follow the reference
+exactly (including its `cfg`-less call, which crashes there, SURVEY Q7, and works here)."""
+from typing import Callable, List, Tuple
+
+import numpy as np
+import torch
+
+
+def tile_offsets(size: int, tile: int, overlap: int) -> List[int]:
+    """Start offsets along one axis (pipeline_dit4sr.py:1454-1486): stride tile-overlap, last tile flush with the end."""
+    n, cur = 0, 0
+    while cur < size:
+        cur = max(n * tile - overlap * n, 0) + tile
+        n += 1
+    return [size - tile if i == n - 1 else max(i * tile - overlap * i, 0) for i in range(n)]
+
+
+def gaussian_weights(tile_w: int, tile_h: int, device=None, dtype=torch.float64) -> torch.Tensor:
+    """pipeline_dit4sr.py:746-761 (`_gaussian_weights`, var 0.01; note the asymmetric midpoints of the original)."""
+    var = 0.01
+    mid = (tile_w - 1) / 2
+    xs = [np.exp(-(x - mid) * (x - mid) / (tile_w * tile_w) / (2 * var)) / np.sqrt(2 * np.pi * var) for x in range(tile_w)]
+    mid = tile_h / 2
+    ys = [np.exp(-(y - mid) * (y - mid) / (tile_h * tile_h) / (2 * var)) / np.sqrt(2 * np.pi * var) for y in range(tile_h)]
+    return torch.tensor(np.outer(ys, xs), device=device, dtype=dtype)
+
+
+def tiled_velocity(model_fn: Callable, latents: torch.Tensor, controlnet_image: torch.Tensor, tile: int, overlap: int,
+                   tile_batch: int = 0) -> torch.Tensor:
+    """Velocity of a large latent from overlapping tiles. model_fn(latent_tiles, control_tiles) -> velocity tiles
+    (batch = tiles x images). tile_batch > 0 caps the number of tiles per model call."""
+    B, C, h, w = latents.shape
+    tile = min(tile, min(h, w))
+    xs, ys = tile_offsets(w, tile, overlap), tile_offsets(h, tile, overlap)
+    coords: List[Tuple[int, int]] = [(y, x) for x in xs for y in ys]        # the reference iterates rows over x first
+    lat = torch.cat([latents[:, :, y:y + tile, x:x + tile] for y, x in coords], dim=0)
+    ctl = torch.cat([controlnet_image[:, :, y:y + tile, x:x + tile] for y, x in coords], dim=0)
+    step = tile_batch * B if tile_batch > 0 else lat.shape[0]
+    outs = [model_fn(lat[i:i + step].contiguous(), ctl[i:i + step].contiguous()) for i in range(0, lat.shape[0], step)]
+    vel = torch.cat(outs, dim=0).float()
+    wts = gaussian_weights(tile, tile, device=latents.device, dtype=torch.float32)
+    acc = torch.zeros(B, C, h, w, device=latents.device, dtype=torch.float32)
+    cnt = torch.zeros_like(acc)
+    for i, (y, x) in enumerate(coords):
+        acc[:, :, y:y + tile, x:x + tile] += vel[i * B:(i + 1) * B] * wts
+        cnt[:, :, y:y + tile, x:x + tile] += wts
+    return acc / cnt

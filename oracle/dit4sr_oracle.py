@@ -538,3 +538,52 @@ def sample_loop(sd, cfg, latents, controlnet_image, encoder_hidden_states, poole
         v = model_fn(x, t)
         x = (x.float() + (float(sig[i + 1]) - float(sig[i])) * v.float()).to(v.dtype)
     return x
+
+
+# --------------------------------------------------------------------------------------------------------------
+# tiled branch of the sampling loop (pipelines/pipeline_dit4sr.py:746-761,1449-1558), restated literally
+# --------------------------------------------------------------------------------------------------------------
+
+def tiled_velocity_as_written(model_fn, latent_model_input, control_image, tile_size, tile_overlap):
+    """One tile per model call, the reference's loops and offsets verbatim (batch_size 1)."""
+    from numpy import pi, exp, sqrt
+    h, w = latent_model_input.shape[-2:]
+    tile_size = min(tile_size, min(h, w))
+    var = 0.01
+    midpoint = (tile_size - 1) / 2
+    x_probs = [exp(-(x - midpoint) * (x - midpoint) / (tile_size * tile_size) / (2 * var)) / sqrt(2 * pi * var) for x in range(tile_size)]
+    midpoint = tile_size / 2
+    y_probs = [exp(-(y - midpoint) * (y - midpoint) / (tile_size * tile_size) / (2 * var)) / sqrt(2 * pi * var) for y in range(tile_size)]
+    tile_weights = torch.tensor(np.outer(y_probs, x_probs)).to(torch.float32)              # :746-761
+    grid_rows, cur_x = 0, 0
+    while cur_x < latent_model_input.size(-1):                                             # :1454-1458
+        cur_x = max(grid_rows * tile_size - tile_overlap * grid_rows, 0) + tile_size
+        grid_rows += 1
+    grid_cols, cur_y = 0, 0
+    while cur_y < latent_model_input.size(-2):                                             # :1460-1464
+        cur_y = max(grid_cols * tile_size - tile_overlap * grid_cols, 0) + tile_size
+        grid_cols += 1
+
+    def offsets(row, col):                                                                 # :1474-1481
+        ofs_x = max(row * tile_size - tile_overlap * row, 0)
+        ofs_y = max(col * tile_size - tile_overlap * col, 0)
+        if row == grid_rows - 1:
+            ofs_x = w - tile_size
+        if col == grid_cols - 1:
+            ofs_y = h - tile_size
+        return ofs_x, ofs_y
+
+    noise_preds = []
+    for row in range(grid_rows):
+        for col in range(grid_cols):
+            ox, oy = offsets(row, col)
+            noise_preds.append(model_fn(latent_model_input[:, :, oy:oy + tile_size, ox:ox + tile_size],
+                                        control_image[:, :, oy:oy + tile_size, ox:ox + tile_size]).float())
+    noise_pred = torch.zeros(latent_model_input.shape)                                     # :1535-1557
+    contributors = torch.zeros(latent_model_input.shape)
+    for row in range(grid_rows):
+        for col in range(grid_cols):
+            ox, oy = offsets(row, col)
+            noise_pred[:, :, oy:oy + tile_size, ox:ox + tile_size] += noise_preds[row * grid_cols + col] * tile_weights
+            contributors[:, :, oy:oy + tile_size, ox:ox + tile_size] += tile_weights
+    return noise_pred / contributors
