@@ -13,7 +13,7 @@ class LnModulateParams(C.Structure):
                 ("shift", c_vp), ("scale", c_vp), ("shift2", c_vp), ("scale2", c_vp),
                 ("mod_batch_stride", c_i64), ("out", c_vp), ("out2", c_vp),
                 ("ldo", c_i64), ("o_batch_stride", c_i64),
-                ("batches", c_int), ("rows", c_int), ("dim", c_int), ("eps", c_float)]
+                ("batches", c_int), ("rows", c_int), ("dim", c_int), ("eps", c_float), ("out_f32", c_int)]
 
 
 class DwconvParams(C.Structure):
@@ -57,6 +57,12 @@ SYMBOLS = {
     "dit4sr_timestep_features": (c_int, [c_vp, c_vp, c_int, c_vp]),
     "dit4sr_silu_cast": (c_int, [c_vp, c_vp, c_i64, c_vp]),
     "dit4sr_add_bf16": (c_int, [c_vp, c_i64, c_i64, c_vp, c_i64, c_i64, c_int, c_int, c_int, c_vp]),
+    "dit4sr_split3": (c_int, [c_vp, c_i64, c_i64, c_vp, c_int, c_int, c_int, c_int, c_int, c_vp]),
+    "dit4sr_split3_transposed": (c_int, [c_vp, c_i64, c_vp, c_int, c_int, c_int, c_vp]),
+    "dit4sr_softmax_rows_f32": (c_int, [c_vp, c_i64, c_int, c_int, c_int, c_float, c_vp]),
+    "dit4sr_add_f32": (c_int, [c_vp, c_i64, c_i64, c_vp, c_i64, c_i64, c_int, c_int, c_int, c_vp]),
+    "dit4sr_dwconv3x3_add_f32": (c_int, [c_vp, c_vp, c_i64, c_i64, c_i64, c_vp, c_vp, c_int, c_int, c_int, c_int, c_int,
+                                         c_int, c_vp]),
     "dit4sr_cast": (c_int, [c_vp, c_vp, c_i64, c_int, c_vp]),
 }
 

@@ -82,6 +82,12 @@ __device__ __forceinline__ float gelu_tanh(float x) {
   return 0.5f * x * (1.0f + ptx::tanh_approx(inner));
 }
 __device__ __forceinline__ float silu(float x) { return x / (1.0f + __expf(-x)); }
+// full-precision variants for fp32 outputs (the fp32-accurate mode)
+__device__ __forceinline__ float gelu_tanh_precise(float x) {
+  const float k0 = 0.7978845608028654f, k1 = 0.044715f;
+  return 0.5f * x * (1.0f + tanhf(k0 * (x + k1 * x * x * x)));
+}
+__device__ __forceinline__ float silu_precise(float x) { return x / (1.0f + expf(-x)); }
 
 __device__ __forceinline__ void store_bf16x32(__nv_bfloat16* dst, const float* f) {
   uint4* d4 = reinterpret_cast<uint4*>(dst);
@@ -281,6 +287,32 @@ gemm_kernel(const __grid_constant__ Maps maps, const __grid_constant__ Group grp
                   f[4 * j4 + 3] *= inv * ww.w;
                 }
               }
+              const int64_t row_shift = rep == 1 ? P.dbl_row_offset : 0;
+              if (P.c_f32) {
+                // fp32 output (accuracy mode): two staged passes of 32 floats per row
+                float* Cf = reinterpret_cast<float*>(P.C) + c_tile_off;
+#pragma unroll
+                for (int hf = 0; hf < 2; ++hf) {
+                  if (hf * 32 < cols) {
+                    __syncwarp();
+                    float4* wr4 = reinterpret_cast<float4*>(stg + lane * EPI_ROW_BYTES);
+#pragma unroll
+                    for (int i = 0; i < 8; ++i)
+                      wr4[i] = make_float4(f[hf * 32 + 4 * i], f[hf * 32 + 4 * i + 1], f[hf * 32 + 4 * i + 2],
+                                           f[hf * 32 + 4 * i + 3]);
+                    __syncwarp();
+#pragma unroll
+                    for (int r4 = 0; r4 < 8; ++r4) {
+                      const int rl = r4 * 4 + sub;
+                      const float4 a4 = *reinterpret_cast<const float4*>(stg + rl * EPI_ROW_BYTES + seg * 16);
+                      const int rg = row_base + rl;
+                      if (rg < P.rows)
+                        *reinterpret_cast<float4*>(Cf + (rg + row_shift) * P.ldc + c0 + hf * 32 + seg * 4) = a4;
+                    }
+                  }
+                }
+                continue;
+              }
               // stage this thread's row (64 bf16 = 128 B), then store 4 whole rows per warp instruction
               __syncwarp();
               uint4* wr = reinterpret_cast<uint4*>(stg + lane * EPI_ROW_BYTES);
@@ -294,7 +326,6 @@ gemm_kernel(const __grid_constant__ Maps maps, const __grid_constant__ Group grp
                 wr[i] = u;
               }
               __syncwarp();
-              const int64_t row_shift = rep == 1 ? P.dbl_row_offset : 0;
               if (seg * 8 < cols) {
 #pragma unroll
                 for (int r4 = 0; r4 < 8; ++r4) {
@@ -381,6 +412,12 @@ gemm_kernel(const __grid_constant__ Maps maps, const __grid_constant__ Group grp
               const int rg = row_base + rl;
               float4 a = *reinterpret_cast<const float4*>(stg + rl * EPI_ROW_BYTES + seg * 16);
               a.x += bb.x; a.y += bb.y; a.z += bb.z; a.w += bb.w;
+              if constexpr (EPI == DIT4SR_EPI_BIAS_GELU) {
+                a.x = gelu_tanh_precise(a.x); a.y = gelu_tanh_precise(a.y);
+                a.z = gelu_tanh_precise(a.z); a.w = gelu_tanh_precise(a.w);
+              } else if constexpr (EPI == DIT4SR_EPI_BIAS_SILU) {
+                a.x = silu_precise(a.x); a.y = silu_precise(a.y); a.z = silu_precise(a.z); a.w = silu_precise(a.w);
+              }
               if constexpr (EPI == DIT4SR_EPI_GATE_RESID) {
                 const float4 rr = rv[ch & 1][r4];
                 a.x = fmaf(gg.x, a.x, rr.x);
@@ -436,8 +473,8 @@ static int check_problem(const dit4sr_gemm_params* p, int epilogue) {
   DIT4SR_REQUIRE(p->bias == nullptr || host::aligned16(p->bias), DIT4SR_E_ALIGN, "gemm: bias must be 16-byte aligned");
   DIT4SR_REQUIRE(p->epilogue == epilogue, DIT4SR_E_BADARG, "gemm: all problems of a group must share the epilogue");
   if (epilogue == DIT4SR_EPI_QKV_NORM) {
-    DIT4SR_REQUIRE(p->N % 64 == 0 && p->sec_cols >= 0 && p->sec_cols % 64 == 0 && p->c_dtype == DIT4SR_DT_BF16,
-                   DIT4SR_E_SHAPE, "gemm/QKV_NORM: N and sec_cols must be multiples of 64 and C bf16");
+    DIT4SR_REQUIRE(p->N % 64 == 0 && p->sec_cols >= 0 && p->sec_cols % 64 == 0, DIT4SR_E_SHAPE,
+                   "gemm/QKV_NORM: N and sec_cols must be multiples of 64");
     DIT4SR_REQUIRE((p->norm_w0 == nullptr || host::aligned16(p->norm_w0)) &&
                        (p->norm_w1 == nullptr || host::aligned16(p->norm_w1)),
                    DIT4SR_E_ALIGN, "gemm/QKV_NORM: norm weights must be 16-byte aligned");
@@ -448,9 +485,6 @@ static int check_problem(const dit4sr_gemm_params* p, int epilogue) {
                    DIT4SR_E_BADARG, "gemm/GATE_RESID: needs 16-byte aligned fp32 resid and fp32 C");
     DIT4SR_REQUIRE(p->gate == nullptr || (host::aligned16(p->gate) && p->gate_batch_stride % 4 == 0), DIT4SR_E_ALIGN,
                    "gemm/GATE_RESID: gate must be 16-byte aligned");
-  }
-  if (epilogue == DIT4SR_EPI_BIAS_GELU || epilogue == DIT4SR_EPI_BIAS_SILU) {
-    DIT4SR_REQUIRE(p->c_dtype == DIT4SR_DT_BF16, DIT4SR_E_BADARG, "gemm: activation epilogues write bf16");
   }
   return 0;
 }

@@ -49,7 +49,10 @@ def ln_modulate(x, shift, scale, out, shift2=None, scale2=None, out2=None, eps=1
     x = _as3(x)
     out = _as3(out)
     _req(x, torch.float32, "x")
-    _req(out, torch.bfloat16, "out")
+    out_dtype = out.dtype
+    if out_dtype not in (torch.bfloat16, torch.float32):
+        raise _lib.Dit4srError("ln_modulate: out must be bf16 or fp32")
+    _req(out, out_dtype, "out")
     for n, t in (("shift", shift), ("scale", scale)):
         _req(t, torch.float32, n)
     B, R, D = x.shape
@@ -62,11 +65,12 @@ def ln_modulate(x, shift, scale, out, shift2=None, scale2=None, out2=None, eps=1
     p.out, p.ldo, p.o_batch_stride = _ptr(out), out.stride(1), out.stride(0)
     if out2 is not None:
         out2 = _as3(out2)
-        _req(out2, torch.bfloat16, "out2")
+        _req(out2, out_dtype, "out2")
         if out2.stride() != out.stride():
             raise _lib.Dit4srError("ln_modulate: out and out2 must share strides")
         p.out2, p.shift2, p.scale2 = _ptr(out2), _ptr(shift2), _ptr(scale2)
     p.batches, p.rows, p.dim, p.eps = B, R, D, eps
+    p.out_f32 = 1 if out_dtype == torch.float32 else 0
     check(_lib.load().dit4sr_ln_modulate(C.byref(p), _stream()), "dit4sr_ln_modulate")
     _count()
 
@@ -240,4 +244,66 @@ def cast(x, out):
         raise _lib.Dit4srError("cast: tensors must be contiguous")
     d = 0 if x.dtype == torch.float32 else 1
     check(_lib.load().dit4sr_cast(_ptr(x), _ptr(out), x.numel(), d, _stream()), "dit4sr_cast")
+    _count()
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# fp32-accurate ("bf16x3") mode helpers
+# ---------------------------------------------------------------------------------------------------------------
+def split3(x, out, pattern=0, rows_pad=None):
+    """x fp32 [B, R, C] (or [R, C]) -> out bf16 [B*rows_pad, 3C]: pattern 0 = [hi|hi|lo] (A), 1 = [hi|lo|hi] (W)."""
+    x = _as3(x)
+    _req(x, torch.float32, "x")
+    _req(out, torch.bfloat16, "out")
+    B, R, Cc = x.shape
+    rp = R if rows_pad is None else rows_pad
+    if not out.is_contiguous() or out.numel() != B * rp * 3 * Cc:
+        raise _lib.Dit4srError("split3: out must be contiguous [B*rows_pad, 3*cols]")
+    check(_lib.load().dit4sr_split3(_ptr(x), x.stride(1), x.stride(0), _ptr(out), B, R, rp, Cc, pattern, _stream()),
+          "dit4sr_split3")
+    _count()
+
+
+def split3_transposed(v, out, rows_pad):
+    """v fp32 [R, C] -> out bf16 [C, 3*rows_pad] = [Vh^T | Vl^T | Vh^T]."""
+    _req(v, torch.float32, "v")
+    _req(out, torch.bfloat16, "out")
+    R, Cc = v.shape
+    if not out.is_contiguous() or out.numel() != Cc * 3 * rows_pad:
+        raise _lib.Dit4srError("split3_transposed: out must be contiguous [cols, 3*rows_pad]")
+    check(_lib.load().dit4sr_split3_transposed(_ptr(v), v.stride(0), _ptr(out), R, rows_pad, Cc, _stream()),
+          "dit4sr_split3_transposed")
+    _count()
+
+
+def softmax_rows(s, cols_valid, scale):
+    """in-place fp32 softmax(scale * s[:, :cols_valid]) per row; padding columns zeroed."""
+    _req(s, torch.float32, "s")
+    R, Ct = s.shape
+    check(_lib.load().dit4sr_softmax_rows_f32(_ptr(s), s.stride(0), R, cols_valid, Ct, float(scale), _stream()),
+          "dit4sr_softmax_rows_f32")
+    _count()
+
+
+def add_f32(dst, src):
+    _req(dst, torch.float32, "dst")
+    _req(src, torch.float32, "src")
+    if dst.shape != src.shape or dst.dim() != 3:
+        raise _lib.Dit4srError("add_f32: shapes must match ([B, R, C])")
+    B, Rr, Cc = dst.shape
+    check(_lib.load().dit4sr_add_f32(_ptr(dst), dst.stride(1), dst.stride(0), _ptr(src), src.stride(1), src.stride(0),
+                                     B, Rr, Cc, _stream()), "dit4sr_add_f32")
+    _count()
+
+
+def dwconv3x3_add_f32(u_hq, u_lr, weight9, bias, grid, grid_w=0, lr_row_offset=0):
+    for n, t in (("u_hq", u_hq), ("u_lr", u_lr), ("weight9", weight9), ("bias", bias)):
+        _req(t, torch.float32, n)
+    B, N, Cc = u_hq.shape
+    W = grid_w or grid
+    if N != grid * W or u_lr.shape[1] % W or u_hq.stride(1) != u_lr.stride(1):
+        raise _lib.Dit4srError("dwconv3x3_add_f32: shape mismatch")
+    check(_lib.load().dit4sr_dwconv3x3_add_f32(_ptr(u_hq), _ptr(u_lr), u_hq.stride(1), u_hq.stride(0), u_lr.stride(0),
+                                               _ptr(weight9), _ptr(bias), B, grid, W, u_lr.shape[1] // W, lr_row_offset,
+                                               Cc, _stream()), "dit4sr_dwconv3x3_add_f32")
     _count()

@@ -23,7 +23,7 @@
 extern "C" {
 #endif
 
-#define DIT4SR_ABI_VERSION 1
+#define DIT4SR_ABI_VERSION 2
 
 enum {
   DIT4SR_OK = 0,
@@ -56,6 +56,7 @@ typedef struct {
   int64_t ldo; int64_t o_batch_stride;
   int batches; int rows; int dim;
   float eps;
+  int out_f32;                         /* 1: out/out2 are fp32 (fp32-accurate mode) instead of bf16 */
 } dit4sr_ln_modulate_params;
 int dit4sr_ln_modulate(const dit4sr_ln_modulate_params* p, void* stream);
 
@@ -89,7 +90,8 @@ int dit4sr_dwconv3x3_add(const dit4sr_dwconv3x3_params* p, void* stream);
  * PatchEmbed.proj / time_text_embed in transformer_sd3.py:326-331,382-383) together with the elementwise work
  * that follows it in the reference, selected by `epilogue`:
  *   DIT4SR_EPI_BIAS       C = acc + bias                                   (C bf16 or fp32)
- *   DIT4SR_EPI_BIAS_GELU  C = gelu_tanh(acc + bias)                        (diffusers GELU(approximate="tanh"))
+ *   DIT4SR_EPI_BIAS_GELU  C = gelu_tanh(acc + bias)                        (diffusers GELU(approximate="tanh"); tanh.approx for
+ *                         bf16 C, tanhf for fp32 C)
  *   DIT4SR_EPI_BIAS_SILU  C = silu(acc + bias)
  *   DIT4SR_EPI_QKV_NORM   per 64-wide head: y = acc + bias; columns [0,sec_cols) use RMSNorm weight norm_w0,
  *                         [sec_cols,2*sec_cols) norm_w1, the rest none (q|k|v fused projection followed by
@@ -167,6 +169,27 @@ int dit4sr_silu_cast(const float* x, void* y_bf16, int64_t n, void* stream);
  * residual add of attention.py:545 when the attention output arrives through the sequence-parallel all-to-all. */
 int dit4sr_add_bf16(void* dst, int64_t dst_row_stride, int64_t dst_batch_stride, const void* src, int64_t src_row_stride,
                     int64_t src_batch_stride, int batches, int rows, int cols, void* stream);
+/* ---------------------------------------------------------------------------------------------------------------
+ * fp32-accurate mode ("bf16x3"): activations stay fp32 between kernels and every tensor-core product A W^T is evaluated
+ * as Ah Wh^T + Ah Wl^T + Al Wh^T (hi/lo bf16 splits) by concatenating the three terms along K, so the unchanged
+ * dit4sr_gemm_bf16 runs on A' = [Ah|Ah|Al], W' = [Wh|Wl|Wh] with K' = 3K (fp32 C is accepted by every epilogue).
+ * Attention is evaluated unfused per (batch, head): scores GEMM -> fp32 row softmax -> probabilities x values GEMM.
+ */
+/* x fp32 [batches, rows, cols] (ldx, x_batch_stride) -> out bf16 [batches*rows_pad, 3*cols]; pattern 0 = [hi|hi|lo]
+ * (A operand), 1 = [hi|lo|hi] (W operand); rows [rows, rows_pad) are zero-filled. */
+int dit4sr_split3(const float* x, int64_t ldx, int64_t x_batch_stride, void* out_bf16, int batches, int rows,
+                  int rows_pad, int cols, int pattern, void* stream);
+/* v fp32 [rows, cols] (ldv) -> out bf16 [cols, 3*rows_pad] = [Vh^T | Vl^T | Vh^T] (W operand of P V). */
+int dit4sr_split3_transposed(const float* v, int64_t ldv, void* out_bf16, int rows, int rows_pad, int cols, void* stream);
+/* in-place softmax(scale * s) over the first cols_valid columns of each row of s [rows, cols_total] (ld); the padding
+ * columns are set to 0 (model_dit4sr/attention.py:528, the softmax inside F.scaled_dot_product_attention). */
+int dit4sr_softmax_rows_f32(float* s, int64_t ld, int rows, int cols_valid, int cols_total, float scale, void* stream);
+int dit4sr_add_f32(float* dst, int64_t dst_row_stride, int64_t dst_batch_stride, const float* src,
+                   int64_t src_row_stride, int64_t src_batch_stride, int batches, int rows, int cols, void* stream);
+/* fp32 version of dit4sr_dwconv3x3_add (same semantics, explicit arguments). */
+int dit4sr_dwconv3x3_add_f32(float* u_hq, const float* u_lr, int64_t ld, int64_t hq_batch_stride,
+                             int64_t lr_batch_stride, const float* weight9, const float* bias, int batches, int grid_h,
+                             int grid_w, int lr_grid_h, int lr_row_offset, int channels, void* stream);
 /* y = x (fp32 -> bf16 or bf16 -> fp32), n elements; dir 0 = f32->bf16, 1 = bf16->f32 */
 int dit4sr_cast(const void* x, void* y, int64_t n, int dir, void* stream);
 
