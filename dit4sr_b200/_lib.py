@@ -63,6 +63,9 @@ SYMBOLS = {
     "dit4sr_add_f32": (c_int, [c_vp, c_i64, c_i64, c_vp, c_i64, c_i64, c_int, c_int, c_int, c_vp]),
     "dit4sr_dwconv3x3_add_f32": (c_int, [c_vp, c_vp, c_i64, c_i64, c_i64, c_vp, c_vp, c_int, c_int, c_int, c_int, c_int,
                                          c_int, c_vp]),
+    "dit4sr_patchify_f32": (c_int, [c_vp, c_vp, c_int, c_int, c_int, c_int, c_vp]),
+    "dit4sr_timestep_features_f32": (c_int, [c_vp, c_vp, c_int, c_vp]),
+    "dit4sr_silu_f32": (c_int, [c_vp, c_vp, c_i64, c_vp]),
     "dit4sr_cast": (c_int, [c_vp, c_vp, c_i64, c_int, c_vp]),
 }
 

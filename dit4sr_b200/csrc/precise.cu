@@ -107,6 +107,39 @@ __global__ void dwconv3x3_f32_kernel(float* __restrict__ hq, const float* __rest
   hq[b * hbs + ((int64_t)y * GW + x) * ld + c] += acc;
 }
 
+
+// fp32 head kernels of the accuracy mode (same math as misc.cu, fp32 outputs)
+__global__ void patchify_f32_kernel(const float* __restrict__ x, float* __restrict__ out, int B, int C, int H, int W) {
+  const int Hp = H / 2, Wp = W / 2;
+  const int64_t total = (int64_t)B * Hp * Wp * C;
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const int c = (int)(i % C);
+  const int64_t tok = i / C;
+  const int wp = (int)(tok % Wp);
+  const int hp = (int)((tok / Wp) % Hp);
+  const int b = (int)(tok / ((int64_t)Wp * Hp));
+  const float* src = x + (((int64_t)b * C + c) * H + 2 * hp) * W + 2 * wp;
+  *reinterpret_cast<float4*>(out + tok * (C * 4) + c * 4) = make_float4(src[0], src[1], src[W], src[W + 1]);
+}
+
+__global__ void timestep_features_f32_kernel(const float* __restrict__ t, float* __restrict__ out, int B) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= B * 128) return;
+  const int b = i / 128, k = i % 128;
+  const float freq = expf(-9.210340371976184f * (float)k / 128.0f);
+  const float a = t[b] * freq;
+  out[b * 256 + k] = cosf(a);
+  out[b * 256 + 128 + k] = sinf(a);
+}
+
+__global__ void silu_f32_kernel(const float* __restrict__ x, float* __restrict__ y, int64_t n) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float v = x[i];
+  y[i] = v / (1.0f + expf(-v));
+}
+
 static inline unsigned blocks(int64_t n, int t) { return (unsigned)((n + t - 1) / t); }
 
 }  // namespace precise
@@ -169,6 +202,36 @@ int dit4sr_dwconv3x3_add_f32(float* u_hq, const float* u_lr, int64_t ld, int64_t
   precise::dwconv3x3_f32_kernel<<<precise::blocks(n, 256), 256, 0, stream>>>(
       u_hq, u_lr, ld, hq_batch_stride, lr_batch_stride, weight9, bias, batches, grid_h, grid_w, lr_grid_h, lr_row_offset,
       channels);
+  DIT4SR_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int dit4sr_patchify_f32(const float* x, float* patches, int batches, int channels, int height, int width, void* stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  DIT4SR_REQUIRE(x && patches && batches > 0 && channels > 0, DIT4SR_E_BADARG, "patchify_f32: bad argument");
+  DIT4SR_REQUIRE(height % 2 == 0 && width % 2 == 0 && height > 0 && width > 0, DIT4SR_E_SHAPE,
+                 "patchify_f32: height/width must be even");
+  DIT4SR_REQUIRE(host::aligned16(patches), DIT4SR_E_ALIGN, "patchify_f32: output not 16-byte aligned");
+  const int64_t total = (int64_t)batches * (height / 2) * (width / 2) * channels;
+  precise::patchify_f32_kernel<<<precise::blocks(total, 256), 256, 0, stream>>>(x, patches, batches, channels, height,
+                                                                               width);
+  DIT4SR_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int dit4sr_timestep_features_f32(const float* timesteps, float* out, int batches, void* stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  DIT4SR_REQUIRE(timesteps && out && batches > 0, DIT4SR_E_BADARG, "timestep_features_f32: bad argument");
+  precise::timestep_features_f32_kernel<<<precise::blocks((int64_t)batches * 128, 128), 128, 0, stream>>>(timesteps, out,
+                                                                                                          batches);
+  DIT4SR_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int dit4sr_silu_f32(const float* x, float* y, int64_t n, void* stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  DIT4SR_REQUIRE(x && y && n > 0, DIT4SR_E_BADARG, "silu_f32: bad argument");
+  precise::silu_f32_kernel<<<precise::blocks(n, 256), 256, 0, stream>>>(x, y, n);
   DIT4SR_CUDA(cudaGetLastError());
   return 0;
 }

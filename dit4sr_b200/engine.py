@@ -27,11 +27,23 @@ def _f32(t):
     return t.detach().to(torch.float32).contiguous()
 
 
+def _pack_w(w, precise):
+    """bf16 [N, K] tensor-core operand; fp32-accurate mode: [N, 3K] = [hi | lo | hi] bf16 split of the fp32 weight
+    (pairs with activations packed [hi | hi | lo], so one K'=3K GEMM evaluates Ah Wh + Ah Wl + Al Wh)."""
+    if not precise:
+        return _bf16(w)
+    w = _f32(w)
+    out = torch.empty(w.shape[0], 3 * w.shape[1], device=w.device, dtype=torch.bfloat16)
+    ops.split3(w, out, pattern=1)
+    return out
+
+
 class _Lin:
     """bf16 weight [N,K] + fp32 bias [N] (possibly a concatenation of several nn.Linear)."""
 
-    def __init__(self, *linears):
-        self.w = _bf16(torch.cat([l.weight for l in linears], dim=0)) if len(linears) > 1 else _bf16(linears[0].weight)
+    def __init__(self, *linears, precise=False):
+        self.w = _pack_w(torch.cat([l.weight for l in linears], dim=0) if len(linears) > 1 else linears[0].weight,
+                         precise)
         self.b = _f32(torch.cat([l.bias for l in linears], dim=0)) if len(linears) > 1 else _f32(linears[0].bias)
 
 
@@ -39,21 +51,25 @@ class _Folded:
     """Exact-algebra fold of a chained pair of Linears  y = Wc (W x + b) + bc  =  (Wc W) x + (Wc b + bc)  (quirk Q3:
     `to_x_control(to_x(lr))`, attention.py:475-477). Product formed in fp32, stored as one bf16 weight."""
 
-    def __init__(self, *pairs):
+    def __init__(self, *pairs, precise=False):
         """pairs: (inner, outer) Linears; several pairs are concatenated along the output dimension."""
         if len(pairs) == 2 and not isinstance(pairs[0], (tuple, list)):
             pairs = (pairs,)
         ws, bs = [], []
         for inner, outer in pairs:
-            wc, w = outer.weight.detach().float(), inner.weight.detach().float()
-            ws.append(wc @ w)
-            bs.append(wc @ inner.bias.detach().float() + outer.bias.detach().float())
-        self.w = torch.cat(ws, 0).to(torch.bfloat16).contiguous()
+            # load-time weight preparation; fp64 in the fp32-accurate mode so the fold itself adds no fp32 rounding
+            dt = torch.float64 if precise else torch.float32
+            wc, w = outer.weight.detach().to(dt), inner.weight.detach().to(dt)
+            ws.append((wc @ w).float())
+            bs.append((wc @ inner.bias.detach().to(dt) + outer.bias.detach().to(dt)).float())
+        self.w = _pack_w(torch.cat(ws, 0), precise)
         self.b = torch.cat(bs, 0).contiguous()
 
 
 class _AttnPack:
-    def __init__(self, attn, has_text: bool, fold: bool):
+    def __init__(self, attn, has_text: bool, fold: bool, precise: bool = False):
+        from functools import partial
+        _Lin, _Folded = partial(globals()["_Lin"], precise=precise), partial(globals()["_Folded"], precise=precise)
         self.qk_norm = attn.norm_q is not None
         self.fold = fold
         self.qkv = _Lin(attn.to_q, attn.to_k, attn.to_v)
@@ -85,11 +101,13 @@ class _AttnPack:
 
 
 class _BlockPack:
-    def __init__(self, blk, fold):
+    def __init__(self, blk, fold, precise=False):
+        from functools import partial
+        _Lin = partial(globals()["_Lin"], precise=precise)
         self.dual = blk.use_dual_attention
         self.last = blk.context_pre_only
-        self.attn = _AttnPack(blk.attn, True, fold)
-        self.attn2 = _AttnPack(blk.attn2, False, fold) if self.dual else None
+        self.attn = _AttnPack(blk.attn, True, fold, precise)
+        self.attn2 = _AttnPack(blk.attn2, False, fold, precise) if self.dual else None
         self.ff1, self.ff2 = _Lin(blk.ff.net[0].proj), _Lin(blk.ff.net[2])
         cw = blk.ff.control_conv.weight
         self.conv_w9 = _f32(cw.reshape(cw.shape[0], 9).t())           # tap-major [9, F]
@@ -105,13 +123,26 @@ class _BlockPack:
 
 
 class Engine:
-    def __init__(self, model, fold_lr_chains: Optional[bool] = None, sp=None):
+    def __init__(self, model, fold_lr_chains: Optional[bool] = None, sp=None, precise: Optional[bool] = None):
         """fold_lr_chains: fold `to_x_control(to_x(.))` into one GEMM per projection (exact algebra, one bf16 rounding
-        of the product weight instead of a bf16 intermediate activation). Default on; DIT4SR_FOLD_LR=0 turns it off."""
+        of the product weight instead of a bf16 intermediate activation). Default on; DIT4SR_FOLD_LR=0 turns it off.
+
+        precise: the fp32-accurate mode (velocity within 1e-4 of the fp32 reference, BASELINE north_star): activations
+        stay fp32 between kernels, every tensor-core product runs on bf16 hi/lo splits (three bf16 products per fp32
+        product, K' = 3K on the same tcgen05 GEMM kernel) and attention is evaluated unfused per head (scores GEMM ->
+        fp32 softmax -> P V GEMM).  Default: on iff the module's parameters are fp32 (DIT4SR_FP32_MODE=bf16 keeps the
+        fast bf16 path for fp32 modules)."""
         import os
         if fold_lr_chains is None:
             fold_lr_chains = os.environ.get("DIT4SR_FOLD_LR", "1") != "0"
         self.fold_lr_chains = fold_lr_chains
+        if precise is None:
+            precise = (next(model.parameters()).dtype == torch.float32
+                       and os.environ.get("DIT4SR_FP32_MODE", "fp32") != "bf16")
+        self.precise = bool(precise)
+        if self.precise and sp is not None:
+            raise NotImplementedError("the fp32-accurate mode is single-GPU (no sequence parallelism)")
+        self._scratch: Dict = {}
         self.sp = sp    # parallel.SequenceParallel or None: Ulysses sequence parallelism over the token-grid rows
         self.streams = 3 if getattr(model, "_ocr_branch", False) else 2   # image streams: [HQ | LR] or [HQ | LR | OCR]
         cfg = model.config
@@ -125,7 +156,9 @@ class Engine:
         if cfg.caption_projection_dim != self.D:
             raise ValueError("dit4sr_b200: caption_projection_dim must equal the inner dim (joint attention)")
         D = self.D
-        self.blocks = [_BlockPack(b, fold_lr_chains) for b in model.transformer_blocks]
+        from functools import partial
+        _Lin = partial(globals()["_Lin"], precise=self.precise)
+        self.blocks = [_BlockPack(b, fold_lr_chains, self.precise) for b in model.transformer_blocks]
         # every adaLN linear of the model in one weight: temb is the same for all blocks, so one GEMM per step
         mods, self.mod_off = [], []
         off = 0
@@ -143,7 +176,7 @@ class Engine:
         self.mod_total = off
         self.mod = _Lin(*mods)
         pe = model.pos_embed.proj
-        self.patch_w = _bf16(pe.weight.reshape(D, -1))
+        self.patch_w = _pack_w(pe.weight.reshape(D, -1), self.precise)
         self.patch_b = _f32(pe.bias)
         self.pos_table = model.pos_embed.pos_embed
         tt = model.time_text_embed
@@ -203,7 +236,8 @@ class Engine:
         D, F = self.D, 4 * self.D
         I = self.streams * N            # image tokens
         S = I + T
-        bf, f32 = torch.bfloat16, torch.float32
+        f32 = torch.float32
+        bf = f32 if self.precise else torch.bfloat16     # activation dtype between kernels
 
         def e(*shape, dtype=bf):
             return torch.empty(*shape, device=device, dtype=dtype)
@@ -226,6 +260,66 @@ class Engine:
                       lr_pad=e(B, N + 2 * grid_w, F))
         self._ws[key] = ws
         return ws
+
+    # ------------------------------------------------------------------------------------------------ GEMM dispatch
+    def _scr(self, key, numel, dtype):
+        """Grow-only scratch buffers of the fp32-accurate mode (operand splits, per-head scores)."""
+        t = self._scratch.get(key)
+        if t is None or t.numel() < numel or t.dtype != dtype:
+            t = torch.empty(numel, device=self._dev, dtype=dtype)
+            self._scratch[key] = t
+        return t[:numel]
+
+    def _split_a(self, A, slot):
+        """fp32 activations [B,R,K] (any row/batch stride) -> contiguous bf16 [B,R,3K] = [hi | hi | lo]."""
+        A3 = A.unsqueeze(0) if A.dim() == 2 else A
+        B, Rr, K = A3.shape
+        out = self._scr(("a3", slot), B * Rr * 3 * K, torch.bfloat16)
+        self._run("split", ops.split3, A3, out, 0)
+        out = out.view(B, Rr, 3 * K)
+        return out[0] if A.dim() == 2 else out
+
+    def _gg(self, name, problems):
+        """One grouped GEMM launch; in the fp32-accurate mode the fp32 A operands are split first (K' = 3K)."""
+        if self.precise:
+            problems = [dict(p, A=self._split_a(p["A"], i)) for i, p in enumerate(problems)]
+        self._run(name, ops.gemm_grouped, problems)
+
+    def _g1(self, name, A, lin_w, bias, out, epilogue, **kw):
+        self._gg(name, [dict(A=A, W=lin_w, bias=bias, out=out, epilogue=epilogue, **kw)])
+
+    def _attention_core_precise(self, ws, S, seq_q, n_in, lr_rows):
+        """softmax(q k^T / 8) v per (batch, head) in the fp32-accurate mode (attention.py:528): scores and P V on the
+        GEMM kernel with split operands, fp32 row softmax in between; then the Q2 residual on the LR rows."""
+        D, H, R = self.D, self.H, self._run
+        qkv, o = ws["qkv"], ws["o"]
+        B = qkv.shape[0]
+        Sp = (S + 127) // 128 * 128
+        bf = torch.bfloat16
+        q3 = self._scr("q3", H * seq_q * 192, bf).view(H, seq_q, 192)
+        k3 = self._scr("k3", H * Sp * 192, bf).view(H, Sp, 192)
+        sc = self._scr("sc", H * seq_q * Sp, torch.float32).view(H, seq_q, Sp)
+        p3 = self._scr("p3", H * seq_q * 3 * Sp, bf).view(H, seq_q, 3 * Sp)
+        vt = self._scr("vt", H * 64 * 3 * Sp, bf).view(H, 64, 3 * Sp)
+        G = ops.GEMM_MAX_GROUP
+        for b in range(B):
+            def heads(c0, rows):   # [H, rows, 64] view of one q/k/v section of image b
+                return qkv[b, :rows, c0:c0 + D].unflatten(-1, (H, 64)).permute(1, 0, 2)
+            R("split", ops.split3, heads(0, seq_q), q3.view(-1), 0)
+            R("split", ops.split3, heads(D, S), k3.view(-1), 1, Sp)
+            for h0 in range(0, H, G):
+                R("attn", ops.gemm_grouped, [dict(A=q3[h], W=k3[h], bias=None, out=sc[h], epilogue=ops.EPI_BIAS)
+                                             for h in range(h0, min(H, h0 + G))])
+            R("attn", ops.softmax_rows, sc.view(H * seq_q, Sp), S, 0.125)
+            R("split", ops.split3, sc.view(1, H * seq_q, Sp), p3.view(-1), 0)
+            for h in range(H):
+                R("split", ops.split3_transposed, qkv[b, :S, 2 * D + h * 64: 2 * D + (h + 1) * 64], vt[h].view(-1), Sp)
+            for h0 in range(0, H, G):
+                R("attn", ops.gemm_grouped, [dict(A=p3[h], W=vt[h], bias=None, out=o[b, :seq_q, h * 64:(h + 1) * 64],
+                                                  epilogue=ops.EPI_BIAS) for h in range(h0, min(H, h0 + G))])
+        r0, r1 = lr_rows
+        if r1 > r0:
+            R("attn", ops.add_f32, o[:, r0:r1], n_in[:, r0:r1])
 
     # ------------------------------------------------------------------------------------------------ attention
     def _attention(self, ap: _AttnPack, ws, n_in, nc, N, T, gate, c_gate, last):
@@ -265,11 +359,13 @@ class Engine:
         if ap.has_text:
             g1.append(dict(A=nc, W=ap.add.w, bias=ap.add.b, out=qkv[:, I:S], epilogue=E,
                            **(dict(norm_w0=ap.waq, norm_w1=ap.wak, sec_cols=D) if ap.qk_norm else {})))
-        R("qkv_group", ops.gemm_grouped, g1)
+        self._gg("qkv_group", g1)
         if g2:
-            R("lr2_group", ops.gemm_grouped, g2)
+            self._gg("lr2_group", g2)
         # the last block's text queries are discarded by the reference (context_pre_only): do not compute them
-        if self.sp is None:
+        if self.precise:
+            self._attention_core_precise(ws, S, I if (last or not ap.has_text) else S, n_in, (N, I))
+        elif self.sp is None:
             seq_q = I if (last or not ap.has_text) else S
             R("attn", ops.attention, qkv[:, :S, :D], qkv[:, :S, D:2 * D], qkv[:, :S, 2 * D:], o, H, seq_q=seq_q,
               lr_res=n_in, lr_rows=(N, I))   # Q2: the LR (and OCR) rows get their normed+modulated input added back
@@ -282,7 +378,7 @@ class Engine:
             g3.append(dict(A=o[:, 2 * N:I], W=ap.outo.w, bias=ap.outo.b, out=x[:, 2 * N:I], epilogue=G, gate=gate))
         if ap.has_text and not last:
             g3.append(dict(A=o[:, I:S], W=ap.add_out.w, bias=ap.add_out.b, out=ctx, epilogue=G, gate=c_gate))
-        R("out_group", ops.gemm_grouped, g3)
+        self._gg("out_group", g3)
 
     def _attention_sp(self, ap, ws, n_in, N, I, S, last):
         """Ulysses: all-to-all (tokens -> heads), local attention on H/P heads over the whole joint sequence,
@@ -310,7 +406,9 @@ class Engine:
     def _conv_add(self, ws, dst, src, w9, b, rows, grid_w):
         """dst += dwconv3x3(src) + b on a (rows x grid_w) token grid; with sequence parallelism the source rows get a
         1-row halo from the neighbouring ranks first."""
-        if self.sp is None:
+        if self.precise:
+            self._run("dwconv", ops.dwconv3x3_add_f32, dst, src, w9, b, rows, grid_w=grid_w)
+        elif self.sp is None:
             self._run("dwconv", ops.dwconv3x3_add, dst, src, w9, b, rows, grid_w=grid_w)
         else:
             padded = self.sp.halo_rows(src, grid_w, out=ws["lr_pad"])
@@ -324,7 +422,7 @@ class Engine:
         recorded once per input shape; replay removes the per-launch host cost, which matters for small batches).
         Same results as `forward` -- the same kernels run. Falls back to direct launches under sequence parallelism,
         while profiling, or if capture is unavailable."""
-        if not self.use_cuda_graph or self.sp is not None or self._prof is not None:
+        if not self.use_cuda_graph or self.sp is not None or self._prof is not None or self.precise:
             return self.forward(hidden_states, controlnet_image, encoder_hidden_states, pooled_projections, timestep,
                                 out=out, euler=euler)
         B = hidden_states.shape[0]
@@ -405,28 +503,31 @@ class Engine:
             raise ValueError("3-stream model: attn2 halves the 3N image tokens, N must be even")
         T = encoder_hidden_states.shape[1]
         dev = hidden_states.device
+        self._dev = dev
         ws = self._workspace(B, N, T, dev, grid_w=grid if self.sp is not None else 0)
         x, ctx, n1, n2, nc, mod = ws["x"], ws["ctx"], ws["n1"], ws["n2"], ws["nc"], ws["mod"]
 
         # ---- head: temb = MLP(sincos(t)) + MLP(pooled)  (CombinedTimestepTextProjEmbeddings, transformer_sd3.py:327)
         ws["t"].copy_(timestep.to(device=dev, dtype=torch.float32).expand(B))
         R("head", ops.timestep_features, ws["t"], ws["tf"])
-        R("head", ops.gemm, ws["tf"], self.t1.w, self.t1.b, ws["th"], ops.EPI_BIAS_SILU)
-        R("head", ops.gemm, ws["th"], self.t2.w, self.t2.b, ws["temb"], ops.EPI_BIAS)
+        gm = self._g1
+        gm("head", ws["tf"], self.t1.w, self.t1.b, ws["th"], ops.EPI_BIAS_SILU)
+        gm("head", ws["th"], self.t2.w, self.t2.b, ws["temb"], ops.EPI_BIAS)
         ws["pooled"].copy_(pooled_projections)
-        R("head", ops.gemm, ws["pooled"], self.p1.w, self.p1.b, ws["ph"], ops.EPI_BIAS_SILU)
-        R("head", ops.gemm, ws["ph"], self.p2.w, self.p2.b, ws["temb"], ops.EPI_GATE_RESID)
+        gm("head", ws["pooled"], self.p1.w, self.p1.b, ws["ph"], ops.EPI_BIAS_SILU)
+        gm("head", ws["ph"], self.p2.w, self.p2.b, ws["temb"], ops.EPI_GATE_RESID)
         R("head", ops.silu_cast, ws["temb"], ws["st"])
-        R("mod_gemm", ops.gemm, ws["st"], self.mod.w, self.mod.b, mod, ops.EPI_BIAS)   # all adaLN vectors of the step
+        gm("mod_gemm", ws["st"], self.mod.w, self.mod.b, mod, ops.EPI_BIAS)   # all adaLN vectors of the step
         # ---- patch embed (+pos) for both streams, context embedder  (:326-332)
         streams = [(hidden_states, x[:, :N]), (controlnet_image, x[:, N:2 * N])]
         if self.streams == 3:   # the OCR stream starts as a second pos_embed(controlnet_image) (ocr model :334-337)
             streams.append((controlnet_image, x[:, 2 * N:]))
         for src, dst_rows in streams:
-            R("head", ops.patchify, src.contiguous(), ws["patches"])
-            R("head", ops.gemm, ws["patches"], self.patch_w, self.patch_b, dst_rows, ops.EPI_GATE_RESID, resid=pos)
+            src = src.contiguous()
+            R("head", ops.patchify, src.float() if self.precise else src, ws["patches"])
+            gm("head", ws["patches"], self.patch_w, self.patch_b, dst_rows, ops.EPI_GATE_RESID, resid=pos)
         ws["enc"].copy_(encoder_hidden_states)
-        R("head", ops.gemm, ws["enc"], self.ctx_embed.w, self.ctx_embed.b, ctx, ops.EPI_BIAS)
+        gm("head", ws["enc"], self.ctx_embed.w, self.ctx_embed.b, ctx, ops.EPI_BIAS)
 
         # ---- blocks (:336-370)
         for i, bp in enumerate(self.blocks):
@@ -464,20 +565,20 @@ class Engine:
                 ff1.append(dict(A=nc, W=bp.ffc1.w, bias=bp.ffc1.b, out=ws["uc"], epilogue=ops.EPI_BIAS_GELU))
                 ff2.append(dict(A=ws["uc"], W=bp.ffc2.w, bias=bp.ffc2.b, out=ctx, epilogue=ops.EPI_GATE_RESID,
                                 gate=c_gate_mlp))
-            R("ff1", ops.gemm_grouped, ff1)
+            self._gg("ff1", ff1)
             u = ws["u"]
             self._conv_add(ws, u[:, :N], u[:, N:2 * N], bp.conv_w9, bp.conv_b, rows, grid)
             if bp.ocr:   # u_hq += conv_o(u_ocr); then u_ocr += conv_h(u_hq updated)  (ocr attention file :184-206)
                 self._conv_add(ws, u[:, :N], u[:, 2 * N:], bp.conv_o_w9, bp.conv_o_b, rows, grid)
                 self._conv_add(ws, u[:, 2 * N:], u[:, :N], bp.conv_h_w9, bp.conv_h_b, rows, grid)
-            R("ff2", ops.gemm_grouped, ff2)
+            self._gg("ff2", ff2)
             if feat_hook is not None:
                 feat_hook(i, x)
 
         # ---- tail: drop the LR half, norm_out (scale, shift order), proj_out, unpatchify (:379-391)
         so = self.mod_out_off
         R("tail", ops.ln_modulate, x[:, :N], mod[:, so + D: so + 2 * D], mod[:, so: so + D], n1[:, :N])
-        R("tail", ops.gemm, n1[:, :N], self.proj_out.w, self.proj_out.b, ws["tok"], ops.EPI_BIAS)
+        gm("tail", n1[:, :N], self.proj_out.w, self.proj_out.b, ws["tok"], ops.EPI_BIAS)
         if out is None:
             out = torch.empty(B, cfg.out_channels, 2 * rows, w, device=dev, dtype=hidden_states.dtype)
         if euler is not None:

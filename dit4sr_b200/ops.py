@@ -204,8 +204,13 @@ def patchify(x, out):
     """x [B,C,H,W] fp32/bf16 -> out bf16 [B, (H/2)(W/2), 4C] (im2col of PatchEmbed's k=2,s=2 conv)."""
     if not x.is_contiguous() or not out.is_contiguous():
         raise _lib.Dit4srError("patchify: tensors must be contiguous")
-    _req(out, torch.bfloat16, "out")
     B, Cc, H, W = x.shape
+    if out.dtype == torch.float32:      # fp32-accurate mode
+        _req(x, torch.float32, "x")
+        check(_lib.load().dit4sr_patchify_f32(_ptr(x), _ptr(out), B, Cc, H, W, _stream()), "dit4sr_patchify_f32")
+        _count()
+        return
+    _req(out, torch.bfloat16, "out")
     dt = DT_F32 if x.dtype == torch.float32 else DT_BF16
     check(_lib.load().dit4sr_patchify(_ptr(x), dt, _ptr(out), B, Cc, H, W, _stream()), "dit4sr_patchify")
     _count()
@@ -227,6 +232,11 @@ def unpatchify(tok, out, latents=None, dsigma=0.0):
 
 def timestep_features(t, out):
     _req(t, torch.float32, "timestep")
+    if out.dtype == torch.float32:      # fp32-accurate mode
+        check(_lib.load().dit4sr_timestep_features_f32(_ptr(t), _ptr(out), t.shape[0], _stream()),
+              "dit4sr_timestep_features_f32")
+        _count()
+        return
     _req(out, torch.bfloat16, "out")
     check(_lib.load().dit4sr_timestep_features(_ptr(t), _ptr(out), t.shape[0], _stream()), "dit4sr_timestep_features")
     _count()
@@ -234,6 +244,10 @@ def timestep_features(t, out):
 
 def silu_cast(x, out):
     _req(x, torch.float32, "x")
+    if out.dtype == torch.float32:      # fp32-accurate mode
+        check(_lib.load().dit4sr_silu_f32(_ptr(x), _ptr(out), x.numel(), _stream()), "dit4sr_silu_f32")
+        _count()
+        return
     _req(out, torch.bfloat16, "out")
     check(_lib.load().dit4sr_silu_cast(_ptr(x), _ptr(out), x.numel(), _stream()), "dit4sr_silu_cast")
     _count()

@@ -238,14 +238,18 @@ class SD3Transformer2DModel(nn.Module):
         self._engine = None
         return super().load_state_dict(*args, **kwargs)
 
-    def engine(self, fold_lr_chains: Optional[bool] = None, sequence_parallel="keep") -> Engine:
+    def engine(self, fold_lr_chains: Optional[bool] = None, sequence_parallel="keep",
+               precise: Optional[bool] = None) -> Engine:
         """The CUDA engine (built lazily). `sequence_parallel`: a `dit4sr_b200.parallel.SequenceParallel` to shard ONE
-        image over the ranks of its process group (Ulysses), None to turn that off, "keep" to leave it as it is."""
+        image over the ranks of its process group (Ulysses), None to turn that off, "keep" to leave it as it is.
+        `precise`: force the fp32-accurate mode on/off (default: on iff the parameters are fp32, see Engine)."""
         e = self._engine
         sp = (e.sp if e is not None else None) if isinstance(sequence_parallel, str) else sequence_parallel
-        if e is None or (fold_lr_chains is not None and e.fold_lr_chains != fold_lr_chains) or e.sp is not sp:
+        if (e is None or (fold_lr_chains is not None and e.fold_lr_chains != fold_lr_chains) or e.sp is not sp
+                or (precise is not None and e.precise != precise)):
             fold = fold_lr_chains if fold_lr_chains is not None else (e.fold_lr_chains if e is not None else None)
-            self._engine = Engine(self, fold_lr_chains=fold, sp=sp)
+            prec = precise if precise is not None else (e.precise if e is not None else None)
+            self._engine = Engine(self, fold_lr_chains=fold, sp=sp, precise=prec)
         return self._engine
 
     # ------------------------------------------------------------------ forward

@@ -190,6 +190,10 @@ int dit4sr_add_f32(float* dst, int64_t dst_row_stride, int64_t dst_batch_stride,
 int dit4sr_dwconv3x3_add_f32(float* u_hq, const float* u_lr, int64_t ld, int64_t hq_batch_stride,
                              int64_t lr_batch_stride, const float* weight9, const float* bias, int batches, int grid_h,
                              int grid_w, int lr_grid_h, int lr_row_offset, int channels, void* stream);
+/* fp32 variants of the head kernels (PatchEmbed im2col, timestep sinusoid, SiLU) for the fp32-accurate mode */
+int dit4sr_patchify_f32(const float* x, float* patches, int batches, int channels, int height, int width, void* stream);
+int dit4sr_timestep_features_f32(const float* timesteps, float* out, int batches, void* stream);
+int dit4sr_silu_f32(const float* x, float* y, int64_t n, void* stream);
 /* y = x (fp32 -> bf16 or bf16 -> fp32), n elements; dir 0 = f32->bf16, 1 = bf16->f32 */
 int dit4sr_cast(const void* x, void* y, int64_t n, int dir, void* stream);
 
