@@ -46,7 +46,8 @@ def build_library(force=False, verbose=False):
     for src in sources():
         obj = os.path.join(objdir, os.path.basename(src) + ".o")
         objs.append(obj)
-        cmd = [nvcc] + NVCC_FLAGS + ["-c", src, "-o", obj]
+        # DIT4SR_EXTRA_NVCC_FLAGS: developer switches (e.g. -DDIT4SR_ATTN_TIMING for tools/attn_prof.py)
+        cmd = [nvcc] + NVCC_FLAGS + os.environ.get("DIT4SR_EXTRA_NVCC_FLAGS", "").split() + ["-c", src, "-o", obj]
         procs.append((cmd, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
     log = []
     for cmd, p in procs:

@@ -1,0 +1,151 @@
+// Micro-benchmark of the softmax inner loop of the attention kernel (registers only: no TMEM, no barriers):
+// one warp = 32 rows x 128 score columns per "tile"; 8 warps per CTA (2 per SM sub-partition), 1 CTA per SM, like the
+// two softmax warpgroups of the kernel.  Reports cycles per tile per warp; the MUFU floor is 128 ex2 x 8 cycles = 1024
+// cycles for one warp alone on its sub-partition and 2048 for two.
+//   nvcc -std=c++17 -O3 -gencode arch=compute_100a,code=sm_100a -I dit4sr_b200/csrc -I include tools/micro/softmax_bench.cu -o tools/micro/softmax_bench
+#include <cstdio>
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+#include <cuda.h>
+#include <stdint.h>
+#include "ptx.cuh"
+
+__device__ __forceinline__ float ex2v(float x) {   // volatile: keeps program order among the MUFU instructions
+  float y;
+  asm volatile("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
+// MODE 0: kernel's current shape (max over the row, then fused fma -> ex2 -> sum -> pack per pair)
+// MODE 1: exponentials only (no max, no pack, sum only)                       -> MUFU issue floor
+// MODE 2: two passes: all fma+ex2 in place (volatile order), then sum+pack
+// MODE 3: blocks of 16 pairs: 32 ex2 back to back, then their sum+pack
+// MODE 4: like 0 without the max phase
+template <int MODE>
+__global__ void __launch_bounds__(384, 1) k(float* out, long long* cyc, int iters, int nwarps) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (warp >= nwarps) return;
+  float v[128];
+#pragma unroll
+  for (int i = 0; i < 128; ++i) v[i] = -0.01f * (float)((i * 37 + lane * 11 + warp) % 97);
+  float m_run = 0.f, l_run = 0.f;
+  uint32_t acc = 0;
+  float sl2 = 0.18f;
+  const long long t0 = clock64();
+  for (int it = 0; it < iters; ++it) {
+    sl2 += 1e-6f;   // every score changes every iteration: nothing is loop-invariant
+    float mx = m_run;
+    if (MODE == 0) {
+      float mxa[8];
+#pragma unroll
+      for (int a = 0; a < 8; ++a) mxa[a] = v[a];
+#pragma unroll
+      for (int i = 8; i < 128; i += 8)
+#pragma unroll
+        for (int a = 0; a < 8; ++a) mxa[a] = fmaxf(mxa[a], v[i + a]);
+      mx = fmaxf(fmaxf(fmaxf(mxa[0], mxa[1]), fmaxf(mxa[2], mxa[3])), fmaxf(fmaxf(mxa[4], mxa[5]), fmaxf(mxa[6], mxa[7])));
+      if ((mx - m_run) * sl2 > 8.0f) m_run = mx;
+    }
+    const float neg_m = -m_run * sl2;
+    const uint64_t sl2_2 = ptx::pack2(sl2, sl2), negm_2 = ptx::pack2(neg_m, neg_m);
+    uint64_t rs2[4];
+#pragma unroll
+    for (int a = 0; a < 4; ++a) rs2[a] = ptx::pack2(0.f, 0.f);
+    uint32_t pk[64];
+    if (MODE == 0 || MODE == 4 || MODE == 1) {
+#pragma unroll
+      for (int i = 0; i < 64; ++i) {
+        const uint64_t x2 = ptx::fma2(ptx::pack2(v[2 * i], v[2 * i + 1]), sl2_2, negm_2);
+        float xa, xb;
+        ptx::unpack2(x2, xa, xb);
+        const float p0 = ptx::ex2(xa), p1 = ptx::ex2(xb);
+        rs2[i & 3] = ptx::add2(rs2[i & 3], ptx::pack2(p0, p1));
+        pk[i] = MODE == 1 ? 0u : ptx::pack_bf16(p0, p1);
+      }
+    } else if (MODE == 2) {
+      float p[128];
+#pragma unroll
+      for (int i = 0; i < 64; ++i) {
+        const uint64_t x2 = ptx::fma2(ptx::pack2(v[2 * i], v[2 * i + 1]), sl2_2, negm_2);
+        float xa, xb;
+        ptx::unpack2(x2, xa, xb);
+        p[2 * i] = ex2v(xa);
+        p[2 * i + 1] = ex2v(xb);
+      }
+#pragma unroll
+      for (int i = 0; i < 64; ++i) {
+        rs2[i & 3] = ptx::add2(rs2[i & 3], ptx::pack2(p[2 * i], p[2 * i + 1]));
+        pk[i] = ptx::pack_bf16(p[2 * i], p[2 * i + 1]);
+      }
+    } else if (MODE == 3) {
+#pragma unroll
+      for (int blk = 0; blk < 4; ++blk) {
+        float p[32];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          const int g = blk * 16 + i;
+          const uint64_t x2 = ptx::fma2(ptx::pack2(v[2 * g], v[2 * g + 1]), sl2_2, negm_2);
+          float xa, xb;
+          ptx::unpack2(x2, xa, xb);
+          p[2 * i] = ex2v(xa);
+          p[2 * i + 1] = ex2v(xb);
+        }
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          const int g = blk * 16 + i;
+          rs2[g & 3] = ptx::add2(rs2[g & 3], ptx::pack2(p[2 * i], p[2 * i + 1]));
+          pk[g] = ptx::pack_bf16(p[2 * i], p[2 * i + 1]);
+        }
+      }
+    }
+    float ra, rb, rc, rd;
+    ptx::unpack2(ptx::add2(rs2[0], rs2[1]), ra, rb);
+    ptx::unpack2(ptx::add2(rs2[2], rs2[3]), rc, rd);
+    l_run += (ra + rb) + (rc + rd);
+#pragma unroll
+    for (int i = 0; i < 64; ++i) acc ^= pk[i];
+    // next "tile": perturb the scores so nothing is loop-invariant
+#pragma unroll
+    for (int i = 0; i < 128; i += 16) v[i] += __uint_as_float((acc & 0x7u) | 0x3a000000u);
+  }
+  const long long t1 = clock64();
+  if (lane == 0) cyc[blockIdx.x * 12 + warp] = t1 - t0;
+  out[(blockIdx.x * 384 + threadIdx.x)] = l_run + __uint_as_float(acc) + m_run;
+}
+
+template <int MODE>
+void run(const char* name, int nwarps) {
+  float* o;
+  long long* c;
+  cudaMalloc(&o, 148 * 384 * 4);
+  cudaMalloc(&c, 148 * 12 * 8);
+  const int iters = 400;
+  k<MODE><<<148, 384>>>(o, c, 10, nwarps);
+  cudaEvent_t e0, e1;
+  cudaEventCreate(&e0);
+  cudaEventCreate(&e1);
+  cudaEventRecord(e0);
+  k<MODE><<<148, 384>>>(o, c, iters, nwarps);
+  cudaEventRecord(e1);
+  cudaError_t e = cudaDeviceSynchronize();
+  float ms = 0.f;
+  cudaEventElapsedTime(&ms, e0, e1);
+  if (e != cudaSuccess) { printf("%s: %s\n", name, cudaGetErrorString(e)); return; }
+  long long h[12];
+  cudaMemcpy(h, c, sizeof(h), cudaMemcpyDeviceToHost);
+  printf("%-64s %d warps/SM: %7.1f cycles per tile per warp  (%.3f ms -> %5.1f ex2 lanes/ns/SM)\n", name, nwarps,
+         (double)h[0] / iters, ms, 128.0 * 32 * nwarps * iters / (ms * 1e6));
+  cudaFree(o);
+  cudaFree(c);
+}
+
+int main() {
+  for (int nw : {4, 8}) {
+    run<1>("exponentials + sum only (MUFU issue floor)", nw);
+    run<4>("fused fma/ex2/sum/pack per pair, no max", nw);
+    run<0>("max, then fused fma/ex2/sum/pack per pair (kernel today)", nw);
+    run<2>("two passes: all ex2 in place, then sum+pack, no max", nw);
+    run<3>("blocks of 16 pairs: 32 ex2, then sum+pack, no max", nw);
+  }
+  return 0;
+}
