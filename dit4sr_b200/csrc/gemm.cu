@@ -7,6 +7,7 @@
 // allocator, warps 4..7 = epilogue (each owns the 32 TMEM lanes of its lane quarter; thread = one output row).
 #include "host_util.h"
 #include "ptx.cuh"
+#include <stdlib.h>
 
 namespace gemm {
 
@@ -44,22 +45,38 @@ struct Problem {
   int64_t dbl_row_offset;
 };
 
+// Tail splitting: with T tiles on G CTAs the last T mod G tiles would occupy a whole extra wave with most SMs idle
+// (e.g. 912 = 6 x 148 + 24 tiles for the N = 1536 projections: 7 waves for 6.16 waves of work).  Those last tiles are
+// cut into `split` column slices of BN/split columns (MMA N = 64 or 128, W loaded through a second tensor map with a
+// matching box), so the remainder spreads over split x as many CTAs and costs a fraction of a wave.
 struct Group {
   int num_problems;
-  int num_tiles;
+  int num_tiles;      // work items of the launch = split_begin + (tiles - split_begin) * split
+  int split_begin;    // first tile (in schedule order) that is cut into column slices
+  int split;          // 1 (no splitting), 2 or 4 slices per 256-column tile
   Problem p[MAX_PROBLEMS];
 };
 
 struct Maps {
   CUtensorMap a[MAX_PROBLEMS];
   CUtensorMap w[MAX_PROBLEMS];
+  CUtensorMap ws[MAX_PROBLEMS];   // W with a BN/split-row box (only valid when split > 1)
 };
 
 struct TileCoord {
-  int pi, b, m_tile, n_tile;
+  int pi, b, m_tile;
+  int col0;   // first output column of the work item
+  int bn;     // its width: BN, or BN/split for a slice of a tail tile
 };
 
-__device__ __forceinline__ TileCoord decode_tile(const Group& g, int tile) {
+__device__ __forceinline__ TileCoord decode_tile(const Group& g, int item) {
+  int tile = item, part = 0, bn = BN;
+  if (item >= g.split_begin) {
+    const int idx = item - g.split_begin;
+    tile = g.split_begin + idx / g.split;
+    part = idx % g.split;
+    bn = BN / g.split;
+  }
   int pi = 0;
 #pragma unroll
   for (int i = 1; i < MAX_PROBLEMS; ++i)
@@ -68,7 +85,8 @@ __device__ __forceinline__ TileCoord decode_tile(const Group& g, int tile) {
   const int local = tile - p.tile_begin;
   TileCoord c;
   c.pi = pi;
-  c.n_tile = local % p.n_tiles;
+  c.col0 = (local % p.n_tiles) * BN + part * bn;
+  c.bn = bn;
   const int rest = local / p.n_tiles;
   c.m_tile = rest % p.m_tiles;
   c.b = rest / p.m_tiles;
@@ -160,14 +178,15 @@ gemm_kernel(const __grid_constant__ Maps maps, const __grid_constant__ Group grp
         const TileCoord tc = decode_tile(grp, tile);
         const int k_blocks = grp.p[tc.pi].k_blocks;
         const CUtensorMap* ma = &maps.a[tc.pi];
-        const CUtensorMap* mw = &maps.w[tc.pi];
+        const CUtensorMap* mw = tc.bn == BN ? &maps.w[tc.pi] : &maps.ws[tc.pi];
+        const uint32_t tx_bytes = A_BYTES + tc.bn * BK * 2;
         for (int kb = 0; kb < k_blocks; ++kb) {
           ptx::mbar_wait(&empty_bar[stage], phase ^ 1);
           uint8_t* sa = smem + stage * STAGE_BYTES;
           uint8_t* sb = sa + A_BYTES;
-          ptx::mbar_expect_tx(&full_bar[stage], STAGE_BYTES);
+          ptx::mbar_expect_tx(&full_bar[stage], tx_bytes);
           ptx::tma_load_3d(sa, ma, &full_bar[stage], kb * BK, tc.m_tile * BM, tc.b);
-          ptx::tma_load_2d(sb, mw, &full_bar[stage], kb * BK, tc.n_tile * BN);
+          ptx::tma_load_2d(sb, mw, &full_bar[stage], kb * BK, tc.col0);
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
       }
@@ -175,7 +194,6 @@ gemm_kernel(const __grid_constant__ Maps maps, const __grid_constant__ Group grp
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
     // The whole warp runs the loop (warp-uniform barrier addresses / descriptors); one elected lane issues.
-    constexpr uint32_t idesc = ptx::make_idesc_bf16(BM, BN, 0, 0);
     const uint64_t desc_base = ptx::make_sdesc_sw128(ptx::smem_u32(smem));
     int stage = 0;
     uint32_t phase = 0;
@@ -185,6 +203,7 @@ gemm_kernel(const __grid_constant__ Maps maps, const __grid_constant__ Group grp
       const int k_blocks = grp.p[tc.pi].k_blocks;
       const int as = it & 1;
       const uint32_t aphase = (it >> 1) & 1;
+      const uint32_t idesc = ptx::make_idesc_bf16(BM, tc.bn, 0, 0);   // N = 256, or 128 / 64 for a tail slice
       ptx::mbar_wait(&tempty_bar[as], aphase ^ 1);
       ptx::tc_fence_after();
       const uint32_t d_tmem = tmem_base + as * BN;
@@ -224,8 +243,8 @@ gemm_kernel(const __grid_constant__ Maps maps, const __grid_constant__ Group grp
 
       const int row_base = tc.m_tile * BM + q * 32;       // first row of this warp
       const uint32_t taddr = tmem_base + as * BN + ((uint32_t)(q * 32) << 16);
-      const int n_base = tc.n_tile * BN;
-      const int n_valid = min(BN, P.N - n_base);          // multiple of 32
+      const int n_base = tc.col0;
+      const int n_valid = min(tc.bn, P.N - n_base);       // multiple of 32
       const int64_t c_tile_off = (int64_t)tc.b * P.c_batch_stride + n_base;
 
       if (EPI == DIT4SR_EPI_QKV_NORM || !P.c_f32) {
@@ -357,8 +376,8 @@ gemm_kernel(const __grid_constant__ Maps maps, const __grid_constant__ Group grp
             const Problem& NP = grp.p[nc.pi];
             const int nr = nc.m_tile * BM + q * 32 + lane;
             if (nr < NP.rows) {
-              const float* np = NP.resid + (int64_t)nc.b * NP.r_batch_stride + (int64_t)nr * NP.ldr + nc.n_tile * BN;
-              const int ncols = min(BN, NP.N - nc.n_tile * BN);
+              const float* np = NP.resid + (int64_t)nc.b * NP.r_batch_stride + (int64_t)nr * NP.ldr + nc.col0;
+              const int ncols = min(nc.bn, NP.N - nc.col0);
 #pragma unroll
               for (int i = 0; i < BN / 32; ++i)
                 if (i * 32 < ncols) ptx::prefetch_l2(np + i * 32);
@@ -553,7 +572,36 @@ extern "C" int dit4sr_gemm_bf16_grouped(const dit4sr_gemm_params* probs, int cou
     maps.a[i] = maps.a[0];
     maps.w[i] = maps.w[0];
   }
+  // tail splitting (see Group): only when every problem's N is a whole number of 256-column tiles
   g.num_tiles = tiles;
+  g.split_begin = tiles;
+  g.split = 1;
+  {
+    static int enabled = -1;
+    if (enabled < 0) { const char* e = getenv("DIT4SR_GEMM_TAIL_SPLIT"); enabled = (e == nullptr || e[0] != '0') ? 1 : 0; }
+    const int sms = host::sm_count();
+    const int rem = tiles % sms;
+    bool whole = true;
+    for (int i = 0; i < count; ++i) whole = whole && (probs[i].N % BN == 0);
+    if (enabled && whole && tiles > sms && rem > 0) {
+      const int split = 4 * rem <= sms ? 4 : (2 * rem <= sms ? 2 : 1);
+      if (split > 1) {
+        g.split = split;
+        g.split_begin = tiles - rem;
+        g.num_tiles = g.split_begin + rem * split;
+        for (int i = 0; i < count; ++i) {
+          const dit4sr_gemm_params* p = &probs[i];
+          uint64_t dims[2] = {(uint64_t)p->K, (uint64_t)p->N};
+          uint64_t strides[1] = {(uint64_t)p->ldw * 2};
+          uint32_t box[2] = {BK, (uint32_t)(BN / split)};
+          if ((rc = host::make_tmap_bf16(&maps.ws[i], p->W, 2, dims, strides, box)) != 0) return rc;
+        }
+      }
+    }
+    if (g.split == 1)
+      for (int i = 0; i < count; ++i) maps.ws[i] = maps.w[i];
+    for (int i = count; i < MAX_PROBLEMS; ++i) maps.ws[i] = maps.ws[0];
+  }
   switch (epilogue) {
     case DIT4SR_EPI_BIAS: return launch<DIT4SR_EPI_BIAS>(maps, g, stream);
     case DIT4SR_EPI_BIAS_GELU: return launch<DIT4SR_EPI_BIAS_GELU>(maps, g, stream);

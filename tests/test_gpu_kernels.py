@@ -150,6 +150,27 @@ def test_gemm_grouped_launch(ops):
     assert rel(x1, e1) < F32_TOL and rel(x2, e2) < F32_TOL
 
 
+@pytest.mark.parametrize("rows,K,N", [(10240, 256, 512), (6400, 128, 768), (25344 - 100, 64, 256)])
+def test_gemm_tail_split(ops, rows, K, N):
+    """Tile counts just over a multiple of the SM count: the last tiles are cut into 64- or 128-column slices (tail
+    splitting, gemm.cu); every epilogue must give the same result as without it."""
+    torch.manual_seed(0)
+    A, W, bias, ref = _mk(1, rows, K, N)
+    o = torch.zeros(1, rows, N, device="cuda", dtype=torch.bfloat16)
+    ops.gemm(A, W, bias, o, ops.EPI_BIAS_GELU)
+    assert rel(o.float(), torch.nn.functional.gelu(ref, approximate="tanh")) < BF16_TOL
+    gate = torch.randn(1, N, device="cuda")
+    x = torch.randn(1, rows, N, device="cuda")
+    x0 = x.clone()
+    ops.gemm(A, W, bias, x, ops.EPI_GATE_RESID, gate=gate)
+    assert rel(x, x0 + gate[:, None] * ref) < F32_TOL
+    assert rel(x[:, -256:], (x0 + gate[:, None] * ref)[:, -256:]) < F32_TOL      # the split tail rows specifically
+    wq = 1 + 0.1 * torch.randn(64, device="cuda")
+    ops.gemm(A, W, bias, o, ops.EPI_QKV_NORM, norm_w0=wq, sec_cols=N)
+    assert rel(o.float(), _rms(ref, wq)) < BF16_TOL
+    assert rel(o[:, -256:].float(), _rms(ref, wq)[:, -256:]) < BF16_TOL
+
+
 def _rms(t, w):
     t = t.reshape(*t.shape[:-1], -1, 64)
     t = t * torch.rsqrt(t.pow(2).mean(-1, keepdim=True) + 1e-6) * w
