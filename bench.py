@@ -33,8 +33,28 @@ WORKLOADS = {
     "c3": (128, 32, 333, "dp_strong", "C3: 1024px (4096 HQ + 4096 LR + 333 text tokens), batch 32 in total, data-parallel"),
     "c4": (256, 1, 333, "sp", "C4: 2048px (16384 HQ + 16384 LR + 333 text tokens), batch 1, Ulysses sequence parallelism "
                               "(head<->sequence all-to-all over NCCL)"),
+    "c5": (128, 8, 333, "dp_strong", "C5: OCR-branch model (transformer_sd3_ocrbranch_ocr2hq2ocr: HQ | LR | OCR | text joint "
+                                     "attention, 3 x 4096 + 333 tokens), 1024px, batch 8 in total, data-parallel"),
     "px1024": (128, 1, 333, "dp_weak", "1024px batch 1 per GPU"),
 }
+
+
+def flops_per_image_step_ocr(N, T, L=24, dual=13, D=1536):
+    """Same for the 3-stream OCR-branch model (LR and OCR projection chains folded, as the engine runs them):
+    SURVEY.md 8d quotes 54.90 TFLOP at 1024px with folded chains."""
+    F = 4 * D
+    gemm = attn = 0.0
+    for i in range(L):
+        last = i == L - 1
+        # q|k|v: HQ 3N, LR q,v 2N, OCR q,k,v 3N, text 3T; out: 3N (+T)
+        gemm += 2 * D * D * (3 * N + 2 * N + 3 * N + 3 * T + 3 * N + (0 if last else T))
+        attn += 4 * (3 * N + T) ** 2 * D
+        if i < dual:   # attn2 is the 2-stream processor on the 3N image tokens split at 1.5N (SURVEY Q6)
+            h = 1.5 * N
+            gemm += 2 * D * D * (3 * h + 2 * h + 2 * h)
+            attn += 4 * (3 * N) ** 2 * D
+        gemm += 4 * (3 * N) * D * F + (0 if last else 4 * T * D * F)
+    return gemm, attn
 
 
 def flops_per_image_step(N, T, L=24, dual=13, D=1536, folded=True):
@@ -108,20 +128,21 @@ class ClockSampler:
         return out
 
 
-def build_model_gpu(device, seed=0):
+def build_model_gpu(device, seed=0, ocr=False):
     """SD3.5-medium-shaped model with EVERY parameter random (SURVEY 8d scales), created directly on the GPU."""
     import torch
     import dit4sr_b200
     from oracle.dit4sr_oracle import sd35_medium_config
     cfg = sd35_medium_config()
+    cls = dit4sr_b200.SD3Transformer2DModel_OCRBranch_OCR2HQ2OCR if ocr else dit4sr_b200.SD3Transformer2DModel
     with torch.device(device):
-        m = dit4sr_b200.SD3Transformer2DModel(**vars(cfg))
+        m = cls(**vars(cfg))
     g = torch.Generator(device=device).manual_seed(seed)
     with torch.no_grad():
         for name, p in m.named_parameters():
             if ".norm_" in name and p.dim() == 1 and p.numel() == 64:
                 p.copy_(1.0 + 0.1 * torch.randn(p.shape, device=device, generator=g))
-            elif "control_conv.weight" in name:
+            elif name.endswith("conv.weight") and p.dim() == 4:      # control_conv (+ the OCR model's two convs)
                 p.copy_(0.1 * torch.randn(p.shape, device=device, generator=g))
             else:
                 p.copy_(0.02 * torch.randn(p.shape, device=device, generator=g))
@@ -150,7 +171,7 @@ def run_ours(args):
     N = (side // 2) ** 2
     bf = torch.bfloat16
 
-    model, cfg = build_model_gpu(dev, seed=0)
+    model, cfg = build_model_gpu(dev, seed=0, ocr=args.workload == "c5")
     if mode == "sp" and world > 1:
         from dit4sr_b200.parallel import SequenceParallel
         eng = model.engine(sequence_parallel=SequenceParallel())
@@ -259,12 +280,16 @@ def run_ours(args):
 
     if rank == 0:
         peaks = measured_peaks()
-        gemm_f, attn_f = flops_per_image_step(N, T, folded=eng.fold_lr_chains)
+        if args.workload == "c5":
+            gemm_f, attn_f = flops_per_image_step_ocr(N, T)
+        else:
+            gemm_f, attn_f = flops_per_image_step(N, T, folded=eng.fold_lr_chains)
         step_flops = (gemm_f + attn_f) * images_total / world      # per-GPU share of one step
         img_steps = images_total * args.steps
         value = img_steps / (ms / 1e3)
         # FF1 launch = image FF1 [B*2N,1536]x[1536,6144] grouped with the text FF1 [B*T,...] (absent in the last block)
-        ff1_flops = 2.0 * (B * 2 * N + B * T * 23.0 / 24.0) * 1536 * 6144
+        streams = 3 if args.workload == "c5" else 2
+        ff1_flops = 2.0 * (B * streams * N + B * T * 23.0 / 24.0) * 1536 * 6144
         ff1_avg_ms = (sum(ff1_ms["ff1"]) / len(ff1_ms["ff1"])) if ff1_ms and ff1_ms.get("ff1") else None
         # DRAM traffic of the same kernel from the committed `ncu --set full` capture (dram__bytes_read + write per launch)
         traffic = None

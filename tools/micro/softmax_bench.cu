@@ -22,7 +22,7 @@ __device__ __forceinline__ float ex2v(float x) {   // volatile: keeps program or
 // MODE 3: blocks of 16 pairs: 32 ex2 back to back, then their sum+pack
 // MODE 4: like 0 without the max phase
 template <int MODE>
-__global__ void __launch_bounds__(384, 1) k(float* out, long long* cyc, int iters, int nwarps) {
+__global__ void __launch_bounds__(384, 1) k(float* out, long long* cyc, int iters, int nwarps, int zlen = 0, int skew = 0, int role = 0) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (warp >= nwarps) return;
   float v[128];
@@ -31,8 +31,20 @@ __global__ void __launch_bounds__(384, 1) k(float* out, long long* cyc, int iter
   float m_run = 0.f, l_run = 0.f;
   uint32_t acc = 0;
   float sl2 = 0.18f;
+  if (warp >= 4 && skew > 0) { const long long ts = clock64(); while (clock64() - ts < skew) {} }
   const long long t0 = clock64();
   for (int it = 0; it < iters; ++it) {
+    if (role == 1 && warp >= 4) {
+      float z = v[5];
+      for (int q = 0; q < 4 * zlen; ++q) z = fmaxf(z * 1.0001f, v[(q & 1)]);
+      v[7] = z * 1e-30f + v[7];
+      continue;
+    }
+    if (zlen > 0 && !(role == 2 && warp >= 4)) {   // non-MUFU phase of a tile-step: a dependent chain (stands for TMEM load + max + store + barrier hops)
+      float z = v[5];
+      for (int q = 0; q < zlen; ++q) z = fmaxf(z * 1.0001f, v[(q & 1)]);
+      v[7] = z * 1e-30f + v[7];
+    }
     sl2 += 1e-6f;   // every score changes every iteration: nothing is loop-invariant
     float mx = m_run;
     if (MODE == 0) {
@@ -139,7 +151,29 @@ void run(const char* name, int nwarps) {
   cudaFree(c);
 }
 
+void run_skew(int zlen, int skew, int role = 0) {
+  float* o;
+  long long* c;
+  cudaMalloc(&o, 148 * 384 * 4);
+  cudaMalloc(&c, 148 * 12 * 8);
+  const int iters = 400;
+  k<4><<<148, 384>>>(o, c, 10, 8, zlen, skew, role);
+  k<4><<<148, 384>>>(o, c, iters, 8, zlen, skew, role);
+  cudaDeviceSynchronize();
+  long long h[12];
+  cudaMemcpy(h, c, sizeof(h), cudaMemcpyDeviceToHost);
+  printf("role %d  non-MUFU chain %4d iterations, second warp skewed %5d cycles: warp0 %7.1f  warp4 %7.1f cycles per tile\n", role, zlen, skew,
+         (double)h[0] / iters, (double)h[4] / iters);
+  cudaFree(o);
+  cudaFree(c);
+}
+
 int main() {
+  for (int z : {0, 100, 200}) for (int sk : {0, 500, 1000, 1500}) run_skew(z, sk);
+  run_skew(100, 0, 1);
+  run_skew(100, 0, 2);
+  run_skew(0, 0, 1);
+  return 0;
   for (int nw : {4, 8}) {
     run<1>("exponentials + sum only (MUFU issue floor)", nw);
     run<4>("fused fma/ex2/sum/pack per pair, no max", nw);
