@@ -2,6 +2,7 @@
 // registers (two-pass mean/variance in fp32), 16-byte coalesced loads, one or two bf16 outputs from a single read.
 #include "host_util.h"
 #include "ptx.cuh"
+#include <stdlib.h>
 
 namespace lnmod {
 
@@ -52,36 +53,165 @@ ln_modulate_f32_kernel(const dit4sr_ln_modulate_params p) {
   }
 }
 
-template <int NV, bool DUAL>  // NV float4 per lane => dim = NV * 128
-__global__ void __launch_bounds__(WARPS * 32)
+
+
+// TMA-staged variant (bf16 outputs): the register kernel below keeps DRAM only ~45 % busy (ncu: long-scoreboard bound,
+// 23 resident warps x one row of loads each).  Here every warp is persistent and keeps LN_STAGES rows in flight as 1-D
+// bulk copies (cp.async.bulk -> its own shared-memory slots, one mbarrier per slot), which costs no registers; a row is
+// read back from shared memory with a lane owning 8 consecutive elements per 256-element chunk, so each output store
+// is 16 bytes per lane (a full 512-byte segment per warp instruction), and the slot is refilled with the row
+// LN_STAGES ahead as soon as the row sits in registers.
+constexpr int LN_STAGES = 3;
+constexpr int LN_WARPS = 8;
+
+template <int NC, bool DUAL>  // NC chunks of 256 elements => dim = NC * 256
+__global__ void __launch_bounds__(LN_WARPS * 32, 1)
+ln_modulate_tma_kernel(const dit4sr_ln_modulate_params p) {
+  extern __shared__ uint8_t ln_smem_raw[];
+  constexpr int ROW_BYTES = NC * 256 * 4;
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(ln_smem_raw) + 127) & ~uintptr_t(127));
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  uint8_t* slots = smem + (size_t)warp * LN_STAGES * ROW_BYTES;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)LN_WARPS * LN_STAGES * ROW_BYTES) + warp * LN_STAGES;
+  const int64_t total = (int64_t)p.batches * p.rows;
+  const int64_t nwarps = (int64_t)gridDim.x * LN_WARPS;
+  const int64_t first = (int64_t)blockIdx.x * LN_WARPS + warp;
+  auto row_ptr = [&](int64_t rid) {
+    const int b = (int)(rid / p.rows);
+    const int r = (int)(rid % p.rows);
+    return p.x + (int64_t)b * p.x_batch_stride + (int64_t)r * p.ldx;
+  };
+  if (lane == 0) {
+    for (int s = 0; s < LN_STAGES; ++s) ptx::mbar_init(&bars[s], 1);
+    ptx::fence_barrier_init();
+    for (int s = 0; s < LN_STAGES; ++s) {
+      const int64_t rid = first + s * nwarps;
+      if (rid < total) {
+        ptx::mbar_expect_tx(&bars[s], ROW_BYTES);
+        ptx::bulk_load(slots + s * ROW_BYTES, row_ptr(rid), ROW_BYTES, &bars[s]);
+      }
+    }
+  }
+  __syncwarp();
+  const float inv_dim = 1.0f / (float)(NC * 256);
+  int k = 0;
+  for (int64_t rid = first; rid < total; rid += nwarps, ++k) {
+    const int s = k % LN_STAGES;
+    ptx::mbar_wait(&bars[s], (k / LN_STAGES) & 1);
+    const float4* src = reinterpret_cast<const float4*>(slots + s * ROW_BYTES) + lane * 2;
+    float4 v[2 * NC];
+#pragma unroll
+    for (int i = 0; i < NC; ++i) {
+      v[2 * i] = src[i * 64];
+      v[2 * i + 1] = src[i * 64 + 1];
+    }
+    __syncwarp();
+    if (lane == 0) {   // refill the slot with the row LN_STAGES ahead
+      const int64_t nrid = rid + (int64_t)LN_STAGES * nwarps;
+      if (nrid < total) {
+        ptx::mbar_expect_tx(&bars[s], ROW_BYTES);
+        ptx::bulk_load(slots + s * ROW_BYTES, row_ptr(nrid), ROW_BYTES, &bars[s]);
+      }
+    }
+    const int b = (int)(rid / p.rows);
+    const int r = (int)(rid % p.rows);
+    // statistics in one pass with packed fp32x2 adds / fmas (FADD2 / FFMA2): var = E[x^2] - mean^2 in fp32 (the
+    // residual stream has |mean| << std, so the cancellation costs ~1e-7 relative)
+    uint64_t s2[2] = {ptx::pack2(0.f, 0.f), ptx::pack2(0.f, 0.f)}, q2[2] = {s2[0], s2[0]};
+#pragma unroll
+    for (int i = 0; i < 2 * NC; ++i) {
+      const uint64_t lo = ptx::pack2(v[i].x, v[i].y), hi = ptx::pack2(v[i].z, v[i].w);
+      s2[0] = ptx::add2(s2[0], lo);
+      s2[1] = ptx::add2(s2[1], hi);
+      q2[0] = ptx::fma2(lo, lo, q2[0]);
+      q2[1] = ptx::fma2(hi, hi, q2[1]);
+    }
+    float sa, sb, qa, qb;
+    ptx::unpack2(ptx::add2(s2[0], s2[1]), sa, sb);
+    ptx::unpack2(ptx::add2(q2[0], q2[1]), qa, qb);
+    float sum = sa + sb, sq = qa + qb;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      sum += __shfl_xor_sync(0xffffffffu, sum, o);
+      sq += __shfl_xor_sync(0xffffffffu, sq, o);
+    }
+    const float mean = sum * inv_dim;
+    const float rstd = rsqrtf(fmaxf(sq * inv_dim - mean * mean, 0.f) + p.eps);
+    const uint64_t rstd2 = ptx::pack2(rstd, rstd), nmean2 = ptx::pack2(-mean, -mean);
+#pragma unroll
+    for (int which = 0; which < (DUAL ? 2 : 1); ++which) {
+      const float4* sh = reinterpret_cast<const float4*>((which ? p.shift2 : p.shift) + (int64_t)b * p.mod_batch_stride) + lane * 2;
+      const float4* sc = reinterpret_cast<const float4*>((which ? p.scale2 : p.scale) + (int64_t)b * p.mod_batch_stride) + lane * 2;
+      uint4* out = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(which ? p.out2 : p.out) +
+                                            (int64_t)b * p.o_batch_stride + (int64_t)r * p.ldo) + lane;
+      // out = (x - mean) rstd (1 + s) + t = x a + (t - mean a),  a = rstd s + rstd: three packed fmas per two elements
+      auto mod2 = [&](float x0, float x1, float sc0, float sc1, float t0, float t1) {
+        const uint64_t a2 = ptx::fma2(ptx::pack2(sc0, sc1), rstd2, rstd2);
+        const uint64_t c2 = ptx::fma2(nmean2, a2, ptx::pack2(t0, t1));
+        float o0, o1;
+        ptx::unpack2(ptx::fma2(ptx::pack2(x0, x1), a2, c2), o0, o1);
+        return ptx::pack_bf16(o0, o1);
+      };
+#pragma unroll
+      for (int i = 0; i < NC; ++i) {
+        const float4 s0 = __ldg(sc + i * 64), s1 = __ldg(sc + i * 64 + 1);
+        const float4 t0 = __ldg(sh + i * 64), t1 = __ldg(sh + i * 64 + 1);
+        const float4 a = v[2 * i], c = v[2 * i + 1];
+        uint4 o;
+        o.x = mod2(a.x, a.y, s0.x, s0.y, t0.x, t0.y);
+        o.y = mod2(a.z, a.w, s0.z, s0.w, t0.z, t0.w);
+        o.z = mod2(c.x, c.y, s1.x, s1.y, t1.x, t1.y);
+        o.w = mod2(c.z, c.w, s1.z, s1.w, t1.z, t1.w);
+        out[i * 32] = o;
+      }
+    }
+  }
+}
+
+// W warps per CTA; ONEPASS: sum and sum of squares reduced together (one shuffle tree instead of two in sequence)
+template <int NV, bool DUAL, int W, bool ONEPASS>  // NV float4 per lane => dim = NV * 128
+__global__ void __launch_bounds__(W * 32)
 ln_modulate_kernel(const dit4sr_ln_modulate_params p) {
   const int lane = threadIdx.x & 31;
-  const int64_t row_id = (int64_t)blockIdx.x * WARPS + (threadIdx.x >> 5);
+  const int64_t row_id = (int64_t)blockIdx.x * W + (threadIdx.x >> 5);
   const int64_t total = (int64_t)p.batches * p.rows;
   if (row_id >= total) return;
   const int b = (int)(row_id / p.rows);
   const int r = (int)(row_id % p.rows);
   const float4* x = reinterpret_cast<const float4*>(p.x + (int64_t)b * p.x_batch_stride + (int64_t)r * p.ldx);
   float4 v[NV];
-  float sum = 0.f;
+  float sum = 0.f, sq = 0.f;
 #pragma unroll
   for (int i = 0; i < NV; ++i) {
     v[i] = __ldg(x + i * 32 + lane);
     sum += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+    if (ONEPASS) sq += (v[i].x * v[i].x + v[i].y * v[i].y) + (v[i].z * v[i].z + v[i].w * v[i].w);
   }
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
   const float inv_dim = 1.0f / (float)(NV * 128);
-  const float mean = sum * inv_dim;
-  float sq = 0.f;
+  float mean, rstd;
+  if (ONEPASS) {
 #pragma unroll
-  for (int i = 0; i < NV; ++i) {
-    v[i].x -= mean; v[i].y -= mean; v[i].z -= mean; v[i].w -= mean;
-    sq += (v[i].x * v[i].x + v[i].y * v[i].y) + (v[i].z * v[i].z + v[i].w * v[i].w);
+    for (int o = 16; o > 0; o >>= 1) {
+      sum += __shfl_xor_sync(0xffffffffu, sum, o);
+      sq += __shfl_xor_sync(0xffffffffu, sq, o);
+    }
+    mean = sum * inv_dim;
+    rstd = rsqrtf(fmaxf(sq * inv_dim - mean * mean, 0.f) + p.eps);
+#pragma unroll
+    for (int i = 0; i < NV; ++i) { v[i].x -= mean; v[i].y -= mean; v[i].z -= mean; v[i].w -= mean; }
+  } else {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+    mean = sum * inv_dim;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      v[i].x -= mean; v[i].y -= mean; v[i].z -= mean; v[i].w -= mean;
+      sq += (v[i].x * v[i].x + v[i].y * v[i].y) + (v[i].z * v[i].z + v[i].w * v[i].w);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, o);
+    rstd = rsqrtf(sq * inv_dim + p.eps);
   }
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, o);
-  const float rstd = rsqrtf(sq * inv_dim + p.eps);
 
   const float4* sh = reinterpret_cast<const float4*>(p.shift + (int64_t)b * p.mod_batch_stride);
   const float4* sc = reinterpret_cast<const float4*>(p.scale + (int64_t)b * p.mod_batch_stride);
@@ -113,13 +243,51 @@ ln_modulate_kernel(const dit4sr_ln_modulate_params p) {
   }
 }
 
+template <int NV, int W, bool ONEPASS>
+static void launch_bf16(const dit4sr_ln_modulate_params& p, cudaStream_t stream) {
+  const int64_t total = (int64_t)p.batches * p.rows;
+  const unsigned grid = (unsigned)((total + W - 1) / W);
+  if (p.out2 != nullptr) ln_modulate_kernel<NV, true, W, ONEPASS><<<grid, W * 32, 0, stream>>>(p);
+  else ln_modulate_kernel<NV, false, W, ONEPASS><<<grid, W * 32, 0, stream>>>(p);
+}
+
 template <int NV>
 static int launch(const dit4sr_ln_modulate_params& p, cudaStream_t stream) {
   const int64_t total = (int64_t)p.batches * p.rows;
-  const unsigned grid = (unsigned)((total + WARPS - 1) / WARPS);
-  if (p.out_f32) ln_modulate_f32_kernel<NV><<<grid, WARPS * 32, 0, stream>>>(p);
-  else if (p.out2 != nullptr) ln_modulate_kernel<NV, true><<<grid, WARPS * 32, 0, stream>>>(p);
-  else ln_modulate_kernel<NV, false><<<grid, WARPS * 32, 0, stream>>>(p);
+  static int variant = -1;   // developer switch DIT4SR_LN_VARIANT: warps per CTA (4|8) + 10 for one-pass statistics
+  if (variant < 0) {
+    const char* e = getenv("DIT4SR_LN_VARIANT");
+    variant = e ? atoi(e) : 8;   // 8 = TMA-staged kernel (default); 1 = register kernel, 8 warps
+  }
+  if constexpr (NV % 2 == 0) {
+    constexpr int SMEM = LN_WARPS * LN_STAGES * NV * 128 * 4 + LN_WARPS * LN_STAGES * 8 + 128;
+    if (!p.out_f32 && variant == 8 && SMEM <= 220 * 1024 && (reinterpret_cast<uintptr_t>(p.out) & 15) == 0 &&
+        p.ldo % 8 == 0 && p.o_batch_stride % 8 == 0 &&
+        (p.out2 == nullptr || (reinterpret_cast<uintptr_t>(p.out2) & 15) == 0)) {
+      static bool configured = false;
+      if (!configured) {
+        DIT4SR_CUDA(cudaFuncSetAttribute(ln_modulate_tma_kernel<NV / 2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
+        DIT4SR_CUDA(cudaFuncSetAttribute(ln_modulate_tma_kernel<NV / 2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
+        configured = true;
+      }
+      unsigned grid = (unsigned)((total + LN_WARPS - 1) / LN_WARPS);
+      const unsigned sms = (unsigned)host::sm_count();
+      if (grid > sms) grid = sms;
+      if (p.out2 != nullptr) ln_modulate_tma_kernel<NV / 2, true><<<grid, LN_WARPS * 32, SMEM, stream>>>(p);
+      else ln_modulate_tma_kernel<NV / 2, false><<<grid, LN_WARPS * 32, SMEM, stream>>>(p);
+      DIT4SR_CUDA(cudaGetLastError());
+      return 0;
+    }
+  }
+  if (p.out_f32) {
+    const unsigned grid = (unsigned)((total + WARPS - 1) / WARPS);
+    ln_modulate_f32_kernel<NV><<<grid, WARPS * 32, 0, stream>>>(p);
+  } else if (variant == 4) launch_bf16<NV, 4, false>(p, stream);
+  else if (variant == 14) launch_bf16<NV, 4, true>(p, stream);
+  else if (variant == 18) launch_bf16<NV, 8, true>(p, stream);
+  else if (variant == 2) launch_bf16<NV, 2, false>(p, stream);
+  else if (variant == 12) launch_bf16<NV, 2, true>(p, stream);
+  else launch_bf16<NV, 8, false>(p, stream);
   DIT4SR_CUDA(cudaGetLastError());
   return 0;
 }

@@ -11,15 +11,31 @@ sys.path.insert(0, ROOT)
 from dit4sr_b200 import ops  # noqa: E402
 
 
+GRAPH = False
+
+
 def timeit(fn, reps, warm=3):
+    """Average device time of fn() over `reps` back-to-back launches; with --graph the launches are replayed from a
+    CUDA graph so that host-side launch cost (python + ctypes, ~10-20 us per call) cannot bound short kernels."""
     for _ in range(warm):
         fn()
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for _ in range(reps):
-        fn()
-    e1.record()
+    if GRAPH:
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            for _ in range(reps):
+                fn()
+        g.replay()
+        torch.cuda.synchronize()
+        e0.record()
+        g.replay()
+        e1.record()
+    else:
+        e0.record()
+        for _ in range(reps):
+            fn()
+        e1.record()
     torch.cuda.synchronize()
     return e0.elapsed_time(e1) / reps
 
@@ -29,7 +45,10 @@ def main():
     ap.add_argument("what")
     ap.add_argument("--reps", type=int, default=20)
     ap.add_argument("--shape", default="c2")
+    ap.add_argument("--graph", action="store_true")
     a = ap.parse_args()
+    global GRAPH
+    GRAPH = a.graph
     B, N, T = (8, 1024, 333) if a.shape == "c2" else (2, 4096, 333)
     D, H, F = 1536, 24, 6144
     S = 2 * N + T
@@ -63,6 +82,8 @@ def main():
         u = torch.randn(B, 2 * N, F, device=dev).bfloat16()
         w9 = torch.randn(9, F, device=dev) * 0.1
         bias = torch.randn(F, device=dev) * 0.1
+        ms = timeit(lambda: u[:, :N].add_(u[:, N:]), a.reps)
+        print(f"torch u_hq += u_lr (same traffic): {ms:.4f} ms  {3.0 * B * N * F * 2 / ms / 1e6:.0f} GB/s")
         ms = timeit(lambda: ops.dwconv3x3_add(u[:, :N], u[:, N:], w9, bias, g), a.reps)
         print(f"dwconv B={B} grid={g}: {ms:.4f} ms  {3.0 * B * N * F * 2 / ms / 1e6:.0f} GB/s (algorithmic)")
     elif a.what == "ln":
@@ -70,6 +91,8 @@ def main():
         mod = torch.randn(B, 4 * D, device=dev)
         o1 = torch.empty(B, 2 * N, D, device=dev, dtype=torch.bfloat16)
         o2 = torch.empty_like(o1)
+        ms = timeit(lambda: o1.copy_(x), a.reps)
+        print(f"torch fp32->bf16 copy of the same tensors (same traffic as ln single): {ms:.4f} ms  {B * 2 * N * D * 6 / ms / 1e6:.0f} GB/s")
         ms = timeit(lambda: ops.ln_modulate(x, mod[:, :D], mod[:, D:2 * D], o1), a.reps)
         print(f"ln single: {ms:.4f} ms  {B * 2 * N * D * 6 / ms / 1e6:.0f} GB/s")
         ms = timeit(lambda: ops.ln_modulate(x, mod[:, :D], mod[:, D:2 * D], o1, mod[:, 2 * D:3 * D], mod[:, 3 * D:], o2), a.reps)
