@@ -293,13 +293,16 @@ def run_ours(args):
         ff1_avg_ms = (sum(ff1_ms["ff1"]) / len(ff1_ms["ff1"])) if ff1_ms and ff1_ms.get("ff1") else None
         # DRAM traffic of the same kernel from the committed `ncu --set full` capture (dram__bytes_read + write per launch)
         traffic = None
+        traffic_source = None
         try:
-            prof = json.load(open(os.path.join(ROOT, "profiles", "r01_ncu_full_kernels.json")))
+            prof = json.load(open(os.path.join(ROOT, "profiles", "r01d_ncu_full_kernels.json")))
             vals = [float(k["dram__bytes_read.sum [Mbyte]"]) + float(k["dram__bytes_write.sum [Mbyte]"])
                     for k in prof if "gemm_kernel<1>" in k["Kernel Name"]]
             if vals:
-                traffic = dict(bytes_per_launch=round(sum(vals) / len(vals) * 1e6), source="profiles/r01_ncu_full_kernels.json "
-                               "(FF1 image problem alone, M=16384: algorithmic 50.3 MB A + 18.9 MB W read + 201.3 MB written)")
+                traffic = round(sum(vals) / len(vals) * 1e6)
+                traffic_source = ("profiles/r01d_ncu_full_kernels.json: dram__bytes_read.sum + dram__bytes_write.sum per launch "
+                                  "of the FF1 image problem alone (M=16384; algorithmic 50.3 MB A + 18.9 MB W read + 201.3 MB "
+                                  "written, part of which is still in L2 when the launch ends)")
         except (OSError, KeyError, ValueError):
             pass
         roof = None
@@ -311,7 +314,7 @@ def run_ours(args):
                         peak_source=peaks["source"] + ", sustained figure (kernel timed inside a long step)",
                         frac_of_burst=round(ach / peaks["tf_burst"], 4), frac_of_spec_2250=round(ach / 2250.0, 4),
                         launch_ms=round(ff1_avg_ms, 4), flops_per_launch=ff1_flops, launches_timed=len(ff1_ms["ff1"]),
-                        traffic=traffic)
+                        traffic=traffic, traffic_source=traffic_source)
         line = dict(
             metric="denoise_steps_per_sec", value=round(value, 3), unit="image-steps/s (one image advanced one denoise step)",
             n_gpus=world, steps=args.steps, warmup=args.warmup, ms_per_step=round(ms / args.steps, 3),
