@@ -600,338 +600,6 @@ attn_fwd2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
 
 }  // namespace v2
 
-// =====================================================================================================================
-// Persistent form of v2: one CTA per SM walks the (query-tile pair, head, batch) work items, and the TMA / MMA side runs
-// ahead across item boundaries: Q is double-buffered, the K/V ring and the three rotating score buffers simply keep
-// rotating, so the first Q K^T of the next item are already in TMEM while the softmax warpgroups normalise and store the
-// current item's output.  With one item per CTA that prologue (first Q/K loads from L2/HBM, first Q K^T) and the
-// epilogue cost ~4-5k of ~60k cycles per item at S = 2381 with nothing else resident on the SM.
-// Extra barriers: q_full/q_empty per Q buffer; o_free[t]: the warpgroup of tile t has read its O accumulator out, the
-// first P V of the next item may overwrite it.  All phase parities come from running counters (items, KV tiles, slots).
-namespace v2p {
-
-using v2::KV_STAGES;
-using v2::NBUF;
-using v2::COL_O;
-using v2::RESCALE_THRESHOLD;
-constexpr int NUM_THREADS = 384;
-constexpr int TMEM_COLS = 512;
-constexpr int SMEM_BYTES = (4 + 2 * KV_STAGES) * TILE_BYTES + 1024 + 256;
-
-struct PArgs {
-  Args a;
-  int q_pairs, heads, n_items;
-};
-
-template <int POLY8>
-__global__ void __launch_bounds__(NUM_THREADS, 1)
-attn_fwd2p_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
-                  const __grid_constant__ CUtensorMap tmV, const PArgs pa) {
-  const Args& args = pa.a;
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint8_t* sQ = smem;                                   // 2 buffers x 2 tiles
-  uint8_t* sK = smem + 4 * TILE_BYTES;                  // KV_STAGES tiles
-  uint8_t* sV = smem + (4 + KV_STAGES) * TILE_BYTES;    // KV_STAGES tiles
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (4 + 2 * KV_STAGES) * TILE_BYTES);
-  uint64_t* q_full = bars;                  // [2]
-  uint64_t* q_empty = q_full + 2;           // [2] both issuers have issued the item's last Q K^T (tcgen05.commit)
-  uint64_t* k_full = q_empty + 2;
-  uint64_t* k_empty = k_full + KV_STAGES;
-  uint64_t* v_full = k_empty + KV_STAGES;
-  uint64_t* v_empty = v_full + KV_STAGES;
-  uint64_t* s_full = v_empty + KV_STAGES;   // [NBUF]
-  uint64_t* p_full = s_full + NBUF;         // [NBUF]
-  uint64_t* o_done = p_full + NBUF;         // [2]
-  uint64_t* o_free = o_done + 2;            // [2]
-  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(o_free + 2);
-
-  const int warp = threadIdx.x >> 5;
-  const int lane = threadIdx.x & 31;
-  const int n_tiles = args.n_kv_tiles;
-  const int n_slots = 2 * n_tiles;
-  const int my_items = (pa.n_items - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;   // items of this CTA
-
-  if (warp == 0 && lane == 0) {
-    ptx::prefetch_tmap(&tmQ);
-    ptx::prefetch_tmap(&tmK);
-    ptx::prefetch_tmap(&tmV);
-    for (int i = 0; i < 2; ++i) {
-      ptx::mbar_init(&q_full[i], 1);
-      ptx::mbar_init(&q_empty[i], 2);
-      ptx::mbar_init(&o_done[i], 1);
-      ptx::mbar_init(&o_free[i], 4);
-    }
-    for (int i = 0; i < KV_STAGES; ++i) {
-      ptx::mbar_init(&k_full[i], 1);
-      ptx::mbar_init(&k_empty[i], 2);
-      ptx::mbar_init(&v_full[i], 1);
-      ptx::mbar_init(&v_empty[i], 2);
-    }
-    for (int i = 0; i < NBUF; ++i) {
-      ptx::mbar_init(&s_full[i], 1);
-      ptx::mbar_init(&p_full[i], 4);
-    }
-    ptx::fence_barrier_init();
-  }
-  if (warp == 2) {
-    ptx::tmem_alloc(tmem_ptr, TMEM_COLS);
-    ptx::tmem_relinquish();
-  }
-  ptx::tc_fence_before();
-  __syncthreads();
-  ptx::tc_fence_after();
-  const uint32_t tmem_base = *tmem_ptr;
-
-  // work item -> (query-tile pair, head, batch); the pair index runs fastest so that CTAs running at the same time
-  // share K/V in L2
-  auto decode = [&](int li, int& q_pair, int& head, int& b) {
-    const int item = (int)blockIdx.x + li * (int)gridDim.x;
-    q_pair = item % pa.q_pairs;
-    const int rest = item / pa.q_pairs;
-    head = rest % pa.heads;
-    b = rest / pa.heads;
-  };
-
-  if (warp == 0) {
-    if (lane == 0) {
-      // ===================== TMA producer =====================
-      int kk = 0;   // running KV tile count
-      for (int li = 0; li < my_items; ++li) {
-        int q_pair, head, b;
-        decode(li, q_pair, head, b);
-        const int qb = li & 1;
-        ptx::mbar_wait(&q_empty[qb], ((li >> 1) & 1) ^ 1);
-        ptx::mbar_expect_tx(&q_full[qb], 2 * TILE_BYTES);
-        ptx::tma_load_3d(sQ + qb * 2 * TILE_BYTES, &tmQ, &q_full[qb], head * DH, q_pair * 2 * BQ, b);
-        ptx::tma_load_3d(sQ + qb * 2 * TILE_BYTES + TILE_BYTES, &tmQ, &q_full[qb], head * DH, q_pair * 2 * BQ + BQ, b);
-        for (int j = 0; j < n_tiles; ++j, ++kk) {
-          const int st = kk % KV_STAGES;
-          const uint32_t ph = (kk / KV_STAGES) & 1;
-          ptx::mbar_wait(&k_empty[st], ph ^ 1);
-          ptx::mbar_expect_tx(&k_full[st], TILE_BYTES);
-          ptx::tma_load_3d(sK + st * TILE_BYTES, &tmK, &k_full[st], head * DH, j * BKV, b);
-          ptx::mbar_wait(&v_empty[st], ph ^ 1);
-          ptx::mbar_expect_tx(&v_full[st], TILE_BYTES);
-          ptx::tma_load_3d(sV + st * TILE_BYTES, &tmV, &v_full[st], head * DH, j * BKV, b);
-        }
-      }
-    }
-  } else if (warp == 1 || warp == 3) {
-    // ===================== MMA issuers =====================
-    // Global slot g = li * n_slots + 2 j + t uses score buffer g % 3; warp 1 owns the even slots (P V of tile 0 and the
-    // Q K^T that reuses that buffer, slot g + 3), warp 3 the odd ones.  The whole warp runs the loop (warp-uniform
-    // barrier addresses / descriptors); one elected lane issues.
-    const int my = warp == 3 ? 1 : 0;
-    constexpr uint32_t idesc_qk = ptx::make_idesc_bf16(BQ, BKV, 0, 0);
-    constexpr uint32_t idesc_pv = ptx::make_idesc_bf16(BQ, DH, 0, 1);
-    const uint64_t qdesc_base = ptx::make_sdesc_sw128(ptx::smem_u32(sQ));
-    const uint64_t kdesc_base = ptx::make_sdesc_sw128(ptx::smem_u32(sK));
-    const uint64_t vdesc_base = ptx::make_sdesc_sw128(ptx::smem_u32(sV));
-    const int total_slots = my_items * n_slots;
-
-    auto issue_qk = [&](int g) {
-      const int li = g / n_slots, n = g - li * n_slots;
-      const int t = n & 1, j = n >> 1, buf = g % NBUF;
-      const int kk = li * n_tiles + j, st = kk % KV_STAGES;
-      if (j == 0) {   // first use of this item's Q by this warp
-        ptx::mbar_wait(&q_full[li & 1], (li >> 1) & 1);
-      }
-      ptx::mbar_wait(&k_full[st], (kk / KV_STAGES) & 1);
-      ptx::tc_fence_after();
-      const uint64_t kdesc = kdesc_base + (uint64_t)(st * (TILE_BYTES >> 4));
-      const uint64_t qd = qdesc_base + (uint64_t)(((li & 1) * 2 + t) * (TILE_BYTES >> 4));
-      if (ptx::elect_one()) {
-#pragma unroll
-        for (int k = 0; k < DH / 16; ++k)
-          ptx::mma_ss(tmem_base + buf * 128, qd + 2 * k, kdesc + 2 * k, idesc_qk, k != 0);
-        ptx::tc_commit(&s_full[buf]);
-        ptx::tc_commit(&k_empty[st]);
-        if (j == n_tiles - 1) ptx::tc_commit(&q_empty[li & 1]);   // this tile's last use of the item's Q
-      }
-      __syncwarp();
-    };
-
-    // Q K^T of slot m is issued by the warp that issued P V of slot m-3 (same buffer): parity (m+1)&1
-    for (int g = 0; g < NBUF && g < total_slots; ++g)
-      if (((g + 1) & 1) == my) issue_qk(g);
-    for (int g = my; g < total_slots; g += 2) {
-      const int li = g / n_slots, n = g - li * n_slots;
-      const int t = n & 1, j = n >> 1, buf = g % NBUF;
-      const int kk = li * n_tiles + j, st = kk % KV_STAGES;
-      ptx::mbar_wait(&v_full[st], (kk / KV_STAGES) & 1);
-      ptx::mbar_wait(&p_full[buf], (g / NBUF) & 1);      // softmax wrote P into the buffer (and rescaled O if needed)
-      if (j == 0 && li > 0) ptx::mbar_wait(&o_free[t], (li - 1) & 1);   // the previous item's O has been read out
-      ptx::tc_fence_after();
-      const uint64_t vdesc = vdesc_base + (uint64_t)(st * (TILE_BYTES >> 4));
-      if (ptx::elect_one()) {
-#pragma unroll
-        for (int k = 0; k < BKV / 16; ++k)   // O_t += P V_j: A = P from TMEM (8 columns per 16 kv), B = V MN-major
-          ptx::mma_ts(tmem_base + COL_O + t * 64, tmem_base + buf * 128 + 8 * k, vdesc + (uint64_t)(128 * k), idesc_pv,
-                      (j | k) != 0);
-        ptx::tc_commit(&o_done[t]);
-        ptx::tc_commit(&v_empty[st]);
-      }
-      __syncwarp();
-      if (g + NBUF < total_slots) issue_qk(g + NBUF);   // reuses this buffer; ordered behind the P V above in the pipe
-    }
-  } else if (warp >= 4) {
-    // ===================== softmax warpgroups =====================
-    const int t = (warp - 4) >> 2;   // query tile of this warpgroup
-    const int q = warp & 3;          // TMEM lane quarter
-    const uint32_t lane_off = (uint32_t)(q * 32) << 16;
-    const uint32_t tO = tmem_base + COL_O + t * 64 + lane_off;
-    const float sl2 = args.scale_log2;
-    const bool ragged = (args.seq_kv % BKV) != 0;
-    for (int li = 0; li < my_items; ++li) {
-      int q_pair, head, b;
-      decode(li, q_pair, head, b);
-      float m_run = -INFINITY;   // the max the running sums are scaled with (raw score units)
-      float l_run = 0.f;
-      auto tile_step = [&](int j, auto masked) {
-        const int g = li * n_slots + 2 * j + t;
-        const int buf = g % NBUF;
-        const uint32_t tS = tmem_base + buf * 128 + lane_off;
-        ptx::mbar_wait(&s_full[buf], (g / NBUF) & 1);
-        ptx::tc_fence_after();
-        uint32_t v[128];
-#pragma unroll
-        for (int c = 0; c < 4; ++c) ptx::tmem_ld32(tS + c * 32, *reinterpret_cast<uint32_t(*)[32]>(&v[c * 32]));
-        ptx::tmem_wait_ld();
-        if constexpr (decltype(masked)::value) {   // only the last KV tile can be ragged
-          const int kv_left = args.seq_kv - j * BKV;
-#pragma unroll
-          for (int i = 0; i < 128; ++i)
-            if (i >= kv_left) v[i] = 0xff800000u;   // -inf
-        }
-        float mxa[8];
-#pragma unroll
-        for (int a = 0; a < 8; ++a) mxa[a] = __uint_as_float(v[a]);
-#pragma unroll
-        for (int i = 8; i < 128; i += 8)
-#pragma unroll
-          for (int a = 0; a < 8; ++a) mxa[a] = fmaxf(mxa[a], __uint_as_float(v[i + a]));
-        const float mx = fmaxf(fmaxf(fmaxf(mxa[0], mxa[1]), fmaxf(mxa[2], mxa[3])),
-                               fmaxf(fmaxf(mxa[4], mxa[5]), fmaxf(mxa[6], mxa[7])));
-        float alpha = 1.0f;
-        const bool grow = (mx - m_run) * sl2 > RESCALE_THRESHOLD;   // true on the first tile (m_run = -inf)
-        if (grow) {
-          alpha = ptx::ex2((m_run - mx) * sl2);
-          m_run = mx;
-        }
-        const float neg_m = -m_run * sl2;
-        uint64_t rs2[4];
-#pragma unroll
-        for (int a = 0; a < 4; ++a) rs2[a] = ptx::pack2(0.f, 0.f);
-        const uint64_t sl2_2 = ptx::pack2(sl2, sl2), negm_2 = ptx::pack2(neg_m, neg_m);
-        uint32_t pk[64];
-#pragma unroll
-        for (int i = 0; i < 64; ++i) {
-          const uint64_t x2 = ptx::fma2(ptx::pack2(__uint_as_float(v[2 * i]), __uint_as_float(v[2 * i + 1])), sl2_2, negm_2);
-          float p0, p1;
-          if (!decltype(masked)::value && (i & 7) < POLY8) {
-            v2::exp2_poly2(x2, p0, p1);
-          } else {
-            float xa, xb;
-            ptx::unpack2(x2, xa, xb);
-            p0 = ptx::ex2(xa);
-            p1 = ptx::ex2(xb);
-          }
-          rs2[i & 3] = ptx::add2(rs2[i & 3], ptx::pack2(p0, p1));
-          pk[i] = ptx::pack_bf16(p0, p1);
-        }
-        float ra, rb, rc, rd;
-        ptx::unpack2(ptx::add2(rs2[0], rs2[1]), ra, rb);
-        ptx::unpack2(ptx::add2(rs2[2], rs2[3]), rc, rd);
-        const float rsum = (ra + rb) + (rc + rd);
-        // O_t may only be touched between P V(j-1) completing and P V(j) being issued (it is issued after our arrive)
-        if (j > 0 && __any_sync(0xffffffffu, grow)) {
-          ptx::mbar_wait(&o_done[t], (li * n_tiles + j - 1) & 1);
-          ptx::tc_fence_after();
-#pragma unroll 1
-          for (int c = 0; c < DH / 32; ++c) {
-            uint32_t o[32];
-            ptx::tmem_ld32(tO + c * 32, o);
-            ptx::tmem_wait_ld();
-#pragma unroll
-            for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
-            ptx::tmem_st32(tO + c * 32, o);
-          }
-        }
-#pragma unroll
-        for (int c = 0; c < 4; ++c) ptx::tmem_st16(tS + c * 16, &pk[c * 16]);
-        l_run = l_run * alpha + rsum;
-        ptx::tmem_wait_st();
-        ptx::tc_fence_before();
-        __syncwarp();
-        if (lane == 0) ptx::mbar_arrive(&p_full[buf]);
-      };
-      for (int j = 0; j + 1 < n_tiles; ++j) tile_step(j, std::false_type{});
-      if (ragged) tile_step(n_tiles - 1, std::true_type{});
-      else tile_step(n_tiles - 1, std::false_type{});
-
-      // epilogue: read O out (then the next item's first P V may overwrite it), O / l (+ LR residual) -> bf16 global
-      ptx::mbar_wait(&o_done[t], (li * n_tiles + n_tiles - 1) & 1);
-      ptx::tc_fence_after();
-      uint32_t o[64];
-      ptx::tmem_ld32(tO, *reinterpret_cast<uint32_t(*)[32]>(&o[0]));
-      ptx::tmem_ld32(tO + 32, *reinterpret_cast<uint32_t(*)[32]>(&o[32]));
-      ptx::tmem_wait_ld();
-      ptx::tc_fence_before();
-      __syncwarp();
-      if (lane == 0) ptx::mbar_arrive(&o_free[t]);
-      const int row = (q_pair * 2 + t) * BQ + q * 32 + lane;
-      const float inv_l = 1.0f / l_run;
-      const bool row_ok = row < args.seq_q;
-      const bool add_lr = args.lr_res != nullptr && row >= args.lr_row_begin && row < args.lr_row_end;
-      if (row_ok) {
-#pragma unroll
-        for (int c = 0; c < DH / 32; ++c) {
-          float f[32];
-#pragma unroll
-          for (int i = 0; i < 32; ++i) f[i] = __uint_as_float(o[c * 32 + i]) * inv_l;
-          if (add_lr) {
-            const uint4* lr = reinterpret_cast<const uint4*>(args.lr_res + (int64_t)b * args.lr_batch_stride +
-                                                             (int64_t)row * args.lr_row_stride + head * DH + c * 32);
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-              const uint4 u = __ldg(lr + i);
-              const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&u);
-#pragma unroll
-              for (int k = 0; k < 4; ++k) {
-                const float2 ff = __bfloat1622float2(h2[k]);
-                f[8 * i + 2 * k] += ff.x;
-                f[8 * i + 2 * k + 1] += ff.y;
-              }
-            }
-          }
-          uint4* dst = reinterpret_cast<uint4*>(args.o + (int64_t)b * args.o_batch_stride +
-                                                (int64_t)row * args.o_row_stride + head * DH + c * 32);
-#pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            uint4 u;
-            u.x = ptx::pack_bf16(f[8 * i + 0], f[8 * i + 1]);
-            u.y = ptx::pack_bf16(f[8 * i + 2], f[8 * i + 3]);
-            u.z = ptx::pack_bf16(f[8 * i + 4], f[8 * i + 5]);
-            u.w = ptx::pack_bf16(f[8 * i + 6], f[8 * i + 7]);
-            dst[i] = u;
-          }
-        }
-      }
-    }
-  }
-
-  __syncwarp();
-  ptx::tc_fence_before();
-  __syncthreads();
-  if (warp == 2) {
-    ptx::tc_fence_after();
-    ptx::tmem_dealloc(tmem_base, TMEM_COLS);
-  }
-}
-
-}  // namespace v2p
-
 }  // namespace attn
 
 extern "C" int dit4sr_attn_fwd(const dit4sr_attn_params* p, void* stream_) {
@@ -981,14 +649,12 @@ extern "C" int dit4sr_attn_fwd(const dit4sr_attn_params* p, void* stream_) {
   // development switches: DIT4SR_ATTN_VARIANT=1 selects the one-tile-per-CTA kernel; DIT4SR_ATTN_POLY=0|2|4 the number
   // of score pairs (of every 8) exponentiated on the FMA pipe instead of MUFU; DIT4SR_ATTN_ISSUERS=1 a single
   // MMA-issuing warp
-  static int variant = 3, poly8 = 2, issuers = 2;   // variant 3 = persistent form of the two-tile kernel
+  static int variant = 2, poly8 = 2, issuers = 2;
   static KernelFn fn2 = nullptr;
-  using KernelFnP = void (*)(const CUtensorMap, const CUtensorMap, const CUtensorMap, const v2p::PArgs);
-  static KernelFnP fn2p = nullptr;
   if (!configured) {
     DIT4SR_CUDA(cudaFuncSetAttribute(attn_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
     const char* e = getenv("DIT4SR_ATTN_VARIANT");
-    if (e != nullptr) variant = atoi(e);
+    if (e != nullptr && e[0] == '1') variant = 1;
     if ((e = getenv("DIT4SR_ATTN_POLY")) != nullptr) poly8 = atoi(e);
     if ((e = getenv("DIT4SR_ATTN_ISSUERS")) != nullptr) issuers = atoi(e) == 1 ? 1 : 2;
     if (issuers == 2)
@@ -996,26 +662,14 @@ extern "C" int dit4sr_attn_fwd(const dit4sr_attn_params* p, void* stream_) {
     else
       fn2 = poly8 == 0 ? v2::attn_fwd2_kernel<0, 1> : (poly8 == 4 ? v2::attn_fwd2_kernel<4, 1> : v2::attn_fwd2_kernel<2, 1>);
     DIT4SR_CUDA(cudaFuncSetAttribute(fn2, cudaFuncAttributeMaxDynamicSharedMemorySize, v2::SMEM_BYTES));
-    fn2p = poly8 == 0 ? v2p::attn_fwd2p_kernel<0> : (poly8 == 4 ? v2p::attn_fwd2p_kernel<4> : v2p::attn_fwd2p_kernel<2>);
-    DIT4SR_CUDA(cudaFuncSetAttribute(fn2p, cudaFuncAttributeMaxDynamicSharedMemorySize, v2p::SMEM_BYTES));
     configured = true;
   }
   if (variant == 1) {
     dim3 grid((p->seq_q + BQ - 1) / BQ, p->heads, p->batches);
     attn_fwd_kernel<<<grid, NUM_THREADS, SMEM_BYTES, stream>>>(tmQ, tmK, tmV, a);
-  } else if (variant == 2 || (variant == 3 && a.n_kv_tiles > 24)) {
-    // long sequences: the per-item prologue is a small share and the hardware's dynamic CTA scheduling balances the
-    // items better than the persistent kernel's static round-robin (S = 8525: 1.09 vs 1.16 ms)
+  } else {
     dim3 grid((p->seq_q + 2 * BQ - 1) / (2 * BQ), p->heads, p->batches);
     fn2<<<grid, v2::NUM_THREADS, v2::SMEM_BYTES, stream>>>(tmQ, tmK, tmV, a);
-  } else {
-    v2p::PArgs pa;
-    pa.a = a;
-    pa.q_pairs = (p->seq_q + 2 * BQ - 1) / (2 * BQ);
-    pa.heads = p->heads;
-    pa.n_items = pa.q_pairs * p->heads * p->batches;
-    const int sms = host::sm_count();
-    fn2p<<<pa.n_items < sms ? pa.n_items : sms, v2p::NUM_THREADS, v2p::SMEM_BYTES, stream>>>(tmQ, tmK, tmV, pa);
   }
   DIT4SR_CUDA(cudaGetLastError());
   return 0;

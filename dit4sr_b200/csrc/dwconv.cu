@@ -59,26 +59,29 @@ dwconv3x3_kernel(const __grid_constant__ CUtensorMap tmLR, const Args a) {
     ptx::tma_load_4d(tile, &tmLR, &bar, c_base, x0 - 1, y0 - 1 + a.lr_row_offset, b);
   }
 
-  // weights + bias for this thread's 8 channels (L2-resident, 221 KB for F=6144)
-  float w[9][8], bias[8];
+  // weights + bias for this thread's 8 channels as packed fp32 pairs (L2-resident, 221 KB for F=6144)
+  uint64_t w2[9][4], bias2[4];
   const bool c_ok = c0 < a.channels;
   if (c_ok) {
 #pragma unroll
     for (int t = 0; t < 9; ++t) {
       const float4* p = reinterpret_cast<const float4*>(a.weight9 + (int64_t)t * a.channels + c0);
       const float4 lo = __ldg(p), hi = __ldg(p + 1);
-      w[t][0] = lo.x; w[t][1] = lo.y; w[t][2] = lo.z; w[t][3] = lo.w;
-      w[t][4] = hi.x; w[t][5] = hi.y; w[t][6] = hi.z; w[t][7] = hi.w;
+      w2[t][0] = ptx::pack2(lo.x, lo.y); w2[t][1] = ptx::pack2(lo.z, lo.w);
+      w2[t][2] = ptx::pack2(hi.x, hi.y); w2[t][3] = ptx::pack2(hi.z, hi.w);
     }
     const float4* p = reinterpret_cast<const float4*>(a.bias + c0);
     const float4 lo = __ldg(p), hi = __ldg(p + 1);
-    bias[0] = lo.x; bias[1] = lo.y; bias[2] = lo.z; bias[3] = lo.w;
-    bias[4] = hi.x; bias[5] = hi.y; bias[6] = hi.z; bias[7] = hi.w;
+    bias2[0] = ptx::pack2(lo.x, lo.y); bias2[1] = ptx::pack2(lo.z, lo.w);
+    bias2[2] = ptx::pack2(hi.x, hi.y); bias2[3] = ptx::pack2(hi.z, hi.w);
   }
   __syncthreads();   // barrier init visible to all waiters
 
   __nv_bfloat16* hq = a.u_hq + (int64_t)b * a.hq_batch_stride + c0;
   const int GH = a.grid_h, GW = a.grid_w;
+
+  // bf16 pair -> packed fp32 pair: (lo << 16, hi & 0xffff0000)
+  auto unpack2 = [](uint32_t u) { return ptx::pack2(__uint_as_float(u << 16), __uint_as_float(u & 0xffff0000u)); };
 
 #pragma unroll 1
   for (int half = 0; half < 2; ++half) {
@@ -94,44 +97,47 @@ dwconv3x3_kernel(const __grid_constant__ CUtensorMap tmLR, const Args a) {
     }
     if (half == 0) ptx::mbar_wait(&bar, 0);
     if (!col_ok) continue;
-    // smem tile layout: [BY][BX][CH] bf16; this thread reads 16 B at channel offset cg*16
+    // smem tile layout: [BY][BX][CH] bf16; this thread reads 16 B at channel offset cg*16.
+    // Every LR row of the halo tile is read and unpacked ONCE and scattered into the (up to three) output rows it
+    // contributes to; all arithmetic is packed fp32x2 (FFMA2): 9 taps x 4 pairs per output pixel.
     const uint8_t* sbase = tile + (size_t)lx * (CH * 2) + cg * 16;
-    uint4 win[3][3];
-#pragma unroll
-    for (int rr = 0; rr < 2; ++rr)
-#pragma unroll
-      for (int dx = 0; dx < 3; ++dx)
-        win[rr][dx] = *reinterpret_cast<const uint4*>(sbase + ((size_t)rr * BX + dx) * (CH * 2));
+    uint64_t acc[TY][4];
 #pragma unroll
     for (int r = 0; r < TY; ++r) {
+      const uint32_t* h = reinterpret_cast<const uint32_t*>(&hv[r]);
 #pragma unroll
-      for (int dx = 0; dx < 3; ++dx)
-        win[2][dx] = *reinterpret_cast<const uint4*>(sbase + ((size_t)(r + 2) * BX + dx) * (CH * 2));
-      const int y = y0 + r;
-      if (y < GH) {
-        float acc[8], t[8];
-        unpack8(hv[r], acc);
+      for (int k = 0; k < 4; ++k) acc[r][k] = ptx::add2(unpack2(h[k]), bias2[k]);
+    }
 #pragma unroll
-        for (int j = 0; j < 8; ++j) acc[j] += bias[j];
-#pragma unroll
-        for (int dy = 0; dy < 3; ++dy)
-#pragma unroll
-          for (int dx = 0; dx < 3; ++dx) {
-            unpack8(win[dy][dx], t);
-#pragma unroll
-            for (int j = 0; j < 8; ++j) acc[j] = fmaf(w[dy * 3 + dx][j], t[j], acc[j]);
-          }
-        uint4 o;
-        o.x = ptx::pack_bf16(acc[0], acc[1]);
-        o.y = ptx::pack_bf16(acc[2], acc[3]);
-        o.z = ptx::pack_bf16(acc[4], acc[5]);
-        o.w = ptx::pack_bf16(acc[6], acc[7]);
-        *reinterpret_cast<uint4*>(hq + ((int64_t)y * GW + x) * a.ld) = o;
-      }
+    for (int ri = 0; ri < BY; ++ri) {
+      uint64_t in[3][4];
 #pragma unroll
       for (int dx = 0; dx < 3; ++dx) {
-        win[0][dx] = win[1][dx];
-        win[1][dx] = win[2][dx];
+        const uint4 u = *reinterpret_cast<const uint4*>(sbase + ((size_t)ri * BX + dx) * (CH * 2));
+        in[dx][0] = unpack2(u.x); in[dx][1] = unpack2(u.y); in[dx][2] = unpack2(u.z); in[dx][3] = unpack2(u.w);
+      }
+#pragma unroll
+      for (int dy = 0; dy < 3; ++dy) {
+        const int r = ri - dy;              // output row fed by this input row through tap row dy
+        if (r >= 0 && r < TY) {
+#pragma unroll
+          for (int dx = 0; dx < 3; ++dx)
+#pragma unroll
+            for (int k = 0; k < 4; ++k) acc[r][k] = ptx::fma2(w2[dy * 3 + dx][k], in[dx][k], acc[r][k]);
+        }
+      }
+      const int r = ri - 2;                 // this output row is complete
+      if (r >= 0) {
+        const int y = y0 + r;
+        if (y < GH) {
+          uint4 o;
+          float f0, f1;
+          ptx::unpack2(acc[r][0], f0, f1); o.x = ptx::pack_bf16(f0, f1);
+          ptx::unpack2(acc[r][1], f0, f1); o.y = ptx::pack_bf16(f0, f1);
+          ptx::unpack2(acc[r][2], f0, f1); o.z = ptx::pack_bf16(f0, f1);
+          ptx::unpack2(acc[r][3], f0, f1); o.w = ptx::pack_bf16(f0, f1);
+          *reinterpret_cast<uint4*>(hq + ((int64_t)y * GW + x) * a.ld) = o;
+        }
       }
     }
   }

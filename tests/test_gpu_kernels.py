@@ -197,7 +197,9 @@ def test_gemm_qkv_rmsnorm_and_double_normed_lr_keys(ops):
 
 @pytest.mark.parametrize("B,H,S,Sq,lr", [(1, 2, 256, 256, None), (2, 3, 333, 333, None), (1, 24, 2381, 2381, (1024, 2048)),
                                          (2, 4, 2381, 2048, (1024, 2048)), (1, 2, 100, 100, None), (1, 1, 1, 1, None),
-                                         (1, 2, 8525, 8525, (4096, 8192))])
+                                         (1, 2, 8525, 8525, (4096, 8192)),
+                                         # many work items per persistent CTA, even / odd KV tile counts
+                                         (4, 24, 700, 700, None), (8, 24, 600, 333, (100, 300)), (3, 24, 129, 129, None)])
 def test_joint_attention(ops, B, H, S, Sq, lr):
     torch.manual_seed(0)
     D = H * 64
@@ -230,6 +232,22 @@ def test_attention_peaked_softmax_is_stable(ops):
     ref = torch.nn.functional.scaled_dot_product_attention(hd(q), hd(k), hd(v)).transpose(1, 2).reshape(B, S, D)
     assert torch.isfinite(o.float()).all()
     assert rel(o.float(), ref) < 6e-3
+
+
+def test_attention_rows_of_ones_at_full_size(ops):
+    """Size-independent property at the C2 shape (B=8, 24 heads, S=2381): with V = 1 every output element is
+    sum(p)/sum(p) = 1 whatever the scores are, and exactly 1 + residual on the LR rows."""
+    torch.manual_seed(0)
+    B, H, N, T = 8, 24, 1024, 333
+    S, D = 2 * N + T, H * 64
+    qkv = torch.randn(B, S, 3 * D, device="cuda").bfloat16()
+    qkv[..., 2 * D:] = 1.0
+    res = torch.randn(B, 2 * N, D, device="cuda").bfloat16()
+    o = torch.zeros(B, S, D, device="cuda", dtype=torch.bfloat16)
+    ops.attention(qkv[..., :D], qkv[..., D:2 * D], qkv[..., 2 * D:], o, H, lr_res=res, lr_rows=(N, 2 * N))
+    ref = torch.ones(B, S, D, device="cuda")
+    ref[:, N:2 * N] += res[:, N:].float()
+    assert (o.float() - ref).abs().max().item() <= 2.0 ** -5      # bf16 rounding of the output (|1 + res| < 8)
 
 
 def test_head_tail_kernels(ops):

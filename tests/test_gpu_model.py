@@ -116,6 +116,20 @@ def test_full_model_24_blocks_velocity():
     assert ebf <= VEL_TOL + floor
 
 
+def test_c3_shape_1024px_velocity():
+    """BASELINE config C3 / C4 shape family: 1024px (4096 HQ + 4096 LR + 333 text tokens, S = 8525: 67 KV tiles, the
+    non-persistent attention path), 2 blocks (1 dual), B=1."""
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.backends.cudnn.allow_tf32 = False
+    cfg = O.sd35_medium_config(num_layers=2, dual_attention_layers=(0,), pos_embed_max_size=96)
+    sd = O.init_state_dict(cfg, seed=0)
+    inputs = O.make_inputs(cfg, 1, 128, 128, 333, seed=1, timestep=500.0)
+    ref32 = _oracle_gpu(sd, cfg, inputs, torch.float32)
+    e = rel(run(build(cfg, sd), inputs), ref32)
+    print(f"1024px, 2 blocks: cuda-vs-fp32 {e:.3e}")
+    assert e <= VEL_TOL
+
+
 def test_unfolded_lr_chains_as_written():
     """fold_lr_chains=False runs the chained LR projections with a bf16 intermediate, as the reference is written."""
     cfg = O.sd35_medium_config(num_layers=3, dual_attention_layers=(0,), pos_embed_max_size=96)
