@@ -66,6 +66,7 @@ SYMBOLS = {
     "dit4sr_patchify_f32": (c_int, [c_vp, c_vp, c_int, c_int, c_int, c_int, c_vp]),
     "dit4sr_timestep_features_f32": (c_int, [c_vp, c_vp, c_int, c_vp]),
     "dit4sr_silu_f32": (c_int, [c_vp, c_vp, c_i64, c_vp]),
+    "dit4sr_euler_update": (c_int, [c_vp, c_vp, c_vp, c_int, c_float, c_i64, c_vp]),
     "dit4sr_cast": (c_int, [c_vp, c_vp, c_i64, c_int, c_vp]),
 }
 

@@ -94,6 +94,17 @@ __global__ void add_bf16_kernel(__nv_bfloat16* __restrict__ dst, int64_t drs, in
   *d = d4;
 }
 
+// x_next = x + dsigma * v (flow-match Euler step in fp32, result cast back to the latent dtype)
+template <typename T>
+__global__ void euler_update_kernel(const T* __restrict__ x, const T* __restrict__ v, T* __restrict__ out, float dsigma,
+                                    int64_t n) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float r = to_f<T>(x[i]) + dsigma * to_f<T>(v[i]);
+  if constexpr (sizeof(T) == 2) out[i] = __float2bfloat16_rn(r);
+  else out[i] = r;
+}
+
 static inline unsigned blocks(int64_t n, int t) { return (unsigned)((n + t - 1) / t); }
 
 }  // namespace misc
@@ -163,6 +174,19 @@ int dit4sr_add_bf16(void* dst, int64_t dst_row_stride, int64_t dst_batch_stride,
   misc::add_bf16_kernel<<<misc::blocks(n, 256), 256, 0, stream>>>((__nv_bfloat16*)dst, dst_row_stride, dst_batch_stride,
                                                                   (const __nv_bfloat16*)src, src_row_stride,
                                                                   src_batch_stride, batches, rows, cols / 8);
+  DIT4SR_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int dit4sr_euler_update(const void* x, const void* v, void* out, int dtype, float dsigma, int64_t n, void* stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  DIT4SR_REQUIRE(x && v && out && n > 0, DIT4SR_E_BADARG, "euler_update: bad argument");
+  if (dtype == DIT4SR_DT_F32)
+    misc::euler_update_kernel<float><<<misc::blocks(n, 256), 256, 0, stream>>>((const float*)x, (const float*)v, (float*)out,
+                                                                               dsigma, n);
+  else
+    misc::euler_update_kernel<__nv_bfloat16><<<misc::blocks(n, 256), 256, 0, stream>>>(
+        (const __nv_bfloat16*)x, (const __nv_bfloat16*)v, (__nv_bfloat16*)out, dsigma, n);
   DIT4SR_CUDA(cudaGetLastError());
   return 0;
 }

@@ -189,6 +189,8 @@ class Engine:
         self._graphs: Dict[Tuple, tuple] = {}
         import os as _os
         self.use_cuda_graph = _os.environ.get("DIT4SR_CUDA_GRAPH", "1") != "0"
+        # capturing the sequence-parallel step (NCCL collectives inside the graph) hung on 2 GPUs in round 1: opt-in only
+        self.sp_graph = _os.environ.get("DIT4SR_SP_GRAPH", "0") == "1"
         self._pos: Dict[Tuple, torch.Tensor] = {}
 
     # ------------------------------------------------------------------------------------------------ profiling
@@ -422,7 +424,9 @@ class Engine:
         recorded once per input shape; replay removes the per-launch host cost, which matters for small batches).
         Same results as `forward` -- the same kernels run. Falls back to direct launches under sequence parallelism,
         while profiling, or if capture is unavailable."""
-        if not self.use_cuda_graph or self.sp is not None or self._prof is not None or self.precise:
+        # sequence parallelism runs with direct launches unless DIT4SR_SP_GRAPH=1 (experimental)
+        if (not self.use_cuda_graph or self._prof is not None or self.precise
+                or (self.sp is not None and not self.sp_graph)):
             return self.forward(hidden_states, controlnet_image, encoder_hidden_states, pooled_projections, timestep,
                                 out=out, euler=euler)
         B = hidden_states.shape[0]
@@ -457,6 +461,11 @@ class Engine:
         st["t"].copy_(timestep.to(device=st["t"].device, dtype=torch.float32).expand(B))
         graph.replay()
         ops._count(n_launch)
+        if euler is not None and self.sp is not None:   # the graph left the gathered velocity image behind
+            if out is None:
+                out = torch.empty_like(euler[0])
+            ops.euler_update(euler[0].contiguous(), vel.to(euler[0].dtype), out, euler[1])
+            return out
         if euler is not None:        # x_next = x + dsigma * v straight from the velocity tokens the graph left behind
             h = hidden_states.shape[-1]
             ws = self._workspace(B, (h // 2) ** 2, encoder_hidden_states.shape[1], hidden_states.device)

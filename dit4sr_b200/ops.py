@@ -230,6 +230,22 @@ def unpatchify(tok, out, latents=None, dsigma=0.0):
     _count()
 
 
+def euler_update(x, v, out, dsigma):
+    """out = x + dsigma * v (contiguous tensors of one dtype, fp32 or bf16)."""
+    if not (x.is_contiguous() and v.is_contiguous() and out.is_contiguous()):
+        raise _lib.Dit4srError("euler_update: tensors must be contiguous")
+    if not (x.dtype == v.dtype == out.dtype) or x.dtype not in (torch.float32, torch.bfloat16):
+        raise _lib.Dit4srError("euler_update: x, v, out must share dtype fp32 or bf16")
+    if not (x.numel() == v.numel() == out.numel()):
+        raise _lib.Dit4srError("euler_update: size mismatch")
+    for n_, t_ in (("x", x), ("v", v), ("out", out)):
+        _req(t_, x.dtype, n_)
+    dt = DT_F32 if x.dtype == torch.float32 else DT_BF16
+    check(_lib.load().dit4sr_euler_update(_ptr(x), _ptr(v), _ptr(out), dt, float(dsigma), x.numel(), _stream()),
+          "dit4sr_euler_update")
+    _count()
+
+
 def timestep_features(t, out):
     _req(t, torch.float32, "timestep")
     if out.dtype == torch.float32:      # fp32-accurate mode

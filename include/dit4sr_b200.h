@@ -194,6 +194,10 @@ int dit4sr_dwconv3x3_add_f32(float* u_hq, const float* u_lr, int64_t ld, int64_t
 int dit4sr_patchify_f32(const float* x, float* patches, int batches, int channels, int height, int width, void* stream);
 int dit4sr_timestep_features_f32(const float* timesteps, float* out, int batches, void* stream);
 int dit4sr_silu_f32(const float* x, float* y, int64_t n, void* stream);
+/* out = x + dsigma * v over n contiguous elements of dtype (DIT4SR_DT_*), fp32 arithmetic: the flow-match Euler step
+ * `scheduler.step` of pipelines/pipeline_dit4sr.py:1567 when the velocity is not taken straight from the unpatchify
+ * kernel (sequence-parallel sampling, where the velocity strips are gathered first). */
+int dit4sr_euler_update(const void* x, const void* v, void* out, int dtype, float dsigma, int64_t n, void* stream);
 /* y = x (fp32 -> bf16 or bf16 -> fp32), n elements; dir 0 = f32->bf16, 1 = bf16->f32 */
 int dit4sr_cast(const void* x, void* y, int64_t n, int dir, void* stream);
 
