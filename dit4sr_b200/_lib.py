@@ -67,6 +67,9 @@ SYMBOLS = {
     "dit4sr_timestep_features_f32": (c_int, [c_vp, c_vp, c_int, c_vp]),
     "dit4sr_silu_f32": (c_int, [c_vp, c_vp, c_i64, c_vp]),
     "dit4sr_euler_update": (c_int, [c_vp, c_vp, c_vp, c_int, c_float, c_i64, c_vp]),
+    "dit4sr_wavelet_blur_f32": (c_int, [c_vp, c_vp, c_vp, c_int, c_int, c_int, c_int, c_vp]),
+    "dit4sr_plane_stats_f32": (c_int, [c_vp, c_int, c_i64, c_vp, c_vp, c_vp]),
+    "dit4sr_adain_apply_f32": (c_int, [c_vp, c_vp, c_int, c_i64, c_vp, c_vp, c_vp, c_vp, c_float, c_vp]),
     "dit4sr_cast": (c_int, [c_vp, c_vp, c_i64, c_int, c_vp]),
 }
 

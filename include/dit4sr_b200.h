@@ -198,6 +198,19 @@ int dit4sr_silu_f32(const float* x, float* y, int64_t n, void* stream);
  * `scheduler.step` of pipelines/pipeline_dit4sr.py:1567 when the velocity is not taken straight from the unpatchify
  * kernel (sequence-parallel sampling, where the velocity strips are gathered first). */
 int dit4sr_euler_update(const void* x, const void* v, void* out, int dtype, float dsigma, int64_t n, void* stream);
+/* ---------------------------------------------------------------------------------------------------------------
+ * Colour fix of the SR result against the LQ input (reference utils/wavelet_color_fix.py, called
+ * from test/test.py:381-383), fp32 images [planes = batch*3, height, width].
+ * wavelet_blur: low = 3x3 [1 2 1]x[1 2 1]/16 blur of `image` with dilation `radius` and replicate padding
+ * (wavelet_color_fix.py:76-94); if high_accum != NULL also high_accum += image - low (one level of
+ * wavelet_decomposition, :96-110).  plane_stats: per-plane mean and UNBIASED variance (calc_mean_std, :47-60).
+ * adain_apply: out = (content - c_mean) / sqrt(c_var + eps) * sqrt(s_var + eps) + s_mean (:62-74). */
+int dit4sr_wavelet_blur_f32(const float* image, float* low, float* high_accum, int planes, int height, int width,
+                            int radius, void* stream);
+int dit4sr_plane_stats_f32(const float* x, int planes, int64_t plane_elems, float* mean, float* var_unbiased,
+                           void* stream);
+int dit4sr_adain_apply_f32(const float* content, float* out, int planes, int64_t plane_elems, const float* c_mean,
+                           const float* c_var, const float* s_mean, const float* s_var, float eps, void* stream);
 /* y = x (fp32 -> bf16 or bf16 -> fp32), n elements; dir 0 = f32->bf16, 1 = bf16->f32 */
 int dit4sr_cast(const void* x, void* y, int64_t n, int dir, void* stream);
 
