@@ -1,5 +1,8 @@
+"""Developer stress test of the joint-attention kernel: repeated launches on shapes with several work items per SM and
+even/odd KV tile counts, each checked against torch SDPA (this is what exposed the intermittent deadlock of the
+withdrawn persistent variant).  Usage: python tools/stress_attn.py"""
 import sys, os, torch
-sys.path.insert(0, "/root/repo")
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from dit4sr_b200 import ops
 torch.manual_seed(0)
 def run(B,H,S,Sq,lr,iters):
