@@ -315,6 +315,17 @@ def run_ours(args):
                         frac_of_burst=round(ach / peaks["tf_burst"], 4), frac_of_spec_2250=round(ach / 2250.0, 4),
                         launch_ms=round(ff1_avg_ms, 4), flops_per_launch=ff1_flops, launches_timed=len(ff1_ms["ff1"]),
                         traffic=traffic, traffic_source=traffic_source)
+        # second roofline entry: the joint-attention kernel (largest share of the step), from the instrumented extra step
+        roof_attn = None
+        if breakdown and breakdown.get("attn"):
+            a_ms = breakdown["attn"]["total_ms"] / breakdown["attn"]["launches"]
+            a_flops = attn_f * images_total / world / breakdown["attn"]["launches"]      # average over joint + attn2 calls
+            a_ach = a_flops / (a_ms / 1e3) / 1e12
+            roof_attn = dict(bound="tensor", kernel="attn_fwd2_kernel (joint attention, head_dim 64: MUFU.EX2-limited to "
+                             "~51% of the tensor pipe, DESIGN.md 3.2)", achieved=round(a_ach, 1), peak=peaks["tf_sustained"],
+                             unit="TFLOP/s", frac=round(a_ach / peaks["tf_sustained"], 4),
+                             frac_of_burst=round(a_ach / peaks["tf_burst"], 4), launch_ms=round(a_ms, 4),
+                             flops_per_launch=a_flops, launches_timed=breakdown["attn"]["launches"], traffic=None)
         line = dict(
             metric="denoise_steps_per_sec", value=round(value, 3), unit="image-steps/s (one image advanced one denoise step)",
             n_gpus=world, steps=args.steps, warmup=args.warmup, ms_per_step=round(ms / args.steps, 3),
@@ -330,7 +341,8 @@ def run_ours(args):
             e2e=dict(value=round(img_steps / (e2e_ms / 1e3), 3), unit="image-steps/s", h2d_bytes_per_step=h2d,
                      d2h_bytes_per_step=d2h, ms_per_step=round(e2e_ms / args.steps, 3),
                      api="dit4sr_b200.SD3Transformer2DModel.forward, pinned host inputs, velocity copied back"),
-            gpu_launches=launches, clocks=clocks, roofline=roof, cpu_baseline=cpu, kernel_breakdown_ms=breakdown,
+            gpu_launches=launches, clocks=clocks, roofline=roof, roofline_attention=roof_attn, cpu_baseline=cpu,
+            kernel_breakdown_ms=breakdown,
         )
         print(json.dumps(line))
     if world > 1:

@@ -22,8 +22,12 @@ constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
 constexpr int NUM_THREADS = 256;
 constexpr int TMEM_COLS = ACC_STAGES * BN;  // 512
 constexpr int EPI_ROW_BYTES = 144;                       // 128 B of payload + 16 B pad: conflict-free 16 B accesses
-constexpr int EPI_STAGE_BYTES = 32 * EPI_ROW_BYTES;      // per epilogue warp
-constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/ + 4 * EPI_STAGE_BYTES;
+constexpr int RED_BOX_BYTES = 32 * 32 * 4;               // 32 rows x 32 fp32 columns, 128-byte swizzled (TMA reduce source)
+constexpr int EPI_STAGE_BYTES = 2 * RED_BOX_BYTES;       // per epilogue warp: two reduce boxes, or one padded staging tile
+static_assert(32 * EPI_ROW_BYTES <= EPI_STAGE_BYTES, "staging tile must fit");
+// layout: [operand ring][4 epilogue staging areas (1024-byte aligned)][barriers]
+constexpr int SMEM_BYTES = 1024 /*align*/ + STAGES * STAGE_BYTES + 4 * EPI_STAGE_BYTES + 256 /*barriers*/;
+static_assert(SMEM_BYTES <= 232448, "exceeds the 227 KB of shared memory per CTA");
 constexpr int MAX_PROBLEMS = DIT4SR_GEMM_MAX_GROUP;
 
 struct Problem {
@@ -43,6 +47,7 @@ struct Problem {
   int sec_cols;
   float eps;
   int64_t dbl_row_offset;
+  int c_reduce;   // GATE_RESID with resid == C: the epilogue adds gate*y into C with TMA reduce-adds (maps.c)
 };
 
 // Tail splitting: with T tiles on G CTAs the last T mod G tiles would occupy a whole extra wave with most SMs idle
@@ -61,6 +66,7 @@ struct Maps {
   CUtensorMap a[MAX_PROBLEMS];
   CUtensorMap w[MAX_PROBLEMS];
   CUtensorMap ws[MAX_PROBLEMS];   // W with a BN/split-row box (only valid when split > 1)
+  CUtensorMap c[MAX_PROBLEMS];    // fp32 C as (N, rows, batches) with a 32x32 box (only valid when c_reduce)
 };
 
 struct TileCoord {
@@ -125,13 +131,15 @@ __device__ __forceinline__ void store_f32x32(float* dst, const float* f) {
   for (int i = 0; i < 8; ++i) d4[i] = make_float4(f[4 * i], f[4 * i + 1], f[4 * i + 2], f[4 * i + 3]);
 }
 
-template <int EPI>
+// RED (GATE_RESID only): every problem of the launch is an in-place gated residual and the epilogue adds into C with TMA
+// reduce-adds (Problem::c_reduce); a separate instance so that neither epilogue pays for the other's registers.
+template <int EPI, bool RED = false>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 gemm_kernel(const __grid_constant__ Maps maps, const __grid_constant__ Group grp) {
   extern __shared__ uint8_t smem_raw[];
   // 1024-byte alignment for SWIZZLE_128B tiles
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES + 4 * EPI_STAGE_BYTES);
   uint64_t* full_bar = bars;                       // [STAGES]
   uint64_t* empty_bar = bars + STAGES;             // [STAGES]
   uint64_t* tfull_bar = bars + 2 * STAGES;         // [ACC_STAGES]
@@ -232,7 +240,7 @@ gemm_kernel(const __grid_constant__ Maps maps, const __grid_constant__ Group grp
     // through a per-warp shared-memory staging tile so that every global access of the warp is a few whole contiguous
     // row segments (128 B per row per instruction) instead of 32 scattered 16-byte pieces.
     const int q = warp & 3;  // TMEM lane quarter this warp may access
-    uint8_t* stg = smem + STAGES * STAGE_BYTES + 256 + q * EPI_STAGE_BYTES;
+    uint8_t* stg = smem + STAGES * STAGE_BYTES + q * EPI_STAGE_BYTES;
     const int sub = lane >> 3, seg = lane & 7;
     int it = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
@@ -367,6 +375,54 @@ gemm_kernel(const __grid_constant__ Maps maps, const __grid_constant__ Group grp
           Rf = P.resid + (int64_t)tc.b * P.r_batch_stride + n_base;
           g_row = P.gate ? P.gate + (int64_t)tc.b * P.gate_batch_stride + n_base : nullptr;
         }
+        if constexpr (EPI == DIT4SR_EPI_GATE_RESID && RED) {
+          {
+            // ---- in-place gated residual: C += gate * (acc + bias) as TMA reduce-adds of 32x32 fp32 boxes.  The SM
+            // never reads the residual (the addition happens at L2) and the stores are asynchronous bulk operations, so
+            // this epilogue is a TMEM read, 32 FMAs per row and eight shared-memory stores per pass.
+            const CUtensorMap* mc = &maps.c[tc.pi];
+            const float* b_row = P.bias != nullptr ? P.bias + n_base : nullptr;
+            ptx::mbar_wait(&tfull_bar[as], aphase);
+            ptx::tc_fence_after();
+            uint32_t v[2][32];
+            ptx::tmem_ld32(taddr, v[0]);
+#pragma unroll
+            for (int ch = 0; ch < BN / 32; ++ch) {
+              const int c0 = ch * 32;
+              if (c0 < n_valid) {
+                ptx::tmem_wait_ld();
+                if (c0 + 32 < n_valid) ptx::tmem_ld32(taddr + c0 + 32, v[(ch + 1) & 1]);
+                uint8_t* box = stg + (ch & 1) * RED_BOX_BYTES;
+                if (lane == 0) ptx::bulk_wait_read<1>();   // the reduce issued from this box two passes ago has read it
+                __syncwarp();
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                  float4 bb = make_float4(0.f, 0.f, 0.f, 0.f), gg = make_float4(1.f, 1.f, 1.f, 1.f);
+                  if (b_row != nullptr) bb = __ldg(reinterpret_cast<const float4*>(b_row + c0) + i);
+                  if (g_row != nullptr) gg = __ldg(reinterpret_cast<const float4*>(g_row + c0) + i);
+                  float4 a;
+                  a.x = gg.x * (__uint_as_float(v[ch & 1][4 * i + 0]) + bb.x);
+                  a.y = gg.y * (__uint_as_float(v[ch & 1][4 * i + 1]) + bb.y);
+                  a.z = gg.z * (__uint_as_float(v[ch & 1][4 * i + 2]) + bb.z);
+                  a.w = gg.w * (__uint_as_float(v[ch & 1][4 * i + 3]) + bb.w);
+                  // 128-byte swizzle: 16-byte chunk i of row r lives at chunk i ^ (r & 7)
+                  *reinterpret_cast<float4*>(box + lane * 128 + ((i ^ (lane & 7)) << 4)) = a;
+                }
+                ptx::fence_proxy_async();
+                __syncwarp();
+                if (lane == 0 && row_base < P.rows) {
+                  ptx::tma_reduce_add_3d(mc, box, n_base + c0, row_base, tc.b);   // rows >= P.rows are clipped
+                  ptx::bulk_commit();
+                }
+              }
+            }
+            ptx::tc_fence_before();
+            __syncwarp();
+            if (lane == 0) ptx::mbar_arrive(&tempty_bar[as]);
+            continue;
+          }
+        }
+        if constexpr (RED) continue;   // (not reached: the block above ends the iteration)
         // The residual rows are the only cold global reads of this epilogue and each warp has just one 32-column pass
         // of them in flight, so pull the NEXT tile's residual rows into L2 now (a whole tile ahead of their use).
         if constexpr (EPI == DIT4SR_EPI_GATE_RESID) {
@@ -456,6 +512,7 @@ gemm_kernel(const __grid_constant__ Maps maps, const __grid_constant__ Group grp
     }
   }
 
+  if (RED && warp >= 4 && lane == 0) ptx::bulk_wait_all();   // outstanding reduce-adds
   __syncwarp();
   ptx::tc_fence_before();
   __syncthreads();
@@ -465,16 +522,16 @@ gemm_kernel(const __grid_constant__ Maps maps, const __grid_constant__ Group grp
   }
 }
 
-template <int EPI>
+template <int EPI, bool RED = false>
 static int launch(const Maps& maps, const Group& g, cudaStream_t stream) {
   static bool configured = false;  // benign race: idempotent attribute set
   if (!configured) {
-    DIT4SR_CUDA(cudaFuncSetAttribute(gemm_kernel<EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+    DIT4SR_CUDA(cudaFuncSetAttribute(gemm_kernel<EPI, RED>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
     configured = true;
   }
   int grid = host::sm_count();
   if (grid > g.num_tiles) grid = g.num_tiles;
-  gemm_kernel<EPI><<<grid, NUM_THREADS, SMEM_BYTES, stream>>>(maps, g);
+  gemm_kernel<EPI, RED><<<grid, NUM_THREADS, SMEM_BYTES, stream>>>(maps, g);
   DIT4SR_CUDA(cudaGetLastError());
   return 0;
 }
@@ -565,12 +622,26 @@ extern "C" int dit4sr_gemm_bf16_grouped(const dit4sr_gemm_params* probs, int cou
     P.sec_cols = p->sec_cols > 0 ? p->sec_cols : p->N;
     P.eps = p->eps;
     P.dbl_row_offset = p->dbl_row_offset;
+    // in-place gated residual -> TMA reduce-add epilogue (DIT4SR_GEMM_REDUCE=0 keeps the load/add/store epilogue)
+    static int reduce_enabled = -1;
+    if (reduce_enabled < 0) { const char* e = getenv("DIT4SR_GEMM_REDUCE"); reduce_enabled = (e == nullptr || e[0] != '0') ? 1 : 0; }
+    P.c_reduce = reduce_enabled && epilogue == DIT4SR_EPI_GATE_RESID && p->resid == p->C && p->ldr == p->ldc &&
+                 (p->batches == 1 || p->r_batch_stride == p->c_batch_stride);
+    maps.c[i] = maps.a[i];
+    if (P.c_reduce) {
+      uint64_t dims[3] = {(uint64_t)p->N, (uint64_t)p->rows, (uint64_t)p->batches};
+      uint64_t strides[2] = {(uint64_t)p->ldc * 4,
+                             (uint64_t)(p->batches > 1 ? p->c_batch_stride : (int64_t)p->rows * p->ldc) * 4};
+      uint32_t box[3] = {32, 32, 1};
+      if ((rc = host::make_tmap_f32(&maps.c[i], p->C, 3, dims, strides, box)) != 0) return rc;
+    }
   }
   for (int i = count; i < MAX_PROBLEMS; ++i) {
     g.p[i] = g.p[0];
     g.p[i].tile_begin = 0x7fffffff;
     maps.a[i] = maps.a[0];
     maps.w[i] = maps.w[0];
+    maps.c[i] = maps.c[0];
   }
   // tail splitting (see Group): only when every problem's N is a whole number of 256-column tiles
   g.num_tiles = tiles;
@@ -607,7 +678,12 @@ extern "C" int dit4sr_gemm_bf16_grouped(const dit4sr_gemm_params* probs, int cou
     case DIT4SR_EPI_BIAS_GELU: return launch<DIT4SR_EPI_BIAS_GELU>(maps, g, stream);
     case DIT4SR_EPI_BIAS_SILU: return launch<DIT4SR_EPI_BIAS_SILU>(maps, g, stream);
     case DIT4SR_EPI_QKV_NORM: return launch<DIT4SR_EPI_QKV_NORM>(maps, g, stream);
-    default: return launch<DIT4SR_EPI_GATE_RESID>(maps, g, stream);
+    default: {
+      bool all_reduce = true;
+      for (int i = 0; i < count; ++i) all_reduce = all_reduce && g.p[i].c_reduce;
+      return all_reduce ? launch<DIT4SR_EPI_GATE_RESID, true>(maps, g, stream)
+                        : launch<DIT4SR_EPI_GATE_RESID, false>(maps, g, stream);
+    }
   }
 }
 

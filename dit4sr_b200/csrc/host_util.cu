@@ -33,7 +33,14 @@ static EncodeTiledFn get_encode() {
 }
 
 static int make_tmap_impl(CUtensorMap* out, const void* base, int rank, const uint64_t* dims,
-                          const uint64_t* strides_bytes, const uint32_t* box, CUtensorMapSwizzle swz);
+                          const uint64_t* strides_bytes, const uint32_t* box, CUtensorMapSwizzle swz,
+                          CUtensorMapDataType dt = CU_TENSOR_MAP_DATA_TYPE_BFLOAT16);
+
+int make_tmap_f32(CUtensorMap* out, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
+                  const uint32_t* box) {
+  return make_tmap_impl(out, base, rank, dims, strides_bytes, box, CU_TENSOR_MAP_SWIZZLE_128B,
+                        CU_TENSOR_MAP_DATA_TYPE_FLOAT32);
+}
 
 int make_tmap_bf16(CUtensorMap* out, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
                    const uint32_t* box) {
@@ -46,7 +53,8 @@ int make_tmap_bf16_noswizzle(CUtensorMap* out, const void* base, int rank, const
 }
 
 static int make_tmap_impl(CUtensorMap* out, const void* base, int rank, const uint64_t* dims,
-                          const uint64_t* strides_bytes, const uint32_t* box, CUtensorMapSwizzle swz) {
+                          const uint64_t* strides_bytes, const uint32_t* box, CUtensorMapSwizzle swz,
+                          CUtensorMapDataType dt) {
   EncodeTiledFn enc = get_encode();
   DIT4SR_REQUIRE(enc != nullptr, DIT4SR_E_DRIVER, "cuTensorMapEncodeTiled entry point not available");
   DIT4SR_REQUIRE(aligned16(base), DIT4SR_E_ALIGN, "TMA base pointer %p not 16-byte aligned", base);
@@ -64,7 +72,7 @@ static int make_tmap_impl(CUtensorMap* out, const void* base, int rank, const ui
       gstr[i - 1] = strides_bytes[i - 1];
     }
   }
-  CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void*>(base), gdim, gstr, bx, es,
+  CUresult r = enc(out, dt, (cuuint32_t)rank, const_cast<void*>(base), gdim, gstr, bx, es,
                    CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   DIT4SR_REQUIRE(r == CUDA_SUCCESS, DIT4SR_E_DRIVER, "cuTensorMapEncodeTiled failed with CUresult %d (rank %d)", (int)r,

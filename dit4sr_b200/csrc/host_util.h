@@ -40,6 +40,10 @@ int make_tmap_bf16(CUtensorMap* out, const void* base, int rank, const uint64_t*
 int make_tmap_bf16_noswizzle(CUtensorMap* out, const void* base, int rank, const uint64_t* dims,
                              const uint64_t* strides_bytes, const uint32_t* box);
 
+// fp32 tensor map with 128-byte swizzle (inner box extent must be 32 floats = 128 bytes).
+int make_tmap_f32(CUtensorMap* out, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
+                  const uint32_t* box);
+
 int sm_count();
 
 }  // namespace host

@@ -60,11 +60,14 @@ __device__ __forceinline__ bool mbar_test_wait(uint64_t* bar, uint32_t parity) {
       : "memory");
   return ok != 0;
 }
-// Bounded spin: a barrier that never completes (a protocol bug) traps instead of hanging the GPU box.
+// Bounded spin: a barrier that never completes (a protocol bug) traps instead of hanging the GPU box.  A failed
+// try_wait comes back after a hardware time-out of a few microseconds, so 2^22 of them are >= ~10 s: far beyond any
+// legitimate wait (longest: a tile time), and short enough that a deadlocked launch fails within seconds (2^26 took
+// minutes of box time per deadlocked launch).
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   uint32_t spins = 0;
   while (!mbar_try_wait(bar, parity)) {
-    if (++spins > (1u << 26)) { __trap(); }
+    if (++spins > (1u << 22)) { __trap(); }
   }
 }
 
@@ -99,6 +102,19 @@ __device__ __forceinline__ void bulk_load(void* smem, const void* gptr, uint32_t
                ::"r"(smem_u32(smem)), "l"(gptr), "r"(bytes), "r"(smem_u32(bar))
                : "memory");
 }
+// Reduce-add of a shared-memory box into global memory through the TMA engine (the addition happens at L2, element type
+// from the tensor map): the issuing SM never reads the destination.  Completion is tracked by bulk async-groups.
+__device__ __forceinline__ void tma_reduce_add_3d(const CUtensorMap* m, const void* smem, int c0, int c1, int c2) {
+  asm volatile("cp.reduce.async.bulk.tensor.3d.global.shared::cta.add.tile.bulk_group [%0, {%2, %3, %4}], [%1];"
+               ::"l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(smem)), "r"(c0), "r"(c1), "r"(c2)
+               : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void bulk_wait_read() {   // <= N groups of this thread still reading their smem source
+  asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory");
+}
+__device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 __device__ __forceinline__ void prefetch_l2(const void* p) {
   asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
 }
@@ -225,6 +241,11 @@ __device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
 __device__ __forceinline__ float ex2(float x) {
   float y;
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float max3(float a, float b, float c) {   // one FMNMX3
+  float y;
+  asm("max.f32 %0, %1, %2, %3;" : "=f"(y) : "f"(a), "f"(b), "f"(c));
   return y;
 }
 __device__ __forceinline__ float tanh_approx(float x) {

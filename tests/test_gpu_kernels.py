@@ -234,6 +234,26 @@ def test_attention_peaked_softmax_is_stable(ops):
     assert rel(o.float(), ref) < 6e-3
 
 
+@pytest.mark.parametrize("S", [640, 1101])
+def test_attention_scores_growing_along_keys(ops, S):
+    """Key norms grow along the sequence, so in every KV tile some rows outgrow their reference max by more than the
+    lazy-rescale threshold: exercises the fall-back of the speculative softmax (exponentials taken against the
+    previous reference, redone when the vote says a row grew) on whole and ragged last tiles."""
+    torch.manual_seed(0)
+    B, H = 2, 3
+    D = H * 64
+    qkv = torch.randn(B, S, 3 * D, device="cuda")
+    qkv[..., D:2 * D] *= torch.linspace(0.05, 6.0, S, device="cuda")[None, :, None]
+    qkv = qkv.bfloat16()
+    q, k, v = qkv[..., :D], qkv[..., D:2 * D], qkv[..., 2 * D:]
+    o = torch.zeros(B, S, D, device="cuda", dtype=torch.bfloat16)
+    ops.attention(q, k, v, o, H)
+    hd = lambda t: t.float().reshape(B, S, H, 64).transpose(1, 2)
+    ref = torch.nn.functional.scaled_dot_product_attention(hd(q), hd(k), hd(v)).transpose(1, 2).reshape(B, S, D)
+    assert torch.isfinite(o.float()).all()
+    assert rel(o.float(), ref) < 6e-3
+
+
 def test_attention_rows_of_ones_at_full_size(ops):
     """Size-independent property at the C2 shape (B=8, 24 heads, S=2381): with V = 1 every output element is
     sum(p)/sum(p) = 1 whatever the scores are, and exactly 1 + residual on the LR rows."""
