@@ -51,6 +51,7 @@ SYMBOLS = {
     "dit4sr_dwconv3x3_add": (c_int, [C.POINTER(DwconvParams), c_vp]),
     "dit4sr_gemm_bf16": (c_int, [C.POINTER(GemmParams), c_vp]),
     "dit4sr_gemm_bf16_grouped": (c_int, [C.POINTER(GemmParams), c_int, c_vp]),
+    "dit4sr_gemm_schedule": (c_int, [C.POINTER(GemmParams), c_int, c_int, C.POINTER(c_int), c_int]),
     "dit4sr_attn_fwd": (c_int, [C.POINTER(AttnParams), c_vp]),
     "dit4sr_patchify": (c_int, [c_vp, c_int, c_vp, c_int, c_int, c_int, c_int, c_vp]),
     "dit4sr_unpatchify": (c_int, [c_vp, c_vp, c_int, c_vp, c_float, c_int, c_int, c_int, c_int, c_vp]),

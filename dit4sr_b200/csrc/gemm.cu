@@ -75,7 +75,7 @@ struct TileCoord {
   int bn;     // its width: BN, or BN/split for a slice of a tail tile
 };
 
-__device__ __forceinline__ TileCoord decode_tile(const Group& g, int item) {
+__host__ __device__ __forceinline__ TileCoord decode_tile(const Group& g, int item) {
   int tile = item, part = 0, bn = BN;
   if (item >= g.split_begin) {
     const int idx = item - g.split_begin;
@@ -565,6 +565,46 @@ static int check_problem(const dit4sr_gemm_params* p, int epilogue) {
   return 0;
 }
 
+// Tile schedule of a group: pure host arithmetic shared by the launch path and dit4sr_gemm_schedule (so that the
+// schedule the CPU tests enumerate is the one the kernel walks).  Fills the shape fields of g.p[0..count) and the
+// work-item counts; does not touch pointers.
+static void plan_tiles(const dit4sr_gemm_params* probs, int count, int sms, bool tail_split, Group& g) {
+  g.num_problems = count;
+  int tiles = 0;
+  bool whole = true;
+  for (int i = 0; i < count; ++i) {
+    const dit4sr_gemm_params* p = &probs[i];
+    Problem& P = g.p[i];
+    P.rows = p->rows;
+    P.N = p->N;
+    P.m_tiles = (p->rows + BM - 1) / BM;
+    P.n_tiles = (p->N + BN - 1) / BN;
+    P.k_blocks = (p->K + BK - 1) / BK;
+    P.tile_begin = tiles;
+    tiles += P.m_tiles * P.n_tiles * p->batches;
+    whole = whole && (p->N % BN == 0);
+  }
+  // tail splitting (see Group): only when every problem's N is a whole number of 256-column tiles
+  g.num_tiles = tiles;
+  g.split_begin = tiles;
+  g.split = 1;
+  const int rem = tiles % sms;
+  if (tail_split && whole && tiles > sms && rem > 0) {
+    const int split = 4 * rem <= sms ? 4 : (2 * rem <= sms ? 2 : 1);
+    if (split > 1) {
+      g.split = split;
+      g.split_begin = tiles - rem;
+      g.num_tiles = g.split_begin + rem * split;
+    }
+  }
+}
+
+static bool tail_split_enabled() {
+  static int enabled = -1;
+  if (enabled < 0) { const char* e = getenv("DIT4SR_GEMM_TAIL_SPLIT"); enabled = (e == nullptr || e[0] != '0') ? 1 : 0; }
+  return enabled != 0;
+}
+
 }  // namespace gemm
 
 extern "C" int dit4sr_gemm_bf16_grouped(const dit4sr_gemm_params* probs, int count, void* stream_) {
@@ -582,8 +622,7 @@ extern "C" int dit4sr_gemm_bf16_grouped(const dit4sr_gemm_params* probs, int cou
 
   Maps maps;
   Group g;
-  g.num_problems = count;
-  int tiles = 0;
+  plan_tiles(probs, count, host::sm_count(), tail_split_enabled(), g);
   for (int i = 0; i < count; ++i) {
     const dit4sr_gemm_params* p = &probs[i];
     {
@@ -599,19 +638,19 @@ extern "C" int dit4sr_gemm_bf16_grouped(const dit4sr_gemm_params* probs, int cou
       uint32_t box[2] = {BK, BN};
       if ((rc = host::make_tmap_bf16(&maps.w[i], p->W, 2, dims, strides, box)) != 0) return rc;
     }
-    Problem& P = g.p[i];
+    maps.ws[i] = maps.w[i];
+    if (g.split > 1) {   // W through a box of BN/split rows for the column slices of the tail tiles
+      uint64_t dims[2] = {(uint64_t)p->K, (uint64_t)p->N};
+      uint64_t strides[1] = {(uint64_t)p->ldw * 2};
+      uint32_t box[2] = {BK, (uint32_t)(BN / g.split)};
+      if ((rc = host::make_tmap_bf16(&maps.ws[i], p->W, 2, dims, strides, box)) != 0) return rc;
+    }
+    Problem& P = g.p[i];   // shape fields were set by plan_tiles
     P.bias = p->bias;
     P.C = p->C;
     P.ldc = p->ldc;
     P.c_batch_stride = p->c_batch_stride;
     P.c_f32 = p->c_dtype == DIT4SR_DT_F32;
-    P.rows = p->rows;
-    P.N = p->N;
-    P.m_tiles = (p->rows + BM - 1) / BM;
-    P.n_tiles = (p->N + BN - 1) / BN;
-    P.k_blocks = (p->K + BK - 1) / BK;
-    P.tile_begin = tiles;
-    tiles += P.m_tiles * P.n_tiles * p->batches;
     P.gate = p->gate;
     P.gate_batch_stride = p->gate_batch_stride;
     P.resid = p->resid;
@@ -641,37 +680,8 @@ extern "C" int dit4sr_gemm_bf16_grouped(const dit4sr_gemm_params* probs, int cou
     g.p[i].tile_begin = 0x7fffffff;
     maps.a[i] = maps.a[0];
     maps.w[i] = maps.w[0];
+    maps.ws[i] = maps.ws[0];
     maps.c[i] = maps.c[0];
-  }
-  // tail splitting (see Group): only when every problem's N is a whole number of 256-column tiles
-  g.num_tiles = tiles;
-  g.split_begin = tiles;
-  g.split = 1;
-  {
-    static int enabled = -1;
-    if (enabled < 0) { const char* e = getenv("DIT4SR_GEMM_TAIL_SPLIT"); enabled = (e == nullptr || e[0] != '0') ? 1 : 0; }
-    const int sms = host::sm_count();
-    const int rem = tiles % sms;
-    bool whole = true;
-    for (int i = 0; i < count; ++i) whole = whole && (probs[i].N % BN == 0);
-    if (enabled && whole && tiles > sms && rem > 0) {
-      const int split = 4 * rem <= sms ? 4 : (2 * rem <= sms ? 2 : 1);
-      if (split > 1) {
-        g.split = split;
-        g.split_begin = tiles - rem;
-        g.num_tiles = g.split_begin + rem * split;
-        for (int i = 0; i < count; ++i) {
-          const dit4sr_gemm_params* p = &probs[i];
-          uint64_t dims[2] = {(uint64_t)p->K, (uint64_t)p->N};
-          uint64_t strides[1] = {(uint64_t)p->ldw * 2};
-          uint32_t box[2] = {BK, (uint32_t)(BN / split)};
-          if ((rc = host::make_tmap_bf16(&maps.ws[i], p->W, 2, dims, strides, box)) != 0) return rc;
-        }
-      }
-    }
-    if (g.split == 1)
-      for (int i = 0; i < count; ++i) maps.ws[i] = maps.w[i];
-    for (int i = count; i < MAX_PROBLEMS; ++i) maps.ws[i] = maps.ws[0];
   }
   switch (epilogue) {
     case DIT4SR_EPI_BIAS: return launch<DIT4SR_EPI_BIAS>(maps, g, stream);
@@ -690,4 +700,32 @@ extern "C" int dit4sr_gemm_bf16_grouped(const dit4sr_gemm_params* probs, int cou
 extern "C" int dit4sr_gemm_bf16(const dit4sr_gemm_params* p, void* stream) {
   DIT4SR_REQUIRE(p != nullptr, DIT4SR_E_BADARG, "gemm: null pointer argument");
   return dit4sr_gemm_bf16_grouped(p, 1, stream);
+}
+
+extern "C" int dit4sr_gemm_schedule(const dit4sr_gemm_params* probs, int count, int sm_count, int* items,
+                                    int max_items) {
+  using namespace gemm;
+  DIT4SR_REQUIRE(probs != nullptr && count >= 1 && count <= MAX_PROBLEMS, DIT4SR_E_BADARG,
+                 "gemm: group size must be 1..%d", MAX_PROBLEMS);
+  DIT4SR_REQUIRE(sm_count >= 1 && max_items >= 0 && (items != nullptr || max_items == 0), DIT4SR_E_BADARG,
+                 "gemm_schedule: bad sm_count / items");
+  for (int i = 0; i < count; ++i) {
+    const dit4sr_gemm_params* p = &probs[i];
+    DIT4SR_REQUIRE(p->batches > 0 && p->rows > 0 && p->N > 0 && p->K > 0, DIT4SR_E_BADARG,
+                   "gemm: non-positive size (batches %d rows %d N %d K %d)", p->batches, p->rows, p->N, p->K);
+    DIT4SR_REQUIRE(p->K % 8 == 0 && p->N % 32 == 0, DIT4SR_E_SHAPE, "gemm: need K %% 8 == 0 and N %% 32 == 0 (K %d N %d)",
+                   p->K, p->N);
+  }
+  Group g;
+  plan_tiles(probs, count, sm_count, tail_split_enabled(), g);
+  for (int item = 0; item < g.num_tiles && item < max_items; ++item) {
+    const TileCoord tc = decode_tile(g, item);
+    int* r = items + 5 * item;
+    r[0] = tc.pi;
+    r[1] = tc.b;
+    r[2] = tc.m_tile;
+    r[3] = tc.col0;
+    r[4] = tc.bn;
+  }
+  return g.num_tiles;
 }

@@ -174,6 +174,23 @@ def gemm_grouped(problems):
     _count()
 
 
+def gemm_schedule(shapes, sm_count=148):
+    """Host-only: the work items (problem, batch, row_tile, first_column, columns) one grouped launch walks on a GPU with
+    `sm_count` SMs, in schedule order.  shapes: list of (batches, rows, N, K).  Needs no device."""
+    import ctypes
+    n = len(shapes)
+    arr = (GemmParams * n)()
+    for p, (b, r, N, K) in zip(arr, shapes):
+        p.batches, p.rows, p.N, p.K = b, r, N, K
+    lib = _lib.load()
+    count = lib.dit4sr_gemm_schedule(arr, n, sm_count, None, 0)
+    if count < 0:
+        check(count, "dit4sr_gemm_schedule")
+    items = (ctypes.c_int * (5 * count))()
+    check(0 if lib.dit4sr_gemm_schedule(arr, n, sm_count, items, count) == count else -1, "dit4sr_gemm_schedule")
+    return [tuple(items[5 * i:5 * i + 5]) for i in range(count)]
+
+
 def attention(q, k, v, o, heads, seq_q=None, scale=None, lr_res=None, lr_rows=(0, 0)):
     """o = softmax(q k^T * scale) v over [B, S, heads*64] bf16 views (row stride may be 3*heads*64 for a fused buffer).
 

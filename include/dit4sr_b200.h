@@ -128,6 +128,12 @@ int dit4sr_gemm_bf16(const dit4sr_gemm_params* p, void* stream);
  * are per problem; tiles of problem i are scheduled before those of problem i+1. */
 #define DIT4SR_GEMM_MAX_GROUP 6
 int dit4sr_gemm_bf16_grouped(const dit4sr_gemm_params* problems, int count, void* stream);
+/* Host-only query (no device, no driver; the pointers inside `problems` are not dereferenced): the work-item schedule
+ * dit4sr_gemm_bf16_grouped walks on a GPU with `sm_count` SMs - 128-row x 256-column tiles in problem order, the last
+ * (tiles mod sm_count) of them cut into 2 or 4 column slices when that fills the final wave better.  Writes up to
+ * max_items records of five ints {problem, batch, row_tile, first_column, columns} in schedule order (work item i runs
+ * on CTA i mod min(sm_count, items)) and returns the number of work items, or a negative DIT4SR_E_* code. */
+int dit4sr_gemm_schedule(const dit4sr_gemm_params* problems, int count, int sm_count, int* items, int max_items);
 
 /* ---------------------------------------------------------------------------------------------------------------
  * Joint attention, flash-style on tcgen05:  O = softmax(Q K^T * scale) V, non-causal, no mask, head_dim 64.

@@ -37,6 +37,70 @@ def test_bad_arguments_are_rejected_without_a_gpu(lib):
     assert rc == -1
 
 
+def _check_schedule(shapes, sms):
+    """Every output tile of every problem is covered exactly once, in problem order, and only the final partial wave is
+    cut into column slices."""
+    from dit4sr_b200 import ops
+    items = ops.gemm_schedule(shapes, sm_count=sms)
+    cover = {}
+    for pi, b, mt, c0, bn in items:
+        B, R, N, K = shapes[pi]
+        assert 0 <= b < B and 0 <= mt < -(-R // 128) and 0 <= c0 < N and bn in (64, 128, 256)
+        cover.setdefault((pi, b, mt), []).append((c0, bn))
+    n_tiles = 0
+    for pi, (B, R, N, K) in enumerate(shapes):
+        for b in range(B):
+            for mt in range(-(-R // 128)):
+                segs = sorted(cover.pop((pi, b, mt)))
+                pos = 0
+                for c0, bn in segs:                  # contiguous, non-overlapping, covering [0, N)
+                    assert c0 == pos
+                    pos += bn
+                assert pos >= N and pos - N < 256
+                n_tiles += -(-N // 256)
+    assert not cover
+    assert [it[0] for it in items] == sorted(it[0] for it in items)      # problems scheduled in order
+    sliced = [i for i, it in enumerate(items) if it[4] != 256]
+    if sliced:
+        rem = n_tiles % sms
+        split = 256 // items[sliced[0]][4]
+        assert rem > 0 and n_tiles > sms and split * rem <= sms
+        assert sliced == list(range(n_tiles - rem, n_tiles - rem + split * rem))   # exactly the remainder tiles
+        assert all(N % 256 == 0 for _, _, N, _ in shapes)
+    else:
+        assert len(items) == n_tiles
+    return items
+
+
+def test_gemm_schedule_of_the_model_launches_without_a_gpu():
+    """The tile schedule (host arithmetic shared with the launch path) for the C2 launches: q|k|v group, out-projection
+    group (912 = 6 x 148 + 24 tiles -> the 24 remainder tiles become 96 slices of 64 columns), FF1/FF2 groups."""
+    B, N, T, D, F = 8, 1024, 333, 1536, 6144
+    _check_schedule([(B, N, 3 * D, D), (B, N, 2 * D, D), (B, T, 3 * D, D)], 148)
+    items = _check_schedule([(B, N, D, D), (B, N, D, D), (B, T, D, D)], 148)
+    assert sum(1 for it in items if it[4] == 64) == 96 and len(items) == 888 + 96
+    _check_schedule([(B, 2 * N, F, D), (B, T, F, D)], 148)
+    _check_schedule([(B, 2 * N, D, F), (B, T, D, F)], 148)
+    _check_schedule([(1, 7, 96, 64)], 148)             # a single ragged tile
+    _check_schedule([(3, 333, 1504, 128)], 4)          # N not a multiple of 256: never sliced
+
+
+def test_gemm_schedule_random_shapes():
+    import random
+    rng = random.Random(0)
+    for _ in range(200):
+        shapes = [(rng.randint(1, 4), rng.randint(1, 700), 32 * rng.randint(1, 40) if rng.random() < 0.5
+                   else 256 * rng.randint(1, 8), 8 * rng.randint(1, 64)) for _ in range(rng.randint(1, 6))]
+        _check_schedule(shapes, rng.choice([1, 4, 37, 148, 160]))
+
+
+def test_gemm_schedule_rejects_bad_groups(lib):
+    arr = (_lib.GemmParams * 7)()
+    assert lib.dit4sr_gemm_schedule(arr, 7, 148, None, 0) == -1          # more than DIT4SR_GEMM_MAX_GROUP problems
+    arr[0].batches, arr[0].rows, arr[0].N, arr[0].K = 1, 128, 48, 64     # N % 32 != 0
+    assert lib.dit4sr_gemm_schedule(arr, 1, 148, None, 0) < 0
+
+
 def test_state_dict_layout_matches_reference_manifest():
     for cfg in (O.tiny_config(), O.tiny_config(qk_norm=None, dual_attention_layers=())):
         m = dit4sr_b200.SD3Transformer2DModel(**vars(cfg))
