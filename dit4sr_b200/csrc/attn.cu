@@ -325,7 +325,12 @@ __device__ __forceinline__ void exp2_poly2(uint64_t x2, float& p0, float& p1) {
 // POLY8: of every 8 score pairs, POLY8 use the polynomial and 8-POLY8 use MUFU.EX2.
 // ISSUERS: 1 = warp 1 issues every MMA; 2 = warp 1 issues for the even slots (P V of tile 0 and the Q K^T that reuses
 // its buffer) and warp 3 for the odd ones, so the issuing warps' barrier-wait / commit latencies overlap.
-template <int POLY8, int ISSUERS>
+// XREG (DIT4SR_ATTN_XREG=1, experimental until it has passed the GPU suite): the helper warpgroup hands 128 registers per
+// thread back (setmaxnreg 40) and the two softmax warpgroups grow to 232, which removes the softmax loop's spills and
+// shortens its ptxas schedule (tools/sass_stalls.py: 1430 -> 1251 scheduled cycles per tile-step at 2/8 polynomial
+// exponentials, 1781 -> 1250 at 4/8).  setmaxnreg must sit inside the role branches: placed before them ptxas applies
+// the SMALLER budget to everything that follows.
+template <int POLY8, int ISSUERS, bool XREG = false>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 attn_fwd2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                  const __grid_constant__ CUtensorMap tmV, const Args args) {
@@ -381,6 +386,8 @@ attn_fwd2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
 
+  if (warp < 4) {
+  if constexpr (XREG) asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
   if (warp == 0) {
     if (lane == 0) {
       // ===================== TMA producer =====================
@@ -448,7 +455,9 @@ attn_fwd2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
       __syncwarp();
       if (n + NBUF < n_slots) issue_qk(n + NBUF);   // reuses this buffer; ordered behind the P V above in the tensor pipe
     }
-  } else if (warp >= 4) {
+  }
+  } else {
+    if constexpr (XREG) asm volatile("setmaxnreg.inc.sync.aligned.u32 232;");
     // ===================== softmax warpgroups =====================
     const int t = (warp - 4) >> 2;   // query tile of this warpgroup
     const int q = warp & 3;          // TMEM lane quarter
@@ -648,7 +657,7 @@ extern "C" int dit4sr_attn_fwd(const dit4sr_attn_params* p, void* stream_) {
   static bool configured = false;
   // development switches: DIT4SR_ATTN_VARIANT=1 selects the one-tile-per-CTA kernel; DIT4SR_ATTN_POLY=0|2|4 the number
   // of score pairs (of every 8) exponentiated on the FMA pipe instead of MUFU; DIT4SR_ATTN_ISSUERS=1 a single
-  // MMA-issuing warp
+  // MMA-issuing warp; DIT4SR_ATTN_XREG=1 the register-rebalanced instance (see attn_fwd2_kernel)
   static int variant = 2, poly8 = 2, issuers = 2;
   static KernelFn fn2 = nullptr;
   if (!configured) {
@@ -657,7 +666,11 @@ extern "C" int dit4sr_attn_fwd(const dit4sr_attn_params* p, void* stream_) {
     if (e != nullptr && e[0] == '1') variant = 1;
     if ((e = getenv("DIT4SR_ATTN_POLY")) != nullptr) poly8 = atoi(e);
     if ((e = getenv("DIT4SR_ATTN_ISSUERS")) != nullptr) issuers = atoi(e) == 1 ? 1 : 2;
-    if (issuers == 2)
+    const char* xr = getenv("DIT4SR_ATTN_XREG");
+    if (xr != nullptr && xr[0] == '1' && issuers == 2)
+      fn2 = poly8 == 0 ? v2::attn_fwd2_kernel<0, 2, true>
+                       : (poly8 == 4 ? v2::attn_fwd2_kernel<4, 2, true> : v2::attn_fwd2_kernel<2, 2, true>);
+    else if (issuers == 2)
       fn2 = poly8 == 0 ? v2::attn_fwd2_kernel<0, 2> : (poly8 == 4 ? v2::attn_fwd2_kernel<4, 2> : v2::attn_fwd2_kernel<2, 2>);
     else
       fn2 = poly8 == 0 ? v2::attn_fwd2_kernel<0, 1> : (poly8 == 4 ? v2::attn_fwd2_kernel<4, 1> : v2::attn_fwd2_kernel<2, 1>);
