@@ -330,7 +330,13 @@ __device__ __forceinline__ void exp2_poly2(uint64_t x2, float& p0, float& p1) {
 // shortens its ptxas schedule (tools/sass_stalls.py: 1430 -> 1251 scheduled cycles per tile-step at 2/8 polynomial
 // exponentials, 1781 -> 1250 at 4/8).  setmaxnreg must sit inside the role branches: placed before them ptxas applies
 // the SMALLER budget to everything that follows.
-template <int POLY8, int ISSUERS, bool XREG = false>
+// SAFE (DIT4SR_ATTN_XREG=2, experimental like XREG): the barrier scheme that tools/attn_protocol_check.py proves free of
+// premature passes and deadlocks for EVERY interleaving: s_full / p_full indexed by slot % 6 = (score buffer, query tile),
+// so that each waiter sees consecutive phases of its barrier, and P V of the previous step awaited in every step before
+// P is published.  The default scheme (slot % 3, o_done awaited only when a row's reference max grew) relies on timing:
+// the MMA side must not fall a whole tile-step behind the softmax warps and the two warpgroups must stay within about
+// one issuer iteration of each other - true on the GPU by a wide margin (equal work per warp), but not by construction.
+template <int POLY8, int ISSUERS, bool XREG = false, bool SAFE = false>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 attn_fwd2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                  const __grid_constant__ CUtensorMap tmV, const Args args) {
@@ -345,9 +351,10 @@ attn_fwd2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
   uint64_t* k_empty = k_full + KV_STAGES;
   uint64_t* v_full = k_empty + KV_STAGES;
   uint64_t* v_empty = v_full + KV_STAGES;
-  uint64_t* s_full = v_empty + KV_STAGES;   // [NBUF] scores of the slot using this buffer are in TMEM
-  uint64_t* p_full = s_full + NBUF;         // [NBUF] probabilities written back into the buffer
-  uint64_t* o_done = p_full + NBUF;         // [2]    P V of the tile's latest step has completed
+  constexpr int NSB = SAFE ? 2 * NBUF : NBUF;   // s_full / p_full barriers: one per buffer, or per (buffer, tile)
+  uint64_t* s_full = v_empty + KV_STAGES;   // [NSB] scores of the slot using this buffer are in TMEM
+  uint64_t* p_full = s_full + NSB;          // [NSB] probabilities written back into the buffer
+  uint64_t* o_done = p_full + NSB;          // [2]   P V of the tile's latest step has completed
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(o_done + 2);
 
   const int warp = threadIdx.x >> 5;
@@ -369,7 +376,7 @@ attn_fwd2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
       ptx::mbar_init(&v_full[i], 1);
       ptx::mbar_init(&v_empty[i], ISSUERS);
     }
-    for (int i = 0; i < NBUF; ++i) {
+    for (int i = 0; i < NSB; ++i) {
       ptx::mbar_init(&s_full[i], 1);
       ptx::mbar_init(&p_full[i], 4);
     }
@@ -428,7 +435,7 @@ attn_fwd2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
 #pragma unroll
         for (int k = 0; k < DH / 16; ++k)
           ptx::mma_ss(tmem_base + buf * 128, qd + 2 * k, kdesc + 2 * k, idesc_qk, k != 0);
-        ptx::tc_commit(&s_full[buf]);
+        ptx::tc_commit(&s_full[n % NSB]);
         if (ISSUERS == 2 || t == 1) ptx::tc_commit(&k_empty[st]);   // both tiles have consumed K_j
       }
       __syncwarp();
@@ -441,7 +448,7 @@ attn_fwd2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
     for (int n = (ISSUERS == 2 ? my : 0); n < n_slots; n += ISSUERS) {
       const int t = n & 1, j = n >> 1, st = j % KV_STAGES, buf = n % NBUF;
       ptx::mbar_wait(&v_full[st], (j / KV_STAGES) & 1);
-      ptx::mbar_wait(&p_full[buf], (n / NBUF) & 1);      // softmax wrote P into the buffer (and rescaled O if needed)
+      ptx::mbar_wait(&p_full[n % NSB], (n / NSB) & 1);   // softmax wrote P into the buffer (and rescaled O if needed)
       ptx::tc_fence_after();
       const uint64_t vdesc = vdesc_base + (uint64_t)(st * (TILE_BYTES >> 4));
       if (ptx::elect_one()) {
@@ -470,7 +477,7 @@ attn_fwd2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
       const int n = 2 * j + t;
       const int buf = n % NBUF;
       const uint32_t tS = tmem_base + buf * 128 + lane_off;
-      ptx::mbar_wait(&s_full[buf], (n / NBUF) & 1);
+      ptx::mbar_wait(&s_full[n % NSB], (n / NSB) & 1);
       ptx::tc_fence_after();
       uint32_t v[128];
 #pragma unroll
@@ -524,10 +531,18 @@ attn_fwd2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
       ptx::unpack2(ptx::add2(rs2[0], rs2[1]), ra, rb);
       ptx::unpack2(ptx::add2(rs2[2], rs2[3]), rc, rd);
       const float rsum = (ra + rb) + (rc + rd);
+      if constexpr (SAFE) {   // every step observes P V of the previous one: consecutive o_done phases, lead <= one step
+        if (j > 0) {
+          ptx::mbar_wait(&o_done[t], (j - 1) & 1);
+          ptx::tc_fence_after();
+        }
+      }
       // O_t may only be touched between P V(j-1) completing and P V(j) being issued (it is issued after our arrive)
       if (j > 0 && __any_sync(0xffffffffu, grow)) {
-        ptx::mbar_wait(&o_done[t], (j - 1) & 1);
-        ptx::tc_fence_after();
+        if constexpr (!SAFE) {
+          ptx::mbar_wait(&o_done[t], (j - 1) & 1);
+          ptx::tc_fence_after();
+        }
 #pragma unroll 1
         for (int c = 0; c < DH / 32; ++c) {
           uint32_t o[32];
@@ -545,7 +560,7 @@ attn_fwd2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
       ptx::tmem_wait_st();
       ptx::tc_fence_before();
       __syncwarp();
-      if (lane == 0) ptx::mbar_arrive(&p_full[buf]);
+      if (lane == 0) ptx::mbar_arrive(&p_full[n % NSB]);
     };
     const bool ragged = (args.seq_kv % BKV) != 0;
     for (int j = 0; j + 1 < n_tiles; ++j) tile_step(j, std::false_type{});
@@ -667,7 +682,10 @@ extern "C" int dit4sr_attn_fwd(const dit4sr_attn_params* p, void* stream_) {
     if ((e = getenv("DIT4SR_ATTN_POLY")) != nullptr) poly8 = atoi(e);
     if ((e = getenv("DIT4SR_ATTN_ISSUERS")) != nullptr) issuers = atoi(e) == 1 ? 1 : 2;
     const char* xr = getenv("DIT4SR_ATTN_XREG");
-    if (xr != nullptr && xr[0] == '1' && issuers == 2)
+    if (xr != nullptr && xr[0] == '2' && issuers == 2)        // register-rebalanced + model-checked barrier scheme
+      fn2 = poly8 == 0 ? v2::attn_fwd2_kernel<0, 2, true, true>
+                       : (poly8 == 4 ? v2::attn_fwd2_kernel<4, 2, true, true> : v2::attn_fwd2_kernel<2, 2, true, true>);
+    else if (xr != nullptr && xr[0] == '1' && issuers == 2)
       fn2 = poly8 == 0 ? v2::attn_fwd2_kernel<0, 2, true>
                        : (poly8 == 4 ? v2::attn_fwd2_kernel<4, 2, true> : v2::attn_fwd2_kernel<2, 2, true>);
     else if (issuers == 2)
