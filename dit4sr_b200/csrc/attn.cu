@@ -32,6 +32,7 @@ struct Args {
   int lr_row_begin, lr_row_end;
   int seq_q, seq_kv, n_kv_tiles;
   float scale_log2;  // scale * log2(e)
+  float ref_log2;    // FIXEDREF instances: fixed softmax reference (upper bound of score * scale_log2), else unused
 };
 
 __global__ void __launch_bounds__(NUM_THREADS, 2)
@@ -336,7 +337,11 @@ __device__ __forceinline__ void exp2_poly2(uint64_t x2, float& p0, float& p1) {
 // P is published.  The default scheme (slot % 3, o_done awaited only when a row's reference max grew) relies on timing:
 // the MMA side must not fall a whole tile-step behind the softmax warps and the two warpgroups must stay within about
 // one issuer iteration of each other - true on the GPU by a wide margin (equal work per warp), but not by construction.
-template <int POLY8, int ISSUERS, bool XREG = false, bool SAFE = false>
+// FIXEDREF (DIT4SR_ATTN_XREG=3 with DIT4SR_ATTN_SCORE_BOUND=<bound>, experimental): with QK-RMSNorm every score is bounded by
+// |q| |k| scale <= (8 max|w_q|) (8 max|w_k|) / 8, so a FIXED reference replaces the online row max: p = 2^(s*sl2 - ref)
+// never overflows, softmax is invariant to the reference, bf16 / fp32 keep their relative precision at any magnitude,
+// and for ref <= ~40 (log2 units) nothing that matters underflows.  No row max, no vote, no O rescale.
+template <int POLY8, int ISSUERS, bool XREG = false, bool SAFE = false, bool FIXEDREF = false>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 attn_fwd2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                  const __grid_constant__ CUtensorMap tmV, const Args args) {
@@ -489,6 +494,9 @@ attn_fwd2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
         for (int i = 0; i < 128; ++i)
           if (i >= kv_left) v[i] = 0xff800000u;   // -inf
       }
+      float alpha = 1.0f;
+      bool grow = false;
+      if constexpr (!FIXEDREF) {
       // 8 independent max chains (a single chain of 128 dependent FMNMX is latency-bound), then a small tree
       float mxa[8];
 #pragma unroll
@@ -500,13 +508,13 @@ attn_fwd2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
       const float mx = fmaxf(fmaxf(fmaxf(mxa[0], mxa[1]), fmaxf(mxa[2], mxa[3])),
                              fmaxf(fmaxf(mxa[4], mxa[5]), fmaxf(mxa[6], mxa[7])));
       // lazy rescale: keep the old reference max unless the new one exceeds it by more than the threshold
-      float alpha = 1.0f;
-      const bool grow = (mx - m_run) * sl2 > RESCALE_THRESHOLD;   // true on the first tile (m_run = -inf)
+      grow = (mx - m_run) * sl2 > RESCALE_THRESHOLD;   // true on the first tile (m_run = -inf)
       if (grow) {
         alpha = ptx::ex2((m_run - mx) * sl2);
         m_run = mx;
       }
-      const float neg_m = -m_run * sl2;
+      }
+      const float neg_m = FIXEDREF ? -args.ref_log2 : -m_run * sl2;
       uint64_t rs2[4];                         // independent packed partial row sums
 #pragma unroll
       for (int a = 0; a < 4; ++a) rs2[a] = ptx::pack2(0.f, 0.f);
@@ -538,7 +546,7 @@ attn_fwd2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
         }
       }
       // O_t may only be touched between P V(j-1) completing and P V(j) being issued (it is issued after our arrive)
-      if (j > 0 && __any_sync(0xffffffffu, grow)) {
+      if (!FIXEDREF && j > 0 && __any_sync(0xffffffffu, grow)) {
         if constexpr (!SAFE) {
           ptx::mbar_wait(&o_done[t], (j - 1) & 1);
           ptx::tc_fence_after();
@@ -667,6 +675,7 @@ extern "C" int dit4sr_attn_fwd(const dit4sr_attn_params* p, void* stream_) {
   a.seq_kv = p->seq_kv;
   a.n_kv_tiles = (p->seq_kv + BKV - 1) / BKV;
   a.scale_log2 = p->scale * 1.4426950408889634f;
+  a.ref_log2 = 0.f;
 
   using KernelFn = void (*)(const CUtensorMap, const CUtensorMap, const CUtensorMap, const Args);
   static bool configured = false;
@@ -674,6 +683,7 @@ extern "C" int dit4sr_attn_fwd(const dit4sr_attn_params* p, void* stream_) {
   // of score pairs (of every 8) exponentiated on the FMA pipe instead of MUFU; DIT4SR_ATTN_ISSUERS=1 a single
   // MMA-issuing warp; DIT4SR_ATTN_XREG=1 the register-rebalanced instance (see attn_fwd2_kernel)
   static int variant = 2, poly8 = 2, issuers = 2;
+  static float fixed_ref = 0.f;
   static KernelFn fn2 = nullptr;
   if (!configured) {
     DIT4SR_CUDA(cudaFuncSetAttribute(attn_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
@@ -682,7 +692,11 @@ extern "C" int dit4sr_attn_fwd(const dit4sr_attn_params* p, void* stream_) {
     if ((e = getenv("DIT4SR_ATTN_POLY")) != nullptr) poly8 = atoi(e);
     if ((e = getenv("DIT4SR_ATTN_ISSUERS")) != nullptr) issuers = atoi(e) == 1 ? 1 : 2;
     const char* xr = getenv("DIT4SR_ATTN_XREG");
-    if (xr != nullptr && xr[0] == '2' && issuers == 2)        // register-rebalanced + model-checked barrier scheme
+    const char* sb = getenv("DIT4SR_ATTN_SCORE_BOUND");
+    if (xr != nullptr && xr[0] == '3' && issuers == 2 && sb != nullptr && atof(sb) > 0.0) {   // + fixed softmax reference
+      fixed_ref = (float)atof(sb);
+      fn2 = v2::attn_fwd2_kernel<2, 2, true, true, true>;
+    } else if (xr != nullptr && xr[0] == '2' && issuers == 2)   // register-rebalanced + model-checked barrier scheme
       fn2 = poly8 == 0 ? v2::attn_fwd2_kernel<0, 2, true, true>
                        : (poly8 == 4 ? v2::attn_fwd2_kernel<4, 2, true, true> : v2::attn_fwd2_kernel<2, 2, true, true>);
     else if (xr != nullptr && xr[0] == '1' && issuers == 2)
@@ -695,6 +709,7 @@ extern "C" int dit4sr_attn_fwd(const dit4sr_attn_params* p, void* stream_) {
     DIT4SR_CUDA(cudaFuncSetAttribute(fn2, cudaFuncAttributeMaxDynamicSharedMemorySize, v2::SMEM_BYTES));
     configured = true;
   }
+  a.ref_log2 = fixed_ref;
   if (variant == 1) {
     dim3 grid((p->seq_q + BQ - 1) / BQ, p->heads, p->batches);
     attn_fwd_kernel<<<grid, NUM_THREADS, SMEM_BYTES, stream>>>(tmQ, tmK, tmV, a);
