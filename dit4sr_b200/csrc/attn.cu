@@ -301,15 +301,18 @@ constexpr float RESCALE_THRESHOLD = 8.0f;   // in log2 units: skip the O rescale
 // 2^x for x <= ~8 on the FMA pipe (Cody-Waite range reduction + degree-3 minimax polynomial, max rel. error 7.5e-5,
 // far below the bf16 rounding of P): takes exponentials off the MUFU unit, which bounds head_dim-64 attention.
 // Two values per instruction with the packed fp32x2 forms (FFMA2 / FADD2).
+template <bool CLAMP = true>
 __device__ __forceinline__ void exp2_poly2(uint64_t x2, float& p0, float& p1) {
   const uint64_t magic = ptx::pack2(12582912.0f, 12582912.0f);        // 1.5 * 2^23: x + magic rounds x to an integer
   const uint64_t nmagic = ptx::pack2(-12582912.0f, -12582912.0f);
   const uint64_t neg1 = ptx::pack2(-1.0f, -1.0f);
   const uint64_t c3 = ptx::pack2(0.05517165f, 0.05517165f), c2 = ptx::pack2(0.24261113f, 0.24261113f);
   const uint64_t c1 = ptx::pack2(0.69326097f, 0.69326097f), c0 = ptx::pack2(0.99992806f, 0.99992806f);
-  float xa, xb;
-  ptx::unpack2(x2, xa, xb);
-  x2 = ptx::pack2(fmaxf(xa, -125.0f), fmaxf(xb, -125.0f));            // keep 2^n representable
+  if constexpr (CLAMP) {   // (bounded scores, FIXEDREF: x >= -2 ref > -125 by construction)
+    float xa, xb;
+    ptx::unpack2(x2, xa, xb);
+    x2 = ptx::pack2(fmaxf(xa, -125.0f), fmaxf(xb, -125.0f));          // keep 2^n representable
+  }
   const uint64_t t2 = ptx::add2(x2, magic);                            // integer part lives in the low mantissa bits
   const uint64_t n2 = ptx::add2(t2, nmagic);
   const uint64_t f2 = ptx::fma2(n2, neg1, x2);                         // f in [-0.5, 0.5]
@@ -341,7 +344,10 @@ __device__ __forceinline__ void exp2_poly2(uint64_t x2, float& p0, float& p1) {
 // |q| |k| scale <= (8 max|w_q|) (8 max|w_k|) / 8, so a FIXED reference replaces the online row max: p = 2^(s*sl2 - ref)
 // never overflows, softmax is invariant to the reference, bf16 / fp32 keep their relative precision at any magnitude,
 // and for ref <= ~40 (log2 units) nothing that matters underflows.  No row max, no vote, no O rescale.
-template <int POLY8, int ISSUERS, bool XREG = false, bool SAFE = false, bool FIXEDREF = false>
+// FIXEDREF = 2 (DIT4SR_ATTN_XREG=4, the engine's DIT4SR_ATTN_PRESCALE path): for bounds <= ~60 no reference is needed at
+// all - 2^60 is far inside fp32 / bf16 range - and with scale * log2(e) folded into the q RMSNorm weights by the host the
+// scores arrive ready for ex2: p = 2^s, no multiply, no subtract (the MUFU path is MUFU, MUFU, FADD2, F2FP per pair).
+template <int POLY8, int ISSUERS, bool XREG = false, bool SAFE = false, int FIXEDREF = 0>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 attn_fwd2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                  const __grid_constant__ CUtensorMap tmV, const Args args) {
@@ -514,7 +520,7 @@ attn_fwd2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
         m_run = mx;
       }
       }
-      const float neg_m = FIXEDREF ? -args.ref_log2 : -m_run * sl2;
+      const float neg_m = FIXEDREF ? -args.ref_log2 : -m_run * sl2;   // (unused when FIXEDREF == 2)
       uint64_t rs2[4];                         // independent packed partial row sums
 #pragma unroll
       for (int a = 0; a < 4; ++a) rs2[a] = ptx::pack2(0.f, 0.f);
@@ -522,10 +528,11 @@ attn_fwd2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
       uint32_t pk[64];
 #pragma unroll
       for (int i = 0; i < 64; ++i) {
-        const uint64_t x2 = ptx::fma2(ptx::pack2(__uint_as_float(v[2 * i]), __uint_as_float(v[2 * i + 1])), sl2_2, negm_2);
+        uint64_t x2 = ptx::pack2(__uint_as_float(v[2 * i]), __uint_as_float(v[2 * i + 1]));
+        if constexpr (FIXEDREF != 2) x2 = ptx::fma2(x2, sl2_2, negm_2);
         float p0, p1;
         if (!decltype(masked)::value && (i & 7) < POLY8) {
-          exp2_poly2(x2, p0, p1);
+          exp2_poly2<FIXEDREF == 0>(x2, p0, p1);
         } else {
           float xa, xb;
           ptx::unpack2(x2, xa, xb);
@@ -693,9 +700,12 @@ extern "C" int dit4sr_attn_fwd(const dit4sr_attn_params* p, void* stream_) {
     if ((e = getenv("DIT4SR_ATTN_ISSUERS")) != nullptr) issuers = atoi(e) == 1 ? 1 : 2;
     const char* xr = getenv("DIT4SR_ATTN_XREG");
     const char* sb = getenv("DIT4SR_ATTN_SCORE_BOUND");
-    if (xr != nullptr && xr[0] == '3' && issuers == 2 && sb != nullptr && atof(sb) > 0.0) {   // + fixed softmax reference
+    if (xr != nullptr && xr[0] == '4' && issuers == 2) {   // + pre-scaled bounded scores: p = 2^s (host folds the scale)
+      fn2 = poly8 == 0 ? v2::attn_fwd2_kernel<0, 2, true, true, 2>
+                       : (poly8 == 4 ? v2::attn_fwd2_kernel<4, 2, true, true, 2> : v2::attn_fwd2_kernel<2, 2, true, true, 2>);
+    } else if (xr != nullptr && xr[0] == '3' && issuers == 2 && sb != nullptr && atof(sb) > 0.0) {   // + fixed reference
       fixed_ref = (float)atof(sb);
-      fn2 = v2::attn_fwd2_kernel<2, 2, true, true, true>;
+      fn2 = v2::attn_fwd2_kernel<2, 2, true, true, 1>;
     } else if (xr != nullptr && xr[0] == '2' && issuers == 2)   // register-rebalanced + model-checked barrier scheme
       fn2 = poly8 == 0 ? v2::attn_fwd2_kernel<0, 2, true, true>
                        : (poly8 == 4 ? v2::attn_fwd2_kernel<4, 2, true, true> : v2::attn_fwd2_kernel<2, 2, true, true>);

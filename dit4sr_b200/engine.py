@@ -12,6 +12,8 @@ Dataflow of one step (reference: transformer_sd3.py:326-391 and attention.py:280
 
 Precision: tensor-core operands bf16, accumulation / residual streams (x, ctx) / LN+RMS statistics / softmax fp32.
 """
+import math
+import os
 from typing import Dict, Optional, Tuple
 
 import torch
@@ -66,6 +68,32 @@ class _Folded:
         self.b = torch.cat(bs, 0).contiguous()
 
 
+LOG2E = 1.4426950408889634
+PRESCALE_MAX_BOUND = 60.0   # log2 units: 2^60 * 8525 keys * |v| is far inside fp32 (and bf16 P) range
+
+
+def prescaled_q_norm_weights(wq, wk, waq=None, wak=None):
+    """Experimental (DIT4SR_ATTN_XREG=4): fold the softmax scale and log2(e) into the q RMSNorm weights, so that the joint
+    attention kernel can take p = 2^score without a multiply, a reference max or a rescale.
+
+    Valid because QK-RMSNorm bounds every score: each normed row has norm <= sqrt(dh) * max|w| (attention.py:484-489,
+    502-505; the twice-normed LR keys included), hence score * scale * log2(e) <= dh * max|w_q| * max|w_k| * scale * log2(e).
+    Returns (wq', waq', bound in log2 units); raises if the bound is too large to drop the reference."""
+    dh = wq.numel()
+    f = LOG2E / math.sqrt(dh)
+    qmax = max(float(wq.abs().max()), float(waq.abs().max()) if waq is not None else 0.0)
+    kmax = max(float(wk.abs().max()), float(wak.abs().max()) if wak is not None else 0.0)
+    bound = dh * qmax * kmax * f
+    if not bound <= PRESCALE_MAX_BOUND:
+        raise ValueError(f"DIT4SR_ATTN_XREG=4: score bound {bound:.1f} (log2 units) exceeds {PRESCALE_MAX_BOUND}: this "
+                         "checkpoint needs the online-max softmax")
+    return wq * f, (waq * f if waq is not None else None), bound
+
+
+def _prescale_requested():
+    return os.environ.get("DIT4SR_ATTN_XREG", "") == "4"
+
+
 class _AttnPack:
     def __init__(self, attn, has_text: bool, fold: bool, precise: bool = False):
         from functools import partial
@@ -98,6 +126,13 @@ class _AttnPack:
             if self.qk_norm:
                 self.waq, self.wak = _f32(attn.norm_added_q.weight), _f32(attn.norm_added_k.weight)
             self.add_out = _Lin(attn.to_add_out) if hasattr(attn, "to_add_out") else None
+        if _prescale_requested() and not precise:
+            if not self.qk_norm:
+                raise ValueError("DIT4SR_ATTN_XREG=4 needs qk_norm='rms_norm' (bounded scores)")
+            self.wq, waq, self.score_bound = prescaled_q_norm_weights(
+                self.wq, self.wk, getattr(self, "waq", None), getattr(self, "wak", None))
+            if waq is not None:
+                self.waq = waq
 
 
 class _BlockPack:

@@ -80,3 +80,27 @@ def test_peaked_rows_keep_their_accuracy():
     v = torch.randn(256, 64, generator=g).bfloat16()
     bound = 8 * 8 / 8 * LOG2E
     assert rel(emulate(q, k, v, bound), exact(q, k, v)) < 3e-3
+
+
+def test_prescaled_q_norm_weights_fold_scale_and_bound_the_scores():
+    """engine.prescaled_q_norm_weights (DIT4SR_ATTN_XREG=4): (x_q * w_q') . k == log2(e)/sqrt(64) * (x_q * w_q) . k, the
+    returned bound dominates every score of RMS-normed rows (image and text streams), and large weights are refused."""
+    import pytest
+    from dit4sr_b200.engine import prescaled_q_norm_weights
+    g = torch.Generator().manual_seed(0)
+    wq, wk = 1 + 0.2 * torch.randn(64, generator=g), 1 + 0.2 * torch.randn(64, generator=g)
+    waq, wak = 1 + 0.2 * torch.randn(64, generator=g), 1 + 0.2 * torch.randn(64, generator=g)
+    wq2, waq2, bound = prescaled_q_norm_weights(wq, wk, waq, wak)
+    xq, xk = torch.randn(300, 64, generator=g) * 5, torch.randn(300, 64, generator=g) * 0.3
+    one = torch.ones(64)
+    for a, a2 in ((wq, wq2), (waq, waq2)):
+        for b in (wk, wak):
+            k = rms_norm(xk, b)
+            kk = rms_norm(k, b)                                    # the twice-normed LR keys (quirk Q1)
+            for keys in (k, kk):
+                s_ref = (rms_norm(xq, a) @ keys.T) * (0.125 * LOG2E)
+                s_new = rms_norm(xq, one) * a2 @ keys.T
+                assert torch.allclose(s_ref, s_new, rtol=1e-5, atol=1e-5)
+                assert s_new.abs().max().item() <= bound
+    with pytest.raises(ValueError):
+        prescaled_q_norm_weights(wq * 3, wk * 3)
