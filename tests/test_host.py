@@ -145,3 +145,18 @@ def test_sampler_sigmas_match_oracle_and_logged_timesteps():
     s = flow_match_sigmas(40)
     assert np.array_equal(s, O.flow_match_sigmas(40))
     assert np.all(np.abs(1000 * s[:-1] - np.array(meta["logged_timesteps_40"])) <= 0.005 + 1e-6)
+
+
+def test_bench_attention_roofline_entry():
+    """bench.py's `roofline` entry (joint attention = the largest share of the step): algorithmic FLOPs / measured time."""
+    import sys
+    sys.path.insert(0, ROOT)
+    import bench
+    peaks = dict(tf_burst=1658.4, tf_sustained=1390.8, hbm=6540.0, source="test")
+    gemm_f, attn_f = bench.flops_per_image_step(1024, 333)
+    r = bench.attention_roofline([0.5] * 37 + [0.4] * 37, attn_f * 8, 37, peaks)
+    assert r["bound"] == "tensor" and r["unit"] == "TFLOP/s" and r["launches_timed"] == 74
+    assert abs(r["achieved"] - attn_f * 8 / 37 / 0.45e-3 / 1e12) < 0.1
+    assert abs(r["frac"] - r["achieved"] / 1390.8) < 1e-3 and r["traffic"] is None or r["traffic"] > 1e8
+    assert bench.attention_roofline([], attn_f, 37, peaks) is None
+    assert abs((gemm_f + attn_f) / 1e12 - 4.724) < 0.01          # SURVEY 8d: folded-chain total at 512px
