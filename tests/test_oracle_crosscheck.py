@@ -1,0 +1,90 @@
+"""Cross-checks of the diffusers-0.31.0 semantics the oracle's shim restates (diffusers itself is not
+installable here, so that layer of the oracle is otherwise unpinned) against INDEPENDENT implementations of the same
+building blocks that ship in this image's `transformers` package.  Skipped when those modules are not importable."""
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.join(ROOT, "oracle", "diffusers_shim"))
+
+from diffusers.models import embeddings as shim_emb        # noqa: E402  (the shim, not a real diffusers)
+from diffusers.models import normalization as shim_norm    # noqa: E402
+
+
+def _omni():
+    return pytest.importorskip("transformers.models.qwen2_5_omni.modeling_qwen2_5_omni")
+
+
+def test_adalayernorm_zero_matches_independent_implementation():
+    """AdaLayerNormZero (attention.py:208-222 uses it for norm1 / norm1_context): Linear(dim, 6 dim) on silu(emb), chunk
+    order shift/scale/gate/shift_mlp/scale_mlp/gate_mlp, LayerNorm(eps 1e-6, no affine) * (1 + scale) + shift."""
+    m = _omni()
+    torch.manual_seed(0)
+    dim = 96
+    ours, theirs = shim_norm.AdaLayerNormZero(dim), m.Qwen2_5_OmniAdaLayerNormZero(dim)
+    theirs.linear.load_state_dict(ours.linear.state_dict())
+    x, emb = torch.randn(3, 17, dim), torch.randn(3, dim)
+    a, b = ours(x, emb=emb), theirs(x, emb=emb)
+    assert len(a) == len(b) == 5
+    for u, v in zip(a, b):
+        assert torch.equal(u, v)
+
+
+def test_adalayernorm_continuous_matches_independent_implementation():
+    """AdaLayerNormContinuous as norm_out / the last block's norm1_context build it (transformer_sd3.py:116,
+    attention.py:214: elementwise_affine=False, eps=1e-6): scale, shift = chunk(2) - in THAT order."""
+    m = _omni()
+    torch.manual_seed(1)
+    dim = 64
+    ours = shim_norm.AdaLayerNormContinuous(dim, dim, elementwise_affine=False, eps=1e-6)
+    theirs = m.Qwen2_5_OmniAdaLayerNormZero_Final(dim)
+    theirs.linear.load_state_dict(ours.linear.state_dict())
+    x, emb = torch.randn(2, 9, dim), torch.randn(2, dim)
+    assert torch.equal(ours(x, emb), theirs(x, emb))
+
+
+def test_rms_norm_matches_llama_rms_norm():
+    """diffusers RMSNorm(64, eps=1e-6) on q / k heads (attention.py:484-489,502-505): variance in fp32, x * rsqrt(var + eps)
+    then * weight - the Llama formulation."""
+    llama = pytest.importorskip("transformers.models.llama.modeling_llama")
+    torch.manual_seed(2)
+    ours, theirs = shim_norm.RMSNorm(64, eps=1e-6), llama.LlamaRMSNorm(64, eps=1e-6)
+    w = 1 + 0.1 * torch.randn(64)
+    with torch.no_grad():
+        ours.weight.copy_(w)
+        theirs.weight.copy_(w)
+    x = torch.randn(2, 24, 50, 64) * 3
+    assert torch.allclose(ours(x), theirs(x), rtol=1e-6, atol=1e-6)
+    xb = x.bfloat16()
+    assert torch.allclose(ours.bfloat16()(xb).float(), theirs.bfloat16()(xb).float(), rtol=2e-2, atol=2e-2)
+
+
+def test_2d_sincos_pos_embed_matches_mae_when_unscaled():
+    """PatchEmbed's pos_embed buffer: with base_size == grid_size and interpolation_scale 1 diffusers' formula reduces to
+    the MAE one (w-first meshgrid, [emb_h | emb_w], [sin | cos] halves, omega = 1 / 10000^(k / (D/4)))."""
+    mae = pytest.importorskip("transformers.models.vit_mae.modeling_vit_mae")
+    for dim, g in ((64, 6), (1536, 12)):
+        ours = shim_emb.get_2d_sincos_pos_embed(dim, g, base_size=g, interpolation_scale=1.0)
+        theirs = mae.get_2d_sincos_pos_embed(dim, g, add_cls_token=False)
+        assert ours.shape == theirs.shape == (g * g, dim)
+        assert np.allclose(ours, theirs, rtol=0, atol=1e-12)
+
+
+def test_oracle_functions_agree_with_the_shim_modules():
+    """The functional oracle (oracle/dit4sr_oracle.py) and the shim modules are two restatements by construction pinned
+    to each other through the golden vectors; spot-check the two pieces above directly."""
+    from oracle import dit4sr_oracle as O
+    torch.manual_seed(3)
+    x = torch.randn(2, 5, 64)
+    w = 1 + 0.1 * torch.randn(64)
+    n = shim_norm.RMSNorm(64, eps=1e-6)
+    with torch.no_grad():
+        n.weight.copy_(w)
+    assert torch.allclose(O.rms_norm(x, w), n(x), rtol=1e-6, atol=1e-6)
+    pe = O.sincos_pos_embed_2d(64, 6, 6)
+    ref = torch.from_numpy(shim_emb.get_2d_sincos_pos_embed(64, 6, base_size=6)).float()
+    assert torch.allclose(pe.reshape(-1, 64).float(), ref, atol=1e-6)
