@@ -76,6 +76,14 @@ def flops_per_image_step(N, T, L=24, dual=13, D=1536, folded=True):
     return gemm, attn
 
 
+# The SD3.5-medium shape the reference loads (SURVEY.md 8d "Model config"); the product arm builds its model from this
+# dict - nothing under oracle/ is imported outside the cpu_baseline / reference legs.
+SD35_MEDIUM_CONFIG = dict(num_layers=24, num_attention_heads=24, attention_head_dim=64, caption_projection_dim=1536,
+                          joint_attention_dim=4096, pooled_projection_dim=2048, patch_size=2, in_channels=16,
+                          out_channels=16, sample_size=128, pos_embed_max_size=384, qk_norm="rms_norm",
+                          dual_attention_layers=tuple(range(13)))
+
+
 def measured_peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -159,11 +167,10 @@ def build_model_gpu(device, seed=0, ocr=False):
     """SD3.5-medium-shaped model with EVERY parameter random (SURVEY 8d scales), created directly on the GPU."""
     import torch
     import dit4sr_b200
-    from oracle.dit4sr_oracle import sd35_medium_config
-    cfg = sd35_medium_config()
+    cfg = dict(SD35_MEDIUM_CONFIG)
     cls = dit4sr_b200.SD3Transformer2DModel_OCRBranch_OCR2HQ2OCR if ocr else dit4sr_b200.SD3Transformer2DModel
     with torch.device(device):
-        m = cls(**vars(cfg))
+        m = cls(**cfg)
     g = torch.Generator(device=device).manual_seed(seed)
     with torch.no_grad():
         for name, p in m.named_parameters():

@@ -160,3 +160,18 @@ def test_bench_attention_roofline_entry():
     assert abs(r["frac"] - r["achieved"] / 1390.8) < 1e-3 and r["traffic"] is None or r["traffic"] > 1e8
     assert bench.attention_roofline([], attn_f, 37, peaks) is None
     assert abs((gemm_f + attn_f) / 1e12 - 4.724) < 0.01          # folded-chain total at 512px
+
+
+def test_bench_product_arm_config_matches_survey_and_avoids_the_oracle():
+    """bench.py builds the product-arm model from its own dict (nothing under oracle/ outside the CPU legs); that dict,
+    completed with the drop-in constructor's defaults, is the oracle's SD3.5-medium config."""
+    import inspect
+    import sys
+    sys.path.insert(0, ROOT)
+    import bench
+    d = {k: v.default for k, v in inspect.signature(dit4sr_b200.SD3Transformer2DModel.__init__).parameters.items()
+         if k != "self"}
+    d.update(bench.SD35_MEDIUM_CONFIG)
+    assert d == vars(O.sd35_medium_config())
+    src = inspect.getsource(bench.run_ours) + inspect.getsource(bench.build_model_gpu)
+    assert "oracle" not in src
