@@ -175,3 +175,14 @@ def test_bench_product_arm_config_matches_survey_and_avoids_the_oracle():
     assert d == vars(O.sd35_medium_config())
     src = inspect.getsource(bench.run_ours) + inspect.getsource(bench.build_model_gpu)
     assert "oracle" not in src
+
+
+def test_every_entry_point_rejects_null_arguments_with_a_message(lib):
+    """Error behaviour of the C ABI: no crash, DIT4SR_E_BADARG (-1) and a message naming the entry point, without a GPU."""
+    for name, (_, args) in _lib.SYMBOLS.items():
+        if name in ("dit4sr_abi_version", "dit4sr_last_error", "dit4sr_check_device"):
+            continue
+        vals = [0 if a in (ctypes.c_int, ctypes.c_int64) else (0.0 if a is ctypes.c_float else None) for a in args]
+        rc = getattr(lib, name)(*vals)
+        assert rc == -1, (name, rc)
+        assert len(lib.dit4sr_last_error()) > 0, name
