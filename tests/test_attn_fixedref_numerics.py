@@ -104,3 +104,23 @@ def test_prescaled_q_norm_weights_fold_scale_and_bound_the_scores():
                 assert s_new.abs().max().item() <= bound
     with pytest.raises(ValueError):
         prescaled_q_norm_weights(wq * 3, wk * 3)
+
+
+def test_prescaled_scores_without_any_reference_keep_the_accuracy():
+    """DIT4SR_ATTN_XREG=4: q arrives as bf16(q * log2(e)/sqrt(64)) (the scale is folded into the q RMSNorm weights before
+    the projection epilogue rounds to bf16) and the kernel takes p = 2^score with no reference.  Against the exact softmax
+    of the unscaled fp32 q the only new error is that one extra bf16 rounding of q."""
+    g = torch.Generator().manual_seed(5)
+    wq = 1 + 0.15 * torch.randn(64, generator=g)
+    wk = 1 + 0.15 * torch.randn(64, generator=g)
+    xq, xk = torch.randn(600, 64, generator=g) * 2, torch.randn(600, 64, generator=g)
+    v = torch.randn(600, 64, generator=g).bfloat16()
+    f = LOG2E / 8.0
+    q32, k = rms_norm(xq, wq), rms_norm(xk, wk).bfloat16()
+    q_scaled = (rms_norm(xq, torch.ones(64)) * (wq * f)).bfloat16()      # what the QKV_NORM epilogue would store
+    o = emulate(q_scaled, k, v, ref_log2=0.0, scale=1.0 / LOG2E)         # p = 2^(q' . k)
+    assert torch.isfinite(o).all()
+    ref = exact(q32, k, v)                                               # exact softmax of the unrounded q
+    base = emulate(q32.bfloat16(), k, v, ref_log2=20.0)                  # today's arithmetic (q rounded unscaled)
+    assert rel(o, ref) < 4e-3
+    assert rel(o, ref) < 1.5 * rel(base, ref) + 1e-3
