@@ -39,6 +39,20 @@ WORKLOADS = {
 }
 
 
+UNIT = "image-steps/s"   # one image advanced one denoise step; the SAME string in both arms (the driver divides them)
+
+
+def workload_config(workload, world):
+    """`config` of the JSON line: identical for the product arm and the reference arm of one workload / world size."""
+    side, B, T, mode, desc = WORKLOADS[workload]
+    per_gpu = B // world if mode == "dp_strong" else B
+    total = B if mode in ("dp_strong", "sp") else B * world
+    N = (side // 2) ** 2
+    return dict(workload=desc, per_gpu_batch=per_gpu, global_batch=total, latent=f"{side}x{side}", tokens_hq=N,
+                tokens_lr=N, tokens_text=T, parallelism=(f"ulysses{world}" if mode == "sp" else f"dp{world}"),
+                l2="working set (5.4 GB bf16 weights + activations) >> 126 MB L2; no explicit flush")
+
+
 def flops_per_image_step_ocr(N, T, L=24, dual=13, D=1536):
     """Same for the 3-stream OCR-branch model (LR and OCR projection chains folded, as the engine runs them):
     SURVEY.md 8d quotes 54.90 TFLOP at 1024px with folded chains."""
@@ -320,7 +334,7 @@ def run_ours(args):
     # ---- CPU baseline on rank 0 (bounded sample)
     cpu = None
     if rank == 0 and not args.no_cpu:
-        cpu = cpu_reference_sample(max_seconds=25.0)
+        cpu = cpu_reference_sample()
 
     if rank == 0:
         peaks = measured_peaks()
@@ -376,18 +390,16 @@ def run_ours(args):
         if roof_attn is None:
             roof_attn, roof = roof, None                                   # keep a `roofline` entry whatever happens
         line = dict(
-            metric="denoise_steps_per_sec", value=round(value, 3), unit="image-steps/s (one image advanced one denoise step)",
+            metric="denoise_steps_per_sec", value=round(value, 3), unit=UNIT,
             n_gpus=world, steps=args.steps, warmup=args.warmup, ms_per_step=round(ms / args.steps, 3),
             higher_is_better=True, scaling="weak" if mode == "dp_weak" else "strong", vs_baseline=None, dtype="bf16",
             data="synthetic",
-            config=dict(workload=desc, per_gpu_batch=B, global_batch=images_total, latent=f"{side}x{side}", tokens_hq=N,
-                        tokens_lr=N, tokens_text=T, parallelism=(f"ulysses{world}" if mode == "sp" else f"dp{world}"),
-                        l2="working set (5.4 GB bf16 weights + activations) >> 126 MB L2; no explicit flush"),
+            config=workload_config(args.workload, world),
             batch_steps_per_sec=round(args.steps * (world if mode == "dp_weak" else 1) / (ms / 1e3), 3),
             step_tflop=round(step_flops / 1e12, 3), lr_chains_folded=bool(eng.fold_lr_chains),
             step_tflops_achieved=round(step_flops * world / (ms / args.steps / 1e3) / 1e12, 1),   # whole job
             step_frac_of_sustained_peak=round(step_flops / (ms / args.steps / 1e3) / 1e12 / peaks["tf_sustained"], 4),
-            e2e=dict(value=round(img_steps / (e2e_ms / 1e3), 3), unit="image-steps/s", h2d_bytes_per_step=h2d,
+            e2e=dict(value=round(img_steps / (e2e_ms / 1e3), 3), unit=UNIT, h2d_bytes_per_step=h2d,
                      d2h_bytes_per_step=d2h, ms_per_step=round(e2e_ms / args.steps, 3),
                      api="dit4sr_b200.SD3Transformer2DModel.forward, pinned host inputs, velocity copied back"),
             gpu_launches=launches, clocks=clocks, roofline=roof_attn, roofline_gemm=roof, cpu_baseline=cpu,
@@ -398,7 +410,7 @@ def run_ours(args):
         dist.destroy_process_group()
 
 
-def cpu_reference_sample(max_seconds=25.0, steps=1, warmup=1):
+def cpu_reference_sample(max_seconds=40.0, steps=3, warmup=1):
     """Times the oracle (plain-PyTorch fp32 restatement of the reference) on the host cores: B=1, 512px, 24 blocks."""
     import torch
     from oracle import dit4sr_oracle as O
@@ -427,7 +439,7 @@ def cpu_reference_sample(max_seconds=25.0, steps=1, warmup=1):
     if not times:
         times = [dt]
     sec = sum(times) / len(times)
-    return dict(value=round(1.0 / sec, 4), unit="image-steps/s", cores=torch.get_num_threads(), kind="port",
+    return dict(value=round(1.0 / sec, 4), unit=UNIT, cores=torch.get_num_threads(), kind="port",
                 sample=f"oracle (plain PyTorch fp32 restatement of the reference), B=1 512px 24 blocks, "
                        f"{len(times)} timed step(s) after {warmup} warm-up, {sec:.2f} s/step, host cpu_count={ncpu}")
 
@@ -463,14 +475,16 @@ def run_reference(args):
                 break
     sec = sum(times) / len(times)
     val = round(1.0 / sec, 4)
-    unit = "image-steps/s (one image advanced one denoise step)"
+    unit = UNIT
+    world = int(os.environ.get("WORLD_SIZE", "1"))
     print(json.dumps(dict(
         impl="reference", metric="denoise_steps_per_sec", value=val, unit=unit, n_gpus=int(os.environ.get("WORLD_SIZE", "1")),
         steps=len(times), warmup=done_w, ms_per_step=round(sec * 1e3, 1), higher_is_better=True, scaling="weak",
         vs_baseline=None, dtype="f32", data="synthetic",
-        config=dict(workload=desc, sample="each step = ONE image of the batch (B=1) through all 24 blocks on the CPU"),
+        config=workload_config(args.workload, world),
         cpu_baseline=dict(value=val, unit=unit, cores=torch.get_num_threads(), kind="port",
-                          sample=f"oracle port, B=1 {side * 8}px, {len(times)} timed steps, wall budget {budget:.0f}s"),
+                          sample=f"oracle port; each step = ONE image of the batch (B=1) at {side * 8}px through all 24 blocks "
+                                 f"on the CPU, {len(times)} timed steps, wall budget {budget:.0f}s"),
         e2e=dict(value=val, unit=unit, h2d_bytes_per_step=0, d2h_bytes_per_step=0))))
 
 

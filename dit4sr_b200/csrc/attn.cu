@@ -1,12 +1,8 @@
 // Joint attention forward (non-causal, head_dim 64) on sm_100a tensor cores, flash style.
 //
-// One CTA = one 128-row query tile of one (batch, head); two CTAs are co-resident per SM so that one CTA's softmax
-// overlaps the other's MMAs.  Warp roles (192 threads): warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer,
-// warps 2..5 = softmax / correction / epilogue (thread = one query row = one TMEM lane; no cross-thread reductions).
-//
-// TMEM (256 columns): S = Q K^T fp32 [0,128) | O accumulator fp32 [128,192) | P = softmax numerators bf16 [192,256).
-// Per KV tile j:  MMA: S = Q K_j^T  ->  softmax: m,l update, P_j -> TMEM, lazily rescale O  ->  MMA: O += P_j V_j
-// (A operand from TMEM, V consumed MN-major straight from the TMA tile), with S_{j+1} issued before PV_j.
+// One CTA = TWO 128-row query tiles of one (batch, head) sharing every K/V tile; one CTA per SM (all 512 TMEM columns).
+// tcgen05.mma for Q K^T (operands from TMA-filled shared memory) and P V (P read straight from TMEM, V consumed MN-major
+// from its TMA tile), accumulators in TMEM, softmax by two warpgroups (thread = one query row = one TMEM lane).
 #include "host_util.h"
 #include "ptx.cuh"
 #include <stdlib.h>
@@ -14,15 +10,10 @@
 
 namespace attn {
 
-constexpr int BQ = 128;    // query rows per CTA
+constexpr int BQ = 128;    // query rows per tile
 constexpr int BKV = 128;   // kv rows per tile
 constexpr int DH = 64;
-constexpr int KV_STAGES = 2;
 constexpr int TILE_BYTES = 128 * DH * 2;  // 16 KB
-constexpr int NUM_THREADS = 192;
-constexpr int TMEM_COLS = 256;
-constexpr int COL_S = 0, COL_O = 128, COL_P = 192;
-constexpr int SMEM_BYTES = (1 + 2 * KV_STAGES) * TILE_BYTES + 1024 + 256;
 
 struct Args {
   __nv_bfloat16* o;
@@ -31,263 +22,37 @@ struct Args {
   int64_t lr_row_stride, lr_batch_stride;
   int lr_row_begin, lr_row_end;
   int seq_q, seq_kv, n_kv_tiles;
-  float scale_log2;  // scale * log2(e)
-  float ref_log2;    // FIXEDREF instances: fixed softmax reference (upper bound of score * scale_log2), else unused
+  float scale_log2;  // scale * log2(e)  (unused by the pre-scaled instances)
 };
 
-__global__ void __launch_bounds__(NUM_THREADS, 2)
-attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
-                const __grid_constant__ CUtensorMap tmV, const Args args) {
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint8_t* sQ = smem;
-  uint8_t* sK = smem + TILE_BYTES;
-  uint8_t* sV = smem + (1 + KV_STAGES) * TILE_BYTES;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (1 + 2 * KV_STAGES) * TILE_BYTES);
-  uint64_t* q_full = bars;
-  uint64_t* k_full = bars + 1;
-  uint64_t* k_empty = k_full + KV_STAGES;
-  uint64_t* v_full = k_empty + KV_STAGES;
-  uint64_t* v_empty = v_full + KV_STAGES;
-  uint64_t* s_full = v_empty + KV_STAGES;
-  uint64_t* p_full = s_full + 1;
-  uint64_t* o_done = p_full + 1;
-  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(o_done + 1);
 
-  const int warp = threadIdx.x >> 5;
-  const int lane = threadIdx.x & 31;
-  const int q_tile = blockIdx.x;
-  const int head = blockIdx.y;
-  const int b = blockIdx.z;
-  const int n_tiles = args.n_kv_tiles;
-
-  if (warp == 0 && lane == 0) {
-    ptx::prefetch_tmap(&tmQ);
-    ptx::prefetch_tmap(&tmK);
-    ptx::prefetch_tmap(&tmV);
-    ptx::mbar_init(q_full, 1);
-    for (int i = 0; i < KV_STAGES; ++i) {
-      ptx::mbar_init(&k_full[i], 1);
-      ptx::mbar_init(&k_empty[i], 1);
-      ptx::mbar_init(&v_full[i], 1);
-      ptx::mbar_init(&v_empty[i], 1);
-    }
-    ptx::mbar_init(s_full, 1);
-    ptx::mbar_init(p_full, 4);
-    ptx::mbar_init(o_done, 1);
-    ptx::fence_barrier_init();
-  }
-  if (warp == 1) {
-    ptx::tmem_alloc(tmem_ptr, TMEM_COLS);
-    ptx::tmem_relinquish();
-  }
-  ptx::tc_fence_before();
-  __syncthreads();
-  ptx::tc_fence_after();
-  const uint32_t tmem_base = *tmem_ptr;
-
-  if (warp == 0) {
-    if (lane == 0) {
-      // ===================== TMA producer =====================
-      ptx::mbar_expect_tx(q_full, TILE_BYTES);
-      ptx::tma_load_3d(sQ, &tmQ, q_full, head * DH, q_tile * BQ, b);
-      for (int j = 0; j < n_tiles; ++j) {
-        const int st = j % KV_STAGES;
-        const uint32_t ph = (j / KV_STAGES) & 1;
-        ptx::mbar_wait(&k_empty[st], ph ^ 1);
-        ptx::mbar_expect_tx(&k_full[st], TILE_BYTES);
-        ptx::tma_load_3d(sK + st * TILE_BYTES, &tmK, &k_full[st], head * DH, j * BKV, b);
-        ptx::mbar_wait(&v_empty[st], ph ^ 1);
-        ptx::mbar_expect_tx(&v_full[st], TILE_BYTES);
-        ptx::tma_load_3d(sV + st * TILE_BYTES, &tmV, &v_full[st], head * DH, j * BKV, b);
-      }
-    }
-  } else if (warp == 1) {
-    if (lane == 0) {
-      // ===================== MMA issuer =====================
-      constexpr uint32_t idesc_qk = ptx::make_idesc_bf16(BQ, BKV, 0, 0);  // A = Q (K-major), B = K tile (K-major)
-      constexpr uint32_t idesc_pv = ptx::make_idesc_bf16(BQ, DH, 0, 1);   // A = P (TMEM), B = V tile (MN-major)
-      const uint64_t qdesc = ptx::make_sdesc_sw128(ptx::smem_u32(sQ));
-      const uint32_t tS = tmem_base + COL_S, tO = tmem_base + COL_O, tP = tmem_base + COL_P;
-
-      auto issue_qk = [&](int j) {
-        const int st = j % KV_STAGES;
-        ptx::mbar_wait(&k_full[st], (j / KV_STAGES) & 1);
-        ptx::tc_fence_after();
-        const uint64_t kdesc = ptx::make_sdesc_sw128(ptx::smem_u32(sK + st * TILE_BYTES));
-#pragma unroll
-        for (int k = 0; k < DH / 16; ++k) ptx::mma_ss(tS, qdesc + 2 * k, kdesc + 2 * k, idesc_qk, k != 0);
-        ptx::tc_commit(&k_empty[st]);
-        ptx::tc_commit(s_full);
-      };
-
-      ptx::mbar_wait(q_full, 0);
-      issue_qk(0);
-      for (int j = 0; j < n_tiles; ++j) {
-        const int st = j % KV_STAGES;
-        ptx::mbar_wait(p_full, j & 1);  // P_j written, S consumed, O rescaled
-        ptx::tc_fence_after();
-        if (j + 1 < n_tiles) issue_qk(j + 1);
-        ptx::mbar_wait(&v_full[st], (j / KV_STAGES) & 1);
-        ptx::tc_fence_after();
-        const uint64_t vdesc = ptx::make_sdesc_sw128(ptx::smem_u32(sV + st * TILE_BYTES));
-#pragma unroll
-        for (int k = 0; k < BKV / 16; ++k) {
-          // A: 16 bf16 of K per step = 8 TMEM columns; B: 16 kv rows = 2048 bytes further down the V tile
-          ptx::mma_ts(tO, tP + 8 * k, vdesc + (uint64_t)(128 * k), idesc_pv, (j | k) != 0);
-        }
-        ptx::tc_commit(&v_empty[st]);
-        ptx::tc_commit(o_done);
-      }
-    }
-  } else {
-    // ===================== softmax / correction / epilogue =====================
-    const int q = warp & 3;
-    const uint32_t lane_off = (uint32_t)(q * 32) << 16;
-    const uint32_t tS = tmem_base + COL_S + lane_off, tO = tmem_base + COL_O + lane_off,
-                   tP = tmem_base + COL_P + lane_off;
-    const float sl2 = args.scale_log2;
-    float m_run = -INFINITY;  // running max of the raw scores
-    float l_run = 0.f;
-    for (int j = 0; j < n_tiles; ++j) {
-      ptx::mbar_wait(s_full, j & 1);
-      ptx::tc_fence_after();
-      const int kv_left = args.seq_kv - j * BKV;  // valid columns in this tile (>=1)
-      // pass 1: row max
-      float mx = m_run;
-#pragma unroll 1
-      for (int c = 0; c < BKV / 32; ++c) {
-        uint32_t v[32];
-        ptx::tmem_ld32(tS + c * 32, v);
-        ptx::tmem_wait_ld();
-        if (kv_left >= (c + 1) * 32) {
-#pragma unroll
-          for (int i = 0; i < 32; ++i) mx = fmaxf(mx, __uint_as_float(v[i]));
-        } else {
-#pragma unroll
-          for (int i = 0; i < 32; ++i)
-            if (c * 32 + i < kv_left) mx = fmaxf(mx, __uint_as_float(v[i]));
-        }
-      }
-      const float m_new = mx;
-      const float alpha = ptx::ex2((m_run - m_new) * sl2);  // 0 on the first tile (m_run = -inf)
-      const float neg_m = -m_new * sl2;
-      // P region and O are read by PV_{j-1}: wait for it before overwriting them
-      if (j > 0) {
-        ptx::mbar_wait(o_done, (j - 1) & 1);
-        ptx::tc_fence_after();
-      }
-      // pass 2: p = 2^(s*sl2 - m*sl2), row sum, bf16 pack -> TMEM
-      float rsum = 0.f;
-#pragma unroll 1
-      for (int c = 0; c < BKV / 32; ++c) {
-        uint32_t v[32];
-        ptx::tmem_ld32(tS + c * 32, v);
-        ptx::tmem_wait_ld();
-        float pv[32];
-        if (kv_left >= (c + 1) * 32) {
-#pragma unroll
-          for (int i = 0; i < 32; ++i) pv[i] = ptx::ex2(fmaf(__uint_as_float(v[i]), sl2, neg_m));
-        } else {
-#pragma unroll
-          for (int i = 0; i < 32; ++i)
-            pv[i] = (c * 32 + i < kv_left) ? ptx::ex2(fmaf(__uint_as_float(v[i]), sl2, neg_m)) : 0.f;
-        }
-        uint32_t pk[16];
-#pragma unroll
-        for (int i = 0; i < 16; ++i) {
-          rsum += pv[2 * i] + pv[2 * i + 1];
-          pk[i] = ptx::pack_bf16(pv[2 * i], pv[2 * i + 1]);
-        }
-        ptx::tmem_st16(tP + c * 16, pk);
-      }
-      // correction: O *= alpha (skipped warp-uniformly when no row's max moved)
-      if (j > 0 && __any_sync(0xffffffffu, alpha != 1.0f)) {
-#pragma unroll 1
-        for (int c = 0; c < DH / 32; ++c) {
-          uint32_t v[32];
-          ptx::tmem_ld32(tO + c * 32, v);
-          ptx::tmem_wait_ld();
-#pragma unroll
-          for (int i = 0; i < 32; ++i) v[i] = __float_as_uint(__uint_as_float(v[i]) * alpha);
-          ptx::tmem_st32(tO + c * 32, v);
-        }
-      }
-      l_run = l_run * alpha + rsum;
-      m_run = m_new;
-      ptx::tmem_wait_st();
-      ptx::tc_fence_before();
-      __syncwarp();
-      if (lane == 0) ptx::mbar_arrive(p_full);
-    }
-    // epilogue: O / l (+ LR residual) -> bf16 global
-    ptx::mbar_wait(o_done, (n_tiles - 1) & 1);
-    ptx::tc_fence_after();
-    const int row = q_tile * BQ + q * 32 + lane;
-    const float inv_l = 1.0f / l_run;
-    const bool row_ok = row < args.seq_q;
-    const bool add_lr = args.lr_res != nullptr && row >= args.lr_row_begin && row < args.lr_row_end;
-#pragma unroll 1
-    for (int c = 0; c < DH / 32; ++c) {
-      uint32_t v[32];
-      ptx::tmem_ld32(tO + c * 32, v);
-      ptx::tmem_wait_ld();
-      if (row_ok) {
-        float f[32];
-#pragma unroll
-        for (int i = 0; i < 32; ++i) f[i] = __uint_as_float(v[i]) * inv_l;
-        if (add_lr) {
-          const uint4* lr = reinterpret_cast<const uint4*>(args.lr_res + (int64_t)b * args.lr_batch_stride +
-                                                           (int64_t)row * args.lr_row_stride + head * DH + c * 32);
-#pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            const uint4 u = __ldg(lr + i);
-            const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&u);
-#pragma unroll
-            for (int t = 0; t < 4; ++t) {
-              const float2 ff = __bfloat1622float2(h2[t]);
-              f[8 * i + 2 * t] += ff.x;
-              f[8 * i + 2 * t + 1] += ff.y;
-            }
-          }
-        }
-        uint4* dst = reinterpret_cast<uint4*>(args.o + (int64_t)b * args.o_batch_stride +
-                                              (int64_t)row * args.o_row_stride + head * DH + c * 32);
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          uint4 u;
-          u.x = ptx::pack_bf16(f[8 * i + 0], f[8 * i + 1]);
-          u.y = ptx::pack_bf16(f[8 * i + 2], f[8 * i + 3]);
-          u.z = ptx::pack_bf16(f[8 * i + 4], f[8 * i + 5]);
-          u.w = ptx::pack_bf16(f[8 * i + 6], f[8 * i + 7]);
-          dst[i] = u;
-        }
-      }
-    }
-  }
-
-  __syncwarp();
-  ptx::tc_fence_before();
-  __syncthreads();
-  if (warp == 1) {
-    ptx::tc_fence_after();
-    ptx::tmem_dealloc(tmem_base, TMEM_COLS);
-  }
-}
-
-
-// =====================================================================================================================
-// v2: one CTA = TWO 128-row query tiles of one (batch, head) sharing every K/V tile (halves the L2->smem traffic), one
-// CTA per SM (all 512 TMEM columns).  Warps (384 threads): 0 = TMA producer, 1 = MMA issuer, 2 = TMEM allocator,
-// (3 = second MMA issuer,) 4..7 = softmax warpgroup of tile 0, 8..11 = softmax warpgroup of tile 1 (thread = one query row).
+// Warps (384 threads): 0 = TMA producer, 1 and 3 = MMA issuers (even / odd slots, so that their barrier-wait / commit
+// latencies overlap), 2 = TMEM allocator, 4..7 = softmax warpgroup of tile 0, 8..11 = softmax warpgroup of tile 1.
+// After the prologue the helper warpgroup hands registers back (setmaxnreg 40) and the softmax warpgroups grow to 232,
+// which keeps the 128-wide score row + its packed probabilities in registers without spills.  (setmaxnreg must sit
+// inside the role branches: placed before them ptxas applies the SMALLER budget to everything that follows.)
 //
 // The (tile, kv-step) pairs form a sequence of "slots" n = 2*j + t that rotate over THREE score buffers in TMEM
-// (buffer n % 3): Q_t K_j^T for slot n+3 is issued right after P V of slot n (same buffer, in-order tensor pipe), i.e.
-// one and a half tiles ahead of the softmax that consumes it, so the softmax warpgroups never wait for an MMA round
-// trip.  P (bf16) overwrites the first 64 columns of its own score buffer once the row is in registers.
+// (buffer n % 3): Q_t K_j^T for slot n+3 is issued right after P V of slot n (same buffer, in-order tensor pipe).
+// P (bf16) overwrites the first 64 columns of its own score buffer once the row is in registers.
 // TMEM: S/P buffers [0,128) [128,256) [256,384) | O0 [384,448) O1 [448,512).
-// Softmax: whole 128-wide score row in registers after one tcgen05.ld round trip, log2-domain online softmax
-// (ex2.approx), O rescaled lazily (only when the running max grew by more than 2^8).
+//
+// Barrier protocol (model-checked for every interleaving by tools/attn_protocol_check.py, tests/test_attn_protocol.py):
+// s_full / p_full are indexed by slot % 6 = (score buffer, query tile), so each waiter sees CONSECUTIVE phases of its
+// barrier, and every softmax step waits for P V of the tile's previous step (o_done) before it publishes P, which bounds
+// the lead of any warp to one step.  (Round 1 shipped slot % 3 barriers with a conditional o_done wait; that scheme
+// relied on the warps staying within one step of each other and produced 1 bad run in 20 under tools/stress_attn.py.)
+//
+// Softmax, two instances:
+//  * online (PRESCALED = false): log2-domain online softmax with the running row max as reference, O rescaled lazily
+//    (only when the max grew by more than 2^8); p = 2^(s * scale*log2e - m).
+//  * pre-scaled bounded scores (PRESCALED = true, dit4sr_attn_params.mode = DIT4SR_ATTN_PRESCALED): the caller has folded
+//    scale * log2(e) into q and guarantees q.k <= score_bound <= 60 for every pair (QK-RMSNorm bounds every score by
+//    64 max|w_q| max|w_k| scale log2e: the engine checks the checkpoint's weights).  2^60 is far inside fp32 / bf16
+//    range and softmax is invariant to the reference, so p = 2^s: no multiply, no row max, no vote, no O rescale
+//    (MUFU path per score pair: MUFU, MUFU, FADD2, F2FP).
+//  In both, POLY8 of every 8 score pairs take their exponential on the FMA pipe (exp2_poly2) instead of MUFU.EX2, which
+//  bounds head_dim-64 attention (16 results/clk/SM: 1024 cycles per 128x128 score tile against 526 for its MMAs).
 namespace v2 {
 
 constexpr int KV_STAGES = 4;
@@ -308,7 +73,7 @@ __device__ __forceinline__ void exp2_poly2(uint64_t x2, float& p0, float& p1) {
   const uint64_t neg1 = ptx::pack2(-1.0f, -1.0f);
   const uint64_t c3 = ptx::pack2(0.05517165f, 0.05517165f), c2 = ptx::pack2(0.24261113f, 0.24261113f);
   const uint64_t c1 = ptx::pack2(0.69326097f, 0.69326097f), c0 = ptx::pack2(0.99992806f, 0.99992806f);
-  if constexpr (CLAMP) {   // (bounded scores, FIXEDREF: x >= -2 ref > -125 by construction)
+  if constexpr (CLAMP) {   // (pre-scaled bounded scores need no clamp: |x| <= 60 by contract)
     float xa, xb;
     ptx::unpack2(x2, xa, xb);
     x2 = ptx::pack2(fmaxf(xa, -125.0f), fmaxf(xb, -125.0f));          // keep 2^n representable
@@ -326,28 +91,10 @@ __device__ __forceinline__ void exp2_poly2(uint64_t x2, float& p0, float& p1) {
   p1 = __int_as_float(__float_as_int(qb) + (__float_as_int(tb) << 23));
 }
 
-// POLY8: of every 8 score pairs, POLY8 use the polynomial and 8-POLY8 use MUFU.EX2.
-// ISSUERS: 1 = warp 1 issues every MMA; 2 = warp 1 issues for the even slots (P V of tile 0 and the Q K^T that reuses
-// its buffer) and warp 3 for the odd ones, so the issuing warps' barrier-wait / commit latencies overlap.
-// XREG (DIT4SR_ATTN_XREG=1, experimental until it has passed the GPU suite): the helper warpgroup hands 128 registers per
-// thread back (setmaxnreg 40) and the two softmax warpgroups grow to 232, which removes the softmax loop's spills and
-// shortens its ptxas schedule (tools/sass_stalls.py: 1430 -> 1251 scheduled cycles per tile-step at 2/8 polynomial
-// exponentials, 1781 -> 1250 at 4/8).  setmaxnreg must sit inside the role branches: placed before them ptxas applies
-// the SMALLER budget to everything that follows.
-// SAFE (DIT4SR_ATTN_XREG=2, experimental like XREG): the barrier scheme that tools/attn_protocol_check.py proves free of
-// premature passes and deadlocks for EVERY interleaving: s_full / p_full indexed by slot % 6 = (score buffer, query tile),
-// so that each waiter sees consecutive phases of its barrier, and P V of the previous step awaited in every step before
-// P is published.  The default scheme (slot % 3, o_done awaited only when a row's reference max grew) relies on timing:
-// the MMA side must not fall a whole tile-step behind the softmax warps and the two warpgroups must stay within about
-// one issuer iteration of each other - true on the GPU by a wide margin (equal work per warp), but not by construction.
-// FIXEDREF (DIT4SR_ATTN_XREG=3 with DIT4SR_ATTN_SCORE_BOUND=<bound>, experimental): with QK-RMSNorm every score is bounded by
-// |q| |k| scale <= (8 max|w_q|) (8 max|w_k|) / 8, so a FIXED reference replaces the online row max: p = 2^(s*sl2 - ref)
-// never overflows, softmax is invariant to the reference, bf16 / fp32 keep their relative precision at any magnitude,
-// and for ref <= ~40 (log2 units) nothing that matters underflows.  No row max, no vote, no O rescale.
-// FIXEDREF = 2 (DIT4SR_ATTN_XREG=4, the engine's DIT4SR_ATTN_PRESCALE path): for bounds <= ~60 no reference is needed at
-// all - 2^60 is far inside fp32 / bf16 range - and with scale * log2(e) folded into the q RMSNorm weights by the host the
-// scores arrive ready for ex2: p = 2^s, no multiply, no subtract (the MUFU path is MUFU, MUFU, FADD2, F2FP per pair).
-template <int POLY8, int ISSUERS, bool XREG = false, bool SAFE = false, int FIXEDREF = 0>
+constexpr int ISSUERS = 2;
+constexpr bool XREG = true, SAFE = true;
+
+template <int POLY8, bool PRESCALED>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 attn_fwd2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                  const __grid_constant__ CUtensorMap tmV, const Args args) {
@@ -502,7 +249,7 @@ attn_fwd2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
       }
       float alpha = 1.0f;
       bool grow = false;
-      if constexpr (!FIXEDREF) {
+      if constexpr (!PRESCALED) {
       // 8 independent max chains (a single chain of 128 dependent FMNMX is latency-bound), then a small tree
       float mxa[8];
 #pragma unroll
@@ -520,7 +267,7 @@ attn_fwd2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
         m_run = mx;
       }
       }
-      const float neg_m = FIXEDREF ? -args.ref_log2 : -m_run * sl2;   // (unused when FIXEDREF == 2)
+      const float neg_m = -m_run * sl2;   // (unused when PRESCALED)
       uint64_t rs2[4];                         // independent packed partial row sums
 #pragma unroll
       for (int a = 0; a < 4; ++a) rs2[a] = ptx::pack2(0.f, 0.f);
@@ -529,10 +276,10 @@ attn_fwd2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
 #pragma unroll
       for (int i = 0; i < 64; ++i) {
         uint64_t x2 = ptx::pack2(__uint_as_float(v[2 * i]), __uint_as_float(v[2 * i + 1]));
-        if constexpr (FIXEDREF != 2) x2 = ptx::fma2(x2, sl2_2, negm_2);
+        if constexpr (!PRESCALED) x2 = ptx::fma2(x2, sl2_2, negm_2);
         float p0, p1;
         if (!decltype(masked)::value && (i & 7) < POLY8) {
-          exp2_poly2<FIXEDREF == 0>(x2, p0, p1);
+          exp2_poly2<!PRESCALED>(x2, p0, p1);
         } else {
           float xa, xb;
           ptx::unpack2(x2, xa, xb);
@@ -553,7 +300,7 @@ attn_fwd2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
         }
       }
       // O_t may only be touched between P V(j-1) completing and P V(j) being issued (it is issued after our arrive)
-      if (!FIXEDREF && j > 0 && __any_sync(0xffffffffu, grow)) {
+      if (!PRESCALED && j > 0 && __any_sync(0xffffffffu, grow)) {
         if constexpr (!SAFE) {
           ptx::mbar_wait(&o_done[t], (j - 1) & 1);
           ptx::tc_fence_after();
@@ -657,6 +404,13 @@ extern "C" int dit4sr_attn_fwd(const dit4sr_attn_params* p, void* stream_) {
                        p->lr_row_begin >= 0 && p->lr_row_end >= p->lr_row_begin,
                    DIT4SR_E_ALIGN, "attn: bad lr_res arguments");
   }
+  const bool prescaled = p->mode == DIT4SR_ATTN_PRESCALED;
+  DIT4SR_REQUIRE(p->mode == DIT4SR_ATTN_ONLINE || prescaled, DIT4SR_E_BADARG, "attn: unknown mode %d", p->mode);
+  DIT4SR_REQUIRE(!prescaled || (p->score_bound > 0.f && p->score_bound <= DIT4SR_ATTN_MAX_SCORE_BOUND), DIT4SR_E_BADARG,
+                 "attn: DIT4SR_ATTN_PRESCALED needs 0 < score_bound <= %g (log2 units), got %g",
+                 (double)DIT4SR_ATTN_MAX_SCORE_BOUND, (double)p->score_bound);
+  DIT4SR_REQUIRE(p->exp_offload >= 0 && p->exp_offload <= 3, DIT4SR_E_BADARG, "attn: exp_offload must be 0..3");
+
   int rc = dit4sr_check_device();
   if (rc != 0) return rc;
 
@@ -682,51 +436,20 @@ extern "C" int dit4sr_attn_fwd(const dit4sr_attn_params* p, void* stream_) {
   a.seq_kv = p->seq_kv;
   a.n_kv_tiles = (p->seq_kv + BKV - 1) / BKV;
   a.scale_log2 = p->scale * 1.4426950408889634f;
-  a.ref_log2 = 0.f;
 
+  // instance = (softmax form, share of the exponentials evaluated on the FMA pipe); exp_offload 0 = the default 2/8
   using KernelFn = void (*)(const CUtensorMap, const CUtensorMap, const CUtensorMap, const Args);
-  static bool configured = false;
-  // development switches: DIT4SR_ATTN_VARIANT=1 selects the one-tile-per-CTA kernel; DIT4SR_ATTN_POLY=0|2|4 the number
-  // of score pairs (of every 8) exponentiated on the FMA pipe instead of MUFU; DIT4SR_ATTN_ISSUERS=1 a single
-  // MMA-issuing warp; DIT4SR_ATTN_XREG=1 the register-rebalanced instance (see attn_fwd2_kernel)
-  static int variant = 2, poly8 = 2, issuers = 2;
-  static float fixed_ref = 0.f;
-  static KernelFn fn2 = nullptr;
-  if (!configured) {
-    DIT4SR_CUDA(cudaFuncSetAttribute(attn_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
-    const char* e = getenv("DIT4SR_ATTN_VARIANT");
-    if (e != nullptr && e[0] == '1') variant = 1;
-    if ((e = getenv("DIT4SR_ATTN_POLY")) != nullptr) poly8 = atoi(e);
-    if ((e = getenv("DIT4SR_ATTN_ISSUERS")) != nullptr) issuers = atoi(e) == 1 ? 1 : 2;
-    const char* xr = getenv("DIT4SR_ATTN_XREG");
-    const char* sb = getenv("DIT4SR_ATTN_SCORE_BOUND");
-    if (xr != nullptr && xr[0] == '4' && issuers == 2) {   // + pre-scaled bounded scores: p = 2^s (host folds the scale)
-      fn2 = poly8 == 0 ? v2::attn_fwd2_kernel<0, 2, true, true, 2>
-                       : (poly8 == 4 ? v2::attn_fwd2_kernel<4, 2, true, true, 2> : v2::attn_fwd2_kernel<2, 2, true, true, 2>);
-    } else if (xr != nullptr && xr[0] == '3' && issuers == 2 && sb != nullptr && atof(sb) > 0.0) {   // + fixed reference
-      fixed_ref = (float)atof(sb);
-      fn2 = v2::attn_fwd2_kernel<2, 2, true, true, 1>;
-    } else if (xr != nullptr && xr[0] == '2' && issuers == 2)   // register-rebalanced + model-checked barrier scheme
-      fn2 = poly8 == 0 ? v2::attn_fwd2_kernel<0, 2, true, true>
-                       : (poly8 == 4 ? v2::attn_fwd2_kernel<4, 2, true, true> : v2::attn_fwd2_kernel<2, 2, true, true>);
-    else if (xr != nullptr && xr[0] == '1' && issuers == 2)
-      fn2 = poly8 == 0 ? v2::attn_fwd2_kernel<0, 2, true>
-                       : (poly8 == 4 ? v2::attn_fwd2_kernel<4, 2, true> : v2::attn_fwd2_kernel<2, 2, true>);
-    else if (issuers == 2)
-      fn2 = poly8 == 0 ? v2::attn_fwd2_kernel<0, 2> : (poly8 == 4 ? v2::attn_fwd2_kernel<4, 2> : v2::attn_fwd2_kernel<2, 2>);
-    else
-      fn2 = poly8 == 0 ? v2::attn_fwd2_kernel<0, 1> : (poly8 == 4 ? v2::attn_fwd2_kernel<4, 1> : v2::attn_fwd2_kernel<2, 1>);
-    DIT4SR_CUDA(cudaFuncSetAttribute(fn2, cudaFuncAttributeMaxDynamicSharedMemorySize, v2::SMEM_BYTES));
-    configured = true;
-  }
-  a.ref_log2 = fixed_ref;
-  if (variant == 1) {
-    dim3 grid((p->seq_q + BQ - 1) / BQ, p->heads, p->batches);
-    attn_fwd_kernel<<<grid, NUM_THREADS, SMEM_BYTES, stream>>>(tmQ, tmK, tmV, a);
-  } else {
-    dim3 grid((p->seq_q + 2 * BQ - 1) / (2 * BQ), p->heads, p->batches);
-    fn2<<<grid, v2::NUM_THREADS, v2::SMEM_BYTES, stream>>>(tmQ, tmK, tmV, a);
-  }
+  static const KernelFn table[2][3] = {
+      {v2::attn_fwd2_kernel<0, false>, v2::attn_fwd2_kernel<2, false>, v2::attn_fwd2_kernel<4, false>},
+      {v2::attn_fwd2_kernel<0, true>, v2::attn_fwd2_kernel<2, true>, v2::attn_fwd2_kernel<4, true>}};
+  const int po = p->exp_offload == 0 ? 1 : p->exp_offload - 1;
+  const KernelFn fn = table[prescaled ? 1 : 0][po];
+  // the opt-in to > 48 KB of dynamic shared memory is per (function, device): remember which pairs are done
+  static unsigned long long configured[2][3] = {};
+  if (host::first_use_on_device(&configured[prescaled ? 1 : 0][po]))
+    DIT4SR_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, v2::SMEM_BYTES));
+  dim3 grid((p->seq_q + 2 * BQ - 1) / (2 * BQ), p->heads, p->batches);
+  fn<<<grid, v2::NUM_THREADS, v2::SMEM_BYTES, stream>>>(tmQ, tmK, tmV, a);
   DIT4SR_CUDA(cudaGetLastError());
   return 0;
 }

@@ -524,11 +524,9 @@ gemm_kernel(const __grid_constant__ Maps maps, const __grid_constant__ Group grp
 
 template <int EPI, bool RED = false>
 static int launch(const Maps& maps, const Group& g, cudaStream_t stream) {
-  static bool configured = false;  // benign race: idempotent attribute set
-  if (!configured) {
+  static unsigned long long configured = 0;   // per (instance, device)
+  if (host::first_use_on_device(&configured))
     DIT4SR_CUDA(cudaFuncSetAttribute(gemm_kernel<EPI, RED>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
-    configured = true;
-  }
   int grid = host::sm_count();
   if (grid > g.num_tiles) grid = g.num_tiles;
   gemm_kernel<EPI, RED><<<grid, NUM_THREADS, SMEM_BYTES, stream>>>(maps, g);

@@ -81,13 +81,22 @@ static int make_tmap_impl(CUtensorMap* out, const void* base, int rank, const ui
 }
 
 int sm_count() {
-  static int n = 0;
-  if (n == 0) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
-  }
+  static int cache[64] = {};   // per device: a process may drive several GPUs
+  int dev = 0, n = 0;
+  cudaGetDevice(&dev);
+  if (dev >= 0 && dev < 64 && cache[dev] != 0) return cache[dev];
+  cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+  if (dev >= 0 && dev < 64) cache[dev] = n;
   return n;
+}
+
+bool first_use_on_device(unsigned long long* mask) {
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev < 0 || dev >= 64) return true;   // beyond the mask: configure every time (cheap, idempotent)
+  if (*mask >> dev & 1ull) return false;
+  *mask |= 1ull << dev;                     // benign race: the attribute set is idempotent
+  return true;
 }
 
 }  // namespace host

@@ -44,6 +44,9 @@ int make_tmap_bf16_noswizzle(CUtensorMap* out, const void* base, int rank, const
 int make_tmap_f32(CUtensorMap* out, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
                   const uint32_t* box);
 
-int sm_count();
+int sm_count();                                      // of the CURRENT device (cached per device)
+// true the first time it is called with `mask` while a given device is current: function attributes such as the opt-in
+// to > 48 KB of dynamic shared memory are per (function, device), so a process-wide "configured" flag is not enough
+bool first_use_on_device(unsigned long long* mask);
 
 }  // namespace host

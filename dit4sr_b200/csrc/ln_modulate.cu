@@ -264,11 +264,10 @@ static int launch(const dit4sr_ln_modulate_params& p, cudaStream_t stream) {
     if (!p.out_f32 && variant == 8 && SMEM <= 220 * 1024 && (reinterpret_cast<uintptr_t>(p.out) & 15) == 0 &&
         p.ldo % 8 == 0 && p.o_batch_stride % 8 == 0 &&
         (p.out2 == nullptr || (reinterpret_cast<uintptr_t>(p.out2) & 15) == 0)) {
-      static bool configured = false;
-      if (!configured) {
+      static unsigned long long configured = 0;   // per (instance, device)
+      if (host::first_use_on_device(&configured)) {
         DIT4SR_CUDA(cudaFuncSetAttribute(ln_modulate_tma_kernel<NV / 2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
         DIT4SR_CUDA(cudaFuncSetAttribute(ln_modulate_tma_kernel<NV / 2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
-        configured = true;
       }
       unsigned grid = (unsigned)((total + LN_WARPS - 1) / LN_WARPS);
       const unsigned sms = (unsigned)host::sm_count();

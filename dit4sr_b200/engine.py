@@ -73,8 +73,8 @@ PRESCALE_MAX_BOUND = 60.0   # log2 units: 2^60 * 8525 keys * |v| is far inside f
 
 
 def prescaled_q_norm_weights(wq, wk, waq=None, wak=None):
-    """Experimental (DIT4SR_ATTN_XREG=4): fold the softmax scale and log2(e) into the q RMSNorm weights, so that the joint
-    attention kernel can take p = 2^score without a multiply, a reference max or a rescale.
+    """Fold the softmax scale and log2(e) into the q RMSNorm weights, so that the joint attention kernel can take
+    p = 2^score without a multiply, a reference max or a rescale (ops.ATTN_PRESCALED).
 
     Valid because QK-RMSNorm bounds every score: each normed row has norm <= sqrt(dh) * max|w| (attention.py:484-489,
     502-505; the twice-normed LR keys included), hence score * scale * log2(e) <= dh * max|w_q| * max|w_k| * scale * log2(e).
@@ -85,17 +85,18 @@ def prescaled_q_norm_weights(wq, wk, waq=None, wak=None):
     kmax = max(float(wk.abs().max()), float(wak.abs().max()) if wak is not None else 0.0)
     bound = dh * qmax * kmax * f
     if not bound <= PRESCALE_MAX_BOUND:
-        raise ValueError(f"DIT4SR_ATTN_XREG=4: score bound {bound:.1f} (log2 units) exceeds {PRESCALE_MAX_BOUND}: this "
-                         "checkpoint needs the online-max softmax")
+        raise ValueError(f"score bound {bound:.1f} (log2 units) exceeds {PRESCALE_MAX_BOUND}: this checkpoint needs the "
+                         "online-max softmax")
     return wq * f, (waq * f if waq is not None else None), bound
 
 
-def _prescale_requested():
-    return os.environ.get("DIT4SR_ATTN_XREG", "") == "4"
+def _prescale_allowed():
+    """DIT4SR_ATTN_PRESCALE=0 keeps the online softmax for every attention (read once per Engine, at pack time)."""
+    return os.environ.get("DIT4SR_ATTN_PRESCALE", "1") != "0"
 
 
 class _AttnPack:
-    def __init__(self, attn, has_text: bool, fold: bool, precise: bool = False):
+    def __init__(self, attn, has_text: bool, fold: bool, precise: bool = False, prescale: bool = False):
         from functools import partial
         _Lin, _Folded = partial(globals()["_Lin"], precise=precise), partial(globals()["_Folded"], precise=precise)
         self.qk_norm = attn.norm_q is not None
@@ -126,23 +127,30 @@ class _AttnPack:
             if self.qk_norm:
                 self.waq, self.wak = _f32(attn.norm_added_q.weight), _f32(attn.norm_added_k.weight)
             self.add_out = _Lin(attn.to_add_out) if hasattr(attn, "to_add_out") else None
-        if _prescale_requested() and not precise:
-            if not self.qk_norm:
-                raise ValueError("DIT4SR_ATTN_XREG=4 needs qk_norm='rms_norm' (bounded scores)")
-            self.wq, waq, self.score_bound = prescaled_q_norm_weights(
-                self.wq, self.wk, getattr(self, "waq", None), getattr(self, "wak", None))
-            if waq is not None:
-                self.waq = waq
+        # Bounded scores (QK-RMSNorm with small enough weights): fold scale*log2(e) into the q norm weights and let the
+        # attention kernel drop the running max; any other checkpoint (qk_norm=None, large norm weights) keeps the online
+        # softmax.  Decided per attention module at pack time; the kernel gets the mode with every call (ABI v3).
+        self.score_bound = None
+        if prescale and self.qk_norm and not precise:
+            try:
+                wq, waq, bound = prescaled_q_norm_weights(self.wq, self.wk, getattr(self, "waq", None),
+                                                          getattr(self, "wak", None))
+            except ValueError:
+                pass
+            else:
+                self.wq, self.score_bound = wq, bound
+                if waq is not None:
+                    self.waq = waq
 
 
 class _BlockPack:
-    def __init__(self, blk, fold, precise=False):
+    def __init__(self, blk, fold, precise=False, prescale=False):
         from functools import partial
         _Lin = partial(globals()["_Lin"], precise=precise)
         self.dual = blk.use_dual_attention
         self.last = blk.context_pre_only
-        self.attn = _AttnPack(blk.attn, True, fold, precise)
-        self.attn2 = _AttnPack(blk.attn2, False, fold, precise) if self.dual else None
+        self.attn = _AttnPack(blk.attn, True, fold, precise, prescale)
+        self.attn2 = _AttnPack(blk.attn2, False, fold, precise, prescale) if self.dual else None
         self.ff1, self.ff2 = _Lin(blk.ff.net[0].proj), _Lin(blk.ff.net[2])
         cw = blk.ff.control_conv.weight
         self.conv_w9 = _f32(cw.reshape(cw.shape[0], 9).t())           # tap-major [9, F]
@@ -158,7 +166,8 @@ class _BlockPack:
 
 
 class Engine:
-    def __init__(self, model, fold_lr_chains: Optional[bool] = None, sp=None, precise: Optional[bool] = None):
+    def __init__(self, model, fold_lr_chains: Optional[bool] = None, sp=None, precise: Optional[bool] = None,
+                 prescale_attention: Optional[bool] = None):
         """fold_lr_chains: fold `to_x_control(to_x(.))` into one GEMM per projection (exact algebra, one bf16 rounding
         of the product weight instead of a bf16 intermediate activation). Default on; DIT4SR_FOLD_LR=0 turns it off.
 
@@ -193,7 +202,11 @@ class Engine:
         D = self.D
         from functools import partial
         _Lin = partial(globals()["_Lin"], precise=self.precise)
-        self.blocks = [_BlockPack(b, fold_lr_chains, self.precise) for b in model.transformer_blocks]
+        if prescale_attention is None:
+            prescale_attention = _prescale_allowed()
+        self.prescale_attention = bool(prescale_attention) and not self.precise
+        self.blocks = [_BlockPack(b, fold_lr_chains, self.precise, self.prescale_attention)
+                       for b in model.transformer_blocks]
         # every adaLN linear of the model in one weight: temb is the same for all blocks, so one GEMM per step
         mods, self.mod_off = [], []
         off = 0
@@ -365,7 +378,8 @@ class Engine:
         Three grouped GEMM launches + one attention launch: {HQ q|k|v, LR stage-1, text q|k|v}, {LR q_c, (k_c,) v_c},
         attention, {to_out, to_out_control, to_add_out}."""
         D, H, R = self.D, self.H, self._run
-        x, ctx, qkv, o, lrtmp = ws["x"], ws["ctx"], ws["qkv"], ws["o"], ws["lrtmp"]
+        x, ctx, qkv, o = ws["x"], ws["ctx"], ws["qkv"], ws["o"]
+        lrtmp = ws["lrtmp"][:, :N]        # sized for the larger segment (attn2 of the 3-stream model: 1.5N rows)
         I = (3 if ap.ocr else 2) * N      # image rows seen by this processor (N = rows per segment)
         S = I + (T if ap.has_text else 0)
         hq, lr = n_in[:, :N], n_in[:, N:2 * N]
@@ -405,7 +419,8 @@ class Engine:
         elif self.sp is None:
             seq_q = I if (last or not ap.has_text) else S
             R("attn", ops.attention, qkv[:, :S, :D], qkv[:, :S, D:2 * D], qkv[:, :S, 2 * D:], o, H, seq_q=seq_q,
-              lr_res=n_in, lr_rows=(N, I))   # Q2: the LR (and OCR) rows get their normed+modulated input added back
+              lr_res=n_in, lr_rows=(N, I),   # Q2: the LR (and OCR) rows get their normed+modulated input added back
+              score_bound=ap.score_bound)
         else:
             self._attention_sp(ap, ws, n_in, N, I, S, last)
         G = ops.EPI_GATE_RESID
@@ -434,7 +449,8 @@ class Engine:
             qs[:, P * I:P * I + T] = qkv[:, I:S].reshape(B, T, 3, H, 64)[:, :, :, h0:h1].reshape(B, T, 3, Dl)
         Ssp = P * I + T
         seq_q = P * I if (last or not T) else Ssp
-        R("attn", ops.attention, qs[:, :Ssp, 0], qs[:, :Ssp, 1], qs[:, :Ssp, 2], os_, Hl, seq_q=seq_q)
+        R("attn", ops.attention, qs[:, :Ssp, 0], qs[:, :Ssp, 1], qs[:, :Ssp, 2], os_, Hl, seq_q=seq_q,
+          score_bound=ap.score_bound)
         o[:, :I] = sp.heads_to_seq(os_[:, :P * I])
         if T and not last:
             o[:, I:S] = sp.gather_heads(os_[:, P * I:Ssp])

@@ -191,10 +191,16 @@ def gemm_schedule(shapes, sm_count=148):
     return [tuple(items[5 * i:5 * i + 5]) for i in range(count)]
 
 
-def attention(q, k, v, o, heads, seq_q=None, scale=None, lr_res=None, lr_rows=(0, 0)):
+ATTN_ONLINE, ATTN_PRESCALED = 0, 1
+ATTN_MAX_SCORE_BOUND = 60.0
+
+
+def attention(q, k, v, o, heads, seq_q=None, scale=None, lr_res=None, lr_rows=(0, 0), score_bound=None, exp_offload=0):
     """o = softmax(q k^T * scale) v over [B, S, heads*64] bf16 views (row stride may be 3*heads*64 for a fused buffer).
 
-    Only the first seq_q query rows are produced. lr_res (bf16 [B, >=lr_rows[1], heads*64]) is added to rows lr_rows."""
+    Only the first seq_q query rows are produced. lr_res (bf16 [B, >=lr_rows[1], heads*64]) is added to rows lr_rows.
+    score_bound (log2 units): q already carries scale*log2(e) and q.k <= score_bound for every pair -> the kernel takes
+    p = 2^(q.k) without a reference max (DIT4SR_ATTN_PRESCALED); None = online softmax (any q, k)."""
     for n, t in (("q", q), ("k", k), ("v", v), ("o", o)):
         _req(t, torch.bfloat16, n)
     B, S, D = k.shape
@@ -213,6 +219,9 @@ def attention(q, k, v, o, heads, seq_q=None, scale=None, lr_res=None, lr_rows=(0
         p.lr_row_begin, p.lr_row_end = lr_rows
     p.batches, p.heads, p.seq_q, p.seq_kv = B, heads, seq_q, S
     p.scale = (1.0 / 8.0) if scale is None else scale
+    if score_bound is not None:
+        p.mode, p.score_bound = ATTN_PRESCALED, float(score_bound)
+    p.exp_offload = exp_offload
     check(_lib.load().dit4sr_attn_fwd(C.byref(p), _stream()), "dit4sr_attn_fwd")
     _count()
 

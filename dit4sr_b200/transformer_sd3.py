@@ -293,7 +293,7 @@ class SD3Transformer2DModel(nn.Module):
                 if i in layers:
                     d = {}
                     if sl is not None:
-                        d["extract_feat"] = x[:, sl[0]:sl[1]].to(in_dtype)
+                        d["extract_feat"] = x[:, sl[0]:sl[1]].to(in_dtype, copy=True)   # x is the live fp32 workspace: never alias it
                     trans_blk_outs.append(d)
 
         hs, ci = hidden_states, controlnet_image

@@ -23,7 +23,7 @@
 extern "C" {
 #endif
 
-#define DIT4SR_ABI_VERSION 2
+#define DIT4SR_ABI_VERSION 3
 
 enum {
   DIT4SR_OK = 0,
@@ -143,7 +143,19 @@ int dit4sr_gemm_schedule(const dit4sr_gemm_params* problems, int count, int sm_c
  * buffer [B, S, 3*H*64] is addressed with row_stride = 3*H*64 and q/k/v pointers 0 / H*64 / 2*H*64 apart).
  * o: bf16 [B, Sq, H*64] (row stride o_row_stride).  Only the first seq_q query rows are computed (the last block
  * drops the text queries).  If lr_res != NULL, rows [lr_row_begin, lr_row_end) of o get lr_res[b, row, :] added.
+ *
+ * mode (ABI v3; selection is per call, nothing is read from the environment):
+ *   DIT4SR_ATTN_ONLINE     online softmax with the running row max as reference: valid for any q, k.
+ *   DIT4SR_ATTN_PRESCALED  the caller has folded scale * log2(e) into q (`scale` is ignored) and guarantees
+ *                          q.k <= score_bound <= DIT4SR_ATTN_MAX_SCORE_BOUND for every (query, key) pair; the kernel
+ *                          then takes p = 2^(q.k) with no reference, no row max and no rescale of O.  With QK-RMSNorm
+ *                          (attention.py:484-489,502-505) every normed row has |x| <= 8 max|w|, so the bound follows
+ *                          from the checkpoint's norm weights; the host refuses the mode when it does not hold.
+ * exp_offload: 0 = default; 1, 2, 3 = 0/8, 2/8, 4/8 of the exponentials evaluated by a polynomial on the FMA pipe instead
+ *              of MUFU.EX2 (tuning knob: same results to within bf16 rounding of P).
  */
+enum { DIT4SR_ATTN_ONLINE = 0, DIT4SR_ATTN_PRESCALED = 1 };
+#define DIT4SR_ATTN_MAX_SCORE_BOUND 60.0f
 typedef struct {
   const void* q; const void* k; const void* v;
   int64_t qkv_row_stride; int64_t qkv_batch_stride;
@@ -152,6 +164,7 @@ typedef struct {
   int lr_row_begin; int lr_row_end;
   int batches; int heads; int seq_q; int seq_kv;
   float scale;
+  int mode; float score_bound; int exp_offload;                          /* ABI v3 */
 } dit4sr_attn_params;
 int dit4sr_attn_fwd(const dit4sr_attn_params* p, void* stream);
 

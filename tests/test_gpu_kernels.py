@@ -219,6 +219,71 @@ def test_joint_attention(ops, B, H, S, Sq, lr):
     assert rel(o.float(), ref) < 4e-3   # bf16 P and bf16 output roundings
 
 
+LOG2E_OVER_8 = 1.4426950408889634 / 8.0
+
+
+@pytest.mark.parametrize("exp_offload", [0, 1, 3])
+@pytest.mark.parametrize("B,H,S,Sq,lr", [(1, 2, 256, 256, None), (2, 3, 333, 333, None), (1, 24, 2381, 2381, (1024, 2048)),
+                                         (2, 4, 2381, 2048, (1024, 2048)), (1, 1, 1, 1, None), (8, 24, 600, 333, (100, 300)),
+                                         (1, 2, 8525, 8525, (4096, 8192))])
+def test_joint_attention_prescaled_bounded_scores(ops, B, H, S, Sq, lr, exp_offload):
+    """DIT4SR_ATTN_PRESCALED (ABI v3): q arrives multiplied by scale*log2(e) and the caller bounds every score; the
+    kernel takes p = 2^(q.k) with no running max.  Reference: fp32 SDPA on the SAME (bf16-rounded, pre-scaled) q with
+    scale = ln 2, i.e. softmax(2^(q'.k))."""
+    torch.manual_seed(0)
+    D = H * 64
+    qkv = torch.randn(B, S, 3 * D, device="cuda")
+    qkv[..., :D] *= LOG2E_OVER_8
+    qkv = qkv.bfloat16()
+    q, k, v = qkv[..., :D], qkv[..., D:2 * D], qkv[..., 2 * D:]
+
+    def hd(t):
+        return t.float().reshape(B, S, H, 64).transpose(1, 2)
+
+    bound = float((hd(q)[:, :, :Sq] @ hd(k).transpose(-1, -2)).max()) if S <= 2381 else 30.0
+    assert bound < 60
+    o = torch.zeros(B, Sq, D, device="cuda", dtype=torch.bfloat16)
+    res = torch.randn(B, S, D, device="cuda").bfloat16() if lr else None
+    ops.attention(q, k, v, o, H, seq_q=Sq, lr_res=res, lr_rows=lr or (0, 0), score_bound=max(bound, 1.0),
+                  exp_offload=exp_offload)
+    ref = torch.nn.functional.scaled_dot_product_attention(hd(q), hd(k), hd(v), scale=math.log(2.0))
+    ref = ref.transpose(1, 2).reshape(B, S, D)[:, :Sq].clone()
+    if lr:
+        ref[:, lr[0]:lr[1]] += res[:, lr[0]:lr[1]].float()
+    assert rel(o.float(), ref) < 4e-3
+
+
+def test_attention_prescaled_large_and_small_scores_stay_finite(ops):
+    """Scores spread over [-55, +55] log2 units (the contract allows up to 60): no overflow, and rows whose scores are
+    all very negative still normalise (2^-55 is far inside bf16 / fp32 range)."""
+    torch.manual_seed(0)
+    B, H, S = 1, 2, 700
+    D = H * 64
+    qkv = torch.randn(B, S, 3 * D, device="cuda")
+    qkv[..., :D] *= 0.85
+    qkv[0, :100, :D] = -qkv[0, :100, D:2 * D].mean(dim=0, keepdim=True) * 6.0   # rows that dislike every key
+    qkv = qkv.bfloat16()
+    q, k, v = qkv[..., :D], qkv[..., D:2 * D], qkv[..., 2 * D:]
+    hd = lambda t: t.float().reshape(B, S, H, 64).transpose(1, 2)
+    sc = hd(q) @ hd(k).transpose(-1, -2)
+    assert float(sc.max()) < 60 and float(sc.max()) > 20
+    o = torch.zeros(B, S, D, device="cuda", dtype=torch.bfloat16)
+    ops.attention(q, k, v, o, H, score_bound=60.0)
+    ref = torch.nn.functional.scaled_dot_product_attention(hd(q), hd(k), hd(v), scale=math.log(2.0))
+    ref = ref.transpose(1, 2).reshape(B, S, D)
+    assert torch.isfinite(o.float()).all()
+    assert rel(o.float(), ref) < 6e-3
+
+
+def test_attention_mode_is_validated(ops):
+    q = torch.zeros(1, 128, 64, device="cuda", dtype=torch.bfloat16)
+    o = torch.zeros_like(q)
+    with pytest.raises(Exception, match="score_bound"):
+        ops.attention(q, q, q, o, 1, score_bound=61.0)
+    with pytest.raises(Exception, match="exp_offload"):
+        ops.attention(q, q, q, o, 1, exp_offload=7)
+
+
 def test_attention_peaked_softmax_is_stable(ops):
     """Large score range (|s| up to ~60): online softmax with running max must not overflow."""
     torch.manual_seed(0)

@@ -46,6 +46,8 @@ def main():
     ap.add_argument("--reps", type=int, default=20)
     ap.add_argument("--shape", default="c2")
     ap.add_argument("--graph", action="store_true")
+    ap.add_argument("--prescaled", action="store_true", help="attn: DIT4SR_ATTN_PRESCALED mode (q pre-multiplied)")
+    ap.add_argument("--exp-offload", type=int, default=0, help="attn: 0 default, 1/2/3 = 0/8, 2/8, 4/8 polynomial")
     a = ap.parse_args()
     global GRAPH
     GRAPH = a.graph
@@ -55,13 +57,17 @@ def main():
     dev = "cuda"
     torch.manual_seed(0)
     if a.what == "attn":
-        qkv = torch.randn(B, S, 3 * D, device=dev).bfloat16()
+        qkv = torch.randn(B, S, 3 * D, device=dev)
+        if a.prescaled:
+            qkv[..., :D] *= 1.4426950408889634 / 8.0
+        qkv = qkv.bfloat16()
         o = torch.empty(B, S, D, device=dev, dtype=torch.bfloat16)
         res = torch.randn(B, 2 * N, D, device=dev).bfloat16()
-        fn = lambda: ops.attention(qkv[..., :D], qkv[..., D:2 * D], qkv[..., 2 * D:], o, H, lr_res=res, lr_rows=(N, 2 * N))
+        fn = lambda: ops.attention(qkv[..., :D], qkv[..., D:2 * D], qkv[..., 2 * D:], o, H, lr_res=res, lr_rows=(N, 2 * N),
+                                   score_bound=30.0 if a.prescaled else None, exp_offload=a.exp_offload)
         ms = timeit(fn, a.reps)
         fl = 4.0 * S * S * D * B
-        print(f"attn B={B} S={S}: {ms:.4f} ms  {fl / ms / 1e9:.1f} TFLOP/s")
+        print(f"attn B={B} S={S} prescaled={a.prescaled} exp_offload={a.exp_offload}: {ms:.4f} ms  {fl / ms / 1e9:.1f} TFLOP/s")
     elif a.what == "gemm":
         for name, M, K, Nn, epi in [("ff1", B * 2 * N, D, F, ops.EPI_BIAS_GELU), ("ff2", B * 2 * N, F, D, ops.EPI_GATE_RESID),
                                     ("qkv", B * N, D, 3 * D, ops.EPI_QKV_NORM), ("out", B * N, D, D, ops.EPI_GATE_RESID)]:
