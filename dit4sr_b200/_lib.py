@@ -40,7 +40,7 @@ class AttnParams(C.Structure):
                 ("lr_res", c_vp), ("lr_row_stride", c_i64), ("lr_batch_stride", c_i64),
                 ("lr_row_begin", c_int), ("lr_row_end", c_int),
                 ("batches", c_int), ("heads", c_int), ("seq_q", c_int), ("seq_kv", c_int), ("scale", c_float),
-                ("mode", c_int), ("score_bound", c_float), ("exp_offload", c_int)]
+                ("mode", c_int), ("score_bound", c_float), ("exp_offload", c_int), ("variant", c_int)]
 
 
 # every symbol include/dit4sr_b200.h declares: name -> (restype, argtypes)

@@ -25,6 +25,49 @@ struct Args {
   float scale_log2;  // scale * log2(e)  (unused by the pre-scaled instances)
 };
 
+// Epilogue of one softmax thread: its row of O (64 fp32 TMEM columns at tO) / l (+ LR residual, attention.py:545) -> bf16.
+__device__ __forceinline__ void store_rows(const Args& args, uint32_t tO, int row, int head, int b, float inv_l) {
+  const bool row_ok = row < args.seq_q;
+  const bool add_lr = args.lr_res != nullptr && row >= args.lr_row_begin && row < args.lr_row_end;
+#pragma unroll 1
+  for (int c = 0; c < DH / 32; ++c) {
+    uint32_t o[32];
+    ptx::tmem_ld32(tO + c * 32, o);
+    ptx::tmem_wait_ld();
+    if (row_ok) {
+      float f[32];
+#pragma unroll
+      for (int i = 0; i < 32; ++i) f[i] = __uint_as_float(o[i]) * inv_l;
+      if (add_lr) {
+        const uint4* lr = reinterpret_cast<const uint4*>(args.lr_res + (int64_t)b * args.lr_batch_stride +
+                                                         (int64_t)row * args.lr_row_stride + head * DH + c * 32);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const uint4 u = __ldg(lr + i);
+          const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&u);
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const float2 ff = __bfloat1622float2(h2[k]);
+            f[8 * i + 2 * k] += ff.x;
+            f[8 * i + 2 * k + 1] += ff.y;
+          }
+        }
+      }
+      uint4* dst = reinterpret_cast<uint4*>(args.o + (int64_t)b * args.o_batch_stride +
+                                            (int64_t)row * args.o_row_stride + head * DH + c * 32);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        uint4 u;
+        u.x = ptx::pack_bf16(f[8 * i + 0], f[8 * i + 1]);
+        u.y = ptx::pack_bf16(f[8 * i + 2], f[8 * i + 3]);
+        u.z = ptx::pack_bf16(f[8 * i + 4], f[8 * i + 5]);
+        u.w = ptx::pack_bf16(f[8 * i + 6], f[8 * i + 7]);
+        dst[i] = u;
+      }
+    }
+  }
+}
+
 
 // Warps (384 threads): 0 = TMA producer, 1 and 3 = MMA issuers (even / odd slots, so that their barrier-wait / commit
 // latencies overlap), 2 = TMEM allocator, 4..7 = softmax warpgroup of tile 0, 8..11 = softmax warpgroup of tile 1.
@@ -54,6 +97,19 @@ struct Args {
 //  In both, POLY8 of every 8 score pairs take their exponential on the FMA pipe (exp2_poly2) instead of MUFU.EX2, which
 //  bounds head_dim-64 attention (16 results/clk/SM: 1024 cycles per 128x128 score tile against 526 for its MMAs).
 namespace v2 {
+
+// Developer build (-DDIT4SR_ATTN_TIMING, tools/attn_prof.py): clock64 phase timers of ONE CTA's warps, summed over its KV
+// steps into g_attn_timing[warp][phase].  Compiled out of the product library.
+#ifdef DIT4SR_ATTN_TIMING
+__device__ long long g_attn_timing[12 * 16];
+#define T_DECL long long tacc[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0}; const bool t_on = blockIdx.x == 3 && blockIdx.y == 5 && blockIdx.z == (gridDim.z > 4 ? 4 : 0); long long t_prev = clock64()
+#define T_MARK(i) do { if (t_on) { const long long t_now = clock64(); tacc[i] += t_now - t_prev; t_prev = t_now; } } while (0)
+#define T_FLUSH() do { if (t_on && lane == 0) for (int i_ = 0; i_ < 10; ++i_) v2::g_attn_timing[warp * 16 + i_] = tacc[i_]; } while (0)
+#else
+#define T_DECL
+#define T_MARK(i)
+#define T_FLUSH()
+#endif
 
 constexpr int KV_STAGES = 4;
 constexpr int NUM_THREADS = 384;
@@ -182,11 +238,14 @@ attn_fwd2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
     const uint64_t kdesc_base = ptx::make_sdesc_sw128(ptx::smem_u32(sK));
     const uint64_t vdesc_base = ptx::make_sdesc_sw128(ptx::smem_u32(sV));
 
+    T_DECL;
     // S[buffer n%3] = Q_t K_j^T for slot n = 2j + t
     auto issue_qk = [&](int n) {
       const int t = n & 1, j = n >> 1, st = j % KV_STAGES, buf = n % NBUF;
+      T_MARK(9);
       ptx::mbar_wait(&k_full[st], (j / KV_STAGES) & 1);
       ptx::tc_fence_after();
+      T_MARK(4);   // wait K
       const uint64_t kdesc = kdesc_base + (uint64_t)(st * (TILE_BYTES >> 4));
       const uint64_t qd = t ? qdesc1 : qdesc0;
       if (ptx::elect_one()) {
@@ -197,6 +256,7 @@ attn_fwd2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
         if (ISSUERS == 2 || t == 1) ptx::tc_commit(&k_empty[st]);   // both tiles have consumed K_j
       }
       __syncwarp();
+      T_MARK(5);   // issue Q K^T + commits
     };
 
     ptx::mbar_wait(q_full, 0);
@@ -205,9 +265,12 @@ attn_fwd2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
       if (ISSUERS == 1 || ((n + 1) & 1) == my) issue_qk(n);
     for (int n = (ISSUERS == 2 ? my : 0); n < n_slots; n += ISSUERS) {
       const int t = n & 1, j = n >> 1, st = j % KV_STAGES, buf = n % NBUF;
+      T_MARK(9);
       ptx::mbar_wait(&v_full[st], (j / KV_STAGES) & 1);
+      T_MARK(1);   // wait V
       ptx::mbar_wait(&p_full[n % NSB], (n / NSB) & 1);   // softmax wrote P into the buffer (and rescaled O if needed)
       ptx::tc_fence_after();
+      T_MARK(2);   // wait P
       const uint64_t vdesc = vdesc_base + (uint64_t)(st * (TILE_BYTES >> 4));
       if (ptx::elect_one()) {
 #pragma unroll
@@ -218,8 +281,10 @@ attn_fwd2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
         if (ISSUERS == 2 || t == 1) ptx::tc_commit(&v_empty[st]);
       }
       __syncwarp();
+      T_MARK(3);   // issue P V + commits
       if (n + NBUF < n_slots) issue_qk(n + NBUF);   // reuses this buffer; ordered behind the P V above in the tensor pipe
     }
+    T_FLUSH();
   }
   } else {
     if constexpr (XREG) asm volatile("setmaxnreg.inc.sync.aligned.u32 232;");
@@ -231,16 +296,20 @@ attn_fwd2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
     const float sl2 = args.scale_log2;
     float m_run = -INFINITY;   // the max the running sums are scaled with (raw score units)
     float l_run = 0.f;
+    T_DECL;
     auto tile_step = [&](int j, auto masked) {
       const int n = 2 * j + t;
       const int buf = n % NBUF;
       const uint32_t tS = tmem_base + buf * 128 + lane_off;
+      T_MARK(9);
       ptx::mbar_wait(&s_full[n % NSB], (n / NSB) & 1);
       ptx::tc_fence_after();
+      T_MARK(1);   // wait S
       uint32_t v[128];
 #pragma unroll
       for (int c = 0; c < 4; ++c) ptx::tmem_ld32(tS + c * 32, *reinterpret_cast<uint32_t(*)[32]>(&v[c * 32]));
       ptx::tmem_wait_ld();
+      T_MARK(2);   // TMEM load
       if constexpr (decltype(masked)::value) {   // only the last KV tile can be ragged
         const int kv_left = args.seq_kv - j * BKV;
 #pragma unroll
@@ -293,12 +362,17 @@ attn_fwd2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
       ptx::unpack2(ptx::add2(rs2[0], rs2[1]), ra, rb);
       ptx::unpack2(ptx::add2(rs2[2], rs2[3]), rc, rd);
       const float rsum = (ra + rb) + (rc + rd);
+#ifdef DIT4SR_ATTN_TIMING
+      asm volatile("" ::"f"(rsum), "r"(pk[0]), "r"(pk[63]) : "memory");
+#endif
+      T_MARK(3);   // max + exponentials + sums + pack
       if constexpr (SAFE) {   // every step observes P V of the previous one: consecutive o_done phases, lead <= one step
         if (j > 0) {
           ptx::mbar_wait(&o_done[t], (j - 1) & 1);
           ptx::tc_fence_after();
         }
       }
+      T_MARK(4);   // wait P V of the previous step
       // O_t may only be touched between P V(j-1) completing and P V(j) being issued (it is issued after our arrive)
       if (!PRESCALED && j > 0 && __any_sync(0xffffffffu, grow)) {
         if constexpr (!SAFE) {
@@ -315,64 +389,29 @@ attn_fwd2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
           ptx::tmem_st32(tO + c * 32, o);
         }
       }
+      T_MARK(5);   // O rescale
       // P overwrites the first 64 columns of the score buffer (the whole row is already in registers)
 #pragma unroll
       for (int c = 0; c < 4; ++c) ptx::tmem_st16(tS + c * 16, &pk[c * 16]);
       l_run = l_run * alpha + rsum;
       ptx::tmem_wait_st();
+      T_MARK(6);   // P store
       ptx::tc_fence_before();
       __syncwarp();
       if (lane == 0) ptx::mbar_arrive(&p_full[n % NSB]);
+      T_MARK(7);   // arrive
     };
     const bool ragged = (args.seq_kv % BKV) != 0;
     for (int j = 0; j + 1 < n_tiles; ++j) tile_step(j, std::false_type{});
     if (ragged) tile_step(n_tiles - 1, std::true_type{});
     else tile_step(n_tiles - 1, std::false_type{});
+    T_FLUSH();
 
     // epilogue: O / l (+ LR residual) -> bf16 global
     ptx::mbar_wait(&o_done[t], (n_tiles - 1) & 1);
     ptx::tc_fence_after();
     const int row = (q_pair * 2 + t) * BQ + q * 32 + lane;
-    const float inv_l = 1.0f / l_run;
-    const bool row_ok = row < args.seq_q;
-    const bool add_lr = args.lr_res != nullptr && row >= args.lr_row_begin && row < args.lr_row_end;
-#pragma unroll 1
-    for (int c = 0; c < DH / 32; ++c) {
-      uint32_t o[32];
-      ptx::tmem_ld32(tO + c * 32, o);
-      ptx::tmem_wait_ld();
-      if (row_ok) {
-        float f[32];
-#pragma unroll
-        for (int i = 0; i < 32; ++i) f[i] = __uint_as_float(o[i]) * inv_l;
-        if (add_lr) {
-          const uint4* lr = reinterpret_cast<const uint4*>(args.lr_res + (int64_t)b * args.lr_batch_stride +
-                                                           (int64_t)row * args.lr_row_stride + head * DH + c * 32);
-#pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            const uint4 u = __ldg(lr + i);
-            const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&u);
-#pragma unroll
-            for (int k = 0; k < 4; ++k) {
-              const float2 ff = __bfloat1622float2(h2[k]);
-              f[8 * i + 2 * k] += ff.x;
-              f[8 * i + 2 * k + 1] += ff.y;
-            }
-          }
-        }
-        uint4* dst = reinterpret_cast<uint4*>(args.o + (int64_t)b * args.o_batch_stride +
-                                              (int64_t)row * args.o_row_stride + head * DH + c * 32);
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          uint4 u;
-          u.x = ptx::pack_bf16(f[8 * i + 0], f[8 * i + 1]);
-          u.y = ptx::pack_bf16(f[8 * i + 2], f[8 * i + 3]);
-          u.z = ptx::pack_bf16(f[8 * i + 4], f[8 * i + 5]);
-          u.w = ptx::pack_bf16(f[8 * i + 6], f[8 * i + 7]);
-          dst[i] = u;
-        }
-      }
-    }
+    store_rows(args, tO, row, head, b, 1.0f / l_run);
   }
 
   __syncwarp();
@@ -386,7 +425,302 @@ attn_fwd2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
 
 }  // namespace v2
 
+// =====================================================================================================================
+// v3: independent query tiles with DOUBLE-BUFFERED score tiles of 96 keys.
+//
+// The phase timers of v2 (tools/attn_prof.py, profiles/r02_attn_prof.log) show its softmax warps waiting 300-600 of every
+// ~2300 cycles for their next score tile: three 128-key buffers rotating over two query tiles hand a buffer from one
+// tile to the other, so  softmax(n) -> P V(n) -> Q K^T(n+3) -> softmax(n+3)  is a serial chain through every buffer.
+// Here each query tile owns TWO score buffers: 4 x 96 columns = 384 = what TMEM leaves beside the two 64-column O
+// accumulators.  Q_t K_{j+2}^T is issued right after P_t V_j into the buffer P_j just left, i.e. a whole softmax step before
+// it is needed, and the two tiles never exchange buffers.  KV tiles are 96 rows (12 KB TMA boxes, MMA N = 96 for Q K^T and
+// six K = 16 steps for P V).  P (bf16) overwrites the first 48 columns of its own score buffer.
+// TMEM: S/P (t,b) at 96*(2t+b), t,b in {0,1}  [0,384) | O0 [384,448) | O1 [448,512).
+//
+// Barriers: s_full[t][b] (MMA -> softmax), p_full[t][b] (4 softmax warps -> MMA), o_done[t] (P V complete).  Every waiter
+// sees consecutive phases of its barrier: Q K^T(j+2) is issued only after all four warps have published P(j), so no warp
+// can be more than one phase ahead on s_full[t][b], and the issuer consumes p_full[t][b] in order.  o_done[t] is awaited
+// only where O is touched (online-softmax rescale, epilogue): when a step-j softmax probes it, S(j) is complete, hence
+// (in-order tensor pipe, Q K^T(j) issued after P V(j-2)) P V(j-2) is, and P V(j) cannot have been issued before this
+// warp's own arrive: the barrier is in phase j-1 or j, which a parity wait tells apart.
+namespace v3 {
+
+constexpr int BKV = 96;
+constexpr int KV_BYTES = BKV * DH * 2;   // 12 KB
+constexpr int KV_STAGES = 4;
+constexpr int NUM_THREADS = 384;
+constexpr int TMEM_COLS = 512;
+constexpr int COL_O = 4 * BKV;
+constexpr int SMEM_BYTES = 2 * TILE_BYTES + 2 * KV_STAGES * KV_BYTES + 1024 + 256;
+constexpr float RESCALE_THRESHOLD = 8.0f;
+
+template <int POLY8, bool PRESCALED>
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+attn_fwd3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
+                 const __grid_constant__ CUtensorMap tmV, const Args args) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sQ = smem;                                            // 2 tiles of 128 rows
+  uint8_t* sK = smem + 2 * TILE_BYTES;                           // KV_STAGES tiles of 96 rows
+  uint8_t* sV = sK + KV_STAGES * KV_BYTES;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sV + KV_STAGES * KV_BYTES);
+  uint64_t* q_full = bars;
+  uint64_t* k_full = bars + 1;
+  uint64_t* k_empty = k_full + KV_STAGES;
+  uint64_t* v_full = k_empty + KV_STAGES;
+  uint64_t* v_empty = v_full + KV_STAGES;
+  uint64_t* s_full = v_empty + KV_STAGES;   // [2 tiles][2 buffers]
+  uint64_t* p_full = s_full + 4;            // [2][2]
+  uint64_t* o_done = p_full + 4;            // [2]
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(o_done + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int q_pair = blockIdx.x;
+  const int head = blockIdx.y;
+  const int b = blockIdx.z;
+  const int n_tiles = args.n_kv_tiles;
+
+  if (warp == 0 && lane == 0) {
+    ptx::prefetch_tmap(&tmQ);
+    ptx::prefetch_tmap(&tmK);
+    ptx::prefetch_tmap(&tmV);
+    ptx::mbar_init(q_full, 1);
+    for (int i = 0; i < KV_STAGES; ++i) {
+      ptx::mbar_init(&k_full[i], 1);
+      ptx::mbar_init(&k_empty[i], 2);   // each tile's issuer commits its own use of the stage
+      ptx::mbar_init(&v_full[i], 1);
+      ptx::mbar_init(&v_empty[i], 2);
+    }
+    for (int i = 0; i < 4; ++i) {
+      ptx::mbar_init(&s_full[i], 1);
+      ptx::mbar_init(&p_full[i], 4);
+    }
+    ptx::mbar_init(&o_done[0], 1);
+    ptx::mbar_init(&o_done[1], 1);
+    ptx::fence_barrier_init();
+  }
+  if (warp == 2) {
+    ptx::tmem_alloc(tmem_ptr, TMEM_COLS);
+    ptx::tmem_relinquish();
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+
+  if (warp < 4) {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
+    if (warp == 0) {
+      if (lane == 0) {
+        // ===================== TMA producer =====================
+        ptx::mbar_expect_tx(q_full, 2 * TILE_BYTES);
+        ptx::tma_load_3d(sQ, &tmQ, q_full, head * DH, q_pair * 2 * BQ, b);
+        ptx::tma_load_3d(sQ + TILE_BYTES, &tmQ, q_full, head * DH, q_pair * 2 * BQ + BQ, b);
+        for (int j = 0; j < n_tiles; ++j) {
+          const int st = j % KV_STAGES;
+          const uint32_t ph = (j / KV_STAGES) & 1;
+          ptx::mbar_wait(&k_empty[st], ph ^ 1);
+          ptx::mbar_expect_tx(&k_full[st], KV_BYTES);
+          ptx::tma_load_3d(sK + st * KV_BYTES, &tmK, &k_full[st], head * DH, j * BKV, b);
+          ptx::mbar_wait(&v_empty[st], ph ^ 1);
+          ptx::mbar_expect_tx(&v_full[st], KV_BYTES);
+          ptx::tma_load_3d(sV + st * KV_BYTES, &tmV, &v_full[st], head * DH, j * BKV, b);
+        }
+      }
+    } else if (warp == 1 || warp == 3) {
+      // ===================== MMA issuer of query tile t (whole warp runs the loop; one elected lane issues) ==========
+      const int t = warp == 3 ? 1 : 0;
+      constexpr uint32_t idesc_qk = ptx::make_idesc_bf16(BQ, BKV, 0, 0);
+      constexpr uint32_t idesc_pv = ptx::make_idesc_bf16(BQ, DH, 0, 1);
+      const uint64_t qdesc = ptx::make_sdesc_sw128(ptx::smem_u32(sQ + t * TILE_BYTES));
+      const uint64_t kdesc_base = ptx::make_sdesc_sw128(ptx::smem_u32(sK));
+      const uint64_t vdesc_base = ptx::make_sdesc_sw128(ptx::smem_u32(sV));
+      const uint32_t tS0 = tmem_base + (2 * t) * BKV;
+      const uint32_t tO = tmem_base + COL_O + t * 64;
+      T_DECL;
+
+      auto issue_qk = [&](int j) {   // S(t, j&1) = Q_t K_j^T
+        const int st = j % KV_STAGES, buf = j & 1;
+        T_MARK(9);
+        ptx::mbar_wait(&k_full[st], (j / KV_STAGES) & 1);
+        ptx::tc_fence_after();
+        T_MARK(4);
+        const uint64_t kdesc = kdesc_base + (uint64_t)(st * (KV_BYTES >> 4));
+        if (ptx::elect_one()) {
+#pragma unroll
+          for (int k = 0; k < DH / 16; ++k)
+            ptx::mma_ss(tS0 + buf * BKV, qdesc + 2 * k, kdesc + 2 * k, idesc_qk, k != 0);
+          ptx::tc_commit(&s_full[2 * t + buf]);
+          ptx::tc_commit(&k_empty[st]);
+        }
+        __syncwarp();
+        T_MARK(5);
+      };
+
+      ptx::mbar_wait(q_full, 0);
+      issue_qk(0);
+      if (n_tiles > 1) issue_qk(1);
+      for (int j = 0; j < n_tiles; ++j) {
+        const int st = j % KV_STAGES, buf = j & 1;
+        T_MARK(9);
+        ptx::mbar_wait(&v_full[st], (j / KV_STAGES) & 1);
+        T_MARK(1);
+        ptx::mbar_wait(&p_full[2 * t + buf], (j >> 1) & 1);   // P_j is in the buffer (and O rescaled if needed)
+        ptx::tc_fence_after();
+        T_MARK(2);
+        const uint64_t vdesc = vdesc_base + (uint64_t)(st * (KV_BYTES >> 4));
+        if (ptx::elect_one()) {
+#pragma unroll
+          for (int k = 0; k < BKV / 16; ++k)   // O_t += P V_j: A = P from TMEM (8 columns per 16 keys), B = V MN-major
+            ptx::mma_ts(tO, tS0 + buf * BKV + 8 * k, vdesc + (uint64_t)(128 * k), idesc_pv, (j | k) != 0);
+          ptx::tc_commit(&o_done[t]);
+          ptx::tc_commit(&v_empty[st]);
+        }
+        __syncwarp();
+        T_MARK(3);
+        if (j + 2 < n_tiles) issue_qk(j + 2);   // into the buffer P_j just left (ordered behind P V_j in the tensor pipe)
+      }
+      T_FLUSH();
+    }
+  } else {
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 232;");
+    // ===================== softmax warpgroups (thread = one query row = one TMEM lane) =====================
+    const int t = (warp - 4) >> 2;   // query tile of this warpgroup
+    const int q = warp & 3;          // TMEM lane quarter
+    const uint32_t lane_off = (uint32_t)(q * 32) << 16;
+    const uint32_t tS0 = tmem_base + (2 * t) * BKV + lane_off;
+    const uint32_t tO = tmem_base + COL_O + t * 64 + lane_off;
+    const float sl2 = args.scale_log2;
+    float m_run = -INFINITY;   // the max the running sums are scaled with (raw score units; online form only)
+    float l_run = 0.f;
+    T_DECL;
+    auto tile_step = [&](int j, auto masked) {
+      const int buf = j & 1;
+      const uint32_t tS = tS0 + buf * BKV;
+      T_MARK(9);
+      ptx::mbar_wait(&s_full[2 * t + buf], (j >> 1) & 1);
+      ptx::tc_fence_after();
+      T_MARK(1);
+      uint32_t v[BKV];
+#pragma unroll
+      for (int c = 0; c < BKV / 32; ++c) ptx::tmem_ld32(tS + c * 32, *reinterpret_cast<uint32_t(*)[32]>(&v[c * 32]));
+      ptx::tmem_wait_ld();
+      T_MARK(2);
+      if constexpr (decltype(masked)::value) {   // only the last KV tile can be ragged
+        const int kv_left = args.seq_kv - j * BKV;
+#pragma unroll
+        for (int i = 0; i < BKV; ++i)
+          if (i >= kv_left) v[i] = 0xff800000u;   // -inf
+      }
+      float alpha = 1.0f;
+      bool grow = false;
+      if constexpr (!PRESCALED) {
+        float mxa[8];   // 8 independent max chains, then a small tree
+#pragma unroll
+        for (int a = 0; a < 8; ++a) mxa[a] = __uint_as_float(v[a]);
+#pragma unroll
+        for (int i = 8; i < BKV; i += 8)
+#pragma unroll
+          for (int a = 0; a < 8; ++a) mxa[a] = fmaxf(mxa[a], __uint_as_float(v[i + a]));
+        const float mx = fmaxf(fmaxf(fmaxf(mxa[0], mxa[1]), fmaxf(mxa[2], mxa[3])),
+                               fmaxf(fmaxf(mxa[4], mxa[5]), fmaxf(mxa[6], mxa[7])));
+        // lazy rescale: keep the old reference max unless the new one exceeds it by more than the threshold
+        grow = (mx - m_run) * sl2 > RESCALE_THRESHOLD;   // true on the first tile (m_run = -inf)
+        if (grow) {
+          alpha = ptx::ex2((m_run - mx) * sl2);
+          m_run = mx;
+        }
+      }
+      const float neg_m = -m_run * sl2;   // (unused when PRESCALED)
+      uint64_t rs2[4];                    // independent packed partial row sums
+#pragma unroll
+      for (int a = 0; a < 4; ++a) rs2[a] = ptx::pack2(0.f, 0.f);
+      const uint64_t sl2_2 = ptx::pack2(sl2, sl2), negm_2 = ptx::pack2(neg_m, neg_m);
+      uint32_t pk[BKV / 2];
+#pragma unroll
+      for (int i = 0; i < BKV / 2; ++i) {
+        uint64_t x2 = ptx::pack2(__uint_as_float(v[2 * i]), __uint_as_float(v[2 * i + 1]));
+        if constexpr (!PRESCALED) x2 = ptx::fma2(x2, sl2_2, negm_2);
+        float p0, p1;
+        if (!decltype(masked)::value && (i & 7) < POLY8) {
+          v2::exp2_poly2<!PRESCALED>(x2, p0, p1);
+        } else {
+          float xa, xb;
+          ptx::unpack2(x2, xa, xb);
+          p0 = ptx::ex2(xa);
+          p1 = ptx::ex2(xb);
+        }
+        rs2[i & 3] = ptx::add2(rs2[i & 3], ptx::pack2(p0, p1));
+        pk[i] = ptx::pack_bf16(p0, p1);
+      }
+      float ra, rb, rc, rd;
+      ptx::unpack2(ptx::add2(rs2[0], rs2[1]), ra, rb);
+      ptx::unpack2(ptx::add2(rs2[2], rs2[3]), rc, rd);
+      const float rsum = (ra + rb) + (rc + rd);
+#ifdef DIT4SR_ATTN_TIMING
+      asm volatile("" ::"f"(rsum), "r"(pk[0]), "r"(pk[BKV / 2 - 1]) : "memory");
+#endif
+      T_MARK(3);
+      // O_t may only be touched between P V(j-1) completing and P V(j) being issued (it is issued after our arrive)
+      if (!PRESCALED && j > 0 && __any_sync(0xffffffffu, grow)) {
+        ptx::mbar_wait(&o_done[t], (j - 1) & 1);
+        ptx::tc_fence_after();
+#pragma unroll 1
+        for (int c = 0; c < DH / 32; ++c) {
+          uint32_t o[32];
+          ptx::tmem_ld32(tO + c * 32, o);
+          ptx::tmem_wait_ld();
+#pragma unroll
+          for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
+          ptx::tmem_st32(tO + c * 32, o);
+        }
+      }
+      T_MARK(5);
+      // P overwrites the first 48 columns of the score buffer (the whole row is already in registers)
+#pragma unroll
+      for (int c = 0; c < BKV / 32; ++c) ptx::tmem_st16(tS + c * 16, &pk[c * 16]);
+      l_run = l_run * alpha + rsum;
+      ptx::tmem_wait_st();
+      T_MARK(6);
+      ptx::tc_fence_before();
+      __syncwarp();
+      if (lane == 0) ptx::mbar_arrive(&p_full[2 * t + buf]);
+      T_MARK(7);
+    };
+    const bool ragged = (args.seq_kv % BKV) != 0;
+    for (int j = 0; j + 1 < n_tiles; ++j) tile_step(j, std::false_type{});
+    if (ragged) tile_step(n_tiles - 1, std::true_type{});
+    else tile_step(n_tiles - 1, std::false_type{});
+    T_FLUSH();
+
+    // epilogue: O / l (+ LR residual) -> bf16 global
+    ptx::mbar_wait(&o_done[t], (n_tiles - 1) & 1);
+    ptx::tc_fence_after();
+    const int row = (q_pair * 2 + t) * BQ + q * 32 + lane;
+    store_rows(args, tO, row, head, b, 1.0f / l_run);
+  }
+
+  __syncwarp();
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    ptx::tc_fence_after();
+    ptx::tmem_dealloc(tmem_base, TMEM_COLS);
+  }
+}
+
+}  // namespace v3
+
 }  // namespace attn
+
+#ifdef DIT4SR_ATTN_TIMING
+extern "C" int dit4sr_attn_timing_read(long long* host_out /* [12*16] */) {
+  DIT4SR_CUDA(cudaDeviceSynchronize());
+  DIT4SR_CUDA(cudaMemcpyFromSymbol(host_out, attn::v2::g_attn_timing, sizeof(long long) * 12 * 16));
+  return 0;
+}
+#endif
 
 extern "C" int dit4sr_attn_fwd(const dit4sr_attn_params* p, void* stream_) {
   using namespace attn;
@@ -410,18 +744,21 @@ extern "C" int dit4sr_attn_fwd(const dit4sr_attn_params* p, void* stream_) {
                  "attn: DIT4SR_ATTN_PRESCALED needs 0 < score_bound <= %g (log2 units), got %g",
                  (double)DIT4SR_ATTN_MAX_SCORE_BOUND, (double)p->score_bound);
   DIT4SR_REQUIRE(p->exp_offload >= 0 && p->exp_offload <= 3, DIT4SR_E_BADARG, "attn: exp_offload must be 0..3");
+  DIT4SR_REQUIRE(p->variant == 0 || p->variant == 2 || p->variant == 3, DIT4SR_E_BADARG, "attn: variant must be 0, 2 or 3");
 
   int rc = dit4sr_check_device();
   if (rc != 0) return rc;
 
+  const int variant = p->variant == 0 ? 3 : p->variant;
+  const int bkv = variant == 3 ? v3::BKV : BKV;
   CUtensorMap tmQ, tmK, tmV;
   const uint64_t dims[3] = {(uint64_t)p->heads * DH, (uint64_t)p->seq_kv, (uint64_t)p->batches};
   const uint64_t strides[2] = {(uint64_t)p->qkv_row_stride * 2,
                                (uint64_t)(p->batches > 1 ? p->qkv_batch_stride : p->qkv_row_stride * p->seq_kv) * 2};
-  const uint32_t box[3] = {DH, 128, 1};
+  const uint32_t box[3] = {DH, 128, 1}, box_kv[3] = {DH, (uint32_t)bkv, 1};
   if ((rc = host::make_tmap_bf16(&tmQ, p->q, 3, dims, strides, box)) != 0) return rc;
-  if ((rc = host::make_tmap_bf16(&tmK, p->k, 3, dims, strides, box)) != 0) return rc;
-  if ((rc = host::make_tmap_bf16(&tmV, p->v, 3, dims, strides, box)) != 0) return rc;
+  if ((rc = host::make_tmap_bf16(&tmK, p->k, 3, dims, strides, box_kv)) != 0) return rc;
+  if ((rc = host::make_tmap_bf16(&tmV, p->v, 3, dims, strides, box_kv)) != 0) return rc;
 
   Args a;
   a.o = reinterpret_cast<__nv_bfloat16*>(p->o);
@@ -434,22 +771,26 @@ extern "C" int dit4sr_attn_fwd(const dit4sr_attn_params* p, void* stream_) {
   a.lr_row_end = p->lr_row_end;
   a.seq_q = p->seq_q;
   a.seq_kv = p->seq_kv;
-  a.n_kv_tiles = (p->seq_kv + BKV - 1) / BKV;
+  a.n_kv_tiles = (p->seq_kv + bkv - 1) / bkv;
   a.scale_log2 = p->scale * 1.4426950408889634f;
 
-  // instance = (softmax form, share of the exponentials evaluated on the FMA pipe); exp_offload 0 = the default 2/8
+  // instance = (kernel, softmax form, share of the exponentials evaluated on the FMA pipe; exp_offload 0 = default 2/8)
   using KernelFn = void (*)(const CUtensorMap, const CUtensorMap, const CUtensorMap, const Args);
-  static const KernelFn table[2][3] = {
-      {v2::attn_fwd2_kernel<0, false>, v2::attn_fwd2_kernel<2, false>, v2::attn_fwd2_kernel<4, false>},
-      {v2::attn_fwd2_kernel<0, true>, v2::attn_fwd2_kernel<2, true>, v2::attn_fwd2_kernel<4, true>}};
+  static const KernelFn table[2][2][3] = {
+      {{v2::attn_fwd2_kernel<0, false>, v2::attn_fwd2_kernel<2, false>, v2::attn_fwd2_kernel<4, false>},
+       {v2::attn_fwd2_kernel<0, true>, v2::attn_fwd2_kernel<2, true>, v2::attn_fwd2_kernel<4, true>}},
+      {{v3::attn_fwd3_kernel<0, false>, v3::attn_fwd3_kernel<2, false>, v3::attn_fwd3_kernel<4, false>},
+       {v3::attn_fwd3_kernel<0, true>, v3::attn_fwd3_kernel<2, true>, v3::attn_fwd3_kernel<4, true>}}};
   const int po = p->exp_offload == 0 ? 1 : p->exp_offload - 1;
-  const KernelFn fn = table[prescaled ? 1 : 0][po];
+  const int vi = variant == 3 ? 1 : 0, mi = prescaled ? 1 : 0;
+  const KernelFn fn = table[vi][mi][po];
+  const int smem = variant == 3 ? v3::SMEM_BYTES : v2::SMEM_BYTES;
   // the opt-in to > 48 KB of dynamic shared memory is per (function, device): remember which pairs are done
-  static unsigned long long configured[2][3] = {};
-  if (host::first_use_on_device(&configured[prescaled ? 1 : 0][po]))
-    DIT4SR_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, v2::SMEM_BYTES));
+  static unsigned long long configured[2][2][3] = {};
+  if (host::first_use_on_device(&configured[vi][mi][po]))
+    DIT4SR_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
   dim3 grid((p->seq_q + 2 * BQ - 1) / (2 * BQ), p->heads, p->batches);
-  fn<<<grid, v2::NUM_THREADS, v2::SMEM_BYTES, stream>>>(tmQ, tmK, tmV, a);
+  fn<<<grid, 384, smem, stream>>>(tmQ, tmK, tmV, a);
   DIT4SR_CUDA(cudaGetLastError());
   return 0;
 }

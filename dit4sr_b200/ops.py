@@ -195,7 +195,7 @@ ATTN_ONLINE, ATTN_PRESCALED = 0, 1
 ATTN_MAX_SCORE_BOUND = 60.0
 
 
-def attention(q, k, v, o, heads, seq_q=None, scale=None, lr_res=None, lr_rows=(0, 0), score_bound=None, exp_offload=0):
+def attention(q, k, v, o, heads, seq_q=None, scale=None, lr_res=None, lr_rows=(0, 0), score_bound=None, exp_offload=0, variant=0):
     """o = softmax(q k^T * scale) v over [B, S, heads*64] bf16 views (row stride may be 3*heads*64 for a fused buffer).
 
     Only the first seq_q query rows are produced. lr_res (bf16 [B, >=lr_rows[1], heads*64]) is added to rows lr_rows.
@@ -221,7 +221,7 @@ def attention(q, k, v, o, heads, seq_q=None, scale=None, lr_res=None, lr_rows=(0
     p.scale = (1.0 / 8.0) if scale is None else scale
     if score_bound is not None:
         p.mode, p.score_bound = ATTN_PRESCALED, float(score_bound)
-    p.exp_offload = exp_offload
+    p.exp_offload, p.variant = exp_offload, variant
     check(_lib.load().dit4sr_attn_fwd(C.byref(p), _stream()), "dit4sr_attn_fwd")
     _count()
 

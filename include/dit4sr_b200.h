@@ -153,6 +153,8 @@ int dit4sr_gemm_schedule(const dit4sr_gemm_params* problems, int count, int sm_c
  *                          from the checkpoint's norm weights; the host refuses the mode when it does not hold.
  * exp_offload: 0 = default; 1, 2, 3 = 0/8, 2/8, 4/8 of the exponentials evaluated by a polynomial on the FMA pipe instead
  *              of MUFU.EX2 (tuning knob: same results to within bf16 rounding of P).
+ * variant:     0 = default; 3 = independent query tiles with double-buffered 96-key score tiles (the default);
+ *              2 = three 128-key score buffers rotating over the two query tiles (round 1's pipeline, kept for A/B).
  */
 enum { DIT4SR_ATTN_ONLINE = 0, DIT4SR_ATTN_PRESCALED = 1 };
 #define DIT4SR_ATTN_MAX_SCORE_BOUND 60.0f
@@ -164,7 +166,7 @@ typedef struct {
   int lr_row_begin; int lr_row_end;
   int batches; int heads; int seq_q; int seq_kv;
   float scale;
-  int mode; float score_bound; int exp_offload;                          /* ABI v3 */
+  int mode; float score_bound; int exp_offload; int variant;             /* ABI v3 */
 } dit4sr_attn_params;
 int dit4sr_attn_fwd(const dit4sr_attn_params* p, void* stream);
 

@@ -45,6 +45,7 @@ def main():
     ap.add_argument("what")
     ap.add_argument("--reps", type=int, default=20)
     ap.add_argument("--shape", default="c2")
+    ap.add_argument("--variant", type=int, default=0, help="attn: 0 default, 2 rotating buffers, 3 double-buffered 96-key tiles")
     ap.add_argument("--graph", action="store_true")
     ap.add_argument("--prescaled", action="store_true", help="attn: DIT4SR_ATTN_PRESCALED mode (q pre-multiplied)")
     ap.add_argument("--exp-offload", type=int, default=0, help="attn: 0 default, 1/2/3 = 0/8, 2/8, 4/8 polynomial")
@@ -64,10 +65,10 @@ def main():
         o = torch.empty(B, S, D, device=dev, dtype=torch.bfloat16)
         res = torch.randn(B, 2 * N, D, device=dev).bfloat16()
         fn = lambda: ops.attention(qkv[..., :D], qkv[..., D:2 * D], qkv[..., 2 * D:], o, H, lr_res=res, lr_rows=(N, 2 * N),
-                                   score_bound=30.0 if a.prescaled else None, exp_offload=a.exp_offload)
+                                   score_bound=30.0 if a.prescaled else None, exp_offload=a.exp_offload, variant=a.variant)
         ms = timeit(fn, a.reps)
         fl = 4.0 * S * S * D * B
-        print(f"attn B={B} S={S} prescaled={a.prescaled} exp_offload={a.exp_offload}: {ms:.4f} ms  {fl / ms / 1e9:.1f} TFLOP/s")
+        print(f"attn B={B} S={S} prescaled={a.prescaled} exp_offload={a.exp_offload} variant={a.variant}: {ms:.4f} ms  {fl / ms / 1e9:.1f} TFLOP/s")
     elif a.what == "gemm":
         for name, M, K, Nn, epi in [("ff1", B * 2 * N, D, F, ops.EPI_BIAS_GELU), ("ff2", B * 2 * N, F, D, ops.EPI_GATE_RESID),
                                     ("qkv", B * N, D, 3 * D, ops.EPI_QKV_NORM), ("out", B * N, D, D, ops.EPI_GATE_RESID)]:
