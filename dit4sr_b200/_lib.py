@@ -34,13 +34,39 @@ class GemmParams(C.Structure):
                 ("dbl_row_offset", c_i64)]
 
 
+SP_MAX_RANKS, SP_CHANNELS = 8, 4
+SP_CH_QKV, SP_CH_OUT, SP_CH_HALO, SP_CH_USER = 0, 1, 2, 3
+
+
+class AttnSpOut(C.Structure):
+    _fields_ = [("world", c_int), ("rows_per_rank", c_int), ("col_offset", c_int), ("o_peer", c_vp * SP_MAX_RANKS)]
+
+
+class SpComm(C.Structure):
+    _fields_ = [("world", c_int), ("rank", c_int), ("flags", c_vp * SP_MAX_RANKS), ("epoch", c_vp)]
+
+
+class A2aParams(C.Structure):
+    _fields_ = [("src", c_vp), ("src_row_stride", c_i64), ("src_batch_stride", c_i64), ("peer", c_vp * SP_MAX_RANKS),
+                ("dst_row_stride", c_i64), ("dst_batch_stride", c_i64),
+                ("batches", c_int), ("image_rows", c_int), ("text_rows", c_int), ("heads", c_int), ("no_barrier", c_int)]
+
+
+class HaloParams(C.Structure):
+    _fields_ = [("peer", c_vp * SP_MAX_RANKS), ("row_stride", c_i64), ("batch_stride", c_i64),
+                ("batches", c_int), ("channels", c_int), ("grid_w", c_int),
+                ("first_lr_row", c_i64), ("lr_rows", c_i64), ("top_halo_row", c_i64), ("bottom_halo_row", c_i64),
+                ("no_barrier", c_int)]
+
+
 class AttnParams(C.Structure):
     _fields_ = [("q", c_vp), ("k", c_vp), ("v", c_vp), ("qkv_row_stride", c_i64), ("qkv_batch_stride", c_i64),
                 ("o", c_vp), ("o_row_stride", c_i64), ("o_batch_stride", c_i64),
                 ("lr_res", c_vp), ("lr_row_stride", c_i64), ("lr_batch_stride", c_i64),
                 ("lr_row_begin", c_int), ("lr_row_end", c_int),
                 ("batches", c_int), ("heads", c_int), ("seq_q", c_int), ("seq_kv", c_int), ("scale", c_float),
-                ("mode", c_int), ("score_bound", c_float), ("exp_offload", c_int), ("variant", c_int)]
+                ("mode", c_int), ("score_bound", c_float), ("exp_offload", c_int), ("variant", c_int),
+                ("sp_out", C.POINTER(AttnSpOut))]
 
 
 # every symbol include/dit4sr_b200.h declares: name -> (restype, argtypes)
@@ -73,6 +99,15 @@ SYMBOLS = {
     "dit4sr_plane_stats_f32": (c_int, [c_vp, c_int, c_i64, c_vp, c_vp, c_vp]),
     "dit4sr_adain_apply_f32": (c_int, [c_vp, c_vp, c_int, c_i64, c_vp, c_vp, c_vp, c_vp, c_float, c_vp]),
     "dit4sr_cast": (c_int, [c_vp, c_vp, c_i64, c_int, c_vp]),
+    "dit4sr_peer_alloc": (c_int, [C.c_size_t, C.POINTER(c_vp)]),
+    "dit4sr_peer_free": (c_int, [c_vp]),
+    "dit4sr_peer_export": (c_int, [c_vp, C.c_char_p]),
+    "dit4sr_peer_open": (c_int, [C.c_char_p, C.POINTER(c_vp)]),
+    "dit4sr_peer_close": (c_int, [c_vp]),
+    "dit4sr_sp_barrier": (c_int, [C.POINTER(SpComm), c_int, c_vp]),
+    "dit4sr_a2a_qkv": (c_int, [C.POINTER(SpComm), C.POINTER(A2aParams), c_vp]),
+    "dit4sr_a2a_out": (c_int, [C.POINTER(SpComm), C.POINTER(A2aParams), c_vp]),
+    "dit4sr_halo_rows": (c_int, [C.POINTER(SpComm), C.POINTER(HaloParams), c_vp]),
 }
 
 _lib = None

@@ -23,6 +23,9 @@ struct Args {
   int lr_row_begin, lr_row_end;
   int seq_q, seq_kv, n_kv_tiles;
   float scale_log2;  // scale * log2(e)  (unused by the pre-scaled instances)
+  // sequence parallelism (sp_world > 0): rows are scattered to the owning ranks' buffers over NVLink (header: sp_out)
+  int sp_world, sp_rows_per_rank, sp_col_offset;
+  __nv_bfloat16* o_peer[DIT4SR_SP_MAX_RANKS];
 };
 
 // Epilogue of one softmax thread: its row of O (64 fp32 TMEM columns at tO) / l (+ LR residual, attention.py:545) -> bf16.
@@ -53,16 +56,32 @@ __device__ __forceinline__ void store_rows(const Args& args, uint32_t tO, int ro
           }
         }
       }
-      uint4* dst = reinterpret_cast<uint4*>(args.o + (int64_t)b * args.o_batch_stride +
-                                            (int64_t)row * args.o_row_stride + head * DH + c * 32);
+      uint4 u[4];
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
-        uint4 u;
-        u.x = ptx::pack_bf16(f[8 * i + 0], f[8 * i + 1]);
-        u.y = ptx::pack_bf16(f[8 * i + 2], f[8 * i + 3]);
-        u.z = ptx::pack_bf16(f[8 * i + 4], f[8 * i + 5]);
-        u.w = ptx::pack_bf16(f[8 * i + 6], f[8 * i + 7]);
-        dst[i] = u;
+        u[i].x = ptx::pack_bf16(f[8 * i + 0], f[8 * i + 1]);
+        u[i].y = ptx::pack_bf16(f[8 * i + 2], f[8 * i + 3]);
+        u[i].z = ptx::pack_bf16(f[8 * i + 4], f[8 * i + 5]);
+        u[i].w = ptx::pack_bf16(f[8 * i + 6], f[8 * i + 7]);
+      }
+      if (args.sp_world == 0) {
+        uint4* dst = reinterpret_cast<uint4*>(args.o + (int64_t)b * args.o_batch_stride +
+                                              (int64_t)row * args.o_row_stride + head * DH + c * 32);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) dst[i] = u[i];
+      } else {
+        // head -> sequence all-to-all fused into the epilogue: the row goes to the rank that owns its token (text rows:
+        // to every rank), 64-byte stores straight into the peer's buffer over NVLink
+        const int owner = row / args.sp_rows_per_rank;
+        const bool text = owner >= args.sp_world;
+        const int64_t drow = text ? row - (int64_t)(args.sp_world - 1) * args.sp_rows_per_rank
+                                  : row - (int64_t)owner * args.sp_rows_per_rank;
+        const int64_t off = (int64_t)b * args.o_batch_stride + drow * args.o_row_stride + args.sp_col_offset + head * DH + c * 32;
+        for (int r = text ? 0 : owner; r < (text ? args.sp_world : owner + 1); ++r) {
+          uint4* dst = reinterpret_cast<uint4*>(args.o_peer[r] + off);
+#pragma unroll
+          for (int i = 0; i < 4; ++i) dst[i] = u[i];
+        }
       }
     }
   }
@@ -738,6 +757,16 @@ extern "C" int dit4sr_attn_fwd(const dit4sr_attn_params* p, void* stream_) {
                        p->lr_row_begin >= 0 && p->lr_row_end >= p->lr_row_begin,
                    DIT4SR_E_ALIGN, "attn: bad lr_res arguments");
   }
+  if (p->sp_out != nullptr) {
+    const dit4sr_attn_sp_out* so = p->sp_out;
+    DIT4SR_REQUIRE(so->world >= 1 && so->world <= DIT4SR_SP_MAX_RANKS && so->rows_per_rank > 0 && so->col_offset >= 0 &&
+                       so->col_offset % 8 == 0 && p->lr_res == nullptr,
+                   DIT4SR_E_BADARG, "attn: bad sp_out (world %d rows_per_rank %d; lr_res must be NULL)", so->world,
+                   so->rows_per_rank);
+    for (int r = 0; r < so->world; ++r)
+      DIT4SR_REQUIRE(so->o_peer[r] != nullptr && host::aligned16(so->o_peer[r]), DIT4SR_E_BADARG,
+                     "attn: sp_out.o_peer[%d] missing or misaligned", r);
+  }
   const bool prescaled = p->mode == DIT4SR_ATTN_PRESCALED;
   DIT4SR_REQUIRE(p->mode == DIT4SR_ATTN_ONLINE || prescaled, DIT4SR_E_BADARG, "attn: unknown mode %d", p->mode);
   DIT4SR_REQUIRE(!prescaled || (p->score_bound > 0.f && p->score_bound <= DIT4SR_ATTN_MAX_SCORE_BOUND), DIT4SR_E_BADARG,
@@ -773,6 +802,17 @@ extern "C" int dit4sr_attn_fwd(const dit4sr_attn_params* p, void* stream_) {
   a.seq_kv = p->seq_kv;
   a.n_kv_tiles = (p->seq_kv + bkv - 1) / bkv;
   a.scale_log2 = p->scale * 1.4426950408889634f;
+  a.sp_world = 0;
+  a.sp_rows_per_rank = 1;
+  a.sp_col_offset = 0;
+  for (int r = 0; r < DIT4SR_SP_MAX_RANKS; ++r) a.o_peer[r] = nullptr;
+  if (p->sp_out != nullptr) {
+    const dit4sr_attn_sp_out* so = p->sp_out;
+    a.sp_world = so->world;
+    a.sp_rows_per_rank = so->rows_per_rank;
+    a.sp_col_offset = so->col_offset;
+    for (int r = 0; r < so->world; ++r) a.o_peer[r] = reinterpret_cast<__nv_bfloat16*>(so->o_peer[r]);
+  }
 
   // instance = (kernel, softmax form, share of the exponentials evaluated on the FMA pipe; exp_offload 0 = default 2/8)
   using KernelFn = void (*)(const CUtensorMap, const CUtensorMap, const CUtensorMap, const Args);

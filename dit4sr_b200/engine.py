@@ -237,8 +237,9 @@ class Engine:
         self._graphs: Dict[Tuple, tuple] = {}
         import os as _os
         self.use_cuda_graph = _os.environ.get("DIT4SR_CUDA_GRAPH", "1") != "0"
-        # capturing the sequence-parallel step (NCCL collectives inside the graph) hung on 2 GPUs in round 1: opt-in only
-        self.sp_graph = _os.environ.get("DIT4SR_SP_GRAPH", "0") == "1"
+        # capturing NCCL collectives inside the graph hung on 2 GPUs in round 1: the torch.distributed path launches
+        # directly; the NVLink peer-memory path consists of this library's kernels only and is captured
+        self.sp_graph = _os.environ.get("DIT4SR_SP_GRAPH", "1" if (sp is not None and sp.peer) else "0") == "1"
         self._pos: Dict[Tuple, torch.Tensor] = {}
 
     # ------------------------------------------------------------------------------------------------ profiling
@@ -303,11 +304,23 @@ class Engine:
             patches=e(B, N, 4 * self.cfg.in_channels), tok=e(B, N, 4 * self.cfg.out_channels, dtype=f32),
             t=e(B, dtype=f32),
         )
-        if self.sp is not None:   # attention-side buffers of the head<->sequence exchange + halo-padded LR hidden state
+        if self.sp is not None and not self.sp.peer:
+            # attention-side buffers of the head<->sequence exchange + halo-padded LR hidden state (torch.distributed path)
             P = self.sp.world
             Dl = D // P
             ws.update(qkv_sp=e(B, P * I + T, 3, Dl), o_sp=e(B, P * I + T, Dl),
                       lr_pad=e(B, N + 2 * grid_w, F))
+        elif self.sp is not None:
+            # NVLink peer-memory path: the buffers the PEERS write into are peer-mapped allocations (collective set-up:
+            # every rank builds the same workspaces in the same order).  q|k|v land on the attention side, attention
+            # outputs come back into `o`, and the MLP hidden state carries one halo grid row above and below its LR rows:
+            #   u rows: [0,N) HQ | [N,N+gw) halo above | [N+gw, 2N+gw) LR | [2N+gw, 2N+2gw) halo below
+            sp, P = self.sp, self.sp.world
+            Dl = D // P
+            ws["qkv_sp"], ws["qkv_sp_peers"] = sp.shared_empty((B * (P * I + T) * 3 * Dl,))
+            ws["o"], ws["o_peers"] = sp.shared_empty((B, S, D))
+            ws["u"], ws["u_peers"] = sp.shared_empty((B, I + 2 * grid_w, F))
+            ws["sp_out"] = ops.attn_sp_out(P, I, sp.rank * Dl, ws["o_peers"])
         self._ws[key] = ws
         return ws
 
@@ -439,9 +452,21 @@ class Engine:
         P = sp.world
         Hl = H // P
         Dl = Hl * 64
-        qkv, o, qs, os_ = ws["qkv"], ws["o"], ws["qkv_sp"], ws["o_sp"]
+        qkv, o = ws["qkv"], ws["o"]
         B = qkv.shape[0]
         T = S - I
+        if sp.peer:
+            # one scatter kernel + arrival barrier, attention with the way back fused into its epilogue, arrival barrier
+            Ssp = P * I + T
+            qs = ws["qkv_sp"][:B * Ssp * 3 * Dl].view(B, Ssp, 3, Dl)
+            R("a2a", ops.a2a_qkv, sp.comm, qkv[:, :S], I, T, H, ws["qkv_sp_peers"])
+            seq_q = P * I if (last or not T) else Ssp
+            R("attn", ops.attention, qs[:, :, 0], qs[:, :, 1], qs[:, :, 2], o, Hl, seq_q=seq_q,
+              score_bound=ap.score_bound, sp_out=ws["sp_out"])
+            R("a2a", ops.a2a_out, sp.comm, None, I, T, H, ws["o_peers"], o.stride(1), o.stride(0))
+            R("attn", ops.add_bf16, o[:, N:I], n_in[:, N:I])                # Q2 residual on the LR rows
+            return
+        qs, os_ = ws["qkv_sp"], ws["o_sp"]
         xs = sp.seq_to_heads(qkv[:, :I].reshape(B, I, 3, H, 64))           # [B, P*I, 3, Hl, 64] rank-major tokens
         qs[:, :P * I] = xs.reshape(B, P * I, 3, Dl)
         if T:
@@ -463,6 +488,10 @@ class Engine:
             self._run("dwconv", ops.dwconv3x3_add_f32, dst, src, w9, b, rows, grid_w=grid_w)
         elif self.sp is None:
             self._run("dwconv", ops.dwconv3x3_add, dst, src, w9, b, rows, grid_w=grid_w)
+        elif self.sp.peer:   # the neighbours store their boundary rows straight into this rank's halo rows of u
+            u, N = ws["u"], dst.shape[1]
+            self._run("halo", ops.halo_rows, self.sp.comm, u, ws["u_peers"], grid_w, N + grid_w, N, N, 2 * N + grid_w)
+            self._run("dwconv", ops.dwconv3x3_add, dst, u[:, N:], w9, b, rows, grid_w=grid_w, lr_row_offset=1)
         else:
             padded = self.sp.halo_rows(src, grid_w, out=ws["lr_pad"])
             self._run("dwconv", ops.dwconv3x3_add, dst, padded, w9, b, rows, grid_w=grid_w, lr_row_offset=1)
@@ -470,16 +499,29 @@ class Engine:
     # ------------------------------------------------------------------------------------------------ CUDA graph
     @torch.no_grad()
     def step(self, hidden_states, controlnet_image, encoder_hidden_states, pooled_projections, timestep,
-             out=None, euler: Optional[Tuple[torch.Tensor, float]] = None):
+             out=None, euler: Optional[Tuple[torch.Tensor, float]] = None, sharded_io: bool = False):
         """One denoiser call, replayed from a captured CUDA graph when possible (the ~300 kernel launches of a step are
         recorded once per input shape; replay removes the per-launch host cost, which matters for small batches).
-        Same results as `forward` -- the same kernels run. Falls back to direct launches under sequence parallelism,
-        while profiling, or if capture is unavailable."""
-        # sequence parallelism runs with direct launches unless DIT4SR_SP_GRAPH=1 (experimental)
+        Same results as `forward` -- the same kernels run. Falls back to direct launches while profiling, if capture is
+        unavailable, and under sequence parallelism over torch.distributed (the NVLink peer-memory path is captured).
+
+        sharded_io (sequence parallelism): the image tensors are this rank's row strips [B, C, 2*grid/P, W] and so is the
+        result - a sampling loop keeps its latents sharded and gathers once at the end (sampler.denoise)."""
+        if self.sp is not None and not sharded_io:
+            # whole images in, whole image out: cut my strip, run the sharded step, gather the strips (outside any graph)
+            g0, g1 = self.sp.row_slice(hidden_states.shape[2] // 2)
+            loc = lambda t: t[:, :, 2 * g0:2 * g1].contiguous()
+            res = self.step(loc(hidden_states), loc(controlnet_image), encoder_hidden_states, pooled_projections, timestep,
+                            euler=None if euler is None else (loc(euler[0]), euler[1]), sharded_io=True)
+            gathered = self.sp.gather_rows(res, dim=2)
+            if out is not None:
+                out.copy_(gathered)
+                return out
+            return gathered
         if (not self.use_cuda_graph or self._prof is not None or self.precise
                 or (self.sp is not None and not self.sp_graph)):
             return self.forward(hidden_states, controlnet_image, encoder_hidden_states, pooled_projections, timestep,
-                                out=out, euler=euler)
+                                out=out, euler=euler, sharded_io=sharded_io)
         B = hidden_states.shape[0]
         key = (tuple(hidden_states.shape), hidden_states.dtype, tuple(encoder_hidden_states.shape),
                encoder_hidden_states.dtype, pooled_projections.dtype, str(hidden_states.device))
@@ -489,14 +531,17 @@ class Engine:
                       enc=encoder_hidden_states.clone().contiguous(), pooled=pooled_projections.clone().contiguous(),
                       t=torch.zeros(B, device=hidden_states.device, dtype=torch.float32))
             try:
-                self.forward(st["hs"], st["ci"], st["enc"], st["pooled"], st["t"])      # warm-up outside capture
+                fw = lambda: self.forward(st["hs"], st["ci"], st["enc"], st["pooled"], st["t"], sharded_io=sharded_io)
+                fw()                                                                    # warm-up outside capture
                 torch.cuda.synchronize()
                 n0 = ops.launch_count()
                 graph = torch.cuda.CUDAGraph()
                 with torch.cuda.graph(graph):
-                    vel = self.forward(st["hs"], st["ci"], st["enc"], st["pooled"], st["t"])
+                    vel = fw()
                 entry = (graph, st, vel, ops.launch_count() - n0)
             except Exception as e:   # capture not possible here: keep launching directly
+                if self.sp is not None:
+                    raise            # the ranks must not diverge (one replaying, another launching directly)
                 import warnings
                 warnings.warn(f"dit4sr_b200: CUDA graph capture failed ({e}); using direct launches")
                 self.use_cuda_graph = False
@@ -512,14 +557,10 @@ class Engine:
         st["t"].copy_(timestep.to(device=st["t"].device, dtype=torch.float32).expand(B))
         graph.replay()
         ops._count(n_launch)
-        if euler is not None and self.sp is not None:   # the graph left the gathered velocity image behind
-            if out is None:
-                out = torch.empty_like(euler[0])
-            ops.euler_update(euler[0].contiguous(), vel.to(euler[0].dtype), out, euler[1])
-            return out
         if euler is not None:        # x_next = x + dsigma * v straight from the velocity tokens the graph left behind
-            h = hidden_states.shape[-1]
-            ws = self._workspace(B, (h // 2) ** 2, encoder_hidden_states.shape[1], hidden_states.device)
+            h, w = hidden_states.shape[-2:]
+            ws = self._workspace(B, (h // 2) * (w // 2), encoder_hidden_states.shape[1], hidden_states.device,
+                                 grid_w=w // 2 if self.sp is not None else 0)
             if out is None:
                 out = torch.empty_like(euler[0])
             ops.unpatchify(ws["tok"], out, latents=euler[0], dsigma=euler[1])
@@ -532,18 +573,19 @@ class Engine:
     # ------------------------------------------------------------------------------------------------ forward
     @torch.no_grad()
     def forward(self, hidden_states, controlnet_image, encoder_hidden_states, pooled_projections, timestep,
-                out=None, euler: Optional[Tuple[torch.Tensor, float]] = None, feat_hook=None):
+                out=None, euler: Optional[Tuple[torch.Tensor, float]] = None, feat_hook=None, sharded_io: bool = False):
         cfg, D, R = self.cfg, self.D, self._run
         B, Cin, h, w = hidden_states.shape
-        if h != w or h % 2:
+        sharded = sharded_io and self.sp is not None   # the image tensors are already this rank's row strips
+        if w % 2 or h % 2 or (not sharded and h != w) or (sharded and h * self.sp.world != w):
             raise ValueError("dit4sr_b200: square, even latents only (reference asserts a square token grid, "
                              "attention.py:169-172)")
-        grid = h // 2
-        rows = grid                     # token-grid rows handled by this rank
+        grid = w // 2
+        rows = h // 2                   # token-grid rows handled by this rank
         pos = self._pos_crop(grid, grid, hidden_states.device)
-        full_out, full_euler = out, euler
+        full_out = out
         if self.sp is not None:         # Ulysses: this rank keeps grid/P contiguous rows of every image stream
-            if self.streams == 3 and any(b.dual for b in self.blocks):
+            if self.streams == 3 and (self.sp.peer or any(b.dual for b in self.blocks)):
                 # Q6: attn2 of the 3-stream model pairs token j of the first 1.5N tokens with token j of the last 1.5N;
                 # under row sharding those partners live on different ranks. BASELINE config #5 is data-parallel.
                 raise NotImplementedError("sequence parallelism is not supported for the OCR-branch model with dual "
@@ -551,13 +593,14 @@ class Engine:
             if self.H % self.sp.world:
                 raise ValueError(f"{self.H} heads do not divide over {self.sp.world} ranks")
             g0, g1 = self.sp.row_slice(grid)
-            rows = g1 - g0
-            hidden_states = hidden_states[:, :, 2 * g0:2 * g1].contiguous()
-            controlnet_image = controlnet_image[:, :, 2 * g0:2 * g1].contiguous()
+            if not sharded:
+                rows = g1 - g0
+                hidden_states = hidden_states[:, :, 2 * g0:2 * g1].contiguous()
+                controlnet_image = controlnet_image[:, :, 2 * g0:2 * g1].contiguous()
+                out = None
+                if euler is not None:
+                    euler = (euler[0][:, :, 2 * g0:2 * g1].contiguous(), euler[1])
             pos = pos[:, g0 * grid:g1 * grid]
-            out = None
-            if euler is not None:
-                euler = (euler[0][:, :, 2 * g0:2 * g1].contiguous(), euler[1])
         N = rows * grid
         if self.streams == 3 and (3 * N) % 2:
             raise ValueError("3-stream model: attn2 halves the 3N image tokens, N must be even")
@@ -618,8 +661,16 @@ class Engine:
                 self._attention(bp.attn2, ws, n2, None, n_seg, T, gate_msa2, None, bp.last)
             # MLP with the LR->HQ depthwise conv (attention.py:322-347, FeedForwardControl :155-178)
             R("ln_mod", ops.ln_modulate, x, shift_mlp, scale_mlp, n1)
-            ff1 = [dict(A=n1, W=bp.ff1.w, bias=bp.ff1.b, out=ws["u"], epilogue=ops.EPI_BIAS_GELU)]
-            ff2 = [dict(A=ws["u"], W=bp.ff2.w, bias=bp.ff2.b, out=x, epilogue=ops.EPI_GATE_RESID, gate=gate_mlp)]
+            if self.sp is not None and self.sp.peer:   # u keeps a halo grid row on either side of its LR rows
+                u_hq, u_lr = ws["u"][:, :N], ws["u"][:, N + grid:2 * N + grid]
+                ff1 = [dict(A=n1[:, :N], W=bp.ff1.w, bias=bp.ff1.b, out=u_hq, epilogue=ops.EPI_BIAS_GELU),
+                       dict(A=n1[:, N:], W=bp.ff1.w, bias=bp.ff1.b, out=u_lr, epilogue=ops.EPI_BIAS_GELU)]
+                ff2 = [dict(A=u_hq, W=bp.ff2.w, bias=bp.ff2.b, out=x[:, :N], epilogue=ops.EPI_GATE_RESID, gate=gate_mlp),
+                       dict(A=u_lr, W=bp.ff2.w, bias=bp.ff2.b, out=x[:, N:], epilogue=ops.EPI_GATE_RESID, gate=gate_mlp)]
+            else:
+                u_hq, u_lr = ws["u"][:, :N], ws["u"][:, N:2 * N]
+                ff1 = [dict(A=n1, W=bp.ff1.w, bias=bp.ff1.b, out=ws["u"], epilogue=ops.EPI_BIAS_GELU)]
+                ff2 = [dict(A=ws["u"], W=bp.ff2.w, bias=bp.ff2.b, out=x, epilogue=ops.EPI_GATE_RESID, gate=gate_mlp)]
             if not bp.last:   # text MLP (attention.py:384-393) rides in the same launches
                 R("ln_mod", ops.ln_modulate, ctx, c_shift_mlp, c_scale_mlp, nc)
                 ff1.append(dict(A=nc, W=bp.ffc1.w, bias=bp.ffc1.b, out=ws["uc"], epilogue=ops.EPI_BIAS_GELU))
@@ -627,7 +678,7 @@ class Engine:
                                 gate=c_gate_mlp))
             self._gg("ff1", ff1)
             u = ws["u"]
-            self._conv_add(ws, u[:, :N], u[:, N:2 * N], bp.conv_w9, bp.conv_b, rows, grid)
+            self._conv_add(ws, u_hq, u_lr, bp.conv_w9, bp.conv_b, rows, grid)
             if bp.ocr:   # u_hq += conv_o(u_ocr); then u_ocr += conv_h(u_hq updated)  (ocr attention file :184-206)
                 self._conv_add(ws, u[:, :N], u[:, 2 * N:], bp.conv_o_w9, bp.conv_o_b, rows, grid)
                 self._conv_add(ws, u[:, 2 * N:], u[:, :N], bp.conv_h_w9, bp.conv_h_b, rows, grid)
@@ -646,7 +697,7 @@ class Engine:
             R("tail", ops.unpatchify, ws["tok"], out, latents=latents, dsigma=dsigma)
         else:
             R("tail", ops.unpatchify, ws["tok"], out)
-        if self.sp is not None:        # every rank returns the whole image (row strips gathered)
+        if self.sp is not None and not sharded:   # every rank returns the whole image (row strips gathered)
             gathered = self.sp.gather_rows(out, dim=2)
             if full_out is not None:
                 full_out.copy_(gathered)

@@ -5,7 +5,7 @@ import ctypes as C
 import torch
 
 from . import _lib
-from ._lib import AttnParams, DwconvParams, GemmParams, LnModulateParams, check
+from ._lib import A2aParams, AttnParams, AttnSpOut, DwconvParams, GemmParams, HaloParams, LnModulateParams, check
 
 EPI_BIAS, EPI_BIAS_GELU, EPI_BIAS_SILU, EPI_QKV_NORM, EPI_GATE_RESID = 0, 1, 2, 3, 4
 DT_BF16, DT_F32 = 0, 1
@@ -195,12 +195,15 @@ ATTN_ONLINE, ATTN_PRESCALED = 0, 1
 ATTN_MAX_SCORE_BOUND = 60.0
 
 
-def attention(q, k, v, o, heads, seq_q=None, scale=None, lr_res=None, lr_rows=(0, 0), score_bound=None, exp_offload=0, variant=0):
+def attention(q, k, v, o, heads, seq_q=None, scale=None, lr_res=None, lr_rows=(0, 0), score_bound=None, exp_offload=0, variant=0,
+              sp_out=None):
     """o = softmax(q k^T * scale) v over [B, S, heads*64] bf16 views (row stride may be 3*heads*64 for a fused buffer).
 
     Only the first seq_q query rows are produced. lr_res (bf16 [B, >=lr_rows[1], heads*64]) is added to rows lr_rows.
     score_bound (log2 units): q already carries scale*log2(e) and q.k <= score_bound for every pair -> the kernel takes
-    p = 2^(q.k) without a reference max (DIT4SR_ATTN_PRESCALED); None = online softmax (any q, k)."""
+    p = 2^(q.k) without a reference max (DIT4SR_ATTN_PRESCALED); None = online softmax (any q, k).
+    sp_out (an AttnSpOut from `attn_sp_out`): the rows are stored into the owning ranks' peer-mapped buffers instead of o,
+    which then only supplies the common strides."""
     for n, t in (("q", q), ("k", k), ("v", v), ("o", o)):
         _req(t, torch.bfloat16, n)
     B, S, D = k.shape
@@ -222,8 +225,73 @@ def attention(q, k, v, o, heads, seq_q=None, scale=None, lr_res=None, lr_rows=(0
     if score_bound is not None:
         p.mode, p.score_bound = ATTN_PRESCALED, float(score_bound)
     p.exp_offload, p.variant = exp_offload, variant
+    if sp_out is not None:
+        p.sp_out = C.pointer(sp_out)
     check(_lib.load().dit4sr_attn_fwd(C.byref(p), _stream()), "dit4sr_attn_fwd")
     _count()
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# Ulysses sequence parallelism over NVLink peer memory (csrc/sp_comm.cu)
+def attn_sp_out(world, rows_per_rank, col_offset, o_peers):
+    so = AttnSpOut()
+    so.world, so.rows_per_rank, so.col_offset = world, rows_per_rank, col_offset
+    for r, ptr in enumerate(o_peers):
+        so.o_peer[r] = ptr
+    return so
+
+
+def sp_barrier(comm, channel):
+    check(_lib.load().dit4sr_sp_barrier(C.byref(comm), channel, _stream()), "dit4sr_sp_barrier")
+    _count()
+
+
+def a2a_qkv(comm, src, image_rows, text_rows, heads, peers, no_barrier=False):
+    """src bf16 [B, image_rows + text_rows, 3*heads*64] (my tokens, all heads) -> every rank's [B, P*image_rows +
+    text_rows, 3, heads*64/P] buffer (`peers`: device pointers as mapped here), then the arrival barrier."""
+    _req(src, torch.bfloat16, "src")
+    p = A2aParams()
+    p.src, p.src_row_stride, p.src_batch_stride = _ptr(src), src.stride(1), src.stride(0)
+    for r, ptr in enumerate(peers):
+        p.peer[r] = ptr
+    p.batches, p.image_rows, p.text_rows, p.heads = src.shape[0], image_rows, text_rows, heads
+    p.no_barrier = 1 if no_barrier else 0
+    check(_lib.load().dit4sr_a2a_qkv(C.byref(comm), C.byref(p), _stream()), "dit4sr_a2a_qkv")
+    _count(1 if no_barrier else 2)
+
+
+def a2a_out(comm, src, image_rows, text_rows, heads, peers, dst_row_stride, dst_batch_stride, no_barrier=False):
+    """The way back: src bf16 [B, P*image_rows + text_rows, heads*64/P] contiguous -> the owning ranks' [B, >= image_rows +
+    text_rows, heads*64] buffers. src=None: the attention kernel already stored through sp_out, arrival barrier only."""
+    p = A2aParams()
+    if src is not None:
+        _req(src, torch.bfloat16, "src")
+        if not src.is_contiguous():
+            raise _lib.Dit4srError("a2a_out: src must be contiguous")
+        p.src = _ptr(src)
+        p.batches = src.shape[0]
+    for r, ptr in enumerate(peers):
+        p.peer[r] = ptr
+    p.dst_row_stride, p.dst_batch_stride = dst_row_stride, dst_batch_stride
+    p.image_rows, p.text_rows, p.heads = image_rows, text_rows, heads
+    p.no_barrier = 1 if no_barrier else 0
+    check(_lib.load().dit4sr_a2a_out(C.byref(comm), C.byref(p), _stream()), "dit4sr_a2a_out")
+    _count((0 if src is None else 1) + (0 if no_barrier else 1))
+
+
+def halo_rows(comm, u, peers, grid_w, first_lr_row, lr_rows, top_halo_row, bottom_halo_row, no_barrier=False):
+    """u bf16 [B, rows, F]: my MLP hidden-state buffer (same layout on every rank, `peers` = its mappings): my first / last
+    LR grid row -> the neighbours' halo rows, then the arrival barrier."""
+    _req(u, torch.bfloat16, "u")
+    p = HaloParams()
+    for r, ptr in enumerate(peers):
+        p.peer[r] = ptr
+    p.row_stride, p.batch_stride = u.stride(1), u.stride(0)
+    p.batches, p.channels, p.grid_w = u.shape[0], u.shape[2], grid_w
+    p.first_lr_row, p.lr_rows, p.top_halo_row, p.bottom_halo_row = first_lr_row, lr_rows, top_halo_row, bottom_halo_row
+    p.no_barrier = 1 if no_barrier else 0
+    check(_lib.load().dit4sr_halo_rows(C.byref(comm), C.byref(p), _stream()), "dit4sr_halo_rows")
+    _count(1 if no_barrier else 2)
 
 
 def patchify(x, out):

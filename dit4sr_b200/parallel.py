@@ -65,6 +65,8 @@ class SequenceParallel:
     The collectives go through torch.distributed (NCCL over NVLink on the GPUs; gloo in the CPU tests).
     """
 
+    peer = False   # True in PeerSequenceParallel: exchanges are CUDA kernels over NVLink peer memory
+
     def __init__(self, group: Optional[dist.ProcessGroup] = None):
         self.group = group
         self.world = dist.get_world_size(group)
@@ -151,3 +153,93 @@ class SequenceParallel:
         parts = [torch.empty_like(t) for _ in range(self.world)]
         dist.all_gather(parts, t.contiguous(), group=self.group)
         return torch.cat(parts, dim=dim)
+
+
+# ======================================================================================================================
+# The same partitioning with the exchanges over NVLink peer memory (csrc/sp_comm.cu) instead of torch.distributed
+# ======================================================================================================================
+class _RawCuda:
+    """Minimal __cuda_array_interface__ holder: lets torch alias a raw device allocation without copying."""
+
+    def __init__(self, ptr, nbytes):
+        self.__cuda_array_interface__ = {"shape": (nbytes,), "typestr": "|u1", "data": (ptr, False), "version": 2}
+
+
+class PeerSequenceParallel(SequenceParallel):
+    """SequenceParallel whose data path never enters a collective library: every exchange buffer is allocated with
+    dit4sr_peer_alloc, exported over CUDA IPC and mapped by the peers (torch.distributed only carries the 64-byte handles
+    at set-up), and the all-to-all / halo kernels store straight into the destination GPU's memory (include/dit4sr_b200.h,
+    "Ulysses sequence parallelism over NVLink peer memory").  The engine can therefore capture the whole sequence-parallel
+    step in ONE CUDA graph.  One process per GPU of one NVLink/NVSwitch box, at most 8 ranks."""
+
+    peer = True
+
+    def __init__(self, group: Optional[dist.ProcessGroup] = None):
+        super().__init__(group)
+        import ctypes as C
+
+        from . import _lib
+        if self.world > _lib.SP_MAX_RANKS:
+            raise ValueError(f"PeerSequenceParallel supports at most {_lib.SP_MAX_RANKS} ranks")
+        self._C, self._lib = C, _lib
+        self._allocs = []      # local allocations (freed by close())
+        self._opened = []      # peer mappings (closed by close())
+        self.device = torch.device("cuda", torch.cuda.current_device())
+        flags_local, flags_peers = self._alloc_shared_raw(_lib.SP_CHANNELS * _lib.SP_MAX_RANKS * 4)
+        epoch = C.c_void_p()
+        _lib.check(_lib.load().dit4sr_peer_alloc(_lib.SP_CHANNELS * 4, C.byref(epoch)), "dit4sr_peer_alloc")
+        self._allocs.append(epoch.value)
+        self.comm = _lib.SpComm()
+        self.comm.world, self.comm.rank = self.world, self.rank
+        for r, p in enumerate(flags_peers):
+            self.comm.flags[r] = p
+        self.comm.epoch = epoch.value
+
+    def _alloc_shared_raw(self, nbytes: int):
+        """Collective: every rank allocates `nbytes`, the handles go round, everybody maps everybody.  Returns
+        (local pointer, [pointer of rank r's allocation as mapped here for r in range(world)])."""
+        C, _lib = self._C, self._lib
+        lib = _lib.load()
+        nbytes = (int(nbytes) + 255) // 256 * 256
+        ptr = C.c_void_p()
+        _lib.check(lib.dit4sr_peer_alloc(nbytes, C.byref(ptr)), "dit4sr_peer_alloc")
+        self._allocs.append(ptr.value)
+        handle = C.create_string_buffer(64)
+        _lib.check(lib.dit4sr_peer_export(ptr, handle), "dit4sr_peer_export")
+        handles = [None] * self.world
+        dist.all_gather_object(handles, (bytes(handle.raw), nbytes), group=self.group)
+        peers = []
+        for r, (h, n) in enumerate(handles):
+            if n != nbytes:
+                raise RuntimeError(f"PeerSequenceParallel: rank {r} allocated {n} bytes, this rank {nbytes}: the ranks "
+                                   "must request the same buffers in the same order")
+            if r == self.rank:
+                peers.append(ptr.value)
+                continue
+            q = C.c_void_p()
+            _lib.check(lib.dit4sr_peer_open(C.create_string_buffer(h, 64), C.byref(q)), "dit4sr_peer_open")
+            self._opened.append(q.value)
+            peers.append(q.value)
+        return ptr.value, peers
+
+    def shared_empty(self, shape, dtype=torch.bfloat16):
+        """Collective. A zero-filled tensor of `shape` on this rank that every peer has mapped: returns (tensor, peers)
+        with peers[r] = device pointer of rank r's tensor in THIS process."""
+        numel = 1
+        for s in shape:
+            numel *= int(s)
+        nbytes = numel * torch.empty((), dtype=dtype).element_size()
+        ptr, peers = self._alloc_shared_raw(nbytes)
+        flat = torch.as_tensor(_RawCuda(ptr, nbytes), device=self.device)
+        if flat.data_ptr() != ptr:
+            raise RuntimeError("PeerSequenceParallel: torch copied the peer allocation instead of aliasing it")
+        return flat.view(dtype).view(*shape), peers
+
+    def close(self):
+        torch.cuda.synchronize()
+        lib = self._lib.load()
+        for q in self._opened:
+            lib.dit4sr_peer_close(q)
+        for p in self._allocs:
+            lib.dit4sr_peer_free(p)
+        self._opened, self._allocs = [], []

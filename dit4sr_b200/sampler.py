@@ -25,12 +25,21 @@ def denoise(model, latents, controlnet_image, encoder_hidden_states, pooled_proj
     eng = model.engine()
     sig = flow_match_sigmas(num_inference_steps) if sigmas is None else np.asarray(sigmas, dtype=np.float32)
     B = latents.shape[0]
-    x = latents.float().contiguous()
+    sp = eng.sp
+    if sp is not None:   # Ulysses: every rank carries its own row strip through the loop; ONE gather at the end
+        g0, g1 = sp.row_slice(latents.shape[2] // 2)
+        latents_l = latents[:, :, 2 * g0:2 * g1]
+        controlnet_image = controlnet_image[:, :, 2 * g0:2 * g1].contiguous()
+    else:
+        latents_l = latents
+    x = latents_l.float().contiguous()
     nxt = torch.empty_like(x)
     t = torch.empty(B, device=latents.device, dtype=torch.float32)
     for i in range(len(sig) - 1):
         t.fill_(float(sig[i]) * 1000.0)
         eng.step(x, controlnet_image, encoder_hidden_states, pooled_projections, t, out=nxt,
-                 euler=(x, float(sig[i + 1]) - float(sig[i])))
+                 euler=(x, float(sig[i + 1]) - float(sig[i])), sharded_io=sp is not None)
         x, nxt = nxt, x
+    if sp is not None:
+        x = sp.gather_rows(x, dim=2)
     return x.to(latents.dtype)

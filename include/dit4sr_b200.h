@@ -17,6 +17,7 @@
 #ifndef DIT4SR_B200_H_
 #define DIT4SR_B200_H_
 
+#include <stddef.h>
 #include <stdint.h>
 
 #ifdef __cplusplus
@@ -155,9 +156,21 @@ int dit4sr_gemm_schedule(const dit4sr_gemm_params* problems, int count, int sm_c
  *              of MUFU.EX2 (tuning knob: same results to within bf16 rounding of P).
  * variant:     0 = default; 3 = independent query tiles with double-buffered 96-key score tiles (the default);
  *              2 = three 128-key score buffers rotating over the two query tiles (round 1's pipeline, kept for A/B).
+ * sp_out (Ulysses sequence parallelism, NULL otherwise): the kernel's epilogue stores each output row straight into the
+ *              token-side buffer of the rank that owns the token, through NVLink peer memory (the head -> sequence
+ *              all-to-all fused into the attention kernel).  Query row i < world*rows_per_rank belongs to rank
+ *              i / rows_per_rank and lands in row i % rows_per_rank of o_peer[rank]; the remaining (text) rows land in
+ *              rows rows_per_rank.. of EVERY o_peer.  Columns: col_offset + head*64 (col_offset = my first head * 64).
+ *              o / o_row_stride / o_batch_stride describe the (identical) layout of every o_peer buffer; lr_res must be
+ *              NULL.  Follow with dit4sr_a2a_out(src = NULL) (arrival barrier) before reading the buffers.
  */
 enum { DIT4SR_ATTN_ONLINE = 0, DIT4SR_ATTN_PRESCALED = 1 };
 #define DIT4SR_ATTN_MAX_SCORE_BOUND 60.0f
+#define DIT4SR_SP_MAX_RANKS 8
+typedef struct {
+  int world; int rows_per_rank; int col_offset;
+  void* o_peer[DIT4SR_SP_MAX_RANKS];
+} dit4sr_attn_sp_out;
 typedef struct {
   const void* q; const void* k; const void* v;
   int64_t qkv_row_stride; int64_t qkv_batch_stride;
@@ -167,8 +180,76 @@ typedef struct {
   int batches; int heads; int seq_q; int seq_kv;
   float scale;
   int mode; float score_bound; int exp_offload; int variant;             /* ABI v3 */
+  const dit4sr_attn_sp_out* sp_out;
 } dit4sr_attn_params;
 int dit4sr_attn_fwd(const dit4sr_attn_params* p, void* stream);
+
+/* ---------------------------------------------------------------------------------------------------------------
+ * Ulysses sequence parallelism over NVLink peer memory (BASELINE config C4; the reference has no counterpart: it runs
+ * F.scaled_dot_product_attention on one GPU, model_dit4sr/attention.py:528).  One process per GPU of one box.  Every rank
+ * owns grid/P rows of the token grid of each image stream; around each joint attention the q|k|v of its tokens are
+ * scattered to the ranks that own the heads and the outputs come back, and the depthwise stencil (attention.py:168-177)
+ * needs one halo row from each neighbour.  All exchange buffers are allocated with dit4sr_peer_alloc on every rank,
+ * exported (CUDA IPC) and mapped by the peers; the kernels store straight into the destination's memory and signal
+ * arrival through per-(channel, source) counters, so an exchange is one or two kernel launches on the caller's stream:
+ * no pack/unpack copies, no library collective, CUDA-graph capturable.  Every rank must issue the same sequence of calls.
+ *
+ * The communicator is passed in explicitly (no global state):
+ *   flags[r]  rank r's arrival counters as mapped in THIS process: uint32 [DIT4SR_SP_CHANNELS][DIT4SR_SP_MAX_RANKS],
+ *             zero-initialised (dit4sr_peer_alloc does that); flags[rank] is the local allocation itself
+ *   epoch     local device memory, uint32 [DIT4SR_SP_CHANNELS], zero-initialised: generation per channel
+ */
+#define DIT4SR_SP_CHANNELS 4
+enum { DIT4SR_SP_CH_QKV = 0, DIT4SR_SP_CH_OUT = 1, DIT4SR_SP_CH_HALO = 2, DIT4SR_SP_CH_USER = 3 };
+typedef struct {
+  int world; int rank;
+  uint32_t* flags[DIT4SR_SP_MAX_RANKS];
+  uint32_t* epoch;
+} dit4sr_sp_comm;
+/* Peer-visible device memory: allocate (zero-filled), export a 64-byte handle for the other processes, map a peer's
+ * handle (enables peer access lazily), unmap, free.  Host-side setup calls; they synchronise the device. */
+int dit4sr_peer_alloc(size_t bytes, void** ptr);
+int dit4sr_peer_free(void* ptr);
+int dit4sr_peer_export(const void* ptr, unsigned char handle[64]);
+int dit4sr_peer_open(const unsigned char handle[64], void** ptr);
+int dit4sr_peer_close(void* ptr);
+/* Signal every peer on `channel` and wait for every peer's signal (also orders all earlier stores of this rank's stream
+ * to peer memory before the signal).  A peer that never arrives traps the kernel after 20 s instead of hanging. */
+int dit4sr_sp_barrier(const dit4sr_sp_comm* comm, int channel, void* stream);
+/* Head <-> sequence exchange.
+ *  dit4sr_a2a_qkv: src = this rank's fused projection buffer, bf16 [batches, image_rows + text_rows, 3 * heads*64]
+ *     (src_row_stride / src_batch_stride in elements).  Image rows go to EVERY rank p as
+ *     peer[p][b, rank*image_rows + s, {q,k,v}, Dl] with the columns of p's heads (Dl = heads*64 / world); the text rows are
+ *     replicated, so only this rank's own head slice is copied, to peer[rank][b, world*image_rows + t, ...].
+ *     peer[p]: bf16 [batches, world*image_rows + text_rows, 3, Dl] contiguous, the same shape on every rank.
+ *  dit4sr_a2a_out: the way back.  src = bf16 [batches, world*image_rows + text_rows, Dl] contiguous (my heads, all tokens)
+ *     -> peer[r][b, s, rank*Dl ...] for the image rows rank r owns, and the text rows to every peer at rows image_rows.. ;
+ *     peer[r]: bf16 [batches, >= image_rows + text_rows, heads*64] with dst_row_stride / dst_batch_stride.
+ *     src == NULL: nothing to move (dit4sr_attn_fwd already stored into the peers through sp_out): arrival barrier only.
+ *  Unless no_barrier is set each call ends with dit4sr_sp_barrier on its own channel, i.e. when the call's work completes
+ *  on the stream, everything the PEERS sent to this rank in their matching call has arrived too. */
+typedef struct {
+  const void* src; int64_t src_row_stride; int64_t src_batch_stride;
+  void* peer[DIT4SR_SP_MAX_RANKS];
+  int64_t dst_row_stride; int64_t dst_batch_stride;      /* a2a_out only */
+  int batches; int image_rows; int text_rows; int heads;
+  int no_barrier;
+} dit4sr_a2a_params;
+int dit4sr_a2a_qkv(const dit4sr_sp_comm* comm, const dit4sr_a2a_params* p, void* stream);
+int dit4sr_a2a_out(const dit4sr_sp_comm* comm, const dit4sr_a2a_params* p, void* stream);
+/* Halo exchange of the LR hidden state for the depthwise stencil.  peer[r] = rank r's MLP hidden-state buffer, bf16
+ * [batches, rows, channels] (row_stride / batch_stride in elements, the same layout on every rank), which holds this
+ * rank's LR token rows at [first_lr_row, first_lr_row + lr_rows) and one grid row (grid_w tokens) of halo above at
+ * top_halo_row and below at bottom_halo_row.  Stores my first LR grid row into rank-1's bottom halo and my last into
+ * rank+1's top halo; the outer halos of the first / last rank are never written (they stay zero = the conv's padding). */
+typedef struct {
+  void* peer[DIT4SR_SP_MAX_RANKS];
+  int64_t row_stride; int64_t batch_stride;
+  int batches; int channels; int grid_w;
+  int64_t first_lr_row; int64_t lr_rows; int64_t top_halo_row; int64_t bottom_halo_row;
+  int no_barrier;
+} dit4sr_halo_params;
+int dit4sr_halo_rows(const dit4sr_sp_comm* comm, const dit4sr_halo_params* p, void* stream);
 
 /* ---------------------------------------------------------------------------------------------------------------
  * Small data-movement kernels of the model head / tail (transformer_sd3.py:326-332,379-391).

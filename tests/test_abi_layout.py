@@ -17,6 +17,10 @@ STRUCTS = {
     "dit4sr_dwconv3x3_params": _lib.DwconvParams,
     "dit4sr_gemm_params": _lib.GemmParams,
     "dit4sr_attn_params": _lib.AttnParams,
+    "dit4sr_attn_sp_out": _lib.AttnSpOut,
+    "dit4sr_sp_comm": _lib.SpComm,
+    "dit4sr_a2a_params": _lib.A2aParams,
+    "dit4sr_halo_params": _lib.HaloParams,
 }
 
 
@@ -51,5 +55,5 @@ def test_header_struct_fields_are_all_bound():
         end = hdr.index("} " + cname + ";")
         body = hdr[hdr.rindex("typedef struct {", 0, end) + len("typedef struct {"):end]
         body = re.sub(r"/\*.*?\*/", "", body, flags=re.S)
-        names = [re.search(r"(\w+)\s*$", d.strip()).group(1) for d in body.split(";") if d.strip()]
+        names = [re.search(r"(\w+)\s*(\[\w+\])?\s*$", d.strip()).group(1) for d in body.split(";") if d.strip()]
         assert names == [f for f, _ in cls._fields_], (cname, names)

@@ -180,9 +180,10 @@ def test_bench_product_arm_config_matches_survey_and_avoids_the_oracle():
 def test_every_entry_point_rejects_null_arguments_with_a_message(lib):
     """Error behaviour of the C ABI: no crash, DIT4SR_E_BADARG (-1) and a message naming the entry point, without a GPU."""
     for name, (_, args) in _lib.SYMBOLS.items():
-        if name in ("dit4sr_abi_version", "dit4sr_last_error", "dit4sr_check_device"):
+        if name in ("dit4sr_abi_version", "dit4sr_last_error", "dit4sr_check_device",
+                    "dit4sr_peer_free", "dit4sr_peer_close"):      # free(NULL) / close(NULL) are no-ops by design
             continue
-        vals = [0 if a in (ctypes.c_int, ctypes.c_int64) else (0.0 if a is ctypes.c_float else None) for a in args]
+        vals = [0 if a in (ctypes.c_int, ctypes.c_int64, ctypes.c_size_t) else (0.0 if a is ctypes.c_float else None) for a in args]
         rc = getattr(lib, name)(*vals)
         assert rc == -1, (name, rc)
         assert len(lib.dit4sr_last_error()) > 0, name
