@@ -121,12 +121,12 @@ def attention_roofline(launch_ms, flops_per_step, launches_per_step, peaks, root
         prof = json.load(open(os.path.join(root, "profiles", "r01e_ncu_full_attention.json")))
         k = next(k for k in prof if "attn_fwd2_kernel" in k["Kernel Name"])
         traffic = round((float(k["dram__bytes_read.sum [Mbyte]"]) + float(k["dram__bytes_write.sum [Mbyte]"])) * 1e6)
-        src = ("profiles/r01e_ncu_full_attention.json: dram__bytes_read.sum + dram__bytes_write.sum of one joint-attention "
+        src = ("from committed capture profiles/r01e_ncu_full_attention.json (not measured in this run): dram__bytes_read.sum + dram__bytes_write.sum of one joint-attention "
                "launch (S=2381, B=8; algorithmic 263 MB q|k|v read + 59 MB o written + 50 MB LR residual read)")
     except (OSError, KeyError, ValueError, StopIteration):
         pass
-    return dict(bound="tensor", kernel="attn_fwd2_kernel (joint attention over [HQ|LR|text], head_dim 64; the largest "
-                "share of the step: MUFU.EX2 / issue limited, DESIGN.md 3.2)", achieved=round(ach, 1),
+    return dict(bound="tensor", kernel="attn_fwd3_kernel / attn_fwd2_kernel (joint attention over [HQ|LR|text] and the image-only attn2, "
+                "head_dim 64; the largest share of the step: MUFU.EX2 / issue limited, DESIGN.md 3.2)", achieved=round(ach, 1),
                 peak=peaks["tf_sustained"], unit="TFLOP/s", frac=round(ach / peaks["tf_sustained"], 4),
                 peak_source=peaks["source"] + ", sustained figure (kernel timed inside a long step)",
                 frac_of_burst=round(ach / peaks["tf_burst"], 4), frac_of_spec_2250=round(ach / 2250.0, 4),
@@ -197,12 +197,149 @@ def build_model_gpu(device, seed=0, ocr=False):
     return m.to(torch.bfloat16).requires_grad_(False).eval(), cfg
 
 
+class Stepper:
+    """Synthetic inputs of one workload on this rank + the closure that advances them one denoise step (model forward +
+    fused Euler update) through the engine.  Under sequence parallelism the image tensors are this rank's row strips."""
+
+    def __init__(self, eng, B, side, T, dev, seed, sp=None):
+        import torch
+        from dit4sr_b200.sampler import flow_match_sigmas
+        bf = torch.bfloat16
+        g = torch.Generator(device=dev).manual_seed(seed)
+        x = torch.randn(B, 16, side, side, device=dev, generator=g)
+        ctrl = torch.randn(B, 16, side, side, device=dev, generator=g).to(bf)
+        self.full = (x, ctrl)
+        if sp is not None:
+            g0, g1 = sp.row_slice(side // 2)
+            x, ctrl = x[:, :, 2 * g0:2 * g1].contiguous(), ctrl[:, :, 2 * g0:2 * g1].contiguous()
+        self.eng, self.sp = eng, sp
+        self.ctrl = ctrl
+        self.enc = (0.5 * torch.randn(B, T, 4096, device=dev, generator=g)).to(bf)
+        self.pooled = torch.randn(B, 2048, device=dev, generator=g).to(bf)
+        self.sig = flow_match_sigmas(40)
+        self.t = torch.empty(B, device=dev, dtype=torch.float32)
+        self.cur, self.oth = x, torch.empty_like(x)
+        self.i = 0
+
+    def step(self):
+        k = self.i % 40
+        self.t.fill_(float(self.sig[k]) * 1000.0)
+        self.eng.step(self.cur, self.ctrl, self.enc, self.pooled, self.t, out=self.oth,
+                      euler=(self.cur, float(self.sig[k + 1]) - float(self.sig[k])), sharded_io=self.sp is not None)
+        self.cur, self.oth = self.oth, self.cur
+        self.i += 1
+
+
+def timed_steps(stepper, steps, warmup, barrier, world, dev):
+    """`warmup` untimed steps, then exactly `steps` steps between CUDA events, barrier + synchronize on both sides; returns
+    the MAX over ranks of the elapsed milliseconds."""
+    import torch
+    import torch.distributed as dist
+    for _ in range(warmup):
+        stepper.step()
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        stepper.step()
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1)
+    if world > 1:
+        tt = torch.tensor([ms], device=dev)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        ms = tt.item()
+    return ms
+
+
+def instrumented_step(eng, stepper, rank):
+    """One extra direct-launch step with CUDA events around every kernel class (every rank runs it: under sequence
+    parallelism the ranks must issue the same exchanges); rank 0's totals are reported."""
+    import torch
+    eng.profile_kernel("*")
+    stepper.step()
+    torch.cuda.synchronize()
+    bd = eng.profile_result()
+    return {k: dict(launches=len(v), total_ms=round(sum(v), 4)) for k, v in bd.items()} if rank == 0 else None
+
+
+def release(eng):
+    """Drop an engine's workspaces and captured graphs (the next workload needs the memory)."""
+    import torch
+    eng._graphs.clear()
+    eng._ws.clear()
+    torch.cuda.empty_cache()
+
+
+def north_star_scaling(model, world, rank, dev, barrier, steps=5, warmup=3):
+    """The two partitioned workloads BASELINE.json's north star names, at THIS world size (the driver runs 1, 2, 4, 8):
+      c4_ulysses    one 2048px image, Ulysses sequence parallelism over all ranks (plain engine at 1 rank)
+      c3_dp_strong  1024px, batch 32 IN TOTAL, data-parallel: this rank's share is 32 / world images, no collective
+    Device-timed (CUDA events, max over ranks), `steps` timed steps after `warmup`; each entry names its limiter split."""
+    import torch
+    out = {}
+    # ---- C4
+    side, _, T, _, _ = WORKLOADS["c4"]
+    N = (side // 2) ** 2
+    try:
+        sp = None
+        if world > 1:
+            from dit4sr_b200.parallel import PeerSequenceParallel
+            sp = PeerSequenceParallel()
+        eng = model.engine(sequence_parallel=sp)
+        st = Stepper(eng, 1, side, T, dev, seed=1, sp=sp)
+        ms = timed_steps(st, steps, warmup, barrier, world, dev)
+        bd = instrumented_step(eng, st, rank)
+        gemm_f, attn_f = flops_per_image_step(N, T, folded=eng.fold_lr_chains)
+        entry = dict(ranks=world, path="nvlink-peer-memory ulysses, cuda graph" if sp else "single gpu, cuda graph",
+                     ms_per_step=round(ms / steps, 3), steps=steps, image_steps_per_sec=round(steps / (ms / 1e3), 4),
+                     step_tflop=round((gemm_f + attn_f) / 1e12, 2),
+                     tflops_per_gpu=round((gemm_f + attn_f) / world / (ms / steps / 1e3) / 1e12, 1))
+        if bd:
+            keep = ("attn", "a2a", "halo", "qkv_group", "out_group", "ff1", "ff2", "dwconv", "ln_mod")
+            entry["breakdown_ms"] = {k: bd[k]["total_ms"] for k in keep if k in bd}
+            entry["breakdown_note"] = ("direct-launch instrumented step on rank 0; a2a = scatter kernels + arrival "
+                                       "barriers (includes waiting for the slowest rank), attn = attention kernel with "
+                                       "the way back fused into its epilogue")
+        if sp is not None:   # parity of the sharded path against the single-GPU engine on the same image (not timed)
+            x_full, c_full = st.full
+            t = torch.full((1,), 741.44, device=dev)
+            v_sp = eng.step(x_full.to(torch.bfloat16), c_full, st.enc, st.pooled, t).float()
+            release(eng)
+            eng1 = model.engine(sequence_parallel=None)
+            v_1 = eng1.step(x_full.to(torch.bfloat16), c_full, st.enc, st.pooled, t).float()
+            entry["parity_rel_l2_vs_single_gpu"] = float(((v_sp - v_1).norm() / v_1.norm()).item())
+            release(eng1)
+            barrier()
+            sp.close()
+        else:
+            release(eng)
+        out["c4_ulysses"] = entry
+    except Exception as e:   # noqa: BLE001  (never lose the headline line to the extra measurements)
+        out["c4_ulysses"] = dict(error=f"{type(e).__name__}: {e}"[:300])
+    # ---- C3 (this rank's share of the batch)
+    side, Btot, T, _, _ = WORKLOADS["c3"]
+    N = (side // 2) ** 2
+    try:
+        eng = model.engine(sequence_parallel=None)
+        Bl = Btot // world
+        st = Stepper(eng, Bl, side, T, dev, seed=1 + rank)
+        ms = timed_steps(st, steps, warmup, barrier, world, dev)
+        gemm_f, attn_f = flops_per_image_step(N, T, folded=eng.fold_lr_chains)
+        out["c3_dp_strong"] = dict(ranks=world, global_batch=Btot, per_gpu_batch=Bl, ms_per_step=round(ms / steps, 3),
+                                   steps=steps, image_steps_per_sec=round(Btot * steps / (ms / 1e3), 3),
+                                   tflops_per_gpu=round((gemm_f + attn_f) * Bl / (ms / steps / 1e3) / 1e12, 1),
+                                   collectives_in_step=0)
+        release(eng)
+    except Exception as e:   # noqa: BLE001
+        out["c3_dp_strong"] = dict(error=f"{type(e).__name__}: {e}"[:300])
+    return out
+
+
 def run_ours(args):
-    import numpy as np
     import torch
     import torch.distributed as dist
     from dit4sr_b200 import ops
-    from dit4sr_b200.sampler import flow_match_sigmas
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -219,38 +356,24 @@ def run_ours(args):
     N = (side // 2) ** 2
     bf = torch.bfloat16
 
-    model, cfg = build_model_gpu(dev, seed=0, ocr=args.workload == "c5")
-    if mode == "sp" and world > 1:
-        from dit4sr_b200.parallel import SequenceParallel
-        eng = model.engine(sequence_parallel=SequenceParallel())
-    else:
-        eng = model.engine()
-    images_total = B * (1 if mode == "sp" else world)       # images advanced per step by the whole job
-    rank_seed = 1 if mode == "sp" else 1 + rank              # sequence parallelism: every rank holds the same image
-    g = torch.Generator(device=dev).manual_seed(rank_seed)
-    x = torch.randn(B, 16, side, side, device=dev, generator=g)
-    ctrl = torch.randn(B, 16, side, side, device=dev, generator=g).to(bf)
-    enc = (0.5 * torch.randn(B, T, 4096, device=dev, generator=g)).to(bf)
-    pooled = torch.randn(B, 2048, device=dev, generator=g).to(bf)
-    sig = flow_match_sigmas(40)
-    t = torch.empty(B, device=dev, dtype=torch.float32)
-    nxt = torch.empty_like(x)
-
-    def step(i, xin, xout):
-        k = i % 40
-        t.fill_(float(sig[k]) * 1000.0)
-        eng.step(xin, ctrl, enc, pooled, t, out=xout, euler=(xin, float(sig[k + 1]) - float(sig[k])))
-
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
+    model, cfg = build_model_gpu(dev, seed=0, ocr=args.workload == "c5")
+    sp = None
+    if mode == "sp" and world > 1:
+        from dit4sr_b200.parallel import PeerSequenceParallel, SequenceParallel
+        sp = SequenceParallel() if os.environ.get("DIT4SR_SP_BACKEND") == "nccl" else PeerSequenceParallel()
+    eng = model.engine(sequence_parallel=sp)
+    images_total = B * (1 if mode == "sp" else world)       # images advanced per step by the whole job
+    rank_seed = 1 if mode == "sp" else 1 + rank              # sequence parallelism: every rank holds the same image
+    st = Stepper(eng, B, side, T, dev, rank_seed, sp=sp)
+
     # ---- device-resident timing (`value`)
-    cur, oth = x, nxt
-    for i in range(args.warmup):
-        step(i, cur, oth)
-        cur, oth = oth, cur
+    for _ in range(args.warmup):
+        st.step()
     barrier()
     sampler = ClockSampler(local) if rank == 0 else None
     l0 = ops.launch_count()
@@ -259,32 +382,30 @@ def run_ours(args):
     if prof_range:
         torch.cuda.profiler.start()
     e0.record()
-    for i in range(args.steps):
-        step(i, cur, oth)
-        cur, oth = oth, cur
+    for _ in range(args.steps):
+        st.step()
     e1.record()
     barrier()
     if prof_range:
         torch.cuda.profiler.stop()
     ms = e0.elapsed_time(e1)
     launches = ops.launch_count() - l0
-    # dominant kernel: CUDA events around every FF1-group launch of the same steps, run again right after the timed region
-    # (same stream, same shapes, same clocks; direct launches because events cannot be recorded inside a graph replay)
-    eng.profile_kernel("ff1")
-    for i in range(args.steps):
-        step(i, cur, oth)
-        cur, oth = oth, cur
-    ff1_ms = eng.profile_result()
-    # same for the joint-attention kernel, the largest single share of the step (never allowed to break the bench line)
-    attn_ms = None
+    # dominant kernels: CUDA events around every FF1-group / attention launch of the same steps, run again right after the
+    # timed region (same stream, same shapes, same clocks; direct launches because events cannot be recorded inside a
+    # graph replay).  Every rank runs them (sequence parallelism: same exchanges everywhere).
+    ff1_ms = attn_ms = None
     try:
+        eng.profile_kernel("ff1")
+        for _ in range(args.steps):
+            st.step()
+        ff1_ms = eng.profile_result()
         eng.profile_kernel("attn")
-        for i in range(args.steps):
-            step(i, cur, oth)
-            cur, oth = oth, cur
+        for _ in range(args.steps):
+            st.step()
         attn_ms = (eng.profile_result() or {}).get("attn")
-    except Exception:   # noqa: BLE001
-        attn_ms = None
+    except Exception:   # noqa: BLE001  (never allowed to break the bench line)
+        if sp is not None:
+            raise
     clocks = sampler.stop() if sampler else None
     if world > 1:
         tt = torch.tensor([ms], device=dev)
@@ -293,9 +414,10 @@ def run_ours(args):
 
     # ---- end-to-end through the public module API with host buffers (`e2e`)
     hx = torch.randn(B, 16, side, side).to(bf).pin_memory()
-    hc, he, hp = ctrl.cpu().pin_memory(), enc.cpu().pin_memory(), pooled.cpu().pin_memory()
+    hc, he, hp = st.full[1].cpu().pin_memory(), st.enc.cpu().pin_memory(), st.pooled.cpu().pin_memory()
     ht = torch.full((B,), 741.44).pin_memory()
     hout = torch.empty(B, 16, side, side, dtype=bf).pin_memory()
+    e2e_velocity = {}
 
     def e2e_step():
         with torch.no_grad():
@@ -304,6 +426,7 @@ def run_ours(args):
                       pooled_projections=hp.to(dev, non_blocking=True), timestep=ht.to(dev, non_blocking=True),
                       return_dict=False)[0]
         hout.copy_(v, non_blocking=True)
+        e2e_velocity["v"] = v
 
     for _ in range(max(1, args.warmup)):
         e2e_step()
@@ -324,17 +447,23 @@ def run_ours(args):
 
     # ---- per-kernel-class breakdown of one extra, instrumented step (not part of any timed number)
     breakdown = None
-    if rank == 0 and not args.no_breakdown:
-        eng.profile_kernel("*")
-        step(0, cur, oth)
-        torch.cuda.synchronize()
-        bd = eng.profile_result()
-        breakdown = {k: dict(launches=len(v), total_ms=round(sum(v), 4)) for k, v in bd.items()}
+    if not args.no_breakdown:
+        breakdown = instrumented_step(eng, st, rank)
 
-    # ---- CPU baseline on rank 0 (bounded sample)
+    # ---- CPU baseline on rank 0 (bounded sample); on C2 the same timed CPU forward is also the parity reference of
+    #      image 0 of the e2e call above (same bf16-rounded weights, same inputs)
     cpu = None
+    parity = None
     if rank == 0 and not args.no_cpu:
-        cpu = cpu_reference_sample()
+        torch.cuda.synchronize()
+        cpu, parity = cpu_baseline_leg(model if args.workload == "c2" else None, (hx, hc, he, hp, ht), hout)
+
+    # ---- the partitioned north-star workloads at this world size (C2 headline only; placed last in the JSON line)
+    ns = None
+    if args.workload == "c2" and not args.no_north_star:
+        release(eng)
+        del st
+        ns = north_star_scaling(model, world, rank, dev, barrier)
 
     if rank == 0:
         peaks = measured_peaks()
@@ -345,11 +474,13 @@ def run_ours(args):
         step_flops = (gemm_f + attn_f) * images_total / world      # per-GPU share of one step
         img_steps = images_total * args.steps
         value = img_steps / (ms / 1e3)
+        n_layers, n_dual = cfg["num_layers"], len(cfg["dual_attention_layers"])
         # FF1 launch = image FF1 [B*2N,1536]x[1536,6144] grouped with the text FF1 [B*T,...] (absent in the last block)
         streams = 3 if args.workload == "c5" else 2
-        ff1_flops = 2.0 * (B * streams * N + B * T * 23.0 / 24.0) * 1536 * 6144
+        rows_local = N // (world if mode == "sp" else 1)
+        ff1_flops = 2.0 * (B * streams * rows_local + B * T * (n_layers - 1.0) / n_layers) * 1536 * 6144
         ff1_avg_ms = (sum(ff1_ms["ff1"]) / len(ff1_ms["ff1"])) if ff1_ms and ff1_ms.get("ff1") else None
-        # DRAM traffic of the same kernel from the committed `ncu --set full` capture (dram__bytes_read + write per launch)
+        # DRAM traffic of the same kernel: NOT measured in this run - read from the committed `ncu --set full` capture
         traffic = None
         traffic_source = None
         try:
@@ -358,9 +489,9 @@ def run_ours(args):
                     for k in prof if "gemm_kernel<1>" in k["Kernel Name"]]
             if vals:
                 traffic = round(sum(vals) / len(vals) * 1e6)
-                traffic_source = ("profiles/r01d_ncu_full_kernels.json: dram__bytes_read.sum + dram__bytes_write.sum per launch "
-                                  "of the FF1 image problem alone (M=16384; algorithmic 50.3 MB A + 18.9 MB W read + 201.3 MB "
-                                  "written, part of which is still in L2 when the launch ends)")
+                traffic_source = ("from committed capture profiles/r01d_ncu_full_kernels.json (not measured in this run): "
+                                  "dram__bytes_read.sum + dram__bytes_write.sum per launch of the FF1 image problem alone "
+                                  "(M=16384; algorithmic 50.3 MB A + 18.9 MB W read + 201.3 MB written)")
         except (OSError, KeyError, ValueError):
             pass
         roof = None
@@ -376,9 +507,9 @@ def run_ours(args):
         # the dominant kernel by time is the joint attention: it is the `roofline` entry; the largest GEMM follows
         roof_attn = None
         try:
-            n_attn = 24 + 13                                              # joint + image-only (dual) calls per step
+            n_attn = n_layers + n_dual                                    # joint + image-only (dual) calls per step
             if mode == "sp":
-                pass   # the 'attn' class also holds the all-to-all glue kernels there: GEMM entry only
+                pass   # the 'attn' class also holds the residual-add kernels there: GEMM entry only
             elif attn_ms:
                 roof_attn = attention_roofline(attn_ms, attn_f * images_total / world, n_attn, peaks)
             elif breakdown and breakdown.get("attn"):
@@ -397,40 +528,46 @@ def run_ours(args):
             config=workload_config(args.workload, world),
             batch_steps_per_sec=round(args.steps * (world if mode == "dp_weak" else 1) / (ms / 1e3), 3),
             step_tflop=round(step_flops / 1e12, 3), lr_chains_folded=bool(eng.fold_lr_chains),
+            attention_softmax=("pre-scaled bounded scores (QK-RMSNorm bound checked per attention module)"
+                               if any(b.attn.score_bound is not None for b in eng.blocks) else "online"),
             step_tflops_achieved=round(step_flops * world / (ms / args.steps / 1e3) / 1e12, 1),   # whole job
             step_frac_of_sustained_peak=round(step_flops / (ms / args.steps / 1e3) / 1e12 / peaks["tf_sustained"], 4),
             e2e=dict(value=round(img_steps / (e2e_ms / 1e3), 3), unit=UNIT, h2d_bytes_per_step=h2d,
                      d2h_bytes_per_step=d2h, ms_per_step=round(e2e_ms / args.steps, 3),
                      api="dit4sr_b200.SD3Transformer2DModel.forward, pinned host inputs, velocity copied back"),
             gpu_launches=launches, clocks=clocks, roofline=roof_attn, roofline_gemm=roof, cpu_baseline=cpu,
-            kernel_breakdown_ms=breakdown,
+            parity=parity, kernel_breakdown_ms=breakdown, north_star_scaling=ns,
         )
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
 
 
-def cpu_reference_sample(max_seconds=40.0, steps=3, warmup=1):
-    """Times the oracle (plain-PyTorch fp32 restatement of the reference) on the host cores: B=1, 512px, 24 blocks."""
+def cpu_reference_sample(max_seconds=40.0, steps=3, warmup=1, state_dict=None, inputs=None):
+    """Times the oracle (plain-PyTorch fp32 restatement of the reference) on the host cores: B=1, 512px, 24 blocks.
+    With `state_dict` / `inputs` (the benchmarked model's weights and image 0 of its batch) the same forward is also the
+    parity reference; returns (cpu_baseline entry, velocity)."""
     import torch
     from oracle import dit4sr_oracle as O
     ncpu = os.cpu_count() or 1
     torch.set_num_threads(ncpu)
-    cfg = O.sd35_medium_config(pos_embed_max_size=96)   # the cropped 32x32 window is what the step reads
-    man = O.state_dict_manifest(cfg)
-    sd = {}
-    for k, shp in man.items():
-        sd[k] = torch.empty(shp).normal_(0, 0.02)
-    for k in sd:
-        if ".norm_" in k and sd[k].dim() == 1 and sd[k].numel() == 64:
-            sd[k] = 1 + 0.1 * torch.randn(64)
-    inp = O.make_inputs(cfg, 1, 64, 64, 333, seed=1, timestep=741.44)
+    if state_dict is None:
+        cfg = O.sd35_medium_config(pos_embed_max_size=96)   # the cropped 32x32 window is what the step reads
+        sd = {k: torch.empty(shp).normal_(0, 0.02) for k, shp in O.state_dict_manifest(cfg).items()}
+        for k in sd:
+            if ".norm_" in k and sd[k].dim() == 1 and sd[k].numel() == 64:
+                sd[k] = 1 + 0.1 * torch.randn(64)
+        inp = O.make_inputs(cfg, 1, 64, 64, 333, seed=1, timestep=741.44)
+    else:
+        cfg = O.sd35_medium_config(**{k: v for k, v in SD35_MEDIUM_CONFIG.items()})
+        sd, inp = state_dict, inputs
     times = []
     t_begin = time.perf_counter()
+    v = None
     with torch.no_grad():
         for i in range(warmup + steps):
             t0 = time.perf_counter()
-            O.model_forward(sd, cfg, *inp, as_written=True)
+            v = O.model_forward(sd, cfg, *inp, as_written=True)
             dt = time.perf_counter() - t0
             if i >= warmup:
                 times.append(dt)
@@ -441,7 +578,24 @@ def cpu_reference_sample(max_seconds=40.0, steps=3, warmup=1):
     sec = sum(times) / len(times)
     return dict(value=round(1.0 / sec, 4), unit=UNIT, cores=torch.get_num_threads(), kind="port",
                 sample=f"oracle (plain PyTorch fp32 restatement of the reference), B=1 512px 24 blocks, "
-                       f"{len(times)} timed step(s) after {warmup} warm-up, {sec:.2f} s/step, host cpu_count={ncpu}")
+                       f"{len(times)} timed step(s) after {warmup} warm-up, {sec:.2f} s/step, host cpu_count={ncpu}"), v
+
+
+def cpu_baseline_leg(model, host_inputs, host_velocity):
+    """The `cpu_baseline` entry and, when `model` is given, the `parity` entry: the CPU restatement of the reference runs
+    image 0 of the benchmarked call on the benchmarked model's own (bf16-rounded) weights, and its velocity is compared
+    with what the GPU path returned for that image.  The only place of the product arm that executes oracle/."""
+    if model is None:
+        cpu, _ = cpu_reference_sample()
+        return cpu, None
+    sd_cpu = {k: v.detach().float().cpu() for k, v in model.state_dict().items()}
+    inp = tuple(t[:1].float() for t in host_inputs)
+    cpu, v_ref = cpu_reference_sample(state_dict=sd_cpu, inputs=inp)
+    v_gpu = host_velocity[:1].float()
+    parity = dict(rel_l2=float(((v_gpu - v_ref).norm() / v_ref.norm()).item()), tolerance=1e-2,
+                  what="velocity of image 0 of the benchmarked C2 call (B=8, 24 blocks, bf16, through the module API) "
+                       "against the fp32 CPU restatement of the reference on the same weights and inputs")
+    return cpu, parity
 
 
 def run_reference(args):
@@ -497,6 +651,8 @@ def main():
     ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-breakdown", action="store_true", help="skip the per-kernel breakdown step")
+    ap.add_argument("--no-north-star", action="store_true",
+                    help="skip the extra C4 (Ulysses) / C3 (strong data-parallel) measurements of the default run")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.impl == "reference":

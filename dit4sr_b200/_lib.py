@@ -23,6 +23,11 @@ class DwconvParams(C.Structure):
                 ("grid_w", c_int), ("lr_grid_h", c_int), ("lr_row_offset", c_int)]
 
 
+class GemmSp(C.Structure):
+    _fields_ = [("world", c_int), ("rank", c_int), ("own_heads_only", c_int), ("inner_dim", c_int), ("col0", c_int),
+                ("rows_dst", c_i64), ("row0", c_i64), ("peer", c_vp * 8)]
+
+
 class GemmParams(C.Structure):
     _fields_ = [("A", c_vp), ("lda", c_i64), ("a_batch_stride", c_i64),
                 ("W", c_vp), ("ldw", c_i64), ("bias", c_vp),
@@ -31,7 +36,7 @@ class GemmParams(C.Structure):
                 ("gate", c_vp), ("gate_batch_stride", c_i64),
                 ("resid", c_vp), ("ldr", c_i64), ("r_batch_stride", c_i64),
                 ("norm_w0", c_vp), ("norm_w1", c_vp), ("sec_cols", c_int), ("eps", c_float),
-                ("dbl_row_offset", c_i64)]
+                ("dbl_row_offset", c_i64), ("sp", C.POINTER(GemmSp))]
 
 
 SP_MAX_RANKS, SP_CHANNELS = 8, 4

@@ -778,7 +778,9 @@ extern "C" int dit4sr_attn_fwd(const dit4sr_attn_params* p, void* stream_) {
   int rc = dit4sr_check_device();
   if (rc != 0) return rc;
 
-  const int variant = p->variant == 0 ? 3 : p->variant;
+  // default: whichever KV tile size pads the sequence less (96-key double-buffered tiles unless 128 divides it better)
+  const int pad96 = (p->seq_kv + 95) / 96 * 96, pad128 = (p->seq_kv + 127) / 128 * 128;
+  const int variant = p->variant != 0 ? p->variant : (pad96 <= pad128 ? 3 : 2);
   const int bkv = variant == 3 ? v3::BKV : BKV;
   CUtensorMap tmQ, tmK, tmV;
   const uint64_t dims[3] = {(uint64_t)p->heads * DH, (uint64_t)p->seq_kv, (uint64_t)p->batches};

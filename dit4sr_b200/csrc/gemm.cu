@@ -48,6 +48,9 @@ struct Problem {
   float eps;
   int64_t dbl_row_offset;
   int c_reduce;   // GATE_RESID with resid == C: the epilogue adds gate*y into C with TMA reduce-adds (maps.c)
+  // Ulysses scatter (dit4sr_gemm_sp): bf16 output heads go straight to the attention-side buffers of the owning ranks
+  int sp_world, sp_rank, sp_own_only, sp_D, sp_col0;
+  int64_t sp_rows_dst, sp_row0;
 };
 
 // Tail splitting: with T tiles on G CTAs the last T mod G tiles would occupy a whole extra wave with most SMs idle
@@ -60,6 +63,7 @@ struct Group {
   int split_begin;    // first tile (in schedule order) that is cut into column slices
   int split;          // 1 (no splitting), 2 or 4 slices per 256-column tile
   Problem p[MAX_PROBLEMS];
+  void* sp_peer[DIT4SR_SP_MAX_RANKS];   // peer-mapped [B, rows_dst, 3, D/world] buffers (problems with sp_world > 0)
 };
 
 struct Maps {
@@ -265,6 +269,20 @@ gemm_kernel(const __grid_constant__ Maps maps, const __grid_constant__ Group grp
           const int c0 = pass * 64;                      // column offset inside the tile
           if (c0 < n_valid) {
             const int cols = min(64, n_valid - c0);      // 32 or 64
+            // where this head goes: the local C, or (sequence parallelism) the q|k|v buffer of the rank owning the head
+            __nv_bfloat16* dst_base = Cb + c0;
+            int64_t dst_ld = P.ldc;
+            bool dst_skip = false;
+            if (P.sp_world > 0) {
+              const int col = P.sp_col0 + n_base + c0;
+              const int sec = col / P.sp_D, within = col - sec * P.sp_D;
+              const int Dl = P.sp_D / P.sp_world;
+              const int owner = within / Dl;
+              dst_skip = P.sp_own_only != 0 && owner != P.sp_rank;     // replicated rows: keep my own heads only
+              dst_base = reinterpret_cast<__nv_bfloat16*>(grp.sp_peer[owner]) +
+                         (((int64_t)tc.b * P.sp_rows_dst + P.sp_row0) * 3 + sec) * Dl + (within - owner * Dl);
+              dst_ld = 3 * (int64_t)Dl;
+            }
             uint32_t v[64];
             ptx::tmem_ld32(taddr + c0, *reinterpret_cast<uint32_t(*)[32]>(&v[0]));
             ptx::tmem_ld32(taddr + c0 + 32, *reinterpret_cast<uint32_t(*)[32]>(&v[32]));
@@ -353,14 +371,14 @@ gemm_kernel(const __grid_constant__ Maps maps, const __grid_constant__ Group grp
                 wr[i] = u;
               }
               __syncwarp();
-              if (seg * 8 < cols) {
+              if (seg * 8 < cols && !dst_skip) {
 #pragma unroll
                 for (int r4 = 0; r4 < 8; ++r4) {
                   const int rl = r4 * 4 + sub;
                   const uint4 u = *reinterpret_cast<const uint4*>(stg + rl * EPI_ROW_BYTES + seg * 16);
                   const int rg = row_base + rl;
                   if (rg < P.rows)
-                    *reinterpret_cast<uint4*>(Cb + (rg + row_shift) * P.ldc + c0 + seg * 8) = u;
+                    *reinterpret_cast<uint4*>(dst_base + (rg + row_shift) * dst_ld + seg * 8) = u;
                 }
               }
             }
@@ -621,6 +639,8 @@ extern "C" int dit4sr_gemm_bf16_grouped(const dit4sr_gemm_params* probs, int cou
   Maps maps;
   Group g;
   plan_tiles(probs, count, host::sm_count(), tail_split_enabled(), g);
+  bool have_sp = false;
+  for (int r = 0; r < DIT4SR_SP_MAX_RANKS; ++r) g.sp_peer[r] = nullptr;
   for (int i = 0; i < count; ++i) {
     const dit4sr_gemm_params* p = &probs[i];
     {
@@ -659,6 +679,31 @@ extern "C" int dit4sr_gemm_bf16_grouped(const dit4sr_gemm_params* probs, int cou
     P.sec_cols = p->sec_cols > 0 ? p->sec_cols : p->N;
     P.eps = p->eps;
     P.dbl_row_offset = p->dbl_row_offset;
+    P.sp_world = 0;
+    if (p->sp != nullptr) {
+      const dit4sr_gemm_sp* sp = p->sp;
+      DIT4SR_REQUIRE(sp->world >= 1 && sp->world <= DIT4SR_SP_MAX_RANKS && sp->rank >= 0 && sp->rank < sp->world &&
+                         sp->inner_dim > 0 && sp->inner_dim % (64 * sp->world) == 0 && sp->col0 >= 0 && sp->col0 % 64 == 0 &&
+                         sp->col0 + p->N <= 3 * sp->inner_dim && sp->rows_dst > 0 && sp->row0 >= 0,
+                     DIT4SR_E_BADARG, "gemm: bad sp scatter description");
+      DIT4SR_REQUIRE(p->c_dtype == DIT4SR_DT_BF16 && p->N % 64 == 0 &&
+                         (epilogue == DIT4SR_EPI_QKV_NORM || epilogue == DIT4SR_EPI_BIAS),
+                     DIT4SR_E_BADARG, "gemm: sp scatter needs a bf16 q|k|v projection (BIAS or QKV_NORM epilogue)");
+      for (int r = 0; r < sp->world; ++r) {
+        DIT4SR_REQUIRE(sp->peer[r] != nullptr && host::aligned16(sp->peer[r]), DIT4SR_E_BADARG, "gemm: sp peer %d missing", r);
+        DIT4SR_REQUIRE(!have_sp || g.sp_peer[r] == sp->peer[r], DIT4SR_E_BADARG,
+                       "gemm: the problems of one launch must scatter into the same peer buffers");
+        g.sp_peer[r] = sp->peer[r];
+      }
+      have_sp = true;
+      P.sp_world = sp->world;
+      P.sp_rank = sp->rank;
+      P.sp_own_only = sp->own_heads_only;
+      P.sp_D = sp->inner_dim;
+      P.sp_col0 = sp->col0;
+      P.sp_rows_dst = sp->rows_dst;
+      P.sp_row0 = sp->row0;
+    }
     // in-place gated residual -> TMA reduce-add epilogue (DIT4SR_GEMM_REDUCE=0 keeps the load/add/store epilogue)
     static int reduce_enabled = -1;
     if (reduce_enabled < 0) { const char* e = getenv("DIT4SR_GEMM_REDUCE"); reduce_enabled = (e == nullptr || e[0] != '0') ? 1 : 0; }

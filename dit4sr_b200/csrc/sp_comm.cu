@@ -211,7 +211,9 @@ int dit4sr_sp_barrier(const dit4sr_sp_comm* comm, int channel, void* stream_) {
 int dit4sr_a2a_qkv(const dit4sr_sp_comm* comm, const dit4sr_a2a_params* p, void* stream_) {
   int rc = spc::check_comm(comm, "a2a_qkv");
   if (rc != 0) return rc;
-  DIT4SR_REQUIRE(p && p->src, DIT4SR_E_BADARG, "a2a_qkv: null argument");
+  DIT4SR_REQUIRE(p, DIT4SR_E_BADARG, "a2a_qkv: null argument");
+  if (p->src == nullptr)   // the projections' epilogues already stored into the peers (dit4sr_gemm_params.sp)
+    return p->no_barrier ? 0 : dit4sr_sp_barrier(comm, DIT4SR_SP_CH_QKV, stream_);
   DIT4SR_REQUIRE(p->batches > 0 && p->image_rows > 0 && p->text_rows >= 0 && p->heads > 0 && p->heads % comm->world == 0,
                  DIT4SR_E_BADARG, "a2a_qkv: bad sizes (heads %d must divide over %d ranks)", p->heads, comm->world);
   DIT4SR_REQUIRE(p->src_row_stride % 8 == 0 && p->src_batch_stride % 8 == 0 && host::aligned16(p->src), DIT4SR_E_ALIGN,

@@ -240,6 +240,9 @@ class Engine:
         # capturing NCCL collectives inside the graph hung on 2 GPUs in round 1: the torch.distributed path launches
         # directly; the NVLink peer-memory path consists of this library's kernels only and is captured
         self.sp_graph = _os.environ.get("DIT4SR_SP_GRAPH", "1" if (sp is not None and sp.peer) else "0") == "1"
+        # peer path: q|k|v heads are stored into the owning ranks' buffers by the projection epilogues themselves
+        # (DIT4SR_SP_FUSED_SCATTER=0: a separate scatter kernel after the projections, kept for A/B)
+        self.sp_fused_scatter = _os.environ.get("DIT4SR_SP_FUSED_SCATTER", "1") != "0"
         self._pos: Dict[Tuple, torch.Tensor] = {}
 
     # ------------------------------------------------------------------------------------------------ profiling
@@ -423,6 +426,26 @@ class Engine:
         if ap.has_text:
             g1.append(dict(A=nc, W=ap.add.w, bias=ap.add.b, out=qkv[:, I:S], epilogue=E,
                            **(dict(norm_w0=ap.waq, norm_w1=ap.wak, sec_cols=D) if ap.qk_norm else {})))
+        fused_scatter = self.sp is not None and self.sp.peer and self.sp_fused_scatter
+        if fused_scatter:
+            # sequence -> head all-to-all fused into the projection epilogues: every problem that writes into the joint
+            # q|k|v buffer stores its heads straight into the owning ranks' attention-side buffers instead
+            P, rk = self.sp.world, self.sp.rank
+            T_ = T if ap.has_text else 0
+            base = qkv.data_ptr()
+            row_bytes, sec_bytes = qkv.stride(1) * 2, D * 2
+            keep = ws.setdefault("_sp_desc", [])
+            keep.clear()
+            for pr in g1 + g2:
+                off = pr["out"].data_ptr() - base
+                if not 0 <= off < qkv.stride(0) * 2:
+                    continue                                   # a scratch output (as-written LR stage 1): stays local
+                row, col = divmod(off, row_bytes)
+                text = row >= I
+                d = ops.gemm_sp(P, rk, D, P * I + T_, ws["qkv_sp_peers"], row0=(P * I + row - I) if text else rk * I + row,
+                                col0=col // 2, own_heads_only=text)
+                keep.append(d)
+                pr["sp"] = d
         self._gg("qkv_group", g1)
         if g2:
             self._gg("lr2_group", g2)
@@ -459,7 +482,7 @@ class Engine:
             # one scatter kernel + arrival barrier, attention with the way back fused into its epilogue, arrival barrier
             Ssp = P * I + T
             qs = ws["qkv_sp"][:B * Ssp * 3 * Dl].view(B, Ssp, 3, Dl)
-            R("a2a", ops.a2a_qkv, sp.comm, qkv[:, :S], I, T, H, ws["qkv_sp_peers"])
+            R("a2a", ops.a2a_qkv, sp.comm, None if self.sp_fused_scatter else qkv[:, :S], I, T, H, ws["qkv_sp_peers"])
             seq_q = P * I if (last or not T) else Ssp
             R("attn", ops.attention, qs[:, :, 0], qs[:, :, 1], qs[:, :, 2], o, Hl, seq_q=seq_q,
               score_bound=ap.score_bound, sp_out=ws["sp_out"])

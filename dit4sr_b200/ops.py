@@ -111,8 +111,18 @@ def add_bf16(dst, src):
     _count()
 
 
+def gemm_sp(world, rank, inner_dim, rows_dst, peers, row0, col0=0, own_heads_only=False):
+    """dit4sr_gemm_sp: scatter description of one q|k|v projection under sequence parallelism (kept alive by the caller)."""
+    sp = _lib.GemmSp()
+    sp.world, sp.rank, sp.own_heads_only, sp.inner_dim, sp.col0 = world, rank, 1 if own_heads_only else 0, inner_dim, col0
+    sp.rows_dst, sp.row0 = rows_dst, row0
+    for r, ptr in enumerate(peers):
+        sp.peer[r] = ptr
+    return sp
+
+
 def _gemm_params(p, A, W, bias, out, epilogue=EPI_BIAS, gate=None, resid=None, norm_w0=None, norm_w1=None, sec_cols=0,
-                 eps=1e-6, dbl_row_offset=0):
+                 eps=1e-6, dbl_row_offset=0, sp=None):
     A = _as3(A)
     out = _as3(out)
     _req(A, torch.bfloat16, "A")
@@ -148,6 +158,8 @@ def _gemm_params(p, A, W, bias, out, epilogue=EPI_BIAS, gate=None, resid=None, n
         p.norm_w0, p.norm_w1 = _ptr(norm_w0), _ptr(norm_w1)
         p.sec_cols, p.dbl_row_offset = sec_cols or N, dbl_row_offset
     p.eps = eps
+    if sp is not None:
+        p.sp = C.pointer(sp)
 
 
 def gemm(A, W, bias, out, epilogue=EPI_BIAS, **kw):
@@ -248,16 +260,19 @@ def sp_barrier(comm, channel):
 
 def a2a_qkv(comm, src, image_rows, text_rows, heads, peers, no_barrier=False):
     """src bf16 [B, image_rows + text_rows, 3*heads*64] (my tokens, all heads) -> every rank's [B, P*image_rows +
-    text_rows, 3, heads*64/P] buffer (`peers`: device pointers as mapped here), then the arrival barrier."""
-    _req(src, torch.bfloat16, "src")
+    text_rows, 3, heads*64/P] buffer (`peers`: device pointers as mapped here), then the arrival barrier.
+    src=None: the projections already stored into the peers (gemm `sp`), arrival barrier only."""
     p = A2aParams()
-    p.src, p.src_row_stride, p.src_batch_stride = _ptr(src), src.stride(1), src.stride(0)
+    if src is not None:
+        _req(src, torch.bfloat16, "src")
+        p.src, p.src_row_stride, p.src_batch_stride = _ptr(src), src.stride(1), src.stride(0)
+        p.batches = src.shape[0]
     for r, ptr in enumerate(peers):
         p.peer[r] = ptr
-    p.batches, p.image_rows, p.text_rows, p.heads = src.shape[0], image_rows, text_rows, heads
+    p.image_rows, p.text_rows, p.heads = image_rows, text_rows, heads
     p.no_barrier = 1 if no_barrier else 0
     check(_lib.load().dit4sr_a2a_qkv(C.byref(comm), C.byref(p), _stream()), "dit4sr_a2a_qkv")
-    _count(1 if no_barrier else 2)
+    _count((0 if src is None else 1) + (0 if no_barrier else 1))
 
 
 def a2a_out(comm, src, image_rows, text_rows, heads, peers, dst_row_stride, dst_batch_stride, no_barrier=False):

@@ -111,6 +111,20 @@ enum {
   DIT4SR_EPI_GATE_RESID = 4
 };
 enum { DIT4SR_DT_BF16 = 0, DIT4SR_DT_F32 = 1 };
+#define DIT4SR_SP_MAX_RANKS 8
+/* Ulysses sequence parallelism: a q|k|v projection (BIAS / QKV_NORM epilogue, bf16 C) may store its output heads
+ * straight into the attention-side buffers of the ranks that own them instead of C (the sequence -> head all-to-all fused
+ * into the GEMM epilogue; NVLink peer stores).  Column c of this problem is column col0 + c of the [3 * inner_dim] q|k|v
+ * row: section s = col / inner_dim, head owner p = (col % inner_dim) / (inner_dim / world).  Row r of batch b lands in
+ *   peer[p] [b, row0 + r, s, col % (inner_dim / world)]   of a bf16 [batches, rows_dst, 3, inner_dim / world] buffer.
+ * own_heads_only: the rows are replicated on every rank (text tokens): store only this rank's own heads (into peer[rank]).
+ * C / ldc still describe a valid local tensor (shape checks) but are not written.  Follow with dit4sr_a2a_qkv(src = NULL)
+ * (arrival barrier).  All problems of one grouped launch must name the same peer buffers. */
+typedef struct {
+  int world; int rank; int own_heads_only; int inner_dim; int col0;
+  int64_t rows_dst; int64_t row0;
+  void* peer[DIT4SR_SP_MAX_RANKS];
+} dit4sr_gemm_sp;
 typedef struct {
   const void* A; int64_t lda; int64_t a_batch_stride;
   const void* W; int64_t ldw;
@@ -122,6 +136,7 @@ typedef struct {
   const float* resid; int64_t ldr; int64_t r_batch_stride;
   const float* norm_w0; const float* norm_w1;             /* QKV_NORM: fp32 [64] each (NULL = no norm) */
   int sec_cols; float eps; int64_t dbl_row_offset;
+  const dit4sr_gemm_sp* sp;                               /* NULL: plain store into C */
 } dit4sr_gemm_params;
 int dit4sr_gemm_bf16(const dit4sr_gemm_params* p, void* stream);
 /* Up to DIT4SR_GEMM_MAX_GROUP independent problems sharing one epilogue kind, run by ONE persistent launch (e.g. the HQ,
@@ -154,8 +169,9 @@ int dit4sr_gemm_schedule(const dit4sr_gemm_params* problems, int count, int sm_c
  *                          from the checkpoint's norm weights; the host refuses the mode when it does not hold.
  * exp_offload: 0 = default; 1, 2, 3 = 0/8, 2/8, 4/8 of the exponentials evaluated by a polynomial on the FMA pipe instead
  *              of MUFU.EX2 (tuning knob: same results to within bf16 rounding of P).
- * variant:     0 = default; 3 = independent query tiles with double-buffered 96-key score tiles (the default);
- *              2 = three 128-key score buffers rotating over the two query tiles (round 1's pipeline, kept for A/B).
+ * variant:     3 = independent query tiles with double-buffered 96-key score tiles; 2 = three 128-key score buffers
+ *              rotating over the two query tiles (round 1's pipeline); 0 = default = whichever of the two KV tile sizes
+ *              pads seq_kv less (same speed per score, so the padding decides).
  * sp_out (Ulysses sequence parallelism, NULL otherwise): the kernel's epilogue stores each output row straight into the
  *              token-side buffer of the rank that owns the token, through NVLink peer memory (the head -> sequence
  *              all-to-all fused into the attention kernel).  Query row i < world*rows_per_rank belongs to rank
@@ -166,7 +182,6 @@ int dit4sr_gemm_schedule(const dit4sr_gemm_params* problems, int count, int sm_c
  */
 enum { DIT4SR_ATTN_ONLINE = 0, DIT4SR_ATTN_PRESCALED = 1 };
 #define DIT4SR_ATTN_MAX_SCORE_BOUND 60.0f
-#define DIT4SR_SP_MAX_RANKS 8
 typedef struct {
   int world; int rows_per_rank; int col_offset;
   void* o_peer[DIT4SR_SP_MAX_RANKS];
@@ -222,6 +237,7 @@ int dit4sr_sp_barrier(const dit4sr_sp_comm* comm, int channel, void* stream);
  *     peer[p][b, rank*image_rows + s, {q,k,v}, Dl] with the columns of p's heads (Dl = heads*64 / world); the text rows are
  *     replicated, so only this rank's own head slice is copied, to peer[rank][b, world*image_rows + t, ...].
  *     peer[p]: bf16 [batches, world*image_rows + text_rows, 3, Dl] contiguous, the same shape on every rank.
+ *     src == NULL: the projections already stored into the peers (dit4sr_gemm_params.sp): arrival barrier only.
  *  dit4sr_a2a_out: the way back.  src = bf16 [batches, world*image_rows + text_rows, Dl] contiguous (my heads, all tokens)
  *     -> peer[r][b, s, rank*Dl ...] for the image rows rank r owns, and the text rows to every peer at rows image_rows.. ;
  *     peer[r]: bf16 [batches, >= image_rows + text_rows, heads*64] with dst_row_stride / dst_batch_stride.

@@ -16,6 +16,7 @@ STRUCTS = {
     "dit4sr_ln_modulate_params": _lib.LnModulateParams,
     "dit4sr_dwconv3x3_params": _lib.DwconvParams,
     "dit4sr_gemm_params": _lib.GemmParams,
+    "dit4sr_gemm_sp": _lib.GemmSp,
     "dit4sr_attn_params": _lib.AttnParams,
     "dit4sr_attn_sp_out": _lib.AttnSpOut,
     "dit4sr_sp_comm": _lib.SpComm,

@@ -275,6 +275,30 @@ def test_attention_prescaled_large_and_small_scores_stay_finite(ops):
     assert rel(o.float(), ref) < 6e-3
 
 
+@pytest.mark.parametrize("prescaled", [False, True])
+def test_attention_at_the_c4_per_rank_shape(ops, prescaled):
+    """BASELINE config C4 on 8 ranks: every rank runs 3 heads over the whole S = 33101 joint sequence (345 KV tiles of 96).
+    fp32 reference by query chunks (the full score matrix would not fit comfortably)."""
+    torch.manual_seed(0)
+    B, H, S = 1, 3, 33101
+    D = H * 64
+    qkv = torch.randn(B, S, 3 * D, device="cuda")
+    if prescaled:
+        qkv[..., :D] *= LOG2E_OVER_8
+    qkv = qkv.bfloat16()
+    q, k, v = qkv[..., :D], qkv[..., D:2 * D], qkv[..., 2 * D:]
+    o = torch.zeros(B, S, D, device="cuda", dtype=torch.bfloat16)
+    ops.attention(q, k, v, o, H, score_bound=30.0 if prescaled else None)
+    hd = lambda t: t.float().reshape(B, -1, H, 64).transpose(1, 2)
+    worst = 0.0
+    for s0 in range(0, S, 4096):
+        ref = torch.nn.functional.scaled_dot_product_attention(
+            hd(q[:, s0:s0 + 4096]), hd(k), hd(v), scale=math.log(2.0) if prescaled else None)
+        ref = ref.transpose(1, 2).reshape(B, -1, D)
+        worst = max(worst, rel(o[:, s0:s0 + 4096].float(), ref))
+    assert worst < 4e-3
+
+
 def test_attention_mode_is_validated(ops):
     q = torch.zeros(1, 128, 64, device="cuda", dtype=torch.bfloat16)
     o = torch.zeros_like(q)

@@ -204,3 +204,109 @@ def test_feature_extraction_outputs():
         _, rf = O.model_forward(sdg, cfg, hs.cuda(), lr.cuda(), enc.cuda(), pooled.cuda(), t.cuda(), as_written=False,
                                 feat_extract_layers=(0, 1), feat_extract="lq_feat")
     assert rel(feats[1]["extract_feat"].float().cpu(), rf[1].cpu()) <= VEL_TOL
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# Round 2: the configurations round 1 left untested (VERDICT "what's weak" 1)
+def test_c4_shape_2048px_velocity():
+    """BASELINE config C4 shape on one GPU: 2048px (16384 HQ + 16384 LR + 333 text tokens, S = 33101), 2 blocks (1 dual),
+    B=1, against the fp32 oracle."""
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.backends.cudnn.allow_tf32 = False
+    cfg = O.sd35_medium_config(num_layers=2, dual_attention_layers=(0,), pos_embed_max_size=128)
+    sd = O.init_state_dict(cfg, seed=0)
+    inputs = O.make_inputs(cfg, 1, 256, 256, 333, seed=1, timestep=500.0)
+    ref32 = _oracle_gpu(sd, cfg, inputs, torch.float32)
+    e = rel(run(build(cfg, sd), inputs), ref32)
+    print(f"2048px, 2 blocks: cuda-vs-fp32 {e:.3e}")
+    assert e <= VEL_TOL
+
+
+def test_c5_shape_ocr_model_1024px_velocity():
+    """BASELINE config C5 shape: the OCR-branch model at 1024px (3 x 4096 + 333 tokens), 2 blocks (1 dual), B=1."""
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.backends.cudnn.allow_tf32 = False
+    cfg = O.sd35_medium_config(num_layers=2, dual_attention_layers=(0,), pos_embed_max_size=96)
+    sd = O.init_state_dict(cfg, seed=0, ocr=True)
+    inputs = O.make_inputs(cfg, 1, 128, 128, 333, seed=1, timestep=500.0)
+    ref32 = _oracle_gpu(sd, cfg, inputs, torch.float32, ocr=True)
+    e = rel(run(build(cfg, sd, ocr=True), inputs), ref32)
+    print(f"OCR model 1024px, 2 blocks: cuda-vs-fp32 {e:.3e}")
+    assert e <= VEL_TOL
+
+
+def test_ocr_model_unfolded_lr_chains():
+    """fold_lr_chains=False on the 3-stream model (the LR scratch buffer is sized for attn2's 1.5 N rows)."""
+    cfg = O.sd35_medium_config(num_layers=2, dual_attention_layers=(0,), pos_embed_max_size=96)
+    sd = O.init_state_dict(cfg, seed=0, ocr=True)
+    inputs = O.make_inputs(cfg, 1, 32, 32, 77, seed=1, timestep=300.0)
+    ref32 = _oracle_gpu(sd, cfg, inputs, torch.float32, ocr=True)
+    m = build(cfg, sd, ocr=True)
+    m.engine(fold_lr_chains=False)
+    assert rel(run(m, inputs), ref32) <= VEL_TOL
+
+
+def test_c2_batch8_24_blocks_velocity_online_and_prescaled():
+    """The benchmarked configuration itself (C2: B=8, 24 blocks, 512px): every image against the fp32 oracle, with the
+    pre-scaled bounded-score attention (default for this checkpoint) and with the online softmax."""
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.backends.cudnn.allow_tf32 = False
+    cfg = O.sd35_medium_config(pos_embed_max_size=96)
+    sd = O.init_state_dict(cfg, seed=0)
+    inputs = O.make_inputs(cfg, 8, 64, 64, 333, seed=1, timestep=741.44)
+    ref32 = _oracle_gpu(sd, cfg, inputs, torch.float32)
+    from dit4sr_b200.engine import Engine
+    for prescale in (True, False):
+        m = build(cfg, sd)
+        m._engine = Engine(m, prescale_attention=prescale)
+        assert (m._engine.blocks[0].attn.score_bound is not None) == prescale
+        y = run(m, inputs)
+        errs = [rel(y[i], ref32[i]) for i in range(8)]
+        print(f"C2 B=8 24 blocks prescale={prescale}: max per-image rel-L2 {max(errs):.3e}")
+        assert max(errs) <= VEL_TOL
+        del m
+
+
+def test_sampling_loop_psnr_40_steps_full_model():
+    """The north star's PSNR gate at full scale: 40-step loop of the 24-block model at 512px (B=1) against the oracle's
+    bf16 loop on the GPU; PSNR of the final latents >= 40 dB."""
+    from dit4sr_b200.sampler import denoise
+    cfg = O.sd35_medium_config(pos_embed_max_size=96)
+    sd = O.init_state_dict(cfg, seed=0)
+    hs, lr, enc, pooled, _ = O.make_inputs(cfg, 1, 64, 64, 333, seed=1)
+    m = build(cfg, sd)
+    bf = torch.bfloat16
+    out = denoise(m, hs.cuda().to(bf), lr.cuda().to(bf), enc.cuda().to(bf), pooled.cuda().to(bf),
+                  num_inference_steps=40).float().cpu()
+    sdg = {k: v.cuda().to(bf) for k, v in sd.items()}
+    sig = O.flow_match_sigmas(40)
+    x = hs.cuda().to(bf)
+    with torch.no_grad():
+        for i in range(40):
+            t = torch.full((1,), float(sig[i]) * 1000.0, device="cuda")
+            v = O.model_forward(sdg, cfg, x, lr.cuda().to(bf), enc.cuda().to(bf), pooled.cuda().to(bf), t, as_written=False)
+            x = (x.float() + (float(sig[i + 1]) - float(sig[i])) * v.float()).to(v.dtype)
+    ref = x.float().cpu()
+    mse = ((out - ref) ** 2).mean().item()
+    peak = (ref.max() - ref.min()).item()
+    psnr = 10 * torch.log10(torch.tensor(peak ** 2 / mse)).item()
+    print(f"40 steps, 24 blocks: PSNR of final latents vs reference bf16 loop: {psnr:.1f} dB")
+    assert psnr >= 40.0
+
+
+def test_fp32_module_feature_outputs_do_not_alias_the_workspace():
+    """with an fp32 module `.to(fp32)` of the fp32 residual workspace is a view; the hook must copy, otherwise
+    an early block's feature ends up holding the last block's state."""
+    from types import SimpleNamespace as NS
+    cfg = O.sd35_medium_config(num_layers=3, dual_attention_layers=(0,), pos_embed_max_size=96)
+    sd = O.init_state_dict(cfg, seed=0)
+    hs, lr, enc, pooled, t = O.make_inputs(cfg, 1, 64, 64, 20, seed=1)
+    m = build(cfg, sd, dtype=torch.float32)
+    rcfg = NS(train=NS(model=["ts_module"], transformer=NS(feat_extract_layer=[0], feat_extract="hq_feat")))
+    with torch.no_grad():
+        out, feats = m(hs.cuda(), lr.cuda(), enc.cuda(), pooled.cuda(), t.cuda(), return_dict=False, cfg=rcfg)
+    sdg = {k: v.cuda() for k, v in sd.items()}
+    with torch.no_grad():
+        _, rf = O.model_forward(sdg, cfg, hs.cuda(), lr.cuda(), enc.cuda(), pooled.cuda(), t.cuda(), as_written=False,
+                                feat_extract_layers=(0,), feat_extract="hq_feat")
+    assert rel(feats[0]["extract_feat"].float().cpu(), rf[0].cpu()) <= 1e-3
