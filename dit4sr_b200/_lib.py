@@ -71,7 +71,7 @@ class AttnParams(C.Structure):
                 ("lr_row_begin", c_int), ("lr_row_end", c_int),
                 ("batches", c_int), ("heads", c_int), ("seq_q", c_int), ("seq_kv", c_int), ("scale", c_float),
                 ("mode", c_int), ("score_bound", c_float), ("exp_offload", c_int), ("variant", c_int),
-                ("sp_out", C.POINTER(AttnSpOut))]
+                ("sp_out", C.POINTER(AttnSpOut)), ("workspace", c_vp), ("workspace_bytes", c_i64), ("split_kv", c_int)]
 
 
 # every symbol include/dit4sr_b200.h declares: name -> (restype, argtypes)
@@ -85,8 +85,11 @@ SYMBOLS = {
     "dit4sr_gemm_bf16_grouped": (c_int, [C.POINTER(GemmParams), c_int, c_vp]),
     "dit4sr_gemm_schedule": (c_int, [C.POINTER(GemmParams), c_int, c_int, C.POINTER(c_int), c_int]),
     "dit4sr_attn_fwd": (c_int, [C.POINTER(AttnParams), c_vp]),
+    "dit4sr_attn_workspace_bytes": (c_i64, []),
     "dit4sr_patchify": (c_int, [c_vp, c_int, c_vp, c_int, c_int, c_int, c_int, c_vp]),
     "dit4sr_unpatchify": (c_int, [c_vp, c_vp, c_int, c_vp, c_float, c_int, c_int, c_int, c_int, c_vp]),
+    "dit4sr_unpatchify_cfg": (c_int, [c_vp, c_vp, c_int, c_vp, c_float, c_float, c_int, c_int, c_int, c_int, c_vp]),
+    "dit4sr_feature_extract": (c_int, [c_vp, c_i64, c_i64, c_int, c_int, c_int, c_int, c_int, c_int, c_vp, c_vp, c_int, c_vp]),
     "dit4sr_timestep_features": (c_int, [c_vp, c_vp, c_int, c_vp]),
     "dit4sr_silu_cast": (c_int, [c_vp, c_vp, c_i64, c_vp]),
     "dit4sr_add_bf16": (c_int, [c_vp, c_i64, c_i64, c_vp, c_i64, c_i64, c_int, c_int, c_int, c_vp]),

@@ -26,12 +26,66 @@ struct Args {
   // sequence parallelism (sp_world > 0): rows are scattered to the owning ranks' buffers over NVLink (header: sp_out)
   int sp_world, sp_rows_per_rank, sp_col_offset;
   __nv_bfloat16* o_peer[DIT4SR_SP_MAX_RANKS];
+  // v3 work decomposition: 1-D grid of work items; item < n_full = one (query pair, head, batch) over all KV tiles, the
+  // rest are `split` consecutive KV ranges of `tiles_per_slice` tiles each of the remaining (tail) pairs, merged through `part`
+  int q_pairs, heads, n_full, split, tiles_per_slice;
+  float* part;      // [tail pairs][split][256 rows][PART_STRIDE] fp32: unnormalised O row, row sum, reference max
 };
+constexpr int PART_STRIDE = 68;   // 64 + l + m, padded to a multiple of 4 floats
+// scratch of the split-KV tail: (sms - 1) tail pairs x 4 slices x 256 rows
+inline int64_t workspace_bytes(int sms) { return (int64_t)(sms - 1) * 4 * 256 * PART_STRIDE * (int64_t)sizeof(float); }
 
-// Epilogue of one softmax thread: its row of O (64 fp32 TMEM columns at tO) / l (+ LR residual, attention.py:545) -> bf16.
+// One 32-column chunk of a finished output row (already normalised) (+ LR residual, attention.py:545) -> bf16, to the local
+// output or, under sequence parallelism, straight into the buffer of the rank that owns the row's token.
+__device__ __forceinline__ void emit_chunk(const Args& args, float (&f)[32], int row, int head, int b, int c) {
+  const bool add_lr = args.lr_res != nullptr && row >= args.lr_row_begin && row < args.lr_row_end;
+  if (add_lr) {
+    const uint4* lr = reinterpret_cast<const uint4*>(args.lr_res + (int64_t)b * args.lr_batch_stride +
+                                                     (int64_t)row * args.lr_row_stride + head * DH + c * 32);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const uint4 u = __ldg(lr + i);
+      const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&u);
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const float2 ff = __bfloat1622float2(h2[k]);
+        f[8 * i + 2 * k] += ff.x;
+        f[8 * i + 2 * k + 1] += ff.y;
+      }
+    }
+  }
+  uint4 u[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    u[i].x = ptx::pack_bf16(f[8 * i + 0], f[8 * i + 1]);
+    u[i].y = ptx::pack_bf16(f[8 * i + 2], f[8 * i + 3]);
+    u[i].z = ptx::pack_bf16(f[8 * i + 4], f[8 * i + 5]);
+    u[i].w = ptx::pack_bf16(f[8 * i + 6], f[8 * i + 7]);
+  }
+  if (args.sp_world == 0) {
+    uint4* dst = reinterpret_cast<uint4*>(args.o + (int64_t)b * args.o_batch_stride +
+                                          (int64_t)row * args.o_row_stride + head * DH + c * 32);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) dst[i] = u[i];
+  } else {
+    // head -> sequence all-to-all fused into the epilogue: the row goes to the rank that owns its token (text rows:
+    // to every rank), 64-byte stores straight into the peer's buffer over NVLink
+    const int owner = row / args.sp_rows_per_rank;
+    const bool text = owner >= args.sp_world;
+    const int64_t drow = text ? row - (int64_t)(args.sp_world - 1) * args.sp_rows_per_rank
+                              : row - (int64_t)owner * args.sp_rows_per_rank;
+    const int64_t off = (int64_t)b * args.o_batch_stride + drow * args.o_row_stride + args.sp_col_offset + head * DH + c * 32;
+    for (int r = text ? 0 : owner; r < (text ? args.sp_world : owner + 1); ++r) {
+      uint4* dst = reinterpret_cast<uint4*>(args.o_peer[r] + off);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) dst[i] = u[i];
+    }
+  }
+}
+
+// Epilogue of one softmax thread: its row of O (64 fp32 TMEM columns at tO) / l -> emit_chunk.
 __device__ __forceinline__ void store_rows(const Args& args, uint32_t tO, int row, int head, int b, float inv_l) {
   const bool row_ok = row < args.seq_q;
-  const bool add_lr = args.lr_res != nullptr && row >= args.lr_row_begin && row < args.lr_row_end;
 #pragma unroll 1
   for (int c = 0; c < DH / 32; ++c) {
     uint32_t o[32];
@@ -41,48 +95,7 @@ __device__ __forceinline__ void store_rows(const Args& args, uint32_t tO, int ro
       float f[32];
 #pragma unroll
       for (int i = 0; i < 32; ++i) f[i] = __uint_as_float(o[i]) * inv_l;
-      if (add_lr) {
-        const uint4* lr = reinterpret_cast<const uint4*>(args.lr_res + (int64_t)b * args.lr_batch_stride +
-                                                         (int64_t)row * args.lr_row_stride + head * DH + c * 32);
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          const uint4 u = __ldg(lr + i);
-          const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&u);
-#pragma unroll
-          for (int k = 0; k < 4; ++k) {
-            const float2 ff = __bfloat1622float2(h2[k]);
-            f[8 * i + 2 * k] += ff.x;
-            f[8 * i + 2 * k + 1] += ff.y;
-          }
-        }
-      }
-      uint4 u[4];
-#pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        u[i].x = ptx::pack_bf16(f[8 * i + 0], f[8 * i + 1]);
-        u[i].y = ptx::pack_bf16(f[8 * i + 2], f[8 * i + 3]);
-        u[i].z = ptx::pack_bf16(f[8 * i + 4], f[8 * i + 5]);
-        u[i].w = ptx::pack_bf16(f[8 * i + 6], f[8 * i + 7]);
-      }
-      if (args.sp_world == 0) {
-        uint4* dst = reinterpret_cast<uint4*>(args.o + (int64_t)b * args.o_batch_stride +
-                                              (int64_t)row * args.o_row_stride + head * DH + c * 32);
-#pragma unroll
-        for (int i = 0; i < 4; ++i) dst[i] = u[i];
-      } else {
-        // head -> sequence all-to-all fused into the epilogue: the row goes to the rank that owns its token (text rows:
-        // to every rank), 64-byte stores straight into the peer's buffer over NVLink
-        const int owner = row / args.sp_rows_per_rank;
-        const bool text = owner >= args.sp_world;
-        const int64_t drow = text ? row - (int64_t)(args.sp_world - 1) * args.sp_rows_per_rank
-                                  : row - (int64_t)owner * args.sp_rows_per_rank;
-        const int64_t off = (int64_t)b * args.o_batch_stride + drow * args.o_row_stride + args.sp_col_offset + head * DH + c * 32;
-        for (int r = text ? 0 : owner; r < (text ? args.sp_world : owner + 1); ++r) {
-          uint4* dst = reinterpret_cast<uint4*>(args.o_peer[r] + off);
-#pragma unroll
-          for (int i = 0; i < 4; ++i) dst[i] = u[i];
-        }
-      }
+      emit_chunk(args, f, row, head, b, c);
     }
   }
 }
@@ -459,9 +472,10 @@ attn_fwd2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
 // Barriers: s_full[t][b] (MMA -> softmax), p_full[t][b] (4 softmax warps -> MMA), o_done[t] (P V complete).  Every waiter
 // sees consecutive phases of its barrier: Q K^T(j+2) is issued only after all four warps have published P(j), so no warp
 // can be more than one phase ahead on s_full[t][b], and the issuer consumes p_full[t][b] in order.  o_done[t] is awaited
-// only where O is touched (online-softmax rescale, epilogue): when a step-j softmax probes it, S(j) is complete, hence
-// (in-order tensor pipe, Q K^T(j) issued after P V(j-2)) P V(j-2) is, and P V(j) cannot have been issued before this
-// warp's own arrive: the barrier is in phase j-1 or j, which a parity wait tells apart.
+// only by the online form's O rescale: when a step-j softmax probes it, S(j) is complete, hence P V(j-2) is (the commit
+// behind Q K^T(j) tracks every earlier MMA of the issuing thread, and Q K^T(j) is issued after P V(j-2)), and P V(j) cannot
+// have been issued before this warp's own arrive: the barrier is in phase j-1 or j, which a parity wait tells apart.  The
+// epilogue waits on o_final[t], committed once behind the last P V.
 namespace v3 {
 
 constexpr int BKV = 96;
@@ -473,7 +487,7 @@ constexpr int COL_O = 4 * BKV;
 constexpr int SMEM_BYTES = 2 * TILE_BYTES + 2 * KV_STAGES * KV_BYTES + 1024 + 256;
 constexpr float RESCALE_THRESHOLD = 8.0f;
 
-template <int POLY8, bool PRESCALED>
+template <int POLY8, bool PRESCALED, bool SLICED>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 attn_fwd3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                  const __grid_constant__ CUtensorMap tmV, const Args args) {
@@ -490,15 +504,35 @@ attn_fwd3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
   uint64_t* v_empty = v_full + KV_STAGES;
   uint64_t* s_full = v_empty + KV_STAGES;   // [2 tiles][2 buffers]
   uint64_t* p_full = s_full + 4;            // [2][2]
-  uint64_t* o_done = p_full + 4;            // [2]
-  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(o_done + 2);
+  uint64_t* o_done = p_full + 4;            // [2] P V of a step complete (awaited by the online form's O rescale only)
+  uint64_t* o_final = o_done + 2;           // [2] the LAST P V complete: what the epilogue waits for (single phase)
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(o_final + 2);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int q_pair = blockIdx.x;
-  const int head = blockIdx.y;
-  const int b = blockIdx.z;
-  const int n_tiles = args.n_kv_tiles;
+  // work item -> (query pair, head, batch) and the range of KV tiles [j0, j0 + n_tiles) this CTA covers
+  // SLICED = false: one (query pair, head, batch) per CTA over all KV tiles, 3-D grid (blockIdx is warp-uniform: the
+  // barrier addresses, descriptors and loop bounds of the helper warps stay on the uniform datapath - decoding a linear
+  // work index with divisions here cost 4 %).  Items >= n_full belong to the sliced launch and exit at once.
+  // SLICED = true: 1-D grid over (tail item, KV slice); the CTA covers KV tiles [j0, j0 + n_tiles) and publishes its
+  // unnormalised rows for attn_merge_kernel.
+  int work, slice, q_pair, head, b, j0, n_tiles;
+  bool last_kv;
+  if constexpr (!SLICED) {
+    q_pair = blockIdx.x, head = blockIdx.y, b = blockIdx.z;
+    work = q_pair + args.q_pairs * (head + args.heads * b);
+    if (work >= args.n_full) return;
+    slice = -1, j0 = 0, n_tiles = args.n_kv_tiles, last_kv = true;
+  } else {
+    work = args.n_full + blockIdx.x / args.split;
+    slice = blockIdx.x % args.split;
+    q_pair = work % args.q_pairs;
+    head = (work / args.q_pairs) % args.heads;
+    b = work / (args.q_pairs * args.heads);
+    j0 = slice * args.tiles_per_slice;
+    n_tiles = min(args.tiles_per_slice, args.n_kv_tiles - j0);
+    last_kv = j0 + n_tiles == args.n_kv_tiles;   // this CTA sees the (possibly ragged) last KV tile
+  }
 
   if (warp == 0 && lane == 0) {
     ptx::prefetch_tmap(&tmQ);
@@ -517,6 +551,8 @@ attn_fwd3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
     }
     ptx::mbar_init(&o_done[0], 1);
     ptx::mbar_init(&o_done[1], 1);
+    ptx::mbar_init(&o_final[0], 1);
+    ptx::mbar_init(&o_final[1], 1);
     ptx::fence_barrier_init();
   }
   if (warp == 2) {
@@ -541,10 +577,10 @@ attn_fwd3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
           const uint32_t ph = (j / KV_STAGES) & 1;
           ptx::mbar_wait(&k_empty[st], ph ^ 1);
           ptx::mbar_expect_tx(&k_full[st], KV_BYTES);
-          ptx::tma_load_3d(sK + st * KV_BYTES, &tmK, &k_full[st], head * DH, j * BKV, b);
+          ptx::tma_load_3d(sK + st * KV_BYTES, &tmK, &k_full[st], head * DH, (j0 + j) * BKV, b);
           ptx::mbar_wait(&v_empty[st], ph ^ 1);
           ptx::mbar_expect_tx(&v_full[st], KV_BYTES);
-          ptx::tma_load_3d(sV + st * KV_BYTES, &tmV, &v_full[st], head * DH, j * BKV, b);
+          ptx::tma_load_3d(sV + st * KV_BYTES, &tmV, &v_full[st], head * DH, (j0 + j) * BKV, b);
         }
       }
     } else if (warp == 1 || warp == 3) {
@@ -595,6 +631,7 @@ attn_fwd3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
             ptx::mma_ts(tO, tS0 + buf * BKV + 8 * k, vdesc + (uint64_t)(128 * k), idesc_pv, (j | k) != 0);
           ptx::tc_commit(&o_done[t]);
           ptx::tc_commit(&v_empty[st]);
+          if (j + 1 == n_tiles) ptx::tc_commit(&o_final[t]);
         }
         __syncwarp();
         T_MARK(3);
@@ -627,7 +664,7 @@ attn_fwd3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
       ptx::tmem_wait_ld();
       T_MARK(2);
       if constexpr (decltype(masked)::value) {   // only the last KV tile can be ragged
-        const int kv_left = args.seq_kv - j * BKV;
+        const int kv_left = args.seq_kv - (j0 + j) * BKV;
 #pragma unroll
         for (int i = 0; i < BKV; ++i)
           if (i >= kv_left) v[i] = 0xff800000u;   // -inf
@@ -707,17 +744,39 @@ attn_fwd3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
       if (lane == 0) ptx::mbar_arrive(&p_full[2 * t + buf]);
       T_MARK(7);
     };
-    const bool ragged = (args.seq_kv % BKV) != 0;
+    const bool ragged = last_kv && (args.seq_kv % BKV) != 0;
     for (int j = 0; j + 1 < n_tiles; ++j) tile_step(j, std::false_type{});
     if (ragged) tile_step(n_tiles - 1, std::true_type{});
     else tile_step(n_tiles - 1, std::false_type{});
     T_FLUSH();
 
-    // epilogue: O / l (+ LR residual) -> bf16 global
-    ptx::mbar_wait(&o_done[t], (n_tiles - 1) & 1);
+    // epilogue: O / l (+ LR residual) -> bf16 global.  o_done cannot be used here: nothing keeps a softmax warp within one
+    // phase of it (a warp may finish its last step while P V of the step before has only just been issued, and a parity
+    // wait two phases ahead passes at once), so the last P V has a barrier of its own.
+    ptx::mbar_wait(&o_final[t], 0);
     ptx::tc_fence_after();
     const int row = (q_pair * 2 + t) * BQ + q * 32 + lane;
-    store_rows(args, tO, row, head, b, 1.0f / l_run);
+    if constexpr (!SLICED) {
+      store_rows(args, tO, row, head, b, 1.0f / l_run);
+    } else {
+      // ---- one KV slice of a tail item: publish the unnormalised row; attn_merge_kernel combines the slices ----
+      // (kept out of this kernel on purpose: the merge code pushed it past the instruction-cache plateau, -4 %)
+      const int tail = work - args.n_full;
+      const int prow = t * BQ + q * 32 + lane;                       // row inside the query pair
+      float* mine = args.part + (((int64_t)tail * args.split + slice) * (2 * BQ) + prow) * PART_STRIDE;
+#pragma unroll 1
+      for (int c = 0; c < DH / 32; ++c) {
+        uint32_t o[32];
+        ptx::tmem_ld32(tO + c * 32, o);
+        ptx::tmem_wait_ld();
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+          __stcg(reinterpret_cast<float4*>(mine + c * 32) + i,
+                 make_float4(__uint_as_float(o[4 * i]), __uint_as_float(o[4 * i + 1]), __uint_as_float(o[4 * i + 2]),
+                             __uint_as_float(o[4 * i + 3])));
+      }
+      __stcg(reinterpret_cast<float2*>(mine + DH), make_float2(l_run, PRESCALED ? 0.f : m_run * sl2));
+    }
   }
 
   __syncwarp();
@@ -726,6 +785,56 @@ attn_fwd3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
   if (warp == 2) {
     ptx::tc_fence_after();
     ptx::tmem_dealloc(tmem_base, TMEM_COLS);
+  }
+}
+
+// Combines the KV slices of the tail items: thread = one query row of one (query pair, head, batch).
+//   O = sum_s alpha_s O_s / sum_s alpha_s l_s,  alpha_s = 2^(m_s - max m)  (all m_s = 0 for pre-scaled scores)
+__global__ void __launch_bounds__(2 * BQ) attn_merge_kernel(const Args args) {
+  const int tail = blockIdx.x;
+  const int work = args.n_full + tail;
+  const int q_pair = work % args.q_pairs;
+  const int head = (work / args.q_pairs) % args.heads;
+  const int b = work / (args.q_pairs * args.heads);
+  const int prow = threadIdx.x;
+  const int row = q_pair * 2 * BQ + prow;
+  if (row >= args.seq_q) return;
+  const float* base = args.part + ((int64_t)tail * args.split * (2 * BQ) + prow) * PART_STRIDE;
+  const int64_t sstride = (int64_t)(2 * BQ) * PART_STRIDE;
+  float m_all = -INFINITY, l_all = 0.f;
+  for (int sl = 0; sl < args.split; ++sl) m_all = fmaxf(m_all, base[sl * sstride + DH + 1]);
+  float alpha[4];
+#pragma unroll
+  for (int sl = 0; sl < 4; ++sl) {
+    alpha[sl] = 0.f;
+    if (sl < args.split) {
+      alpha[sl] = exp2f(base[sl * sstride + DH + 1] - m_all);      // references are already in log2 units
+      l_all += base[sl * sstride + DH] * alpha[sl];
+    }
+  }
+  const float inv_l = 1.0f / l_all;
+#pragma unroll 1
+  for (int c = 0; c < DH / 32; ++c) {
+    float f[32];
+#pragma unroll
+    for (int i = 0; i < 32; ++i) f[i] = 0.f;
+#pragma unroll
+    for (int sl = 0; sl < 4; ++sl) {
+      if (sl < args.split) {
+        const float4* src = reinterpret_cast<const float4*>(base + sl * sstride + c * 32);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const float4 v4 = src[i];
+          f[4 * i] = fmaf(v4.x, alpha[sl], f[4 * i]);
+          f[4 * i + 1] = fmaf(v4.y, alpha[sl], f[4 * i + 1]);
+          f[4 * i + 2] = fmaf(v4.z, alpha[sl], f[4 * i + 2]);
+          f[4 * i + 3] = fmaf(v4.w, alpha[sl], f[4 * i + 3]);
+        }
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < 32; ++i) f[i] *= inv_l;
+    emit_chunk(args, f, row, head, b, c);
   }
 }
 
@@ -740,6 +849,14 @@ extern "C" int dit4sr_attn_timing_read(long long* host_out /* [12*16] */) {
   return 0;
 }
 #endif
+
+extern "C" int64_t dit4sr_attn_workspace_bytes(void) {
+  int dev = 0, sms = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess ||
+      sms < 1)
+    sms = 148;   // no device: the B200 figure
+  return attn::workspace_bytes(sms);
+}
 
 extern "C" int dit4sr_attn_fwd(const dit4sr_attn_params* p, void* stream_) {
   using namespace attn;
@@ -774,13 +891,41 @@ extern "C" int dit4sr_attn_fwd(const dit4sr_attn_params* p, void* stream_) {
                  (double)DIT4SR_ATTN_MAX_SCORE_BOUND, (double)p->score_bound);
   DIT4SR_REQUIRE(p->exp_offload >= 0 && p->exp_offload <= 3, DIT4SR_E_BADARG, "attn: exp_offload must be 0..3");
   DIT4SR_REQUIRE(p->variant == 0 || p->variant == 2 || p->variant == 3, DIT4SR_E_BADARG, "attn: variant must be 0, 2 or 3");
+  DIT4SR_REQUIRE(p->workspace == nullptr || host::aligned16(p->workspace), DIT4SR_E_ALIGN, "attn: workspace must be 16-byte aligned");
 
   int rc = dit4sr_check_device();
   if (rc != 0) return rc;
 
-  // default: whichever KV tile size pads the sequence less (96-key double-buffered tiles unless 128 divides it better)
-  const int pad96 = (p->seq_kv + 95) / 96 * 96, pad128 = (p->seq_kv + 127) / 128 * 128;
-  const int variant = p->variant != 0 ? p->variant : (pad96 <= pad128 ? 3 : 2);
+  // Work decomposition.  v3 runs a 1-D grid of work items; when the items do not fill the last wave of SMs, the tail
+  // items are cut into `split` KV slices whose partial results are merged by the last slice to finish (needs workspace).
+  const int sms = host::sm_count();
+  const int q_pairs = (p->seq_q + 2 * BQ - 1) / (2 * BQ);
+  const int64_t items64 = (int64_t)q_pairs * p->heads * p->batches;
+  DIT4SR_REQUIRE(items64 < (1ll << 30), DIT4SR_E_SHAPE, "attn: too many work items");
+  const int items = (int)items64;
+  const int tiles96 = (p->seq_kv + v3::BKV - 1) / v3::BKV;
+  int split = 1, n_full = items;
+  double tail_cost = 0.0;
+  {
+    const int tail = items % sms;
+    tail_cost = tail > 0 ? 1.0 : 0.0;
+    const int64_t need = attn::workspace_bytes(sms);
+    if (tail > 0 && p->workspace != nullptr && p->workspace_bytes >= need && p->split_kv >= 0) {
+      for (int sdiv = 2; sdiv <= 4; ++sdiv) {
+        if (tiles96 / sdiv < 4) break;                                   // keep slices long enough to amortise a prologue
+        const double c = (double)((tail * sdiv + sms - 1) / sms) / sdiv + 0.03 * (sdiv - 1);
+        if (c < tail_cost - 1e-9) { tail_cost = c; split = sdiv; }
+      }
+      if (p->split_kv > 0 && tiles96 / p->split_kv >= 1) split = p->split_kv > 4 ? 4 : p->split_kv;   // forced (tests / A-B)
+      if (split > 1) n_full = items - tail;
+    }
+  }
+  // default kernel: compare padded length x waves of the two tilings (v2 has no tail splitting)
+  const int pad96 = tiles96 * v3::BKV, pad128 = (p->seq_kv + 127) / 128 * 128;
+  const double cost3 = pad96 * ((double)(items / sms) + (split > 1 ? tail_cost : (items % sms ? 1.0 : 0.0)));
+  const double cost2 = pad128 * (double)((items + sms - 1) / sms);
+  const int variant = p->variant != 0 ? p->variant : (cost3 <= cost2 ? 3 : 2);
+  if (variant != 3) { split = 1; n_full = items; }
   const int bkv = variant == 3 ? v3::BKV : BKV;
   CUtensorMap tmQ, tmK, tmV;
   const uint64_t dims[3] = {(uint64_t)p->heads * DH, (uint64_t)p->seq_kv, (uint64_t)p->batches};
@@ -804,6 +949,13 @@ extern "C" int dit4sr_attn_fwd(const dit4sr_attn_params* p, void* stream_) {
   a.seq_kv = p->seq_kv;
   a.n_kv_tiles = (p->seq_kv + bkv - 1) / bkv;
   a.scale_log2 = p->scale * 1.4426950408889634f;
+  a.q_pairs = q_pairs;
+  a.heads = p->heads;
+  a.n_full = n_full;
+  a.split = split;
+  a.tiles_per_slice = (a.n_kv_tiles + split - 1) / split;
+  a.part = nullptr;
+  if (split > 1) a.part = reinterpret_cast<float*>(p->workspace);
   a.sp_world = 0;
   a.sp_rows_per_rank = 1;
   a.sp_col_offset = 0;
@@ -821,18 +973,30 @@ extern "C" int dit4sr_attn_fwd(const dit4sr_attn_params* p, void* stream_) {
   static const KernelFn table[2][2][3] = {
       {{v2::attn_fwd2_kernel<0, false>, v2::attn_fwd2_kernel<2, false>, v2::attn_fwd2_kernel<4, false>},
        {v2::attn_fwd2_kernel<0, true>, v2::attn_fwd2_kernel<2, true>, v2::attn_fwd2_kernel<4, true>}},
-      {{v3::attn_fwd3_kernel<0, false>, v3::attn_fwd3_kernel<2, false>, v3::attn_fwd3_kernel<4, false>},
-       {v3::attn_fwd3_kernel<0, true>, v3::attn_fwd3_kernel<2, true>, v3::attn_fwd3_kernel<4, true>}}};
+      {{v3::attn_fwd3_kernel<0, false, false>, v3::attn_fwd3_kernel<2, false, false>, v3::attn_fwd3_kernel<4, false, false>},
+       {v3::attn_fwd3_kernel<0, true, false>, v3::attn_fwd3_kernel<2, true, false>, v3::attn_fwd3_kernel<4, true, false>}}};
+  static const KernelFn sliced[2][3] = {
+      {v3::attn_fwd3_kernel<0, false, true>, v3::attn_fwd3_kernel<2, false, true>, v3::attn_fwd3_kernel<4, false, true>},
+      {v3::attn_fwd3_kernel<0, true, true>, v3::attn_fwd3_kernel<2, true, true>, v3::attn_fwd3_kernel<4, true, true>}};
   const int po = p->exp_offload == 0 ? 1 : p->exp_offload - 1;
   const int vi = variant == 3 ? 1 : 0, mi = prescaled ? 1 : 0;
   const KernelFn fn = table[vi][mi][po];
   const int smem = variant == 3 ? v3::SMEM_BYTES : v2::SMEM_BYTES;
   // the opt-in to > 48 KB of dynamic shared memory is per (function, device): remember which pairs are done
-  static unsigned long long configured[2][2][3] = {};
+  static unsigned long long configured[2][2][3] = {}, configured_s[2][3] = {};
   if (host::first_use_on_device(&configured[vi][mi][po]))
     DIT4SR_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-  dim3 grid((p->seq_q + 2 * BQ - 1) / (2 * BQ), p->heads, p->batches);
-  fn<<<grid, 384, smem, stream>>>(tmQ, tmK, tmV, a);
+  dim3 grid(q_pairs, p->heads, p->batches);
+  fn<<<grid, 384, smem, stream>>>(tmQ, tmK, tmV, a);   // (v3: items >= n_full exit at once)
   DIT4SR_CUDA(cudaGetLastError());
+  if (split > 1) {   // the tail items again, as KV slices, then the merge
+    const KernelFn fs = sliced[mi][po];
+    if (host::first_use_on_device(&configured_s[mi][po]))
+      DIT4SR_CUDA(cudaFuncSetAttribute(fs, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    fs<<<(items - n_full) * split, 384, smem, stream>>>(tmQ, tmK, tmV, a);
+    DIT4SR_CUDA(cudaGetLastError());
+    v3::attn_merge_kernel<<<items - n_full, 2 * BQ, 0, stream>>>(a);
+    DIT4SR_CUDA(cudaGetLastError());
+  }
   return 0;
 }

@@ -47,6 +47,66 @@ __global__ void unpatchify_kernel(const float* __restrict__ tok, TO* __restrict_
   else out[i] = v;
 }
 
+// classifier-free guidance (pipeline_dit4sr.py:1561-1563) fused with unpatchify and the Euler update: tok holds the
+// velocity tokens of the doubled batch [uncond (B) | text (B)]; v = v_u + g (v_t - v_u)
+template <typename TO>
+__global__ void unpatchify_cfg_kernel(const float* __restrict__ tok, TO* __restrict__ out, const TO* __restrict__ latents,
+                                      float dsigma, float guidance, int B, int C, int H, int W) {
+  const int64_t total = (int64_t)B * C * H * W;
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const int x = (int)(i % W);
+  const int y = (int)((i / W) % H);
+  const int d = (int)((i / ((int64_t)W * H)) % C);
+  const int b = (int)(i / ((int64_t)W * H * C));
+  const int Wp = W / 2, Hp = H / 2;
+  const int64_t t = ((int64_t)b * Hp + y / 2) * Wp + x / 2;
+  const int64_t e = ((y & 1) * 2 + (x & 1)) * C + d;
+  const float vu = tok[t * (4 * C) + e];
+  const float vt = tok[(t + (int64_t)B * Hp * Wp) * (4 * C) + e];
+  float v = vu + guidance * (vt - vu);
+  if (latents != nullptr) v = to_f<TO>(latents[i]) + dsigma * v;
+  if constexpr (sizeof(TO) == 2) out[i] = __float2bfloat16_rn(v);
+  else out[i] = v;
+}
+
+// Per-block feature output for the text-spotting module (pipeline_dit4sr.py:1214-1245): the rows [row0, row0 + n*Hp*Wp) of
+// the fp32 residual stream, 'b (N H W) (pH pW d) -> b (N d) (H pH) (W pW)' to fp32 NCHW, and optionally the token-major
+// copy the reference returns as `extract_feat` (attention.py:363-374), in one pass.
+// One CTA = one (b, n, h) token-grid row and one chunk of 32 channels d: coalesced 128-byte reads along d, shared-memory
+// transpose, coalesced row writes along x.
+template <typename TT>
+__global__ void feature_extract_kernel(const float* __restrict__ x, int64_t ldx, int64_t xbs, int row0, int n_concat, int Hp,
+                                       int Wp, int d, float* __restrict__ nchw, TT* __restrict__ tok) {
+  extern __shared__ float tile[];   // [2 ph][32 dd][2*Wp + 1]
+  const int dd0 = blockIdx.x * 32;
+  const int h = blockIdx.y % Hp, n = blockIdx.y / Hp;
+  const int b = blockIdx.z;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
+  const int W2 = 2 * Wp, pitch = W2 + 1;
+  const int D = 4 * d;
+  for (int item = warp; item < Wp * 4; item += nwarp) {     // (w, ph, pw)
+    const int w = item >> 2, pp = item & 3;
+    const int64_t trow = (int64_t)row0 + ((int64_t)n * Hp + h) * Wp + w;
+    const float v = x[b * xbs + trow * ldx + pp * d + dd0 + lane];
+    tile[((pp >> 1) * 32 + lane) * pitch + 2 * w + (pp & 1)] = v;
+    if (tok != nullptr) {
+      const int64_t orow = ((int64_t)n * Hp + h) * Wp + w;
+      const int64_t o = ((int64_t)b * n_concat * Hp * Wp + orow) * D + pp * d + dd0 + lane;
+      if constexpr (sizeof(TT) == 2) tok[o] = __float2bfloat16_rn(v);
+      else tok[o] = v;
+    }
+  }
+  __syncthreads();
+  if (nchw != nullptr) {
+    for (int item = warp; item < 64; item += nwarp) {          // (ph, dd)
+      const int ph = item >> 5, dl = item & 31;
+      float* dst = nchw + (((int64_t)b * n_concat * d + (int64_t)n * d + dd0 + dl) * (2 * Hp) + 2 * h + ph) * W2;
+      for (int xx = lane; xx < W2; xx += 32) dst[xx] = tile[(ph * 32 + dl) * pitch + xx];
+    }
+  }
+}
+
 __global__ void timestep_features_kernel(const float* __restrict__ t, __nv_bfloat16* __restrict__ out, int B) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= B * 128) return;
@@ -142,6 +202,44 @@ int dit4sr_unpatchify(const float* tok, void* out, int out_dtype, const void* la
   else
     misc::unpatchify_kernel<__nv_bfloat16><<<misc::blocks(total, 256), 256, 0, stream>>>(
         tok, (__nv_bfloat16*)out, (const __nv_bfloat16*)latents, dsigma, batches, channels, height, width);
+  DIT4SR_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int dit4sr_unpatchify_cfg(const float* tok, void* out, int out_dtype, const void* latents, float dsigma, float guidance,
+                          int batches, int channels, int height, int width, void* stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  DIT4SR_REQUIRE(tok && out && batches > 0 && channels > 0, DIT4SR_E_BADARG, "unpatchify_cfg: bad argument");
+  DIT4SR_REQUIRE(height % 2 == 0 && width % 2 == 0 && height > 0 && width > 0, DIT4SR_E_SHAPE,
+                 "unpatchify_cfg: height/width must be even");
+  const int64_t total = (int64_t)batches * channels * height * width;
+  if (out_dtype == DIT4SR_DT_F32)
+    misc::unpatchify_cfg_kernel<float><<<misc::blocks(total, 256), 256, 0, stream>>>(
+        tok, (float*)out, (const float*)latents, dsigma, guidance, batches, channels, height, width);
+  else
+    misc::unpatchify_cfg_kernel<__nv_bfloat16><<<misc::blocks(total, 256), 256, 0, stream>>>(
+        tok, (__nv_bfloat16*)out, (const __nv_bfloat16*)latents, dsigma, guidance, batches, channels, height, width);
+  DIT4SR_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int dit4sr_feature_extract(const float* x, int64_t ldx, int64_t x_batch_stride, int row0, int batches, int n_concat,
+                           int grid_h, int grid_w, int dim, float* nchw_f32, void* tok, int tok_dtype, void* stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  DIT4SR_REQUIRE(x && (nchw_f32 || tok) && batches > 0 && n_concat > 0 && grid_h > 0 && grid_w > 0 && row0 >= 0,
+                 DIT4SR_E_BADARG, "feature_extract: bad argument");
+  DIT4SR_REQUIRE(dim > 0 && dim % 128 == 0, DIT4SR_E_SHAPE, "feature_extract: dim must be a multiple of 128 (4 x 32)");
+  const int d = dim / 4;
+  const size_t smem = (size_t)2 * 32 * (2 * grid_w + 1) * sizeof(float);
+  DIT4SR_REQUIRE(smem <= 48 * 1024 && (int64_t)n_concat * grid_h <= 65535 && batches <= 65535, DIT4SR_E_SHAPE,
+                 "feature_extract: token grid too large");
+  dim3 grid(d / 32, n_concat * grid_h, batches);
+  if (tok_dtype == DIT4SR_DT_F32)
+    misc::feature_extract_kernel<float><<<grid, 256, smem, stream>>>(x, ldx, x_batch_stride, row0, n_concat, grid_h, grid_w, d,
+                                                                     nchw_f32, (float*)tok);
+  else
+    misc::feature_extract_kernel<__nv_bfloat16><<<grid, 256, smem, stream>>>(x, ldx, x_batch_stride, row0, n_concat, grid_h,
+                                                                             grid_w, d, nchw_f32, (__nv_bfloat16*)tok);
   DIT4SR_CUDA(cudaGetLastError());
   return 0;
 }

@@ -244,6 +244,8 @@ class Engine:
         # (DIT4SR_SP_FUSED_SCATTER=0: a separate scatter kernel after the projections, kept for A/B)
         self.sp_fused_scatter = _os.environ.get("DIT4SR_SP_FUSED_SCATTER", "1") != "0"
         self._pos: Dict[Tuple, torch.Tensor] = {}
+        self._attn_ws: Dict = {}
+        self._attn_split = _os.environ.get("DIT4SR_ATTN_SPLIT_KV", "1") != "0"
 
     # ------------------------------------------------------------------------------------------------ profiling
     def profile_kernel(self, pattern: str):
@@ -326,6 +328,30 @@ class Engine:
             ws["sp_out"] = ops.attn_sp_out(P, I, sp.rank * Dl, ws["o_peers"])
         self._ws[key] = ws
         return ws
+
+    def _attn_scratch(self, device):
+        """Zero-filled scratch of the attention kernel's split-KV tail (one per engine and device; the kernel keeps its
+        counters zero between launches).  DIT4SR_ATTN_SPLIT_KV=0 turns the splitting off."""
+        if not self._attn_split:
+            return None
+        t = self._attn_ws.get(device)
+        if t is None:
+            t = torch.zeros(ops.attention_workspace_bytes(), device=device, dtype=torch.uint8)
+            self._attn_ws[device] = t
+        return t
+
+    def _feature_buffers(self, features, B, grid, device):
+        """Static outputs of the per-block feature kernels for one feature spec (allocated once: graph replays refill them)."""
+        if not hasattr(self, "_feat_bufs"):
+            self._feat_bufs = {}
+        bufs = self._feat_bufs.get(features)
+        layers, row0, n_concat, tdt = features
+        if bufs is None or bufs[0][0].shape[0] != B or bufs[0][1].shape[-1] != 2 * grid or bufs[0][0].device != device:
+            bufs = [(torch.empty(B, n_concat * grid * grid, self.D, device=device, dtype=tdt),
+                     torch.empty(B, n_concat * self.D // 4, 2 * grid, 2 * grid, device=device, dtype=torch.float32))
+                    for _ in layers]
+            self._feat_bufs[features] = bufs
+        return bufs
 
     # ------------------------------------------------------------------------------------------------ GEMM dispatch
     def _scr(self, key, numel, dtype):
@@ -456,7 +482,7 @@ class Engine:
             seq_q = I if (last or not ap.has_text) else S
             R("attn", ops.attention, qkv[:, :S, :D], qkv[:, :S, D:2 * D], qkv[:, :S, 2 * D:], o, H, seq_q=seq_q,
               lr_res=n_in, lr_rows=(N, I),   # Q2: the LR (and OCR) rows get their normed+modulated input added back
-              score_bound=ap.score_bound)
+              score_bound=ap.score_bound, workspace=self._attn_scratch(qkv.device))
         else:
             self._attention_sp(ap, ws, n_in, N, I, S, last)
         G = ops.EPI_GATE_RESID
@@ -485,7 +511,7 @@ class Engine:
             R("a2a", ops.a2a_qkv, sp.comm, None if self.sp_fused_scatter else qkv[:, :S], I, T, H, ws["qkv_sp_peers"])
             seq_q = P * I if (last or not T) else Ssp
             R("attn", ops.attention, qs[:, :, 0], qs[:, :, 1], qs[:, :, 2], o, Hl, seq_q=seq_q,
-              score_bound=ap.score_bound, sp_out=ws["sp_out"])
+              score_bound=ap.score_bound, sp_out=ws["sp_out"], workspace=self._attn_scratch(qkv.device))
             R("a2a", ops.a2a_out, sp.comm, None, I, T, H, ws["o_peers"], o.stride(1), o.stride(0))
             R("attn", ops.add_bf16, o[:, N:I], n_in[:, N:I])                # Q2 residual on the LR rows
             return
@@ -522,20 +548,27 @@ class Engine:
     # ------------------------------------------------------------------------------------------------ CUDA graph
     @torch.no_grad()
     def step(self, hidden_states, controlnet_image, encoder_hidden_states, pooled_projections, timestep,
-             out=None, euler: Optional[Tuple[torch.Tensor, float]] = None, sharded_io: bool = False):
+             out=None, euler: Optional[Tuple[torch.Tensor, float]] = None, sharded_io: bool = False,
+             guidance: Optional[float] = None, features: Optional[tuple] = None):
         """One denoiser call, replayed from a captured CUDA graph when possible (the ~300 kernel launches of a step are
         recorded once per input shape; replay removes the per-launch host cost, which matters for small batches).
         Same results as `forward` -- the same kernels run. Falls back to direct launches while profiling, if capture is
         unavailable, and under sequence parallelism over torch.distributed (the NVLink peer-memory path is captured).
 
         sharded_io (sequence parallelism): the image tensors are this rank's row strips [B, C, 2*grid/P, W] and so is the
-        result - a sampling loop keeps its latents sharded and gathers once at the end (sampler.denoise)."""
+        result - a sampling loop keeps its latents sharded and gathers once at the end (sampler.denoise).
+        guidance: classifier-free guidance - the inputs are the doubled batch [uncond | text] (2B) and the result (velocity
+        or Euler update of euler[0], B images) uses v_uncond + guidance * (v_text - v_uncond), fused into the last kernel.
+        features: (layers, row0, n_concat, token dtype) - per-block feature outputs (see `forward`); with them the call
+        returns (result, [ {extract_feat, extract_feat_nchw_f32}, ... ]) and still replays the graph."""
+        if features is not None and self.sp is not None:
+            raise NotImplementedError("feature outputs are not available under sequence parallelism")
         if self.sp is not None and not sharded_io:
             # whole images in, whole image out: cut my strip, run the sharded step, gather the strips (outside any graph)
             g0, g1 = self.sp.row_slice(hidden_states.shape[2] // 2)
             loc = lambda t: t[:, :, 2 * g0:2 * g1].contiguous()
             res = self.step(loc(hidden_states), loc(controlnet_image), encoder_hidden_states, pooled_projections, timestep,
-                            euler=None if euler is None else (loc(euler[0]), euler[1]), sharded_io=True)
+                            euler=None if euler is None else (loc(euler[0]), euler[1]), sharded_io=True, guidance=guidance)
             gathered = self.sp.gather_rows(res, dim=2)
             if out is not None:
                 out.copy_(gathered)
@@ -543,18 +576,21 @@ class Engine:
             return gathered
         if (not self.use_cuda_graph or self._prof is not None or self.precise
                 or (self.sp is not None and not self.sp_graph)):
-            return self.forward(hidden_states, controlnet_image, encoder_hidden_states, pooled_projections, timestep,
-                                out=out, euler=euler, sharded_io=sharded_io)
+            res = self.forward(hidden_states, controlnet_image, encoder_hidden_states, pooled_projections, timestep,
+                               out=out, euler=euler, sharded_io=sharded_io, guidance=guidance, features=features)
+            return (res, self._feature_results(features)) if features is not None else res
         B = hidden_states.shape[0]
         key = (tuple(hidden_states.shape), hidden_states.dtype, tuple(encoder_hidden_states.shape),
-               encoder_hidden_states.dtype, pooled_projections.dtype, str(hidden_states.device))
+               encoder_hidden_states.dtype, pooled_projections.dtype, str(hidden_states.device), guidance is not None,
+               features)
         entry = self._graphs.get(key)
         if entry is None:
             st = dict(hs=hidden_states.clone().contiguous(), ci=controlnet_image.clone().contiguous(),
                       enc=encoder_hidden_states.clone().contiguous(), pooled=pooled_projections.clone().contiguous(),
                       t=torch.zeros(B, device=hidden_states.device, dtype=torch.float32))
             try:
-                fw = lambda: self.forward(st["hs"], st["ci"], st["enc"], st["pooled"], st["t"], sharded_io=sharded_io)
+                fw = lambda: self.forward(st["hs"], st["ci"], st["enc"], st["pooled"], st["t"], sharded_io=sharded_io,
+                                          guidance=guidance, features=features)
                 fw()                                                                    # warm-up outside capture
                 torch.cuda.synchronize()
                 n0 = ops.launch_count()
@@ -569,8 +605,9 @@ class Engine:
                 warnings.warn(f"dit4sr_b200: CUDA graph capture failed ({e}); using direct launches")
                 self.use_cuda_graph = False
                 torch.cuda.synchronize()
-                return self.forward(hidden_states, controlnet_image, encoder_hidden_states, pooled_projections,
-                                    timestep, out=out, euler=euler)
+                res = self.forward(hidden_states, controlnet_image, encoder_hidden_states, pooled_projections,
+                                   timestep, out=out, euler=euler, guidance=guidance, features=features)
+                return (res, self._feature_results(features)) if features is not None else res
             self._graphs[key] = entry
         graph, st, vel, n_launch = entry
         st["hs"].copy_(hidden_states)
@@ -586,17 +623,28 @@ class Engine:
                                  grid_w=w // 2 if self.sp is not None else 0)
             if out is None:
                 out = torch.empty_like(euler[0])
-            ops.unpatchify(ws["tok"], out, latents=euler[0], dsigma=euler[1])
-            return out
-        if out is not None:
+            ops.unpatchify(ws["tok"], out, latents=euler[0], dsigma=euler[1], guidance=guidance)
+            res = out
+        elif out is not None:
             out.copy_(vel)
-            return out
-        return vel.clone()
+            res = out
+        else:
+            res = vel.clone()
+        return (res, self._feature_results(features)) if features is not None else res
+
+    def _feature_results(self, features):
+        """Fresh copies of the per-block feature buffers the last forward / replay filled (they are static workspace)."""
+        return [dict(extract_feat=t.clone(), extract_feat_nchw_f32=n.clone()) for t, n in self._feat_bufs[features]]
 
     # ------------------------------------------------------------------------------------------------ forward
     @torch.no_grad()
     def forward(self, hidden_states, controlnet_image, encoder_hidden_states, pooled_projections, timestep,
-                out=None, euler: Optional[Tuple[torch.Tensor, float]] = None, feat_hook=None, sharded_io: bool = False):
+                out=None, euler: Optional[Tuple[torch.Tensor, float]] = None, feat_hook=None, sharded_io: bool = False,
+                guidance: Optional[float] = None, features: Optional[tuple] = None):
+        """features = (layers, row0, n_concat, token dtype): after each block in `layers` the rows [row0, row0 + n_concat *
+        grid^2) of the residual stream are written (one kernel, also inside a captured graph) as the token-major slice the
+        reference returns (attention.py:363-374) and as fp32 NCHW 'b (N H W) (pH pW d) -> b (N d) (H pH) (W pW)', what
+        pipelines/pipeline_dit4sr.py:1214-1245 hands to the text-spotting module."""
         cfg, D, R = self.cfg, self.D, self._run
         B, Cin, h, w = hidden_states.shape
         sharded = sharded_io and self.sp is not None   # the image tensors are already this rank's row strips
@@ -708,18 +756,24 @@ class Engine:
             self._gg("ff2", ff2)
             if feat_hook is not None:
                 feat_hook(i, x)
+            if features is not None and i in features[0]:
+                tokb, nchw = self._feature_buffers(features, B, grid, dev)[features[0].index(i)]
+                R("feat", ops.feature_extract, x, features[1], features[2], grid, grid, nchw=nchw, tok=tokb)
 
         # ---- tail: drop the LR half, norm_out (scale, shift order), proj_out, unpatchify (:379-391)
         so = self.mod_out_off
         R("tail", ops.ln_modulate, x[:, :N], mod[:, so + D: so + 2 * D], mod[:, so: so + D], n1[:, :N])
         gm("tail", n1[:, :N], self.proj_out.w, self.proj_out.b, ws["tok"], ops.EPI_BIAS)
+        if guidance is not None and B % 2:
+            raise ValueError("guidance needs the doubled batch [uncond | text]")
         if out is None:
-            out = torch.empty(B, cfg.out_channels, 2 * rows, w, device=dev, dtype=hidden_states.dtype)
+            out = torch.empty(B // 2 if guidance is not None else B, cfg.out_channels, 2 * rows, w, device=dev,
+                              dtype=hidden_states.dtype)
         if euler is not None:
             latents, dsigma = euler
-            R("tail", ops.unpatchify, ws["tok"], out, latents=latents, dsigma=dsigma)
+            R("tail", ops.unpatchify, ws["tok"], out, latents=latents, dsigma=dsigma, guidance=guidance)
         else:
-            R("tail", ops.unpatchify, ws["tok"], out)
+            R("tail", ops.unpatchify, ws["tok"], out, guidance=guidance)
         if self.sp is not None and not sharded:   # every rank returns the whole image (row strips gathered)
             gathered = self.sp.gather_rows(out, dim=2)
             if full_out is not None:

@@ -203,12 +203,16 @@ def gemm_schedule(shapes, sm_count=148):
     return [tuple(items[5 * i:5 * i + 5]) for i in range(count)]
 
 
+def attention_workspace_bytes():
+    return int(_lib.load().dit4sr_attn_workspace_bytes())
+
+
 ATTN_ONLINE, ATTN_PRESCALED = 0, 1
 ATTN_MAX_SCORE_BOUND = 60.0
 
 
 def attention(q, k, v, o, heads, seq_q=None, scale=None, lr_res=None, lr_rows=(0, 0), score_bound=None, exp_offload=0, variant=0,
-              sp_out=None):
+              sp_out=None, workspace=None, split_kv=0):
     """o = softmax(q k^T * scale) v over [B, S, heads*64] bf16 views (row stride may be 3*heads*64 for a fused buffer).
 
     Only the first seq_q query rows are produced. lr_res (bf16 [B, >=lr_rows[1], heads*64]) is added to rows lr_rows.
@@ -239,6 +243,9 @@ def attention(q, k, v, o, heads, seq_q=None, scale=None, lr_res=None, lr_rows=(0
     p.exp_offload, p.variant = exp_offload, variant
     if sp_out is not None:
         p.sp_out = C.pointer(sp_out)
+    if workspace is not None:     # zero-filled uint8 scratch of attention_workspace_bytes(): enables the split-KV tail
+        p.workspace, p.workspace_bytes = _ptr(workspace), workspace.numel() * workspace.element_size()
+    p.split_kv = split_kv
     check(_lib.load().dit4sr_attn_fwd(C.byref(p), _stream()), "dit4sr_attn_fwd")
     _count()
 
@@ -325,8 +332,10 @@ def patchify(x, out):
     _count()
 
 
-def unpatchify(tok, out, latents=None, dsigma=0.0):
-    """tok fp32 [B, (H/2)(W/2), 4C] -> out [B,C,H,W]; with latents: out = latents + dsigma * velocity (Euler step)."""
+def unpatchify(tok, out, latents=None, dsigma=0.0, guidance=None):
+    """tok fp32 [B, (H/2)(W/2), 4C] -> out [B,C,H,W]; with latents: out = latents + dsigma * velocity (Euler step).
+    guidance (classifier-free guidance): tok is the doubled batch [uncond | text] (2B rows) and the velocity is
+    v_uncond + guidance * (v_text - v_uncond)."""
     _req(tok, torch.float32, "tok")
     if not tok.is_contiguous() or not out.is_contiguous():
         raise _lib.Dit4srError("unpatchify: tensors must be contiguous")
@@ -334,8 +343,33 @@ def unpatchify(tok, out, latents=None, dsigma=0.0):
     dt = DT_F32 if out.dtype == torch.float32 else DT_BF16
     if latents is not None and (latents.dtype != out.dtype or not latents.is_contiguous()):
         raise _lib.Dit4srError("unpatchify: latents must match out")
-    check(_lib.load().dit4sr_unpatchify(_ptr(tok), _ptr(out), dt, _ptr(latents), float(dsigma), B, Cc, H, W,
-                                        _stream()), "dit4sr_unpatchify")
+    if guidance is None:
+        if tok.shape[0] != B:
+            raise _lib.Dit4srError("unpatchify: batch mismatch")
+        check(_lib.load().dit4sr_unpatchify(_ptr(tok), _ptr(out), dt, _ptr(latents), float(dsigma), B, Cc, H, W,
+                                            _stream()), "dit4sr_unpatchify")
+    else:
+        if tok.shape[0] != 2 * B:
+            raise _lib.Dit4srError("unpatchify: guidance needs the doubled batch [uncond | text]")
+        check(_lib.load().dit4sr_unpatchify_cfg(_ptr(tok), _ptr(out), dt, _ptr(latents), float(dsigma), float(guidance), B,
+                                                Cc, H, W, _stream()), "dit4sr_unpatchify_cfg")
+    _count()
+
+
+def feature_extract(x, row0, n_concat, grid_h, grid_w, nchw=None, tok=None):
+    """Rows [row0, row0 + n_concat*grid_h*grid_w) of the fp32 residual stream x [B, rows, D] -> tok [B, n*gh*gw, D] (bf16 or
+    fp32, the reference's `extract_feat`) and / or nchw fp32 [B, n*D/4, 2gh, 2gw] (what the pipeline feeds the ts_module)."""
+    _req(x, torch.float32, "x")
+    B, _, D = x.shape
+    if nchw is not None and (nchw.dtype != torch.float32 or not nchw.is_contiguous()
+                             or tuple(nchw.shape) != (B, n_concat * D // 4, 2 * grid_h, 2 * grid_w)):
+        raise _lib.Dit4srError("feature_extract: nchw must be contiguous fp32 [B, n*D/4, 2*gh, 2*gw]")
+    if tok is not None and (tok.dtype not in (torch.float32, torch.bfloat16) or not tok.is_contiguous()
+                            or tuple(tok.shape) != (B, n_concat * grid_h * grid_w, D)):
+        raise _lib.Dit4srError("feature_extract: tok must be contiguous bf16/fp32 [B, n*gh*gw, D]")
+    td = DT_F32 if (tok is not None and tok.dtype == torch.float32) else DT_BF16
+    check(_lib.load().dit4sr_feature_extract(_ptr(x), x.stride(1), x.stride(0), row0, B, n_concat, grid_h, grid_w, D,
+                                             _ptr(nchw), _ptr(tok), td, _stream()), "dit4sr_feature_extract")
     _count()
 
 

@@ -16,15 +16,39 @@ def flow_match_sigmas(num_steps: int, shift: float = 3.0, num_train_timesteps: i
     return np.concatenate([sig, np.zeros(1)]).astype(np.float32)
 
 
+def lre_start_point(latents, controlnet_image, sigma0: float):
+    """start_point == 'lr' (the LRE strategy), pipelines/pipeline_dit4sr.py:1025-1034: the noise is blended with the
+    control latent, (1 - sigma_0) * control[:1] + sigma_0 * noise - with the FIRST control latent for every image of the
+    batch, as the reference writes it."""
+    return (1.0 - sigma0) * controlnet_image[:1].to(latents.dtype) + sigma0 * latents
+
+
 @torch.no_grad()
 def denoise(model, latents, controlnet_image, encoder_hidden_states, pooled_projections, num_inference_steps=40,
-            sigmas=None):
+            sigmas=None, guidance_scale: float = 1.0, negative_prompt_embeds=None, negative_pooled_prompt_embeds=None,
+            start_point: str = "noise"):
     """Runs the full sampling loop on the CUDA engine; returns the final latents (same dtype as `latents`).
 
-    latents are carried in fp32 between steps (scheduler.step upcasts to fp32, pipeline_dit4sr.py:1567)."""
+    latents are carried in fp32 between steps (scheduler.step upcasts to fp32, pipeline_dit4sr.py:1567).
+    guidance_scale > 1 (classifier-free guidance, pipeline_dit4sr.py:1085,1106-1108,1561-1563): every step runs the model
+    on the doubled batch [uncond | text] with [negative | positive] prompt embeddings and the combine
+    v_uncond + g (v_text - v_uncond) is fused with the Euler update into the model's last kernel.
+    start_point: 'noise' or 'lr' (LRE strategy, :1025-1034)."""
     eng = model.engine()
     sig = flow_match_sigmas(num_inference_steps) if sigmas is None else np.asarray(sigmas, dtype=np.float32)
     B = latents.shape[0]
+    if start_point == "lr":
+        latents = lre_start_point(latents, controlnet_image, float(sig[0]))
+    elif start_point != "noise":
+        raise ValueError("start_point must be 'noise' or 'lr'")
+    cfg_on = guidance_scale > 1.0                                  # do_classifier_free_guidance
+    if cfg_on:
+        if negative_prompt_embeds is None or negative_pooled_prompt_embeds is None:
+            raise ValueError("guidance_scale > 1 needs negative_prompt_embeds and negative_pooled_prompt_embeds")
+        encoder_hidden_states = torch.cat([negative_prompt_embeds, encoder_hidden_states], dim=0)
+        pooled_projections = torch.cat([negative_pooled_prompt_embeds, pooled_projections], dim=0)
+        if controlnet_image.shape[0] == B:                         # prepare_image doubles it (:714-715)
+            controlnet_image = torch.cat([controlnet_image] * 2, dim=0)
     sp = eng.sp
     if sp is not None:   # Ulysses: every rank carries its own row strip through the loop; ONE gather at the end
         g0, g1 = sp.row_slice(latents.shape[2] // 2)
@@ -34,11 +58,16 @@ def denoise(model, latents, controlnet_image, encoder_hidden_states, pooled_proj
         latents_l = latents
     x = latents_l.float().contiguous()
     nxt = torch.empty_like(x)
-    t = torch.empty(B, device=latents.device, dtype=torch.float32)
+    x2 = torch.empty((2 * B,) + tuple(x.shape[1:]), device=x.device, dtype=x.dtype) if cfg_on else None
+    t = torch.empty(2 * B if cfg_on else B, device=latents.device, dtype=torch.float32)
     for i in range(len(sig) - 1):
         t.fill_(float(sig[i]) * 1000.0)
-        eng.step(x, controlnet_image, encoder_hidden_states, pooled_projections, t, out=nxt,
-                 euler=(x, float(sig[i + 1]) - float(sig[i])), sharded_io=sp is not None)
+        if cfg_on:
+            x2[:B].copy_(x)
+            x2[B:].copy_(x)
+        eng.step(x2 if cfg_on else x, controlnet_image, encoder_hidden_states, pooled_projections, t, out=nxt,
+                 euler=(x, float(sig[i + 1]) - float(sig[i])), sharded_io=sp is not None,
+                 guidance=float(guidance_scale) if cfg_on else None)
         x, nxt = nxt, x
     if sp is not None:
         x = sp.gather_rows(x, dim=2)

@@ -279,31 +279,38 @@ class SD3Transformer2DModel(nn.Module):
         #  returns the (output, trans_blk_outs) pair: transformer_sd3_ocrbranch_ocr2hq2ocr.py:344,371-374,407-408)
         want_feats = cfg is not None and (self._ocr_branch or "ts_module" in cfg.train.model)
         trans_blk_outs = []
-        hook = None
         in_dtype = hidden_states.dtype
+        features = None
         if want_feats:
-            layers = set(cfg.train.transformer.feat_extract_layer)
+            layers = tuple(sorted(set(int(i) for i in cfg.train.transformer.feat_extract_layer)))
             mode = cfg.train.transformer.feat_extract
-            slices = {"hq_feat": (0, 1024), "lq_feat": (1024, 2048), "hqlq_feat": (0, 2048)}          # attention.py:363-374
+            # fixed 1024-token slices exactly as written (attention.py:363-374: the reference assumes 64x64 latents)
+            slices = {"hq_feat": (0, 1), "lq_feat": (1024, 1), "hqlq_feat": (0, 2)}
             if self._ocr_branch:
-                slices["ocr_feat"] = (2048, 3072)
+                slices["ocr_feat"] = (2048, 1)
             sl = slices.get(mode)
-
-            def hook(i, x):
-                if i in layers:
-                    d = {}
-                    if sl is not None:
-                        d["extract_feat"] = x[:, sl[0]:sl[1]].to(in_dtype, copy=True)   # x is the live fp32 workspace: never alias it
-                    trans_blk_outs.append(d)
+            if sl is not None and layers:
+                if hidden_states.shape[-1] != 64 or hidden_states.shape[-2] != 64:
+                    raise ValueError("feature extraction slices 1024-token streams (attention.py:363-374): 64x64 latents only")
+                tdt = in_dtype if in_dtype in (torch.float32, torch.bfloat16) else torch.float32
+                features = (layers, sl[0], sl[1], tdt)
+            else:
+                trans_blk_outs = [{} for _ in layers]
 
         hs, ci = hidden_states, controlnet_image
         if in_dtype not in (torch.float32, torch.bfloat16):
             hs, ci = hs.float(), ci.float()
         eng = self.engine()
-        if hook is None:
+        if features is None:
             out = eng.step(hs, ci, encoder_hidden_states, pooled_projections, timestep)
         else:
-            out = eng.forward(hs, ci, encoder_hidden_states, pooled_projections, timestep, feat_hook=hook)
+            # the feature kernels run inside the captured graph; each dict carries the reference's token-major slice
+            # (`extract_feat`) and the fp32 NCHW tensor the pipeline builds from it (`extract_feat_nchw_f32`,
+            # pipelines/pipeline_dit4sr.py:1214-1245: dit4sr_b200.unpatchify_features returns it without recomputing)
+            out, feats = eng.step(hs, ci, encoder_hidden_states, pooled_projections, timestep, features=features)
+            for d in feats:
+                d["extract_feat"] = d["extract_feat"].to(in_dtype)
+            trans_blk_outs = feats
         output = out.to(in_dtype)
         if not return_dict:
             if want_feats or self._ocr_branch:

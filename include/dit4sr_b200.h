@@ -172,6 +172,11 @@ int dit4sr_gemm_schedule(const dit4sr_gemm_params* problems, int count, int sm_c
  * variant:     3 = independent query tiles with double-buffered 96-key score tiles; 2 = three 128-key score buffers
  *              rotating over the two query tiles (round 1's pipeline); 0 = default = whichever of the two KV tile sizes
  *              pads seq_kv less (same speed per score, so the padding decides).
+ * workspace:   optional scratch of dit4sr_attn_workspace_bytes() bytes (contents irrelevant).  With it, work items that would
+ *              only partly fill the last wave of SMs are cut into 2-4 slices along the keys; each slice publishes its
+ *              unnormalised row + row sum (+ reference max) and a small second kernel merges them (e.g. 390 items on 148
+ *              SMs: 2.67 instead of 3 waves).  Without it, or with split_kv < 0, every item runs over all keys.
+ *              split_kv > 0 forces that many slices (tests).
  * sp_out (Ulysses sequence parallelism, NULL otherwise): the kernel's epilogue stores each output row straight into the
  *              token-side buffer of the rank that owns the token, through NVLink peer memory (the head -> sequence
  *              all-to-all fused into the attention kernel).  Query row i < world*rows_per_rank belongs to rank
@@ -196,8 +201,10 @@ typedef struct {
   float scale;
   int mode; float score_bound; int exp_offload; int variant;             /* ABI v3 */
   const dit4sr_attn_sp_out* sp_out;
+  void* workspace; int64_t workspace_bytes; int split_kv;
 } dit4sr_attn_params;
 int dit4sr_attn_fwd(const dit4sr_attn_params* p, void* stream);
+int64_t dit4sr_attn_workspace_bytes(void);   /* for the current device (148 SMs assumed when there is none) */
 
 /* ---------------------------------------------------------------------------------------------------------------
  * Ulysses sequence parallelism over NVLink peer memory (BASELINE config C4; the reference has no counterpart: it runs
@@ -279,6 +286,19 @@ int dit4sr_patchify(const void* x, int x_dtype, void* patches, int batches, int 
  *   out = latents + dsigma * velocity   (pipelines/pipeline_dit4sr.py:1567, scheduler.step) */
 int dit4sr_unpatchify(const float* tok, void* out, int out_dtype, const void* latents, float dsigma, int batches,
                       int channels, int height, int width, void* stream);
+/* The same for a classifier-free-guidance step (pipelines/pipeline_dit4sr.py:1092-1108,1561-1563): tok holds the velocity
+ * tokens of the doubled batch [uncond (batches) | text (batches)]; v = v_uncond + guidance * (v_text - v_uncond), then the
+ * plain store or the Euler update as above.  out / latents: [batches, C, H, W]. */
+int dit4sr_unpatchify_cfg(const float* tok, void* out, int out_dtype, const void* latents, float dsigma, float guidance,
+                          int batches, int channels, int height, int width, void* stream);
+/* Per-block feature outputs for the text-spotting module: rows [row0, row0 + n_concat*grid_h*grid_w) of the fp32 residual
+ * stream x [batches, rows, dim] (ldx, x_batch_stride) are written as
+ *   tok       [batches, n_concat*grid_h*grid_w, dim]  (tok_dtype; the `extract_feat` slice of model_dit4sr/attention.py:363-374)
+ *   nchw_f32  [batches, n_concat*dim/4, 2*grid_h, 2*grid_w] fp32 = rearrange('b (N H W) (pH pW d) -> b (N d) (H pH) (W pW)')
+ *             followed by .to(float32), i.e. what pipelines/pipeline_dit4sr.py:1214-1245 feeds to the ts_module.
+ * Either output may be NULL. dim % 128 == 0. */
+int dit4sr_feature_extract(const float* x, int64_t ldx, int64_t x_batch_stride, int row0, int batches, int n_concat,
+                           int grid_h, int grid_w, int dim, float* nchw_f32, void* tok, int tok_dtype, void* stream);
 /* sinusoidal timestep features [cos | sin] (diffusers Timesteps(256, flip_sin_to_cos=True, shift 0)) -> bf16 [B, 256] */
 int dit4sr_timestep_features(const float* timesteps, void* out_bf16, int batches, void* stream);
 /* y = silu(x) (fp32 -> bf16), n elements */

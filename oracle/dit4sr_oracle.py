@@ -540,6 +540,43 @@ def sample_loop(sd, cfg, latents, controlnet_image, encoder_hidden_states, poole
     return x
 
 
+def lre_start_point(latents, control_image, sigma0):
+    """start_point == 'lr' (LRE strategy), pipelines/pipeline_dit4sr.py:1025-1034, as written: every image of the batch
+    is blended with the FIRST control latent (`control_image[:1]`):  (1 - sigma_0) * control[:1] + sigma_0 * noise."""
+    cond = control_image[:1]
+    sigma = torch.as_tensor(sigma0, dtype=latents.dtype, device=latents.device).flatten()
+    while sigma.dim() < 4:
+        sigma = sigma.unsqueeze(-1)
+    return (1.0 - sigma) * cond + sigma * latents
+
+
+def sample_loop_cfg(sd, cfg, latents, controlnet_image, encoder_hidden_states, pooled_projections,
+                    negative_prompt_embeds, negative_pooled_prompt_embeds, guidance_scale, num_steps=40,
+                    start_point="noise", model_fn=None):
+    """The loop with classifier-free guidance as pipelines/pipeline_dit4sr.py runs it (9 of the 36 shipped configs use
+    guidance 8.0): doubled latents (:1085), control image doubled by prepare_image (:714-715), prompt embeddings
+    [negative | positive] (:1106-1108), one model call on the 2B batch (:1122-1131), combine (:1561-1563)
+    noise_pred = uncond + guidance_scale * (text - uncond) in the model dtype, scheduler.step in fp32 (:1567)."""
+    sig = flow_match_sigmas(num_steps)
+    B = latents.shape[0]
+    ctrl2 = torch.cat([controlnet_image] * 2) if controlnet_image.shape[0] == B else controlnet_image
+    enc2 = torch.cat([negative_prompt_embeds, encoder_hidden_states], dim=0)
+    pooled2 = torch.cat([negative_pooled_prompt_embeds, pooled_projections], dim=0)
+    if model_fn is None:
+        def model_fn(x, c, e, p, t):
+            return model_forward(sd, cfg, x, c, e, p, t, as_written=False)
+    x = latents
+    if start_point == "lr":
+        x = lre_start_point(x, controlnet_image, float(sig[0]))
+    for i in range(num_steps):
+        t = torch.full((2 * B,), float(sig[i]) * 1000.0, device=x.device)
+        v = model_fn(torch.cat([x] * 2), ctrl2, enc2, pooled2, t)
+        vu, vt = v.chunk(2)
+        v = vu + guidance_scale * (vt - vu)
+        x = (x.float() + (float(sig[i + 1]) - float(sig[i])) * v.float()).to(v.dtype)
+    return x
+
+
 # --------------------------------------------------------------------------------------------------------------
 # tiled branch of the sampling loop (pipelines/pipeline_dit4sr.py:746-761,1449-1558), restated literally
 # --------------------------------------------------------------------------------------------------------------

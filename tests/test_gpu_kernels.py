@@ -299,6 +299,39 @@ def test_attention_at_the_c4_per_rank_shape(ops, prescaled):
     assert worst < 4e-3
 
 
+@pytest.mark.parametrize("prescaled", [False, True])
+@pytest.mark.parametrize("split_kv", [0, 2, 3, 4])
+@pytest.mark.parametrize("B,H,S,Sq,lr", [(1, 24, 2381, 2381, (1024, 2048)),      # 240 items on 148 SMs: 92 tail items
+                                         (2, 3, 4000, 3900, None),                 # 96 items: everything is tail
+                                         (1, 2, 1000, 1000, None)])
+def test_attention_split_kv_tail(ops, B, H, S, Sq, lr, split_kv, prescaled):
+    """Work items that do not fill the last wave of SMs are cut into KV slices whose partial rows (unnormalised O, row sum,
+    reference max) are merged by a second small kernel: same result as the unsplit kernel, for both softmax forms, ragged
+    last tiles and the LR residual (two launches on the same scratch)."""
+    torch.manual_seed(0)
+    D = H * 64
+    qkv = torch.randn(B, S, 3 * D, device="cuda")
+    if prescaled:
+        qkv[..., :D] *= LOG2E_OVER_8
+    else:
+        qkv[..., D:2 * D] *= torch.linspace(0.3, 3.0, S, device="cuda")[None, :, None]   # maxima differ between slices
+    qkv = qkv.bfloat16()
+    q, k, v = qkv[..., :D], qkv[..., D:2 * D], qkv[..., 2 * D:]
+    res = torch.randn(B, S, D, device="cuda").bfloat16() if lr else None
+    ws = torch.empty(ops.attention_workspace_bytes(), device="cuda", dtype=torch.uint8)
+    hd = lambda t: t.float().reshape(B, S, H, 64).transpose(1, 2)
+    ref = torch.nn.functional.scaled_dot_product_attention(hd(q), hd(k), hd(v), scale=math.log(2.0) if prescaled else None)
+    ref = ref.transpose(1, 2).reshape(B, S, D)[:, :Sq].clone()
+    if lr:
+        ref[:, lr[0]:lr[1]] += res[:, lr[0]:lr[1]].float()
+    for _ in range(2):
+        o = torch.zeros(B, Sq, D, device="cuda", dtype=torch.bfloat16)
+        ops.attention(q, k, v, o, H, seq_q=Sq, lr_res=res, lr_rows=lr or (0, 0), score_bound=30.0 if prescaled else None,
+                      variant=3, workspace=ws, split_kv=split_kv)
+        err = rel(o.float(), ref)
+        assert err < (4e-3 if prescaled else 6e-3), err
+
+
 def test_attention_mode_is_validated(ops):
     q = torch.zeros(1, 128, 64, device="cuda", dtype=torch.bfloat16)
     o = torch.zeros_like(q)

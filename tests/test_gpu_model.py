@@ -310,3 +310,87 @@ def test_fp32_module_feature_outputs_do_not_alias_the_workspace():
         _, rf = O.model_forward(sdg, cfg, hs.cuda(), lr.cuda(), enc.cuda(), pooled.cuda(), t.cuda(), as_written=False,
                                 feat_extract_layers=(0,), feat_extract="hq_feat")
     assert rel(feats[0]["extract_feat"].float().cpu(), rf[0].cpu()) <= 1e-3
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# N1 / N2 of SURVEY 8f: classifier-free guidance + LRE start point, feature outputs for the text-spotting module
+def _psnr(out, ref):
+    mse = ((out - ref) ** 2).mean().item()
+    peak = (ref.max() - ref.min()).item()
+    return 10 * torch.log10(torch.tensor(peak ** 2 / mse)).item()
+
+
+@pytest.mark.parametrize("start_point", ["noise", "lr"])
+def test_sampling_loop_with_guidance_and_lre_start(start_point):
+    """guidance_scale 8.0 (9 of the 36 shipped configs) with [negative | positive] prompt embeddings and the LRE start point,
+    against the oracle's restatement of pipelines/pipeline_dit4sr.py:1025-1034,1085,1106-1108,1561-1567 in bf16."""
+    from dit4sr_b200.sampler import denoise
+    cfg = O.sd35_medium_config(num_layers=4, dual_attention_layers=(0, 1), pos_embed_max_size=96)
+    sd = O.init_state_dict(cfg, seed=0)
+    hs, lr, enc, pooled, _ = O.make_inputs(cfg, 2, 32, 32, 77, seed=1)
+    g = torch.Generator().manual_seed(5)
+    neg, negp = 0.5 * torch.randn(enc.shape, generator=g), torch.randn(pooled.shape, generator=g)
+    bf = torch.bfloat16
+    c = lambda t: t.cuda().to(bf)
+    m = build(cfg, sd)
+    out = denoise(m, c(hs), c(lr), c(enc), c(pooled), num_inference_steps=10, guidance_scale=8.0,
+                  negative_prompt_embeds=c(neg), negative_pooled_prompt_embeds=c(negp), start_point=start_point).float().cpu()
+    sdg = {k: v.cuda().to(bf) for k, v in sd.items()}
+    with torch.no_grad():
+        ref = O.sample_loop_cfg(sdg, cfg, c(hs), c(lr), c(enc), c(pooled), c(neg), c(negp), 8.0, num_steps=10,
+                                start_point=start_point).float().cpu()
+    # the guided loop amplifies bf16 differences by the guidance scale: the two bf16 runs are compared as images
+    psnr = _psnr(out, ref)
+    print(f"guidance 8.0, start point {start_point}: PSNR vs the oracle's bf16 loop {psnr:.1f} dB")
+    assert psnr >= 40.0
+    # and one guided step against fp32 (velocity tolerance scaled by the guidance amplification)
+    from dit4sr_b200 import ops as _ops  # noqa: F401
+    eng = m.engine()
+    x2 = torch.cat([c(hs)] * 2)
+    t = torch.full((4,), 500.0, device="cuda")
+    v = eng.step(x2, torch.cat([c(lr)] * 2), torch.cat([c(neg), c(enc)]), torch.cat([c(negp), c(pooled)]), t,
+                 guidance=8.0).float().cpu()
+    sd32 = {k: v_.cuda() for k, v_ in sd.items()}
+    with torch.no_grad():
+        vv = O.model_forward(sd32, cfg, x2.float(), torch.cat([lr.cuda()] * 2), torch.cat([neg, enc]).cuda(),
+                             torch.cat([negp, pooled]).cuda(), t, as_written=False).cpu()
+    vu, vt = vv.chunk(2)
+    assert v.shape == vu.shape
+    assert rel(v, vu + 8.0 * (vt - vu)) <= 8 * VEL_TOL
+
+
+def test_feature_outputs_nchw_fp32_inside_the_graph():
+    """pipelines/pipeline_dit4sr.py:1214-1245: 'b (N H W) (pH pW d) -> b (N d) (H pH) (W pW)' to fp32, produced by the engine
+    while the graph replays (two calls: capture, then replay with other inputs), for the hq+lq concatenation."""
+    from types import SimpleNamespace as NS
+    from einops import rearrange
+    import dit4sr_b200
+    cfg = O.sd35_medium_config(num_layers=3, dual_attention_layers=(0,), pos_embed_max_size=96)
+    sd = O.init_state_dict(cfg, seed=0)
+    m = build(cfg, sd)
+    rcfg = NS(train=NS(model=["ts_module"], transformer=NS(feat_extract_layer=[0, 2], feat_extract="hqlq_feat")))
+    bf = torch.bfloat16
+    sdg = {k: v.cuda() for k, v in sd.items()}
+    for seed in (1, 2):      # first call captures the graph, second replays it
+        hs, lr, enc, pooled, t = O.make_inputs(cfg, 1, 64, 64, 20, seed=seed)
+        with torch.no_grad():
+            out, feats = m(hs.cuda().to(bf), lr.cuda().to(bf), enc.cuda().to(bf), pooled.cuda().to(bf), t.cuda(),
+                           return_dict=False, cfg=rcfg)
+            _, rf = O.model_forward(sdg, cfg, hs.cuda(), lr.cuda(), enc.cuda(), pooled.cuda(), t.cuda(), as_written=False,
+                                    feat_extract_layers=(0, 2), feat_extract="hqlq_feat")
+        assert len(feats) == 2 and feats[0]["extract_feat"].shape == (1, 2048, 1536)
+        nchw = dit4sr_b200.unpatchify_features(feats, "hqlq_feat")
+        for k in range(2):
+            want = rearrange(rf[k], "b (N H W) (pH pW d) -> b (N d) (H pH) (W pW)", N=2, H=32, W=32, pH=2, pW=2).float()
+            assert nchw[k].dtype == torch.float32 and nchw[k].shape == (1, 768, 64, 64)
+            assert rel(nchw[k].cpu(), want.cpu()) <= VEL_TOL
+            assert rel(feats[k]["extract_feat"].float().cpu(), rf[k].cpu()) <= VEL_TOL
+            # the layout itself is exact: the engine's two outputs describe the same numbers up to the bf16 cast of one
+            again = rearrange(feats[k]["extract_feat"].float(), "b (N H W) (pH pW d) -> b (N d) (H pH) (W pW)", N=2, H=32,
+                              W=32, pH=2, pW=2)
+            assert rel(again, nchw[k]) <= 4e-3
+    # a bare extract_feat (e.g. from a saved tensor) goes through the same kernel: exact rearrange
+    bare = [{"extract_feat": feats[0]["extract_feat"]}]
+    got = dit4sr_b200.unpatchify_features(bare, "hqlq_feat")[0]
+    assert torch.equal(got, rearrange(feats[0]["extract_feat"].float(), "b (N H W) (pH pW d) -> b (N d) (H pH) (W pW)",
+                                      N=2, H=32, W=32, pH=2, pW=2))

@@ -102,3 +102,19 @@ def test_sample_loop_euler():
     v = torch.ones_like(hs)
     y = O.sample_loop(sd, cfg, hs, lr, enc, pooled, num_steps=7, model_fn=lambda x_, t_: v)
     assert torch.allclose(y, hs - v, atol=1e-5)
+
+
+def test_cfg_loop_reduces_to_the_plain_loop_and_lre_blend():
+    """oracle.sample_loop_cfg (pipeline_dit4sr.py:1085,1106-1108,1561-1567): with the negative prompt equal to the positive
+    one the guided velocity equals the plain one whatever the scale; the LRE start point blends with control[:1]."""
+    import torch
+    from oracle import dit4sr_oracle as O
+    cfg = O.tiny_config()
+    sd = O.init_state_dict(cfg, seed=0)
+    hs, lr, enc, pooled, _ = O.make_inputs(cfg, 2, 8, 8, 5, seed=1)
+    with torch.no_grad():
+        a = O.sample_loop(sd, cfg, hs, lr, enc, pooled, num_steps=3)
+        b = O.sample_loop_cfg(sd, cfg, hs, lr, enc, pooled, enc, pooled, 8.0, num_steps=3)
+    assert torch.allclose(a, b, atol=2e-4, rtol=1e-4)
+    x0 = O.lre_start_point(hs, lr, 0.75)
+    assert torch.allclose(x0[1], 0.25 * lr[0] + 0.75 * hs[1])

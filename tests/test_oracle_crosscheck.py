@@ -88,3 +88,42 @@ def test_oracle_functions_agree_with_the_shim_modules():
     pe = O.sincos_pos_embed_2d(64, 6, 6)
     ref = torch.from_numpy(shim_emb.get_2d_sincos_pos_embed(64, 6, base_size=6)).float()
     assert torch.allclose(pe.reshape(-1, 64).float(), ref, atol=1e-6)
+
+
+def test_timesteps_match_the_flux_reference_embedding():
+    """diffusers Timesteps(256, flip_sin_to_cos=True, downscale_freq_shift=0) as CombinedTimestepTextProjEmbeddings builds it
+    (transformer_sd3.py:95-97) against an independent implementation of the same rectified-flow-transformer embedding:
+    torchtitan's copy of the Flux reference `timestep_embedding` ([cos | sin], freq_k = exp(-ln(1e4) k / 128), which takes
+    t in [0, 1] and multiplies by 1000).  (TVM's port of diffusers' get_timestep_embedding, tilelang/3rdparty/tvm/python/
+    tvm/relax/frontend/nn/op.py:1741-1800, documents the same flip: [sin | cos] -> [cos | sin].)"""
+    layers = pytest.importorskip("torchtitan.experiments.flux.model.layers")
+    t = torch.tensor([1000.0, 741.44, 8.93, 0.0, 333.3])
+    ours = shim_emb.Timesteps(256, flip_sin_to_cos=True, downscale_freq_shift=0)(t)
+    theirs = layers.timestep_embedding(t / 1000.0, 256)
+    assert ours.shape == theirs.shape == (5, 256)
+    assert torch.allclose(ours, theirs, atol=2e-4, rtol=0)     # fp32 phase t * freq evaluated as (t/1000)*1000*freq there
+    # and the oracle's own restatement used by model_forward
+    from oracle import dit4sr_oracle as O
+    assert torch.allclose(O.timestep_sincos(t, 256), ours, atol=1e-6, rtol=0)
+
+
+def test_gelu_tanh_matches_the_independent_closed_form():
+    """GELU(approximate='tanh') of FeedForward / FeedForwardControl (attention.py:75,135) against transformers' own
+    closed-form implementation 0.5 x (1 + tanh(sqrt(2/pi) (x + 0.044715 x^3)))."""
+    act = pytest.importorskip("transformers.activations")
+    x = torch.linspace(-6, 6, 4001)
+    g = shim_emb.nn.functional.gelu(x, approximate="tanh")
+    assert torch.allclose(g, act.NewGELUActivation()(x), atol=2e-6, rtol=0)
+
+
+def test_pos_embed_crop_is_the_centred_window_of_the_independent_table():
+    """PatchEmbed.cropped_pos_embed (transformer_sd3.py:326 -> pos_embed): the window of the pos_embed_max_size^2 table is
+    centred, top = (max - h/2) // 2, left = (max - w/2) // 2.  The table itself is cross-checked against ViT-MAE's 2-D
+    sincos; the centring rule is restated from memory of diffusers 0.31.0 (no independent copy ships in this image) - but
+    real checkpoints carry the table as a buffer, so only the window arithmetic is at stake."""
+    pe = shim_emb.PatchEmbed(height=16, width=16, patch_size=2, in_channels=4, embed_dim=32, pos_embed_max_size=12)
+    table = pe.pos_embed.reshape(12, 12, 32)
+    for h, w in ((16, 16), (8, 20), (24, 4)):
+        got = pe.cropped_pos_embed(h, w).reshape(h // 2, w // 2, 32)
+        top, left = (12 - h // 2) // 2, (12 - w // 2) // 2
+        assert torch.equal(got, table[top:top + h // 2, left:left + w // 2])
