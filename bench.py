@@ -125,7 +125,7 @@ def attention_roofline(launch_ms, flops_per_step, launches_per_step, peaks, root
                "launch (S=2381, B=8; algorithmic 263 MB q|k|v read + 59 MB o written + 50 MB LR residual read)")
     except (OSError, KeyError, ValueError, StopIteration):
         pass
-    return dict(bound="tensor", kernel="attn_fwd3_kernel / attn_fwd2_kernel (joint attention over [HQ|LR|text] and the image-only attn2, "
+    return dict(bound="tensor", kernel="attn_fwd4_kernel / attn_fwd2_kernel (joint attention over [HQ|LR|text] and the image-only attn2, "
                 "head_dim 64; the largest share of the step: MUFU.EX2 / issue limited, DESIGN.md 3.2)", achieved=round(ach, 1),
                 peak=peaks["tf_sustained"], unit="TFLOP/s", frac=round(ach / peaks["tf_sustained"], 4),
                 peak_source=peaks["source"] + ", sustained figure (kernel timed inside a long step)",
@@ -295,6 +295,9 @@ def north_star_scaling(model, world, rank, dev, barrier, steps=5, warmup=3):
                      ms_per_step=round(ms / steps, 3), steps=steps, image_steps_per_sec=round(steps / (ms / 1e3), 4),
                      step_tflop=round((gemm_f + attn_f) / 1e12, 2),
                      tflops_per_gpu=round((gemm_f + attn_f) / world / (ms / steps / 1e3) / 1e12, 1))
+        from dit4sr_b200 import ops as _ops
+        entry["attention_plan_last_call"] = dict(zip(("variant", "kv_slices", "whole_items", "tail_items"),
+                                                     _ops.attention_last_plan()))
         if bd:
             keep = ("attn", "a2a", "halo", "qkv_group", "out_group", "ff1", "ff2", "dwconv", "ln_mod")
             entry["breakdown_ms"] = {k: bd[k]["total_ms"] for k in keep if k in bd}

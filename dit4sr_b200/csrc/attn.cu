@@ -32,8 +32,8 @@ struct Args {
   float* part;      // [tail pairs][split][256 rows][PART_STRIDE] fp32: unnormalised O row, row sum, reference max
 };
 constexpr int PART_STRIDE = 68;   // 64 + l + m, padded to a multiple of 4 floats
-// scratch of the split-KV tail: (sms - 1) tail pairs x 4 slices x 256 rows
-inline int64_t workspace_bytes(int sms) { return (int64_t)(sms - 1) * 4 * 256 * PART_STRIDE * (int64_t)sizeof(float); }
+// scratch of the split-KV tail: up to sms tail pairs (or 2 sms tail tiles) x 4 slices x 256 (128) rows
+inline int64_t workspace_bytes(int sms) { return (int64_t)sms * 4 * 256 * PART_STRIDE * (int64_t)sizeof(float); }
 
 // One 32-column chunk of a finished output row (already normalised) (+ LR residual, attention.py:545) -> bf16, to the local
 // output or, under sequence parallelism, straight into the buffer of the rank that owns the row's token.
@@ -790,17 +790,18 @@ attn_fwd3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
 
 // Combines the KV slices of the tail items: thread = one query row of one (query pair, head, batch).
 //   O = sum_s alpha_s O_s / sum_s alpha_s l_s,  alpha_s = 2^(m_s - max m)  (all m_s = 0 for pre-scaled scores)
-__global__ void __launch_bounds__(2 * BQ) attn_merge_kernel(const Args args) {
+__global__ void __launch_bounds__(2 * BQ) attn_merge_kernel(const Args args) {   // blockDim.x = query rows per item
   const int tail = blockIdx.x;
   const int work = args.n_full + tail;
   const int q_pair = work % args.q_pairs;
   const int head = (work / args.q_pairs) % args.heads;
   const int b = work / (args.q_pairs * args.heads);
   const int prow = threadIdx.x;
-  const int row = q_pair * 2 * BQ + prow;
+  const int rows_item = blockDim.x;
+  const int row = q_pair * rows_item + prow;
   if (row >= args.seq_q) return;
-  const float* base = args.part + ((int64_t)tail * args.split * (2 * BQ) + prow) * PART_STRIDE;
-  const int64_t sstride = (int64_t)(2 * BQ) * PART_STRIDE;
+  const float* base = args.part + ((int64_t)tail * args.split * rows_item + prow) * PART_STRIDE;
+  const int64_t sstride = (int64_t)rows_item * PART_STRIDE;
   float m_all = -INFINITY, l_all = 0.f;
   for (int sl = 0; sl < args.split; ++sl) m_all = fmaxf(m_all, base[sl * sstride + DH + 1]);
   float alpha[4];
@@ -840,6 +841,297 @@ __global__ void __launch_bounds__(2 * BQ) attn_merge_kernel(const Args args) {
 
 }  // namespace v3
 
+// =====================================================================================================================
+// v4: ONE 128-row query tile per CTA, two CTAs co-resident per SM.
+//
+// v3 at the C2 shape spends ~11 % of a CTA's life outside its KV loop (first Q/K/V loads from L2, TMEM allocation, the
+// epilogue, the relaunch gap) and its two query tiles start and end together.  Here the two tiles of an SM are separate
+// CTAs: the hardware scheduler starts the next one while the neighbour is still in its KV loop, so one CTA's prologue /
+// epilogue runs under the other's exponentials, and the work items are half as long (finer tail).  Each CTA is v3 for a
+// single tile: 256 TMEM columns (two 96-key score buffers + the 64-column O accumulator), three K/V stages (89 KB of
+// shared memory), 256 threads = warpgroup 0 (TMA producer, MMA issuer + TMEM allocator, two idle warps: setmaxnreg is per
+// warpgroup) + warpgroup 1 (softmax).  K/V are loaded once per tile instead of once per tile pair: the L2 reads of v3 use
+// 13 % of the L2 throughput (profiles/r02_ncu_full_attention.json), so doubling them is affordable.
+// Barriers as in v3: s_full[b], p_full[b], o_done (online rescale only), o_final (epilogue).
+namespace v4 {
+
+constexpr int BKV = 96;
+constexpr int KV_BYTES = BKV * DH * 2;   // 12 KB
+constexpr int KV_STAGES = 3;
+constexpr int NUM_THREADS = 256;
+constexpr int TMEM_COLS = 256;
+constexpr int COL_O = 2 * BKV;
+constexpr int SMEM_BYTES = TILE_BYTES + 2 * KV_STAGES * KV_BYTES + 1024 + 256;
+constexpr float RESCALE_THRESHOLD = 8.0f;
+
+template <int POLY8, bool PRESCALED, bool SLICED>
+__global__ void __launch_bounds__(NUM_THREADS, 2)
+attn_fwd4_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
+                 const __grid_constant__ CUtensorMap tmV, const Args args) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sQ = smem;                                            // one tile of 128 rows
+  uint8_t* sK = smem + TILE_BYTES;                               // KV_STAGES tiles of 96 rows
+  uint8_t* sV = sK + KV_STAGES * KV_BYTES;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sV + KV_STAGES * KV_BYTES);
+  uint64_t* q_full = bars;
+  uint64_t* k_full = bars + 1;
+  uint64_t* k_empty = k_full + KV_STAGES;
+  uint64_t* v_full = k_empty + KV_STAGES;
+  uint64_t* v_empty = v_full + KV_STAGES;
+  uint64_t* s_full = v_empty + KV_STAGES;   // [2 buffers]
+  uint64_t* p_full = s_full + 2;            // [2]
+  uint64_t* o_done = p_full + 2;            // P V of a step complete (online rescale only)
+  uint64_t* o_final = o_done + 1;           // the last P V complete (epilogue)
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(o_final + 1);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  // (see v3 for why the whole items come as a 3-D grid and the KV slices of the tail items as a second launch)
+  int work, slice, q_tile, head, b, j0, n_tiles;
+  bool last_kv;
+  if constexpr (!SLICED) {
+    q_tile = blockIdx.x, head = blockIdx.y, b = blockIdx.z;
+    work = q_tile + args.q_pairs * (head + args.heads * b);      // (q_pairs = query tiles per (head, batch) here)
+    if (work >= args.n_full) return;
+    slice = -1, j0 = 0, n_tiles = args.n_kv_tiles, last_kv = true;
+  } else {
+    work = args.n_full + blockIdx.x / args.split;
+    slice = blockIdx.x % args.split;
+    q_tile = work % args.q_pairs;
+    head = (work / args.q_pairs) % args.heads;
+    b = work / (args.q_pairs * args.heads);
+    j0 = slice * args.tiles_per_slice;
+    n_tiles = min(args.tiles_per_slice, args.n_kv_tiles - j0);
+    last_kv = j0 + n_tiles == args.n_kv_tiles;
+  }
+
+  if (warp == 0 && lane == 0) {
+    ptx::prefetch_tmap(&tmQ);
+    ptx::prefetch_tmap(&tmK);
+    ptx::prefetch_tmap(&tmV);
+    ptx::mbar_init(q_full, 1);
+    for (int i = 0; i < KV_STAGES; ++i) {
+      ptx::mbar_init(&k_full[i], 1);
+      ptx::mbar_init(&k_empty[i], 1);
+      ptx::mbar_init(&v_full[i], 1);
+      ptx::mbar_init(&v_empty[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      ptx::mbar_init(&s_full[i], 1);
+      ptx::mbar_init(&p_full[i], 4);
+    }
+    ptx::mbar_init(o_done, 1);
+    ptx::mbar_init(o_final, 1);
+    ptx::fence_barrier_init();
+  }
+  if (warp == 1) {
+    ptx::tmem_alloc(tmem_ptr, TMEM_COLS);
+    ptx::tmem_relinquish();
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+
+  if (warp < 4) {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
+    if (warp == 0) {
+      if (lane == 0) {
+        // ===================== TMA producer =====================
+        ptx::mbar_expect_tx(q_full, TILE_BYTES);
+        ptx::tma_load_3d(sQ, &tmQ, q_full, head * DH, q_tile * BQ, b);
+        for (int j = 0; j < n_tiles; ++j) {
+          const int st = j % KV_STAGES;
+          const uint32_t ph = (j / KV_STAGES) & 1;
+          ptx::mbar_wait(&k_empty[st], ph ^ 1);
+          ptx::mbar_expect_tx(&k_full[st], KV_BYTES);
+          ptx::tma_load_3d(sK + st * KV_BYTES, &tmK, &k_full[st], head * DH, (j0 + j) * BKV, b);
+          ptx::mbar_wait(&v_empty[st], ph ^ 1);
+          ptx::mbar_expect_tx(&v_full[st], KV_BYTES);
+          ptx::tma_load_3d(sV + st * KV_BYTES, &tmV, &v_full[st], head * DH, (j0 + j) * BKV, b);
+        }
+      }
+    } else if (warp == 1) {
+      // ===================== MMA issuer (whole warp runs the loop; one elected lane issues) =====================
+      constexpr uint32_t idesc_qk = ptx::make_idesc_bf16(BQ, BKV, 0, 0);
+      constexpr uint32_t idesc_pv = ptx::make_idesc_bf16(BQ, DH, 0, 1);
+      const uint64_t qdesc = ptx::make_sdesc_sw128(ptx::smem_u32(sQ));
+      const uint64_t kdesc_base = ptx::make_sdesc_sw128(ptx::smem_u32(sK));
+      const uint64_t vdesc_base = ptx::make_sdesc_sw128(ptx::smem_u32(sV));
+      const uint32_t tS0 = tmem_base;
+      const uint32_t tO = tmem_base + COL_O;
+
+      auto issue_qk = [&](int j) {   // S(j&1) = Q K_j^T
+        const int st = j % KV_STAGES, buf = j & 1;
+        ptx::mbar_wait(&k_full[st], (j / KV_STAGES) & 1);
+        ptx::tc_fence_after();
+        const uint64_t kdesc = kdesc_base + (uint64_t)(st * (KV_BYTES >> 4));
+        if (ptx::elect_one()) {
+#pragma unroll
+          for (int k = 0; k < DH / 16; ++k)
+            ptx::mma_ss(tS0 + buf * BKV, qdesc + 2 * k, kdesc + 2 * k, idesc_qk, k != 0);
+          ptx::tc_commit(&s_full[buf]);
+          ptx::tc_commit(&k_empty[st]);
+        }
+        __syncwarp();
+      };
+
+      ptx::mbar_wait(q_full, 0);
+      issue_qk(0);
+      if (n_tiles > 1) issue_qk(1);
+      for (int j = 0; j < n_tiles; ++j) {
+        const int st = j % KV_STAGES, buf = j & 1;
+        ptx::mbar_wait(&v_full[st], (j / KV_STAGES) & 1);
+        ptx::mbar_wait(&p_full[buf], (j >> 1) & 1);   // P_j is in the buffer (and O rescaled if needed)
+        ptx::tc_fence_after();
+        const uint64_t vdesc = vdesc_base + (uint64_t)(st * (KV_BYTES >> 4));
+        if (ptx::elect_one()) {
+#pragma unroll
+          for (int k = 0; k < BKV / 16; ++k)   // O += P V_j: A = P from TMEM (8 columns per 16 keys), B = V MN-major
+            ptx::mma_ts(tO, tS0 + buf * BKV + 8 * k, vdesc + (uint64_t)(128 * k), idesc_pv, (j | k) != 0);
+          ptx::tc_commit(o_done);
+          ptx::tc_commit(&v_empty[st]);
+          if (j + 1 == n_tiles) ptx::tc_commit(o_final);
+        }
+        __syncwarp();
+        if (j + 2 < n_tiles) issue_qk(j + 2);   // into the buffer P_j just left (ordered behind P V_j in the tensor pipe)
+      }
+    }
+  } else {
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 216;");
+    // ===================== softmax warpgroup (thread = one query row = one TMEM lane) =====================
+    const int q = warp & 3;          // TMEM lane quarter
+    const uint32_t lane_off = (uint32_t)(q * 32) << 16;
+    const uint32_t tS0 = tmem_base + lane_off;
+    const uint32_t tO = tmem_base + COL_O + lane_off;
+    const float sl2 = args.scale_log2;
+    float m_run = -INFINITY;   // the max the running sums are scaled with (raw score units; online form only)
+    float l_run = 0.f;
+    auto tile_step = [&](int j, auto masked) {
+      const int buf = j & 1;
+      const uint32_t tS = tS0 + buf * BKV;
+      ptx::mbar_wait(&s_full[buf], (j >> 1) & 1);
+      ptx::tc_fence_after();
+      uint32_t v[BKV];
+#pragma unroll
+      for (int c = 0; c < BKV / 32; ++c) ptx::tmem_ld32(tS + c * 32, *reinterpret_cast<uint32_t(*)[32]>(&v[c * 32]));
+      ptx::tmem_wait_ld();
+      if constexpr (decltype(masked)::value) {   // only the last KV tile can be ragged
+        const int kv_left = args.seq_kv - (j0 + j) * BKV;
+#pragma unroll
+        for (int i = 0; i < BKV; ++i)
+          if (i >= kv_left) v[i] = 0xff800000u;   // -inf
+      }
+      float alpha = 1.0f;
+      bool grow = false;
+      if constexpr (!PRESCALED) {
+        float mxa[8];   // 8 independent max chains, then a small tree
+#pragma unroll
+        for (int a = 0; a < 8; ++a) mxa[a] = __uint_as_float(v[a]);
+#pragma unroll
+        for (int i = 8; i < BKV; i += 8)
+#pragma unroll
+          for (int a = 0; a < 8; ++a) mxa[a] = fmaxf(mxa[a], __uint_as_float(v[i + a]));
+        const float mx = fmaxf(fmaxf(fmaxf(mxa[0], mxa[1]), fmaxf(mxa[2], mxa[3])),
+                               fmaxf(fmaxf(mxa[4], mxa[5]), fmaxf(mxa[6], mxa[7])));
+        grow = (mx - m_run) * sl2 > RESCALE_THRESHOLD;   // true on the first tile (m_run = -inf)
+        if (grow) {
+          alpha = ptx::ex2((m_run - mx) * sl2);
+          m_run = mx;
+        }
+      }
+      const float neg_m = -m_run * sl2;   // (unused when PRESCALED)
+      uint64_t rs2[4];                    // independent packed partial row sums
+#pragma unroll
+      for (int a = 0; a < 4; ++a) rs2[a] = ptx::pack2(0.f, 0.f);
+      const uint64_t sl2_2 = ptx::pack2(sl2, sl2), negm_2 = ptx::pack2(neg_m, neg_m);
+      uint32_t pk[BKV / 2];
+#pragma unroll
+      for (int i = 0; i < BKV / 2; ++i) {
+        uint64_t x2 = ptx::pack2(__uint_as_float(v[2 * i]), __uint_as_float(v[2 * i + 1]));
+        if constexpr (!PRESCALED) x2 = ptx::fma2(x2, sl2_2, negm_2);
+        float p0, p1;
+        if (!decltype(masked)::value && (i & 7) < POLY8) {
+          v2::exp2_poly2<!PRESCALED>(x2, p0, p1);
+        } else {
+          float xa, xb;
+          ptx::unpack2(x2, xa, xb);
+          p0 = ptx::ex2(xa);
+          p1 = ptx::ex2(xb);
+        }
+        rs2[i & 3] = ptx::add2(rs2[i & 3], ptx::pack2(p0, p1));
+        pk[i] = ptx::pack_bf16(p0, p1);
+      }
+      float ra, rb, rc, rd;
+      ptx::unpack2(ptx::add2(rs2[0], rs2[1]), ra, rb);
+      ptx::unpack2(ptx::add2(rs2[2], rs2[3]), rc, rd);
+      const float rsum = (ra + rb) + (rc + rd);
+      // O may only be touched between P V(j-1) completing and P V(j) being issued (it is issued after our arrive)
+      if (!PRESCALED && j > 0 && __any_sync(0xffffffffu, grow)) {
+        ptx::mbar_wait(o_done, (j - 1) & 1);
+        ptx::tc_fence_after();
+#pragma unroll 1
+        for (int c = 0; c < DH / 32; ++c) {
+          uint32_t o[32];
+          ptx::tmem_ld32(tO + c * 32, o);
+          ptx::tmem_wait_ld();
+#pragma unroll
+          for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
+          ptx::tmem_st32(tO + c * 32, o);
+        }
+      }
+      // P overwrites the first 48 columns of the score buffer (the whole row is already in registers)
+#pragma unroll
+      for (int c = 0; c < BKV / 32; ++c) ptx::tmem_st16(tS + c * 16, &pk[c * 16]);
+      l_run = l_run * alpha + rsum;
+      ptx::tmem_wait_st();
+      ptx::tc_fence_before();
+      __syncwarp();
+      if (lane == 0) ptx::mbar_arrive(&p_full[buf]);
+    };
+    const bool ragged = last_kv && (args.seq_kv % BKV) != 0;
+    for (int j = 0; j + 1 < n_tiles; ++j) tile_step(j, std::false_type{});
+    if (ragged) tile_step(n_tiles - 1, std::true_type{});
+    else tile_step(n_tiles - 1, std::false_type{});
+
+    // epilogue (see v3 for why the last P V has its own barrier)
+    ptx::mbar_wait(o_final, 0);
+    ptx::tc_fence_after();
+    const int row = q_tile * BQ + q * 32 + lane;
+    if constexpr (!SLICED) {
+      store_rows(args, tO, row, head, b, 1.0f / l_run);
+    } else {
+      // one KV slice of a tail item: publish the unnormalised row; attn_merge_kernel combines the slices
+      const int tail = work - args.n_full;
+      const int prow = q * 32 + lane;
+      float* mine = args.part + (((int64_t)tail * args.split + slice) * BQ + prow) * PART_STRIDE;
+#pragma unroll 1
+      for (int c = 0; c < DH / 32; ++c) {
+        uint32_t o[32];
+        ptx::tmem_ld32(tO + c * 32, o);
+        ptx::tmem_wait_ld();
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+          __stcg(reinterpret_cast<float4*>(mine + c * 32) + i,
+                 make_float4(__uint_as_float(o[4 * i]), __uint_as_float(o[4 * i + 1]), __uint_as_float(o[4 * i + 2]),
+                             __uint_as_float(o[4 * i + 3])));
+      }
+      __stcg(reinterpret_cast<float2*>(mine + DH), make_float2(l_run, PRESCALED ? 0.f : m_run * sl2));
+    }
+  }
+
+  __syncwarp();
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    ptx::tc_fence_after();
+    ptx::tmem_dealloc(tmem_base, TMEM_COLS);
+  }
+}
+
+}  // namespace v4
+
 }  // namespace attn
 
 #ifdef DIT4SR_ATTN_TIMING
@@ -849,6 +1141,14 @@ extern "C" int dit4sr_attn_timing_read(long long* host_out /* [12*16] */) {
   return 0;
 }
 #endif
+
+static int g_last_plan[4] = {0, 0, 0, 0};   // variant, split, whole items, tail items of the latest dit4sr_attn_fwd call
+
+extern "C" int dit4sr_attn_last_plan(int plan[4]) {
+  DIT4SR_REQUIRE(plan != nullptr, DIT4SR_E_BADARG, "attn_last_plan: null argument");
+  for (int i = 0; i < 4; ++i) plan[i] = g_last_plan[i];
+  return 0;
+}
 
 extern "C" int64_t dit4sr_attn_workspace_bytes(void) {
   int dev = 0, sms = 0;
@@ -890,43 +1190,61 @@ extern "C" int dit4sr_attn_fwd(const dit4sr_attn_params* p, void* stream_) {
                  "attn: DIT4SR_ATTN_PRESCALED needs 0 < score_bound <= %g (log2 units), got %g",
                  (double)DIT4SR_ATTN_MAX_SCORE_BOUND, (double)p->score_bound);
   DIT4SR_REQUIRE(p->exp_offload >= 0 && p->exp_offload <= 3, DIT4SR_E_BADARG, "attn: exp_offload must be 0..3");
-  DIT4SR_REQUIRE(p->variant == 0 || p->variant == 2 || p->variant == 3, DIT4SR_E_BADARG, "attn: variant must be 0, 2 or 3");
+  DIT4SR_REQUIRE(p->variant == 0 || (p->variant >= 2 && p->variant <= 4), DIT4SR_E_BADARG, "attn: variant must be 0, 2, 3 or 4");
   DIT4SR_REQUIRE(p->workspace == nullptr || host::aligned16(p->workspace), DIT4SR_E_ALIGN, "attn: workspace must be 16-byte aligned");
 
   int rc = dit4sr_check_device();
   if (rc != 0) return rc;
 
-  // Work decomposition.  v3 runs a 1-D grid of work items; when the items do not fill the last wave of SMs, the tail
-  // items are cut into `split` KV slices whose partial results are merged by the last slice to finish (needs workspace).
+  // Work decomposition.  An item = one (query tile pair | query tile, head, batch); `slots` items run at a time (one per SM
+  // for v2 / v3, two for v4).  When the items do not fill the last wave of slots, the tail items are cut into `split` KV
+  // slices (second launch) whose partial rows a small merge kernel combines (v3 / v4, needs workspace).
   const int sms = host::sm_count();
-  const int q_pairs = (p->seq_q + 2 * BQ - 1) / (2 * BQ);
-  const int64_t items64 = (int64_t)q_pairs * p->heads * p->batches;
-  DIT4SR_REQUIRE(items64 < (1ll << 30), DIT4SR_E_SHAPE, "attn: too many work items");
-  const int items = (int)items64;
   const int tiles96 = (p->seq_kv + v3::BKV - 1) / v3::BKV;
-  int split = 1, n_full = items;
-  double tail_cost = 0.0;
-  {
-    const int tail = items % sms;
-    tail_cost = tail > 0 ? 1.0 : 0.0;
-    const int64_t need = attn::workspace_bytes(sms);
-    if (tail > 0 && p->workspace != nullptr && p->workspace_bytes >= need && p->split_kv >= 0) {
+  const int pad96 = tiles96 * v3::BKV, pad128 = (p->seq_kv + 127) / 128 * 128;
+  auto plan = [&](int rows_per_item, int slots, bool can_split, int* items_out, int* split_out, int* n_full_out) {
+    const int64_t items64 = (int64_t)((p->seq_q + rows_per_item - 1) / rows_per_item) * p->heads * p->batches;
+    const int items = (int)(items64 < (1ll << 30) ? items64 : (1ll << 30));
+    int split = 1, n_full = items;
+    const int tail = items % slots;
+    double tail_cost = tail > 0 ? 1.0 : 0.0;
+    if (can_split && tail > 0 && p->workspace != nullptr && p->workspace_bytes >= attn::workspace_bytes(sms) &&
+        p->split_kv >= 0) {
       for (int sdiv = 2; sdiv <= 4; ++sdiv) {
         if (tiles96 / sdiv < 4) break;                                   // keep slices long enough to amortise a prologue
-        const double c = (double)((tail * sdiv + sms - 1) / sms) / sdiv + 0.03 * (sdiv - 1);
+        const double c = (double)((tail * sdiv + slots - 1) / slots) / sdiv + 0.03 * (sdiv - 1);
         if (c < tail_cost - 1e-9) { tail_cost = c; split = sdiv; }
       }
-      if (p->split_kv > 0 && tiles96 / p->split_kv >= 1) split = p->split_kv > 4 ? 4 : p->split_kv;   // forced (tests / A-B)
+      if (p->split_kv > 0 && tiles96 / p->split_kv >= 1) {               // forced (tests / A-B)
+        split = p->split_kv > 4 ? 4 : p->split_kv;
+        tail_cost = (double)((tail * split + slots - 1) / slots) / split;
+      }
       if (split > 1) n_full = items - tail;
     }
+    *items_out = items, *split_out = split, *n_full_out = n_full;
+    return (double)(items / slots) + tail_cost;                          // waves of item-lengths
+  };
+  int items2, split2, nf2, items3, split3, nf3, items4, split4, nf4;
+  const double waves2 = plan(2 * BQ, sms, false, &items2, &split2, &nf2);
+  const double waves3 = plan(2 * BQ, sms, true, &items3, &split3, &nf3);
+  const double waves4 = plan(BQ, 2 * sms, true, &items4, &split4, &nf4);
+  DIT4SR_REQUIRE(items4 < (1 << 30), DIT4SR_E_SHAPE, "attn: too many work items");
+  // default kernel: the cheapest under a cost model fitted to kbench timings on B200 (profiles/r02_attn_v4.log):
+  //   time ~ waves x (KV steps + fixed per-CTA overhead in steps) x time per step
+  // v3 shares every K/V tile between two query tiles (0.848 us per 96-key step and SM) but pays ~7.5 steps of prologue /
+  // epilogue per CTA; v4's co-resident CTAs hide most of that (2.3) at 0.888 us per step; v2 steps are 128 keys wide.
+  int variant = p->variant;
+  if (variant == 0) {
+    const int tiles128 = pad128 / 128;
+    const double c2 = waves2 * (tiles128 + 5.5) * 1.130, c3 = waves3 * (tiles96 + 7.5) * 0.848,
+                 c4 = waves4 * (tiles96 + 2.3) * 0.888;
+    variant = c4 <= c3 ? (c4 <= c2 ? 4 : 2) : (c3 <= c2 ? 3 : 2);
   }
-  // default kernel: compare padded length x waves of the two tilings (v2 has no tail splitting)
-  const int pad96 = tiles96 * v3::BKV, pad128 = (p->seq_kv + 127) / 128 * 128;
-  const double cost3 = pad96 * ((double)(items / sms) + (split > 1 ? tail_cost : (items % sms ? 1.0 : 0.0)));
-  const double cost2 = pad128 * (double)((items + sms - 1) / sms);
-  const int variant = p->variant != 0 ? p->variant : (cost3 <= cost2 ? 3 : 2);
-  if (variant != 3) { split = 1; n_full = items; }
-  const int bkv = variant == 3 ? v3::BKV : BKV;
+  const int items = variant == 4 ? items4 : (variant == 3 ? items3 : items2);
+  const int split = variant == 4 ? split4 : (variant == 3 ? split3 : 1);
+  const int n_full = variant == 4 ? nf4 : (variant == 3 ? nf3 : items2);
+  const int q_pairs = (p->seq_q + (variant == 4 ? BQ : 2 * BQ) - 1) / (variant == 4 ? BQ : 2 * BQ);   // items per (head, batch)
+  const int bkv = variant == 2 ? BKV : v3::BKV;
   CUtensorMap tmQ, tmK, tmV;
   const uint64_t dims[3] = {(uint64_t)p->heads * DH, (uint64_t)p->seq_kv, (uint64_t)p->batches};
   const uint64_t strides[2] = {(uint64_t)p->qkv_row_stride * 2,
@@ -970,32 +1288,38 @@ extern "C" int dit4sr_attn_fwd(const dit4sr_attn_params* p, void* stream_) {
 
   // instance = (kernel, softmax form, share of the exponentials evaluated on the FMA pipe; exp_offload 0 = default 2/8)
   using KernelFn = void (*)(const CUtensorMap, const CUtensorMap, const CUtensorMap, const Args);
-  static const KernelFn table[2][2][3] = {
+  static const KernelFn whole[3][2][3] = {
       {{v2::attn_fwd2_kernel<0, false>, v2::attn_fwd2_kernel<2, false>, v2::attn_fwd2_kernel<4, false>},
        {v2::attn_fwd2_kernel<0, true>, v2::attn_fwd2_kernel<2, true>, v2::attn_fwd2_kernel<4, true>}},
       {{v3::attn_fwd3_kernel<0, false, false>, v3::attn_fwd3_kernel<2, false, false>, v3::attn_fwd3_kernel<4, false, false>},
-       {v3::attn_fwd3_kernel<0, true, false>, v3::attn_fwd3_kernel<2, true, false>, v3::attn_fwd3_kernel<4, true, false>}}};
-  static const KernelFn sliced[2][3] = {
-      {v3::attn_fwd3_kernel<0, false, true>, v3::attn_fwd3_kernel<2, false, true>, v3::attn_fwd3_kernel<4, false, true>},
-      {v3::attn_fwd3_kernel<0, true, true>, v3::attn_fwd3_kernel<2, true, true>, v3::attn_fwd3_kernel<4, true, true>}};
+       {v3::attn_fwd3_kernel<0, true, false>, v3::attn_fwd3_kernel<2, true, false>, v3::attn_fwd3_kernel<4, true, false>}},
+      {{v4::attn_fwd4_kernel<0, false, false>, v4::attn_fwd4_kernel<2, false, false>, v4::attn_fwd4_kernel<4, false, false>},
+       {v4::attn_fwd4_kernel<0, true, false>, v4::attn_fwd4_kernel<2, true, false>, v4::attn_fwd4_kernel<4, true, false>}}};
+  static const KernelFn sliced[2][2][3] = {
+      {{v3::attn_fwd3_kernel<0, false, true>, v3::attn_fwd3_kernel<2, false, true>, v3::attn_fwd3_kernel<4, false, true>},
+       {v3::attn_fwd3_kernel<0, true, true>, v3::attn_fwd3_kernel<2, true, true>, v3::attn_fwd3_kernel<4, true, true>}},
+      {{v4::attn_fwd4_kernel<0, false, true>, v4::attn_fwd4_kernel<2, false, true>, v4::attn_fwd4_kernel<4, false, true>},
+       {v4::attn_fwd4_kernel<0, true, true>, v4::attn_fwd4_kernel<2, true, true>, v4::attn_fwd4_kernel<4, true, true>}}};
   const int po = p->exp_offload == 0 ? 1 : p->exp_offload - 1;
-  const int vi = variant == 3 ? 1 : 0, mi = prescaled ? 1 : 0;
-  const KernelFn fn = table[vi][mi][po];
-  const int smem = variant == 3 ? v3::SMEM_BYTES : v2::SMEM_BYTES;
+  const int vi = variant - 2, mi = prescaled ? 1 : 0;
+  const KernelFn fn = whole[vi][mi][po];
+  const int smem = variant == 4 ? v4::SMEM_BYTES : (variant == 3 ? v3::SMEM_BYTES : v2::SMEM_BYTES);
+  const int threads = variant == 4 ? v4::NUM_THREADS : 384;
   // the opt-in to > 48 KB of dynamic shared memory is per (function, device): remember which pairs are done
-  static unsigned long long configured[2][2][3] = {}, configured_s[2][3] = {};
+  static unsigned long long configured[3][2][3] = {}, configured_s[2][2][3] = {};
   if (host::first_use_on_device(&configured[vi][mi][po]))
     DIT4SR_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  g_last_plan[0] = variant, g_last_plan[1] = split, g_last_plan[2] = n_full, g_last_plan[3] = items - n_full;
   dim3 grid(q_pairs, p->heads, p->batches);
-  fn<<<grid, 384, smem, stream>>>(tmQ, tmK, tmV, a);   // (v3: items >= n_full exit at once)
+  fn<<<grid, threads, smem, stream>>>(tmQ, tmK, tmV, a);   // (v3 / v4: items >= n_full exit at once)
   DIT4SR_CUDA(cudaGetLastError());
   if (split > 1) {   // the tail items again, as KV slices, then the merge
-    const KernelFn fs = sliced[mi][po];
-    if (host::first_use_on_device(&configured_s[mi][po]))
+    const KernelFn fs = sliced[variant - 3][mi][po];
+    if (host::first_use_on_device(&configured_s[variant - 3][mi][po]))
       DIT4SR_CUDA(cudaFuncSetAttribute(fs, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    fs<<<(items - n_full) * split, 384, smem, stream>>>(tmQ, tmK, tmV, a);
+    fs<<<(items - n_full) * split, threads, smem, stream>>>(tmQ, tmK, tmV, a);
     DIT4SR_CUDA(cudaGetLastError());
-    v3::attn_merge_kernel<<<items - n_full, 2 * BQ, 0, stream>>>(a);
+    v3::attn_merge_kernel<<<items - n_full, variant == 4 ? BQ : 2 * BQ, 0, stream>>>(a);
     DIT4SR_CUDA(cudaGetLastError());
   }
   return 0;

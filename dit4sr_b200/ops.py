@@ -207,6 +207,13 @@ def attention_workspace_bytes():
     return int(_lib.load().dit4sr_attn_workspace_bytes())
 
 
+def attention_last_plan():
+    """(kernel variant, KV slices per tail item, whole items, tail items) of the latest attention call (diagnostics)."""
+    plan = (C.c_int * 4)()
+    check(_lib.load().dit4sr_attn_last_plan(plan), "dit4sr_attn_last_plan")
+    return tuple(plan)
+
+
 ATTN_ONLINE, ATTN_PRESCALED = 0, 1
 ATTN_MAX_SCORE_BOUND = 60.0
 

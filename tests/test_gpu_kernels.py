@@ -222,6 +222,27 @@ def test_joint_attention(ops, B, H, S, Sq, lr):
 LOG2E_OVER_8 = 1.4426950408889634 / 8.0
 
 
+@pytest.mark.parametrize("variant", [0, 2, 3, 4])
+@pytest.mark.parametrize("B,H,S,Sq,lr", [(1, 2, 256, 256, None), (2, 3, 333, 333, None), (2, 4, 2381, 2048, (1024, 2048)),
+                                         (1, 1, 1, 1, None), (3, 24, 129, 129, None)])
+def test_joint_attention_every_kernel_variant(ops, B, H, S, Sq, lr, variant):
+    """The three pipelines (2: rotating 128-key buffers, 3: two tiles per CTA with double-buffered 96-key tiles, 4: one tile
+    per CTA, two CTAs per SM) and the default choice, online softmax, against fp32 SDPA."""
+    torch.manual_seed(0)
+    D = H * 64
+    qkv = torch.randn(B, S, 3 * D, device="cuda").bfloat16()
+    q, k, v = qkv[..., :D], qkv[..., D:2 * D], qkv[..., 2 * D:]
+    o = torch.zeros(B, Sq, D, device="cuda", dtype=torch.bfloat16)
+    res = torch.randn(B, S, D, device="cuda").bfloat16() if lr else None
+    ops.attention(q, k, v, o, H, seq_q=Sq, lr_res=res, lr_rows=lr or (0, 0), variant=variant)
+    hd = lambda t: t.float().reshape(B, S, H, 64).transpose(1, 2)
+    ref = torch.nn.functional.scaled_dot_product_attention(hd(q), hd(k), hd(v)).transpose(1, 2).reshape(B, S, D)
+    ref = ref[:, :Sq].clone()
+    if lr:
+        ref[:, lr[0]:lr[1]] += res[:, lr[0]:lr[1]].float()
+    assert rel(o.float(), ref) < 4e-3
+
+
 @pytest.mark.parametrize("exp_offload", [0, 1, 3])
 @pytest.mark.parametrize("B,H,S,Sq,lr", [(1, 2, 256, 256, None), (2, 3, 333, 333, None), (1, 24, 2381, 2381, (1024, 2048)),
                                          (2, 4, 2381, 2048, (1024, 2048)), (1, 1, 1, 1, None), (8, 24, 600, 333, (100, 300)),
@@ -299,12 +320,13 @@ def test_attention_at_the_c4_per_rank_shape(ops, prescaled):
     assert worst < 4e-3
 
 
+@pytest.mark.parametrize("variant", [3, 4])
 @pytest.mark.parametrize("prescaled", [False, True])
 @pytest.mark.parametrize("split_kv", [0, 2, 3, 4])
-@pytest.mark.parametrize("B,H,S,Sq,lr", [(1, 24, 2381, 2381, (1024, 2048)),      # 240 items on 148 SMs: 92 tail items
+@pytest.mark.parametrize("B,H,S,Sq,lr", [(1, 24, 2381, 2381, (1024, 2048)),      # 240 pair items on 148 SMs: 92 tail items
                                          (2, 3, 4000, 3900, None),                 # 96 items: everything is tail
                                          (1, 2, 1000, 1000, None)])
-def test_attention_split_kv_tail(ops, B, H, S, Sq, lr, split_kv, prescaled):
+def test_attention_split_kv_tail(ops, B, H, S, Sq, lr, split_kv, prescaled, variant):
     """Work items that do not fill the last wave of SMs are cut into KV slices whose partial rows (unnormalised O, row sum,
     reference max) are merged by a second small kernel: same result as the unsplit kernel, for both softmax forms, ragged
     last tiles and the LR residual (two launches on the same scratch)."""
@@ -327,7 +349,7 @@ def test_attention_split_kv_tail(ops, B, H, S, Sq, lr, split_kv, prescaled):
     for _ in range(2):
         o = torch.zeros(B, Sq, D, device="cuda", dtype=torch.bfloat16)
         ops.attention(q, k, v, o, H, seq_q=Sq, lr_res=res, lr_rows=lr or (0, 0), score_bound=30.0 if prescaled else None,
-                      variant=3, workspace=ws, split_kv=split_kv)
+                      variant=variant, workspace=ws, split_kv=split_kv)
         err = rel(o.float(), ref)
         assert err < (4e-3 if prescaled else 6e-3), err
 

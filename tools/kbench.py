@@ -45,6 +45,7 @@ def main():
     ap.add_argument("what")
     ap.add_argument("--reps", type=int, default=20)
     ap.add_argument("--shape", default="c2")
+    ap.add_argument("--split", type=int, default=-1, help="attn: -1 no workspace, 0 automatic split-KV tail, 2..4 forced")
     ap.add_argument("--variant", type=int, default=0, help="attn: 0 default, 2 rotating buffers, 3 double-buffered 96-key tiles")
     ap.add_argument("--graph", action="store_true")
     ap.add_argument("--prescaled", action="store_true", help="attn: DIT4SR_ATTN_PRESCALED mode (q pre-multiplied)")
@@ -54,6 +55,8 @@ def main():
     GRAPH = a.graph
     B, N, T = (8, 1024, 333) if a.shape == "c2" else (2, 4096, 333)
     D, H, F = 1536, 24, 6144
+    if a.shape == "c4rank":      # what one of 8 ranks runs under Ulysses at 2048px: 3 heads over the whole sequence
+        B, N, T, D, H = 1, 16384, 333, 192, 3
     S = 2 * N + T
     dev = "cuda"
     torch.manual_seed(0)
@@ -64,11 +67,13 @@ def main():
         qkv = qkv.bfloat16()
         o = torch.empty(B, S, D, device=dev, dtype=torch.bfloat16)
         res = torch.randn(B, 2 * N, D, device=dev).bfloat16()
+        wsp = torch.empty(ops.attention_workspace_bytes(), device=dev, dtype=torch.uint8) if a.split >= 0 else None
         fn = lambda: ops.attention(qkv[..., :D], qkv[..., D:2 * D], qkv[..., 2 * D:], o, H, lr_res=res, lr_rows=(N, 2 * N),
-                                   score_bound=30.0 if a.prescaled else None, exp_offload=a.exp_offload, variant=a.variant)
+                                   score_bound=30.0 if a.prescaled else None, exp_offload=a.exp_offload, variant=a.variant,
+                                   workspace=wsp, split_kv=max(a.split, 0))
         ms = timeit(fn, a.reps)
         fl = 4.0 * S * S * D * B
-        print(f"attn B={B} S={S} prescaled={a.prescaled} exp_offload={a.exp_offload} variant={a.variant}: {ms:.4f} ms  {fl / ms / 1e9:.1f} TFLOP/s")
+        print(f"attn B={B} S={S} prescaled={a.prescaled} exp_offload={a.exp_offload} variant={a.variant} split={a.split}: {ms:.4f} ms  {fl / ms / 1e9:.1f} TFLOP/s")
     elif a.what == "gemm":
         for name, M, K, Nn, epi in [("ff1", B * 2 * N, D, F, ops.EPI_BIAS_GELU), ("ff2", B * 2 * N, F, D, ops.EPI_GATE_RESID),
                                     ("qkv", B * N, D, 3 * D, ops.EPI_QKV_NORM), ("out", B * N, D, D, ops.EPI_GATE_RESID)]:

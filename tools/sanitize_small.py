@@ -26,7 +26,7 @@ def report(name, err, tol):
 
 
 # ---- attention: both kernels, both softmax forms, ragged tails, residual rows
-for variant in (2, 3):
+for variant in (2, 3, 4):
     for prescaled in (False, True):
         B, H, S, Sq = 2, 2, 333, 300
         D = H * 64

@@ -6,7 +6,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from dit4sr_b200 import ops
 torch.manual_seed(0)
 import math
-def run(B,H,S,Sq,lr,iters,prescaled=False):
+def run(B,H,S,Sq,lr,iters,prescaled=False,variant=0):
     D=H*64
     bad=0
     for it in range(iters):
@@ -15,7 +15,7 @@ def run(B,H,S,Sq,lr,iters,prescaled=False):
         qkv=qkv.bfloat16()
         o=torch.zeros(B,Sq,D,device="cuda",dtype=torch.bfloat16)
         res=torch.randn(B,S,D,device="cuda").bfloat16() if lr else None
-        ops.attention(qkv[...,:D],qkv[...,D:2*D],qkv[...,2*D:],o,H,seq_q=Sq,lr_res=res,lr_rows=lr or (0,0),score_bound=30.0 if prescaled else None)
+        ops.attention(qkv[...,:D],qkv[...,D:2*D],qkv[...,2*D:],o,H,seq_q=Sq,lr_res=res,lr_rows=lr or (0,0),score_bound=30.0 if prescaled else None,variant=variant)
         hd=lambda t: t.float().reshape(B,S,H,64).transpose(1,2)
         ref=torch.nn.functional.scaled_dot_product_attention(hd(qkv[...,:D]),hd(qkv[...,D:2*D]),hd(qkv[...,2*D:]),scale=math.log(2.0) if prescaled else None).transpose(1,2).reshape(B,S,D)[:,:Sq].clone()
         if lr: ref[:,lr[0]:lr[1]]+=res[:,lr[0]:lr[1]].float()
@@ -25,8 +25,9 @@ def run(B,H,S,Sq,lr,iters,prescaled=False):
             nan=torch.isnan(o.float())
             idx=nan.nonzero()
             print(f"  iter {it}: err {e}, nan count {int(nan.sum())}, first {idx[:3].tolist()}, rows {sorted(set(idx[:,1].tolist()))[:8]} batches {sorted(set(idx[:,0].tolist()))[:8]} cols {sorted(set((idx[:,2]//64).tolist()))[:8]}")
-    print(f"prescaled {prescaled} shape {(B,H,S,Sq,lr)}: {bad}/{iters} bad")
-for pre in (False, True):
-    run(8,24,600,333,(100,300),60,pre)
-    run(8,24,2381,2381,(1024,2048),30,pre)
-    run(4,24,700,700,None,40,pre)
+    print(f"variant {variant} prescaled {prescaled} shape {(B,H,S,Sq,lr)}: {bad}/{iters} bad")
+for var in ([int(a) for a in sys.argv[1:]] or [0]):
+    for pre in (False, True):
+        run(8,24,600,333,(100,300),60,pre,var)
+        run(8,24,2381,2381,(1024,2048),30,pre,var)
+        run(4,24,700,700,None,40,pre,var)
