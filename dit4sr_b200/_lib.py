@@ -87,6 +87,7 @@ SYMBOLS = {
     "dit4sr_attn_fwd": (c_int, [C.POINTER(AttnParams), c_vp]),
     "dit4sr_attn_workspace_bytes": (c_i64, []),
     "dit4sr_attn_last_plan": (c_int, [C.POINTER(c_int)]),
+    "dit4sr_attn_plan": (c_int, [C.POINTER(AttnParams), c_int, C.POINTER(c_int)]),
     "dit4sr_patchify": (c_int, [c_vp, c_int, c_vp, c_int, c_int, c_int, c_int, c_vp]),
     "dit4sr_unpatchify": (c_int, [c_vp, c_vp, c_int, c_vp, c_float, c_int, c_int, c_int, c_int, c_vp]),
     "dit4sr_unpatchify_cfg": (c_int, [c_vp, c_vp, c_int, c_vp, c_float, c_float, c_int, c_int, c_int, c_int, c_vp]),

@@ -1142,11 +1142,94 @@ extern "C" int dit4sr_attn_timing_read(long long* host_out /* [12*16] */) {
 }
 #endif
 
+namespace attn {
+
+struct Plan {
+  int variant, split, n_full, items, items_per_bh, bkv, n_kv_tiles, tiles_per_slice;
+};
+
+// Host-side work decomposition and kernel choice of one call on a device with `sms` SMs (no device access).
+static int make_plan(const dit4sr_attn_params* p, int sms, Plan* out) {
+  // Work decomposition.  An item = one (query tile pair | query tile, head, batch); `slots` items run at a time (one per SM
+  // for v2 / v3, two for v4).  When the items do not fill the last wave of slots, the tail items are cut into `split` KV
+  // slices (second launch) whose partial rows a small merge kernel combines (v3 / v4, needs workspace).
+    const int tiles96 = (p->seq_kv + v3::BKV - 1) / v3::BKV;
+  const int pad96 = tiles96 * v3::BKV, pad128 = (p->seq_kv + 127) / 128 * 128;
+  auto plan = [&](int rows_per_item, int slots, bool can_split, int* items_out, int* split_out, int* n_full_out) {
+    const int64_t items64 = (int64_t)((p->seq_q + rows_per_item - 1) / rows_per_item) * p->heads * p->batches;
+    const int items = (int)(items64 < (1ll << 30) ? items64 : (1ll << 30));
+    int split = 1, n_full = items;
+    const int tail = items % slots;
+    double tail_cost = tail > 0 ? 1.0 : 0.0;
+    if (can_split && tail > 0 && p->workspace != nullptr && p->workspace_bytes >= attn::workspace_bytes(sms) &&
+        p->split_kv >= 0) {
+      for (int sdiv = 2; sdiv <= 4; ++sdiv) {
+        if (tiles96 / sdiv < 4) break;                                   // keep slices long enough to amortise a prologue
+        const double c = (double)((tail * sdiv + slots - 1) / slots) / sdiv + 0.03 * (sdiv - 1);
+        if (c < tail_cost - 1e-9) { tail_cost = c; split = sdiv; }
+      }
+      if (p->split_kv > 0 && tiles96 / p->split_kv >= 1) {               // forced (tests / A-B)
+        split = p->split_kv > 4 ? 4 : p->split_kv;
+        tail_cost = (double)((tail * split + slots - 1) / slots) / split;
+      }
+      if (split > 1) n_full = items - tail;
+    }
+    *items_out = items, *split_out = split, *n_full_out = n_full;
+    return (double)(items / slots) + tail_cost;                          // waves of item-lengths
+  };
+  int items2, split2, nf2, items3, split3, nf3, items4, split4, nf4;
+  const double waves2 = plan(2 * BQ, sms, false, &items2, &split2, &nf2);
+  const double waves3 = plan(2 * BQ, sms, true, &items3, &split3, &nf3);
+  const double waves4 = plan(BQ, 2 * sms, true, &items4, &split4, &nf4);
+  DIT4SR_REQUIRE(items4 < (1 << 30), DIT4SR_E_SHAPE, "attn: too many work items");
+  // default kernel: the cheapest under a cost model fitted to kbench timings on B200 (profiles/r02_attn_v4.log):
+  //   time ~ waves x (KV steps + fixed per-CTA overhead in steps) x time per step
+  // v3 shares every K/V tile between two query tiles (0.848 us per 96-key step and SM) but pays ~7.5 steps of prologue /
+  // epilogue per CTA; v4's co-resident CTAs hide most of that (2.3) at 0.888 us per step; v2 steps are 128 keys wide.
+  int variant = p->variant;
+  if (variant == 0) {
+    const int tiles128 = pad128 / 128;
+    const double c2 = waves2 * (tiles128 + 5.5) * 1.130, c3 = waves3 * (tiles96 + 7.5) * 0.848,
+                 c4 = waves4 * (tiles96 + 2.3) * 0.888;
+    variant = c4 <= c3 ? (c4 <= c2 ? 4 : 2) : (c3 <= c2 ? 3 : 2);
+  }
+  const int items = variant == 4 ? items4 : (variant == 3 ? items3 : items2);
+  const int split = variant == 4 ? split4 : (variant == 3 ? split3 : 1);
+  const int n_full = variant == 4 ? nf4 : (variant == 3 ? nf3 : items2);
+  const int q_pairs = (p->seq_q + (variant == 4 ? BQ : 2 * BQ) - 1) / (variant == 4 ? BQ : 2 * BQ);   // items per (head, batch)
+  const int bkv = variant == 2 ? BKV : v3::BKV;
+  out->variant = variant;
+  out->split = split;
+  out->n_full = n_full;
+  out->items = items;
+  out->items_per_bh = q_pairs;
+  out->bkv = bkv;
+  out->n_kv_tiles = (p->seq_kv + bkv - 1) / bkv;
+  out->tiles_per_slice = (out->n_kv_tiles + split - 1) / split;
+  return 0;
+}
+
+}  // namespace attn
+
 static int g_last_plan[4] = {0, 0, 0, 0};   // variant, split, whole items, tail items of the latest dit4sr_attn_fwd call
 
 extern "C" int dit4sr_attn_last_plan(int plan[4]) {
   DIT4SR_REQUIRE(plan != nullptr, DIT4SR_E_BADARG, "attn_last_plan: null argument");
   for (int i = 0; i < 4; ++i) plan[i] = g_last_plan[i];
+  return 0;
+}
+
+extern "C" int dit4sr_attn_plan(const dit4sr_attn_params* p, int sm_count, int plan[6]) {
+  DIT4SR_REQUIRE(p != nullptr && plan != nullptr && sm_count >= 1, DIT4SR_E_BADARG, "attn_plan: bad argument");
+  DIT4SR_REQUIRE(p->batches > 0 && p->heads > 0 && p->seq_q > 0 && p->seq_kv > 0 && p->seq_q <= p->seq_kv &&
+                     p->split_kv <= 4 && (p->variant == 0 || (p->variant >= 2 && p->variant <= 4)),
+                 DIT4SR_E_BADARG, "attn_plan: bad sizes");
+  attn::Plan pl;
+  // (the workspace pointer is only tested against NULL and workspace_bytes against the need for `sm_count` SMs)
+  int rc = attn::make_plan(p, sm_count, &pl);
+  if (rc != 0) return rc;
+  plan[0] = pl.variant, plan[1] = pl.split, plan[2] = pl.n_full, plan[3] = pl.items - pl.n_full, plan[4] = pl.n_kv_tiles,
+  plan[5] = pl.tiles_per_slice;
   return 0;
 }
 
@@ -1196,55 +1279,10 @@ extern "C" int dit4sr_attn_fwd(const dit4sr_attn_params* p, void* stream_) {
   int rc = dit4sr_check_device();
   if (rc != 0) return rc;
 
-  // Work decomposition.  An item = one (query tile pair | query tile, head, batch); `slots` items run at a time (one per SM
-  // for v2 / v3, two for v4).  When the items do not fill the last wave of slots, the tail items are cut into `split` KV
-  // slices (second launch) whose partial rows a small merge kernel combines (v3 / v4, needs workspace).
-  const int sms = host::sm_count();
-  const int tiles96 = (p->seq_kv + v3::BKV - 1) / v3::BKV;
-  const int pad96 = tiles96 * v3::BKV, pad128 = (p->seq_kv + 127) / 128 * 128;
-  auto plan = [&](int rows_per_item, int slots, bool can_split, int* items_out, int* split_out, int* n_full_out) {
-    const int64_t items64 = (int64_t)((p->seq_q + rows_per_item - 1) / rows_per_item) * p->heads * p->batches;
-    const int items = (int)(items64 < (1ll << 30) ? items64 : (1ll << 30));
-    int split = 1, n_full = items;
-    const int tail = items % slots;
-    double tail_cost = tail > 0 ? 1.0 : 0.0;
-    if (can_split && tail > 0 && p->workspace != nullptr && p->workspace_bytes >= attn::workspace_bytes(sms) &&
-        p->split_kv >= 0) {
-      for (int sdiv = 2; sdiv <= 4; ++sdiv) {
-        if (tiles96 / sdiv < 4) break;                                   // keep slices long enough to amortise a prologue
-        const double c = (double)((tail * sdiv + slots - 1) / slots) / sdiv + 0.03 * (sdiv - 1);
-        if (c < tail_cost - 1e-9) { tail_cost = c; split = sdiv; }
-      }
-      if (p->split_kv > 0 && tiles96 / p->split_kv >= 1) {               // forced (tests / A-B)
-        split = p->split_kv > 4 ? 4 : p->split_kv;
-        tail_cost = (double)((tail * split + slots - 1) / slots) / split;
-      }
-      if (split > 1) n_full = items - tail;
-    }
-    *items_out = items, *split_out = split, *n_full_out = n_full;
-    return (double)(items / slots) + tail_cost;                          // waves of item-lengths
-  };
-  int items2, split2, nf2, items3, split3, nf3, items4, split4, nf4;
-  const double waves2 = plan(2 * BQ, sms, false, &items2, &split2, &nf2);
-  const double waves3 = plan(2 * BQ, sms, true, &items3, &split3, &nf3);
-  const double waves4 = plan(BQ, 2 * sms, true, &items4, &split4, &nf4);
-  DIT4SR_REQUIRE(items4 < (1 << 30), DIT4SR_E_SHAPE, "attn: too many work items");
-  // default kernel: the cheapest under a cost model fitted to kbench timings on B200 (profiles/r02_attn_v4.log):
-  //   time ~ waves x (KV steps + fixed per-CTA overhead in steps) x time per step
-  // v3 shares every K/V tile between two query tiles (0.848 us per 96-key step and SM) but pays ~7.5 steps of prologue /
-  // epilogue per CTA; v4's co-resident CTAs hide most of that (2.3) at 0.888 us per step; v2 steps are 128 keys wide.
-  int variant = p->variant;
-  if (variant == 0) {
-    const int tiles128 = pad128 / 128;
-    const double c2 = waves2 * (tiles128 + 5.5) * 1.130, c3 = waves3 * (tiles96 + 7.5) * 0.848,
-                 c4 = waves4 * (tiles96 + 2.3) * 0.888;
-    variant = c4 <= c3 ? (c4 <= c2 ? 4 : 2) : (c3 <= c2 ? 3 : 2);
-  }
-  const int items = variant == 4 ? items4 : (variant == 3 ? items3 : items2);
-  const int split = variant == 4 ? split4 : (variant == 3 ? split3 : 1);
-  const int n_full = variant == 4 ? nf4 : (variant == 3 ? nf3 : items2);
-  const int q_pairs = (p->seq_q + (variant == 4 ? BQ : 2 * BQ) - 1) / (variant == 4 ? BQ : 2 * BQ);   // items per (head, batch)
-  const int bkv = variant == 2 ? BKV : v3::BKV;
+  attn::Plan plan;
+  if ((rc = attn::make_plan(p, host::sm_count(), &plan)) != 0) return rc;
+  const int variant = plan.variant, split = plan.split, n_full = plan.n_full, items = plan.items, q_pairs = plan.items_per_bh,
+            bkv = plan.bkv;
   CUtensorMap tmQ, tmK, tmV;
   const uint64_t dims[3] = {(uint64_t)p->heads * DH, (uint64_t)p->seq_kv, (uint64_t)p->batches};
   const uint64_t strides[2] = {(uint64_t)p->qkv_row_stride * 2,
@@ -1265,13 +1303,13 @@ extern "C" int dit4sr_attn_fwd(const dit4sr_attn_params* p, void* stream_) {
   a.lr_row_end = p->lr_row_end;
   a.seq_q = p->seq_q;
   a.seq_kv = p->seq_kv;
-  a.n_kv_tiles = (p->seq_kv + bkv - 1) / bkv;
+  a.n_kv_tiles = plan.n_kv_tiles;
   a.scale_log2 = p->scale * 1.4426950408889634f;
   a.q_pairs = q_pairs;
   a.heads = p->heads;
   a.n_full = n_full;
   a.split = split;
-  a.tiles_per_slice = (a.n_kv_tiles + split - 1) / split;
+  a.tiles_per_slice = plan.tiles_per_slice;
   a.part = nullptr;
   if (split > 1) a.part = reinterpret_cast<float*>(p->workspace);
   a.sp_world = 0;

@@ -206,6 +206,10 @@ typedef struct {
 } dit4sr_attn_params;
 int dit4sr_attn_fwd(const dit4sr_attn_params* p, void* stream);
 int64_t dit4sr_attn_workspace_bytes(void);   /* for the current device (148 SMs assumed when there is none) */
+/* Host-only query (no device; pointers are only compared with NULL): the work decomposition dit4sr_attn_fwd would use on a
+ * GPU with sm_count SMs: plan = {kernel variant, KV slices per tail item, whole items, tail items, KV tiles, KV tiles per
+ * slice}.  workspace_bytes is compared with 4 * 256 * 68 * 4 bytes per SM. */
+int dit4sr_attn_plan(const dit4sr_attn_params* p, int sm_count, int plan[6]);
 /* Diagnostics: {kernel variant, KV slices per tail item, whole items, tail items} the latest dit4sr_attn_fwd call of this
  * process chose (host-side bookkeeping, not thread-safe). */
 int dit4sr_attn_last_plan(int plan[4]);

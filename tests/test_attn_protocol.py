@@ -47,3 +47,36 @@ def test_each_ingredient_removes_one_assumption():
         assert ok, msg
     assert not check(2, 2, "six_barriers_only", mma_keeps_up=False)[0]
     assert not check(2, 2, "o_done_always_only", slots_in_order=False)[0]
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# v3 / v4 (double-buffered score tiles per query tile): tools/attn_protocol_check_v4.py
+def _check_v4(*a, **k):
+    import importlib.util
+    import os
+    spec = importlib.util.spec_from_file_location(
+        "attn_protocol_check_v4", os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tools",
+                                               "attn_protocol_check_v4.py"))
+    m = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(m)
+    return m.check(*a, **k)
+
+
+def test_v4_protocol_is_safe_for_every_interleaving():
+    """s_full / p_full per score buffer, o_done awaited only by the online form's rescale, the epilogue on o_final: no
+    premature pass, no hazard, no deadlock for any interleaving, with and without the rescale path, 2 and 3 softmax warps."""
+    for n_tiles in range(1, 7):
+        for warps in (2, 3):
+            for online in (False, True):
+                ok, msg, _ = _check_v4(n_tiles, warps, "o_final", online)
+                assert ok, (n_tiles, warps, online, msg)
+
+
+def test_v3_first_epilogue_wait_was_a_premature_pass():
+    """What v3 first shipped (epilogue waits on o_done with the parity of the last phase): a warp may get there while P V of
+    the step before is still outstanding, the parity wait passes two phases early and O is read too soon - the model check
+    finds it for every tile count >= 2 (on the GPU: 3 of 36 split-KV runs off by 5e-3..8e-3)."""
+    assert _check_v4(1, 2, "o_done_parity")[0]
+    for n_tiles in range(2, 6):
+        ok, msg, _ = _check_v4(n_tiles, 2, "o_done_parity")
+        assert not ok and "premature pass" in msg and "epilogue" in msg

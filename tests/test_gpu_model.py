@@ -394,3 +394,24 @@ def test_feature_outputs_nchw_fp32_inside_the_graph():
     got = dit4sr_b200.unpatchify_features(bare, "hqlq_feat")[0]
     assert torch.equal(got, rearrange(feats[0]["extract_feat"].float(), "b (N H W) (pH pW d) -> b (N d) (H pH) (W pW)",
                                       N=2, H=32, W=32, pH=2, pW=2))
+
+
+def test_fp16_module_runs_in_bf16_within_the_stated_tolerance():
+    """Every shipped reference config runs `mixed_precision: fp16` (run_configs/val/*.yaml).  This product has no fp16
+    arithmetic: an fp16 module is computed with bf16 tensor-core operands and fp32 accumulation / residual streams, fp16
+    inputs are converted at the boundary and the output is returned in fp16.  Stated tolerance: the velocity stays within
+    the north star's bf16 gate (1e-2) of the fp32 oracle, and is no further from it than the reference's own fp16 run
+    (the oracle evaluated in fp16 on the GPU) plus that gate."""
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.backends.cudnn.allow_tf32 = False
+    cfg = O.sd35_medium_config(num_layers=4, dual_attention_layers=(0, 1), pos_embed_max_size=96)
+    sd = O.init_state_dict(cfg, seed=0)
+    inputs = O.make_inputs(cfg, 1, 64, 64, 333, seed=1, timestep=600.0)
+    ref32 = _oracle_gpu(sd, cfg, inputs, torch.float32)
+    ref16 = _oracle_gpu(sd, cfg, inputs, torch.float16)
+    m = build(cfg, sd, dtype=torch.float16)
+    y = run(m, inputs, dtype=torch.float16)
+    e_ours, e_ref16 = rel(y, ref32), rel(ref16, ref32)
+    print(f"fp16 module: cuda(bf16 arithmetic) vs fp32 {e_ours:.3e}; reference fp16 run vs fp32 {e_ref16:.3e}")
+    assert e_ours <= VEL_TOL
+    assert rel(y, ref16) <= VEL_TOL + e_ref16
