@@ -238,6 +238,8 @@ attn_fwd2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
   __syncthreads();
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
+  ptx::pdl_wait();                 // (programmatic dependent launch: the prologue ran under the previous kernel's tail)
+  ptx::pdl_launch_dependents();
 
   if (warp < 4) {
   if constexpr (XREG) asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
@@ -563,6 +565,8 @@ attn_fwd3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
   __syncthreads();
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
+  ptx::pdl_wait();                 // (programmatic dependent launch: the prologue ran under the previous kernel's tail)
+  ptx::pdl_launch_dependents();
 
   if (warp < 4) {
     asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
@@ -933,6 +937,8 @@ attn_fwd4_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
   __syncthreads();
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
+  ptx::pdl_wait();                 // (programmatic dependent launch: the prologue ran under the previous kernel's tail)
+  ptx::pdl_launch_dependents();
 
   if (warp < 4) {
     asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
@@ -1349,8 +1355,8 @@ extern "C" int dit4sr_attn_fwd(const dit4sr_attn_params* p, void* stream_) {
     DIT4SR_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
   g_last_plan[0] = variant, g_last_plan[1] = split, g_last_plan[2] = n_full, g_last_plan[3] = items - n_full;
   dim3 grid(q_pairs, p->heads, p->batches);
-  fn<<<grid, threads, smem, stream>>>(tmQ, tmK, tmV, a);   // (v3 / v4: items >= n_full exit at once)
-  DIT4SR_CUDA(cudaGetLastError());
+  // (v3 / v4: items >= n_full exit at once; nothing to launch when every item is a tail item)
+  if (n_full > 0) DIT4SR_CUDA(host::launch_pdl(fn, grid, dim3(threads), (size_t)smem, stream, tmQ, tmK, tmV, a));
   if (split > 1) {   // the tail items again, as KV slices, then the merge
     const KernelFn fs = sliced[variant - 3][mi][po];
     if (host::first_use_on_device(&configured_s[variant - 3][mi][po]))

@@ -54,6 +54,10 @@ dwconv3x3_kernel(const __grid_constant__ CUtensorMap tmLR, const Args a) {
   if (tid == 0) {
     ptx::mbar_init(&bar, 1);
     ptx::fence_barrier_init();
+  }
+  ptx::pdl_wait();                 // (programmatic dependent launch: everything below reads the previous kernel's output)
+  ptx::pdl_launch_dependents();
+  if (tid == 0) {
     ptx::mbar_expect_tx(&bar, TILE_BYTES);
     // negative / past-the-end coordinates read as zero: the conv's zero padding
     ptx::tma_load_4d(tile, &tmLR, &bar, c_base, x0 - 1, y0 - 1 + a.lr_row_offset, b);
@@ -182,7 +186,6 @@ extern "C" int dit4sr_dwconv3x3_add(const dit4sr_dwconv3x3_params* p, void* stre
   a.x_tiles = (gw + TX - 1) / TX;
   a.y_tiles = (p->grid + TY - 1) / TY;
   dim3 grid((p->channels + CH - 1) / CH, a.x_tiles * a.y_tiles, p->batches);
-  dwconv3x3_kernel<<<grid, THREADS, 0, stream>>>(tm, a);
-  DIT4SR_CUDA(cudaGetLastError());
+  DIT4SR_CUDA(host::launch_pdl(dwconv3x3_kernel, grid, dim3(THREADS), (size_t)0, stream, tm, a));
   return 0;
 }

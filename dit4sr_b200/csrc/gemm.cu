@@ -178,6 +178,10 @@ gemm_kernel(const __grid_constant__ Maps maps, const __grid_constant__ Group grp
   __syncthreads();
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
+  // programmatic dependent launch: the prologue above ran under the previous kernel's tail; nothing of global memory has
+  // been touched yet.  From here on the previous kernels are complete, and the next kernel's CTAs may be scheduled.
+  ptx::pdl_wait();
+  ptx::pdl_launch_dependents();
 
   const int num_tiles = grp.num_tiles;
 
@@ -547,8 +551,7 @@ static int launch(const Maps& maps, const Group& g, cudaStream_t stream) {
     DIT4SR_CUDA(cudaFuncSetAttribute(gemm_kernel<EPI, RED>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
   int grid = host::sm_count();
   if (grid > g.num_tiles) grid = g.num_tiles;
-  gemm_kernel<EPI, RED><<<grid, NUM_THREADS, SMEM_BYTES, stream>>>(maps, g);
-  DIT4SR_CUDA(cudaGetLastError());
+  DIT4SR_CUDA(host::launch_pdl(gemm_kernel<EPI, RED>, dim3(grid), dim3(NUM_THREADS), SMEM_BYTES, stream, maps, g));
   return 0;
 }
 

@@ -1,4 +1,5 @@
 #include "host_util.h"
+#include <stdlib.h>
 
 #include <mutex>
 #include <string.h>
@@ -88,6 +89,15 @@ int sm_count() {
   cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
   if (dev >= 0 && dev < 64) cache[dev] = n;
   return n;
+}
+
+bool pdl_enabled() {
+  static int on = -1;
+  if (on < 0) {
+    const char* e = getenv("DIT4SR_PDL");
+    on = (e != nullptr && e[0] == '1') ? 1 : 0;   // opt-in: measured slightly slower at C2 (43.3 vs 43.0 ms), see DESIGN.md
+  }
+  return on != 0;
 }
 
 bool first_use_on_device(unsigned long long* mask) {

@@ -84,6 +84,10 @@ ln_modulate_tma_kernel(const dit4sr_ln_modulate_params p) {
   if (lane == 0) {
     for (int s = 0; s < LN_STAGES; ++s) ptx::mbar_init(&bars[s], 1);
     ptx::fence_barrier_init();
+  }
+  ptx::pdl_wait();                 // (programmatic dependent launch: barrier set-up ran under the previous kernel's tail)
+  ptx::pdl_launch_dependents();
+  if (lane == 0) {
     for (int s = 0; s < LN_STAGES; ++s) {
       const int64_t rid = first + s * nwarps;
       if (rid < total) {
@@ -272,9 +276,10 @@ static int launch(const dit4sr_ln_modulate_params& p, cudaStream_t stream) {
       unsigned grid = (unsigned)((total + LN_WARPS - 1) / LN_WARPS);
       const unsigned sms = (unsigned)host::sm_count();
       if (grid > sms) grid = sms;
-      if (p.out2 != nullptr) ln_modulate_tma_kernel<NV / 2, true><<<grid, LN_WARPS * 32, SMEM, stream>>>(p);
-      else ln_modulate_tma_kernel<NV / 2, false><<<grid, LN_WARPS * 32, SMEM, stream>>>(p);
-      DIT4SR_CUDA(cudaGetLastError());
+      if (p.out2 != nullptr)
+        DIT4SR_CUDA(host::launch_pdl(ln_modulate_tma_kernel<NV / 2, true>, dim3(grid), dim3(LN_WARPS * 32), (size_t)SMEM, stream, p));
+      else
+        DIT4SR_CUDA(host::launch_pdl(ln_modulate_tma_kernel<NV / 2, false>, dim3(grid), dim3(LN_WARPS * 32), (size_t)SMEM, stream, p));
       return 0;
     }
   }
