@@ -62,6 +62,7 @@ struct Group {
   int num_tiles;      // work items of the launch = split_begin + (tiles - split_begin) * split
   int split_begin;    // first tile (in schedule order) that is cut into column slices
   int split;          // 1 (no splitting), 2 or 4 slices per 256-column tile
+  int pair;           // 1: CTA pairs (cta_group::2) work on 256-row x 256-column tiles, m_tiles count 256-row tiles
   Problem p[MAX_PROBLEMS];
   void* sp_peer[DIT4SR_SP_MAX_RANKS];   // peer-mapped [B, rows_dst, 3, D/world] buffers (problems with sp_world > 0)
 };
@@ -69,8 +70,9 @@ struct Group {
 struct Maps {
   CUtensorMap a[MAX_PROBLEMS];
   CUtensorMap w[MAX_PROBLEMS];
-  CUtensorMap ws[MAX_PROBLEMS];   // W with a BN/split-row box (only valid when split > 1)
+  CUtensorMap ws[MAX_PROBLEMS];   // W with a BN/split-row box (split > 1), or a BN/2-row box (pair: each CTA loads half of W)
   CUtensorMap c[MAX_PROBLEMS];    // fp32 C as (N, rows, batches) with a 32x32 box (only valid when c_reduce)
+  CUtensorMap wt[MAX_PROBLEMS];   // pair + split > 1: W with a BN/(2 split)-row box (half of a tail slice per CTA)
 };
 
 struct TileCoord {
@@ -137,21 +139,37 @@ __device__ __forceinline__ void store_f32x32(float* dst, const float* f) {
 
 // RED (GATE_RESID only): every problem of the launch is an in-place gated residual and the epilogue adds into C with TMA
 // reduce-adds (Problem::c_reduce); a separate instance so that neither epilogue pays for the other's registers.
-template <int EPI, bool RED = false>
+// PAIR: two CTAs of a cluster (one TPC) run ONE 256-row x 256-column tile with tcgen05.mma.cta_group::2: each CTA
+// loads its own 128 rows of A and HALF of the W tile, the leader (cluster rank 0) issues M = 256 MMAs that read A from
+// each CTA's shared memory and W from both, and each CTA's TMEM receives the accumulators of its 128 rows.  Per SM the
+// shared-memory operand traffic falls from 96 to 64 bytes per clock and the L2 -> SM traffic of W is halved.
+//   both CTAs' TMA loads (cta_group::2 form) complete on the LEADER's full_bar, which expects the bytes of the pair;
+//   the leader's commits are multicast to both CTAs' empty_bar / tfull_bar;  both CTAs' epilogue warps arrive on the
+//   leader's tempty_bar (8 arrivals, the non-leader's through remote mbarrier arrives).
+template <int EPI, bool RED = false, bool PAIR = false>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 gemm_kernel(const __grid_constant__ Maps maps, const __grid_constant__ Group grp) {
   extern __shared__ uint8_t smem_raw[];
   // 1024-byte alignment for SWIZZLE_128B tiles
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  // operand ring: 4 stages of (A 16 KB + W 32 KB), or for CTA pairs 6 stages of (A 16 KB + half of W 16 KB) - the same
+  // 192 KB; the pair needs the deeper ring because a stage is only consumable after the peer's relay hop
+  constexpr int NST = PAIR ? 6 : STAGES;
+  constexpr int STG = PAIR ? (A_BYTES + B_BYTES / 2) : STAGE_BYTES;
+  static_assert(NST * STG == STAGES * STAGE_BYTES, "ring size");
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES + 4 * EPI_STAGE_BYTES);
-  uint64_t* full_bar = bars;                       // [STAGES]
-  uint64_t* empty_bar = bars + STAGES;             // [STAGES]
-  uint64_t* tfull_bar = bars + 2 * STAGES;         // [ACC_STAGES]
+  uint64_t* full_bar = bars;                       // [NST]
+  uint64_t* empty_bar = bars + NST;                // [NST]
+  uint64_t* tfull_bar = bars + 2 * NST;            // [ACC_STAGES]
   uint64_t* tempty_bar = tfull_bar + ACC_STAGES;   // [ACC_STAGES]
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tempty_bar + ACC_STAGES);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
+  const int rank = PAIR ? (int)ptx::cluster_ctarank() : 0;          // position in the CTA pair
+  const int cta_first = PAIR ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
+  const int cta_stride = PAIR ? (int)(gridDim.x >> 1) : (int)gridDim.x;
+  constexpr int BMT = PAIR ? 2 * BM : BM;                            // rows of a work item
 
   if (warp == 0 && lane == 0) {
     for (int i = 0; i < grp.num_problems; ++i) {
@@ -160,22 +178,28 @@ gemm_kernel(const __grid_constant__ Maps maps, const __grid_constant__ Group grp
     }
   }
   if (warp == 1 && lane == 0) {
-    for (int i = 0; i < STAGES; ++i) {
+    for (int i = 0; i < NST; ++i) {
       ptx::mbar_init(&full_bar[i], 1);
       ptx::mbar_init(&empty_bar[i], 1);
     }
     for (int i = 0; i < ACC_STAGES; ++i) {
       ptx::mbar_init(&tfull_bar[i], 1);
-      ptx::mbar_init(&tempty_bar[i], 4);  // one arrive per epilogue warp
+      ptx::mbar_init(&tempty_bar[i], PAIR ? 8 : 4);  // one arrive per epilogue warp (of both CTAs)
     }
     ptx::fence_barrier_init();
   }
   if (warp == 2) {
-    ptx::tmem_alloc(tmem_ptr, TMEM_COLS);
-    ptx::tmem_relinquish();
+    if constexpr (PAIR) {
+      ptx::tmem_alloc2(tmem_ptr, TMEM_COLS);
+      ptx::tmem_relinquish2();
+    } else {
+      ptx::tmem_alloc(tmem_ptr, TMEM_COLS);
+      ptx::tmem_relinquish();
+    }
   }
   ptx::tc_fence_before();
   __syncthreads();
+  if constexpr (PAIR) ptx::cluster_sync();   // the peer's barriers exist before anything arrives on them
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
   // programmatic dependent launch: the prologue above ran under the previous kernel's tail; nothing of global memory has
@@ -190,56 +214,72 @@ gemm_kernel(const __grid_constant__ Maps maps, const __grid_constant__ Group grp
       // ===================== TMA producer =====================
       int stage = 0;
       uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      for (int tile = cta_first; tile < num_tiles; tile += cta_stride) {
         const TileCoord tc = decode_tile(grp, tile);
         const int k_blocks = grp.p[tc.pi].k_blocks;
         const CUtensorMap* ma = &maps.a[tc.pi];
-        const CUtensorMap* mw = tc.bn == BN ? &maps.w[tc.pi] : &maps.ws[tc.pi];
-        const uint32_t tx_bytes = A_BYTES + tc.bn * BK * 2;
+        const CUtensorMap* mw = PAIR ? (tc.bn == BN ? &maps.ws[tc.pi] : &maps.wt[tc.pi])
+                                     : (tc.bn == BN ? &maps.w[tc.pi] : &maps.ws[tc.pi]);
+        const int w_rows = PAIR ? tc.bn / 2 : tc.bn;                  // W rows this CTA loads
+        const uint32_t tx_bytes = A_BYTES + w_rows * BK * 2;
         for (int kb = 0; kb < k_blocks; ++kb) {
           ptx::mbar_wait(&empty_bar[stage], phase ^ 1);
-          uint8_t* sa = smem + stage * STAGE_BYTES;
+          uint8_t* sa = smem + stage * STG;
           uint8_t* sb = sa + A_BYTES;
-          ptx::mbar_expect_tx(&full_bar[stage], tx_bytes);
-          ptx::tma_load_3d(sa, ma, &full_bar[stage], kb * BK, tc.m_tile * BM, tc.b);
-          ptx::tma_load_2d(sb, mw, &full_bar[stage], kb * BK, tc.col0);
-          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+          if constexpr (PAIR) {
+            // both CTAs' loads complete on the LEADER's full barrier, which expects the bytes of the pair
+            if (rank == 0) ptx::mbar_expect_tx(&full_bar[stage], 2 * tx_bytes);
+            const uint32_t lead_bar = ptx::mapa_u32(&full_bar[stage], 0);
+            ptx::tma_load_3d_2sm(sa, ma, lead_bar, kb * BK, tc.m_tile * BMT + rank * BM, tc.b);
+            ptx::tma_load_2d_2sm(sb, mw, lead_bar, kb * BK, tc.col0 + rank * w_rows);
+          } else {
+            ptx::mbar_expect_tx(&full_bar[stage], tx_bytes);
+            ptx::tma_load_3d(sa, ma, &full_bar[stage], kb * BK, tc.m_tile * BM, tc.b);
+            ptx::tma_load_2d(sb, mw, &full_bar[stage], kb * BK, tc.col0);
+          }
+          if (++stage == NST) { stage = 0; phase ^= 1; }
         }
       }
     }
-  } else if (warp == 1) {
-    // ===================== MMA issuer =====================
+  } else if (warp == 1 && rank == 0) {
+    // ===================== MMA issuer (PAIR: the leader CTA only) =====================
     // The whole warp runs the loop (warp-uniform barrier addresses / descriptors); one elected lane issues.
     const uint64_t desc_base = ptx::make_sdesc_sw128(ptx::smem_u32(smem));
     int stage = 0;
     uint32_t phase = 0;
     int it = 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+    for (int tile = cta_first; tile < num_tiles; tile += cta_stride, ++it) {
       const TileCoord tc = decode_tile(grp, tile);
       const int k_blocks = grp.p[tc.pi].k_blocks;
       const int as = it & 1;
       const uint32_t aphase = (it >> 1) & 1;
-      const uint32_t idesc = ptx::make_idesc_bf16(BM, tc.bn, 0, 0);   // N = 256, or 128 / 64 for a tail slice
+      const uint32_t idesc = ptx::make_idesc_bf16(BMT, tc.bn, 0, 0);   // N = 256, or 128 / 64 for a tail slice
       ptx::mbar_wait(&tempty_bar[as], aphase ^ 1);
       ptx::tc_fence_after();
       const uint32_t d_tmem = tmem_base + as * BN;
       for (int kb = 0; kb < k_blocks; ++kb) {
         ptx::mbar_wait(&full_bar[stage], phase);
         ptx::tc_fence_after();
-        const uint64_t adesc = desc_base + (uint64_t)(stage * (STAGE_BYTES >> 4));
+        const uint64_t adesc = desc_base + (uint64_t)(stage * (STG >> 4));
         const uint64_t bdesc = adesc + (uint64_t)(A_BYTES >> 4);
         if (ptx::elect_one()) {
 #pragma unroll
           for (int k = 0; k < BK / 16; ++k) {
             // advance 16 bf16 = 32 bytes along K inside the 128B swizzle atom: +2 in the (addr>>4) field
-            ptx::mma_ss(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0);
+            if constexpr (PAIR) ptx::mma_ss2(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0);
+            else ptx::mma_ss(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0);
           }
-          ptx::tc_commit(&empty_bar[stage]);  // frees the smem slot when these MMAs have read it
+          // frees the smem slot (of both CTAs) when these MMAs have read it
+          if constexpr (PAIR) ptx::tc_commit_mc(&empty_bar[stage], 3);
+          else ptx::tc_commit(&empty_bar[stage]);
         }
         __syncwarp();
-        if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        if (++stage == NST) { stage = 0; phase ^= 1; }
       }
-      if (ptx::elect_one()) ptx::tc_commit(&tfull_bar[as]);  // accumulator complete
+      if (ptx::elect_one()) {   // accumulator complete
+        if constexpr (PAIR) ptx::tc_commit_mc(&tfull_bar[as], 3);
+        else ptx::tc_commit(&tfull_bar[as]);
+      }
       __syncwarp();
     }
   } else if (warp >= 4) {
@@ -251,13 +291,13 @@ gemm_kernel(const __grid_constant__ Maps maps, const __grid_constant__ Group grp
     uint8_t* stg = smem + STAGES * STAGE_BYTES + q * EPI_STAGE_BYTES;
     const int sub = lane >> 3, seg = lane & 7;
     int it = 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+    for (int tile = cta_first; tile < num_tiles; tile += cta_stride, ++it) {
       const TileCoord tc = decode_tile(grp, tile);
       const Problem& P = grp.p[tc.pi];
       const int as = it & 1;
       const uint32_t aphase = (it >> 1) & 1;
 
-      const int row_base = tc.m_tile * BM + q * 32;       // first row of this warp
+      const int row_base = tc.m_tile * BMT + rank * BM + q * 32;       // first row of this warp
       const uint32_t taddr = tmem_base + as * BN + ((uint32_t)(q * 32) << 16);
       const int n_base = tc.col0;
       const int n_valid = min(tc.bn, P.N - n_base);       // multiple of 32
@@ -440,7 +480,10 @@ gemm_kernel(const __grid_constant__ Maps maps, const __grid_constant__ Group grp
             }
             ptx::tc_fence_before();
             __syncwarp();
-            if (lane == 0) ptx::mbar_arrive(&tempty_bar[as]);
+            if (lane == 0) {
+              if (PAIR && rank == 1) ptx::mbar_arrive_remote(&tempty_bar[as], 0);
+              else ptx::mbar_arrive(&tempty_bar[as]);
+            }
             continue;
           }
         }
@@ -448,11 +491,11 @@ gemm_kernel(const __grid_constant__ Maps maps, const __grid_constant__ Group grp
         // The residual rows are the only cold global reads of this epilogue and each warp has just one 32-column pass
         // of them in flight, so pull the NEXT tile's residual rows into L2 now (a whole tile ahead of their use).
         if constexpr (EPI == DIT4SR_EPI_GATE_RESID) {
-          const int nt = tile + gridDim.x;
+          const int nt = tile + cta_stride;
           if (nt < num_tiles) {
             const TileCoord nc = decode_tile(grp, nt);
             const Problem& NP = grp.p[nc.pi];
-            const int nr = nc.m_tile * BM + q * 32 + lane;
+            const int nr = nc.m_tile * BMT + rank * BM + q * 32 + lane;
             if (nr < NP.rows) {
               const float* np = NP.resid + (int64_t)nc.b * NP.r_batch_stride + (int64_t)nr * NP.ldr + nc.col0;
               const int ncols = min(nc.bn, NP.N - nc.col0);
@@ -527,10 +570,13 @@ gemm_kernel(const __grid_constant__ Maps maps, const __grid_constant__ Group grp
           }
         }
       }
-      // release the accumulator stage
+      // release the accumulator stage (PAIR: the leader's issuer counts the epilogue warps of both CTAs)
       ptx::tc_fence_before();
       __syncwarp();
-      if (lane == 0) ptx::mbar_arrive(&tempty_bar[as]);
+      if (lane == 0) {
+        if (PAIR && rank == 1) ptx::mbar_arrive_remote(&tempty_bar[as], 0);
+        else ptx::mbar_arrive(&tempty_bar[as]);
+      }
     }
   }
 
@@ -538,14 +584,37 @@ gemm_kernel(const __grid_constant__ Maps maps, const __grid_constant__ Group grp
   __syncwarp();
   ptx::tc_fence_before();
   __syncthreads();
+  if constexpr (PAIR) ptx::cluster_sync();   // nobody leaves while the peer may still read its shared memory / barriers
   if (warp == 2) {
     ptx::tc_fence_after();
-    ptx::tmem_dealloc(tmem_base, TMEM_COLS);
+    if constexpr (PAIR) ptx::tmem_dealloc2(tmem_base, TMEM_COLS);
+    else ptx::tmem_dealloc(tmem_base, TMEM_COLS);
   }
 }
 
 template <int EPI, bool RED = false>
 static int launch(const Maps& maps, const Group& g, cudaStream_t stream) {
+  if (g.pair) {   // clusters of two CTAs (one TPC each), one 256x256 tile per pair at a time
+    static unsigned long long configured2 = 0;
+    if (host::first_use_on_device(&configured2))
+      DIT4SR_CUDA(cudaFuncSetAttribute(gemm_kernel<EPI, RED, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+    int pairs = host::sm_count() / 2;
+    if (pairs > g.num_tiles) pairs = g.num_tiles;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(2 * pairs);
+    cfg.blockDim = dim3(NUM_THREADS);
+    cfg.dynamicSmemBytes = SMEM_BYTES;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    DIT4SR_CUDA(cudaLaunchKernelEx(&cfg, gemm_kernel<EPI, RED, true>, maps, g));
+    return 0;
+  }
   static unsigned long long configured = 0;   // per (instance, device)
   if (host::first_use_on_device(&configured))
     DIT4SR_CUDA(cudaFuncSetAttribute(gemm_kernel<EPI, RED>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
@@ -587,8 +656,11 @@ static int check_problem(const dit4sr_gemm_params* p, int epilogue) {
 // Tile schedule of a group: pure host arithmetic shared by the launch path and dit4sr_gemm_schedule (so that the
 // schedule the CPU tests enumerate is the one the kernel walks).  Fills the shape fields of g.p[0..count) and the
 // work-item counts; does not touch pointers.
-static void plan_tiles(const dit4sr_gemm_params* probs, int count, int sms, bool tail_split, Group& g) {
+static void plan_tiles(const dit4sr_gemm_params* probs, int count, int sms, bool tail_split, Group& g, bool pair = false) {
   g.num_problems = count;
+  g.pair = pair ? 1 : 0;
+  const int bm = pair ? 2 * BM : BM;
+  if (pair) sms /= 2;   // work items are handed to CTA pairs
   int tiles = 0;
   bool whole = true;
   for (int i = 0; i < count; ++i) {
@@ -596,7 +668,7 @@ static void plan_tiles(const dit4sr_gemm_params* probs, int count, int sms, bool
     Problem& P = g.p[i];
     P.rows = p->rows;
     P.N = p->N;
-    P.m_tiles = (p->rows + BM - 1) / BM;
+    P.m_tiles = (p->rows + bm - 1) / bm;
     P.n_tiles = (p->N + BN - 1) / BN;
     P.k_blocks = (p->K + BK - 1) / BK;
     P.tile_begin = tiles;
@@ -616,6 +688,12 @@ static void plan_tiles(const dit4sr_gemm_params* probs, int count, int sms, bool
       g.num_tiles = g.split_begin + rem * split;
     }
   }
+}
+
+static bool pair_enabled() {   // DIT4SR_GEMM_PAIR=0: never use CTA pairs (cta_group::2)
+  static int enabled = -1;
+  if (enabled < 0) { const char* e = getenv("DIT4SR_GEMM_PAIR"); enabled = (e != nullptr && e[0] == '0') ? 0 : 1; }
+  return enabled != 0;
 }
 
 static bool tail_split_enabled() {
@@ -641,7 +719,17 @@ extern "C" int dit4sr_gemm_bf16_grouped(const dit4sr_gemm_params* probs, int cou
 
   Maps maps;
   Group g;
-  plan_tiles(probs, count, host::sm_count(), tail_split_enabled(), g);
+  // CTA pairs (cta_group::2): every problem a whole number of 256-column tiles and enough 256-row tiles to go round
+  bool pair = pair_enabled() && host::sm_count() % 2 == 0;
+  {
+    int64_t pair_tiles = 0;
+    for (int i = 0; i < count; ++i) {
+      pair = pair && probs[i].N % BN == 0;
+      pair_tiles += (int64_t)((probs[i].rows + 2 * BM - 1) / (2 * BM)) * (probs[i].N / BN) * probs[i].batches;
+    }
+    pair = pair && pair_tiles >= host::sm_count() / 2;
+  }
+  plan_tiles(probs, count, host::sm_count(), tail_split_enabled(), g, pair);
   bool have_sp = false;
   for (int r = 0; r < DIT4SR_SP_MAX_RANKS; ++r) g.sp_peer[r] = nullptr;
   for (int i = 0; i < count; ++i) {
@@ -660,11 +748,18 @@ extern "C" int dit4sr_gemm_bf16_grouped(const dit4sr_gemm_params* probs, int cou
       if ((rc = host::make_tmap_bf16(&maps.w[i], p->W, 2, dims, strides, box)) != 0) return rc;
     }
     maps.ws[i] = maps.w[i];
-    if (g.split > 1) {   // W through a box of BN/split rows for the column slices of the tail tiles
+    if (g.split > 1 || g.pair) {   // W through a box of BN/split rows (column slices of the tail tiles) or BN/2 (pairs)
       uint64_t dims[2] = {(uint64_t)p->K, (uint64_t)p->N};
       uint64_t strides[1] = {(uint64_t)p->ldw * 2};
-      uint32_t box[2] = {BK, (uint32_t)(BN / g.split)};
+      uint32_t box[2] = {BK, (uint32_t)(g.pair ? BN / 2 : BN / g.split)};
       if ((rc = host::make_tmap_bf16(&maps.ws[i], p->W, 2, dims, strides, box)) != 0) return rc;
+    }
+    maps.wt[i] = maps.ws[i];
+    if (g.pair && g.split > 1) {
+      uint64_t dims[2] = {(uint64_t)p->K, (uint64_t)p->N};
+      uint64_t strides[1] = {(uint64_t)p->ldw * 2};
+      uint32_t box[2] = {BK, (uint32_t)(BN / (2 * g.split))};
+      if ((rc = host::make_tmap_bf16(&maps.wt[i], p->W, 2, dims, strides, box)) != 0) return rc;
     }
     Problem& P = g.p[i];   // shape fields were set by plan_tiles
     P.bias = p->bias;
@@ -728,6 +823,7 @@ extern "C" int dit4sr_gemm_bf16_grouped(const dit4sr_gemm_params* probs, int cou
     maps.w[i] = maps.w[0];
     maps.ws[i] = maps.ws[0];
     maps.c[i] = maps.c[0];
+    maps.wt[i] = maps.wt[0];
   }
   switch (epilogue) {
     case DIT4SR_EPI_BIAS: return launch<DIT4SR_EPI_BIAS>(maps, g, stream);
