@@ -1138,6 +1138,279 @@ attn_fwd4_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
 
 }  // namespace v4
 
+// =====================================================================================================================
+// v5: v4 with TWO softmax warpgroups per query tile, each owning HALF of every 96-key score row (pre-scaled form only).
+//
+// v4 keeps one softmax warp per SM sub-partition and CTA (two with its co-resident neighbour): a warp's tile-step is a
+// serial chain (TMEM load -> 96 exponentials -> TMEM store -> arrive) and with two warps per scheduler the MUFU unit and
+// the issue slots idle whenever both are in their non-MUFU phases (steady state: ~1700 cycles per step pair against a
+// MUFU demand of 1152).  The pre-scaled form has no row max, so a row splits across threads for free: thread (row, h)
+// takes keys [48 h, 48 h + 48) of every tile (48 + 24 live registers instead of 96 + 48 -> 104 registers per thread, four
+// softmax warps per scheduler at two CTAs per SM), the halves of the row sum meet once in the epilogue, and each
+// warpgroup stores 32 of the 64 output columns.  P of half h lives in the first 24 columns of ITS OWN half of the score
+// buffer (the other warpgroup may still be loading its scores), so the P V MMAs take A from 48 (k / 3) + 8 (k % 3).
+// Barriers as in v4 (p_full counts 8 warps).  The online form keeps v4.
+namespace v5 {
+
+constexpr int BKV = 96, HALF = 48;
+constexpr int KV_BYTES = BKV * DH * 2;   // 12 KB
+constexpr int KV_STAGES = 3;
+constexpr int NUM_THREADS = 384;
+constexpr int TMEM_COLS = 256;
+constexpr int COL_O = 2 * BKV;
+constexpr int SMEM_BYTES = TILE_BYTES + 2 * KV_STAGES * KV_BYTES + 1024 + 256 + 2 * BQ * 4;
+
+template <int POLY8, bool SLICED>
+__global__ void __launch_bounds__(NUM_THREADS, 2)
+attn_fwd5_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
+                 const __grid_constant__ CUtensorMap tmV, const Args args) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sQ = smem;                                            // one tile of 128 rows
+  uint8_t* sK = smem + TILE_BYTES;                               // KV_STAGES tiles of 96 rows
+  uint8_t* sV = sK + KV_STAGES * KV_BYTES;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sV + KV_STAGES * KV_BYTES);
+  uint64_t* q_full = bars;
+  uint64_t* k_full = bars + 1;
+  uint64_t* k_empty = k_full + KV_STAGES;
+  uint64_t* v_full = k_empty + KV_STAGES;
+  uint64_t* v_empty = v_full + KV_STAGES;
+  uint64_t* s_full = v_empty + KV_STAGES;   // [2 buffers]
+  uint64_t* p_full = s_full + 2;            // [2]
+  uint64_t* o_final = p_full + 2;           // the last P V complete (epilogue)
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(o_final + 1);
+  float* l_half = reinterpret_cast<float*>(bars + 32);           // [2 halves][128 rows]
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  int work, slice, q_tile, head, b, j0, n_tiles;
+  bool last_kv;
+  if constexpr (!SLICED) {
+    q_tile = blockIdx.x, head = blockIdx.y, b = blockIdx.z;
+    work = q_tile + args.q_pairs * (head + args.heads * b);
+    if (work >= args.n_full) return;
+    slice = -1, j0 = 0, n_tiles = args.n_kv_tiles, last_kv = true;
+  } else {
+    work = args.n_full + blockIdx.x / args.split;
+    slice = blockIdx.x % args.split;
+    q_tile = work % args.q_pairs;
+    head = (work / args.q_pairs) % args.heads;
+    b = work / (args.q_pairs * args.heads);
+    j0 = slice * args.tiles_per_slice;
+    n_tiles = min(args.tiles_per_slice, args.n_kv_tiles - j0);
+    last_kv = j0 + n_tiles == args.n_kv_tiles;
+  }
+
+  if (warp == 0 && lane == 0) {
+    ptx::prefetch_tmap(&tmQ);
+    ptx::prefetch_tmap(&tmK);
+    ptx::prefetch_tmap(&tmV);
+    ptx::mbar_init(q_full, 1);
+    for (int i = 0; i < KV_STAGES; ++i) {
+      ptx::mbar_init(&k_full[i], 1);
+      ptx::mbar_init(&k_empty[i], 1);
+      ptx::mbar_init(&v_full[i], 1);
+      ptx::mbar_init(&v_empty[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      ptx::mbar_init(&s_full[i], 1);
+      ptx::mbar_init(&p_full[i], 8);
+    }
+    ptx::mbar_init(o_final, 1);
+    ptx::fence_barrier_init();
+  }
+  if (warp == 1) {
+    ptx::tmem_alloc(tmem_ptr, TMEM_COLS);
+    ptx::tmem_relinquish();
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+  ptx::pdl_wait();
+  ptx::pdl_launch_dependents();
+
+  if (warp < 4) {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 32;");
+    if (warp == 0) {
+      if (lane == 0) {
+        // ===================== TMA producer =====================
+        ptx::mbar_expect_tx(q_full, TILE_BYTES);
+        ptx::tma_load_3d(sQ, &tmQ, q_full, head * DH, q_tile * BQ, b);
+        for (int j = 0; j < n_tiles; ++j) {
+          const int st = j % KV_STAGES;
+          const uint32_t ph = (j / KV_STAGES) & 1;
+          ptx::mbar_wait(&k_empty[st], ph ^ 1);
+          ptx::mbar_expect_tx(&k_full[st], KV_BYTES);
+          ptx::tma_load_3d(sK + st * KV_BYTES, &tmK, &k_full[st], head * DH, (j0 + j) * BKV, b);
+          ptx::mbar_wait(&v_empty[st], ph ^ 1);
+          ptx::mbar_expect_tx(&v_full[st], KV_BYTES);
+          ptx::tma_load_3d(sV + st * KV_BYTES, &tmV, &v_full[st], head * DH, (j0 + j) * BKV, b);
+        }
+      }
+    } else if (warp == 1) {
+      // ===================== MMA issuer (whole warp runs the loop; one elected lane issues) =====================
+      constexpr uint32_t idesc_qk = ptx::make_idesc_bf16(BQ, BKV, 0, 0);
+      constexpr uint32_t idesc_pv = ptx::make_idesc_bf16(BQ, DH, 0, 1);
+      const uint64_t qdesc = ptx::make_sdesc_sw128(ptx::smem_u32(sQ));
+      const uint64_t kdesc_base = ptx::make_sdesc_sw128(ptx::smem_u32(sK));
+      const uint64_t vdesc_base = ptx::make_sdesc_sw128(ptx::smem_u32(sV));
+      const uint32_t tS0 = tmem_base;
+      const uint32_t tO = tmem_base + COL_O;
+
+      T_DECL;
+      auto issue_qk = [&](int j) {   // S(j&1) = Q K_j^T
+        const int st = j % KV_STAGES, buf = j & 1;
+        T_MARK(9);
+        ptx::mbar_wait(&k_full[st], (j / KV_STAGES) & 1);
+        ptx::tc_fence_after();
+        T_MARK(4);   // wait K
+        const uint64_t kdesc = kdesc_base + (uint64_t)(st * (KV_BYTES >> 4));
+        if (ptx::elect_one()) {
+#pragma unroll
+          for (int k = 0; k < DH / 16; ++k)
+            ptx::mma_ss(tS0 + buf * BKV, qdesc + 2 * k, kdesc + 2 * k, idesc_qk, k != 0);
+          ptx::tc_commit(&s_full[buf]);
+          ptx::tc_commit(&k_empty[st]);
+        }
+        __syncwarp();
+        T_MARK(5);   // issue Q K^T + commits
+      };
+
+      ptx::mbar_wait(q_full, 0);
+      issue_qk(0);
+      if (n_tiles > 1) issue_qk(1);
+      for (int j = 0; j < n_tiles; ++j) {
+        const int st = j % KV_STAGES, buf = j & 1;
+        T_MARK(9);
+        ptx::mbar_wait(&v_full[st], (j / KV_STAGES) & 1);
+        T_MARK(1);   // wait V
+        ptx::mbar_wait(&p_full[buf], (j >> 1) & 1);   // both halves of P_j are in the buffer
+        ptx::tc_fence_after();
+        T_MARK(2);   // wait P
+        const uint64_t vdesc = vdesc_base + (uint64_t)(st * (KV_BYTES >> 4));
+        if (ptx::elect_one()) {
+#pragma unroll
+          for (int k = 0; k < BKV / 16; ++k)   // O += P V_j: A = P from TMEM (half k/3, 8 columns per 16 keys), B = V MN-major
+            ptx::mma_ts(tO, tS0 + buf * BKV + (k / 3) * HALF + 8 * (k % 3), vdesc + (uint64_t)(128 * k), idesc_pv,
+                        (j | k) != 0);
+          ptx::tc_commit(&v_empty[st]);
+          if (j + 1 == n_tiles) ptx::tc_commit(o_final);
+        }
+        __syncwarp();
+        T_MARK(3);   // issue P V + commits
+        if (j + 2 < n_tiles) issue_qk(j + 2);   // into the buffer P_j just left (ordered behind P V_j in the tensor pipe)
+      }
+      T_FLUSH();
+    }
+  } else {
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 104;");
+    // ============ softmax warpgroups (thread = half h of one query row; row = TMEM lane) ============
+    const int q = warp & 3;          // TMEM lane quarter
+    const int h = (warp >> 2) - 1;   // which half of the keys of every tile
+    const uint32_t lane_off = (uint32_t)(q * 32) << 16;
+    const uint32_t tS0 = tmem_base + lane_off + h * HALF;
+    float l_run = 0.f;
+    T_DECL;
+    auto tile_step = [&](int j, auto masked) {
+      const int buf = j & 1;
+      const uint32_t tS = tS0 + buf * BKV;
+      T_MARK(9);
+      ptx::mbar_wait(&s_full[buf], (j >> 1) & 1);
+      ptx::tc_fence_after();
+      T_MARK(1);   // wait S
+      uint32_t v[HALF];
+      ptx::tmem_ld32(tS, *reinterpret_cast<uint32_t(*)[32]>(&v[0]));
+      ptx::tmem_ld16(tS + 32, &v[32]);
+      ptx::tmem_wait_ld();
+      T_MARK(2);   // TMEM load
+      if constexpr (decltype(masked)::value) {   // only the last KV tile can be ragged
+        const int kv_left = args.seq_kv - (j0 + j) * BKV - h * HALF;
+#pragma unroll
+        for (int i = 0; i < HALF; ++i)
+          if (i >= kv_left) v[i] = 0xff800000u;   // -inf
+      }
+      uint64_t rs2[4];                    // independent packed partial row sums
+#pragma unroll
+      for (int a = 0; a < 4; ++a) rs2[a] = ptx::pack2(0.f, 0.f);
+      uint32_t pk[HALF / 2];
+#pragma unroll
+      for (int i = 0; i < HALF / 2; ++i) {
+        const uint64_t x2 = ptx::pack2(__uint_as_float(v[2 * i]), __uint_as_float(v[2 * i + 1]));
+        float p0, p1;
+        if (!decltype(masked)::value && (i & 7) < POLY8) {
+          v2::exp2_poly2<false>(x2, p0, p1);
+        } else {
+          p0 = ptx::ex2(__uint_as_float(v[2 * i]));
+          p1 = ptx::ex2(__uint_as_float(v[2 * i + 1]));
+        }
+        rs2[i & 3] = ptx::add2(rs2[i & 3], ptx::pack2(p0, p1));
+        pk[i] = ptx::pack_bf16(p0, p1);
+      }
+      float ra, rb, rc, rd;
+      ptx::unpack2(ptx::add2(rs2[0], rs2[1]), ra, rb);
+      ptx::unpack2(ptx::add2(rs2[2], rs2[3]), rc, rd);
+      l_run += (ra + rb) + (rc + rd);
+      T_MARK(3);   // exponentials + sums + pack
+      // P overwrites the first 24 columns of this half of the score buffer (the half row is already in registers)
+      ptx::tmem_st16(tS, &pk[0]);
+      ptx::tmem_st8(tS + 16, &pk[16]);
+      ptx::tmem_wait_st();
+      ptx::tc_fence_before();
+      T_MARK(6);   // P store
+      __syncwarp();
+      if (lane == 0) ptx::mbar_arrive(&p_full[buf]);
+      T_MARK(7);   // arrive
+    };
+    const bool ragged = last_kv && (args.seq_kv % BKV) != 0;
+    for (int j = 0; j + 1 < n_tiles; ++j) tile_step(j, std::false_type{});
+    if (ragged) tile_step(n_tiles - 1, std::true_type{});
+    else tile_step(n_tiles - 1, std::false_type{});
+    T_FLUSH();
+
+    // epilogue: the halves of the row sum meet in shared memory; warpgroup h stores output columns [32 h, 32 h + 32)
+    const int prow = q * 32 + lane;
+    l_half[h * BQ + prow] = l_run;
+    asm volatile("bar.sync 1, 256;" ::: "memory");
+    const float l_tot = l_half[prow] + l_half[BQ + prow];
+    ptx::mbar_wait(o_final, 0);
+    ptx::tc_fence_after();
+    const int row = q_tile * BQ + prow;
+    uint32_t o[32];
+    ptx::tmem_ld32(tmem_base + lane_off + COL_O + h * 32, o);
+    ptx::tmem_wait_ld();
+    if constexpr (!SLICED) {
+      if (row < args.seq_q) {
+        const float inv_l = 1.0f / l_tot;
+        float f[32];
+#pragma unroll
+        for (int i = 0; i < 32; ++i) f[i] = __uint_as_float(o[i]) * inv_l;
+        emit_chunk(args, f, row, head, b, h);
+      }
+    } else {
+      // one KV slice of a tail item: publish the unnormalised row; attn_merge_kernel combines the slices
+      const int tail = work - args.n_full;
+      float* mine = args.part + (((int64_t)tail * args.split + slice) * BQ + prow) * PART_STRIDE;
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+        __stcg(reinterpret_cast<float4*>(mine + h * 32) + i,
+               make_float4(__uint_as_float(o[4 * i]), __uint_as_float(o[4 * i + 1]), __uint_as_float(o[4 * i + 2]),
+                           __uint_as_float(o[4 * i + 3])));
+      if (h == 0) __stcg(reinterpret_cast<float2*>(mine + DH), make_float2(l_tot, 0.f));
+    }
+  }
+
+  __syncwarp();
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    ptx::tc_fence_after();
+    ptx::tmem_dealloc(tmem_base, TMEM_COLS);
+  }
+}
+
+}  // namespace v5
+
 }  // namespace attn
 
 #ifdef DIT4SR_ATTN_TIMING
@@ -1198,11 +1471,15 @@ static int make_plan(const dit4sr_attn_params* p, int sms, Plan* out) {
     const double c2 = waves2 * (tiles128 + 5.5) * 1.130, c3 = waves3 * (tiles96 + 7.5) * 0.848,
                  c4 = waves4 * (tiles96 + 2.3) * 0.888;
     variant = c4 <= c3 ? (c4 <= c2 ? 4 : 2) : (c3 <= c2 ? 3 : 2);
+    // pre-scaled scores: the split-row form of v4 is 1-1.5 % faster at every measured shape (profiles/r02_attn_v5.log)
+    if (variant == 4 && p->mode == DIT4SR_ATTN_PRESCALED) variant = 5;
   }
-  const int items = variant == 4 ? items4 : (variant == 3 ? items3 : items2);
-  const int split = variant == 4 ? split4 : (variant == 3 ? split3 : 1);
-  const int n_full = variant == 4 ? nf4 : (variant == 3 ? nf3 : items2);
-  const int q_pairs = (p->seq_q + (variant == 4 ? BQ : 2 * BQ) - 1) / (variant == 4 ? BQ : 2 * BQ);   // items per (head, batch)
+  if (variant == 5 && p->mode != DIT4SR_ATTN_PRESCALED) variant = 4;   // (v5 has no online form)
+  const bool one_tile = variant == 4 || variant == 5;
+  const int items = one_tile ? items4 : (variant == 3 ? items3 : items2);
+  const int split = one_tile ? split4 : (variant == 3 ? split3 : 1);
+  const int n_full = one_tile ? nf4 : (variant == 3 ? nf3 : items2);
+  const int q_pairs = (p->seq_q + (one_tile ? BQ : 2 * BQ) - 1) / (one_tile ? BQ : 2 * BQ);   // items per (head, batch)
   const int bkv = variant == 2 ? BKV : v3::BKV;
   out->variant = variant;
   out->split = split;
@@ -1217,6 +1494,7 @@ static int make_plan(const dit4sr_attn_params* p, int sms, Plan* out) {
 
 }  // namespace attn
 
+constexpr int V5_DEFAULT_PO = 1;   // v5's default share of exponentials on the FMA pipe: index into {0/8, 2/8, 4/8}
 static int g_last_plan[4] = {0, 0, 0, 0};   // variant, split, whole items, tail items of the latest dit4sr_attn_fwd call
 
 extern "C" int dit4sr_attn_last_plan(int plan[4]) {
@@ -1228,7 +1506,7 @@ extern "C" int dit4sr_attn_last_plan(int plan[4]) {
 extern "C" int dit4sr_attn_plan(const dit4sr_attn_params* p, int sm_count, int plan[6]) {
   DIT4SR_REQUIRE(p != nullptr && plan != nullptr && sm_count >= 1, DIT4SR_E_BADARG, "attn_plan: bad argument");
   DIT4SR_REQUIRE(p->batches > 0 && p->heads > 0 && p->seq_q > 0 && p->seq_kv > 0 && p->seq_q <= p->seq_kv &&
-                     p->split_kv <= 4 && (p->variant == 0 || (p->variant >= 2 && p->variant <= 4)),
+                     p->split_kv <= 4 && (p->variant == 0 || (p->variant >= 2 && p->variant <= 5)),
                  DIT4SR_E_BADARG, "attn_plan: bad sizes");
   attn::Plan pl;
   // (the workspace pointer is only tested against NULL and workspace_bytes against the need for `sm_count` SMs)
@@ -1279,7 +1557,7 @@ extern "C" int dit4sr_attn_fwd(const dit4sr_attn_params* p, void* stream_) {
                  "attn: DIT4SR_ATTN_PRESCALED needs 0 < score_bound <= %g (log2 units), got %g",
                  (double)DIT4SR_ATTN_MAX_SCORE_BOUND, (double)p->score_bound);
   DIT4SR_REQUIRE(p->exp_offload >= 0 && p->exp_offload <= 3, DIT4SR_E_BADARG, "attn: exp_offload must be 0..3");
-  DIT4SR_REQUIRE(p->variant == 0 || (p->variant >= 2 && p->variant <= 4), DIT4SR_E_BADARG, "attn: variant must be 0, 2, 3 or 4");
+  DIT4SR_REQUIRE(p->variant == 0 || (p->variant >= 2 && p->variant <= 5), DIT4SR_E_BADARG, "attn: variant must be 0 or 2..5");
   DIT4SR_REQUIRE(p->workspace == nullptr || host::aligned16(p->workspace), DIT4SR_E_ALIGN, "attn: workspace must be 16-byte aligned");
 
   int rc = dit4sr_check_device();
@@ -1344,26 +1622,28 @@ extern "C" int dit4sr_attn_fwd(const dit4sr_attn_params* p, void* stream_) {
        {v3::attn_fwd3_kernel<0, true, true>, v3::attn_fwd3_kernel<2, true, true>, v3::attn_fwd3_kernel<4, true, true>}},
       {{v4::attn_fwd4_kernel<0, false, true>, v4::attn_fwd4_kernel<2, false, true>, v4::attn_fwd4_kernel<4, false, true>},
        {v4::attn_fwd4_kernel<0, true, true>, v4::attn_fwd4_kernel<2, true, true>, v4::attn_fwd4_kernel<4, true, true>}}};
-  const int po = p->exp_offload == 0 ? 1 : p->exp_offload - 1;
-  const int vi = variant - 2, mi = prescaled ? 1 : 0;
-  const KernelFn fn = whole[vi][mi][po];
-  const int smem = variant == 4 ? v4::SMEM_BYTES : (variant == 3 ? v3::SMEM_BYTES : v2::SMEM_BYTES);
+  static const KernelFn whole5[3] = {v5::attn_fwd5_kernel<0, false>, v5::attn_fwd5_kernel<2, false>, v5::attn_fwd5_kernel<4, false>};
+  static const KernelFn sliced5[3] = {v5::attn_fwd5_kernel<0, true>, v5::attn_fwd5_kernel<2, true>, v5::attn_fwd5_kernel<4, true>};
+  const int po = p->exp_offload == 0 ? (variant == 5 ? V5_DEFAULT_PO : 1) : p->exp_offload - 1;
+  const int vi = variant == 5 ? 2 : variant - 2, mi = prescaled ? 1 : 0;
+  const KernelFn fn = variant == 5 ? whole5[po] : whole[vi][mi][po];
+  const int smem = variant == 5 ? v5::SMEM_BYTES : variant == 4 ? v4::SMEM_BYTES : (variant == 3 ? v3::SMEM_BYTES : v2::SMEM_BYTES);
   const int threads = variant == 4 ? v4::NUM_THREADS : 384;
   // the opt-in to > 48 KB of dynamic shared memory is per (function, device): remember which pairs are done
-  static unsigned long long configured[3][2][3] = {}, configured_s[2][2][3] = {};
-  if (host::first_use_on_device(&configured[vi][mi][po]))
+  static unsigned long long configured[3][2][3] = {}, configured_s[2][2][3] = {}, configured5[3] = {}, configured5_s[3] = {};
+  if (host::first_use_on_device(variant == 5 ? &configured5[po] : &configured[vi][mi][po]))
     DIT4SR_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
   g_last_plan[0] = variant, g_last_plan[1] = split, g_last_plan[2] = n_full, g_last_plan[3] = items - n_full;
   dim3 grid(q_pairs, p->heads, p->batches);
   // (v3 / v4: items >= n_full exit at once; nothing to launch when every item is a tail item)
   if (n_full > 0) DIT4SR_CUDA(host::launch_pdl(fn, grid, dim3(threads), (size_t)smem, stream, tmQ, tmK, tmV, a));
   if (split > 1) {   // the tail items again, as KV slices, then the merge
-    const KernelFn fs = sliced[variant - 3][mi][po];
-    if (host::first_use_on_device(&configured_s[variant - 3][mi][po]))
+    const KernelFn fs = variant == 5 ? sliced5[po] : sliced[variant - 3][mi][po];
+    if (host::first_use_on_device(variant == 5 ? &configured5_s[po] : &configured_s[variant - 3][mi][po]))
       DIT4SR_CUDA(cudaFuncSetAttribute(fs, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     fs<<<(items - n_full) * split, threads, smem, stream>>>(tmQ, tmK, tmV, a);
     DIT4SR_CUDA(cudaGetLastError());
-    v3::attn_merge_kernel<<<items - n_full, variant == 4 ? BQ : 2 * BQ, 0, stream>>>(a);
+    v3::attn_merge_kernel<<<items - n_full, variant >= 4 ? BQ : 2 * BQ, 0, stream>>>(a);
     DIT4SR_CUDA(cudaGetLastError());
   }
   return 0;

@@ -207,11 +207,12 @@ def attention_workspace_bytes():
     return int(_lib.load().dit4sr_attn_workspace_bytes())
 
 
-def attention_plan(batches, heads, seq_q, seq_kv, sm_count=148, workspace=True, split_kv=0, variant=0):
+def attention_plan(batches, heads, seq_q, seq_kv, sm_count=148, workspace=True, split_kv=0, variant=0, prescaled=False):
     """Host-only: (kernel variant, KV slices, whole items, tail items, KV tiles, KV tiles per slice) dit4sr_attn_fwd would use
     for this shape on a GPU with `sm_count` SMs.  Needs no device."""
     p = AttnParams()
     p.batches, p.heads, p.seq_q, p.seq_kv, p.split_kv, p.variant = batches, heads, seq_q, seq_kv, split_kv, variant
+    p.mode = 1 if prescaled else 0      # (ATTN_PRESCALED: the split-row form of the one-tile kernel is the default there)
     if workspace:
         p.workspace, p.workspace_bytes = C.c_void_p(16), 1 << 40      # only compared with NULL / the size needed
     plan = (C.c_int * 6)()

@@ -169,10 +169,13 @@ int dit4sr_gemm_schedule(const dit4sr_gemm_params* problems, int count, int sm_c
  *                          from the checkpoint's norm weights; the host refuses the mode when it does not hold.
  * exp_offload: 0 = default; 1, 2, 3 = 0/8, 2/8, 4/8 of the exponentials evaluated by a polynomial on the FMA pipe instead
  *              of MUFU.EX2 (tuning knob: same results to within bf16 rounding of P).
- * variant:     4 = one 128-row query tile per CTA, two CTAs per SM, double-buffered 96-key score tiles; 3 = the same tiles,
+ * variant:     5 = 4 with two softmax warpgroups per tile, each owning half of every 96-key score row (pre-scaled form only;
+ *              an online-mode call asking for 5 runs 4);
+ *              4 = one 128-row query tile per CTA, two CTAs per SM, double-buffered 96-key score tiles; 3 = the same tiles,
  *              two query tiles per CTA sharing K/V; 2 = three 128-key score buffers rotating over the two query tiles of
  *              a CTA (round 1's pipeline); 0 = default: the cheapest of the three under a fitted cost model (waves x
- *              (KV steps + per-CTA overhead) x step time): 4 for short and medium sequences, 3 for very long ones.
+ *              (KV steps + per-CTA overhead) x step time): 4 (5 with pre-scaled scores) for short and medium sequences, 3 for very
+ *              long ones.
  * workspace:   optional scratch of dit4sr_attn_workspace_bytes() bytes (contents irrelevant).  With it, work items that would
  *              only partly fill the last wave of SMs are cut into 2-4 slices along the keys; each slice publishes its
  *              unnormalised row + row sum (+ reference max) and a small second kernel merges them (e.g. 390 items on 148

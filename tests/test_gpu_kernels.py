@@ -243,11 +243,12 @@ def test_joint_attention_every_kernel_variant(ops, B, H, S, Sq, lr, variant):
     assert rel(o.float(), ref) < 4e-3
 
 
+@pytest.mark.parametrize("variant", [0, 5])
 @pytest.mark.parametrize("exp_offload", [0, 1, 3])
 @pytest.mark.parametrize("B,H,S,Sq,lr", [(1, 2, 256, 256, None), (2, 3, 333, 333, None), (1, 24, 2381, 2381, (1024, 2048)),
                                          (2, 4, 2381, 2048, (1024, 2048)), (1, 1, 1, 1, None), (8, 24, 600, 333, (100, 300)),
-                                         (1, 2, 8525, 8525, (4096, 8192))])
-def test_joint_attention_prescaled_bounded_scores(ops, B, H, S, Sq, lr, exp_offload):
+                                         (1, 2, 8525, 8525, (4096, 8192)), (1, 2, 50, 50, None), (2, 2, 2350, 2350, None)])
+def test_joint_attention_prescaled_bounded_scores(ops, B, H, S, Sq, lr, exp_offload, variant):
     """DIT4SR_ATTN_PRESCALED (ABI v3): q arrives multiplied by scale*log2(e) and the caller bounds every score; the
     kernel takes p = 2^(q.k) with no running max.  Reference: fp32 SDPA on the SAME (bf16-rounded, pre-scaled) q with
     scale = ln 2, i.e. softmax(2^(q'.k))."""
@@ -266,7 +267,7 @@ def test_joint_attention_prescaled_bounded_scores(ops, B, H, S, Sq, lr, exp_offl
     o = torch.zeros(B, Sq, D, device="cuda", dtype=torch.bfloat16)
     res = torch.randn(B, S, D, device="cuda").bfloat16() if lr else None
     ops.attention(q, k, v, o, H, seq_q=Sq, lr_res=res, lr_rows=lr or (0, 0), score_bound=max(bound, 1.0),
-                  exp_offload=exp_offload)
+                  exp_offload=exp_offload, variant=variant)
     ref = torch.nn.functional.scaled_dot_product_attention(hd(q), hd(k), hd(v), scale=math.log(2.0))
     ref = ref.transpose(1, 2).reshape(B, S, D)[:, :Sq].clone()
     if lr:
@@ -320,7 +321,7 @@ def test_attention_at_the_c4_per_rank_shape(ops, prescaled):
     assert worst < 4e-3
 
 
-@pytest.mark.parametrize("variant", [3, 4])
+@pytest.mark.parametrize("variant", [3, 4, 5])
 @pytest.mark.parametrize("prescaled", [False, True])
 @pytest.mark.parametrize("split_kv", [0, 2, 3, 4])
 @pytest.mark.parametrize("B,H,S,Sq,lr", [(1, 24, 2381, 2381, (1024, 2048)),      # 240 pair items on 148 SMs: 92 tail items

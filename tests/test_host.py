@@ -197,6 +197,9 @@ def test_attention_work_decomposition_without_a_gpu():
     v, split, whole, tail, tiles, tps = ops.attention_plan(8, 24, 2381, 2381)
     assert (v, split, whole, tail) == (4, 3, 12 * 296, 96) and tiles == 25 and tps == 9
     assert ops.attention_plan(8, 24, 2381, 2381, workspace=False)[:4] == (4, 1, 19 * 24 * 8, 0)
+    # pre-scaled scores: same decomposition on the split-row form (5); an explicit 5 without pre-scaled scores runs as 4
+    assert ops.attention_plan(8, 24, 2381, 2381, prescaled=True)[:4] == (5, 3, 12 * 296, 96)
+    assert ops.attention_plan(8, 24, 2381, 2381, variant=5)[0] == 4
     # C4 on 8 ranks: 3 heads over S = 33101: 390 pair items on 148 SMs = 2.64 waves -> v3, 94 tail items in 3 KV slices
     v, split, whole, tail, tiles, tps = ops.attention_plan(1, 3, 33101, 33101)
     assert (v, split, whole, tail) == (3, 3, 296, 94) and tiles == 345 and tps == 115
@@ -207,14 +210,16 @@ def test_attention_work_decomposition_without_a_gpu():
     for B, H, Sq, S in [(1, 1, 1, 1), (2, 3, 3900, 4000), (8, 24, 2048, 2048), (2, 24, 8525, 8525), (1, 24, 32768, 33101),
                         (4, 24, 8192, 8525), (1, 2, 100, 100), (3, 24, 129, 129)]:
         for force in (0, 2, 3, 4):
-            for variant in (0, 3, 4):
-                v, split, whole, tail, tiles, tps = ops.attention_plan(B, H, Sq, S, split_kv=force, variant=variant)
-                rows = 128 if v == 4 else 256
+            for variant in (0, 3, 4, 5):
+                v, split, whole, tail, tiles, tps = ops.attention_plan(B, H, Sq, S, split_kv=force, variant=variant,
+                                                                       prescaled=variant == 5)
+                assert variant == 0 or v == variant
+                rows = 128 if v >= 4 else 256
                 items = -(-Sq // rows) * H * B
                 assert whole + tail == items and 1 <= split <= 4
                 assert (split == 1) == (tail == 0)
                 assert tiles == -(-S // (128 if v == 2 else 96))
                 assert tps * split >= tiles and tps * (split - 1) < tiles      # every slice has at least one KV tile
-                slots = 296 if v == 4 else 148
+                slots = 296 if v >= 4 else 148
                 if split > 1:
                     assert whole % slots == 0 and tail < slots

@@ -78,7 +78,7 @@ def main():
     lib.dit4sr_attn_timing_read.restype = C.c_int
     rc = lib.dit4sr_attn_timing_read(buf)
     assert rc == 0
-    steps = (S + 127) // 128
+    steps = (S + 127) // 128 if a.variant == 2 else (S + 95) // 96
     print(f"shape B={B} S={S} prescaled={a.prescaled} exp_offload={a.exp_offload} variant={a.variant}: {e0.elapsed_time(e1) / 10:.4f} ms "
           f"(instrumented build), {steps} KV steps; cycles per KV step of one CTA:")
     for w in range(12):

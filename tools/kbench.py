@@ -46,8 +46,9 @@ def main():
     ap.add_argument("--reps", type=int, default=20)
     ap.add_argument("--shape", default="c2")
     ap.add_argument("--split", type=int, default=-1, help="attn: -1 no workspace, 0 automatic split-KV tail, 2..4 forced")
-    ap.add_argument("--variant", type=int, default=0, help="attn: 0 default, 2 rotating buffers, 3 double-buffered 96-key tiles")
+    ap.add_argument("--variant", type=int, default=0, help="attn: 0 default, 2 rotating buffers, 3 double-buffered 96-key tiles, 4 one tile per CTA, 5 = 4 with split rows")
     ap.add_argument("--graph", action="store_true")
+    ap.add_argument("--sustain", type=float, default=0.0, help="attn: also run back to back for this many seconds, sampling clocks and power")
     ap.add_argument("--prescaled", action="store_true", help="attn: DIT4SR_ATTN_PRESCALED mode (q pre-multiplied)")
     ap.add_argument("--exp-offload", type=int, default=0, help="attn: 0 default, 1/2/3 = 0/8, 2/8, 4/8 polynomial")
     a = ap.parse_args()
@@ -73,6 +74,25 @@ def main():
                                    workspace=wsp, split_kv=max(a.split, 0))
         ms = timeit(fn, a.reps)
         fl = 4.0 * S * S * D * B
+        if a.sustain > 0:   # same kernel back to back for `sustain` seconds with nvidia-smi sampling clocks / power
+            import subprocess, tempfile, time
+            f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+            pr = subprocess.Popen(["nvidia-smi", "--query-gpu=clocks.sm,power.draw,clocks_event_reasons.sw_power_cap",
+                                   "--format=csv,noheader,nounits", "-lms", "100", "-i", "0"], stdout=f)
+            n = max(int(a.sustain * 1e3 / ms), 10)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(n):
+                fn()
+            e1.record()
+            torch.cuda.synchronize()
+            pr.terminate(); pr.wait()
+            rows = [l.strip().split(", ") for l in open(f.name) if l.strip()]
+            rows = rows[len(rows) // 3:]
+            mhz = sorted(float(r[0]) for r in rows); watts = sorted(float(r[1]) for r in rows)
+            cap = sum(r[2].lower().startswith("active") for r in rows)
+            print(f"  sustained {n} launches: {e0.elapsed_time(e1) / n:.4f} ms  {fl * n / e0.elapsed_time(e1) / 1e9:.1f} TFLOP/s; "
+                  f"median {mhz[len(mhz) // 2]:.0f} MHz, {watts[len(watts) // 2]:.0f} W, power-cap active in {cap}/{len(rows)} samples")
         print(f"attn B={B} S={S} prescaled={a.prescaled} exp_offload={a.exp_offload} variant={a.variant} split={a.split}: {ms:.4f} ms  {fl / ms / 1e9:.1f} TFLOP/s")
     elif a.what == "gemm":
         for name, M, K, Nn, epi in [("ff1", B * 2 * N, D, F, ops.EPI_BIAS_GELU), ("ff2", B * 2 * N, F, D, ops.EPI_GATE_RESID),
