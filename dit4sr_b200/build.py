@@ -10,7 +10,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB_PATH = os.path.join(HERE, "libdit4sr_b200.so")
-SOURCES = ["host_util.cu", "gemm.cu", "attn.cu", "ln_modulate.cu", "dwconv.cu", "misc.cu", "precise.cu", "colorfix.cu", "sp_comm.cu"]
+SOURCES = ["host_util.cu", "gemm.cu", "attn.cu", "ln_modulate.cu", "dwconv.cu", "misc.cu", "precise.cu", "colorfix.cu", "sp_comm.cu", "vae.cu"]
 NVCC_FLAGS = ["-std=c++17", "-O3", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
               "-Xcompiler", "-fPIC", "-Xptxas", "-v"]
 

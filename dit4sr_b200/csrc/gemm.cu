@@ -51,6 +51,10 @@ struct Problem {
   // Ulysses scatter (dit4sr_gemm_sp): bf16 output heads go straight to the attention-side buffers of the owning ranks
   int sp_world, sp_rank, sp_own_only, sp_D, sp_col0;
   int64_t sp_rows_dst, sp_row0;
+  // implicit-GEMM convolution (dit4sr_gemm_params.conv_*): A is an NHWC image read through a 4-D tensor map
+  int conv_w, conv_cblocks, conv_kw, conv_org;
+  const __nv_bfloat16* resid_b;   // BIAS epilogue, bf16 C: added to the output
+  int64_t ld_rb, rb_batch_stride;
 };
 
 // Tail splitting: with T tiles on G CTAs the last T mod G tiles would occupy a whole extra wave with most SMs idle
@@ -216,8 +220,16 @@ gemm_kernel(const __grid_constant__ Maps maps, const __grid_constant__ Group grp
       uint32_t phase = 0;
       for (int tile = cta_first; tile < num_tiles; tile += cta_stride) {
         const TileCoord tc = decode_tile(grp, tile);
-        const int k_blocks = grp.p[tc.pi].k_blocks;
+        const Problem& PP = grp.p[tc.pi];
+        const int k_blocks = PP.k_blocks;
         const CUtensorMap* ma = &maps.a[tc.pi];
+        const bool conv = PP.conv_w > 0;
+        int cy0 = 0, cx0 = 0;
+        if (conv) {   // first output pixel of this CTA's 128 rows (a whole number of image rows, or a 128-pixel run of one)
+          const int pix0 = tc.m_tile * BMT + rank * BM;
+          cy0 = pix0 / PP.conv_w;
+          cx0 = pix0 - cy0 * PP.conv_w;
+        }
         const CUtensorMap* mw = PAIR ? (tc.bn == BN ? &maps.ws[tc.pi] : &maps.wt[tc.pi])
                                      : (tc.bn == BN ? &maps.w[tc.pi] : &maps.ws[tc.pi]);
         const int w_rows = PAIR ? tc.bn / 2 : tc.bn;                  // W rows this CTA loads
@@ -230,11 +242,23 @@ gemm_kernel(const __grid_constant__ Maps maps, const __grid_constant__ Group grp
             // both CTAs' loads complete on the LEADER's full barrier, which expects the bytes of the pair
             if (rank == 0) ptx::mbar_expect_tx(&full_bar[stage], 2 * tx_bytes);
             const uint32_t lead_bar = ptx::mapa_u32(&full_bar[stage], 0);
-            ptx::tma_load_3d_2sm(sa, ma, lead_bar, kb * BK, tc.m_tile * BMT + rank * BM, tc.b);
+            if (conv) {
+              const int tap = kb / PP.conv_cblocks, cb = kb - tap * PP.conv_cblocks, ty = tap / PP.conv_kw;
+              ptx::tma_load_4d_2sm(sa, ma, lead_bar, cb * BK, cx0 + (tap - ty * PP.conv_kw) + PP.conv_org,
+                                   cy0 + ty + PP.conv_org, tc.b);
+            } else {
+              ptx::tma_load_3d_2sm(sa, ma, lead_bar, kb * BK, tc.m_tile * BMT + rank * BM, tc.b);
+            }
             ptx::tma_load_2d_2sm(sb, mw, lead_bar, kb * BK, tc.col0 + rank * w_rows);
           } else {
             ptx::mbar_expect_tx(&full_bar[stage], tx_bytes);
-            ptx::tma_load_3d(sa, ma, &full_bar[stage], kb * BK, tc.m_tile * BM, tc.b);
+            if (conv) {
+              const int tap = kb / PP.conv_cblocks, cb = kb - tap * PP.conv_cblocks, ty = tap / PP.conv_kw;
+              ptx::tma_load_4d(sa, ma, &full_bar[stage], cb * BK, cx0 + (tap - ty * PP.conv_kw) + PP.conv_org,
+                               cy0 + ty + PP.conv_org, tc.b);
+            } else {
+              ptx::tma_load_3d(sa, ma, &full_bar[stage], kb * BK, tc.m_tile * BM, tc.b);
+            }
             ptx::tma_load_2d(sb, mw, &full_bar[stage], kb * BK, tc.col0);
           }
           if (++stage == NST) { stage = 0; phase ^= 1; }
@@ -416,13 +440,32 @@ gemm_kernel(const __grid_constant__ Maps maps, const __grid_constant__ Group grp
               }
               __syncwarp();
               if (seg * 8 < cols && !dst_skip) {
+                const __nv_bfloat16* rb = nullptr;
+                if constexpr (EPI == DIT4SR_EPI_BIAS) {
+                  if (P.resid_b != nullptr) rb = P.resid_b + (int64_t)tc.b * P.rb_batch_stride + n_base + c0 + seg * 8;
+                }
 #pragma unroll
                 for (int r4 = 0; r4 < 8; ++r4) {
                   const int rl = r4 * 4 + sub;
-                  const uint4 u = *reinterpret_cast<const uint4*>(stg + rl * EPI_ROW_BYTES + seg * 16);
+                  uint4 u = *reinterpret_cast<const uint4*>(stg + rl * EPI_ROW_BYTES + seg * 16);
                   const int rg = row_base + rl;
-                  if (rg < P.rows)
+                  if (rg < P.rows) {
+                    if constexpr (EPI == DIT4SR_EPI_BIAS) {
+                      if (rb != nullptr) {   // skip connection (VAE resnet / attention block), added in fp32
+                        const uint4 r = *reinterpret_cast<const uint4*>(rb + (int64_t)rg * P.ld_rb);
+                        const __nv_bfloat162* ua = reinterpret_cast<const __nv_bfloat162*>(&u);
+                        const __nv_bfloat162* ra = reinterpret_cast<const __nv_bfloat162*>(&r);
+                        uint32_t o[4];
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) {
+                          const float2 x = __bfloat1622float2(ua[k]), y = __bfloat1622float2(ra[k]);
+                          o[k] = ptx::pack_bf16(x.x + y.x, x.y + y.y);
+                        }
+                        u = make_uint4(o[0], o[1], o[2], o[3]);
+                      }
+                    }
                     *reinterpret_cast<uint4*>(dst_base + (rg + row_shift) * dst_ld + seg * 8) = u;
+                  }
                 }
               }
             }
@@ -643,6 +686,20 @@ static int check_problem(const dit4sr_gemm_params* p, int epilogue) {
                        (p->norm_w1 == nullptr || host::aligned16(p->norm_w1)),
                    DIT4SR_E_ALIGN, "gemm/QKV_NORM: norm weights must be 16-byte aligned");
   }
+  if (p->conv_w != 0) {
+    DIT4SR_REQUIRE(p->conv_w > 0 && p->conv_h > 0 && p->conv_kw > 0 && p->conv_taps > 0 && p->conv_taps <= 16 &&
+                       p->K % p->conv_taps == 0 && (p->K / p->conv_taps) % BK == 0 &&
+                       p->rows == p->conv_w * p->conv_h && (BM % p->conv_w == 0 || p->conv_w % BM == 0),
+                   DIT4SR_E_SHAPE, "gemm/conv: need rows == conv_h*conv_w, C_in = K/conv_taps a multiple of 64, conv_w "
+                   "dividing 128 or a multiple of 128 (w %d h %d taps %d K %d rows %d)", p->conv_w, p->conv_h, p->conv_taps,
+                   p->K, p->rows);
+    DIT4SR_REQUIRE(p->sp == nullptr, DIT4SR_E_BADARG, "gemm/conv: no sp scatter");
+  }
+  if (p->resid_bf16 != nullptr) {
+    DIT4SR_REQUIRE(epilogue == DIT4SR_EPI_BIAS && p->c_dtype == DIT4SR_DT_BF16 && host::aligned16(p->resid_bf16) &&
+                       p->ld_rb % 8 == 0 && p->rb_batch_stride % 8 == 0 && p->sp == nullptr,
+                   DIT4SR_E_BADARG, "gemm: resid_bf16 needs the BIAS epilogue, bf16 C and 16-byte aligned rows");
+  }
   if (epilogue == DIT4SR_EPI_GATE_RESID) {
     DIT4SR_REQUIRE(p->resid != nullptr && p->c_dtype == DIT4SR_DT_F32 && p->ldr % 4 == 0 && p->r_batch_stride % 4 == 0 &&
                        host::aligned16(p->resid),
@@ -734,7 +791,14 @@ extern "C" int dit4sr_gemm_bf16_grouped(const dit4sr_gemm_params* probs, int cou
   for (int r = 0; r < DIT4SR_SP_MAX_RANKS; ++r) g.sp_peer[r] = nullptr;
   for (int i = 0; i < count; ++i) {
     const dit4sr_gemm_params* p = &probs[i];
-    {
+    if (p->conv_w > 0) {   // NHWC image: (channels, x, y, batch); a box = 128 output pixels x 64 input channels
+      const int bw = p->conv_w < BM ? p->conv_w : BM;
+      uint64_t dims[4] = {(uint64_t)(p->K / p->conv_taps), (uint64_t)p->conv_w, (uint64_t)p->conv_h, (uint64_t)p->batches};
+      uint64_t strides[3] = {(uint64_t)p->lda * 2, (uint64_t)p->lda * 2 * p->conv_w,
+                             (uint64_t)(p->batches > 1 ? p->a_batch_stride : (int64_t)p->rows * p->lda) * 2};
+      uint32_t box[4] = {BK, (uint32_t)bw, (uint32_t)(BM / bw), 1};
+      if ((rc = host::make_tmap_bf16(&maps.a[i], p->A, 4, dims, strides, box)) != 0) return rc;
+    } else {
       uint64_t dims[3] = {(uint64_t)p->K, (uint64_t)p->rows, (uint64_t)p->batches};
       uint64_t strides[2] = {(uint64_t)p->lda * 2,
                              (uint64_t)(p->batches > 1 ? p->a_batch_stride : (int64_t)p->rows * p->lda) * 2};
@@ -777,6 +841,13 @@ extern "C" int dit4sr_gemm_bf16_grouped(const dit4sr_gemm_params* probs, int cou
     P.sec_cols = p->sec_cols > 0 ? p->sec_cols : p->N;
     P.eps = p->eps;
     P.dbl_row_offset = p->dbl_row_offset;
+    P.conv_w = p->conv_w;
+    P.conv_cblocks = p->conv_w > 0 ? p->K / p->conv_taps / BK : 1;
+    P.conv_kw = p->conv_w > 0 ? p->conv_kw : 1;
+    P.conv_org = p->conv_org;
+    P.resid_b = reinterpret_cast<const __nv_bfloat16*>(p->resid_bf16);
+    P.ld_rb = p->ld_rb;
+    P.rb_batch_stride = p->rb_batch_stride;
     P.sp_world = 0;
     if (p->sp != nullptr) {
       const dit4sr_gemm_sp* sp = p->sp;

@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define DIT4SR_ABI_VERSION 3
+#define DIT4SR_ABI_VERSION 4
 
 enum {
   DIT4SR_OK = 0,
@@ -137,6 +137,15 @@ typedef struct {
   const float* norm_w0; const float* norm_w1;             /* QKV_NORM: fp32 [64] each (NULL = no norm) */
   int sec_cols; float eps; int64_t dbl_row_offset;
   const dit4sr_gemm_sp* sp;                               /* NULL: plain store into C */
+  /* ABI v4.  Implicit-GEMM convolution (the VAE's 3x3 / strided convolutions, row N4): conv_w > 0 makes A an NHWC image
+   * bf16 [batches, conv_h, conv_w, C_in] (pixel stride lda, C_in % 64 == 0), rows = conv_h * conv_w output pixels in
+   * raster order, K = conv_taps * C_in with W laid out [N, tap, C_in].  K-block kb belongs to tap t = kb / (C_in / 64) and
+   * is read from the image shifted by (t / conv_kw + conv_org) rows and (t % conv_kw + conv_org) columns; pixels outside
+   * the image read as zero (TMA out-of-bounds fill = the convolution's zero padding).  3x3, pad 1: conv_kw 3, conv_taps 9,
+   * conv_org -1.  conv_w must divide 128 or be a multiple of 128. */
+  int conv_w; int conv_h; int conv_kw; int conv_taps; int conv_org;
+  /* BIAS epilogue with bf16 C: C = acc + bias + resid_bf16 (same row/column indexing as C; NULL = none) */
+  const void* resid_bf16; int64_t ld_rb; int64_t rb_batch_stride;
 } dit4sr_gemm_params;
 int dit4sr_gemm_bf16(const dit4sr_gemm_params* p, void* stream);
 /* Up to DIT4SR_GEMM_MAX_GROUP independent problems sharing one epilogue kind, run by ONE persistent launch (e.g. the HQ,
@@ -362,6 +371,45 @@ int dit4sr_adain_apply_f32(const float* content, float* out, int planes, int64_t
                            const float* c_var, const float* s_mean, const float* s_var, float eps, void* stream);
 /* y = x (fp32 -> bf16 or bf16 -> fp32), n elements; dir 0 = f32->bf16, 1 = bf16->f32 */
 int dit4sr_cast(const void* x, void* y, int64_t n, int dir, void* stream);
+
+/* ---------------------------------------------------------------------------------------------------------------
+ * VAE encode / decode around the sampling loop: diffusers AutoencoderKL as the reference calls it at
+ * pipelines/pipeline_dit4sr.py:1001-1002 (`vae.encode(control_image).latent_dist.sample()`) and :1602-1605
+ * (`vae.decode(latents)`), whose layer sequence utils/vaehook.py:279-358 walks for its tiled variant.  Activations are
+ * channels-last bf16 ([batches, H*W, C], C % 64 == 0); every convolution / linear layer is dit4sr_gemm_bf16 (3x3: conv_*
+ * fields); the skip stream of the residual blocks is fp32 (GATE_RESID epilogue without a gate, added in place with TMA
+ * reduce-adds); the entry points below are the layers in between.
+ */
+/* GroupNorm(groups, eps, affine) (+ SiLU when silu != 0) over NHWC x (x_dtype: bf16, or the fp32 skip stream) -> bf16 y: statistics per (batch, group) over pixels x
+ * (channels / groups), fixed summation order (bit-reproducible; per-CTA partial sums in `stats`, a caller-owned scratch of
+ * dit4sr_groupnorm_workspace_bytes(batches, groups) bytes, contents irrelevant, combined in double), then
+ * y = (x - mean) rstd gamma + beta.  ResnetBlock2D.norm1/norm2, Attention.group_norm, conv_norm_out. */
+typedef struct {
+  const void* x; int64_t ldx; int64_t x_batch_stride;
+  void* y; int64_t ldy; int64_t y_batch_stride;
+  const float* gamma; const float* beta;
+  void* stats; int64_t stats_bytes;
+  int batches; int pixels; int channels; int groups;
+  float eps; int silu;
+  int x_dtype;                              /* DIT4SR_DT_BF16 / DIT4SR_DT_F32 (strides in elements of that type) */
+} dit4sr_groupnorm_params;
+int dit4sr_groupnorm_nhwc(const dit4sr_groupnorm_params* p, void* stream);
+int64_t dit4sr_groupnorm_workspace_bytes(int batches, int groups);
+/* y[b, 2h, 2w, c] = x[b, h, w, c] nearest-neighbour repeat (Upsample2D before its 3x3 convolution); contiguous NHWC, x of
+ * x_dtype (DIT4SR_DT_*), y bf16 */
+int dit4sr_upsample2x_nhwc(const void* x, int x_dtype, void* y, int batches, int h, int w, int channels, void* stream);
+/* y[b, Y, X, (py*2+px)*C + c] = x[b, 2Y+py, 2X+px, c]: with it Downsample2D (pad (0,1,0,1), 3x3, stride 2) is a 2x2
+ * stride-1 convolution over 4C channels (conv_kw 2, conv_taps 4, conv_org 0; weights repacked by the host) */
+int dit4sr_space_to_depth2_nhwc(const void* x, int x_dtype, void* y, int batches, int h, int w, int channels, void* stream);
+/* p[r, :] = softmax(scale * s[r, :]) for fp32 score rows -> bf16 probabilities (the mid-block's single-head attention
+ * with head_dim = channels: scores and P.V are plain GEMMs) */
+int dit4sr_softmax_rows_to_bf16(const float* s, int64_t lds, void* p, int64_t ldp, int rows, int cols, float scale, void* stream);
+/* NCHW (x_dtype DIT4SR_DT_*) [batches, channels, hw] -> NHWC bf16 [batches, hw, c_pad] (channels >= `channels` zero),
+ * y = a x + b on the way (latents: a = 1 / scaling_factor, b = shift_factor) */
+int dit4sr_nchw_to_nhwc_bf16(const void* x, int x_dtype, void* y, int batches, int channels, int c_pad, int64_t hw, float a,
+                             float b, void* stream);
+/* fp32 [batches, hw, ld] (first `channels` columns) -> NCHW fp32 [batches, channels, hw] */
+int dit4sr_nhwc_to_nchw_f32(const float* x, int64_t ld, float* y, int batches, int channels, int64_t hw, void* stream);
 
 #ifdef __cplusplus
 }

@@ -26,7 +26,7 @@ def test_header_symbols_all_exported(lib):
     assert declared == set(_lib.SYMBOLS), declared ^ set(_lib.SYMBOLS)
     for name in declared:
         assert hasattr(lib, name)
-    assert lib.dit4sr_abi_version() == 3
+    assert lib.dit4sr_abi_version() == 4
 
 
 def test_bad_arguments_are_rejected_without_a_gpu(lib):
@@ -182,7 +182,8 @@ def test_every_entry_point_rejects_null_arguments_with_a_message(lib):
     for name, (_, args) in _lib.SYMBOLS.items():
         if name in ("dit4sr_abi_version", "dit4sr_last_error", "dit4sr_check_device",
                     "dit4sr_peer_free", "dit4sr_peer_close",       # free(NULL) / close(NULL) are no-ops by design
-                    "dit4sr_attn_workspace_bytes"):                # a size query without arguments
+                    "dit4sr_attn_workspace_bytes",                 # a size query without arguments
+                    "dit4sr_groupnorm_workspace_bytes"):           # a size query (0 for non-positive sizes)
             continue
         vals = [0 if a in (ctypes.c_int, ctypes.c_int64, ctypes.c_size_t) else (0.0 if a is ctypes.c_float else None) for a in args]
         rc = getattr(lib, name)(*vals)
