@@ -72,3 +72,33 @@ def denoise(model, latents, controlnet_image, encoder_hidden_states, pooled_proj
     if sp is not None:
         x = sp.gather_rows(x, dim=2)
     return x.to(latents.dtype)
+
+
+@torch.no_grad()
+def super_resolve(model, vae, lr_image, encoder_hidden_states, pooled_projections, num_inference_steps=40, generator=None,
+                  latents=None, guidance_scale: float = 1.0, negative_prompt_embeds=None,
+                  negative_pooled_prompt_embeds=None, start_point: str = "noise", sample_posterior: bool = True,
+                  output_type: str = "pt"):
+    """The image path of the reference's pipeline call around the loop (pipelines/pipeline_dit4sr.py:1001-1002, 1004-1034,
+    1561-1567, 1602-1605), every stage on the CUDA library:
+        control = (vae.encode(lr_image).latent_dist.sample() - shift_factor) * scaling_factor
+        latents = 40-step flow-match Euler loop of the model (`denoise`)
+        image   = vae.decode(latents / scaling_factor + shift_factor); postprocess: (image / 2 + 0.5).clamp(0, 1)
+    lr_image: [B, 3, H, W] in [-1, 1] (what prepare_image / VaeImageProcessor.preprocess hand over), H and W multiples
+    of 16.  latents: optional start noise [B, 16, H/8, W/8] (drawn from `generator` otherwise).  output_type "pt" returns
+    the image tensor in [0, 1], "latent" the final latents (pipeline_dit4sr.py:1598-1599)."""
+    cfg = vae.config
+    post = vae.encode(lr_image).latent_dist
+    control = post.sample(generator=generator) if sample_posterior else post.mode()
+    control = (control.float() - cfg.shift_factor) * cfg.scaling_factor
+    dt = model.dtype
+    if latents is None:
+        latents = torch.randn(control.shape, generator=generator, device=control.device, dtype=torch.float32)
+    final = denoise(model, latents.to(dt), control.to(dt), encoder_hidden_states, pooled_projections,
+                    num_inference_steps=num_inference_steps, guidance_scale=guidance_scale,
+                    negative_prompt_embeds=negative_prompt_embeds, negative_pooled_prompt_embeds=negative_pooled_prompt_embeds,
+                    start_point=start_point)
+    if output_type == "latent":
+        return final
+    image = vae.decode(final.float() / cfg.scaling_factor + cfg.shift_factor, return_dict=False)[0]
+    return (image / 2 + 0.5).clamp(0, 1)

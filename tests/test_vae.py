@@ -264,3 +264,35 @@ def test_vae_round_trip_is_deterministic_and_roundtrips_through_save(tmp_path):
     a = m.decode(z).sample
     assert torch.equal(a, m.decode(z).sample) and torch.equal(a, m2.decode(z).sample)
     assert m(torch.rand(1, 3, 64, 64, device="cuda")).sample.shape == (1, 3, 64, 64)
+
+
+@pytest.mark.gpu
+def test_super_resolve_image_path_against_the_oracle():
+    """LR image -> VAE encode -> 8-step loop of a 4-block full-width model -> VAE decode -> [0, 1] image, every stage on
+    the CUDA library, against the same chain of CPU oracles (posterior mode instead of a sample so that both sides see the
+    same control latent).  PSNR of the final image >= 35 dB (bf16 through two VAE passes and 8 denoiser calls)."""
+    import dit4sr_b200
+    from dit4sr_b200.sampler import super_resolve
+    from oracle import dit4sr_oracle as O
+    torch.manual_seed(0)
+    vcfg = VO.sd3_vae_config()
+    vae, vsd = _build(vcfg, seed=0)
+    cfg = O.sd35_medium_config(num_layers=4, dual_attention_layers=(0, 1), pos_embed_max_size=96)
+    sd = O.init_state_dict(cfg, seed=0)
+    m = dit4sr_b200.SD3Transformer2DModel(**vars(cfg))
+    m.load_state_dict(sd)
+    m = m.to("cuda", torch.bfloat16).eval()
+    lr_img = torch.rand(1, 3, 128, 128) * 2 - 1
+    noise, _, enc, pooled, _ = O.make_inputs(cfg, 1, 16, 16, 77, seed=1)
+    bf = torch.bfloat16
+    img = super_resolve(m, vae, lr_img.cuda(), enc.cuda().to(bf), pooled.cuda().to(bf), num_inference_steps=8,
+                        latents=noise.cuda(), sample_posterior=False).float().cpu()
+    with torch.no_grad():
+        control = VO.encode_latents(vsd, vcfg, lr_img)
+        final = O.sample_loop(sd, cfg, noise, control, enc, pooled, num_steps=8)
+        ref = (VO.decode_latents(vsd, vcfg, final) / 2 + 0.5).clamp(0, 1)
+    assert img.shape == ref.shape == (1, 3, 128, 128)
+    mse = ((img - ref) ** 2).mean().item()
+    psnr = 10 * math.log10(1.0 / mse)
+    print(f"super_resolve image PSNR vs the oracle chain: {psnr:.1f} dB")
+    assert psnr >= 35.0
