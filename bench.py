@@ -125,7 +125,7 @@ def attention_roofline(launch_ms, flops_per_step, launches_per_step, peaks, root
                "launch (S=2381, B=8; algorithmic 263 MB q|k|v read + 59 MB o written + 50 MB LR residual read)")
     except (OSError, KeyError, ValueError, StopIteration):
         pass
-    return dict(bound="tensor", kernel="attn_fwd4_kernel / attn_fwd2_kernel (joint attention over [HQ|LR|text] and the image-only attn2, "
+    return dict(bound="tensor", kernel="attn_fwd5_kernel (joint attention over [HQ|LR|text] and the image-only attn2, "
                 "head_dim 64; the largest share of the step: MUFU.EX2 / issue limited, DESIGN.md 3.2)", achieved=round(ach, 1),
                 peak=peaks["tf_sustained"], unit="TFLOP/s", frac=round(ach / peaks["tf_sustained"], 4),
                 peak_source=peaks["source"] + ", sustained figure (kernel timed inside a long step)",
