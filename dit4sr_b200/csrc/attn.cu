@@ -1434,22 +1434,33 @@ static int make_plan(const dit4sr_attn_params* p, int sms, Plan* out) {
   // slices (second launch) whose partial rows a small merge kernel combines (v3 / v4, needs workspace).
     const int tiles96 = (p->seq_kv + v3::BKV - 1) / v3::BKV;
   const int pad96 = tiles96 * v3::BKV, pad128 = (p->seq_kv + 127) / 128 * 128;
-  auto plan = [&](int rows_per_item, int slots, bool can_split, int* items_out, int* split_out, int* n_full_out) {
+  // Cost of the last, partly filled wave in item-lengths (fitted to kbench, profiles/r02_attn_split_c2.log):
+  //  * two-CTAs-per-SM kernels (v4 / v5): a tail of at most one item per SM runs alone on its SM at ~0.65 of the shared
+  //    step time, so an unsplit short tail is cheaper than a full wave;
+  //  * splitting costs two more launches (sliced kernel + merge, ~18 us with their ramps), which only long items amortise:
+  //    at C2 (25 KV steps, 22 us per item) the split tail measured 5 % SLOWER (0.314 vs 0.298 ms), at the C4 per-rank shape
+  //    (345 steps) 6 % faster.
+  auto plan = [&](int rows_per_item, int slots, bool can_split, double item_us, int* items_out, int* split_out,
+                  int* n_full_out) {
     const int64_t items64 = (int64_t)((p->seq_q + rows_per_item - 1) / rows_per_item) * p->heads * p->batches;
     const int items = (int)(items64 < (1ll << 30) ? items64 : (1ll << 30));
     int split = 1, n_full = items;
     const int tail = items % slots;
-    double tail_cost = tail > 0 ? 1.0 : 0.0;
+    const bool two_per_sm = slots == 2 * sms;
+    auto speed = [&](int ctas) { return two_per_sm && ctas <= sms ? 0.65 : 1.0; };
+    double tail_cost = tail > 0 ? speed(tail) : 0.0;
     if (can_split && tail > 0 && p->workspace != nullptr && p->workspace_bytes >= attn::workspace_bytes(sms) &&
         p->split_kv >= 0) {
+      const double fixed = 18.0 / item_us;
       for (int sdiv = 2; sdiv <= 4; ++sdiv) {
         if (tiles96 / sdiv < 4) break;                                   // keep slices long enough to amortise a prologue
-        const double c = (double)((tail * sdiv + slots - 1) / slots) / sdiv + 0.03 * (sdiv - 1);
+        const int n = tail * sdiv;
+        const double c = (double)((n + slots - 1) / slots) / sdiv * speed(n) + fixed + 0.03 * (sdiv - 1);
         if (c < tail_cost - 1e-9) { tail_cost = c; split = sdiv; }
       }
       if (p->split_kv > 0 && tiles96 / p->split_kv >= 1) {               // forced (tests / A-B)
         split = p->split_kv > 4 ? 4 : p->split_kv;
-        tail_cost = (double)((tail * split + slots - 1) / slots) / split;
+        tail_cost = (double)((tail * split + slots - 1) / slots) / split + fixed;
       }
       if (split > 1) n_full = items - tail;
     }
@@ -1457,9 +1468,9 @@ static int make_plan(const dit4sr_attn_params* p, int sms, Plan* out) {
     return (double)(items / slots) + tail_cost;                          // waves of item-lengths
   };
   int items2, split2, nf2, items3, split3, nf3, items4, split4, nf4;
-  const double waves2 = plan(2 * BQ, sms, false, &items2, &split2, &nf2);
-  const double waves3 = plan(2 * BQ, sms, true, &items3, &split3, &nf3);
-  const double waves4 = plan(BQ, 2 * sms, true, &items4, &split4, &nf4);
+  const double waves2 = plan(2 * BQ, sms, false, 1.0, &items2, &split2, &nf2);
+  const double waves3 = plan(2 * BQ, sms, true, (tiles96 + 7.5) * 0.848, &items3, &split3, &nf3);
+  const double waves4 = plan(BQ, 2 * sms, true, (tiles96 + 2.3) * 0.888, &items4, &split4, &nf4);
   DIT4SR_REQUIRE(items4 < (1 << 30), DIT4SR_E_SHAPE, "attn: too many work items");
   // default kernel: the cheapest under a cost model fitted to kbench timings on B200 (profiles/r02_attn_v4.log):
   //   time ~ waves x (KV steps + fixed per-CTA overhead in steps) x time per step

@@ -172,6 +172,142 @@ ln_modulate_tma_kernel(const dit4sr_ln_modulate_params p) {
   }
 }
 
+// Second form of the TMA-staged kernel (default since round 2b).  ncu of the first form (profiles/r02b_ncu_full.json): DRAM
+// 45 % busy with l1tex at 61 %: per 6 KB row the SM moved 6 KB (TMA fill) + 12 KB (row read back with 32-byte lane stride:
+// two-way bank conflicts) + 12 KB (scale / shift re-read from L1 for EVERY row) + 3 KB (stores) through its L1.  Here
+//  * a lane owns float4 number i*32 + lane of the row (conflict-free 16-byte shared-memory reads, coalesced 8-byte stores),
+//  * the single-output instance keeps (1 + scale) and shift of the CURRENT batch in registers (96 per lane for dim 1536)
+//    and reloads them only when a row of another batch arrives (rows are visited in batch order), so the steady state
+//    touches L1 for the row itself only.  The dual-output instance has no registers left for that and reads the four
+//    vectors per row as before (coalesced).
+template <int NV, bool DUAL>  // NV float4 per lane => dim = NV * 128
+__global__ void __launch_bounds__(LN_WARPS * 32, 1)
+ln_modulate_tma2_kernel(const dit4sr_ln_modulate_params p) {
+  extern __shared__ uint8_t ln_smem_raw[];
+  constexpr int ROW_BYTES = NV * 128 * 4;
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(ln_smem_raw) + 127) & ~uintptr_t(127));
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  uint8_t* slots = smem + (size_t)warp * LN_STAGES * ROW_BYTES;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)LN_WARPS * LN_STAGES * ROW_BYTES) + warp * LN_STAGES;
+  const int64_t total = (int64_t)p.batches * p.rows;
+  const int64_t nwarps = (int64_t)gridDim.x * LN_WARPS;
+  const int64_t first = (int64_t)blockIdx.x * LN_WARPS + warp;
+  auto row_ptr = [&](int64_t rid) {
+    const int b = (int)(rid / p.rows);
+    const int r = (int)(rid % p.rows);
+    return p.x + (int64_t)b * p.x_batch_stride + (int64_t)r * p.ldx;
+  };
+  if (lane == 0) {
+    for (int s = 0; s < LN_STAGES; ++s) ptx::mbar_init(&bars[s], 1);
+    ptx::fence_barrier_init();
+  }
+  ptx::pdl_wait();
+  ptx::pdl_launch_dependents();
+  if (lane == 0) {
+    for (int s = 0; s < LN_STAGES; ++s) {
+      const int64_t rid = first + s * nwarps;
+      if (rid < total) {
+        ptx::mbar_expect_tx(&bars[s], ROW_BYTES);
+        ptx::bulk_load(slots + s * ROW_BYTES, row_ptr(rid), ROW_BYTES, &bars[s]);
+      }
+    }
+  }
+  __syncwarp();
+  const float inv_dim = 1.0f / (float)(NV * 128);
+  float4 ca[DUAL ? 1 : NV], ct[DUAL ? 1 : NV];   // (1 + scale), shift of batch `cached_b` (single-output instance)
+  int cached_b = -1;
+  int k = 0;
+  for (int64_t rid = first; rid < total; rid += nwarps, ++k) {
+    const int s = k % LN_STAGES;
+    const int b = (int)(rid / p.rows);
+    const int r = (int)(rid % p.rows);
+    if constexpr (!DUAL) {
+      if (b != cached_b) {
+        const float4* sh = reinterpret_cast<const float4*>(p.shift + (int64_t)b * p.mod_batch_stride) + lane;
+        const float4* sc = reinterpret_cast<const float4*>(p.scale + (int64_t)b * p.mod_batch_stride) + lane;
+#pragma unroll
+        for (int i = 0; i < NV; ++i) {
+          const float4 a = __ldg(sc + i * 32);
+          ca[i] = make_float4(1.f + a.x, 1.f + a.y, 1.f + a.z, 1.f + a.w);
+          ct[i] = __ldg(sh + i * 32);
+        }
+        cached_b = b;
+      }
+    }
+    ptx::mbar_wait(&bars[s], (k / LN_STAGES) & 1);
+    const float4* src = reinterpret_cast<const float4*>(slots + s * ROW_BYTES) + lane;
+    float4 v[NV];
+#pragma unroll
+    for (int i = 0; i < NV; ++i) v[i] = src[i * 32];
+    __syncwarp();
+    if (lane == 0) {   // refill the slot with the row LN_STAGES ahead
+      const int64_t nrid = rid + (int64_t)LN_STAGES * nwarps;
+      if (nrid < total) {
+        ptx::mbar_expect_tx(&bars[s], ROW_BYTES);
+        ptx::bulk_load(slots + s * ROW_BYTES, row_ptr(nrid), ROW_BYTES, &bars[s]);
+      }
+    }
+    // one-pass statistics in packed fp32x2 (see the first form)
+    uint64_t s2[2] = {ptx::pack2(0.f, 0.f), ptx::pack2(0.f, 0.f)}, q2[2] = {s2[0], s2[0]};
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      const uint64_t lo = ptx::pack2(v[i].x, v[i].y), hi = ptx::pack2(v[i].z, v[i].w);
+      s2[0] = ptx::add2(s2[0], lo);
+      s2[1] = ptx::add2(s2[1], hi);
+      q2[0] = ptx::fma2(lo, lo, q2[0]);
+      q2[1] = ptx::fma2(hi, hi, q2[1]);
+    }
+    float sa, sb, qa, qb;
+    ptx::unpack2(ptx::add2(s2[0], s2[1]), sa, sb);
+    ptx::unpack2(ptx::add2(q2[0], q2[1]), qa, qb);
+    float sum = sa + sb, sq = qa + qb;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      sum += __shfl_xor_sync(0xffffffffu, sum, o);
+      sq += __shfl_xor_sync(0xffffffffu, sq, o);
+    }
+    const float mean = sum * inv_dim;
+    const float rstd = rsqrtf(fmaxf(sq * inv_dim - mean * mean, 0.f) + p.eps);
+    const uint64_t rstd2 = ptx::pack2(rstd, rstd), nmean2 = ptx::pack2(-mean, -mean);
+    // out = (x - mean) rstd (1 + s) + t = x a + (t - mean a),  a = rstd (1 + s)
+    auto mod2 = [&](float x0, float x1, uint64_t a1_2, float t0, float t1) {
+      uint64_t a2;
+      asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(a2) : "l"(a1_2), "l"(rstd2));
+      const uint64_t c2 = ptx::fma2(nmean2, a2, ptx::pack2(t0, t1));
+      float o0, o1;
+      ptx::unpack2(ptx::fma2(ptx::pack2(x0, x1), a2, c2), o0, o1);
+      return ptx::pack_bf16(o0, o1);
+    };
+    if constexpr (!DUAL) {
+      uint2* out = reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(p.out) + (int64_t)b * p.o_batch_stride +
+                                            (int64_t)r * p.ldo) + lane;
+#pragma unroll
+      for (int i = 0; i < NV; ++i) {
+        uint2 o;
+        o.x = mod2(v[i].x, v[i].y, ptx::pack2(ca[i].x, ca[i].y), ct[i].x, ct[i].y);
+        o.y = mod2(v[i].z, v[i].w, ptx::pack2(ca[i].z, ca[i].w), ct[i].z, ct[i].w);
+        out[i * 32] = o;
+      }
+    } else {
+#pragma unroll
+      for (int which = 0; which < 2; ++which) {
+        const float4* sh = reinterpret_cast<const float4*>((which ? p.shift2 : p.shift) + (int64_t)b * p.mod_batch_stride) + lane;
+        const float4* sc = reinterpret_cast<const float4*>((which ? p.scale2 : p.scale) + (int64_t)b * p.mod_batch_stride) + lane;
+        uint2* out = reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(which ? p.out2 : p.out) +
+                                              (int64_t)b * p.o_batch_stride + (int64_t)r * p.ldo) + lane;
+#pragma unroll
+        for (int i = 0; i < NV; ++i) {
+          const float4 a = __ldg(sc + i * 32), t = __ldg(sh + i * 32);
+          uint2 o;
+          o.x = mod2(v[i].x, v[i].y, ptx::pack2(1.f + a.x, 1.f + a.y), t.x, t.y);
+          o.y = mod2(v[i].z, v[i].w, ptx::pack2(1.f + a.z, 1.f + a.w), t.z, t.w);
+          out[i * 32] = o;
+        }
+      }
+    }
+  }
+}
+
 // W warps per CTA; ONEPASS: sum and sum of squares reduced together (one shuffle tree instead of two in sequence)
 template <int NV, bool DUAL, int W, bool ONEPASS>  // NV float4 per lane => dim = NV * 128
 __global__ void __launch_bounds__(W * 32)
@@ -261,12 +397,31 @@ static int launch(const dit4sr_ln_modulate_params& p, cudaStream_t stream) {
   static int variant = -1;   // developer switch DIT4SR_LN_VARIANT: warps per CTA (4|8) + 10 for one-pass statistics
   if (variant < 0) {
     const char* e = getenv("DIT4SR_LN_VARIANT");
-    variant = e ? atoi(e) : 8;   // 8 = TMA-staged kernel (default); 1 = register kernel, 8 warps
+    variant = e ? atoi(e) : 9;   // 9 = TMA-staged kernel, second form (default); 8 = first form; 1 = register kernel
+  }
+  {
+    constexpr int SMEM2 = LN_WARPS * LN_STAGES * NV * 128 * 4 + LN_WARPS * LN_STAGES * 8 + 128;
+    if (!p.out_f32 && variant == 9 && SMEM2 <= 220 * 1024 && (reinterpret_cast<uintptr_t>(p.out) & 7) == 0 &&
+        p.ldo % 4 == 0 && p.o_batch_stride % 4 == 0 && (p.out2 == nullptr || (reinterpret_cast<uintptr_t>(p.out2) & 7) == 0)) {
+      static unsigned long long configured2 = 0;   // per (instance, device)
+      if (host::first_use_on_device(&configured2)) {
+        DIT4SR_CUDA(cudaFuncSetAttribute(ln_modulate_tma2_kernel<NV, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM2));
+        DIT4SR_CUDA(cudaFuncSetAttribute(ln_modulate_tma2_kernel<NV, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM2));
+      }
+      unsigned grid = (unsigned)((total + LN_WARPS - 1) / LN_WARPS);
+      const unsigned sms = (unsigned)host::sm_count();
+      if (grid > sms) grid = sms;
+      if (p.out2 != nullptr)
+        DIT4SR_CUDA(host::launch_pdl(ln_modulate_tma2_kernel<NV, true>, dim3(grid), dim3(LN_WARPS * 32), (size_t)SMEM2, stream, p));
+      else
+        DIT4SR_CUDA(host::launch_pdl(ln_modulate_tma2_kernel<NV, false>, dim3(grid), dim3(LN_WARPS * 32), (size_t)SMEM2, stream, p));
+      return 0;
+    }
   }
   if constexpr (NV % 2 == 0) {
     constexpr int SMEM = LN_WARPS * LN_STAGES * NV * 128 * 4 + LN_WARPS * LN_STAGES * 8 + 128;
-    if (!p.out_f32 && variant == 8 && SMEM <= 220 * 1024 && (reinterpret_cast<uintptr_t>(p.out) & 15) == 0 &&
-        p.ldo % 8 == 0 && p.o_batch_stride % 8 == 0 &&
+    if (!p.out_f32 && (variant == 8 || variant == 9) && SMEM <= 220 * 1024 && (reinterpret_cast<uintptr_t>(p.out) & 15) == 0 &&
+        p.ldo % 8 == 0 && p.o_batch_stride % 8 == 0 && (variant == 8 || variant == 9) &&
         (p.out2 == nullptr || (reinterpret_cast<uintptr_t>(p.out2) & 15) == 0)) {
       static unsigned long long configured = 0;   // per (instance, device)
       if (host::first_use_on_device(&configured)) {

@@ -194,12 +194,14 @@ def test_every_entry_point_rejects_null_arguments_with_a_message(lib):
 def test_attention_work_decomposition_without_a_gpu():
     """dit4sr_attn_plan (host only): kernel choice and the split-KV tail for the shapes of BASELINE's configs on 148 SMs."""
     from dit4sr_b200 import ops
-    # C2 joint attention: 3648 query tiles on 296 slots = 12.32 waves: v4, the 96 tail tiles run as 3 KV slices (288 CTAs)
+    # C2 joint attention: 3648 query tiles on 296 slots = 12.32 waves: v4; the 96 tail tiles are NOT sliced: they run one
+    # per SM at single-CTA speed, and two extra launches cost more than a third of a 22 us item (measured: 0.298 vs 0.314 ms)
     v, split, whole, tail, tiles, tps = ops.attention_plan(8, 24, 2381, 2381)
-    assert (v, split, whole, tail) == (4, 3, 12 * 296, 96) and tiles == 25 and tps == 9
+    assert (v, split, whole, tail) == (4, 1, 19 * 24 * 8, 0) and tiles == 25 and tps == 25
     assert ops.attention_plan(8, 24, 2381, 2381, workspace=False)[:4] == (4, 1, 19 * 24 * 8, 0)
+    assert ops.attention_plan(8, 24, 2381, 2381, split_kv=3)[:4] == (4, 3, 12 * 296, 96)          # forced
     # pre-scaled scores: same decomposition on the split-row form (5); an explicit 5 without pre-scaled scores runs as 4
-    assert ops.attention_plan(8, 24, 2381, 2381, prescaled=True)[:4] == (5, 3, 12 * 296, 96)
+    assert ops.attention_plan(8, 24, 2381, 2381, prescaled=True)[:4] == (5, 1, 19 * 24 * 8, 0)
     assert ops.attention_plan(8, 24, 2381, 2381, variant=5)[0] == 4
     # C4 on 8 ranks: 3 heads over S = 33101: 390 pair items on 148 SMs = 2.64 waves -> v3, 94 tail items in 3 KV slices
     v, split, whole, tail, tiles, tps = ops.attention_plan(1, 3, 33101, 33101)

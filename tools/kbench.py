@@ -59,6 +59,8 @@ def main():
     if a.shape == "c4rank":      # what one of 8 ranks runs under Ulysses at 2048px: 3 heads over the whole sequence
         B, N, T, D, H = 1, 16384, 333, 192, 3
     S = 2 * N + T
+    if a.shape == "attn2":       # the image-only second attention of the dual blocks at C2
+        S, T = 2 * N, 0
     dev = "cuda"
     torch.manual_seed(0)
     if a.what == "attn":
@@ -68,6 +70,7 @@ def main():
         qkv = qkv.bfloat16()
         o = torch.empty(B, S, D, device=dev, dtype=torch.bfloat16)
         res = torch.randn(B, 2 * N, D, device=dev).bfloat16()
+        last = ops.attention_last_plan
         wsp = torch.empty(ops.attention_workspace_bytes(), device=dev, dtype=torch.uint8) if a.split >= 0 else None
         fn = lambda: ops.attention(qkv[..., :D], qkv[..., D:2 * D], qkv[..., 2 * D:], o, H, lr_res=res, lr_rows=(N, 2 * N),
                                    score_bound=30.0 if a.prescaled else None, exp_offload=a.exp_offload, variant=a.variant,
@@ -93,7 +96,7 @@ def main():
             cap = sum(r[2].lower().startswith("active") for r in rows)
             print(f"  sustained {n} launches: {e0.elapsed_time(e1) / n:.4f} ms  {fl * n / e0.elapsed_time(e1) / 1e9:.1f} TFLOP/s; "
                   f"median {mhz[len(mhz) // 2]:.0f} MHz, {watts[len(watts) // 2]:.0f} W, power-cap active in {cap}/{len(rows)} samples")
-        print(f"attn B={B} S={S} prescaled={a.prescaled} exp_offload={a.exp_offload} variant={a.variant} split={a.split}: {ms:.4f} ms  {fl / ms / 1e9:.1f} TFLOP/s")
+        print(f"attn B={B} S={S} prescaled={a.prescaled} exp_offload={a.exp_offload} variant={a.variant} split={a.split}: {ms:.4f} ms  {fl / ms / 1e9:.1f} TFLOP/s  plan {last()}")
     elif a.what == "gemm":
         for name, M, K, Nn, epi in [("ff1", B * 2 * N, D, F, ops.EPI_BIAS_GELU), ("ff2", B * 2 * N, F, D, ops.EPI_GATE_RESID),
                                     ("qkv", B * N, D, 3 * D, ops.EPI_QKV_NORM), ("out", B * N, D, D, ops.EPI_GATE_RESID)]:
