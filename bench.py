@@ -422,22 +422,48 @@ def run_ours(args):
     hout = torch.empty(B, 16, side, side, dtype=bf).pin_memory()
     e2e_velocity = {}
 
-    def e2e_step():
+    # Input pipeline of the e2e loop: every step's inputs are copied from pinned host memory inside the timed region, on a
+    # copy stream into one of two device slots, so that step i+1's 24 MB ride under step i's kernels (what a serving loop
+    # does); the forward waits for its slot's copy, the copy waits for the forward that last read the slot.
+    hosts = (hx, hc, he, hp, ht)
+    dslots = [tuple(torch.empty(h.shape, device=dev, dtype=h.dtype) for h in hosts) for _ in range(2)]
+    copy_stream = torch.cuda.Stream(device=dev)
+    ready = [torch.cuda.Event() for _ in range(2)]
+    consumed = [torch.cuda.Event() for _ in range(2)]
+
+    def e2e_prefetch(i):
+        sl = i & 1
+        with torch.cuda.stream(copy_stream):
+            copy_stream.wait_event(consumed[sl])
+            for d, h in zip(dslots[sl], hosts):
+                d.copy_(h, non_blocking=True)
+            ready[sl].record(copy_stream)
+
+    def e2e_step(i, last):
+        sl = i & 1
+        cur = torch.cuda.current_stream()
+        cur.wait_event(ready[sl])
+        if not last:
+            e2e_prefetch(i + 1)
+        dx, dc, de, dp, dt = dslots[sl]
         with torch.no_grad():
-            v = model(hidden_states=hx.to(dev, non_blocking=True), controlnet_image=hc.to(dev, non_blocking=True),
-                      encoder_hidden_states=he.to(dev, non_blocking=True),
-                      pooled_projections=hp.to(dev, non_blocking=True), timestep=ht.to(dev, non_blocking=True),
+            v = model(hidden_states=dx, controlnet_image=dc, encoder_hidden_states=de, pooled_projections=dp, timestep=dt,
                       return_dict=False)[0]
+        consumed[sl].record(cur)
         hout.copy_(v, non_blocking=True)
         e2e_velocity["v"] = v
 
-    for _ in range(max(1, args.warmup)):
-        e2e_step()
+    nw = max(1, args.warmup)
+    e2e_prefetch(0)
+    for i in range(nw):
+        e2e_step(i, i + 1 == nw)
     barrier()
     f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     f0.record()
-    for _ in range(args.steps):
-        e2e_step()
+    copy_stream.wait_event(f0)          # the first copy of the timed region starts inside it
+    e2e_prefetch(nw)
+    for i in range(nw, nw + args.steps):
+        e2e_step(i, i + 1 == nw + args.steps)
     f1.record()
     barrier()
     e2e_ms = f0.elapsed_time(f1)
@@ -537,7 +563,7 @@ def run_ours(args):
             step_frac_of_sustained_peak=round(step_flops / (ms / args.steps / 1e3) / 1e12 / peaks["tf_sustained"], 4),
             e2e=dict(value=round(img_steps / (e2e_ms / 1e3), 3), unit=UNIT, h2d_bytes_per_step=h2d,
                      d2h_bytes_per_step=d2h, ms_per_step=round(e2e_ms / args.steps, 3),
-                     api="dit4sr_b200.SD3Transformer2DModel.forward, pinned host inputs, velocity copied back"),
+                     api="dit4sr_b200.SD3Transformer2DModel.forward; every step copies its inputs from pinned host memory (double-buffered on a copy stream, one step ahead) and reads the velocity back"),
             gpu_launches=launches, clocks=clocks, roofline=roof_attn, roofline_gemm=roof, cpu_baseline=cpu,
             parity=parity, kernel_breakdown_ms=breakdown, north_star_scaling=ns,
         )
