@@ -37,7 +37,7 @@ class GemmParams(C.Structure):
                 ("resid", c_vp), ("ldr", c_i64), ("r_batch_stride", c_i64),
                 ("norm_w0", c_vp), ("norm_w1", c_vp), ("sec_cols", c_int), ("eps", c_float),
                 ("dbl_row_offset", c_i64), ("sp", C.POINTER(GemmSp)),
-                ("conv_w", c_int), ("conv_h", c_int), ("conv_kw", c_int), ("conv_taps", c_int), ("conv_org", c_int),
+                ("conv_w", c_int), ("conv_h", c_int), ("conv_kw", c_int), ("conv_taps", c_int), ("conv_org", c_int), ("conv_w_valid", c_int),
                 ("resid_bf16", c_vp), ("ld_rb", c_i64), ("rb_batch_stride", c_i64)]
 
 
@@ -45,7 +45,7 @@ class GroupNormParams(C.Structure):
     _fields_ = [("x", c_vp), ("ldx", c_i64), ("x_batch_stride", c_i64), ("y", c_vp), ("ldy", c_i64), ("y_batch_stride", c_i64),
                 ("gamma", c_vp), ("beta", c_vp), ("stats", c_vp), ("stats_bytes", c_i64),
                 ("batches", c_int), ("pixels", c_int), ("channels", c_int), ("groups", c_int), ("eps", c_float), ("silu", c_int),
-                ("x_dtype", c_int)]
+                ("x_dtype", c_int), ("width", c_int), ("pitch", c_int)]
 
 
 SP_MAX_RANKS, SP_CHANNELS = 8, 4
@@ -120,11 +120,11 @@ SYMBOLS = {
     "dit4sr_cast": (c_int, [c_vp, c_vp, c_i64, c_int, c_vp]),
     "dit4sr_groupnorm_nhwc": (c_int, [C.POINTER(GroupNormParams), c_vp]),
     "dit4sr_groupnorm_workspace_bytes": (c_i64, [c_int, c_int]),
-    "dit4sr_upsample2x_nhwc": (c_int, [c_vp, c_int, c_vp, c_int, c_int, c_int, c_int, c_vp]),
-    "dit4sr_space_to_depth2_nhwc": (c_int, [c_vp, c_int, c_vp, c_int, c_int, c_int, c_int, c_vp]),
-    "dit4sr_softmax_rows_to_bf16": (c_int, [c_vp, c_i64, c_vp, c_i64, c_int, c_int, c_float, c_vp]),
-    "dit4sr_nchw_to_nhwc_bf16": (c_int, [c_vp, c_int, c_vp, c_int, c_int, c_int, c_i64, c_float, c_float, c_vp]),
-    "dit4sr_nhwc_to_nchw_f32": (c_int, [c_vp, c_i64, c_vp, c_int, c_int, c_i64, c_vp]),
+    "dit4sr_upsample2x_nhwc": (c_int, [c_vp, c_int, c_vp, c_int, c_int, c_int, c_int, c_int, c_int, c_vp]),
+    "dit4sr_space_to_depth2_nhwc": (c_int, [c_vp, c_int, c_vp, c_int, c_int, c_int, c_int, c_int, c_int, c_vp]),
+    "dit4sr_softmax_rows_to_bf16": (c_int, [c_vp, c_i64, c_vp, c_i64, c_int, c_int, c_int, c_float, c_vp]),
+    "dit4sr_nchw_to_nhwc_bf16": (c_int, [c_vp, c_int, c_vp, c_int, c_int, c_int, c_int, c_int, c_int, c_float, c_float, c_vp]),
+    "dit4sr_nhwc_to_nchw_f32": (c_int, [c_vp, c_i64, c_vp, c_int, c_int, c_int, c_int, c_int, c_vp]),
     "dit4sr_peer_alloc": (c_int, [C.c_size_t, C.POINTER(c_vp)]),
     "dit4sr_peer_free": (c_int, [c_vp]),
     "dit4sr_peer_export": (c_int, [c_vp, C.c_char_p]),

@@ -689,7 +689,8 @@ static int check_problem(const dit4sr_gemm_params* p, int epilogue) {
   if (p->conv_w != 0) {
     DIT4SR_REQUIRE(p->conv_w > 0 && p->conv_h > 0 && p->conv_kw > 0 && p->conv_taps > 0 && p->conv_taps <= 16 &&
                        p->K % p->conv_taps == 0 && (p->K / p->conv_taps) % BK == 0 &&
-                       p->rows == p->conv_w * p->conv_h && (BM % p->conv_w == 0 || p->conv_w % BM == 0),
+                       p->rows == p->conv_w * p->conv_h && (BM % p->conv_w == 0 || p->conv_w % BM == 0) &&
+                       p->conv_w_valid >= 0 && p->conv_w_valid <= p->conv_w,
                    DIT4SR_E_SHAPE, "gemm/conv: need rows == conv_h*conv_w, C_in = K/conv_taps a multiple of 64, conv_w "
                    "dividing 128 or a multiple of 128 (w %d h %d taps %d K %d rows %d)", p->conv_w, p->conv_h, p->conv_taps,
                    p->K, p->rows);
@@ -793,7 +794,8 @@ extern "C" int dit4sr_gemm_bf16_grouped(const dit4sr_gemm_params* probs, int cou
     const dit4sr_gemm_params* p = &probs[i];
     if (p->conv_w > 0) {   // NHWC image: (channels, x, y, batch); a box = 128 output pixels x 64 input channels
       const int bw = p->conv_w < BM ? p->conv_w : BM;
-      uint64_t dims[4] = {(uint64_t)(p->K / p->conv_taps), (uint64_t)p->conv_w, (uint64_t)p->conv_h, (uint64_t)p->batches};
+      const int wv = p->conv_w_valid > 0 ? p->conv_w_valid : p->conv_w;     // pitched image: the map clips at the real width
+      uint64_t dims[4] = {(uint64_t)(p->K / p->conv_taps), (uint64_t)wv, (uint64_t)p->conv_h, (uint64_t)p->batches};
       uint64_t strides[3] = {(uint64_t)p->lda * 2, (uint64_t)p->lda * 2 * p->conv_w,
                              (uint64_t)(p->batches > 1 ? p->a_batch_stride : (int64_t)p->rows * p->lda) * 2};
       uint32_t box[4] = {BK, (uint32_t)bw, (uint32_t)(BM / bw), 1};

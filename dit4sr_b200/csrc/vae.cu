@@ -45,8 +45,8 @@ constexpr int GN_MAX_CHUNKS = 256;
 
 template <typename T>
 __global__ void __launch_bounds__(THREADS)
-gn_stats_kernel(const T* __restrict__ x, int64_t ld, int64_t batch_stride, int pixels, int channels, int groups,
-                int pixels_per_cta, double* __restrict__ part) {
+gn_stats_kernel(const T* __restrict__ x, int64_t ld, int64_t batch_stride, int pixels, int width, int pitch, int channels,
+                int groups, int pixels_per_cta, double* __restrict__ part) {
   extern __shared__ float gn_sm[];   // [2][lanes][channels], then [2][channels]
   const int vecs = channels >> 3;
   const int lanes = THREADS / vecs;
@@ -64,6 +64,7 @@ gn_stats_kernel(const T* __restrict__ x, int64_t ld, int64_t batch_stride, int p
   if (pl < lanes) {
     const T* base = x + (int64_t)b * batch_stride + v * 8;
     for (int p = p0 + pl; p < p1; p += lanes) {
+      if (pitch != width && p % pitch >= width) continue;      // pad columns of a pitched image hold no data
       float f[8];
       load8(base + (int64_t)p * ld, f);
 #pragma unroll
@@ -121,12 +122,13 @@ __global__ void gn_finalize_kernel(const double* __restrict__ part, int chunks, 
 template <typename T>
 __global__ void __launch_bounds__(THREADS)
 gn_apply_kernel(const T* __restrict__ x, int64_t ldx, int64_t x_batch_stride, __nv_bfloat16* __restrict__ y,
-                int64_t ldy, int64_t y_batch_stride, int pixels, int channels, int groups, const double* __restrict__ stats,
-                const float* __restrict__ gamma, const float* __restrict__ beta, float eps, int silu) {
+                int64_t ldy, int64_t y_batch_stride, int pixels, int valid_pixels, int channels, int groups,
+                const double* __restrict__ stats, const float* __restrict__ gamma, const float* __restrict__ beta, float eps,
+                int silu) {
   const int vecs = channels >> 3;
   const int b = blockIdx.y;
   const int cpg = channels / groups;
-  const double inv_n = 1.0 / ((double)pixels * cpg);
+  const double inv_n = 1.0 / ((double)valid_pixels * cpg);
   const int64_t total = (int64_t)pixels * vecs;
   for (int64_t i = (int64_t)blockIdx.x * THREADS + threadIdx.x; i < total; i += (int64_t)gridDim.x * THREADS) {
     const int v = (int)(i % vecs);
@@ -154,19 +156,24 @@ gn_apply_kernel(const T* __restrict__ x, int64_t ldx, int64_t x_batch_stride, __
   }
 }
 
-// ---- nearest-neighbour 2x upsampling, NHWC bf16 (diffusers Upsample2D: F.interpolate(scale_factor=2.0, mode="nearest"))
+// Images may be PITCHED: row y of a (H x W) image starts at pixel y * pitch, pitch >= W (the implicit-GEMM convolution
+// needs a pitch that divides 128 or is a multiple of it); pad pixels hold no data and are written as zeros here.
+
+// ---- nearest-neighbour 2x upsampling, NHWC (diffusers Upsample2D: F.interpolate(scale_factor=2.0, mode="nearest"))
 template <typename T>
 __global__ void __launch_bounds__(THREADS)
-upsample2x_kernel(const T* __restrict__ x, uint4* __restrict__ y, int H, int W, int vecs, int64_t total) {
+upsample2x_kernel(const T* __restrict__ x, uint4* __restrict__ y, int H, int W, int pitch_in, int pitch_out, int vecs,
+                  int64_t total) {
   for (int64_t i = (int64_t)blockIdx.x * THREADS + threadIdx.x; i < total; i += (int64_t)gridDim.x * THREADS) {
     const int v = (int)(i % vecs);
     int64_t r = i / vecs;
-    const int ox = (int)(r % (2 * W));
-    r /= 2 * W;
+    const int ox = (int)(r % pitch_out);
+    r /= pitch_out;
     const int oy = (int)(r % (2 * H));
     const int64_t b = r / (2 * H);
+    if (ox >= 2 * W) { y[i] = make_uint4(0, 0, 0, 0); continue; }
     float f[8];
-    load8(x + (((b * H + (oy >> 1)) * W + (ox >> 1)) * vecs + v) * 8, f);
+    load8(x + (((b * H + (oy >> 1)) * pitch_in + (ox >> 1)) * vecs + v) * 8, f);
     y[i] = pack8(f);
   }
 }
@@ -174,34 +181,45 @@ upsample2x_kernel(const T* __restrict__ x, uint4* __restrict__ y, int H, int W, 
 // ---- space to depth: y[b, Y, X, (py*2+px)*C + c] = x[b, 2Y+py, 2X+px, c]  (H, W even)
 template <typename T>
 __global__ void __launch_bounds__(THREADS)
-space_to_depth2_kernel(const T* __restrict__ x, uint4* __restrict__ y, int H, int W, int vecs, int64_t total) {
+space_to_depth2_kernel(const T* __restrict__ x, uint4* __restrict__ y, int H, int W, int pitch_in, int pitch_out, int vecs,
+                       int64_t total) {
   for (int64_t i = (int64_t)blockIdx.x * THREADS + threadIdx.x; i < total; i += (int64_t)gridDim.x * THREADS) {
     const int v = (int)(i % vecs);
     int64_t r = i / vecs;
     const int ph = (int)(r % 4);
     r /= 4;
-    const int X = (int)(r % (W / 2));
-    r /= W / 2;
+    const int X = (int)(r % pitch_out);
+    r /= pitch_out;
     const int Y = (int)(r % (H / 2));
     const int64_t b = r / (H / 2);
+    if (X >= W / 2) { y[i] = make_uint4(0, 0, 0, 0); continue; }
     float f[8];
-    load8(x + (((b * H + 2 * Y + (ph >> 1)) * W + 2 * X + (ph & 1)) * vecs + v) * 8, f);
+    load8(x + (((b * H + 2 * Y + (ph >> 1)) * pitch_in + 2 * X + (ph & 1)) * vecs + v) * 8, f);
     y[i] = pack8(f);
   }
 }
 
-// ---- fp32 score rows -> bf16 probabilities: p = softmax(scale * s); one CTA per row, three passes over the row (the row
-// stays in L1 / L2: <= 256 KB).
+// ---- fp32 score rows -> bf16 probabilities: p = softmax(scale * s) over the first `valid` columns, zeros in the rest (key
+// padding to the GEMM's granularity); one CTA per row, three passes over the row (it stays in L1 / L2: <= 256 KB).
 __global__ void __launch_bounds__(THREADS)
-softmax_rows_kernel(const float* __restrict__ s, int64_t lds, __nv_bfloat16* __restrict__ p, int64_t ldp, int cols, float scale_log2) {
+softmax_rows_kernel(const float* __restrict__ s, int64_t lds, __nv_bfloat16* __restrict__ p, int64_t ldp, int cols, int valid,
+                    float scale_log2) {
   __shared__ float red[THREADS / 32];
   const float* row = s + (int64_t)blockIdx.x * lds;
   __nv_bfloat16* out = p + (int64_t)blockIdx.x * ldp;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  auto load4 = [&](int c, float (&v)[4]) {
+    const float4 t = *reinterpret_cast<const float4*>(row + c);
+    v[0] = t.x, v[1] = t.y, v[2] = t.z, v[3] = t.w;
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+      if (c + i >= valid) v[i] = -INFINITY;
+  };
   float m = -INFINITY;
   for (int c = threadIdx.x * 4; c < cols; c += THREADS * 4) {
-    const float4 v = *reinterpret_cast<const float4*>(row + c);
-    m = fmaxf(m, fmaxf(fmaxf(v.x, v.y), fmaxf(v.z, v.w)));
+    float v[4];
+    load4(c, v);
+    m = fmaxf(m, fmaxf(fmaxf(v[0], v[1]), fmaxf(v[2], v[3])));
   }
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
@@ -214,9 +232,10 @@ softmax_rows_kernel(const float* __restrict__ s, int64_t lds, __nv_bfloat16* __r
   const float nm = -m * scale_log2;
   float sum = 0.f;
   for (int c = threadIdx.x * 4; c < cols; c += THREADS * 4) {
-    const float4 v = *reinterpret_cast<const float4*>(row + c);
-    sum += (ptx::ex2(fmaf(v.x, scale_log2, nm)) + ptx::ex2(fmaf(v.y, scale_log2, nm))) +
-           (ptx::ex2(fmaf(v.z, scale_log2, nm)) + ptx::ex2(fmaf(v.w, scale_log2, nm)));
+    float v[4];
+    load4(c, v);
+    sum += (ptx::ex2(fmaf(v[0], scale_log2, nm)) + ptx::ex2(fmaf(v[1], scale_log2, nm))) +
+           (ptx::ex2(fmaf(v[2], scale_log2, nm)) + ptx::ex2(fmaf(v[3], scale_log2, nm)));
   }
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
@@ -227,21 +246,27 @@ softmax_rows_kernel(const float* __restrict__ s, int64_t lds, __nv_bfloat16* __r
   for (int w = 0; w < THREADS / 32; ++w) sum += red[w];
   const float inv = 1.0f / sum;
   for (int c = threadIdx.x * 4; c < cols; c += THREADS * 4) {
-    const float4 v = *reinterpret_cast<const float4*>(row + c);
+    float v[4];
+    load4(c, v);
     uint2 o;
-    o.x = ptx::pack_bf16(ptx::ex2(fmaf(v.x, scale_log2, nm)) * inv, ptx::ex2(fmaf(v.y, scale_log2, nm)) * inv);
-    o.y = ptx::pack_bf16(ptx::ex2(fmaf(v.z, scale_log2, nm)) * inv, ptx::ex2(fmaf(v.w, scale_log2, nm)) * inv);
+    o.x = ptx::pack_bf16(ptx::ex2(fmaf(v[0], scale_log2, nm)) * inv, ptx::ex2(fmaf(v[1], scale_log2, nm)) * inv);
+    o.y = ptx::pack_bf16(ptx::ex2(fmaf(v[2], scale_log2, nm)) * inv, ptx::ex2(fmaf(v[3], scale_log2, nm)) * inv);
     *reinterpret_cast<uint2*>(out + c) = o;
   }
 }
 
-// ---- NCHW (fp32 / bf16) -> NHWC bf16 with the channels zero-padded to c_pad, y = a x + b on the way
+// ---- NCHW (fp32 / bf16) [B, C, H, W] -> NHWC bf16 [B, H, pitch, c_pad] with the channels zero-padded to c_pad, y = a x + b
 template <typename T>
 __global__ void __launch_bounds__(THREADS)
-nchw_to_nhwc_kernel(const T* __restrict__ x, __nv_bfloat16* __restrict__ y, int C, int c_pad, int64_t hw, float a, float bb) {
+nchw_to_nhwc_kernel(const T* __restrict__ x, __nv_bfloat16* __restrict__ y, int C, int c_pad, int H, int W, int pitch, float a,
+                    float bb) {
   const int b = blockIdx.y;
-  for (int64_t p = (int64_t)blockIdx.x * THREADS + threadIdx.x; p < hw; p += (int64_t)gridDim.x * THREADS) {
-    __nv_bfloat16* dst = y + ((int64_t)b * hw + p) * c_pad;
+  const int64_t hw = (int64_t)H * W, hp = (int64_t)H * pitch;
+  for (int64_t p = (int64_t)blockIdx.x * THREADS + threadIdx.x; p < hp; p += (int64_t)gridDim.x * THREADS) {
+    const int yy = (int)(p / pitch), xx = (int)(p % pitch);
+    const bool ok = xx < W;
+    const int64_t src = (int64_t)yy * W + xx;
+    __nv_bfloat16* dst = y + ((int64_t)b * hp + p) * c_pad;
     for (int c0 = 0; c0 < c_pad; c0 += 8) {
       uint32_t o[4];
 #pragma unroll
@@ -250,7 +275,7 @@ nchw_to_nhwc_kernel(const T* __restrict__ x, __nv_bfloat16* __restrict__ y, int 
 #pragma unroll
         for (int e = 0; e < 2; ++e) {
           const int c = c0 + k + e;
-          f[e] = c < C ? fmaf((float)x[((int64_t)b * C + c) * hw + p], a, bb) : 0.f;
+          f[e] = (ok && c < C) ? fmaf((float)x[((int64_t)b * C + c) * hw + src], a, bb) : 0.f;
         }
         o[k >> 1] = ptx::pack_bf16(f[0], f[1]);
       }
@@ -259,12 +284,14 @@ nchw_to_nhwc_kernel(const T* __restrict__ x, __nv_bfloat16* __restrict__ y, int 
   }
 }
 
-// ---- fp32 [B, HW, ld] (first C columns) -> NCHW fp32 [B, C, H, W]
+// ---- fp32 NHWC [B, H, pitch, ld] (first C columns) -> NCHW fp32 [B, C, H, W]
 __global__ void __launch_bounds__(THREADS)
-nhwc_to_nchw_kernel(const float* __restrict__ x, int64_t ld, float* __restrict__ y, int C, int64_t hw) {
+nhwc_to_nchw_kernel(const float* __restrict__ x, int64_t ld, float* __restrict__ y, int C, int H, int W, int pitch) {
   const int b = blockIdx.y;
+  const int64_t hw = (int64_t)H * W;
   for (int64_t p = (int64_t)blockIdx.x * THREADS + threadIdx.x; p < hw; p += (int64_t)gridDim.x * THREADS) {
-    const float* src = x + ((int64_t)b * hw + p) * ld;
+    const int yy = (int)(p / W), xx = (int)(p % W);
+    const float* src = x + (((int64_t)b * H + yy) * pitch + xx) * ld;
     for (int c = 0; c < C; ++c) y[((int64_t)b * C + c) * hw + p] = src[c];
   }
 }
@@ -290,6 +317,10 @@ extern "C" int dit4sr_groupnorm_nhwc(const dit4sr_groupnorm_params* p, void* str
   DIT4SR_REQUIRE(p->batches > 0 && p->batches <= 65535 && p->pixels > 0 && p->channels > 0 && p->groups > 0,
                  DIT4SR_E_BADARG, "groupnorm: non-positive size");
   DIT4SR_REQUIRE(p->x_dtype == DIT4SR_DT_BF16 || p->x_dtype == DIT4SR_DT_F32, DIT4SR_E_BADARG, "groupnorm: unknown x_dtype");
+  DIT4SR_REQUIRE(p->width >= 0 && p->pitch >= p->width && (p->width == 0 || p->pixels % p->pitch == 0), DIT4SR_E_BADARG,
+                 "groupnorm: pitched image needs 0 < width <= pitch and pixels a multiple of pitch");
+  const int width = p->width > 0 ? p->width : 1, pitch = p->width > 0 ? p->pitch : 1;
+  const int valid_pixels = p->width > 0 ? p->pixels / p->pitch * p->width : p->pixels;
   DIT4SR_REQUIRE(p->channels % 8 == 0 && p->channels % p->groups == 0 && p->channels <= 8 * THREADS &&
                      THREADS % (p->channels / 8) == 0,
                  DIT4SR_E_SHAPE, "groupnorm: channels %d must be 8 * a divisor of %d and a multiple of groups %d", p->channels,
@@ -316,106 +347,111 @@ extern "C" int dit4sr_groupnorm_nhwc(const dit4sr_groupnorm_params* p, void* str
   __nv_bfloat16* y = reinterpret_cast<__nv_bfloat16*>(p->y);
   if (p->x_dtype == DIT4SR_DT_F32) {
     const float* x = reinterpret_cast<const float*>(p->x);
-    gn_stats_kernel<<<dim3(chunks, p->batches), THREADS, sm, stream>>>(x, p->ldx, p->x_batch_stride, p->pixels, p->channels,
-                                                                       p->groups, per, part);
+    gn_stats_kernel<<<dim3(chunks, p->batches), THREADS, sm, stream>>>(x, p->ldx, p->x_batch_stride, p->pixels, width, pitch,
+                                                                       p->channels, p->groups, per, part);
     gn_finalize_kernel<<<p->batches, 64, 0, stream>>>(part, chunks, p->groups, stats);
     gn_apply_kernel<<<dim3(gx, p->batches), THREADS, 0, stream>>>(x, p->ldx, p->x_batch_stride, y, p->ldy, p->y_batch_stride,
-                                                                 p->pixels, p->channels, p->groups, stats, p->gamma, p->beta,
-                                                                 p->eps, p->silu);
+                                                                 p->pixels, valid_pixels, p->channels, p->groups, stats,
+                                                                 p->gamma, p->beta, p->eps, p->silu);
   } else {
     const __nv_bfloat16* x = reinterpret_cast<const __nv_bfloat16*>(p->x);
-    gn_stats_kernel<<<dim3(chunks, p->batches), THREADS, sm, stream>>>(x, p->ldx, p->x_batch_stride, p->pixels, p->channels,
-                                                                       p->groups, per, part);
+    gn_stats_kernel<<<dim3(chunks, p->batches), THREADS, sm, stream>>>(x, p->ldx, p->x_batch_stride, p->pixels, width, pitch,
+                                                                       p->channels, p->groups, per, part);
     gn_finalize_kernel<<<p->batches, 64, 0, stream>>>(part, chunks, p->groups, stats);
     gn_apply_kernel<<<dim3(gx, p->batches), THREADS, 0, stream>>>(x, p->ldx, p->x_batch_stride, y, p->ldy, p->y_batch_stride,
-                                                                 p->pixels, p->channels, p->groups, stats, p->gamma, p->beta,
-                                                                 p->eps, p->silu);
+                                                                 p->pixels, valid_pixels, p->channels, p->groups, stats,
+                                                                 p->gamma, p->beta, p->eps, p->silu);
   }
   DIT4SR_CUDA(cudaGetLastError());
   return 0;
 }
 
-extern "C" int dit4sr_upsample2x_nhwc(const void* x, int x_dtype, void* y, int batches, int h, int w, int channels,
-                                      void* stream_) {
+extern "C" int dit4sr_upsample2x_nhwc(const void* x, int x_dtype, void* y, int batches, int h, int w, int pitch_in,
+                                      int pitch_out, int channels, void* stream_) {
   using namespace vae;
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
   DIT4SR_REQUIRE(x && y, DIT4SR_E_BADARG, "upsample2x: null pointer argument");
-  DIT4SR_REQUIRE(batches > 0 && h > 0 && w > 0 && channels > 0 && channels % 8 == 0, DIT4SR_E_SHAPE,
-                 "upsample2x: sizes must be positive, channels a multiple of 8");
+  DIT4SR_REQUIRE(batches > 0 && h > 0 && w > 0 && channels > 0 && channels % 8 == 0 && pitch_in >= w && pitch_out >= 2 * w,
+                 DIT4SR_E_SHAPE, "upsample2x: sizes must be positive, channels a multiple of 8, pitches >= the widths");
   DIT4SR_REQUIRE(host::aligned16(x) && host::aligned16(y), DIT4SR_E_ALIGN, "upsample2x: pointers not 16-byte aligned");
-  const int64_t total = (int64_t)batches * 4 * h * w * (channels / 8);
+  const int64_t total = (int64_t)batches * 2 * h * pitch_out * (channels / 8);
   if (x_dtype == DIT4SR_DT_F32)
     upsample2x_kernel<<<grid_for(total), THREADS, 0, stream>>>(reinterpret_cast<const float*>(x), reinterpret_cast<uint4*>(y), h,
-                                                              w, channels / 8, total);
+                                                              w, pitch_in, pitch_out, channels / 8, total);
   else
     upsample2x_kernel<<<grid_for(total), THREADS, 0, stream>>>(reinterpret_cast<const __nv_bfloat16*>(x),
-                                                              reinterpret_cast<uint4*>(y), h, w, channels / 8, total);
+                                                              reinterpret_cast<uint4*>(y), h, w, pitch_in, pitch_out,
+                                                              channels / 8, total);
   DIT4SR_CUDA(cudaGetLastError());
   return 0;
 }
 
-extern "C" int dit4sr_space_to_depth2_nhwc(const void* x, int x_dtype, void* y, int batches, int h, int w, int channels,
-                                           void* stream_) {
+extern "C" int dit4sr_space_to_depth2_nhwc(const void* x, int x_dtype, void* y, int batches, int h, int w, int pitch_in,
+                                           int pitch_out, int channels, void* stream_) {
   using namespace vae;
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
   DIT4SR_REQUIRE(x && y, DIT4SR_E_BADARG, "space_to_depth2: null pointer argument");
-  DIT4SR_REQUIRE(batches > 0 && h > 0 && w > 0 && h % 2 == 0 && w % 2 == 0 && channels > 0 && channels % 8 == 0, DIT4SR_E_SHAPE,
-                 "space_to_depth2: h, w must be even, channels a multiple of 8");
+  DIT4SR_REQUIRE(batches > 0 && h > 0 && w > 0 && h % 2 == 0 && w % 2 == 0 && channels > 0 && channels % 8 == 0 &&
+                     pitch_in >= w && pitch_out >= w / 2,
+                 DIT4SR_E_SHAPE, "space_to_depth2: h, w must be even, channels a multiple of 8, pitches >= the widths");
   DIT4SR_REQUIRE(host::aligned16(x) && host::aligned16(y), DIT4SR_E_ALIGN, "space_to_depth2: pointers not 16-byte aligned");
-  const int64_t total = (int64_t)batches * h * w * (channels / 8);
+  const int64_t total = (int64_t)batches * (h / 2) * pitch_out * 4 * (channels / 8);
   if (x_dtype == DIT4SR_DT_F32)
     space_to_depth2_kernel<<<grid_for(total), THREADS, 0, stream>>>(reinterpret_cast<const float*>(x), reinterpret_cast<uint4*>(y),
-                                                                   h, w, channels / 8, total);
+                                                                   h, w, pitch_in, pitch_out, channels / 8, total);
   else
     space_to_depth2_kernel<<<grid_for(total), THREADS, 0, stream>>>(reinterpret_cast<const __nv_bfloat16*>(x),
-                                                                   reinterpret_cast<uint4*>(y), h, w, channels / 8, total);
+                                                                   reinterpret_cast<uint4*>(y), h, w, pitch_in, pitch_out,
+                                                                   channels / 8, total);
   DIT4SR_CUDA(cudaGetLastError());
   return 0;
 }
 
-extern "C" int dit4sr_softmax_rows_to_bf16(const float* s, int64_t lds, void* p, int64_t ldp, int rows, int cols, float scale,
-                                           void* stream_) {
+extern "C" int dit4sr_softmax_rows_to_bf16(const float* s, int64_t lds, void* p, int64_t ldp, int rows, int cols, int valid_cols,
+                                           float scale, void* stream_) {
   using namespace vae;
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
   DIT4SR_REQUIRE(s && p, DIT4SR_E_BADARG, "softmax_rows_to_bf16: null pointer argument");
-  DIT4SR_REQUIRE(rows > 0 && cols > 0 && cols % 4 == 0, DIT4SR_E_SHAPE, "softmax_rows_to_bf16: cols must be a multiple of 4");
+  DIT4SR_REQUIRE(rows > 0 && cols > 0 && cols % 4 == 0 && valid_cols > 0 && valid_cols <= cols, DIT4SR_E_SHAPE,
+                 "softmax_rows_to_bf16: cols must be a multiple of 4, 0 < valid_cols <= cols");
   DIT4SR_REQUIRE(lds % 4 == 0 && ldp % 4 == 0 && host::aligned16(s) && (reinterpret_cast<uintptr_t>(p) & 7) == 0, DIT4SR_E_ALIGN,
                  "softmax_rows_to_bf16: pointers/strides not aligned");
-  softmax_rows_kernel<<<rows, THREADS, 0, stream>>>(s, lds, reinterpret_cast<__nv_bfloat16*>(p), ldp, cols,
+  softmax_rows_kernel<<<rows, THREADS, 0, stream>>>(s, lds, reinterpret_cast<__nv_bfloat16*>(p), ldp, cols, valid_cols,
                                                    scale * 1.4426950408889634f);
   DIT4SR_CUDA(cudaGetLastError());
   return 0;
 }
 
-extern "C" int dit4sr_nchw_to_nhwc_bf16(const void* x, int x_dtype, void* y, int batches, int channels, int c_pad, int64_t hw,
-                                        float a, float b, void* stream_) {
+extern "C" int dit4sr_nchw_to_nhwc_bf16(const void* x, int x_dtype, void* y, int batches, int channels, int c_pad, int h, int w,
+                                        int pitch, float a, float b, void* stream_) {
   using namespace vae;
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
   DIT4SR_REQUIRE(x && y, DIT4SR_E_BADARG, "nchw_to_nhwc: null pointer argument");
-  DIT4SR_REQUIRE(batches > 0 && batches <= 65535 && channels > 0 && c_pad >= channels && c_pad % 8 == 0 && hw > 0,
-                 DIT4SR_E_SHAPE, "nchw_to_nhwc: bad sizes (c_pad must be a multiple of 8 and >= channels)");
+  DIT4SR_REQUIRE(batches > 0 && batches <= 65535 && channels > 0 && c_pad >= channels && c_pad % 8 == 0 && h > 0 && w > 0 &&
+                     pitch >= w,
+                 DIT4SR_E_SHAPE, "nchw_to_nhwc: bad sizes (c_pad must be a multiple of 8 and >= channels, pitch >= w)");
   DIT4SR_REQUIRE(host::aligned16(y), DIT4SR_E_ALIGN, "nchw_to_nhwc: output not 16-byte aligned");
   DIT4SR_REQUIRE(x_dtype == DIT4SR_DT_BF16 || x_dtype == DIT4SR_DT_F32, DIT4SR_E_BADARG,
                  "nchw_to_nhwc: unknown input dtype %d", x_dtype);
-  const dim3 grid(grid_for(hw), batches);
+  const dim3 grid(grid_for((int64_t)h * pitch), batches);
   if (x_dtype == DIT4SR_DT_F32)
     nchw_to_nhwc_kernel<<<grid, THREADS, 0, stream>>>(reinterpret_cast<const float*>(x), reinterpret_cast<__nv_bfloat16*>(y),
-                                                     channels, c_pad, hw, a, b);
+                                                     channels, c_pad, h, w, pitch, a, b);
   else
     nchw_to_nhwc_kernel<<<grid, THREADS, 0, stream>>>(reinterpret_cast<const __nv_bfloat16*>(x),
-                                                     reinterpret_cast<__nv_bfloat16*>(y), channels, c_pad, hw, a, b);
+                                                     reinterpret_cast<__nv_bfloat16*>(y), channels, c_pad, h, w, pitch, a, b);
   DIT4SR_CUDA(cudaGetLastError());
   return 0;
 }
 
-extern "C" int dit4sr_nhwc_to_nchw_f32(const float* x, int64_t ld, float* y, int batches, int channels, int64_t hw,
+extern "C" int dit4sr_nhwc_to_nchw_f32(const float* x, int64_t ld, float* y, int batches, int channels, int h, int w, int pitch,
                                        void* stream_) {
   using namespace vae;
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
   DIT4SR_REQUIRE(x && y, DIT4SR_E_BADARG, "nhwc_to_nchw: null pointer argument");
-  DIT4SR_REQUIRE(batches > 0 && batches <= 65535 && channels > 0 && ld >= channels && hw > 0, DIT4SR_E_SHAPE,
-                 "nhwc_to_nchw: bad sizes");
-  nhwc_to_nchw_kernel<<<dim3(grid_for(hw), batches), THREADS, 0, stream>>>(x, ld, y, channels, hw);
+  DIT4SR_REQUIRE(batches > 0 && batches <= 65535 && channels > 0 && ld >= channels && h > 0 && w > 0 && pitch >= w,
+                 DIT4SR_E_SHAPE, "nhwc_to_nchw: bad sizes");
+  nhwc_to_nchw_kernel<<<dim3(grid_for((int64_t)h * w), batches), THREADS, 0, stream>>>(x, ld, y, channels, h, w, pitch);
   DIT4SR_CUDA(cudaGetLastError());
   return 0;
 }

@@ -124,8 +124,8 @@ def gemm_sp(world, rank, inner_dim, rows_dst, peers, row0, col0=0, own_heads_onl
 
 def _gemm_params(p, A, W, bias, out, epilogue=EPI_BIAS, gate=None, resid=None, norm_w0=None, norm_w1=None, sec_cols=0,
                  eps=1e-6, dbl_row_offset=0, sp=None, conv=None, resid_bf16=None):
-    """conv = (H, W, kernel_width, taps, origin): A [B, H*W, C_in] is an NHWC image and W is [N, taps * C_in]
-    (implicit-GEMM convolution); resid_bf16 [B, R, N] is added to a bf16 output (BIAS epilogue)."""
+    """conv = (H, W, kernel_width, taps, origin[, valid width]): A [B, H*W, C_in] is an NHWC image (pitched when a valid width
+    < W is given) and W is [N, taps * C_in] (implicit-GEMM convolution); resid_bf16 [B, R, N] is added to a bf16 output."""
     A = _as3(A)
     out = _as3(out)
     _req(A, torch.bfloat16, "A")
@@ -136,11 +136,12 @@ def _gemm_params(p, A, W, bias, out, epilogue=EPI_BIAS, gate=None, resid=None, n
     B, R, K = A.shape
     N = W.shape[0]
     if conv is not None:
-        ch, cw, ckw, ctaps, corg = conv
+        ch, cw, ckw, ctaps, corg = conv[:5]
         if R != ch * cw:
             raise _lib.Dit4srError(f"gemm/conv: A has {R} rows for a {ch}x{cw} image")
         K = K * ctaps
         p.conv_h, p.conv_w, p.conv_kw, p.conv_taps, p.conv_org = ch, cw, ckw, ctaps, corg
+        p.conv_w_valid = conv[5] if len(conv) > 5 else 0
     if W.shape[1] != K or out.shape[0] != B or out.shape[1] != R or out.shape[2] != N:
         raise _lib.Dit4srError(f"gemm: shape mismatch A{tuple(A.shape)} W{tuple(W.shape)} out{tuple(out.shape)}")
     p.A, p.lda, p.a_batch_stride = _ptr(A), A.stride(1), A.stride(0)
@@ -518,24 +519,37 @@ def dwconv3x3_add_f32(u_hq, u_lr, weight9, bias, grid, grid_w=0, lr_row_offset=0
 
 
 # ---------------------------------------------------------------------------------------------------------------- VAE (row N4)
-def conv3x3(x, H, W, weight, bias, out, resid_bf16=None, resid=None):
+def conv_pitch(w):
+    """Row pitch (in pixels) an image of width w is stored with for the implicit-GEMM convolution: the smallest value
+    >= w that divides 128 or is a multiple of 128."""
+    if w >= 128:
+        return (w + 127) // 128 * 128
+    p = 1
+    while p < w:
+        p *= 2
+    return p
+
+
+def conv3x3(x, H, W, weight, bias, out, resid_bf16=None, resid=None, width=0):
     """3x3 convolution, zero pad 1, on NHWC bf16 x [B, H*W, C_in] with weight bf16 [N, 9 * C_in] (tap-major) -> out [B, H*W, N]
-    bf16 (+ resid_bf16) or fp32 (+ resid fp32; resid may be out itself: added in place with TMA reduce-adds)."""
+    bf16 (+ resid_bf16) or fp32 (+ resid fp32; resid may be out itself: added in place with TMA reduce-adds).
+    width: the image is pitched - rows of W pixels of which the first `width` exist (0 = all W)."""
     if resid is not None:
-        gemm(x, weight, bias, out, EPI_GATE_RESID, resid=resid, conv=(H, W, 3, 9, -1))
+        gemm(x, weight, bias, out, EPI_GATE_RESID, resid=resid, conv=(H, W, 3, 9, -1, width))
     else:
-        gemm(x, weight, bias, out, EPI_BIAS, conv=(H, W, 3, 9, -1), resid_bf16=resid_bf16)
+        gemm(x, weight, bias, out, EPI_BIAS, conv=(H, W, 3, 9, -1, width), resid_bf16=resid_bf16)
 
 
-def conv2x2_s2d(x, H, W, weight, bias, out):
+def conv2x2_s2d(x, H, W, weight, bias, out, width=0):
     """The 2x2 stride-1 convolution (taps at offsets 0 / +1, zero beyond the image) that a space-to-depth input turns
     Downsample2D's padded stride-2 3x3 convolution into: x [B, H*W, 4C], weight [N, 4 * 4C]."""
-    gemm(x, weight, bias, out, EPI_BIAS, conv=(H, W, 2, 4, 0))
+    gemm(x, weight, bias, out, EPI_BIAS, conv=(H, W, 2, 4, 0, width))
 
 
-def groupnorm_nhwc(x, gamma, beta, out, groups=32, eps=1e-6, silu=False, stats=None):
+def groupnorm_nhwc(x, gamma, beta, out, groups=32, eps=1e-6, silu=False, stats=None, width=0, pitch=0):
     """out (bf16) = [silu](GroupNorm(x)) on NHWC x [B, pixels, C] (bf16 or fp32); stats: scratch of
-    dit4sr_groupnorm_workspace_bytes(B, groups) bytes (allocated if None)."""
+    dit4sr_groupnorm_workspace_bytes(B, groups) bytes (allocated if None).  width / pitch: pitched image (pixels = rows *
+    pitch, only the first `width` of every `pitch` pixels enter the statistics)."""
     _req(x, x.dtype if x.dtype == torch.float32 else torch.bfloat16, "x")
     _req(out, torch.bfloat16, "out")
     _req(gamma, torch.float32, "gamma")
@@ -554,67 +568,79 @@ def groupnorm_nhwc(x, gamma, beta, out, groups=32, eps=1e-6, silu=False, stats=N
     p.gamma, p.beta, p.stats, p.stats_bytes = _ptr(gamma), _ptr(beta), _ptr(stats), stats.numel() * stats.element_size()
     p.batches, p.pixels, p.channels, p.groups, p.eps, p.silu = B, P, Cc, groups, eps, 1 if silu else 0
     p.x_dtype = DT_F32 if x.dtype == torch.float32 else DT_BF16
+    if width and pitch and width != pitch:
+        p.width, p.pitch = width, pitch
     check(_lib.load().dit4sr_groupnorm_nhwc(C.byref(p), _stream()), "dit4sr_groupnorm_nhwc")
     _count(3)
 
 
-def upsample2x_nhwc(x, H, W, out):
-    """out [B, 2H*2W, C] (bf16) = nearest-neighbour repeat of x [B, H*W, C] (contiguous, bf16 or fp32)."""
+def _dt(x):
+    return DT_F32 if x.dtype == torch.float32 else DT_BF16
+
+
+def upsample2x_nhwc(x, H, W, out, pitch_in=0, pitch_out=0):
+    """out [B, 2H*pitch_out, C] (bf16) = nearest-neighbour repeat of the (H x W) image x [B, H*pitch_in, C] (contiguous, bf16
+    or fp32); pitches default to the widths."""
     _req(x, x.dtype if x.dtype == torch.float32 else torch.bfloat16, "x")
     _req(out, torch.bfloat16, "out")
+    pi, po = pitch_in or W, pitch_out or 2 * W
     B, P, Cc = x.shape
-    if P != H * W or tuple(out.shape) != (B, 4 * P, Cc) or not x.is_contiguous() or not out.is_contiguous():
-        raise _lib.Dit4srError("upsample2x_nhwc: contiguous [B, H*W, C] -> [B, 4*H*W, C]")
-    check(_lib.load().dit4sr_upsample2x_nhwc(_ptr(x), DT_F32 if x.dtype == torch.float32 else DT_BF16, _ptr(out), B, H, W, Cc,
-                                             _stream()), "dit4sr_upsample2x_nhwc")
+    if P != H * pi or tuple(out.shape) != (B, 2 * H * po, Cc) or not x.is_contiguous() or not out.is_contiguous():
+        raise _lib.Dit4srError("upsample2x_nhwc: contiguous [B, H*pitch_in, C] -> [B, 2H*pitch_out, C]")
+    check(_lib.load().dit4sr_upsample2x_nhwc(_ptr(x), _dt(x), _ptr(out), B, H, W, pi, po, Cc, _stream()), "dit4sr_upsample2x_nhwc")
     _count()
 
 
-def space_to_depth2_nhwc(x, H, W, out):
-    """out [B, (H/2)*(W/2), 4C] (bf16) with channel (py*2+px)*C + c = x[b, (2Y+py)*W + 2X+px, c] (contiguous, bf16 or fp32)."""
+def space_to_depth2_nhwc(x, H, W, out, pitch_in=0, pitch_out=0):
+    """out [B, (H/2)*pitch_out, 4C] (bf16) with channel (py*2+px)*C + c = x[b, (2Y+py)*pitch_in + 2X+px, c] (contiguous, bf16
+    or fp32); pitches default to the widths."""
     _req(x, x.dtype if x.dtype == torch.float32 else torch.bfloat16, "x")
     _req(out, torch.bfloat16, "out")
+    pi, po = pitch_in or W, pitch_out or W // 2
     B, P, Cc = x.shape
-    if P != H * W or tuple(out.shape) != (B, P // 4, 4 * Cc) or not x.is_contiguous() or not out.is_contiguous():
-        raise _lib.Dit4srError("space_to_depth2_nhwc: contiguous [B, H*W, C] -> [B, H*W/4, 4C]")
-    check(_lib.load().dit4sr_space_to_depth2_nhwc(_ptr(x), DT_F32 if x.dtype == torch.float32 else DT_BF16, _ptr(out), B, H, W,
-                                                  Cc, _stream()), "dit4sr_space_to_depth2_nhwc")
+    if P != H * pi or tuple(out.shape) != (B, (H // 2) * po, 4 * Cc) or not x.is_contiguous() or not out.is_contiguous():
+        raise _lib.Dit4srError("space_to_depth2_nhwc: contiguous [B, H*pitch_in, C] -> [B, (H/2)*pitch_out, 4C]")
+    check(_lib.load().dit4sr_space_to_depth2_nhwc(_ptr(x), _dt(x), _ptr(out), B, H, W, pi, po, Cc, _stream()),
+          "dit4sr_space_to_depth2_nhwc")
     _count()
 
 
-def softmax_rows_to_bf16(scores, probs, scale):
-    """probs[r, :] = softmax(scale * scores[r, :]); scores fp32 [R, C], probs bf16 [R, C]."""
+def softmax_rows_to_bf16(scores, probs, scale, valid_cols=None):
+    """probs[r, :valid] = softmax(scale * scores[r, :valid]), zeros beyond; scores fp32 [R, C], probs bf16 [R, C]."""
     _req(scores, torch.float32, "scores")
     _req(probs, torch.bfloat16, "probs")
     if scores.shape != probs.shape or scores.dim() != 2:
         raise _lib.Dit4srError("softmax_rows_to_bf16: [R, C] fp32 -> [R, C] bf16")
+    valid = scores.shape[1] if valid_cols is None else valid_cols
     check(_lib.load().dit4sr_softmax_rows_to_bf16(_ptr(scores), scores.stride(0), _ptr(probs), probs.stride(0), scores.shape[0],
-                                                  scores.shape[1], float(scale), _stream()), "dit4sr_softmax_rows_to_bf16")
+                                                  scores.shape[1], valid, float(scale), _stream()), "dit4sr_softmax_rows_to_bf16")
     _count()
 
 
-def nchw_to_nhwc_bf16(x, c_pad, a=1.0, b=0.0):
-    """x [B, C, H, W] (fp32 / bf16, contiguous) -> bf16 [B, H*W, c_pad] = a x + b, channels >= C zero."""
+def nchw_to_nhwc_bf16(x, c_pad, a=1.0, b=0.0, pitch=0):
+    """x [B, C, H, W] (fp32 / bf16, contiguous) -> bf16 [B, H*pitch, c_pad] = a x + b, channels >= C and pad pixels zero."""
     if x.dtype not in (torch.float32, torch.bfloat16):
         x = x.float()
     x = x.contiguous()
     _req(x, x.dtype, "x")
     B, Cc, H, W = x.shape
-    out = torch.empty(B, H * W, c_pad, device=x.device, dtype=torch.bfloat16)
-    check(_lib.load().dit4sr_nchw_to_nhwc_bf16(_ptr(x), DT_F32 if x.dtype == torch.float32 else DT_BF16, _ptr(out), B, Cc, c_pad,
-                                               H * W, float(a), float(b), _stream()), "dit4sr_nchw_to_nhwc_bf16")
+    pitch = pitch or W
+    out = torch.empty(B, H * pitch, c_pad, device=x.device, dtype=torch.bfloat16)
+    check(_lib.load().dit4sr_nchw_to_nhwc_bf16(_ptr(x), _dt(x), _ptr(out), B, Cc, c_pad, H, W, pitch, float(a), float(b),
+                                               _stream()), "dit4sr_nchw_to_nhwc_bf16")
     _count()
     return out
 
 
-def nhwc_to_nchw_f32(x, channels, H, W):
-    """fp32 [B, H*W, ld] -> fp32 [B, channels, H, W] (the first `channels` columns)."""
+def nhwc_to_nchw_f32(x, channels, H, W, pitch=0):
+    """fp32 [B, H*pitch, ld] -> fp32 [B, channels, H, W] (the first `channels` columns of the first W pixels per row)."""
     _req(x, torch.float32, "x")
+    pitch = pitch or W
     B, P, _ = x.shape
-    if P != H * W or x.stride(0) != P * x.stride(1):
-        raise _lib.Dit4srError("nhwc_to_nchw_f32: expected [B, H*W, ld] with dense batches")
+    if P != H * pitch or x.stride(0) != P * x.stride(1):
+        raise _lib.Dit4srError("nhwc_to_nchw_f32: expected [B, H*pitch, ld] with dense batches")
     out = torch.empty(B, channels, H, W, device=x.device, dtype=torch.float32)
-    check(_lib.load().dit4sr_nhwc_to_nchw_f32(_ptr(x), x.stride(1), _ptr(out), B, channels, H * W, _stream()),
+    check(_lib.load().dit4sr_nhwc_to_nchw_f32(_ptr(x), x.stride(1), _ptr(out), B, channels, H, W, pitch, _stream()),
           "dit4sr_nhwc_to_nchw_f32")
     _count()
     return out

@@ -13,8 +13,9 @@ the reference's tiled-VAE hook walks (utils/vaehook.py:279-358), and the diffuse
 Every layer runs in the sm_100a library on channels-last bf16 activations: 3x3 convolutions as implicit GEMMs on tcgen05
 (TMA box loads shifted per tap, out-of-bounds zero fill = padding; `ops.conv3x3`), skip connections fused into the GEMM
 epilogue, Downsample2D as space-to-depth + a 2x2 convolution, GroupNorm / SiLU / up-sampling / softmax in `csrc/vae.cu`.
-No tiling: vaehook's tiles exist to fit 8-24 GB GPUs; a B200 holds the activations of a 2048 x 2048 decode (1 GB per
-128-channel full-resolution tensor).  There is no PyTorch fallback.
+Any image size that is a multiple of 8 works: an (H x W) activation is stored with a row pitch that suits the convolution's
+128-pixel tiles (ops.conv_pitch) and the tensor maps clip at W.  No tiling: vaehook's tiles exist to fit 8-24 GB GPUs; a
+B200 holds the activations of a 2048 x 2048 decode (1 GB per 128-channel full-resolution tensor).  No PyTorch fallback.
 """
 import inspect
 import json
@@ -322,66 +323,81 @@ class AutoencoderKL(nn.Module):
         self._packed = P
         return P
 
-    # ---- layers on channels-last activations [B, H*W, C]: the skip stream x is fp32, GEMM operands are bf16
-    def _gn(self, x, key, silu):
+    # ---- layers on channels-last activations [B, H*P, C]: the skip stream x is fp32, GEMM operands are bf16.  P is the row
+    # pitch of the (H x W) image (ops.conv_pitch: divides 128 or a multiple of it; pad pixels are never read as data: the
+    # convolutions' tensor maps clip at W, GroupNorm skips them, attention runs on the compacted tokens)
+    def _gn(self, x, key, silu, W, P):
         g, b = self._packed[key]
         out = torch.empty(x.shape, device=x.device, dtype=torch.bfloat16)
-        ops.groupnorm_nhwc(x, g, b, out, groups=self.config.norm_num_groups, eps=1e-6, silu=silu)
+        ops.groupnorm_nhwc(x, g, b, out, groups=self.config.norm_num_groups, eps=1e-6, silu=silu, width=W, pitch=P)
         return out
 
-    def _conv(self, x, H, W, key, dtype=torch.float32):
+    def _conv(self, x, H, W, P, key, dtype=torch.float32):
         w, b = self._packed[key]
-        out = torch.empty(x.shape[0], H * W, w.shape[0], device=x.device, dtype=dtype)
-        ops.conv3x3(x, H, W, w, b, out)
+        out = torch.empty(x.shape[0], H * P, w.shape[0], device=x.device, dtype=dtype)
+        ops.conv3x3(x, H, P, w, b, out, width=W)
         return out
 
-    def _resnet(self, x, H, W, key):
+    def _resnet(self, x, H, W, P, key):
         """x (fp32) -> shortcut(x) + conv2(silu(norm2(conv1(silu(norm1(x)))))); the sum is formed in place in the fp32
         stream by the conv2 GEMM's epilogue (TMA reduce-adds)."""
-        P = self._packed
-        h = self._gn(x, key + "norm1", True)
-        h = self._conv(h, H, W, key + "conv1", torch.bfloat16)
-        h = self._gn(h, key + "norm2", True)
-        if key + "conv_shortcut" in P:
-            w, b = P[key + "conv_shortcut"]
+        Pk = self._packed
+        h = self._gn(x, key + "norm1", True, W, P)
+        h = self._conv(h, H, W, P, key + "conv1", torch.bfloat16)
+        h = self._gn(h, key + "norm2", True, W, P)
+        if key + "conv_shortcut" in Pk:
+            w, b = Pk[key + "conv_shortcut"]
             xb = torch.empty(x.shape, device=x.device, dtype=torch.bfloat16)
             ops.cast(x, xb)
-            x = torch.empty(x.shape[0], H * W, w.shape[0], device=x.device, dtype=torch.float32)
+            x = torch.empty(x.shape[0], H * P, w.shape[0], device=x.device, dtype=torch.float32)
             ops.gemm(xb, w, b, x)
-        w, b = P[key + "conv2"]
-        ops.conv3x3(h, H, W, w, b, x, resid=x)
+        w, b = Pk[key + "conv2"]
+        ops.conv3x3(h, H, P, w, b, x, resid=x, width=W)
         return x
 
-    def _attention(self, x, key):
+    def _attention(self, x, H, W, P, key):
         """x += to_out(softmax(q k^T / sqrt(C)) v) with one head of head_dim C: scores and P V are plain tcgen05 GEMMs,
-        the fp32 score rows (chunked to <= 1 GB) are normalised into bf16 probabilities by a row kernel."""
-        P = self._packed
-        B, S, Cc = x.shape
-        h = self._gn(x, key + "attn.norm", False)
-        wqk, bqk = P[key + "attn.qk"]
-        qk = torch.empty(B, S, 2 * Cc, device=x.device, dtype=torch.bfloat16)
+        the fp32 score rows (chunked to <= 1 GB) are normalised into bf16 probabilities by a row kernel.  A pitched image
+        is compacted first (pad pixels must not act as keys) and written back afterwards (strided device copies)."""
+        Pk = self._packed
+        B, _, Cc = x.shape
+        xp = None
+        if P != W:
+            xp = x
+            x = x.view(B, H, P, Cc)[:, :, :W].reshape(B, H * W, Cc)
+        S = H * W
+        Sp = (S + 31) // 32 * 32           # key / token padding to the GEMM's granularity (pad keys get probability 0)
+        g, bt = Pk[key + "attn.norm"]
+        h = torch.zeros(B, Sp, Cc, device=x.device, dtype=torch.bfloat16) if Sp != S else \
+            torch.empty(B, S, Cc, device=x.device, dtype=torch.bfloat16)
+        ops.groupnorm_nhwc(x, g, bt, h[:, :S], groups=self.config.norm_num_groups, eps=1e-6, silu=False)
+        wqk, bqk = Pk[key + "attn.qk"]
+        qk = torch.empty(B, Sp, 2 * Cc, device=x.device, dtype=torch.bfloat16)
         ops.gemm(h, wqk, bqk, qk)
-        wo, bo = P[key + "attn.out"]
-        rows = max(128, min(S, (1 << 28) // S // 128 * 128))
-        scores = torch.empty(rows, S, device=x.device, dtype=torch.float32)
-        probs = torch.empty(rows, S, device=x.device, dtype=torch.bfloat16)
-        vt = torch.empty(Cc, S, device=x.device, dtype=torch.bfloat16)
+        wo, bo = Pk[key + "attn.out"]
+        rows = max(128, min(S, (1 << 28) // Sp // 128 * 128))
+        scores = torch.empty(rows, Sp, device=x.device, dtype=torch.float32)
+        probs = torch.empty(rows, Sp, device=x.device, dtype=torch.bfloat16)
+        vt = torch.empty(Cc, Sp, device=x.device, dtype=torch.bfloat16)
         o = torch.empty(S, Cc, device=x.device, dtype=torch.bfloat16)
         for b in range(B):
-            ops.gemm(P[key + "attn.v"], h[b], None, vt)                  # V^T [C, S] = W_v h^T (bias folded into to_out)
+            ops.gemm(Pk[key + "attn.v"], h[b], None, vt)                 # V^T [C, S] = W_v h^T (bias folded into to_out)
             for r0 in range(0, S, rows):
                 r1 = min(S, r0 + rows)
                 ops.gemm(qk[b, r0:r1, :Cc], qk[b, :, Cc:], None, scores[:r1 - r0])
-                ops.softmax_rows_to_bf16(scores[:r1 - r0], probs[:r1 - r0], 1.0 / math.sqrt(Cc))
+                ops.softmax_rows_to_bf16(scores[:r1 - r0], probs[:r1 - r0], 1.0 / math.sqrt(Cc), valid_cols=S)
                 ops.gemm(probs[:r1 - r0], vt, None, o[r0:r1])
             ops.gemm(o, wo, bo, x[b], ops.EPI_GATE_RESID)                # in place: x[b] += o W_o^T + bias
+        if xp is not None:
+            xp.view(B, H, P, Cc)[:, :, :W].copy_(x.view(B, H, W, Cc))
+            x = xp
         return x
 
-    def _mid(self, x, H, W, key, attention):
-        x = self._resnet(x, H, W, key + "resnets.0.")
+    def _mid(self, x, H, W, P, key, attention):
+        x = self._resnet(x, H, W, P, key + "resnets.0.")
         if attention:
-            x = self._attention(x, key)
-        return self._resnet(x, H, W, key + "resnets.1.")
+            x = self._attention(x, H, W, P, key)
+        return self._resnet(x, H, W, P, key + "resnets.1.")
 
     # ---- public API
     def _check_input(self, t, channels):
@@ -399,23 +415,25 @@ class AutoencoderKL(nn.Module):
         n = len(cfg.block_out_channels)
         if H % (1 << (n - 1)) or W % (1 << (n - 1)):
             raise ValueError("image sides must be multiples of the VAE scale factor")
-        h = ops.nchw_to_nhwc_bf16(x, _pad64(cfg.in_channels))
-        h = self._conv(h, H, W, "enc.conv_in")
+        P = ops.conv_pitch(W)
+        h = ops.nchw_to_nhwc_bf16(x, _pad64(cfg.in_channels), pitch=P)
+        h = self._conv(h, H, W, P, "enc.conv_in")
         for i, blk in enumerate(self.encoder.down_blocks):
             for j in range(len(blk.resnets)):
-                h = self._resnet(h, H, W, f"enc.down.{i}.{j}.")
+                h = self._resnet(h, H, W, P, f"enc.down.{i}.{j}.")
             if blk.downsamplers is not None:
                 Cc = h.shape[2]
-                s2d = torch.empty(B, H * W // 4, 4 * Cc, device=h.device, dtype=torch.bfloat16)
-                ops.space_to_depth2_nhwc(h, H, W, s2d)
-                H, W = H // 2, W // 2
+                P2 = ops.conv_pitch(W // 2)
+                s2d = torch.empty(B, (H // 2) * P2, 4 * Cc, device=h.device, dtype=torch.bfloat16)
+                ops.space_to_depth2_nhwc(h, H, W, s2d, pitch_in=P, pitch_out=P2)
+                H, W, P = H // 2, W // 2, P2
                 w, b = self._packed[f"enc.down.{i}.ds"]
-                h = torch.empty(B, H * W, w.shape[0], device=h.device, dtype=torch.float32)
-                ops.conv2x2_s2d(s2d, H, W, w, b, h)
-        h = self._mid(h, H, W, "enc.mid.", cfg.mid_block_add_attention)
-        h = self._gn(h, "enc.norm_out", True)
-        m = self._conv(h, H, W, "enc.conv_out")
-        return ops.nhwc_to_nchw_f32(m, 2 * cfg.latent_channels, H, W)
+                h = torch.empty(B, H * P, w.shape[0], device=h.device, dtype=torch.float32)
+                ops.conv2x2_s2d(s2d, H, P, w, b, h, width=W)
+        h = self._mid(h, H, W, P, "enc.mid.", cfg.mid_block_add_attention)
+        h = self._gn(h, "enc.norm_out", True, W, P)
+        m = self._conv(h, H, W, P, "enc.conv_out")
+        return ops.nhwc_to_nchw_f32(m, 2 * cfg.latent_channels, H, W, pitch=P)
 
     def encode(self, x: torch.Tensor, return_dict: bool = True):
         posterior = DiagonalGaussianDistribution(self._encode_moments(x).to(x.dtype if x.is_floating_point() else torch.float32))
@@ -427,20 +445,22 @@ class AutoencoderKL(nn.Module):
         self._check_input(z, cfg.latent_channels)
         self._pack()
         B, _, H, W = z.shape
-        h = ops.nchw_to_nhwc_bf16(z, _pad64(cfg.latent_channels))
-        h = self._conv(h, H, W, "dec.conv_in")
-        h = self._mid(h, H, W, "dec.mid.", cfg.mid_block_add_attention)
+        P = ops.conv_pitch(W)
+        h = ops.nchw_to_nhwc_bf16(z, _pad64(cfg.latent_channels), pitch=P)
+        h = self._conv(h, H, W, P, "dec.conv_in")
+        h = self._mid(h, H, W, P, "dec.mid.", cfg.mid_block_add_attention)
         for i, blk in enumerate(self.decoder.up_blocks):
             for j in range(len(blk.resnets)):
-                h = self._resnet(h, H, W, f"dec.up.{i}.{j}.")
+                h = self._resnet(h, H, W, P, f"dec.up.{i}.{j}.")
             if blk.upsamplers is not None:
-                up = torch.empty(B, 4 * H * W, h.shape[2], device=h.device, dtype=torch.bfloat16)
-                ops.upsample2x_nhwc(h, H, W, up)
-                H, W = 2 * H, 2 * W
-                h = self._conv(up, H, W, f"dec.up.{i}.us")
-        h = self._gn(h, "dec.norm_out", True)
-        img = self._conv(h, H, W, "dec.conv_out")
-        return ops.nhwc_to_nchw_f32(img, cfg.out_channels, H, W)
+                P2 = ops.conv_pitch(2 * W)
+                up = torch.empty(B, 2 * H * P2, h.shape[2], device=h.device, dtype=torch.bfloat16)
+                ops.upsample2x_nhwc(h, H, W, up, pitch_in=P, pitch_out=P2)
+                H, W, P = 2 * H, 2 * W, P2
+                h = self._conv(up, H, W, P, f"dec.up.{i}.us")
+        h = self._gn(h, "dec.norm_out", True, W, P)
+        img = self._conv(h, H, W, P, "dec.conv_out")
+        return ops.nhwc_to_nchw_f32(img, cfg.out_channels, H, W, pitch=P)
 
     def decode(self, z: torch.Tensor, return_dict: bool = True, generator=None):
         dec = self._decode(z).to(z.dtype)

@@ -142,8 +142,9 @@ typedef struct {
    * raster order, K = conv_taps * C_in with W laid out [N, tap, C_in].  K-block kb belongs to tap t = kb / (C_in / 64) and
    * is read from the image shifted by (t / conv_kw + conv_org) rows and (t % conv_kw + conv_org) columns; pixels outside
    * the image read as zero (TMA out-of-bounds fill = the convolution's zero padding).  3x3, pad 1: conv_kw 3, conv_taps 9,
-   * conv_org -1.  conv_w must divide 128 or be a multiple of 128. */
+   * conv_org -1.  conv_w must divide 128 or be a multiple of 128 (other widths: pitched images, conv_w_valid). */
   int conv_w; int conv_h; int conv_kw; int conv_taps; int conv_org;
+  int conv_w_valid;   /* 0 = conv_w; else the image is pitched: rows of conv_w pixels of which the first conv_w_valid exist */
   /* BIAS epilogue with bf16 C: C = acc + bias + resid_bf16 (same row/column indexing as C; NULL = none) */
   const void* resid_bf16; int64_t ld_rb; int64_t rb_batch_stride;
 } dit4sr_gemm_params;
@@ -392,24 +393,36 @@ typedef struct {
   int batches; int pixels; int channels; int groups;
   float eps; int silu;
   int x_dtype;                              /* DIT4SR_DT_BF16 / DIT4SR_DT_F32 (strides in elements of that type) */
+  int width; int pitch;                     /* pitched image (see below): `pixels` = rows * pitch, only the first `width`
+                                               pixels of every `pitch` enter the statistics; 0, 0 = every pixel counts */
 } dit4sr_groupnorm_params;
 int dit4sr_groupnorm_nhwc(const dit4sr_groupnorm_params* p, void* stream);
 int64_t dit4sr_groupnorm_workspace_bytes(int batches, int groups);
-/* y[b, 2h, 2w, c] = x[b, h, w, c] nearest-neighbour repeat (Upsample2D before its 3x3 convolution); contiguous NHWC, x of
- * x_dtype (DIT4SR_DT_*), y bf16 */
-int dit4sr_upsample2x_nhwc(const void* x, int x_dtype, void* y, int batches, int h, int w, int channels, void* stream);
-/* y[b, Y, X, (py*2+px)*C + c] = x[b, 2Y+py, 2X+px, c]: with it Downsample2D (pad (0,1,0,1), 3x3, stride 2) is a 2x2
- * stride-1 convolution over 4C channels (conv_kw 2, conv_taps 4, conv_org 0; weights repacked by the host) */
-int dit4sr_space_to_depth2_nhwc(const void* x, int x_dtype, void* y, int batches, int h, int w, int channels, void* stream);
-/* p[r, :] = softmax(scale * s[r, :]) for fp32 score rows -> bf16 probabilities (the mid-block's single-head attention
- * with head_dim = channels: scores and P.V are plain GEMMs) */
-int dit4sr_softmax_rows_to_bf16(const float* s, int64_t lds, void* p, int64_t ldp, int rows, int cols, float scale, void* stream);
-/* NCHW (x_dtype DIT4SR_DT_*) [batches, channels, hw] -> NHWC bf16 [batches, hw, c_pad] (channels >= `channels` zero),
- * y = a x + b on the way (latents: a = 1 / scaling_factor, b = shift_factor) */
-int dit4sr_nchw_to_nhwc_bf16(const void* x, int x_dtype, void* y, int batches, int channels, int c_pad, int64_t hw, float a,
-                             float b, void* stream);
-/* fp32 [batches, hw, ld] (first `channels` columns) -> NCHW fp32 [batches, channels, hw] */
-int dit4sr_nhwc_to_nchw_f32(const float* x, int64_t ld, float* y, int batches, int channels, int64_t hw, void* stream);
+/* PITCHED images: the convolution mode of the GEMM needs an image width that divides 128 or is a multiple of 128, so an
+ * (h x w) activation is stored with a row pitch >= w of that kind (row y starts at pixel y * pitch; conv_w = pitch,
+ * conv_w_valid = w: the tensor map clips at w, so whatever the pad pixels hold is read as the zero padding).  The layer
+ * kernels below take the width and the pitches of their input and output and write zeros into pad pixels. */
+/* y[b, 2h, 2w, c] = x[b, h, w, c] nearest-neighbour repeat (Upsample2D before its 3x3 convolution); NHWC, x of
+ * x_dtype (DIT4SR_DT_*) [batches, h, pitch_in, c], y bf16 [batches, 2h, pitch_out, c] */
+int dit4sr_upsample2x_nhwc(const void* x, int x_dtype, void* y, int batches, int h, int w, int pitch_in, int pitch_out,
+                           int channels, void* stream);
+/* y[b, Y, X, (py*2+px)*C + c] = x[b, 2Y+py, 2X+px, c] (y bf16 [batches, h/2, pitch_out, 4C]): with it Downsample2D
+ * (pad (0,1,0,1), 3x3, stride 2) is a 2x2 stride-1 convolution over 4C channels (conv_kw 2, conv_taps 4, conv_org 0;
+ * weights repacked by the host) */
+int dit4sr_space_to_depth2_nhwc(const void* x, int x_dtype, void* y, int batches, int h, int w, int pitch_in, int pitch_out,
+                                int channels, void* stream);
+/* p[r, c] = softmax(scale * s[r, :valid_cols])[c] for c < valid_cols, 0 for valid_cols <= c < cols: fp32 score rows -> bf16
+ * probabilities (the mid-block's single-head attention with head_dim = channels: scores and P.V are plain GEMMs whose key
+ * dimension is padded to a multiple of 32) */
+int dit4sr_softmax_rows_to_bf16(const float* s, int64_t lds, void* p, int64_t ldp, int rows, int cols, int valid_cols,
+                                float scale, void* stream);
+/* NCHW (x_dtype DIT4SR_DT_*) [batches, channels, h, w] -> NHWC bf16 [batches, h, pitch, c_pad] (channels >= `channels`
+ * and pad pixels zero), y = a x + b on the way (latents: a = 1 / scaling_factor, b = shift_factor) */
+int dit4sr_nchw_to_nhwc_bf16(const void* x, int x_dtype, void* y, int batches, int channels, int c_pad, int h, int w, int pitch,
+                             float a, float b, void* stream);
+/* fp32 NHWC [batches, h, pitch, ld] (first `channels` columns) -> NCHW fp32 [batches, channels, h, w] */
+int dit4sr_nhwc_to_nchw_f32(const float* x, int64_t ld, float* y, int batches, int channels, int h, int w, int pitch,
+                            void* stream);
 
 #ifdef __cplusplus
 }

@@ -200,6 +200,8 @@ def test_upsample_softmax_and_layout_kernels(ops):
     p = torch.empty(300, 4096, device="cuda", dtype=torch.bfloat16)
     ops.softmax_rows_to_bf16(s, p, 0.05)
     assert rel(p, torch.softmax(s * 0.05, dim=-1)) < 4e-3
+    ops.softmax_rows_to_bf16(s, p, 0.05, valid_cols=4001)          # key padding: columns >= 4001 get probability 0
+    assert rel(p[:, :4001], torch.softmax(s[:, :4001] * 0.05, dim=-1)) < 4e-3 and float(p[:, 4001:].abs().max()) == 0.0
     img = torch.randn(2, 3, 8, 12, device="cuda")
     n = ops.nchw_to_nhwc_bf16(img, 64, a=0.5, b=0.25)
     assert n.shape == (2, 96, 64) and float(n[..., 3:].abs().max()) == 0.0
@@ -250,6 +252,79 @@ def test_vae_decode_and_encode_against_the_oracle(over, size, batch):
     noise = torch.randn(post.mean.shape, generator=g, device="cuda")
     assert torch.allclose(s1, post.mean + post.std * noise)
     assert rel(post.mode().cpu(), mom[:, :16]) < 1e-2
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("over,hh,ww", [(SMALL, 96, 160), (SMALL, 40, 24), (SMALL, 12, 20), ({}, 192, 320), ({}, 136, 1032)])
+def test_vae_arbitrary_image_sizes_pitched_rows(over, hh, ww):
+    """Image sides that are multiples of 8 but not powers of two: every level is stored with a row pitch that suits the
+    convolution's 128-pixel tiles (ops.conv_pitch), the tensor maps clip at the real width, GroupNorm skips the pad pixels
+    and the mid-block attention runs on the compacted tokens.  Same gates as the square cases."""
+    from dit4sr_b200 import ops
+    torch.manual_seed(2)
+    cfg = VO.sd3_vae_config(**over)
+    m, sd = _build(cfg, seed=1)
+    f = 2 ** (len(cfg.block_out_channels) - 1)
+    assert ops.conv_pitch(ww // f) != ww // f or ops.conv_pitch(ww) != ww      # at least one level is really pitched
+    z = torch.randn(1, 16, hh // f, ww // f) / cfg.scaling_factor + cfg.shift_factor
+    img = torch.rand(1, 3, hh, ww) * 2 - 1
+    with torch.no_grad():
+        got = m.decode(z.cuda(), return_dict=False)[0].float().cpu()
+        ref = VO.decoder_forward(sd, cfg, z)
+        assert got.shape == ref.shape == (1, 3, hh, ww)
+        e = rel(got, ref)
+        print(f"decode {hh}x{ww} rel-L2 {e:.3e}")
+        assert e < 1e-2
+        mom = m.encode(img.cuda()).latent_dist.parameters.cpu()
+        ref = VO.encoder_forward(sd, cfg, img)
+        assert mom.shape == ref.shape
+        e = rel(mom, ref)
+        print(f"encode {hh}x{ww} rel-L2 {e:.3e}")
+        assert e < 1e-2
+
+
+@pytest.mark.gpu
+def test_pitched_layer_kernels(ops):
+    """GroupNorm / upsample / space-to-depth / layout kernels and the 3x3 convolution on a pitched (H x W, pitch P) image
+    against the dense ones: pad pixels never influence valid pixels."""
+    from dit4sr_b200.vae import pack_conv3x3
+    torch.manual_seed(0)
+    B, H, W, C, N = 2, 6, 20, 64, 64
+    P = ops.conv_pitch(W)
+    assert P == 32
+    dense = torch.randn(B, H, W, C, device="cuda")
+    pitched = torch.full((B, H, P, C), 7.0, device="cuda")                   # pad pixels hold garbage on purpose
+    pitched[:, :, :W] = dense
+    g, b = 1 + 0.1 * torch.randn(C, device="cuda"), 0.1 * torch.randn(C, device="cuda")
+    for dt in (torch.float32, torch.bfloat16):
+        a = torch.empty(B, H * W, C, device="cuda", dtype=torch.bfloat16)
+        c = torch.empty(B, H * P, C, device="cuda", dtype=torch.bfloat16)
+        ops.groupnorm_nhwc(dense.to(dt).reshape(B, H * W, C), g, b, a, silu=True)
+        ops.groupnorm_nhwc(pitched.to(dt).reshape(B, H * P, C), g, b, c, silu=True, width=W, pitch=P)
+        assert rel(c.view(B, H, P, C)[:, :, :W], a.view(B, H, W, C)) < 2e-3
+        up = torch.empty(B, 2 * H * 2 * W, C, device="cuda", dtype=torch.bfloat16)
+        upp = torch.empty(B, 2 * H * 64, C, device="cuda", dtype=torch.bfloat16)
+        ops.upsample2x_nhwc(dense.to(dt).reshape(B, H * W, C), H, W, up)
+        ops.upsample2x_nhwc(pitched.to(dt).reshape(B, H * P, C), H, W, upp, pitch_in=P, pitch_out=64)
+        assert torch.equal(upp.view(B, 2 * H, 64, C)[:, :, :2 * W], up.view(B, 2 * H, 2 * W, C))
+        assert float(upp.view(B, 2 * H, 64, C)[:, :, 2 * W:].abs().max()) == 0.0
+        sd_ = torch.empty(B, (H // 2) * (W // 2), 4 * C, device="cuda", dtype=torch.bfloat16)
+        sdp = torch.empty(B, (H // 2) * 16, 4 * C, device="cuda", dtype=torch.bfloat16)
+        ops.space_to_depth2_nhwc(dense.to(dt).reshape(B, H * W, C), H, W, sd_)
+        ops.space_to_depth2_nhwc(pitched.to(dt).reshape(B, H * P, C), H, W, sdp, pitch_in=P, pitch_out=16)
+        assert torch.equal(sdp.view(B, H // 2, 16, 4 * C)[:, :, :W // 2], sd_.view(B, H // 2, W // 2, 4 * C))
+    w = (torch.randn(N, C, 3, 3, device="cuda") / 24).bfloat16()
+    bias = torch.randn(N, device="cuda")
+    wk, bk = pack_conv3x3(w.float(), bias)
+    out = torch.empty(B, H * P, N, device="cuda", dtype=torch.float32)
+    ops.conv3x3(pitched.bfloat16().reshape(B, H * P, C), H, P, wk.bfloat16(), bk, out, width=W)
+    ref = F.conv2d(dense.bfloat16().float().permute(0, 3, 1, 2), w.float(), bias, padding=1).permute(0, 2, 3, 1)
+    assert rel(out.view(B, H, P, N)[:, :, :W], ref) < 1e-4
+    img = torch.randn(B, 3, H, W, device="cuda")
+    n = ops.nchw_to_nhwc_bf16(img, 64, pitch=P).view(B, H, P, 64)
+    assert float(n[:, :, W:].abs().max()) == 0.0 and rel(n[:, :, :W, :3], img.permute(0, 2, 3, 1)) < 4e-3
+    f32 = torch.randn(B, H * P, 32, device="cuda")
+    assert torch.equal(ops.nhwc_to_nchw_f32(f32, 3, H, W, pitch=P), f32.view(B, H, P, 32)[:, :, :W, :3].permute(0, 3, 1, 2))
 
 
 @pytest.mark.gpu
