@@ -26,14 +26,23 @@ def lre_start_point(latents, controlnet_image, sigma0: float):
 @torch.no_grad()
 def denoise(model, latents, controlnet_image, encoder_hidden_states, pooled_projections, num_inference_steps=40,
             sigmas=None, guidance_scale: float = 1.0, negative_prompt_embeds=None, negative_pooled_prompt_embeds=None,
-            start_point: str = "noise"):
+            start_point: str = "noise", latent_tiled_size: int = 0, latent_tiled_overlap: int = 0, tile_batch: int = 0):
     """Runs the full sampling loop on the CUDA engine; returns the final latents (same dtype as `latents`).
 
     latents are carried in fp32 between steps (scheduler.step upcasts to fp32, pipeline_dit4sr.py:1567).
     guidance_scale > 1 (classifier-free guidance, pipeline_dit4sr.py:1085,1106-1108,1561-1563): every step runs the model
     on the doubled batch [uncond | text] with [negative | positive] prompt embeddings and the combine
     v_uncond + g (v_text - v_uncond) is fused with the Euler update into the model's last kernel.
-    start_point: 'noise' or 'lr' (LRE strategy, :1025-1034)."""
+    start_point: 'noise' or 'lr' (LRE strategy, :1025-1034).
+    latent_tiled_size / latent_tiled_overlap (:794-795, :1042): latents with more than tile^2 pixels (:1088) - the only way
+    non-square images reach the model, whose token grid is square (attention.py:169-172) - are denoised from overlapping
+    square tiles blended with the gaussian window (`tiling.tiled_velocity`, :1449-1558); all tiles of a step run as ONE
+    batch (tile_batch > 0 caps the tiles per model call)."""
+    h_lat, w_lat = latents.shape[-2:]
+    if latent_tiled_size > 0 and h_lat * w_lat > latent_tiled_size * latent_tiled_size:
+        return _denoise_tiled(model, latents, controlnet_image, encoder_hidden_states, pooled_projections,
+                              num_inference_steps, sigmas, guidance_scale, start_point, latent_tiled_size,
+                              latent_tiled_overlap, tile_batch)
     eng = model.engine()
     sig = flow_match_sigmas(num_inference_steps) if sigmas is None else np.asarray(sigmas, dtype=np.float32)
     B = latents.shape[0]
@@ -78,14 +87,14 @@ def denoise(model, latents, controlnet_image, encoder_hidden_states, pooled_proj
 def super_resolve(model, vae, lr_image, encoder_hidden_states, pooled_projections, num_inference_steps=40, generator=None,
                   latents=None, guidance_scale: float = 1.0, negative_prompt_embeds=None,
                   negative_pooled_prompt_embeds=None, start_point: str = "noise", sample_posterior: bool = True,
-                  output_type: str = "pt"):
+                  output_type: str = "pt", latent_tiled_size: int = 0, latent_tiled_overlap: int = 0, tile_batch: int = 0):
     """The image path of the reference's pipeline call around the loop (pipelines/pipeline_dit4sr.py:1001-1002, 1004-1034,
     1561-1567, 1602-1605), every stage on the CUDA library:
         control = (vae.encode(lr_image).latent_dist.sample() - shift_factor) * scaling_factor
         latents = 40-step flow-match Euler loop of the model (`denoise`)
         image   = vae.decode(latents / scaling_factor + shift_factor); postprocess: (image / 2 + 0.5).clamp(0, 1)
     lr_image: [B, 3, H, W] in [-1, 1] (what prepare_image / VaeImageProcessor.preprocess hand over), H and W multiples
-    of 16.  latents: optional start noise [B, 16, H/8, W/8] (drawn from `generator` otherwise).  output_type "pt" returns
+    of 16; non-square or large images need latent_tiled_size (the shipped configs use 64 with overlap 24).  latents: optional start noise [B, 16, H/8, W/8] (drawn from `generator` otherwise).  output_type "pt" returns
     the image tensor in [0, 1], "latent" the final latents (pipeline_dit4sr.py:1598-1599)."""
     cfg = vae.config
     post = vae.encode(lr_image).latent_dist
@@ -97,8 +106,40 @@ def super_resolve(model, vae, lr_image, encoder_hidden_states, pooled_projection
     final = denoise(model, latents.to(dt), control.to(dt), encoder_hidden_states, pooled_projections,
                     num_inference_steps=num_inference_steps, guidance_scale=guidance_scale,
                     negative_prompt_embeds=negative_prompt_embeds, negative_pooled_prompt_embeds=negative_pooled_prompt_embeds,
-                    start_point=start_point)
+                    start_point=start_point, latent_tiled_size=latent_tiled_size, latent_tiled_overlap=latent_tiled_overlap,
+                    tile_batch=tile_batch)
     if output_type == "latent":
         return final
     image = vae.decode(final.float() / cfg.scaling_factor + cfg.shift_factor, return_dict=False)[0]
     return (image / 2 + 0.5).clamp(0, 1)
+
+
+def _denoise_tiled(model, latents, controlnet_image, encoder_hidden_states, pooled_projections, num_inference_steps, sigmas,
+                   guidance_scale, start_point, tile, overlap, tile_batch):
+    from . import ops
+    from .tiling import tiled_velocity
+    if guidance_scale > 1.0:
+        raise NotImplementedError("tiled sampling runs at guidance_scale 1 (the reference's shipped tiled configs)")
+    sig = flow_match_sigmas(num_inference_steps) if sigmas is None else np.asarray(sigmas, dtype=np.float32)
+    B = latents.shape[0]
+    if start_point == "lr":
+        latents = lre_start_point(latents, controlnet_image, float(sig[0]))
+    elif start_point != "noise":
+        raise ValueError("start_point must be 'noise' or 'lr'")
+    dt = model.dtype
+    control = controlnet_image.to(dt)
+    x = latents.float().contiguous()
+    nxt = torch.empty_like(x)
+    for i in range(len(sig) - 1):
+        t_i = float(sig[i]) * 1000.0
+
+        def model_fn(lat, ctl):
+            n = lat.shape[0] // B                                      # tiles in this call (batch index = tile * B + image)
+            t = torch.full((lat.shape[0],), t_i, device=lat.device, dtype=torch.float32)
+            return model(lat.to(dt), ctl, encoder_hidden_states.repeat(n, 1, 1), pooled_projections.repeat(n, 1), t,
+                         return_dict=False)[0]
+
+        v = tiled_velocity(model_fn, x, control, tile, overlap, tile_batch=tile_batch).contiguous()
+        ops.euler_update(x, v, nxt, float(sig[i + 1]) - float(sig[i]))
+        x, nxt = nxt, x
+    return x.to(latents.dtype)

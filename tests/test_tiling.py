@@ -67,3 +67,34 @@ def test_tiled_velocity_on_gpu_matches_oracle():
     out = tiled_velocity(gpu_fn, lat.cuda(), ctl.cuda(), 32, 8).cpu()
     ref = O.tiled_velocity_as_written(cpu_fn, lat, ctl, 32, 8)
     assert ((out - ref).norm() / ref.norm()).item() <= 1e-2
+
+
+@pytest.mark.gpu
+def test_tiled_sampling_loop_of_a_non_square_latent():
+    """denoise(..., latent_tiled_size, latent_tiled_overlap) on a 40x56 latent (a 320x448 image): three Euler steps, every
+    step's velocity blended from overlapping 32x32 tiles run as one batch, against the oracle's as-written tile loop."""
+    import dit4sr_b200
+    from dit4sr_b200.sampler import denoise
+    cfg = O.sd35_medium_config(num_layers=2, dual_attention_layers=(0,), pos_embed_max_size=96)
+    sd = O.init_state_dict(cfg, seed=0)
+    m = dit4sr_b200.SD3Transformer2DModel(**vars(cfg))
+    m.load_state_dict(sd)
+    m = m.to("cuda", torch.bfloat16).requires_grad_(False).eval()
+    g = torch.Generator().manual_seed(5)
+    lat, ctl = torch.randn(1, 16, 40, 56, generator=g), torch.randn(1, 16, 40, 56, generator=g)
+    _, _, enc, pooled, _ = O.make_inputs(cfg, 1, 8, 8, 20)
+    bf = torch.bfloat16
+    out = denoise(m, lat.cuda(), ctl.cuda(), enc.cuda().to(bf), pooled.cuda().to(bf), num_inference_steps=3,
+                  latent_tiled_size=32, latent_tiled_overlap=8).float().cpu()
+    sig = O.flow_match_sigmas(3)
+    x = lat.clone()
+    for i in range(3):
+        t = torch.full((1,), float(sig[i]) * 1000.0)
+
+        def cpu_fn(xt, ct):
+            n = xt.shape[0]
+            return O.model_forward(sd, cfg, xt, ct, enc.expand(n, -1, -1), pooled.expand(n, -1), t.expand(n), as_written=False)
+
+        x = x + (float(sig[i + 1]) - float(sig[i])) * O.tiled_velocity_as_written(cpu_fn, x, ctl, 32, 8)
+    assert out.shape == x.shape
+    assert ((out - x).norm() / x.norm()).item() <= 1e-2
