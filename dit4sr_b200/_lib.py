@@ -13,7 +13,9 @@ class LnModulateParams(C.Structure):
                 ("shift", c_vp), ("scale", c_vp), ("shift2", c_vp), ("scale2", c_vp),
                 ("mod_batch_stride", c_i64), ("out", c_vp), ("out2", c_vp),
                 ("ldo", c_i64), ("o_batch_stride", c_i64),
-                ("batches", c_int), ("rows", c_int), ("dim", c_int), ("eps", c_float), ("out_f32", c_int)]
+                ("batches", c_int), ("rows", c_int), ("dim", c_int), ("eps", c_float), ("out_f32", c_int),
+                ("x_b", c_vp), ("ldx_b", c_i64), ("x_b_batch_stride", c_i64), ("shift_b", c_vp), ("scale_b", c_vp),
+                ("out_b", c_vp), ("ldo_b", c_i64), ("o_b_batch_stride", c_i64), ("rows_b", c_int)]
 
 
 class DwconvParams(C.Structure):

@@ -189,13 +189,22 @@ ln_modulate_tma2_kernel(const dit4sr_ln_modulate_params p) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   uint8_t* slots = smem + (size_t)warp * LN_STAGES * ROW_BYTES;
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)LN_WARPS * LN_STAGES * ROW_BYTES) + warp * LN_STAGES;
-  const int64_t total = (int64_t)p.batches * p.rows;
+  // rows [0, total_a) are the main problem, [total_a, total) the companion (ABI v5: the text stream's rows ride in the
+  // image stream's launch; always single-output)
+  const int64_t total_a = (int64_t)p.batches * p.rows;
+  const int64_t total = total_a + (int64_t)p.batches * p.rows_b;
   const int64_t nwarps = (int64_t)gridDim.x * LN_WARPS;
   const int64_t first = (int64_t)blockIdx.x * LN_WARPS + warp;
   auto row_ptr = [&](int64_t rid) {
-    const int b = (int)(rid / p.rows);
-    const int r = (int)(rid % p.rows);
-    return p.x + (int64_t)b * p.x_batch_stride + (int64_t)r * p.ldx;
+    if (rid < total_a) {
+      const int b = (int)(rid / p.rows);
+      const int r = (int)(rid % p.rows);
+      return p.x + (int64_t)b * p.x_batch_stride + (int64_t)r * p.ldx;
+    }
+    rid -= total_a;
+    const int b = (int)(rid / p.rows_b);
+    const int r = (int)(rid % p.rows_b);
+    return p.x_b + (int64_t)b * p.x_b_batch_stride + (int64_t)r * p.ldx_b;
   };
   if (lane == 0) {
     for (int s = 0; s < LN_STAGES; ++s) ptx::mbar_init(&bars[s], 1);
@@ -215,23 +224,31 @@ ln_modulate_tma2_kernel(const dit4sr_ln_modulate_params p) {
   __syncwarp();
   const float inv_dim = 1.0f / (float)(NV * 128);
   float4 ca[DUAL ? 1 : NV], ct[DUAL ? 1 : NV];   // (1 + scale), shift of batch `cached_b` (single-output instance)
-  int cached_b = -1;
+  int cached_b = -1;                             // companion rows use the keys batches + b
   int k = 0;
   for (int64_t rid = first; rid < total; rid += nwarps, ++k) {
     const int s = k % LN_STAGES;
-    const int b = (int)(rid / p.rows);
-    const int r = (int)(rid % p.rows);
+    const bool comp = rid >= total_a;
+    const int64_t lrid = comp ? rid - total_a : rid;
+    const int prow = comp ? p.rows_b : p.rows;
+    const int b = (int)(lrid / prow);
+    const int r = (int)(lrid % prow);
+    const float* shift_v = (comp ? p.shift_b : p.shift) + (int64_t)b * p.mod_batch_stride;
+    const float* scale_v = (comp ? p.scale_b : p.scale) + (int64_t)b * p.mod_batch_stride;
+    __nv_bfloat16* out_row = comp ? reinterpret_cast<__nv_bfloat16*>(p.out_b) + (int64_t)b * p.o_b_batch_stride + (int64_t)r * p.ldo_b
+                                  : reinterpret_cast<__nv_bfloat16*>(p.out) + (int64_t)b * p.o_batch_stride + (int64_t)r * p.ldo;
     if constexpr (!DUAL) {
-      if (b != cached_b) {
-        const float4* sh = reinterpret_cast<const float4*>(p.shift + (int64_t)b * p.mod_batch_stride) + lane;
-        const float4* sc = reinterpret_cast<const float4*>(p.scale + (int64_t)b * p.mod_batch_stride) + lane;
+      const int key = comp ? p.batches + b : b;
+      if (key != cached_b) {
+        const float4* sh = reinterpret_cast<const float4*>(shift_v) + lane;
+        const float4* sc = reinterpret_cast<const float4*>(scale_v) + lane;
 #pragma unroll
         for (int i = 0; i < NV; ++i) {
           const float4 a = __ldg(sc + i * 32);
           ca[i] = make_float4(1.f + a.x, 1.f + a.y, 1.f + a.z, 1.f + a.w);
           ct[i] = __ldg(sh + i * 32);
         }
-        cached_b = b;
+        cached_b = key;
       }
     }
     ptx::mbar_wait(&bars[s], (k / LN_STAGES) & 1);
@@ -279,8 +296,7 @@ ln_modulate_tma2_kernel(const dit4sr_ln_modulate_params p) {
       return ptx::pack_bf16(o0, o1);
     };
     if constexpr (!DUAL) {
-      uint2* out = reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(p.out) + (int64_t)b * p.o_batch_stride +
-                                            (int64_t)r * p.ldo) + lane;
+      uint2* out = reinterpret_cast<uint2*>(out_row) + lane;
 #pragma unroll
       for (int i = 0; i < NV; ++i) {
         uint2 o;
@@ -289,12 +305,13 @@ ln_modulate_tma2_kernel(const dit4sr_ln_modulate_params p) {
         out[i * 32] = o;
       }
     } else {
-#pragma unroll
-      for (int which = 0; which < 2; ++which) {
-        const float4* sh = reinterpret_cast<const float4*>((which ? p.shift2 : p.shift) + (int64_t)b * p.mod_batch_stride) + lane;
-        const float4* sc = reinterpret_cast<const float4*>((which ? p.scale2 : p.scale) + (int64_t)b * p.mod_batch_stride) + lane;
-        uint2* out = reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(which ? p.out2 : p.out) +
-                                              (int64_t)b * p.o_batch_stride + (int64_t)r * p.ldo) + lane;
+      const int n_out = comp ? 1 : 2;
+      for (int which = 0; which < n_out; ++which) {
+        const float4* sh = reinterpret_cast<const float4*>(which ? p.shift2 + (int64_t)b * p.mod_batch_stride : shift_v) + lane;
+        const float4* sc = reinterpret_cast<const float4*>(which ? p.scale2 + (int64_t)b * p.mod_batch_stride : scale_v) + lane;
+        uint2* out = reinterpret_cast<uint2*>(which ? reinterpret_cast<__nv_bfloat16*>(p.out2) + (int64_t)b * p.o_batch_stride +
+                                                          (int64_t)r * p.ldo
+                                                    : out_row) + lane;
 #pragma unroll
         for (int i = 0; i < NV; ++i) {
           const float4 a = __ldg(sc + i * 32), t = __ldg(sh + i * 32);
@@ -393,7 +410,7 @@ static void launch_bf16(const dit4sr_ln_modulate_params& p, cudaStream_t stream)
 
 template <int NV>
 static int launch(const dit4sr_ln_modulate_params& p, cudaStream_t stream) {
-  const int64_t total = (int64_t)p.batches * p.rows;
+  const int64_t total = (int64_t)p.batches * p.rows + (int64_t)p.batches * p.rows_b;
   static int variant = -1;   // developer switch DIT4SR_LN_VARIANT: warps per CTA (4|8) + 10 for one-pass statistics
   if (variant < 0) {
     const char* e = getenv("DIT4SR_LN_VARIANT");
@@ -401,7 +418,9 @@ static int launch(const dit4sr_ln_modulate_params& p, cudaStream_t stream) {
   }
   {
     constexpr int SMEM2 = LN_WARPS * LN_STAGES * NV * 128 * 4 + LN_WARPS * LN_STAGES * 8 + 128;
-    if (!p.out_f32 && variant == 9 && SMEM2 <= 220 * 1024 && (reinterpret_cast<uintptr_t>(p.out) & 7) == 0 &&
+    const bool comp_ok = p.rows_b == 0 || ((reinterpret_cast<uintptr_t>(p.out_b) & 7) == 0 && p.ldo_b % 4 == 0 &&
+                                           p.o_b_batch_stride % 4 == 0);
+    if (!p.out_f32 && variant == 9 && SMEM2 <= 220 * 1024 && (reinterpret_cast<uintptr_t>(p.out) & 7) == 0 && comp_ok &&
         p.ldo % 4 == 0 && p.o_batch_stride % 4 == 0 && (p.out2 == nullptr || (reinterpret_cast<uintptr_t>(p.out2) & 7) == 0)) {
       static unsigned long long configured2 = 0;   // per (instance, device)
       if (host::first_use_on_device(&configured2)) {
@@ -417,6 +436,17 @@ static int launch(const dit4sr_ln_modulate_params& p, cudaStream_t stream) {
         DIT4SR_CUDA(host::launch_pdl(ln_modulate_tma2_kernel<NV, false>, dim3(grid), dim3(LN_WARPS * 32), (size_t)SMEM2, stream, p));
       return 0;
     }
+  }
+  if (p.rows_b > 0) {   // the other kernels serve one problem per launch: main problem, then the companion as its own
+    dit4sr_ln_modulate_params a = p, c = p;
+    a.rows_b = 0;
+    c.rows_b = 0;
+    c.x = p.x_b; c.ldx = p.ldx_b; c.x_batch_stride = p.x_b_batch_stride;
+    c.shift = p.shift_b; c.scale = p.scale_b; c.shift2 = nullptr; c.scale2 = nullptr;
+    c.out = p.out_b; c.out2 = nullptr; c.ldo = p.ldo_b; c.o_batch_stride = p.o_b_batch_stride;
+    c.rows = p.rows_b;
+    const int rc = launch<NV>(a, stream);
+    return rc != 0 ? rc : launch<NV>(c, stream);
   }
   if constexpr (NV % 2 == 0) {
     constexpr int SMEM = LN_WARPS * LN_STAGES * NV * 128 * 4 + LN_WARPS * LN_STAGES * 8 + 128;
@@ -463,6 +493,16 @@ extern "C" int dit4sr_ln_modulate(const dit4sr_ln_modulate_params* p, void* stre
                      p->mod_batch_stride % 4 == 0 && host::aligned16(p->x) && host::aligned16(p->shift) &&
                      host::aligned16(p->scale) && (reinterpret_cast<uintptr_t>(p->out) & 7) == 0,
                  DIT4SR_E_ALIGN, "ln_modulate: pointers/strides not 16-byte aligned");
+  if (p->rows_b > 0) {   // companion problem (ABI v5)
+    DIT4SR_REQUIRE(p->x_b && p->shift_b && p->scale_b && p->out_b, DIT4SR_E_BADARG,
+                   "ln_modulate: companion problem (rows_b > 0) with a null pointer");
+    DIT4SR_REQUIRE(p->ldx_b % 4 == 0 && p->x_b_batch_stride % 4 == 0 && p->ldo_b % 4 == 0 && p->o_b_batch_stride % 4 == 0 &&
+                       host::aligned16(p->x_b) && host::aligned16(p->shift_b) && host::aligned16(p->scale_b) &&
+                       (reinterpret_cast<uintptr_t>(p->out_b) & 7) == 0,
+                   DIT4SR_E_ALIGN, "ln_modulate: companion pointers/strides not 16-byte aligned");
+  } else {
+    DIT4SR_REQUIRE(p->rows_b == 0, DIT4SR_E_BADARG, "ln_modulate: negative rows_b");
+  }
   switch (p->dim) {
     case 128: return lnmod::launch<1>(*p, stream);
     case 256: return lnmod::launch<2>(*p, stream);

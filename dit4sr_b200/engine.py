@@ -712,26 +712,28 @@ class Engine:
 
             shift_msa, scale_msa, gate_msa = ch(o1, 0), ch(o1, 1), ch(o1, 2)
             shift_mlp, scale_mlp, gate_mlp = ch(o1, 3), ch(o1, 4), ch(o1, 5)
-            if bp.dual:
-                shift_msa2, scale_msa2, gate_msa2 = ch(o1, 6), ch(o1, 7), ch(o1, 8)
-                R("ln_mod", ops.ln_modulate, x, shift_msa, scale_msa, n1, shift_msa2, scale_msa2, n2)
-            else:
-                R("ln_mod", ops.ln_modulate, x, shift_msa, scale_msa, n1)
+            # the text stream's LayerNorm rides in the image stream's launch (companion problem of dit4sr_ln_modulate)
             if bp.last:   # AdaLayerNormContinuous: (scale, shift) order (Q12)
                 c_scale, c_shift = ch(o2, 0), ch(o2, 1)
-                R("ln_mod", ops.ln_modulate, ctx, c_shift, c_scale, nc)
                 c_gate_msa = None
+                text_ln = (ctx, c_shift, c_scale, nc)
             else:
                 c_shift_msa, c_scale_msa, c_gate_msa = ch(o2, 0), ch(o2, 1), ch(o2, 2)
                 c_shift_mlp, c_scale_mlp, c_gate_mlp = ch(o2, 3), ch(o2, 4), ch(o2, 5)
-                R("ln_mod", ops.ln_modulate, ctx, c_shift_msa, c_scale_msa, nc)
+                text_ln = (ctx, c_shift_msa, c_scale_msa, nc)
+            if bp.dual:
+                shift_msa2, scale_msa2, gate_msa2 = ch(o1, 6), ch(o1, 7), ch(o1, 8)
+                R("ln_mod", ops.ln_modulate, x, shift_msa, scale_msa, n1, shift_msa2, scale_msa2, n2, companion=text_ln)
+            else:
+                R("ln_mod", ops.ln_modulate, x, shift_msa, scale_msa, n1, companion=text_ln)
             self._attention(bp.attn, ws, n1, nc, N, T, gate_msa, c_gate_msa, bp.last)
             if bp.dual:
                 # 3-stream model: attn2 is still the 2-stream processor, so it halves the 3N tokens at 1.5N (Q6)
                 n_seg = N if self.streams == 2 else (3 * N) // 2
                 self._attention(bp.attn2, ws, n2, None, n_seg, T, gate_msa2, None, bp.last)
             # MLP with the LR->HQ depthwise conv (attention.py:322-347, FeedForwardControl :155-178)
-            R("ln_mod", ops.ln_modulate, x, shift_mlp, scale_mlp, n1)
+            R("ln_mod", ops.ln_modulate, x, shift_mlp, scale_mlp, n1,
+              companion=None if bp.last else (ctx, c_shift_mlp, c_scale_mlp, nc))
             if self.sp is not None and self.sp.peer:   # u keeps a halo grid row on either side of its LR rows
                 u_hq, u_lr = ws["u"][:, :N], ws["u"][:, N + grid:2 * N + grid]
                 ff1 = [dict(A=n1[:, :N], W=bp.ff1.w, bias=bp.ff1.b, out=u_hq, epilogue=ops.EPI_BIAS_GELU),
@@ -743,7 +745,6 @@ class Engine:
                 ff1 = [dict(A=n1, W=bp.ff1.w, bias=bp.ff1.b, out=ws["u"], epilogue=ops.EPI_BIAS_GELU)]
                 ff2 = [dict(A=ws["u"], W=bp.ff2.w, bias=bp.ff2.b, out=x, epilogue=ops.EPI_GATE_RESID, gate=gate_mlp)]
             if not bp.last:   # text MLP (attention.py:384-393) rides in the same launches
-                R("ln_mod", ops.ln_modulate, ctx, c_shift_mlp, c_scale_mlp, nc)
                 ff1.append(dict(A=nc, W=bp.ffc1.w, bias=bp.ffc1.b, out=ws["uc"], epilogue=ops.EPI_BIAS_GELU))
                 ff2.append(dict(A=ws["uc"], W=bp.ffc2.w, bias=bp.ffc2.b, out=ctx, epilogue=ops.EPI_GATE_RESID,
                                 gate=c_gate_mlp))

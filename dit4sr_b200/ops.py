@@ -45,8 +45,9 @@ def _as3(t):
     return t.unsqueeze(0) if t.dim() == 2 else t
 
 
-def ln_modulate(x, shift, scale, out, shift2=None, scale2=None, out2=None, eps=1e-6):
-    """out = LN(x) * (1 + scale[b]) + shift[b]  (and optionally out2 with shift2/scale2). x fp32 [B,R,D]; out bf16."""
+def ln_modulate(x, shift, scale, out, shift2=None, scale2=None, out2=None, eps=1e-6, companion=None):
+    """out = LN(x) * (1 + scale[b]) + shift[b]  (and optionally out2 with shift2/scale2). x fp32 [B,R,D]; out bf16.
+    companion = (x_b, shift_b, scale_b, out_b): a second tensor [B,R_b,D] (the text stream) normalised by the same launch."""
     x = _as3(x)
     out = _as3(out)
     _req(x, torch.float32, "x")
@@ -72,6 +73,22 @@ def ln_modulate(x, shift, scale, out, shift2=None, scale2=None, out2=None, eps=1
         p.out2, p.shift2, p.scale2 = _ptr(out2), _ptr(shift2), _ptr(scale2)
     p.batches, p.rows, p.dim, p.eps = B, R, D, eps
     p.out_f32 = 1 if out_dtype == torch.float32 else 0
+    if companion is not None:
+        xb, shb, scb, ob = companion
+        xb, ob = _as3(xb), _as3(ob)
+        _req(xb, torch.float32, "companion x")
+        _req(ob, out_dtype, "companion out")
+        for n, t in (("companion shift", shb), ("companion scale", scb)):
+            _req(t, torch.float32, n)
+        if xb.shape[0] != B or xb.shape[2] != D or ob.shape != xb.shape:
+            raise _lib.Dit4srError("ln_modulate: companion must be [batches, rows_b, dim] like x, with an output of its shape")
+        mbs = shb.stride(0) if shb.dim() == 2 else 0
+        if mbs != p.mod_batch_stride or (scb.stride(0) if scb.dim() == 2 else 0) != mbs:
+            raise _lib.Dit4srError("ln_modulate: companion shift/scale must share the batch stride of shift/scale")
+        p.x_b, p.ldx_b, p.x_b_batch_stride = _ptr(xb), xb.stride(1), xb.stride(0)
+        p.shift_b, p.scale_b = _ptr(shb), _ptr(scb)
+        p.out_b, p.ldo_b, p.o_b_batch_stride = _ptr(ob), ob.stride(1), ob.stride(0)
+        p.rows_b = xb.shape[1]
     check(_lib.load().dit4sr_ln_modulate(C.byref(p), _stream()), "dit4sr_ln_modulate")
     _count()
 

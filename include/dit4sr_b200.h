@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define DIT4SR_ABI_VERSION 4
+#define DIT4SR_ABI_VERSION 5
 
 enum {
   DIT4SR_OK = 0,
@@ -58,6 +58,14 @@ typedef struct {
   int batches; int rows; int dim;
   float eps;
   int out_f32;                         /* 1: out/out2 are fp32 (fp32-accurate mode) instead of bf16 */
+  /* ABI v5.  Optional companion problem served by the same launch (rows_b > 0): a second fp32 [batches, rows_b, dim] tensor
+   * with its own modulation vectors (same mod_batch_stride) and one output of the same kind as `out`.  The engine passes
+   * the text stream here (norm1_context / the text half of norm2, attention.py:294-302,384-385) next to the image stream,
+   * which halves the number of LayerNorm launches per block; a few thousand text rows alone cannot fill the GPU. */
+  const float* x_b; int64_t ldx_b; int64_t x_b_batch_stride;
+  const float* shift_b; const float* scale_b;
+  void* out_b; int64_t ldo_b; int64_t o_b_batch_stride;
+  int rows_b;
 } dit4sr_ln_modulate_params;
 int dit4sr_ln_modulate(const dit4sr_ln_modulate_params* p, void* stream);
 

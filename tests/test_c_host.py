@@ -20,4 +20,4 @@ def test_plain_c_host_links_and_runs(tmp_path):
                            os.path.join(ROOT, "tools", "c_host", "schedule_demo.c"), "-L", libdir, "-ldit4sr_b200",
                            "-Wl,-rpath," + libdir, "-o", exe])
     out = subprocess.check_output([exe], text=True)
-    assert out.startswith("abi 4 items 984 sliced 96 "), out      # 888 whole tiles + 24 remainder tiles in 4 slices each
+    assert out.startswith("abi 5 items 984 sliced 96 "), out      # 888 whole tiles + 24 remainder tiles in 4 slices each

@@ -38,6 +38,35 @@ def test_ln_modulate(ops, B, R, D):
     assert rel(o2.float(), ln * (1 + sc2[:, None]) + sh2[:, None]) < BF16_TOL
 
 
+@pytest.mark.parametrize("B,R,Rb,D,dual,f32", [(2, 2048, 333, 1536, False, False), (3, 700, 333, 1536, True, False),
+                                               (1, 5, 9, 128, False, False), (8, 1, 1, 1536, True, False),
+                                               (2, 300, 77, 1536, False, True)])
+def test_ln_modulate_companion(ops, B, R, Rb, D, dual, f32):
+    """ABI v5: the text stream's rows normalised by the image stream's launch (own modulation vectors, single output);
+    bit-identical to two separate launches."""
+    torch.manual_seed(0)
+    x = torch.randn(B, R, D, device="cuda") * 2 + 0.5
+    xb = torch.randn(B, Rb, D, device="cuda") * 3 - 0.25
+    mod = torch.randn(B, 6 * D, device="cuda") * 0.5
+    sh, sc, sh2, sc2, shb, scb = (mod[:, i * D:(i + 1) * D] for i in range(6))
+    dt = torch.float32 if f32 else torch.bfloat16
+    o1, o2, ob = (torch.full((B, r, D), float("nan"), device="cuda", dtype=dt) for r in (R, R, Rb))
+    if dual:
+        ops.ln_modulate(x, sh, sc, o1, sh2, sc2, o2, companion=(xb, shb, scb, ob))
+    else:
+        ops.ln_modulate(x, sh, sc, o1, companion=(xb, shb, scb, ob))
+    tol = F32_TOL if f32 else BF16_TOL
+    ln, lnb = (torch.nn.functional.layer_norm(t, (D,), eps=1e-6) for t in (x, xb))
+    assert rel(o1.float(), ln * (1 + sc[:, None]) + sh[:, None]) < tol
+    assert rel(ob.float(), lnb * (1 + scb[:, None]) + shb[:, None]) < tol
+    if dual:
+        assert rel(o2.float(), ln * (1 + sc2[:, None]) + sh2[:, None]) < tol
+    s1, sb = torch.empty_like(o1), torch.empty_like(ob)
+    ops.ln_modulate(x, sh, sc, s1)
+    ops.ln_modulate(xb, shb, scb, sb)
+    assert torch.equal(s1, o1) and torch.equal(sb, ob)
+
+
 @pytest.mark.parametrize("B,G,C", [(2, 32, 6144), (1, 5, 512), (1, 64, 256), (1, 1, 8)])
 def test_dwconv_matches_conv2d(ops, B, G, C):
     torch.manual_seed(0)

@@ -26,7 +26,7 @@ def test_header_symbols_all_exported(lib):
     assert declared == set(_lib.SYMBOLS), declared ^ set(_lib.SYMBOLS)
     for name in declared:
         assert hasattr(lib, name)
-    assert lib.dit4sr_abi_version() == 4
+    assert lib.dit4sr_abi_version() == 5
 
 
 def test_bad_arguments_are_rejected_without_a_gpu(lib):

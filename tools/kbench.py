@@ -132,6 +132,12 @@ def main():
         print(f"ln single: {ms:.4f} ms  {B * 2 * N * D * 6 / ms / 1e6:.0f} GB/s")
         ms = timeit(lambda: ops.ln_modulate(x, mod[:, :D], mod[:, D:2 * D], o1, mod[:, 2 * D:3 * D], mod[:, 3 * D:], o2), a.reps)
         print(f"ln dual: {ms:.4f} ms  {B * 2 * N * D * 8 / ms / 1e6:.0f} GB/s")
+        # text stream: its own launch against riding in the image stream's launch (companion problem, ABI v5)
+        ctx = torch.randn(B, T, D, device=dev)
+        oc = torch.empty(B, T, D, device=dev, dtype=torch.bfloat16)
+        ms_t = timeit(lambda: ops.ln_modulate(ctx, mod[:, :D], mod[:, D:2 * D], oc), a.reps)
+        ms_c = timeit(lambda: ops.ln_modulate(x, mod[:, :D], mod[:, D:2 * D], o1, companion=(ctx, mod[:, 2 * D:3 * D], mod[:, 3 * D:], oc)), a.reps)
+        print(f"ln text alone: {ms_t:.4f} ms; image + text in one launch: {ms_c:.4f} ms  {B * (2 * N + T) * D * 6 / ms_c / 1e6:.0f} GB/s")
 
 
 if __name__ == "__main__":
