@@ -107,6 +107,31 @@ def measured_peaks():
     return dict(tf_burst=1590.0, tf_sustained=1400.0, hbm=6650.0, source="B200_PROFILING.md fallback")
 
 
+def hbm_rooflines(breakdown, B, N, T, n_layers, n_dual, peaks, D=1536, F=6144):
+    """`roofline_hbm`: the two HBM-bound kernel classes of a 2-stream step against the measured copy bandwidth, from the
+    instrumented step's CUDA-event times (in situ: cold L2, clocks of the power-capped step).  Algorithmic bytes (SURVEY
+    8d with the fp32 residual stream this build keeps): LayerNorm+modulate reads 4 B and writes 2 B per element and output
+    (two outputs on the dual blocks; the text rows ride in the same launches); the stencil reads u_lr, reads and writes u_hq.
+    In situ these kernels also carry the write-back of what the kernel before them left dirty in the 126 MB L2 (the fp32
+    residual stream after a reduce-add epilogue, the MLP hidden state after FF1), which is not in their algorithmic bytes:
+    alone, on warm buffers, tools/kbench.py measures 0.84 (LayerNorm) and 0.91 (stencil) of the same peak."""
+    if not breakdown or "ln_mod" not in breakdown or "dwconv" not in breakdown:
+        return None
+    img, txt = 2 * N * B, T * B
+    ln = 0
+    for i in range(n_layers):
+        ln += img * D * (4 + 2 * (2 if i < n_dual else 1)) + txt * D * 6      # norm1 (+ second modulation), norm1_context
+        ln += img * D * 6 + (txt * D * 6 if i < n_layers - 1 else 0)          # norm2, text norm2 (absent in the last block)
+    conv = n_layers * 3 * N * B * F * 2
+    out = {}
+    for name, key, nbytes in (("ln_modulate", "ln_mod", ln), ("dwconv3x3", "dwconv", conv)):
+        ms = breakdown[key]["total_ms"]
+        ach = nbytes / (ms / 1e3) / 1e9
+        out[name] = dict(bound="hbm", achieved=round(ach, 1), peak=peaks["hbm"], unit="GB/s", frac=round(ach / peaks["hbm"], 4),
+                         launches=breakdown[key]["launches"], total_ms=ms, algorithmic_bytes_per_step=nbytes)
+    return out
+
+
 def attention_roofline(launch_ms, flops_per_step, launches_per_step, peaks, root=ROOT):
     """`roofline` entry of the joint-attention kernel: algorithmic FLOPs per launch (average over the joint and the
     image-only calls of a step) / average launch duration measured with CUDA events; traffic from the committed ncu
@@ -118,10 +143,11 @@ def attention_roofline(launch_ms, flops_per_step, launches_per_step, peaks, root
     ach = flops / (avg_ms / 1e3) / 1e12
     traffic = src = None
     try:
-        prof = json.load(open(os.path.join(root, "profiles", "r01e_ncu_full_attention.json")))
-        k = next(k for k in prof if "attn_fwd2_kernel" in k["Kernel Name"])
+        prof = json.load(open(os.path.join(root, "profiles", "r02b_ncu_full.json")))
+        k = next(k for k in prof if "attn_fwd5_kernel" in k["Kernel Name"])
         traffic = round((float(k["dram__bytes_read.sum [Mbyte]"]) + float(k["dram__bytes_write.sum [Mbyte]"])) * 1e6)
-        src = ("from committed capture profiles/r01e_ncu_full_attention.json (not measured in this run): dram__bytes_read.sum + dram__bytes_write.sum of one joint-attention "
+        src = ("from committed capture profiles/r02b_ncu_full.json of the same kernel (attn_fwd5_kernel; not measured in this run): "
+               "dram__bytes_read.sum + dram__bytes_write.sum of one joint-attention "
                "launch (S=2381, B=8; algorithmic 263 MB q|k|v read + 59 MB o written + 50 MB LR residual read)")
     except (OSError, KeyError, ValueError, StopIteration):
         pass
@@ -564,7 +590,10 @@ def run_ours(args):
             e2e=dict(value=round(img_steps / (e2e_ms / 1e3), 3), unit=UNIT, h2d_bytes_per_step=h2d,
                      d2h_bytes_per_step=d2h, ms_per_step=round(e2e_ms / args.steps, 3),
                      api="dit4sr_b200.SD3Transformer2DModel.forward; every step copies its inputs from pinned host memory (double-buffered on a copy stream, one step ahead) and reads the velocity back"),
-            gpu_launches=launches, clocks=clocks, roofline=roof_attn, roofline_gemm=roof, cpu_baseline=cpu,
+            gpu_launches=launches, clocks=clocks, roofline=roof_attn, roofline_gemm=roof,
+            roofline_hbm=(hbm_rooflines(breakdown, B, N, T, n_layers, n_dual, peaks)
+                          if mode != "sp" and args.workload != "c5" else None),
+            cpu_baseline=cpu,
             parity=parity, kernel_breakdown_ms=breakdown, north_star_scaling=ns,
         )
         print(json.dumps(line))
