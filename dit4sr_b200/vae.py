@@ -207,6 +207,9 @@ class AutoencoderKL(nn.Module):
         self.quant_conv = None
         self.post_quant_conv = None
         self._packed = None
+        # CUDA graphs of encode / decode per input shape (the ~140 launches of a decode are launch-paced at small sizes)
+        self.use_cuda_graph = os.environ.get("DIT4SR_VAE_GRAPH", "1") != "0"
+        self._graphs = {}
 
     # ---- config / io surface
     @property
@@ -246,11 +249,44 @@ class AutoencoderKL(nn.Module):
 
     def _apply(self, fn, *args, **kwargs):
         self._packed = None
+        self._graphs = {}
         return super()._apply(fn, *args, **kwargs)
 
     def load_state_dict(self, *args, **kwargs):
         self._packed = None
+        self._graphs = {}
         return super().load_state_dict(*args, **kwargs)
+
+    GRAPH_MAX_PIXELS = 1024 * 1024     # image pixels per batch entry times batch: beyond this the kernels are long enough
+    GRAPH_MAX_CACHED = 4               # captured graphs keep their activations (about 2.9 GiB for a 1024px decode)
+
+    def _graphed(self, kind, fn, x, pixels):
+        """fn(x) replayed from a CUDA graph captured per (kind, shape, dtype, device): same kernels, same results.  Large
+        images (and anything that fails to capture) are launched directly."""
+        if not self.use_cuda_graph or pixels > self.GRAPH_MAX_PIXELS or torch.cuda.is_current_stream_capturing():
+            return fn(x)
+        key = (kind, tuple(x.shape), x.dtype, x.device)
+        ent = self._graphs.get(key)
+        if ent is None:
+            static_in = x.clone()
+            fn(static_in)                                   # warm-up outside capture: packs weights, function attributes
+            torch.cuda.synchronize(x.device)
+            try:
+                graph = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(graph):
+                    static_out = fn(static_in)
+            except Exception as e:   # noqa: BLE001  (capture not possible here: keep launching directly)
+                import warnings
+                warnings.warn(f"dit4sr_b200.AutoencoderKL: CUDA graph capture failed ({e}); using direct launches")
+                self.use_cuda_graph = False
+                return fn(x)
+            if len(self._graphs) >= self.GRAPH_MAX_CACHED:
+                self._graphs.pop(next(iter(self._graphs)))
+            ent = self._graphs[key] = (graph, static_in, static_out)
+        graph, static_in, static_out = ent
+        static_in.copy_(x)
+        graph.replay()
+        return static_out.clone()
 
     # tiling / slicing switches of diffusers' class: accepted, nothing to switch (the untiled network fits)
     def enable_tiling(self, *a, **k): pass
@@ -436,7 +472,9 @@ class AutoencoderKL(nn.Module):
         return ops.nhwc_to_nchw_f32(m, 2 * cfg.latent_channels, H, W, pitch=P)
 
     def encode(self, x: torch.Tensor, return_dict: bool = True):
-        posterior = DiagonalGaussianDistribution(self._encode_moments(x).to(x.dtype if x.is_floating_point() else torch.float32))
+        self._check_input(x, self.config.in_channels)
+        moments = self._graphed("enc", self._encode_moments, x, x.shape[0] * x.shape[2] * x.shape[3])
+        posterior = DiagonalGaussianDistribution(moments.to(x.dtype if x.is_floating_point() else torch.float32))
         return AutoencoderKLOutput(latent_dist=posterior) if return_dict else (posterior,)
 
     @torch.no_grad()
@@ -463,7 +501,9 @@ class AutoencoderKL(nn.Module):
         return ops.nhwc_to_nchw_f32(img, cfg.out_channels, H, W, pitch=P)
 
     def decode(self, z: torch.Tensor, return_dict: bool = True, generator=None):
-        dec = self._decode(z).to(z.dtype)
+        self._check_input(z, self.config.latent_channels)
+        f = 1 << (len(self.config.block_out_channels) - 1)
+        dec = self._graphed("dec", self._decode, z, z.shape[0] * z.shape[2] * z.shape[3] * f * f).to(z.dtype)
         return DecoderOutput(sample=dec) if return_dict else (dec,)
 
     def forward(self, sample: torch.Tensor, sample_posterior: bool = False, return_dict: bool = True,
