@@ -83,6 +83,8 @@ struct TileCoord {
   int pi, b, m_tile;
   int col0;   // first output column of the work item
   int bn;     // its width: BN, or BN/split for a slice of a tail tile
+  int mma_n;  // MMA N of the item: bn, or what is left of a problem whose N ends inside the tile (N = 128 / 32 layers of
+              // the VAE: an MMA over 256 columns would spend 2-8x the tensor time on zero padding)
 };
 
 __host__ __device__ __forceinline__ TileCoord decode_tile(const Group& g, int item) {
@@ -103,6 +105,7 @@ __host__ __device__ __forceinline__ TileCoord decode_tile(const Group& g, int it
   c.pi = pi;
   c.col0 = (local % p.n_tiles) * BN + part * bn;
   c.bn = bn;
+  c.mma_n = min(bn, p.N - c.col0);   // N % 32 == 0 (checked at the entry point): a legal tcgen05 N for M = 128
   const int rest = local / p.n_tiles;
   c.m_tile = rest % p.m_tiles;
   c.b = rest / p.m_tiles;
@@ -277,7 +280,7 @@ gemm_kernel(const __grid_constant__ Maps maps, const __grid_constant__ Group grp
       const int k_blocks = grp.p[tc.pi].k_blocks;
       const int as = it & 1;
       const uint32_t aphase = (it >> 1) & 1;
-      const uint32_t idesc = ptx::make_idesc_bf16(BMT, tc.bn, 0, 0);   // N = 256, or 128 / 64 for a tail slice
+      const uint32_t idesc = ptx::make_idesc_bf16(BMT, tc.mma_n, 0, 0);   // N = 256, 128 / 64 for a tail slice, or a ragged end
       ptx::mbar_wait(&tempty_bar[as], aphase ^ 1);
       ptx::tc_fence_after();
       const uint32_t d_tmem = tmem_base + as * BN;

@@ -103,22 +103,32 @@ gn_stats_kernel(const T* __restrict__ x, int64_t ld, int64_t batch_stride, int p
   }
 }
 
-// stats[b][g] = sum over the chunks, in chunk order
-__global__ void gn_finalize_kernel(const double* __restrict__ part, int chunks, int groups, double* __restrict__ stats) {
-  const int b = blockIdx.x;
-  for (int g = threadIdx.x; g < groups; g += blockDim.x) {
-    double ds = 0.0, dq = 0.0;
-    for (int c = 0; c < chunks; ++c) {
-      const double* src = part + (((int64_t)b * GN_MAX_CHUNKS + c) * groups + g) * 2;
-      ds += src[0];
-      dq += src[1];
-    }
+// stats[b][g] = sum over the chunks in a fixed order (deterministic): one warp per (group, batch); lane l adds chunks l,
+// l + 32, ... in order, then the 32 lane sums meet in a shuffle tree.  (The first form - one thread per group walking up to
+// 256 chunks with dependent double adds - took 42 us per call, a fifth of a 512px decode: profiles/r02b_vae_launches.csv.)
+__global__ void __launch_bounds__(32) gn_finalize_kernel(const double* __restrict__ part, int chunks, int groups,
+                                                         double* __restrict__ stats) {
+  const int g = blockIdx.x, b = blockIdx.y, lane = threadIdx.x;
+  double ds = 0.0, dq = 0.0;
+  for (int c = lane; c < chunks; c += 32) {
+    const double* src = part + (((int64_t)b * GN_MAX_CHUNKS + c) * groups + g) * 2;
+    ds += __ldg(src);
+    dq += __ldg(src + 1);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    ds += __shfl_xor_sync(0xffffffffu, ds, o);
+    dq += __shfl_xor_sync(0xffffffffu, dq, o);
+  }
+  if (lane == 0) {
     stats[((int64_t)b * groups + g) * 2] = ds;
     stats[((int64_t)b * groups + g) * 2 + 1] = dq;
   }
 }
 
-// ---- GroupNorm apply (+ SiLU): y = (x - mean_g) rstd_g gamma_c + beta_c; one 8-channel vector per thread and step.
+// ---- GroupNorm apply (+ SiLU): y = (x - mean_g) rstd_g gamma_c + beta_c = x a_c + b_c; one 8-channel vector per thread
+// and step.  The grid stride is a multiple of the vectors per pixel (THREADS % vecs == 0), so a thread keeps the same eight
+// channels for its whole loop and forms a_c, b_c once (the statistics are finished in double, once per thread).
 template <typename T>
 __global__ void __launch_bounds__(THREADS)
 gn_apply_kernel(const T* __restrict__ x, int64_t ldx, int64_t x_batch_stride, __nv_bfloat16* __restrict__ y,
@@ -130,29 +140,32 @@ gn_apply_kernel(const T* __restrict__ x, int64_t ldx, int64_t x_batch_stride, __
   const int cpg = channels / groups;
   const double inv_n = 1.0 / ((double)valid_pixels * cpg);
   const int64_t total = (int64_t)pixels * vecs;
-  for (int64_t i = (int64_t)blockIdx.x * THREADS + threadIdx.x; i < total; i += (int64_t)gridDim.x * THREADS) {
-    const int v = (int)(i % vecs);
+  const int64_t first = (int64_t)blockIdx.x * THREADS + threadIdx.x;
+  const int v = (int)(first % vecs);
+  float ca[8], cb[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    const int c = v * 8 + k;
+    const int g = c / cpg;
+    const double m = stats[((int64_t)b * groups + g) * 2] * inv_n;
+    const double var = fmax(stats[((int64_t)b * groups + g) * 2 + 1] * inv_n - m * m, 0.0);
+    const float rstd = rsqrtf((float)var + eps);
+    ca[k] = rstd * __ldg(gamma + c);
+    cb[k] = __ldg(beta + c) - (float)m * ca[k];
+  }
+  const T* xb = x + (int64_t)b * x_batch_stride + v * 8;
+  __nv_bfloat16* yb = y + (int64_t)b * y_batch_stride + v * 8;
+  for (int64_t i = first; i < total; i += (int64_t)gridDim.x * THREADS) {
     const int64_t p = i / vecs;
     float f[8];
-    load8(x + (int64_t)b * x_batch_stride + p * ldx + v * 8, f);
-    uint32_t o[4];
+    load8(xb + p * ldx, f);
 #pragma unroll
-    for (int k = 0; k < 8; k += 2) {
-      float r[2];
-#pragma unroll
-      for (int e = 0; e < 2; ++e) {
-        const int c = v * 8 + k + e;
-        const int g = c / cpg;
-        const double m = stats[((int64_t)b * groups + g) * 2] * inv_n;
-        const double var = fmax(stats[((int64_t)b * groups + g) * 2 + 1] * inv_n - m * m, 0.0);
-        const float rstd = rsqrtf((float)var + eps);
-        float t = (f[k + e] - (float)m) * rstd * __ldg(gamma + c) + __ldg(beta + c);
-        if (silu) t = t / (1.0f + __expf(-t));
-        r[e] = t;
-      }
-      o[k >> 1] = ptx::pack_bf16(r[0], r[1]);
+    for (int k = 0; k < 8; ++k) {
+      float t = fmaf(f[k], ca[k], cb[k]);
+      if (silu) t = t / (1.0f + __expf(-t));
+      f[k] = t;
     }
-    *reinterpret_cast<uint4*>(y + (int64_t)b * y_batch_stride + p * ldy + v * 8) = make_uint4(o[0], o[1], o[2], o[3]);
+    *reinterpret_cast<uint4*>(yb + p * ldy) = pack8(f);
   }
 }
 
@@ -349,7 +362,7 @@ extern "C" int dit4sr_groupnorm_nhwc(const dit4sr_groupnorm_params* p, void* str
     const float* x = reinterpret_cast<const float*>(p->x);
     gn_stats_kernel<<<dim3(chunks, p->batches), THREADS, sm, stream>>>(x, p->ldx, p->x_batch_stride, p->pixels, width, pitch,
                                                                        p->channels, p->groups, per, part);
-    gn_finalize_kernel<<<p->batches, 64, 0, stream>>>(part, chunks, p->groups, stats);
+    gn_finalize_kernel<<<dim3(p->groups, p->batches), 32, 0, stream>>>(part, chunks, p->groups, stats);
     gn_apply_kernel<<<dim3(gx, p->batches), THREADS, 0, stream>>>(x, p->ldx, p->x_batch_stride, y, p->ldy, p->y_batch_stride,
                                                                  p->pixels, valid_pixels, p->channels, p->groups, stats,
                                                                  p->gamma, p->beta, p->eps, p->silu);
@@ -357,7 +370,7 @@ extern "C" int dit4sr_groupnorm_nhwc(const dit4sr_groupnorm_params* p, void* str
     const __nv_bfloat16* x = reinterpret_cast<const __nv_bfloat16*>(p->x);
     gn_stats_kernel<<<dim3(chunks, p->batches), THREADS, sm, stream>>>(x, p->ldx, p->x_batch_stride, p->pixels, width, pitch,
                                                                        p->channels, p->groups, per, part);
-    gn_finalize_kernel<<<p->batches, 64, 0, stream>>>(part, chunks, p->groups, stats);
+    gn_finalize_kernel<<<dim3(p->groups, p->batches), 32, 0, stream>>>(part, chunks, p->groups, stats);
     gn_apply_kernel<<<dim3(gx, p->batches), THREADS, 0, stream>>>(x, p->ldx, p->x_batch_stride, y, p->ldy, p->y_batch_stride,
                                                                  p->pixels, valid_pixels, p->channels, p->groups, stats,
                                                                  p->gamma, p->beta, p->eps, p->silu);
