@@ -549,7 +549,7 @@ class Engine:
     @torch.no_grad()
     def step(self, hidden_states, controlnet_image, encoder_hidden_states, pooled_projections, timestep,
              out=None, euler: Optional[Tuple[torch.Tensor, float]] = None, sharded_io: bool = False,
-             guidance: Optional[float] = None, features: Optional[tuple] = None):
+             guidance: Optional[float] = None, features: Optional[tuple] = None, loop=None):
         """One denoiser call, replayed from a captured CUDA graph when possible (the ~300 kernel launches of a step are
         recorded once per input shape; replay removes the per-launch host cost, which matters for small batches).
         Same results as `forward` -- the same kernels run. Falls back to direct launches while profiling, if capture is
@@ -560,7 +560,9 @@ class Engine:
         guidance: classifier-free guidance - the inputs are the doubled batch [uncond | text] (2B) and the result (velocity
         or Euler update of euler[0], B images) uses v_uncond + guidance * (v_text - v_uncond), fused into the last kernel.
         features: (layers, row0, n_concat, token dtype) - per-block feature outputs (see `forward`); with them the call
-        returns (result, [ {extract_feat, extract_feat_nchw_f32}, ... ]) and still replays the graph."""
+        returns (result, [ {extract_feat, extract_feat_nchw_f32}, ... ]) and still replays the graph.
+        loop: (cache, i) from `prepare_loop` - step i of a sampling loop takes its adaLN vectors and text embedding from the
+        loop's table (the head of the step is not recomputed)."""
         if features is not None and self.sp is not None:
             raise NotImplementedError("feature outputs are not available under sequence parallelism")
         if self.sp is not None and not sharded_io:
@@ -568,7 +570,8 @@ class Engine:
             g0, g1 = self.sp.row_slice(hidden_states.shape[2] // 2)
             loc = lambda t: t[:, :, 2 * g0:2 * g1].contiguous()
             res = self.step(loc(hidden_states), loc(controlnet_image), encoder_hidden_states, pooled_projections, timestep,
-                            euler=None if euler is None else (loc(euler[0]), euler[1]), sharded_io=True, guidance=guidance)
+                            euler=None if euler is None else (loc(euler[0]), euler[1]), sharded_io=True, guidance=guidance,
+                            loop=loop)
             gathered = self.sp.gather_rows(res, dim=2)
             if out is not None:
                 out.copy_(gathered)
@@ -577,12 +580,17 @@ class Engine:
         if (not self.use_cuda_graph or self._prof is not None or self.precise
                 or (self.sp is not None and not self.sp_graph)):
             res = self.forward(hidden_states, controlnet_image, encoder_hidden_states, pooled_projections, timestep,
-                               out=out, euler=euler, sharded_io=sharded_io, guidance=guidance, features=features)
+                               out=out, euler=euler, sharded_io=sharded_io, guidance=guidance, features=features, loop=loop)
             return (res, self._feature_results(features)) if features is not None else res
         B = hidden_states.shape[0]
         key = (tuple(hidden_states.shape), hidden_states.dtype, tuple(encoder_hidden_states.shape),
                encoder_hidden_states.dtype, pooled_projections.dtype, str(hidden_states.device), guidance is not None,
-               features)
+               features, loop is not None)
+        h, w = hidden_states.shape[-2:]
+        ws = self._workspace(B, (h // 2) * (w // 2), encoder_hidden_states.shape[1], hidden_states.device,
+                             grid_w=w // 2 if self.sp is not None else 0)
+        if loop is not None:
+            self._load_loop_slice(ws, loop)      # this step's adaLN vectors / text embedding -> the buffers the graph reads
         entry = self._graphs.get(key)
         if entry is None:
             st = dict(hs=hidden_states.clone().contiguous(), ci=controlnet_image.clone().contiguous(),
@@ -590,7 +598,8 @@ class Engine:
                       t=torch.zeros(B, device=hidden_states.device, dtype=torch.float32))
             try:
                 fw = lambda: self.forward(st["hs"], st["ci"], st["enc"], st["pooled"], st["t"], sharded_io=sharded_io,
-                                          guidance=guidance, features=features)
+                                          guidance=guidance, features=features,
+                                          loop="preloaded" if loop is not None else None)
                 fw()                                                                    # warm-up outside capture
                 torch.cuda.synchronize()
                 n0 = ops.launch_count()
@@ -606,21 +615,19 @@ class Engine:
                 self.use_cuda_graph = False
                 torch.cuda.synchronize()
                 res = self.forward(hidden_states, controlnet_image, encoder_hidden_states, pooled_projections,
-                                   timestep, out=out, euler=euler, guidance=guidance, features=features)
+                                   timestep, out=out, euler=euler, guidance=guidance, features=features, loop=loop)
                 return (res, self._feature_results(features)) if features is not None else res
             self._graphs[key] = entry
         graph, st, vel, n_launch = entry
         st["hs"].copy_(hidden_states)
         st["ci"].copy_(controlnet_image)
-        st["enc"].copy_(encoder_hidden_states)
-        st["pooled"].copy_(pooled_projections)
-        st["t"].copy_(timestep.to(device=st["t"].device, dtype=torch.float32).expand(B))
+        if loop is None:             # (with a loop cache the graph reads neither: their products are in the workspace)
+            st["enc"].copy_(encoder_hidden_states)
+            st["pooled"].copy_(pooled_projections)
+            st["t"].copy_(timestep.to(device=st["t"].device, dtype=torch.float32).expand(B))
         graph.replay()
         ops._count(n_launch)
         if euler is not None:        # x_next = x + dsigma * v straight from the velocity tokens the graph left behind
-            h, w = hidden_states.shape[-2:]
-            ws = self._workspace(B, (h // 2) * (w // 2), encoder_hidden_states.shape[1], hidden_states.device,
-                                 grid_w=w // 2 if self.sp is not None else 0)
             if out is None:
                 out = torch.empty_like(euler[0])
             ops.unpatchify(ws["tok"], out, latents=euler[0], dsigma=euler[1], guidance=guidance)
@@ -632,6 +639,53 @@ class Engine:
             res = vel.clone()
         return (res, self._feature_results(features)) if features is not None else res
 
+    LOOP_TABLE_MAX_BYTES = 4 << 30
+
+    @torch.no_grad()
+    def prepare_loop(self, encoder_hidden_states, pooled_projections, timesteps):
+        """What a sampling loop can form once instead of once per step (pipelines/pipeline_dit4sr.py:1078-1132 calls the model
+        with the same prompt embeddings at every step and the schedule is known up front): the adaLN vectors of EVERY step
+        - temb = MLP(sincos(t_i)) + MLP(pooled) and the [B, 325 D] modulation GEMM, one launch with steps x B rows, so its
+        1.5 GB of weights are streamed once per loop instead of once per step - and the embedded text tokens
+        (context_embedder).  Same kernels and operands as the per-step head, so the values are identical.  Returns the
+        cache `step(..., loop=(cache, i))` takes, or None when the table would not be worth its memory (or in the
+        fp32-accurate mode, which keeps the as-written order)."""
+        B = encoder_hidden_states.shape[0]
+        n = len(timesteps)
+        if self.precise or n * B * self.mod_total * 4 > self.LOOP_TABLE_MAX_BYTES:
+            return None
+        dev, D, R, gm = encoder_hidden_states.device, self.D, self._run, self._g1
+        bf, f32 = torch.bfloat16, torch.float32
+        M = n * B
+
+        def e(*shape, dtype=bf):
+            return torch.empty(*shape, device=dev, dtype=dtype)
+
+        t_all = torch.tensor([float(t) for t in timesteps], device=dev, dtype=f32).repeat_interleave(B)   # rows [step, batch]
+        tf, th, ph, temb, st = e(M, 256), e(M, D), e(M, D), e(M, D, dtype=f32), e(M, D)
+        R("head", ops.timestep_features, t_all, tf)
+        gm("head", tf, self.t1.w, self.t1.b, th, ops.EPI_BIAS_SILU)
+        gm("head", th, self.t2.w, self.t2.b, temb, ops.EPI_BIAS)
+        pooled = pooled_projections.to(bf).repeat(n, 1).contiguous()
+        gm("head", pooled, self.p1.w, self.p1.b, ph, ops.EPI_BIAS_SILU)
+        gm("head", ph, self.p2.w, self.p2.b, temb, ops.EPI_GATE_RESID)
+        R("head", ops.silu_cast, temb, st)
+        mod_all = e(M, self.mod_total, dtype=f32)
+        gm("mod_gemm", st, self.mod.w, self.mod.b, mod_all, ops.EPI_BIAS)
+        enc = encoder_hidden_states.to(bf).contiguous()
+        ctx0 = e(B, enc.shape[1], D, dtype=f32)
+        gm("head", enc, self.ctx_embed.w, self.ctx_embed.b, ctx0, ops.EPI_BIAS)
+        return dict(mod=mod_all.view(n, B, self.mod_total), ctx=ctx0, steps=n, batch=B)
+
+    def _load_loop_slice(self, ws, loop):
+        cache, i = loop
+        if cache["batch"] != ws["mod"].shape[0] or not 0 <= i < cache["steps"]:
+            raise ValueError("loop cache does not belong to this batch / step")
+        if "ctx0" not in ws:
+            ws["ctx0"] = torch.empty_like(ws["ctx"])
+        ws["mod"].copy_(cache["mod"][i])
+        ws["ctx0"].copy_(cache["ctx"])
+
     def _feature_results(self, features):
         """Fresh copies of the per-block feature buffers the last forward / replay filled (they are static workspace)."""
         return [dict(extract_feat=t.clone(), extract_feat_nchw_f32=n.clone()) for t, n in self._feat_bufs[features]]
@@ -640,8 +694,10 @@ class Engine:
     @torch.no_grad()
     def forward(self, hidden_states, controlnet_image, encoder_hidden_states, pooled_projections, timestep,
                 out=None, euler: Optional[Tuple[torch.Tensor, float]] = None, feat_hook=None, sharded_io: bool = False,
-                guidance: Optional[float] = None, features: Optional[tuple] = None):
-        """features = (layers, row0, n_concat, token dtype): after each block in `layers` the rows [row0, row0 + n_concat *
+                guidance: Optional[float] = None, features: Optional[tuple] = None, loop=None):
+        """loop = (cache of `prepare_loop`, step index): the adaLN vectors and the embedded text tokens come from the
+        sampling loop's table instead of being recomputed (or "preloaded": `step` has put them into the workspace).
+        features = (layers, row0, n_concat, token dtype): after each block in `layers` the rows [row0, row0 + n_concat *
         grid^2) of the residual stream are written (one kernel, also inside a captured graph) as the token-major slice the
         reference returns (attention.py:363-374) and as fp32 NCHW 'b (N H W) (pH pW d) -> b (N d) (H pH) (W pW)', what
         pipelines/pipeline_dit4sr.py:1214-1245 hands to the text-spotting module."""
@@ -682,16 +738,25 @@ class Engine:
         x, ctx, n1, n2, nc, mod = ws["x"], ws["ctx"], ws["n1"], ws["n2"], ws["nc"], ws["mod"]
 
         # ---- head: temb = MLP(sincos(t)) + MLP(pooled)  (CombinedTimestepTextProjEmbeddings, transformer_sd3.py:327)
-        ws["t"].copy_(timestep.to(device=dev, dtype=torch.float32).expand(B))
-        R("head", ops.timestep_features, ws["t"], ws["tf"])
         gm = self._g1
-        gm("head", ws["tf"], self.t1.w, self.t1.b, ws["th"], ops.EPI_BIAS_SILU)
-        gm("head", ws["th"], self.t2.w, self.t2.b, ws["temb"], ops.EPI_BIAS)
-        ws["pooled"].copy_(pooled_projections)
-        gm("head", ws["pooled"], self.p1.w, self.p1.b, ws["ph"], ops.EPI_BIAS_SILU)
-        gm("head", ws["ph"], self.p2.w, self.p2.b, ws["temb"], ops.EPI_GATE_RESID)
-        R("head", ops.silu_cast, ws["temb"], ws["st"])
-        gm("mod_gemm", ws["st"], self.mod.w, self.mod.b, mod, ops.EPI_BIAS)   # all adaLN vectors of the step
+        if loop is None:
+            ws["t"].copy_(timestep.to(device=dev, dtype=torch.float32).expand(B))
+            R("head", ops.timestep_features, ws["t"], ws["tf"])
+            gm("head", ws["tf"], self.t1.w, self.t1.b, ws["th"], ops.EPI_BIAS_SILU)
+            gm("head", ws["th"], self.t2.w, self.t2.b, ws["temb"], ops.EPI_BIAS)
+            ws["pooled"].copy_(pooled_projections)
+            gm("head", ws["pooled"], self.p1.w, self.p1.b, ws["ph"], ops.EPI_BIAS_SILU)
+            gm("head", ws["ph"], self.p2.w, self.p2.b, ws["temb"], ops.EPI_GATE_RESID)
+            R("head", ops.silu_cast, ws["temb"], ws["st"])
+            gm("mod_gemm", ws["st"], self.mod.w, self.mod.b, mod, ops.EPI_BIAS)   # all adaLN vectors of the step
+        else:
+            # sampling loop: timesteps, pooled and text embeddings are known before the loop starts, so the adaLN vectors of
+            # every step and the embedded text tokens were formed once (prepare_loop); a step copies its slice
+            if "ctx0" not in ws:
+                ws["ctx0"] = torch.empty_like(ctx)
+            if loop != "preloaded":
+                self._load_loop_slice(ws, loop)
+            ctx.copy_(ws["ctx0"])
         # ---- patch embed (+pos) for both streams, context embedder  (:326-332)
         streams = [(hidden_states, x[:, :N]), (controlnet_image, x[:, N:2 * N])]
         if self.streams == 3:   # the OCR stream starts as a second pos_embed(controlnet_image) (ocr model :334-337)
@@ -700,8 +765,9 @@ class Engine:
             src = src.contiguous()
             R("head", ops.patchify, src.float() if self.precise else src, ws["patches"])
             gm("head", ws["patches"], self.patch_w, self.patch_b, dst_rows, ops.EPI_GATE_RESID, resid=pos)
-        ws["enc"].copy_(encoder_hidden_states)
-        gm("head", ws["enc"], self.ctx_embed.w, self.ctx_embed.b, ctx, ops.EPI_BIAS)
+        if loop is None:
+            ws["enc"].copy_(encoder_hidden_states)
+            gm("head", ws["enc"], self.ctx_embed.w, self.ctx_embed.b, ctx, ops.EPI_BIAS)
 
         # ---- blocks (:336-370)
         for i, bp in enumerate(self.blocks):

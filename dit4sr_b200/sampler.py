@@ -26,7 +26,8 @@ def lre_start_point(latents, controlnet_image, sigma0: float):
 @torch.no_grad()
 def denoise(model, latents, controlnet_image, encoder_hidden_states, pooled_projections, num_inference_steps=40,
             sigmas=None, guidance_scale: float = 1.0, negative_prompt_embeds=None, negative_pooled_prompt_embeds=None,
-            start_point: str = "noise", latent_tiled_size: int = 0, latent_tiled_overlap: int = 0, tile_batch: int = 0):
+            start_point: str = "noise", latent_tiled_size: int = 0, latent_tiled_overlap: int = 0, tile_batch: int = 0,
+            hoist_loop_invariants: bool = True):
     """Runs the full sampling loop on the CUDA engine; returns the final latents (same dtype as `latents`).
 
     latents are carried in fp32 between steps (scheduler.step upcasts to fp32, pipeline_dit4sr.py:1567).
@@ -69,6 +70,10 @@ def denoise(model, latents, controlnet_image, encoder_hidden_states, pooled_proj
     nxt = torch.empty_like(x)
     x2 = torch.empty((2 * B,) + tuple(x.shape[1:]), device=x.device, dtype=x.dtype) if cfg_on else None
     t = torch.empty(2 * B if cfg_on else B, device=latents.device, dtype=torch.float32)
+    # loop-invariant work hoisted out of the loop: the adaLN vectors of all steps (one GEMM over steps x batch rows) and the
+    # embedded text tokens (Engine.prepare_loop); None = recompute per step
+    cache = eng.prepare_loop(encoder_hidden_states, pooled_projections, [float(s) * 1000.0 for s in sig[:-1]]) \
+        if hoist_loop_invariants else None
     for i in range(len(sig) - 1):
         t.fill_(float(sig[i]) * 1000.0)
         if cfg_on:
@@ -76,7 +81,7 @@ def denoise(model, latents, controlnet_image, encoder_hidden_states, pooled_proj
             x2[B:].copy_(x)
         eng.step(x2 if cfg_on else x, controlnet_image, encoder_hidden_states, pooled_projections, t, out=nxt,
                  euler=(x, float(sig[i + 1]) - float(sig[i])), sharded_io=sp is not None,
-                 guidance=float(guidance_scale) if cfg_on else None)
+                 guidance=float(guidance_scale) if cfg_on else None, loop=None if cache is None else (cache, i))
         x, nxt = nxt, x
     if sp is not None:
         x = sp.gather_rows(x, dim=2)

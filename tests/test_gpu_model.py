@@ -415,3 +415,25 @@ def test_fp16_module_runs_in_bf16_within_the_stated_tolerance():
     print(f"fp16 module: cuda(bf16 arithmetic) vs fp32 {e_ours:.3e}; reference fp16 run vs fp32 {e_ref16:.3e}")
     assert e_ours <= VEL_TOL
     assert rel(y, ref16) <= VEL_TOL + e_ref16
+
+
+def test_sampling_loop_hoisted_invariants_match_per_step_head():
+    """denoise() forms the adaLN vectors of all steps and the embedded text tokens once (Engine.prepare_loop) - the same
+    kernels on the same operands as the per-step head, so the loop must end where the per-step loop ends (with and without
+    guidance; graph replay and direct launches)."""
+    from dit4sr_b200.sampler import denoise
+    cfg = O.sd35_medium_config(num_layers=3, dual_attention_layers=(0,), pos_embed_max_size=96)
+    sd = O.init_state_dict(cfg, seed=0)
+    hs, lr, enc, pooled, _ = O.make_inputs(cfg, 2, 32, 32, 77, seed=1)
+    bf = torch.bfloat16
+    m = build(cfg, sd)
+    a = [t.cuda().to(bf) for t in (hs, lr, enc, pooled)]
+    neg = dict(negative_prompt_embeds=torch.zeros_like(a[2]), negative_pooled_prompt_embeds=torch.zeros_like(a[3]))
+    for kw in (dict(), dict(guidance_scale=4.0, **neg)):
+        for graph in (True, False):
+            m.engine().use_cuda_graph = graph
+            y1 = denoise(m, *a, num_inference_steps=6, hoist_loop_invariants=True, **kw).float()
+            y0 = denoise(m, *a, num_inference_steps=6, hoist_loop_invariants=False, **kw).float()
+            err = rel(y1, y0)
+            print(f"hoisted vs per-step head (guidance {kw.get('guidance_scale', 1.0)}, graph {graph}): rel-L2 {err:.2e}")
+            assert err < 1e-5
