@@ -143,10 +143,10 @@ def attention_roofline(launch_ms, flops_per_step, launches_per_step, peaks, root
     ach = flops / (avg_ms / 1e3) / 1e12
     traffic = src = None
     try:
-        prof = json.load(open(os.path.join(root, "profiles", "r02b_ncu_full.json")))
+        prof = json.load(open(os.path.join(root, "profiles", "r02f_ncu_full.json")))
         k = next(k for k in prof if "attn_fwd5_kernel" in k["Kernel Name"])
         traffic = round((float(k["dram__bytes_read.sum [Mbyte]"]) + float(k["dram__bytes_write.sum [Mbyte]"])) * 1e6)
-        src = ("from committed capture profiles/r02b_ncu_full.json of the same kernel (attn_fwd5_kernel; not measured in this run): "
+        src = ("from committed capture profiles/r02f_ncu_full.json of the same kernel (attn_fwd5_kernel; not measured in this run): "
                "dram__bytes_read.sum + dram__bytes_write.sum of one joint-attention "
                "launch (S=2381, B=8; algorithmic 263 MB q|k|v read + 59 MB o written + 50 MB LR residual read)")
     except (OSError, KeyError, ValueError, StopIteration):
