@@ -260,6 +260,7 @@ class AutoencoderKL(nn.Module):
     GRAPH_MAX_PIXELS = 1024 * 1024     # image pixels per batch entry times batch: beyond this the kernels are long enough
     GRAPH_MAX_CACHED = 4               # captured graphs keep their activations (about 2.9 GiB for a 1024px decode)
 
+    @torch.no_grad()
     def _graphed(self, kind, fn, x, pixels):
         """fn(x) replayed from a CUDA graph captured per (kind, shape, dtype, device): same kernels, same results.  Large
         images (and anything that fails to capture) are launched directly."""
