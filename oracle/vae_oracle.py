@@ -12,8 +12,13 @@ conv_shortcut added to the input), :136-169 (attention: to_q / to_k / to_v, soft
 down-sampling convolution, nearest 2x up-sampling, DiagonalGaussianDistribution with logvar clamped to [-30, 20], the SD3
 VAE configuration) is restated from the published diffusers 0.31.0 sources from memory.
 
-PARITY UNPINNED: the reference holds no golden vector for this path and diffusers cannot be imported here; both sides of
-the parity tests (this oracle and dit4sr_b200.vae) share this restatement of the layer semantics.
+PINNING: the reference holds no golden vector for this path and diffusers cannot be imported here, so the oracle is pinned
+against INDEPENDENT implementations of the same (LDM-lineage) architecture that ship in this image's `transformers` package:
+`encoder_forward` equals Chameleon's `ChameleonVQVAEEncoder` and `decoder_forward` equals Janus' `JanusVQVAEDecoder` (its extra
+up-level attention blocks neutralised) to 2e-4 on random weights mapped through the LDM -> diffusers key conversion, parameter
+names and shapes included (tests/test_oracle_crosscheck.py::test_vae_oracle_*).  What stays unpinned w.r.t. a real diffusers
+install: that AutoencoderKL 0.31.0 is this architecture under those key names (the reference's own vaehook walk above says so),
+DiagonalGaussianDistribution's clamp, and the SD3 VAE configuration values.
 
 The tiled variant (VAEHook.vae_tile_forward) is an out-of-memory work-around that reproduces the untiled network (GroupNorm
 statistics are shared across tiles; its `fast` modes estimate them from a down-sampled copy); a 180 GB B200 decodes

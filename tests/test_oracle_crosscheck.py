@@ -127,3 +127,92 @@ def test_pos_embed_crop_is_the_centred_window_of_the_independent_table():
         got = pe.cropped_pos_embed(h, w).reshape(h // 2, w // 2, 32)
         top, left = (12 - h // 2) // 2, (12 - w // 2) // 2
         assert torch.equal(got, table[top:top + h // 2, left:left + w // 2])
+
+
+# ---- VAE oracle (oracle/vae_oracle.py restates diffusers' AutoencoderKL from memory) against the LDM-lineage VQ-VAE encoder /
+# decoder modules that ship in `transformers` (Chameleon's encoder, Janus' decoder): the architecture diffusers' AutoencoderKL
+# checkpoints were converted from (convert_ldm_vae_checkpoint: down.{i}.block.{j} -> down_blocks.{i}.resnets.{j}, nin_shortcut ->
+# conv_shortcut, mid.block_1 / attn_1 / block_2 -> mid_block.resnets.0 / attentions.0 / resnets.1, q / k / v / proj_out 1x1
+# convolutions -> to_q / to_k / to_v / to_out.0 linears, norm_out -> conv_norm_out).
+def _ldm_to_diffusers(sd_ldm, side, levels):
+    """State dict of an LDM-style encoder / decoder (`side` = "encoder" | "decoder") under diffusers' AutoencoderKL key names."""
+    out = {}
+    blocks, res, samp, samp_new = (("down", "down_blocks", "downsample", "downsamplers.0") if side == "encoder"
+                                   else ("up", "up_blocks", "upsample", "upsamplers.0"))
+    for k, v in sd_ldm.items():
+        p = k.split(".")
+        if p[0] == blocks and p[2] == "block":
+            name = f"{res}.{p[1]}.resnets.{p[3]}." + ".".join(p[4:]).replace("nin_shortcut", "conv_shortcut")
+        elif p[0] == blocks and p[2] == samp:
+            name = f"{res}.{p[1]}.{samp_new}." + ".".join(p[3:])
+        elif p[0] == blocks and p[2] == "attn":
+            continue                                        # (neutralised up-level attention of the Janus decoder, see below)
+        elif p[0] == "mid" and p[1] in ("block_1", "block_2"):
+            name = f"mid_block.resnets.{0 if p[1] == 'block_1' else 1}." + ".".join(p[2:])
+        elif p[0] == "mid" and p[1] == "attn_1":
+            sub = {"norm": "group_norm", "q": "to_q", "k": "to_k", "v": "to_v", "proj_out": "to_out.0"}[p[2]]
+            name = f"mid_block.attentions.0.{sub}.{p[3]}"
+            if p[2] != "norm" and p[3] == "weight":
+                v = v[:, :, 0, 0]                           # 1x1 convolution -> linear
+        elif p[0] == "norm_out":
+            name = "conv_norm_out." + p[1]
+        else:
+            name = k                                        # conv_in, conv_out
+        out[f"{side}.{name}"] = v.detach().clone()
+    return out
+
+
+def _ldm_config():
+    from types import SimpleNamespace
+    return SimpleNamespace(channel_multiplier=(1, 2, 4, 4), num_res_blocks=2, base_channels=32, resolution=64, in_channels=3,
+                           out_channels=3, double_latent=True, latent_channels=16, attn_resolutions=None, attn_type="vanilla",
+                           dropout=0.0)
+
+
+def _randomise(module, seed):
+    g = torch.Generator().manual_seed(seed)
+    with torch.no_grad():
+        for p in module.parameters():
+            p.copy_(torch.randn(p.shape, generator=g) * (0.3 if p.dim() > 1 else 0.5) + (1.0 if p.dim() == 1 else 0.0))
+
+
+def test_vae_oracle_encoder_matches_the_ldm_encoder_in_transformers():
+    cham = pytest.importorskip("transformers.models.chameleon.modeling_chameleon")
+    from oracle import vae_oracle as V
+    torch.manual_seed(0)
+    enc = cham.ChameleonVQVAEEncoder(_ldm_config()).eval()
+    _randomise(enc, 1)
+    cfg = V.sd3_vae_config(block_out_channels=(32, 64, 128, 128))
+    sd = _ldm_to_diffusers(enc.state_dict(), "encoder", 4)
+    want = {k: s for k, s in V.state_dict_shapes(cfg).items() if k.startswith("encoder.")}
+    assert {k: tuple(v.shape) for k, v in sd.items()} == want          # same parameters, same shapes, nothing left over
+    x = torch.randn(2, 3, 48, 80)
+    with torch.no_grad():
+        ref = enc(x.clone())
+        got = V.encoder_forward(sd, cfg, x)
+    assert got.shape == ref.shape == (2, 32, 6, 10)
+    assert torch.allclose(got, ref, atol=2e-4, rtol=1e-4), (got - ref).abs().max()
+
+
+def test_vae_oracle_decoder_matches_the_ldm_decoder_in_transformers():
+    janus = pytest.importorskip("transformers.models.janus.modeling_janus")
+    from oracle import vae_oracle as V
+    torch.manual_seed(0)
+    dec = janus.JanusVQVAEDecoder(_ldm_config()).eval()
+    _randomise(dec, 2)
+    # Janus adds attention blocks after the residual blocks of its lowest-resolution up level, which the SD VAE decoder does not
+    # have: with a zero output projection each of them is `residual + 0`
+    with torch.no_grad():
+        for a in dec.up[0].attn:
+            a.proj_out.weight.zero_()
+            a.proj_out.bias.zero_()
+    cfg = V.sd3_vae_config(block_out_channels=(32, 64, 128, 128))
+    sd = _ldm_to_diffusers(dec.state_dict(), "decoder", 4)
+    want = {k: s for k, s in V.state_dict_shapes(cfg).items() if k.startswith("decoder.")}
+    assert {k: tuple(v.shape) for k, v in sd.items()} == want
+    z = torch.randn(2, 16, 6, 10)
+    with torch.no_grad():
+        ref = dec(z.clone())
+        got = V.decoder_forward(sd, cfg, z)
+    assert got.shape == ref.shape == (2, 3, 48, 80)
+    assert torch.allclose(got, ref, atol=2e-4, rtol=1e-4), (got - ref).abs().max()
