@@ -162,6 +162,24 @@ def test_bench_attention_roofline_entry():
     assert abs((gemm_f + attn_f) / 1e12 - 4.724) < 0.01          # folded-chain total at 512px
 
 
+def test_bench_hbm_roofline_entries():
+    """bench.py's `roofline_hbm`: algorithmic bytes of the LayerNorm+modulate launches and of the stencil of one C2 step
+    (3 N F 2 bytes per image and block for the stencil; LayerNorm reads the fp32 stream, writes bf16) / time."""
+    import sys
+    sys.path.insert(0, ROOT)
+    import bench
+    B, N, T, D, F = 8, 1024, 333, 1536, 6144
+    bd = {"ln_mod": {"launches": 48, "total_ms": 2.0}, "dwconv": {"launches": 24, "total_ms": 1.5}}
+    r = bench.hbm_rooflines(bd, B, N, T, 24, 13, dict(hbm=6541.1))
+    assert r["dwconv3x3"]["algorithmic_bytes_per_step"] == 24 * 3 * N * B * F * 2
+    img, txt = 2 * N * B * D, T * B * D
+    ln = 13 * img * 8 + 11 * img * 6 + 24 * img * 6 + (24 + 23) * txt * 6      # dual norm1, single norm1, norm2, text rows
+    assert r["ln_modulate"]["algorithmic_bytes_per_step"] == ln
+    assert abs(r["ln_modulate"]["achieved"] - ln / 2.0e-3 / 1e9) < 0.1 and r["ln_modulate"]["bound"] == "hbm"
+    assert abs(r["dwconv3x3"]["frac"] - r["dwconv3x3"]["achieved"] / 6541.1) < 1e-3
+    assert bench.hbm_rooflines(None, B, N, T, 24, 13, dict(hbm=1.0)) is None
+
+
 def test_bench_product_arm_config_matches_survey_and_avoids_the_oracle():
     """bench.py builds the product-arm model from its own dict (nothing under oracle/ outside the CPU legs); that dict,
     completed with the drop-in constructor's defaults, is the oracle's SD3.5-medium config."""
