@@ -182,7 +182,7 @@ ln_modulate_tma_kernel(const dit4sr_ln_modulate_params p) {
 //    vectors per row as before (coalesced).
 template <int NV, bool DUAL>  // NV float4 per lane => dim = NV * 128
 __global__ void __launch_bounds__(LN_WARPS * 32, 1)
-ln_modulate_tma2_kernel(const dit4sr_ln_modulate_params p) {
+ln_modulate_tma2_kernel(const dit4sr_ln_modulate_params p, const int reverse) {
   extern __shared__ uint8_t ln_smem_raw[];
   constexpr int ROW_BYTES = NV * 128 * 4;
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(ln_smem_raw) + 127) & ~uintptr_t(127));
@@ -195,7 +195,10 @@ ln_modulate_tma2_kernel(const dit4sr_ln_modulate_params p) {
   const int64_t total = total_a + (int64_t)p.batches * p.rows_b;
   const int64_t nwarps = (int64_t)gridDim.x * LN_WARPS;
   const int64_t first = (int64_t)blockIdx.x * LN_WARPS + warp;
+  // reverse: rows are visited from the last one down - the kernel that produced x wrote them in ascending order, so the
+  // rows written last are the ones most likely still in L2
   auto row_ptr = [&](int64_t rid) {
+    if (reverse) rid = total - 1 - rid;
     if (rid < total_a) {
       const int b = (int)(rid / p.rows);
       const int r = (int)(rid % p.rows);
@@ -228,8 +231,9 @@ ln_modulate_tma2_kernel(const dit4sr_ln_modulate_params p) {
   int k = 0;
   for (int64_t rid = first; rid < total; rid += nwarps, ++k) {
     const int s = k % LN_STAGES;
-    const bool comp = rid >= total_a;
-    const int64_t lrid = comp ? rid - total_a : rid;
+    const int64_t row = reverse ? total - 1 - rid : rid;
+    const bool comp = row >= total_a;
+    const int64_t lrid = comp ? row - total_a : row;
     const int prow = comp ? p.rows_b : p.rows;
     const int b = (int)(lrid / prow);
     const int r = (int)(lrid % prow);
@@ -430,10 +434,12 @@ static int launch(const dit4sr_ln_modulate_params& p, cudaStream_t stream) {
       unsigned grid = (unsigned)((total + LN_WARPS - 1) / LN_WARPS);
       const unsigned sms = (unsigned)host::sm_count();
       if (grid > sms) grid = sms;
+      static int reverse = -1;   // DIT4SR_LN_REVERSE=0: visit the rows in ascending order
+      if (reverse < 0) { const char* e = getenv("DIT4SR_LN_REVERSE"); reverse = (e != nullptr && e[0] == '0') ? 0 : 1; }
       if (p.out2 != nullptr)
-        DIT4SR_CUDA(host::launch_pdl(ln_modulate_tma2_kernel<NV, true>, dim3(grid), dim3(LN_WARPS * 32), (size_t)SMEM2, stream, p));
+        DIT4SR_CUDA(host::launch_pdl(ln_modulate_tma2_kernel<NV, true>, dim3(grid), dim3(LN_WARPS * 32), (size_t)SMEM2, stream, p, reverse));
       else
-        DIT4SR_CUDA(host::launch_pdl(ln_modulate_tma2_kernel<NV, false>, dim3(grid), dim3(LN_WARPS * 32), (size_t)SMEM2, stream, p));
+        DIT4SR_CUDA(host::launch_pdl(ln_modulate_tma2_kernel<NV, false>, dim3(grid), dim3(LN_WARPS * 32), (size_t)SMEM2, stream, p, reverse));
       return 0;
     }
   }
