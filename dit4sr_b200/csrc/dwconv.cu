@@ -25,6 +25,7 @@ struct Args {
   const float* weight9;
   const float* bias;
   int grid_h, grid_w, lr_row_offset, channels, x_tiles, y_tiles, batches;
+  int reverse;   // pipelined form: walk the tiles from the last one down (the producing GEMM wrote the rows ascending)
 };
 
 __device__ __forceinline__ void unpack8(const uint4& u, float* f) {
@@ -189,6 +190,7 @@ dwconv3x3_pipe_kernel(const __grid_constant__ CUtensorMap tmLR, const __grid_con
   __syncthreads();
 
   auto coords = [&](int t, int& x0, int& y0, int& b) {
+    if (a.reverse) t = total - 1 - t;
     b = t / tiles_per_image;
     const int r = t - b * tiles_per_image;
     const int yt = r / a.x_tiles;
@@ -335,6 +337,9 @@ extern "C" int dit4sr_dwconv3x3_add(const dit4sr_dwconv3x3_params* p, void* stre
   a.x_tiles = (gw + TX - 1) / TX;
   a.y_tiles = (p->grid + TY - 1) / TY;
   a.batches = p->batches;
+  static int reverse = -1;   // DIT4SR_DWCONV_REVERSE=0: ascending tile order
+  if (reverse < 0) { const char* e = getenv("DIT4SR_DWCONV_REVERSE"); reverse = (e != nullptr && e[0] == '0') ? 0 : 1; }
+  a.reverse = reverse;
   static int variant = -1;   // developer switch DIT4SR_DWCONV_VARIANT: 0 = first form (one tile per CTA), 1 = pipelined (default)
   if (variant < 0) { const char* e = getenv("DIT4SR_DWCONV_VARIANT"); variant = e ? atoi(e) : 1; }
   if (variant == 1) {
