@@ -244,3 +244,49 @@ def test_attention_work_decomposition_without_a_gpu():
                 slots = 296 if v >= 4 else 148
                 if split > 1:
                     assert whole % slots == 0 and tail < slots
+
+
+def test_sampler_forms_the_loop_table_once_and_hands_every_step_its_slice():
+    """Host logic of sampler.denoise around Engine.prepare_loop (no GPU: a recording stand-in for the engine): one table per
+    loop built from the doubled prompt batch and the schedule's timesteps, step i called with loop=(cache, i); with
+    hoist_loop_invariants=False (or when prepare_loop declines) every step recomputes its head (loop=None)."""
+    from dit4sr_b200 import sampler
+
+    class FakeEngine:
+        sp = None
+
+        def __init__(self, decline=False):
+            self.decline, self.tables, self.steps = decline, [], []
+
+        def prepare_loop(self, enc, pooled, timesteps):
+            self.tables.append((tuple(enc.shape), tuple(pooled.shape), [round(float(t), 3) for t in timesteps]))
+            return None if self.decline else {"id": len(self.tables)}
+
+        def step(self, x, control, enc, pooled, t, out=None, euler=None, sharded_io=False, guidance=None, loop=None):
+            self.steps.append((loop, float(t[0]), guidance, x.shape[0]))
+            out.copy_(euler[0])
+
+    class FakeModel:
+        def __init__(self, eng):
+            self._eng = eng
+
+        def engine(self):
+            return self._eng
+
+    lat, ctl = torch.randn(2, 16, 8, 8), torch.randn(2, 16, 8, 8)
+    enc, pooled = torch.randn(2, 5, 32), torch.randn(2, 16)
+    sig = sampler.flow_match_sigmas(4)
+    eng = FakeEngine()
+    sampler.denoise(FakeModel(eng), lat, ctl, enc, pooled, num_inference_steps=4)
+    assert len(eng.tables) == 1 and eng.tables[0][0] == (2, 5, 32)
+    assert eng.tables[0][2] == [round(float(s) * 1000.0, 3) for s in sig[:-1]]
+    assert [s[0][1] for s in eng.steps] == [0, 1, 2, 3] and all(s[0][0] == {"id": 1} for s in eng.steps)
+    assert [round(s[1], 3) for s in eng.steps] == eng.tables[0][2]
+    eng = FakeEngine()
+    sampler.denoise(FakeModel(eng), lat, ctl, enc, pooled, num_inference_steps=4, guidance_scale=8.0,
+                    negative_prompt_embeds=torch.zeros_like(enc), negative_pooled_prompt_embeds=torch.zeros_like(pooled))
+    assert eng.tables[0][0] == (4, 5, 32) and eng.tables[0][1] == (4, 16)       # [negative | positive] prompt batch
+    assert all(s[2] == 8.0 and s[3] == 4 for s in eng.steps)
+    for kw, eng in ((dict(hoist_loop_invariants=False), FakeEngine()), (dict(), FakeEngine(decline=True))):
+        sampler.denoise(FakeModel(eng), lat, ctl, enc, pooled, num_inference_steps=3, **kw)
+        assert all(s[0] is None for s in eng.steps) and len(eng.steps) == 3
