@@ -59,6 +59,8 @@ def denoise(model, latents, controlnet_image, encoder_hidden_states, pooled_proj
         pooled_projections = torch.cat([negative_pooled_prompt_embeds, pooled_projections], dim=0)
         if controlnet_image.shape[0] == B:                         # prepare_image doubles it (:714-715)
             controlnet_image = torch.cat([controlnet_image] * 2, dim=0)
+    if controlnet_image.dtype not in (torch.float32, torch.bfloat16):
+        controlnet_image = controlnet_image.float()                # fp16 modules: the engine takes fp32 / bf16 images
     sp = eng.sp
     if sp is not None:   # Ulysses: every rank carries its own row strip through the loop; ONE gather at the end
         g0, g1 = sp.row_slice(latents.shape[2] // 2)
@@ -121,8 +123,11 @@ def super_resolve(model, vae, lr_image, encoder_hidden_states, pooled_projection
 
 def _denoise_tiled(model, latents, controlnet_image, encoder_hidden_states, pooled_projections, num_inference_steps, sigmas,
                    guidance_scale, start_point, tile, overlap, tile_batch):
+    """The tiled branch of the loop (pipeline_dit4sr.py:1449-1558).  Everything that does not change from step to step is
+    formed once: tile placement, window and weight sum (`TilePlan`), the control tiles, the prompt embeddings repeated per
+    tile, and the engine's loop table (adaLN vectors of every step, embedded text tokens) per model-call size."""
     from . import ops
-    from .tiling import tiled_velocity
+    from .tiling import TilePlan
     if guidance_scale > 1.0:
         raise NotImplementedError("tiled sampling runs at guidance_scale 1 (the reference's shipped tiled configs)")
     sig = flow_match_sigmas(num_inference_steps) if sigmas is None else np.asarray(sigmas, dtype=np.float32)
@@ -132,19 +137,33 @@ def _denoise_tiled(model, latents, controlnet_image, encoder_hidden_states, pool
     elif start_point != "noise":
         raise ValueError("start_point must be 'noise' or 'lr'")
     dt = model.dtype
-    control = controlnet_image.to(dt)
+    eng = model.engine()
+    h, w = latents.shape[-2:]
+    plan = TilePlan(h, w, tile, overlap, device=latents.device)
+    n_tiles = len(plan)
+    per_call = min(tile_batch, n_tiles) if tile_batch > 0 else n_tiles          # tiles per model call
+    if dt not in (torch.float32, torch.bfloat16):
+        dt = torch.float32                                                        # fp16 modules: the engine takes fp32 / bf16 images
+    ctl_tiles = plan.extract(controlnet_image.to(dt)).contiguous()                # batch index = tile * B + image
+    calls = [(i * B, min(i + per_call, n_tiles) * B) for i in range(0, n_tiles, per_call)]
+    enc_rep = encoder_hidden_states.to(dt).repeat(per_call, 1, 1)
+    pooled_rep = pooled_projections.to(dt).repeat(per_call, 1)
+    timesteps = [float(s) * 1000.0 for s in sig[:-1]]
+    caches = {}                                                                   # rows of a call -> loop table
+    for a, b in calls:
+        if b - a not in caches:
+            caches[b - a] = eng.prepare_loop(enc_rep[:b - a], pooled_rep[:b - a], timesteps)
     x = latents.float().contiguous()
     nxt = torch.empty_like(x)
     for i in range(len(sig) - 1):
-        t_i = float(sig[i]) * 1000.0
-
-        def model_fn(lat, ctl):
-            n = lat.shape[0] // B                                      # tiles in this call (batch index = tile * B + image)
-            t = torch.full((lat.shape[0],), t_i, device=lat.device, dtype=torch.float32)
-            return model(lat.to(dt), ctl, encoder_hidden_states.repeat(n, 1, 1), pooled_projections.repeat(n, 1), t,
-                         return_dict=False)[0]
-
-        v = tiled_velocity(model_fn, x, control, tile, overlap, tile_batch=tile_batch).contiguous()
+        lat_tiles = plan.extract(x.to(dt)).contiguous()
+        outs = []
+        for a, b in calls:
+            t = torch.full((b - a,), timesteps[i], device=x.device, dtype=torch.float32)
+            cache = caches[b - a]
+            outs.append(eng.step(lat_tiles[a:b], ctl_tiles[a:b], enc_rep[:b - a], pooled_rep[:b - a], t,
+                                 loop=None if cache is None else (cache, i)))
+        v = plan.blend(torch.cat(outs, dim=0).float()).contiguous()
         ops.euler_update(x, v, nxt, float(sig[i + 1]) - float(sig[i]))
         x, nxt = nxt, x
     return x.to(latents.dtype)

@@ -29,23 +29,46 @@ def gaussian_weights(tile_w: int, tile_h: int, device=None, dtype=torch.float64)
     return torch.tensor(np.outer(ys, xs), device=device, dtype=dtype)
 
 
+class TilePlan:
+    """Tile placement, gaussian window and weight sum of one latent size (everything about the tiling that does not change
+    from step to step): `extract` cuts a [B, C, h, w] tensor into the tile batch (batch index = tile * B + image, the
+    reference's loop order: rows over x first), `blend` folds per-tile results back with the gaussian weights
+    (pipeline_dit4sr.py:1449-1558)."""
+
+    def __init__(self, h: int, w: int, tile: int, overlap: int, device=None):
+        self.h, self.w = h, w
+        self.tile = tile = min(tile, min(h, w))
+        xs, ys = tile_offsets(w, tile, overlap), tile_offsets(h, tile, overlap)
+        self.coords: List[Tuple[int, int]] = [(y, x) for x in xs for y in ys]
+        self.weights = gaussian_weights(tile, tile, device=device, dtype=torch.float32)
+        cnt = torch.zeros(h, w, device=device, dtype=torch.float32)
+        for y, x in self.coords:
+            cnt[y:y + tile, x:x + tile] += self.weights
+        self.weight_sum = cnt
+
+    def __len__(self):
+        return len(self.coords)
+
+    def extract(self, t: torch.Tensor) -> torch.Tensor:
+        T = self.tile
+        return torch.cat([t[:, :, y:y + T, x:x + T] for y, x in self.coords], dim=0)
+
+    def blend(self, vel: torch.Tensor) -> torch.Tensor:
+        n, T = len(self.coords), self.tile
+        B = vel.shape[0] // n
+        acc = torch.zeros(B, vel.shape[1], self.h, self.w, device=vel.device, dtype=torch.float32)
+        for i, (y, x) in enumerate(self.coords):
+            acc[:, :, y:y + T, x:x + T] += vel[i * B:(i + 1) * B] * self.weights
+        return acc / self.weight_sum
+
+
 def tiled_velocity(model_fn: Callable, latents: torch.Tensor, controlnet_image: torch.Tensor, tile: int, overlap: int,
                    tile_batch: int = 0) -> torch.Tensor:
     """Velocity of a large latent from overlapping tiles. model_fn(latent_tiles, control_tiles) -> velocity tiles
     (batch = tiles x images). tile_batch > 0 caps the number of tiles per model call."""
     B, C, h, w = latents.shape
-    tile = min(tile, min(h, w))
-    xs, ys = tile_offsets(w, tile, overlap), tile_offsets(h, tile, overlap)
-    coords: List[Tuple[int, int]] = [(y, x) for x in xs for y in ys]        # the reference iterates rows over x first
-    lat = torch.cat([latents[:, :, y:y + tile, x:x + tile] for y, x in coords], dim=0)
-    ctl = torch.cat([controlnet_image[:, :, y:y + tile, x:x + tile] for y, x in coords], dim=0)
+    plan = TilePlan(h, w, tile, overlap, device=latents.device)
+    lat, ctl = plan.extract(latents), plan.extract(controlnet_image)
     step = tile_batch * B if tile_batch > 0 else lat.shape[0]
     outs = [model_fn(lat[i:i + step].contiguous(), ctl[i:i + step].contiguous()) for i in range(0, lat.shape[0], step)]
-    vel = torch.cat(outs, dim=0).float()
-    wts = gaussian_weights(tile, tile, device=latents.device, dtype=torch.float32)
-    acc = torch.zeros(B, C, h, w, device=latents.device, dtype=torch.float32)
-    cnt = torch.zeros_like(acc)
-    for i, (y, x) in enumerate(coords):
-        acc[:, :, y:y + tile, x:x + tile] += vel[i * B:(i + 1) * B] * wts
-        cnt[:, :, y:y + tile, x:x + tile] += wts
-    return acc / cnt
+    return plan.blend(torch.cat(outs, dim=0).float())

@@ -16,6 +16,7 @@ def main():
     ap.add_argument("--steps", type=int, default=40)
     ap.add_argument("--side", type=int, default=64)
     ap.add_argument("--guidance", type=float, default=1.0)
+    ap.add_argument("--tile", type=int, default=0, help="latent tile size: time the tiled loop (overlap 24) against the per-step composition it replaced")
     a = ap.parse_args()
     import bench
     from dit4sr_b200.sampler import denoise
@@ -32,6 +33,47 @@ def main():
         kw = dict(guidance_scale=a.guidance, negative_prompt_embeds=torch.zeros_like(enc),
                   negative_pooled_prompt_embeds=torch.zeros_like(pooled))
     res = {}
+    if a.tile:
+        import numpy as np
+        from dit4sr_b200 import ops
+        from dit4sr_b200.sampler import flow_match_sigmas
+        from dit4sr_b200.tiling import tiled_velocity
+
+        def legacy(steps):     # what sampler._denoise_tiled did before: everything re-formed per step, model called as a module
+            sig = flow_match_sigmas(steps)
+            xx = x.float().contiguous()
+            nxt = torch.empty_like(xx)
+            for i in range(steps):
+                t_i = float(sig[i]) * 1000.0
+
+                def model_fn(lat, ctl):
+                    n = lat.shape[0] // B
+                    t = torch.full((lat.shape[0],), t_i, device=lat.device, dtype=torch.float32)
+                    return m(lat.to(bf), ctl, enc.repeat(n, 1, 1), pooled.repeat(n, 1), t, return_dict=False)[0]
+
+                v = tiled_velocity(model_fn, xx, c, a.tile, 24).contiguous()
+                ops.euler_update(xx, v, nxt, float(sig[i + 1]) - float(sig[i]))
+                xx, nxt = nxt, xx
+            return xx.to(bf)
+
+        fns = {"tiled loop (plan + loop table)": lambda n: denoise(m, x, c, enc, pooled, num_inference_steps=n, latent_tiled_size=a.tile,
+                                                                   latent_tiled_overlap=24),
+               "per-step composition": legacy}
+        outs = {}
+        for _ in range(2):
+            for name, fn in fns.items():
+                fn(2)
+                torch.cuda.synchronize()
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                outs[name] = fn(a.steps)
+                e1.record()
+                torch.cuda.synchronize()
+                ms = e0.elapsed_time(e1)
+                print(f"{name}: B={B} latent {s}x{s} tile {a.tile} {a.steps} steps: {ms:.1f} ms ({ms / a.steps:.3f} ms/step)")
+        d = (outs["tiled loop (plan + loop table)"].float() - outs["per-step composition"].float()).abs().max().item()
+        print(f"max abs difference of the final latents: {d:.3e}")
+        return
     import time
     eng = m.engine()
     for _ in range(2):      # what the table itself costs (host wall clock around a synchronised call)
